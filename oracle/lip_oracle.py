@@ -1,0 +1,650 @@
+"""CPU oracle for the matrix-free linearized-Laplace hot path.  TEST INFRASTRUCTURE ONLY.
+
+Each function cites the reference file:line it restates (paths relative to /root/reference).
+Arithmetic is float64 (torch CPU for autodiff, numpy elsewhere) unless a dtype is passed
+(the fp32 structure-faithful variants are what bench.py times as the CPU baseline).
+
+PARITY PINNING
+  * pinned: G1 (tests/fixtures.py:24 linear model GGN = e^{-logvar}[[14.46,3.6],[3.6,4]]),
+    G2 (tests/test_sample.py:334-355 Lanczos-20 inverse sqrt on diag(1..100)/100, rtol 1e-1),
+    G3 (tests/fixtures.py:201-209 traces 6 / 3894, hutchpp_v2 exact for s1>=n, tests/test_stochtrace.py:90-97),
+    G4 identities (vmap(ggn_vp)(I)==dense GGN, W(W^T(I))==GGN, L L^T==diag(p)-pp^T, null-space projector).
+    See tests/test_oracle_golden.py.
+  * PARITY UNPINNED: matfree (requirements.txt:5, no version pin, source absent from /root/reference and
+    not installed) and jax (absent).  `tridiag_sym`, `bidiag`, `funm_lanczos_sym`, `integrand_funm_*`,
+    `estimator` and `cg` below restate the published algorithms of matfree>=0.1 / jax.scipy.sparse.linalg.cg
+    from memory; only the mathematics (not the rounding order) is anchored, through G2 and through
+    dense-linear-algebra cross checks in tests/.  No reference test touches decomp.bidiag +
+    integrand_funm_product_logdet or the clip(min=1.0) of matfree_monkeypatch.py:19.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from .models import OracleState, flatten_nn_params
+
+F64 = torch.float64
+
+
+# ======================================================================================
+# helpers
+# ======================================================================================
+def _t(x, dtype=F64):
+    return torch.as_tensor(np.asarray(x), dtype=dtype)
+
+
+def softmax_np(f):
+    f = f - f.max(axis=-1, keepdims=True)
+    e = np.exp(f)
+    return e / e.sum(axis=-1, keepdims=True)
+
+
+def _model_fn(state: OracleState, Z, dtype=F64):
+    """theta -> f(theta, Z) [M, K]; per ggn.py:42-52,115-123 (BN eval mode, return_logvar=False)."""
+    Zt = _t(Z, dtype)
+
+    def f(theta):
+        return state.f_theta(theta, Zt)
+
+    return f
+
+
+def model_outputs(state: OracleState, Z) -> np.ndarray:
+    theta, _ = state.flat()
+    with torch.no_grad():
+        return _model_fn(state, Z)(_t(theta)).numpy()
+
+
+def jacobians(state: OracleState, Z) -> np.ndarray:
+    """Explicit per-point Jacobians J[i] = d f(z_i;theta)/d theta, shape [M, K, D] (ground truth)."""
+    theta, _ = state.flat()
+    th = _t(theta)
+    Zt = _t(Z)
+    rows = []
+    for i in range(Zt.shape[0]):
+        zi = Zt[i:i + 1]
+        J = torch.func.jacrev(lambda p: state.f_theta(p, zi)[0])(th)
+        rows.append(J.reshape(-1, th.numel()).numpy())
+    return np.stack(rows)
+
+
+# ======================================================================================
+# src/ggn.py
+# ======================================================================================
+def _H_action(model_type, f_out, u):
+    """ggn.py:125-131 : (diag(p) - p p^T) u  for classifiers, identity for regressors."""
+    if model_type == "classifier":
+        p = softmax_np(f_out)
+        return p * u - p * (p * u).sum(-1, keepdims=True)
+    return u
+
+
+def _sqrt_H_apply_T(model_type, f_out, vec, logvar):
+    """ggn.py:16-27  ('sqrt_Hi_apply_T'):  L vec = s*vec - (s.vec) p."""
+    if model_type == "regressor":
+        return math.sqrt(math.exp(-logvar)) * vec
+    p = softmax_np(f_out)
+    s = np.sqrt(p)
+    return s * vec - (s * vec).sum(-1, keepdims=True) * p
+
+
+def _sqrt_H_apply(model_type, f_out, vec, logvar):
+    """ggn.py:29-39  ('sqrt_Hi_apply'):  L^T vec = s*vec - (p.vec) s."""
+    if model_type == "regressor":
+        return math.sqrt(math.exp(-logvar)) * vec
+    p = softmax_np(f_out)
+    s = np.sqrt(p)
+    return s * vec - (p * vec).sum(-1, keepdims=True) * s
+
+
+def compute_ggn_vp(state: OracleState, Z, model_type, full_set_size=None, *, sequential=False,
+                   dtype=F64) -> Callable:
+    """ggn.py:97-146.  v[D] -> (N/M) * sum_i J_i^T H_i J_i v  (x exp(-logvar) for regressors).
+
+    sequential=True mirrors the reference structure literally (fori_loop over points, per-point jvp,
+    redundant forward, per-point vjp: ggn.py:133-144); the default does the same arithmetic batched
+    over points (identical up to summation order)."""
+    theta, _ = state.flat()
+    th = _t(theta, dtype)
+    Z = np.asarray(Z)
+    M = Z.shape[0]
+    N = full_set_size or M
+    recal = N / M
+    if model_type == "regressor":
+        recal *= math.exp(-state.logvar)
+
+    def ggn_vp(v):
+        vt = _t(v, dtype)
+        if sequential:
+            acc = torch.zeros_like(th)
+            for i in range(M):
+                fzi = lambda p: state.f_theta(p, _t(Z[i:i + 1], dtype))[0].squeeze()
+                _, jv = torch.func.jvp(fzi, (th,), (vt,))
+                f_val = fzi(th)
+                hv = _t(_H_action(model_type, f_val.detach().numpy().astype(np.float64),
+                                  jv.detach().numpy().astype(np.float64)), dtype)
+                _, vjp_fn = torch.func.vjp(fzi, th)
+                acc = acc + vjp_fn(hv)[0]
+            return (acc * recal).detach().numpy()
+        f = _model_fn(state, Z, dtype)
+        fz, jv = torch.func.jvp(f, (th,), (vt,))
+        hv = _t(_H_action(model_type, fz.detach().numpy().astype(np.float64),
+                          jv.detach().numpy().astype(np.float64)), dtype)
+        _, vjp_fn = torch.func.vjp(f, th)
+        return (vjp_fn(hv)[0] * recal).detach().numpy()
+
+    return ggn_vp
+
+
+def compute_W_vps(state: OracleState, Z, model_type, full_set_size=None, blockwise=False):
+    """ggn.py:9-93.  Returns (Wfun: [M,K]->[D], WTfun: [D]->[M,K]) ([M] for regressors)."""
+    theta, _ = state.flat()
+    th = _t(theta)
+    Z = np.asarray(Z)
+    M = Z.shape[0]
+    N = full_set_size or M
+    recal = math.sqrt(N / M)
+    lv = state.logvar
+
+    def WT_per_point(i, v):
+        fzi = lambda p: state.f_theta(p, _t(Z[i:i + 1]))[0].squeeze()
+        f_val, jv = torch.func.jvp(fzi, (th,), (_t(v),))
+        return recal * _sqrt_H_apply(model_type, f_val.detach().numpy(), jv.detach().numpy(), lv)
+
+    def W_per_point(i, U_i):
+        fzi = lambda p: state.f_theta(p, _t(Z[i:i + 1]))[0].squeeze()
+        f_val, vjp_fn = torch.func.vjp(fzi, th)
+        h = _sqrt_H_apply_T(model_type, f_val.detach().numpy(), np.asarray(U_i, dtype=np.float64), lv)
+        return recal * vjp_fn(_t(h).reshape(f_val.shape))[0].detach().numpy()
+
+    if blockwise:
+        return W_per_point, WT_per_point
+
+    f = _model_fn(state, Z)
+    squeeze = model_type == "regressor"
+
+    def WTfun(v):
+        fz, jv = torch.func.jvp(f, (th,), (_t(v),))
+        out = recal * _sqrt_H_apply(model_type, fz.detach().numpy(), jv.detach().numpy(), lv)
+        return out[:, 0] if squeeze else out  # regressor: (M,) (ggn.py:58,85)
+
+    def Wfun(U):
+        U = np.asarray(U, dtype=np.float64)
+        if squeeze:
+            U = U.reshape(M, 1)
+        fz, vjp_fn = torch.func.vjp(f, th)
+        h = _sqrt_H_apply_T(model_type, fz.detach().numpy(), U, lv)
+        return recal * vjp_fn(_t(h))[0].detach().numpy()
+
+    return Wfun, WTfun
+
+
+def compute_ggn_dense(state: OracleState, Z, model_type, full_set_size=None):
+    """ggn.py:149-193 from explicit Jacobians."""
+    J = jacobians(state, Z)  # [M,K,D]
+    M = J.shape[0]
+    D = J.shape[2]
+    G = np.zeros((D, D))
+    if model_type == "classifier":
+        P = softmax_np(model_outputs(state, Z))
+        for i in range(M):
+            H = np.diag(P[i]) - np.outer(P[i], P[i])
+            G += J[i].T @ H @ J[i]
+    else:
+        for i in range(M):
+            G += J[i].T @ J[i]
+        G *= math.exp(-state.logvar)
+    N = full_set_size or M
+    G *= N / M
+    theta, unravel = state.flat()
+    return G, theta, unravel
+
+
+def build_WTW(W, WT, inner_shape, d, *, dtype=np.float64, block=64):
+    """ggn.py:198-227: columns = WT(W(one_hot)), symmetrised from the upper triangle (:227)."""
+    G = np.zeros((d, d), dtype=dtype)
+    for j in range(d):
+        e = np.zeros(d, dtype=dtype)
+        e[j] = 1.0
+        G[:, j] = np.asarray(WT(W(e.reshape(inner_shape)))).reshape(-1)
+    return np.triu(G) + np.triu(G, 1).T
+
+
+def ensure_symmetry(Mx, jitter=1e-8):
+    """ggn.py:277"""
+    return 0.5 * (Mx + Mx.T) + jitter * np.eye(Mx.shape[0])
+
+
+# ======================================================================================
+# src/lla.py
+# ======================================================================================
+def compute_curvature_approx(map_state, Z, model_type, alpha, full_set_size=None, **kw):
+    """lla.py:11-23"""
+    ggn_vp = compute_ggn_vp(map_state, Z, model_type, full_set_size, **kw)
+
+    def curvature_vp(v):
+        return ggn_vp(v) + alpha * np.asarray(v, dtype=np.float64)
+
+    return curvature_vp
+
+
+def compute_curvature_approx_dense(map_state, x, model_type, alpha, full_set_size=None):
+    """lla.py:26-34"""
+    G, theta, unravel = compute_ggn_dense(map_state, x, model_type, full_set_size)
+    return G + alpha * np.eye(G.shape[0]), theta, unravel
+
+
+def materialize_covariance(f_cov_vp, N, out_dim, mode="diag"):
+    """lla.py:160-217"""
+    K = N * out_dim
+    if mode == "diag":
+        diag = np.zeros(K)
+        for i in range(K):
+            e = np.zeros(K)
+            e[i] = 1.0
+            diag[i] = np.asarray(f_cov_vp(e)).reshape(K)[i]
+        return diag.reshape(N, out_dim)
+    if mode == "full":
+        cov = np.zeros((K, K))
+        for i in range(K):
+            e = np.zeros(K)
+            e[i] = 1.0
+            cov[:, i] = np.asarray(f_cov_vp(e)).reshape(K)
+        return cov
+    raise ValueError("mode must be 'diag' or 'full'")
+
+
+# ======================================================================================
+# jax.scipy.sparse.linalg.cg  (third-party, absent; restated from its published algorithm)
+# ======================================================================================
+def cg(A: Callable, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None):
+    """x0=0; stop when r.r <= max(tol^2 b.b, atol^2) or k == maxiter (default 10*n); M = identity.
+    Call sites: stochtrace.py:146,192; sample.py:71."""
+    b = np.asarray(b, dtype=np.float64)
+    n = b.size
+    maxiter = 10 * n if maxiter is None else maxiter
+    x = np.zeros_like(b) if x0 is None else np.asarray(x0, dtype=np.float64).copy()
+    r = b - A(x) if x0 is not None else b.copy()
+    p = r.copy()
+    gamma = float(r.ravel() @ r.ravel())
+    atol2 = max(tol * tol * float(b.ravel() @ b.ravel()), atol * atol)
+    k = 0
+    while gamma > atol2 and k < maxiter:
+        Ap = np.asarray(A(p), dtype=np.float64)
+        a = gamma / float(p.ravel() @ Ap.ravel())
+        x = x + a * p
+        r = r - a * Ap
+        gamma_ = float(r.ravel() @ r.ravel())
+        p = r + (gamma_ / gamma) * p
+        gamma = gamma_
+        k += 1
+    return x, k
+
+
+# ======================================================================================
+# matfree (third-party, absent): decomp.tridiag_sym / decomp.bidiag / funm.* / stochtrace.estimator
+# ======================================================================================
+def tridiag_sym(num_matvecs: int):
+    """matfree.decomp.tridiag_sym(k) with full re-orthogonalisation (call sites sample.py:114,
+    tests/test_sample.py:338).  Arnoldi/Hessenberg form: for i<k: q_i = v/|v|; v = A q_i; h = Q^T v;
+    v -= Q h; v -= Q (Q^T v); H[:,i] = h, H[i+1,i] = |v|.  T = (H + H^T)/2 restricted to its three
+    diagonals.  Returns (Q[n,k], T[k,k])."""
+    k = num_matvecs
+
+    def decompose(matvec, vec):
+        v = np.asarray(vec, dtype=np.float64).copy()
+        n = v.size
+        if k > n:
+            raise ValueError(f"num_matvecs={k} exceeds the operator dimension {n}")
+        Q = np.zeros((n, k))
+        H = np.zeros((k, k))
+        length = np.linalg.norm(v)
+        for i in range(k):
+            v = v / length
+            Q[:, i] = v
+            v = np.asarray(matvec(v), dtype=np.float64)
+            h = Q.T @ v
+            v = v - Q @ h
+            v = v - Q @ (Q.T @ v)
+            length = np.linalg.norm(v)
+            H[:, i] = h
+            if i + 1 < k:
+                H[i + 1, i] = length
+        T = 0.5 * (H + H.T)
+        diag = np.diagonal(T).copy()
+        off = np.diagonal(T, 1).copy()
+        return Q, np.diag(diag) + np.diag(off, 1) + np.diag(off, -1)
+
+    return decompose
+
+
+def bidiag(num_matvecs: int):
+    """matfree.decomp.bidiag(k): Golub-Kahan-Lanczos with full re-orthogonalisation
+    (call site train_inducing.py:156).  Returns (U[k,nrows], B[k,k] upper-bidiagonal, V[k,ncols])."""
+    k = num_matvecs
+
+    def nrm(x):
+        l = np.linalg.norm(x)
+        return x / l, l
+
+    def decompose(Av, vA, v0):
+        v0 = np.asarray(v0, dtype=np.float64)
+        ncols = v0.size
+        vk, _ = nrm(v0)
+        vk, _ = nrm(vk)
+        nrows = np.asarray(Av(vk)).size
+        Us = np.zeros((k, nrows))
+        Vs = np.zeros((k, ncols))
+        alphas = np.zeros(k)
+        betas = np.zeros(k)
+        beta = 0.0
+        for i in range(k):
+            Vs[i] = vk
+            betas[i] = beta
+            uk = np.asarray(Av(vk), dtype=np.float64) - beta * Us[i - 1]
+            uk, alpha = nrm(uk)
+            uk = uk - Us.T @ (Us @ uk)
+            uk, _ = nrm(uk)
+            Us[i] = uk
+            alphas[i] = alpha
+            vk = np.asarray(vA(uk), dtype=np.float64) - alpha * Vs[i]
+            vk, beta = nrm(vk)
+            vk = vk - Vs.T @ (Vs @ vk)
+            vk, _ = nrm(vk)
+        B = np.diag(alphas) + np.diag(betas[1:], 1)
+        return Us, B, Vs
+
+    return decompose
+
+
+def dense_funm_sym_eigh(matfun, *, clip_min: Optional[float] = 1.0):
+    """matfree_monkeypatch.py:8-22 (clip_min=1.0, line 19); clip_min=None is matfree's own
+    (unpatched) dense_funm_sym_eigh used by tests/test_sample.py:9,337."""
+
+    def fun(dense):
+        w, V = np.linalg.eigh(dense)
+        if clip_min is not None:
+            w = np.clip(w, clip_min, None)
+        return V @ np.diag(matfun(w)) @ V.T
+
+    return fun
+
+
+def funm_lanczos_sym(dense_funm, tridiag):
+    """matfree.funm.funm_lanczos_sym: f(A)v ~= |v| Q f(T) e1  (call site sample.py:115)."""
+
+    def estimate(matvec, vec):
+        vec = np.asarray(vec, dtype=np.float64)
+        length = np.linalg.norm(vec)
+        Q, T = tridiag(matvec, vec / length)
+        fT = dense_funm(T)
+        return length * (Q @ fT[:, 0])
+
+    return estimate
+
+
+def integrand_funm_sym(dense_funm, tridiag):
+    """matfree.funm.integrand_funm_sym: v -> |v|^2 e1^T f(T) e1."""
+
+    def quadform(matvec, v0):
+        v0 = np.asarray(v0, dtype=np.float64).ravel()
+        length = np.linalg.norm(v0)
+        _, T = tridiag(matvec, v0 / length)
+        return length ** 2 * dense_funm(T)[0, 0]
+
+    return quadform
+
+
+def integrand_funm_sym_logdet(tridiag, *, clip_min: Optional[float] = 1.0):
+    """matfree_monkeypatch.py:25-41 (patched: eigenvalues clipped to >= 1 before log)."""
+    return integrand_funm_sym(dense_funm_sym_eigh(np.log, clip_min=clip_min), tridiag)
+
+
+def dense_funm_product_svd(matfun):
+    """matfree.funm.dense_funm_product_svd: B -> V f(S^2) V^T  (no clip; matfree's own)."""
+
+    def fun(B):
+        _, S, Vt = np.linalg.svd(B, full_matrices=False)
+        return Vt.T @ (matfun(S ** 2)[:, None] * Vt)
+
+    return fun
+
+
+def integrand_funm_product_logdet(bidiag_alg):
+    """matfree.funm.integrand_funm_product_logdet (call site train_inducing.py:157):
+    v -> |v|^2 e1^T V log(S^2) V^T e1 with B = U S V^T the GKL bidiagonal of A; A^T via vjp."""
+    dense = dense_funm_product_svd(np.log)
+
+    def quadform(Av, vA, v0):
+        v0 = np.asarray(v0, dtype=np.float64).ravel()
+        length = np.linalg.norm(v0)
+        _, B, _ = bidiag_alg(Av, vA, v0 / length)
+        return length ** 2 * dense(B)[0, 0]
+
+    return quadform
+
+
+def estimator(integrand, probes):
+    """matfree.stochtrace.estimator with a sampler that ignores its key
+    (train_inducing.py:141-142): mean over probe rows."""
+
+    def estimate(*ops):
+        return float(np.mean([integrand(*ops, p) for p in probes]))
+
+    return estimate
+
+
+# ======================================================================================
+# src/stochtrace.py   (probe matrices are INPUTS: jax.random is not reproducible without JAX)
+# ======================================================================================
+def stochastic_trace_estimator_dense(X, eps):
+    """stochtrace.py:7-19"""
+    return float(np.mean([e @ (X @ e) for e in eps]))
+
+
+def stochastic_trace_estimator_mvp(Xfun, eps):
+    """stochtrace.py:22-34 : mean_b eps_b . X eps_b"""
+    return float(np.mean([e @ np.asarray(Xfun(e)) for e in eps]))
+
+
+def hutchpp_dense(X, eps):
+    """stochtrace.py:37-49 ; eps [2*num_samples, n]"""
+    ns = eps.shape[0] // 2
+    S, G = eps[:ns], eps[ns:]
+    Q, _ = np.linalg.qr(X @ S.T)
+    P = np.eye(Q.shape[0]) - Q @ Q.T
+    return float(np.trace(Q.T @ X @ Q) + np.trace(G @ P @ X @ P @ G.T) / ns)
+
+
+def hutchpp_mvp(Xfun, eps):
+    """stochtrace.py:52-79 ; Xfun takes a MATRIX [n,k] (:64,74)."""
+    ns = eps.shape[0] // 2
+    S, G = eps[:ns], eps[ns:]
+    Q, _ = np.linalg.qr(np.asarray(Xfun(S.T)))
+    P = np.eye(Q.shape[0]) - Q @ Q.T
+    quad = lambda Mx: Mx.T @ np.asarray(Xfun(Mx))
+    return float(np.trace(quad(Q)) + np.trace(quad(P @ G.T)) / ns)
+
+
+def hutchpp(Xfun, eps):
+    """stochtrace.py:82-111 ; Xfun takes a VECTOR; note the 1/num_samples uses the FULL probe count (:84,109)."""
+    num_samples = eps.shape[0]
+    S, G = eps[:num_samples // 2], eps[num_samples // 2:]
+    Y = np.stack([np.asarray(Xfun(s)) for s in S], axis=1)
+    Q, _ = np.linalg.qr(Y)
+    P = np.eye(Q.shape[0]) - Q @ Q.T
+
+    def quad(Mx):
+        Yx = np.stack([np.asarray(Xfun(Mx[:, j])) for j in range(Mx.shape[1])], axis=1)
+        return Mx.T @ Yx
+
+    return float(np.trace(quad(Q)) + np.trace(quad(P @ G.T)) / num_samples)
+
+
+def apply_X(Xfun, Mx):
+    """stochtrace.py:113-114 : rows are probes -> columns of the result"""
+    return np.stack([np.asarray(Xfun(r)) for r in Mx], axis=1)
+
+
+def hutchpp_v2(Xfun, eps, *, s1, s2):
+    """stochtrace.py:118-135"""
+    S, G = eps[:s1], eps[s1:]
+    Y = apply_X(Xfun, S)
+    Q, _ = np.linalg.qr(Y)
+    XQ = apply_X(Xfun, Q.T)
+    low_rank = np.trace(XQ.T @ Q)
+    G_perp = G - (G @ Q) @ Q.T
+    XGp = apply_X(Xfun, G_perp)
+    resid = np.trace(G_perp @ XGp) / s2
+    return float(low_rank + resid)
+
+
+def hutchpp_inv_mvp(Xfun, eps):
+    """stochtrace.py:138-148 ; Xfun takes a vector; CG is applied column-wise."""
+    def Xinv(Mx):
+        Mx = np.asarray(Mx)
+        if Mx.ndim == 1:
+            return cg(Xfun, Mx)[0]
+        return np.stack([cg(Xfun, Mx[:, j])[0] for j in range(Mx.shape[1])], axis=1)
+    return hutchpp_mvp(Xinv, eps)
+
+
+def na_hutchpp_dense(X, eps):
+    """stochtrace.py:151-163 ; eps [4*num_samples, n]"""
+    ns = eps.shape[0] // 4
+    c3 = 0.25
+    S, R, G = eps[:ns], eps[ns:3 * ns], eps[3 * ns:]
+    W = X @ S.T
+    Zm = X @ R.T
+    pin = np.linalg.pinv(S @ Zm)
+    return float(np.trace(pin @ (W.T @ Zm))
+                 + (np.trace(G @ X @ G.T) - np.trace(G @ Zm @ pin @ W.T @ G.T)) / (c3 * 4 * ns))
+
+
+def na_hutchpp_mvp(Xfun, eps):
+    """stochtrace.py:166-180 ; Xfun takes a matrix"""
+    ns = eps.shape[0] // 4
+    c3 = 0.25
+    S, R, G = eps[:ns], eps[ns:3 * ns], eps[3 * ns:]
+    W = np.asarray(Xfun(S.T))
+    Zm = np.asarray(Xfun(R.T))
+    pin = np.linalg.pinv(S @ Zm)
+    return float(np.trace(pin @ (W.T @ Zm))
+                 + (np.trace(G @ np.asarray(Xfun(G.T))) - np.trace(G @ Zm @ pin @ W.T @ G.T)) / (c3 * 4 * ns))
+
+
+def na_hutchpp_inv_mvp(Xfun, eps):
+    """stochtrace.py:183-194"""
+    def Xinv(Mx):
+        Mx = np.asarray(Mx, dtype=np.float64)
+        if Mx.ndim == 1:
+            return cg(Xfun, Mx)[0]
+        return np.stack([cg(Xfun, Mx[:, j])[0] for j in range(Mx.shape[1])], axis=1)
+    return na_hutchpp_mvp(Xinv, eps)
+
+
+# ======================================================================================
+# train_inducing.py:148-171  — the production SLQ logdet (GKL form) and the Lanczos form
+# ======================================================================================
+def slq_logdet_gkl(state, Z, model_type, alpha, probes, num_matvecs):
+    """logdet(alpha I + Wz Wz^T) via GKL on A = [sqrt(alpha) I; Wz^T]  (train_inducing.py:114-116,
+    156-171; NB full_set_size=None inside compute_W_vps, i.e. no beta)."""
+    Wz, WzT = compute_W_vps(state, Z, model_type, full_set_size=None)
+    sa = math.sqrt(alpha)
+    D = state.flat()[0].size
+    inner = np.asarray(WzT(np.zeros(D))).shape
+
+    def Av(v):
+        return np.concatenate([sa * v, np.asarray(WzT(v)).ravel()])
+
+    def vA(u):
+        return sa * u[:D] + Wz(u[D:].reshape(inner))
+
+    integrand = integrand_funm_product_logdet(bidiag(num_matvecs))
+    return estimator(integrand, probes)(Av, vA)
+
+
+def slq_logdet_lanczos(matvec, probes, num_matvecs, *, clip_min=1.0):
+    """train_inducing.py:152-153 (commented 'old tridiagonal formulation') / tests/test_variational.py:126-150."""
+    integrand = integrand_funm_sym_logdet(tridiag_sym(num_matvecs), clip_min=clip_min)
+    return estimator(integrand, probes)(matvec)
+
+
+# ======================================================================================
+# src/sample.py
+# ======================================================================================
+def inv_matsqrt_dense(state, Z, alpha, model_type, full_set_size=None):
+    """sample.py:16-52 (debug twin)."""
+    theta, _ = state.flat()
+    D = theta.size
+    M = np.asarray(Z).shape[0]
+    N = full_set_size or M
+    beta = N / M
+    Wfun, WTfun = compute_W_vps(state, Z, model_type, full_set_size=None)
+    I_D = np.eye(D)
+    W = np.stack([np.asarray(WTfun(I_D[j])).ravel() for j in range(D)], axis=0)  # (D, d)
+    WT = W.T
+    comp = WT @ W
+    inv_comp = np.linalg.solve(comp, np.eye(comp.shape[0]))
+    nullproj = I_D - W @ inv_comp @ WT
+    term1 = nullproj / math.sqrt(alpha)
+    w, V = np.linalg.eigh(alpha * np.eye(comp.shape[0]) + beta * comp)
+    inv_sqrt = (V * (1.0 / np.sqrt(np.clip(w, 0, np.inf)))) @ V.T
+    return term1 + W @ inv_comp @ inv_sqrt @ WT
+
+
+def inv_matsqrt_vp(state, Z, D, alpha, model_type, full_set_size=None):
+    """sample.py:55-145 with key=None (direct projection; sample.py:150 forces it)."""
+    Wfun, WTfun = compute_W_vps(state, Z, model_type, full_set_size=None)
+    dummy = np.asarray(WTfun(np.zeros(D)))
+    inner_shape, d = dummy.shape, dummy.size
+    WTW = build_WTW(Wfun, WTfun, inner_shape, d, dtype=np.float64, block=2)
+    import scipy.linalg as sla
+
+    def nullproj_vp(v):
+        u = np.asarray(WTfun(v)).ravel()
+        x = sla.solve(WTW, u)
+        return v - Wfun(x.reshape(inner_shape))
+
+    M = np.asarray(Z).shape[0]
+    N = full_set_size or M
+    beta = N / M
+    invsqrt_fun = dense_funm_sym_eigh(lambda x: 1.0 / np.sqrt(x), clip_min=1.0)  # sample.py:113
+    invmatsqrt = funm_lanczos_sym(invsqrt_fun, tridiag_sym(2 * M))              # sample.py:114-115
+
+    def invmatsqrt_term(V):
+        Vflat = np.asarray(V).ravel()
+        return invmatsqrt(lambda u: alpha * u + beta * (WTW @ u), Vflat).reshape(inner_shape)
+
+    def outer_fun(v):
+        u = invmatsqrt_term(WTfun(v)).ravel()
+        x = sla.solve(WTW, u)
+        return Wfun(x.reshape(inner_shape))
+
+    def vp(v):
+        v = np.asarray(v, dtype=np.float64)
+        return outer_fun(v) + nullproj_vp(v) / math.sqrt(alpha)
+
+    return vp
+
+
+def sample(state, Z, D, alpha, Eps, model_type, full_set_size=None):
+    """sample.py:148-156 with the N(0,I) draws Eps[S,D] supplied by the caller."""
+    f = inv_matsqrt_vp(state, Z, D, alpha, model_type, full_set_size=full_set_size)
+    return np.stack([f(e) for e in np.asarray(Eps, dtype=np.float64)])
+
+
+def predict_lla_scalable(map_state, Xnew, Z, model_type, alpha, Eps, full_set_size=None):
+    """lla.py:133-156: f(theta*,X) + J_X w_s for w_s = A^{-1/2} eps_s."""
+    theta, _ = map_state.flat()
+    D = theta.size
+    w_samples = sample(map_state, Z, D, alpha, Eps, model_type, full_set_size=full_set_size)
+    f = _model_fn(map_state, Xnew)
+    th = _t(theta)
+    fmu = f(th).detach().numpy()
+    dys = np.stack([torch.func.jvp(f, (th,), (_t(w),))[1].detach().numpy() for w in w_samples])
+    return fmu[None] + dys
