@@ -1,0 +1,183 @@
+/*
+ * lip_b200.h — C ABI of liblip_b200.so: the B200-native (sm_100a) matrix-free linearized-Laplace hot path.
+ *
+ * Every entry point takes plain pointers and sizes (no torch / JAX types), enqueues its work on the
+ * caller's CUDA stream, performs no host synchronisation and no allocation on the hot calls (scratch is
+ * caller-owned), and returns 0 (LIP_OK) or a negative lip_status; lip_last_error() gives the message.
+ * Device pointers are fp32 unless stated.  Flat parameter vectors use the reference's layout
+ * (/root/reference/src/utils.py:12-17 flatten_nn_params == ravel_pytree: sorted keys, bias before kernel,
+ * Dense kernel [in,out] row-major).
+ *
+ * Each function cites the reference interface it replaces (paths relative to /root/reference).
+ * The reference is pure Python/JAX: these are the symbols a jax.ffi / XLA custom-call shim (or the ctypes
+ * loader shipped in laplace-inducing-points_b200/_cabi.py) binds; see INTEGRATION.md.
+ */
+#ifndef LIP_B200_H_
+#define LIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lip_model lip_model;   /* opaque: layer program + activation cache at the bound points */
+typedef void* lip_stream_t;           /* a cudaStream_t */
+
+typedef enum {
+  LIP_OK = 0,
+  LIP_ERR_INVALID = -1,      /* bad argument / shape / unsupported model (-> ValueError / ffi::InvalidArgument) */
+  LIP_ERR_CUDA = -2,         /* CUDA runtime failure (-> RuntimeError / ffi::Internal) */
+  LIP_ERR_WORKSPACE = -3,    /* caller workspace too small */
+  LIP_ERR_UNSUPPORTED = -4,  /* no sm_100a device / feature not built */
+  LIP_ERR_NOT_BOUND = -5
+} lip_status;
+
+/* layer program ops.  Round 1 executes DENSE + activations (models M1/M2 of SURVEY.md 8a:
+ * src/toymodels.py:4-37, src/scalemodels.py:52-67); the conv ops are reserved for M3/M4. */
+typedef enum {
+  LIP_OP_DENSE = 0,      /* y = x @ kernel[in,out] + bias[out]   (flax nn.Dense) */
+  LIP_OP_TANH = 1,
+  LIP_OP_GELU_TANH = 2,  /* flax nn.gelu(approximate=True) */
+  LIP_OP_RELU = 3
+} lip_op;
+
+typedef struct {
+  int32_t op;            /* lip_op */
+  int32_t in_features;   /* DENSE only */
+  int32_t out_features;  /* DENSE only */
+  int64_t bias_offset;   /* DENSE: offset of bias[out] in the flat parameter vector */
+  int64_t kernel_offset; /* DENSE: offset of kernel[in,out] in the flat parameter vector */
+} lip_layer_desc;
+
+typedef enum { LIP_REGRESSOR = 0, LIP_CLASSIFIER = 1 } lip_model_type;
+
+/* which output-space factor an operator applies (src/ggn.py:16-39,125-131) */
+typedef enum {
+  LIP_FACTOR_NONE = 0,  /* plain Jacobian (lla.py:153 predictive JVP) */
+  LIP_FACTOR_SQRT = 1   /* L / L^T with L = diag(sqrt p) - p sqrt(p)^T (classifier) or exp(-logvar/2) (regressor) */
+} lip_factor;
+
+const char* lip_last_error(void);
+int lip_version(void);
+/* 1 if the current device is sm_100 (tcgen05 path usable), 0 otherwise, <0 on error */
+int lip_device_is_sm100(void);
+
+/* ---- model handle ------------------------------------------------------------------------------------
+ * Replaces the `state` + `Z` closure capture of compute_ggn_vp / compute_W_vps (src/ggn.py:9-14,97-113). */
+int lip_model_create(const lip_layer_desc* layers, int32_t n_layers, int32_t model_type,
+                     int64_t num_params, lip_model** out);
+int lip_model_destroy(lip_model* m);
+int64_t lip_model_num_params(const lip_model* m);
+int64_t lip_model_num_outputs(const lip_model* m);
+int64_t lip_model_num_points(const lip_model* m);
+/* 0: SIMT fp32 only; 1: tcgen05 3xTF32 for qualifying layers (default when the device is sm_100) */
+int lip_model_set_tensor_path(lip_model* m, int32_t enable);
+
+/* Bind weights theta[D] (flat, reference order) and points Z[M, in_features]; runs and caches the forward
+ * pass (activations, activation derivatives, softmax p and sqrt p).  Replaces the per-call forward passes of
+ * ggn.py:139-142 (three forwards per point per probe in the reference).  logvar is the regressor's
+ * log-variance (ggn.py:112-113); ignored for classifiers.  Allocates the cache (not a hot call). */
+int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, float logvar,
+                   lip_stream_t stream);
+/* Copies the cached model outputs f(theta, Z) [M,K] (logits / means) to out. */
+int lip_model_outputs(lip_model* m, float* out, lip_stream_t stream);
+
+/* scratch bytes the hot calls below need for B probes */
+size_t lip_workspace_bytes(const lip_model* m, int64_t B);
+
+/* ---- GGN-vector product ------------------------------------------------------------------------------
+ * out[b,:] = recal * sum_i J_i^T H_i J_i V[b,:] + alpha * V[b,:]       V, out: [B, D] row-major.
+ * Replaces ggn_vp (src/ggn.py:133-144) vmapped over probes (src/stochtrace.py:113-114) and
+ * curvature_vp (src/lla.py:19-23).  recal = N/M (x exp(-logvar) for regressors, ggn.py:109-113). */
+int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha,
+               void* workspace, size_t workspace_bytes, lip_stream_t stream);
+
+/* out[b,i,:] = scale * F_i^T J_i V[b,:]      V: [B, D] -> out: [B, M, K]
+ * factor=SQRT replaces WTfun (src/ggn.py:54-62,84-85); factor=NONE is the batched JVP of lla.py:153. */
+int lip_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scale, int32_t factor,
+                 void* workspace, size_t workspace_bytes, lip_stream_t stream);
+
+/* out[b,:] = scale * sum_i J_i^T F_i U[b,i,:] + add_scale * add[b,:]   U: [B, M, K] -> out: [B, D]
+ * Replaces Wfun (src/ggn.py:64-76,87-91) without materialising the [M,D] per-example gradients.
+ * add may be NULL (then add_scale is ignored). */
+int lip_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor,
+                const float* add, float add_scale,
+                void* workspace, size_t workspace_bytes, lip_stream_t stream);
+
+/* Dense Gram  G = scale^2 * W^T W  [d,d], d = M*K, symmetrised from the upper triangle as
+ * src/ggn.py:227.  Replaces build_WTW (src/ggn.py:198-227): one batched W over one-hot blocks followed by
+ * W^T instead of d/block sequential pairs.  block = one-hot columns pushed per pass. */
+int lip_gram_wtw(lip_model* m, float* G, float scale, int64_t block,
+                 void* workspace, size_t workspace_bytes, lip_stream_t stream);
+size_t lip_gram_workspace_bytes(const lip_model* m, int64_t block);
+
+/* ---- vector stage (CG / Lanczos / GKL building blocks; all batched over B independent columns) --------
+ * Vectors are [B, n] row-major.  Scalars stay on the device (no host readback). */
+
+/* out[b] = sum_j x[b,j] * y[b,j]           (deterministic two-stage reduction; scratch >= lip_dot_scratch_bytes) */
+size_t lip_dot_scratch_bytes(int64_t n, int64_t B);
+int lip_dot(const float* x, const float* y, float* out, int64_t n, int64_t B, int64_t ldx, int64_t ldy,
+            void* scratch, lip_stream_t stream);
+/* y[b,:] = a[b] * x[b,:] + c[b] * y[b,:]   (a, c device arrays [B]; NULL means 1 / 0 resp.) */
+int lip_axpby(const float* a, const float* x, const float* c, float* y, int64_t n, int64_t B,
+              int64_t ldx, int64_t ldy, lip_stream_t stream);
+/* y[b,:] = x[b,:] * (invert ? 1/s[b] : s[b]) */
+int lip_scale(const float* s, int32_t invert, const float* x, float* y, int64_t n, int64_t B,
+              int64_t ldx, int64_t ldy, lip_stream_t stream);
+
+/* One CG iteration's vector work for jax.scipy.sparse.linalg.cg semantics (call sites
+ * src/stochtrace.py:146,192; src/sample.py:71): given Ap = A p,
+ *   a = gamma/(p.Ap); x += a p; r -= a Ap; gamma' = r.r; p = r + (gamma'/gamma) p; gamma = gamma'
+ * for every column b with active[b] != 0; active[b] is then recomputed as (gamma'[b] > thresh[b]).
+ * iters[b] is incremented for active columns.  state arrays gamma, thresh: [B] fp32; active, iters: [B] int32. */
+int lip_cg_step(float* x, float* r, float* p, const float* Ap, float* gamma, const float* thresh,
+                int32_t* active, int32_t* iters, int64_t n, int64_t B, void* scratch, lip_stream_t stream);
+/* r = p = b, x = 0, gamma = b.b, thresh = max(tol^2 b.b, atol^2), active = gamma > thresh, iters = 0 */
+int lip_cg_init(const float* b, float* x, float* r, float* p, float* gamma, float* thresh,
+                int32_t* active, int32_t* iters, float tol, float atol, int64_t n, int64_t B,
+                void* scratch, lip_stream_t stream);
+
+/* Full re-orthogonalisation against the first kk rows of a basis Q[B, kmax, ldq] (row stride ldq >= n,
+ * batch stride kmax*ldq; pad ldq to a multiple of 4 for 128-bit loads):
+ *   h = Q w;  w -= Q^T h;  [if passes == 2:  w -= Q^T (Q w)  with the 2nd coefficients discarded]
+ * w: [B, ldw].  h_out[B, kmax] (optional) receives the first-pass coefficients (entries >= kk untouched).
+ * norm_out[B] (optional) receives |w| after the update.  This is the Gram-Schmidt of matfree's
+ * decomp.tridiag_sym / decomp.bidiag with reortho="full" (call sites src/sample.py:114,
+ * src/train_inducing.py:156).  scratch >= lip_reorth_scratch_bytes. */
+size_t lip_reorth_scratch_bytes(int64_t n, int64_t B, int64_t kmax);
+int lip_reorth(const float* Q, int64_t ldq, int64_t kk, int64_t kmax, float* w, int64_t ldw, float* h_out,
+               float* norm_out, int32_t passes, int64_t n, int64_t B, void* scratch, lip_stream_t stream);
+/* out[b,:] = sum_{j<kk} c[b,j] * Q[b,j,:]      (c: [B, ldc], out: [B, ldo]) */
+int lip_basis_combine(const float* Q, int64_t ldq, int64_t kk, int64_t kmax, const float* c, int64_t ldc,
+                      float* out, int64_t ldo, int64_t n, int64_t B, lip_stream_t stream);
+
+/* ---- small dense stage ---------------------------------------------------------------------------------
+ * Symmetric tridiagonal eigen-decomposition + matrix function, one thread block per problem, float64 inside.
+ * diag[B,k], off[B,k-1] (fp32 in).  fn: 0 log, 1 inverse sqrt, 2 inverse, 3 identity.
+ * clip_min < 0 disables the clip; the reference's patched eigh clips eigenvalues to >= 1.0
+ * (src/matfree_monkeypatch.py:19).
+ *   quad_out[B]   (optional) = e1^T f(T) e1                       (matfree funm.integrand_funm_sym)
+ *   fe1_out[B,k]  (optional) = f(T) e1                            (matfree funm.funm_lanczos_sym)
+ *   eig_out[B,k]  (optional) = eigenvalues (ascending not guaranteed)
+ * Replaces dense_funm_sym_eigh (src/matfree_monkeypatch.py:8-22) and the dense SVD of matfree's
+ * dense_funm_product_svd when fed T = B^T B (see lip_bidiag_to_tridiag). */
+size_t lip_tridiag_scratch_bytes(int64_t k, int64_t B, int32_t want_vectors);
+int lip_tridiag_funm(const float* diag, const float* off, int64_t k, int64_t B, int32_t fn, float clip_min,
+                     float* quad_out, float* fe1_out, float* eig_out, void* scratch, lip_stream_t stream);
+/* T = Bd^T Bd for upper-bidiagonal Bd = diag(alphas) + superdiag(betas[1:]):  tdiag[i] = a_i^2 + b_i^2
+ * (b_0 := 0), toff[i] = a_i * b_{i+1}.  alphas, betas: [B,k]. */
+int lip_bidiag_to_tridiag(const float* alphas, const float* betas, float* tdiag, float* toff, int64_t k,
+                          int64_t B, lip_stream_t stream);
+
+/* ---- self test of the tensor-core GEMM (3xTF32 tcgen05) against the SIMT fp32 GEMM; returns max rel err
+ * through *max_rel_err.  variant: 0 = JVP-type (A K-major, B N-major), 1 = weight-grad type (both MN-major),
+ * 2 = delta-backprop type (both K-major). */
+int lip_selftest_tc_gemm(int32_t variant, int64_t Mrows, int64_t N, int64_t K, int64_t batch,
+                         float* max_rel_err, lip_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIP_B200_H_ */

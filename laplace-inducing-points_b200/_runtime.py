@@ -1,0 +1,170 @@
+"""Host-side plumbing over the C ABI: device tensors (torch), workspaces, the bound-model handle."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi as cabi
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise cabi.LipError("lip_b200 needs a CUDA device (sm_100a); there is no CPU fallback for this path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def dev_f32(x, device=None) -> torch.Tensor:
+    device = device or _require_cuda()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32).contiguous()
+    import numpy as np
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32).to(device).contiguous()
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Scratch:
+    """A growable byte buffer (caller-owned scratch of the C ABI)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int) -> Tuple[C.c_void_p, int]:
+        nbytes = int(nbytes)
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=_require_cuda())
+        return C.c_void_p(self.buf.data_ptr()), self.buf.numel()
+
+
+_GLOBAL_SCRATCH = Scratch()
+
+
+def scratch(nbytes: int):
+    return _GLOBAL_SCRATCH.get(nbytes)
+
+
+class MLPSpec:
+    """Architecture of an MLP extracted from a reference-layout parameter tree (Dense_i: bias, kernel)."""
+
+    def __init__(self, dims: Sequence[int], act: int, model_type: str):
+        self.dims = list(dims)
+        self.act = act
+        self.model_type = model_type
+        off = 0
+        self.layers = []
+        for i in range(len(self.dims) - 1):
+            nin, nout = self.dims[i], self.dims[i + 1]
+            self.layers.append((nin, nout, off, off + nout))  # bias then kernel (sorted keys)
+            off += nout + nin * nout
+        self.num_params = off
+
+    def descs(self):
+        out = []
+        n = len(self.layers)
+        for i, (nin, nout, boff, woff) in enumerate(self.layers):
+            out.append(cabi.LayerDesc(cabi.OP_DENSE, nin, nout, boff, woff))
+            if i < n - 1:
+                out.append(cabi.LayerDesc(self.act, 0, 0, 0, 0))
+        arr = (cabi.LayerDesc * len(out))(*out)
+        return arr, len(out)
+
+
+class BoundModel:
+    """lip_model handle bound to (theta, Z): owns the activation cache; exposes the probe-batched operators."""
+
+    def __init__(self, spec: MLPSpec, theta: torch.Tensor, Z: torch.Tensor, logvar: float = 0.0,
+                 tensor_path: Optional[bool] = None):
+        L = cabi.lib()
+        self.spec = spec
+        self.device = _require_cuda()
+        self.theta = dev_f32(theta, self.device)
+        if self.theta.numel() != spec.num_params:
+            raise ValueError(f"flat parameter vector has {self.theta.numel()} entries, architecture needs {spec.num_params}")
+        Zf = dev_f32(Z, self.device)
+        self.M = int(Zf.shape[0])
+        self.Z = Zf.reshape(self.M, -1)
+        if self.Z.shape[1] != spec.dims[0]:
+            raise ValueError(f"points have {self.Z.shape[1]} features, model expects {spec.dims[0]}")
+        self.D = spec.num_params
+        self.K = spec.dims[-1]
+        self.model_type = spec.model_type
+        self.logvar = float(logvar)
+        arr, n = spec.descs()
+        h = C.c_void_p()
+        mt = cabi.REGRESSOR if spec.model_type == "regressor" else cabi.CLASSIFIER
+        cabi.check(L.lip_model_create(arr, n, mt, self.D, C.byref(h)), "lip_model_create")
+        self._h = h
+        self._finalizer = weakref.finalize(self, L.lip_model_destroy, h)
+        if tensor_path is not None:
+            cabi.check(L.lip_model_set_tensor_path(self._h, 1 if tensor_path else 0))
+        cabi.check(L.lip_model_bind(self._h, ptr(self.theta), ptr(self.Z), self.M, self.logvar, stream()),
+                   "lip_model_bind")
+        self._ws = Scratch()
+        self.launches = 0
+
+    # ---- helpers ----
+    def _workspace(self, B: int):
+        need = cabi.lib().lip_workspace_bytes(self._h, B)
+        return self._ws.get(need)
+
+    def outputs(self) -> torch.Tensor:
+        out = torch.empty(self.M, self.K, device=self.device, dtype=torch.float32)
+        cabi.check(cabi.lib().lip_model_outputs(self._h, ptr(out), stream()))
+        return out
+
+    # ---- operators (all probe-batched: leading dim B) ----
+    def ggn_vp(self, V: torch.Tensor, recal: float, alpha: float = 0.0) -> torch.Tensor:
+        V = dev_f32(V, self.device)
+        single = V.dim() == 1
+        Vb = V.reshape(-1, self.D)
+        B = Vb.shape[0]
+        out = torch.empty_like(Vb)
+        ws, nb = self._workspace(B)
+        cabi.check(cabi.lib().lip_ggn_vp(self._h, ptr(Vb), ptr(out), B, recal, alpha, ws, nb, stream()), "lip_ggn_vp")
+        return out.reshape(self.D) if single else out
+
+    def wt(self, V: torch.Tensor, scale: float = 1.0, factor: int = cabi.FACTOR_SQRT) -> torch.Tensor:
+        V = dev_f32(V, self.device)
+        single = V.dim() == 1
+        Vb = V.reshape(-1, self.D)
+        B = Vb.shape[0]
+        out = torch.empty(B, self.M, self.K, device=self.device, dtype=torch.float32)
+        ws, nb = self._workspace(B)
+        cabi.check(cabi.lib().lip_wt_apply(self._h, ptr(Vb), ptr(out), B, scale, factor, ws, nb, stream()), "lip_wt_apply")
+        return out[0] if single else out
+
+    def w(self, U: torch.Tensor, scale: float = 1.0, factor: int = cabi.FACTOR_SQRT, add: Optional[torch.Tensor] = None,
+          add_scale: float = 0.0, batched: Optional[bool] = None) -> torch.Tensor:
+        U = dev_f32(U, self.device)
+        d = self.M * self.K
+        if batched is None:
+            batched = U.numel() != d
+        Ub = U.reshape(-1, d)
+        B = Ub.shape[0]
+        out = torch.empty(B, self.D, device=self.device, dtype=torch.float32)
+        addp = None
+        if add is not None:
+            addp = dev_f32(add, self.device).reshape(B, self.D)
+        ws, nb = self._workspace(B)
+        cabi.check(cabi.lib().lip_w_apply(self._h, ptr(Ub), ptr(out), B, scale, factor, ptr(addp), add_scale, ws, nb,
+                                          stream()), "lip_w_apply")
+        return out if batched else out.reshape(self.D)
+
+    def gram(self, scale: float = 1.0, block: int = 256) -> torch.Tensor:
+        d = self.M * self.K
+        block = max(1, min(int(block), d))
+        G = torch.empty(d, d, device=self.device, dtype=torch.float32)
+        need = cabi.lib().lip_gram_workspace_bytes(self._h, block)
+        ws, nb = self._ws.get(need)
+        cabi.check(cabi.lib().lip_gram_wtw(self._h, ptr(G), scale, block, ws, nb, stream()), "lip_gram_wtw")
+        return G

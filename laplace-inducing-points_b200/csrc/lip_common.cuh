@@ -1,0 +1,112 @@
+// lip_common.cuh — shared helpers for liblip_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/lip_b200.h"
+
+namespace lip {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define LIP_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::lip::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,              \
+                       cudaGetErrorString(_e));                                           \
+      return LIP_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define LIP_REQUIRE(cond, ...)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::lip::set_error(__VA_ARGS__);                                                      \
+      return LIP_ERR_INVALID;                                                             \
+    }                                                                                     \
+  } while (0)
+
+#define LIP_LAUNCH_CHECK() LIP_CHECK_CUDA(cudaGetLastError())
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- generic strided batched GEMM (SIMT fp32) with the fused epilogue every hot-path stage needs -------
+//   acc[z][m][n] = sum_k A1[z][m][k] B1[z][k][n]  (+ sum_k A2[z][m][k] B2[z][k][n])
+//   v = scale*acc + bias[z][n];  (act) ;  v *= mask[m][n];  v += add_scale * add[z][m][n]
+//   C[z][m][n] = v;   dphi_out[z][m][n] = act'(pre-activation)   (forward pass only)
+struct GemmOperand {
+  const float* ptr = nullptr;
+  int64_t sz = 0;   // batch stride
+  int64_t s0 = 0;   // stride of the row index (m for A, k for B)
+  int64_t s1 = 0;   // stride of the col index (k for A, n for B)
+};
+
+struct GemmEpilogue {
+  float scale = 1.f;
+  const float* bias = nullptr;  int64_t bias_sz = 0;              // [z][n]
+  const float* mask = nullptr;  int64_t mask_sm = 0;              // [m][n], shared by all z
+  const float* add = nullptr;   int64_t add_sz = 0; float add_scale = 0.f;  // same m/n strides as C
+  int act = -1;                 // -1 none, else lip_op activation
+  float* dphi_out = nullptr;    // same layout as C (only with act >= 0)
+};
+
+struct GemmProblem {
+  int64_t M = 0, N = 0, K = 0, batch = 1;
+  GemmOperand A1, B1, A2, B2;   // A2/B2 optional (ptr == nullptr)
+  int64_t K2 = 0;
+  float* C = nullptr; int64_t c_sz = 0, c_sm = 0;  // n stride is 1
+  GemmEpilogue epi;
+};
+
+int gemm_simt(const GemmProblem& p, cudaStream_t stream);
+
+// tcgen05 3xTF32 path (lip_gemm_tc.cu).  Operands are pre-split TF32 hi/lo pairs in padded buffers.
+struct TcOperand {
+  const float* hi = nullptr;
+  const float* lo = nullptr;
+  int64_t sz = 0;      // batch stride (elements), multiple of 4
+  int64_t ld = 0;      // leading dimension (elements), multiple of 4
+  int major_k = 1;     // 1: contraction index contiguous ("K-major"), 0: M/N index contiguous
+  int64_t rows = 0;    // extent of the non-contiguous index
+  int64_t cols = 0;    // extent of the contiguous index
+};
+struct TcGemmProblem {
+  int64_t M = 0, N = 0, K = 0, batch = 1;
+  TcOperand A1, B1, A2, B2;   // second pair optional
+  int a_batched = 1, b_batched = 1, a2_batched = 1, b2_batched = 1;
+  float* C = nullptr; int64_t c_sz = 0, c_sm = 0;
+  float* C_lo = nullptr;      // optional: C receives tf32-hi(v), C_lo the remainder (feeds the next GEMM)
+  GemmEpilogue epi;
+};
+bool tc_available();
+int gemm_tc(const TcGemmProblem& p, cudaStream_t stream);
+// x -> (hi, lo) TF32 split into a padded destination: dst[r*ld_dst + c] for r<rows, c<cols
+int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows,
+               int64_t cols, cudaStream_t stream);
+
+__device__ __forceinline__ float act_apply(int act, float h, float* dphi) {
+  float a, d;
+  if (act == LIP_OP_TANH) {
+    a = tanhf(h);
+    d = 1.f - a * a;
+  } else if (act == LIP_OP_RELU) {
+    a = h > 0.f ? h : 0.f;
+    d = h > 0.f ? 1.f : 0.f;
+  } else {  // LIP_OP_GELU_TANH
+    const float c = 0.7978845608028654f;
+    float u = c * (h + 0.044715f * h * h * h);
+    float t = tanhf(u);
+    a = 0.5f * h * (1.f + t);
+    d = 0.5f * (1.f + t) + 0.5f * h * (1.f - t * t) * c * (1.f + 3.f * 0.044715f * h * h);
+  }
+  *dphi = d;
+  return a;
+}
+
+}  // namespace lip

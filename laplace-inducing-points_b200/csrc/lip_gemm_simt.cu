@@ -1,0 +1,192 @@
+// lip_gemm_simt.cu — exact-fp32 SIMT strided batched GEMM with the hot path's fused epilogue.
+//
+// This is the any-shape path: toy models (D <= 2274, launch-bound), the K=10 logit layer, the forward
+// pass at bind time, and the reference result the tcgen05 3xTF32 kernel is self-tested against.
+// 128x128x16 CTA tile, 256 threads, 8x8 register micro-tile (split 4+4 so shared-memory reads are
+// conflict-free float4), register-prefetch double buffering.
+#include "lip_common.cuh"
+
+namespace lip {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256, PAD = 4;
+
+struct DevOperand {
+  const float* ptr;
+  long long sz, s0, s1;
+};
+
+struct DevGemm {
+  int M, N, K1, K2;
+  DevOperand A1, B1, A2, B2;
+  float* C;
+  long long c_sz, c_sm;
+  float scale;
+  const float* bias; long long bias_sz;
+  const float* mask; long long mask_sm;
+  const float* add;  long long add_sz; float add_scale;
+  int act;
+  float* dphi_out;
+};
+
+template <bool KC>  // KC: the contraction index is the contiguous one for this operand
+__device__ __forceinline__ void load_tile(const DevOperand& op, long long zoff, int row0, int rows, int k0, int K,
+                                          bool is_a, float (&reg)[8]) {
+  // A tile: [BM rows(m)] x [BK k]; B tile: [BK k] x [BN cols(n)].  "row" below = the non-k index.
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = tid + NT * i;
+    int k, r;
+    if (KC) { k = idx % BK; r = idx / BK; } else { r = idx % BM; k = idx / BM; }
+    int gr = row0 + r, gk = k0 + k;
+    float v = 0.f;
+    if (gr < rows && gk < K) {
+      long long off = is_a ? ((long long)gr * op.s0 + (long long)gk * op.s1)
+                           : ((long long)gk * op.s0 + (long long)gr * op.s1);
+      v = __ldg(op.ptr + zoff + off);
+    }
+    reg[i] = v;
+  }
+}
+
+template <bool KC>
+__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], const float (&reg)[8]) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int idx = tid + NT * i;
+    int k, r;
+    if (KC) { k = idx % BK; r = idx / BK; } else { r = idx % BM; k = idx / BM; }
+    S[k][r] = reg[i];
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int npairs = g.A2.ptr ? 2 : 1;
+  for (int pair = 0; pair < npairs; ++pair) {
+    const DevOperand& A = pair ? g.A2 : g.A1;
+    const DevOperand& B = pair ? g.B2 : g.B1;
+    const int K = pair ? g.K2 : g.K1;
+    const long long za = (long long)z * A.sz, zb = (long long)z * B.sz;
+    const int nk = (K + BK - 1) / BK;
+    float ra[8], rb[8];
+    load_tile<A_KC>(A, za, m0, g.M, 0, K, true, ra);
+    load_tile<B_KC>(B, zb, n0, g.N, 0, K, false, rb);
+    store_tile<A_KC>(As[0], ra);
+    store_tile<B_KC>(Bs[0], rb);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+      const int cur = kt & 1;
+      if (kt + 1 < nk) {
+        load_tile<A_KC>(A, za, m0, g.M, (kt + 1) * BK, K, true, ra);
+        load_tile<B_KC>(B, zb, n0, g.N, (kt + 1) * BK, K, false, rb);
+      }
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+        float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (kt + 1 < nk) {
+        store_tile<A_KC>(As[cur ^ 1], ra);
+        store_tile<B_KC>(Bs[cur ^ 1], rb);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- fused epilogue ----
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= g.N) continue;
+      float v = g.scale * acc[i][j];
+      if (g.bias) v += __ldg(g.bias + (long long)z * g.bias_sz + n);
+      const long long co = (long long)z * g.c_sz + (long long)m * g.c_sm + n;
+      if (g.act >= 0) {
+        float d;
+        v = act_apply(g.act, v, &d);
+        if (g.dphi_out) g.dphi_out[co] = d;
+      }
+      if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
+      if (g.add) v += g.add_scale * __ldg(g.add + (long long)z * g.add_sz + (long long)m * g.c_sm + n);
+      g.C[co] = v;
+    }
+  }
+}
+
+}  // namespace
+
+int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return LIP_OK;
+  LIP_REQUIRE(p.A1.ptr && p.B1.ptr && p.C, "gemm_simt: null operand");
+  const bool a_kc = (p.A1.s1 == 1);   // A contiguous along k
+  const bool b_kc = (p.B1.s1 != 1);   // B contiguous along k (else along n)
+  LIP_REQUIRE(a_kc || p.A1.s0 == 1, "gemm_simt: A must be contiguous along m or k");
+  LIP_REQUIRE(!b_kc || p.B1.s0 == 1, "gemm_simt: B must be contiguous along k or n");
+  if (p.A2.ptr) {
+    LIP_REQUIRE(p.B2.ptr != nullptr, "gemm_simt: A2 without B2");
+    LIP_REQUIRE(a_kc ? p.A2.s1 == 1 : p.A2.s0 == 1, "gemm_simt: A2 must share A1's contiguous index");
+    LIP_REQUIRE(b_kc ? p.B2.s0 == 1 : p.B2.s1 == 1, "gemm_simt: B2 must share B1's contiguous index");
+  }
+  DevGemm g;
+  g.M = (int)p.M; g.N = (int)p.N; g.K1 = (int)p.K; g.K2 = (int)p.K2;
+  auto cv = [](const GemmOperand& o) { return DevOperand{o.ptr, o.sz, o.s0, o.s1}; };
+  g.A1 = cv(p.A1); g.B1 = cv(p.B1); g.A2 = cv(p.A2); g.B2 = cv(p.B2);
+  g.C = p.C; g.c_sz = p.c_sz; g.c_sm = p.c_sm;
+  g.scale = p.epi.scale;
+  g.bias = p.epi.bias; g.bias_sz = p.epi.bias_sz;
+  g.mask = p.epi.mask; g.mask_sm = p.epi.mask_sm;
+  g.add = p.epi.add; g.add_sz = p.epi.add_sz; g.add_scale = p.epi.add_scale;
+  g.act = p.epi.act; g.dphi_out = p.epi.dphi_out;
+
+  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM), 1);
+  // gridDim.z is limited to 65535: chunk the batch.
+  const int64_t zmax = 65535;
+  for (int64_t z0 = 0; z0 < p.batch; z0 += zmax) {
+    DevGemm gz = g;
+    int64_t zc = p.batch - z0 < zmax ? p.batch - z0 : zmax;
+    gz.A1.ptr += z0 * g.A1.sz; gz.B1.ptr += z0 * g.B1.sz;
+    if (gz.A2.ptr) { gz.A2.ptr += z0 * g.A2.sz; gz.B2.ptr += z0 * g.B2.sz; }
+    gz.C += z0 * g.c_sz;
+    if (gz.bias) gz.bias += z0 * g.bias_sz;
+    if (gz.add) gz.add += z0 * g.add_sz;
+    if (gz.dphi_out) gz.dphi_out += z0 * g.c_sz;
+    grid.z = (unsigned)zc;
+    if (a_kc && !b_kc) gemm_simt_kernel<true, false><<<grid, NT, 0, stream>>>(gz);
+    else if (!a_kc && !b_kc) gemm_simt_kernel<false, false><<<grid, NT, 0, stream>>>(gz);
+    else if (a_kc && b_kc) gemm_simt_kernel<true, true><<<grid, NT, 0, stream>>>(gz);
+    else gemm_simt_kernel<false, true><<<grid, NT, 0, stream>>>(gz);
+    LIP_LAUNCH_CHECK();
+  }
+  return LIP_OK;
+}
+
+}  // namespace lip

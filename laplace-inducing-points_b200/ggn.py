@@ -1,0 +1,223 @@
+"""Drop-in mirror of /root/reference/src/ggn.py on the B200 path.
+
+Same names / argument meaning as the reference; arrays are torch CUDA tensors instead of jnp arrays.
+Every returned closure is PROBE-BATCHED: it accepts the reference's single vector (`v[D]`) or a stack of
+probes (`V[B, D]`, leading axis) and maps to one C-ABI call (lip_ggn_vp / lip_wt_apply / lip_w_apply), which is
+what `jax.vmap(closure)` does in the reference's callers (stochtrace.py:113-114, tests/test_ggn.py:99).
+"""
+from __future__ import annotations
+
+import math
+import re
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from ._runtime import BoundModel, MLPSpec, dev_f32
+from .utils import flatten_nn_params
+
+_ACT_BY_CLASS = {"SimpleRegressor": cabi.OP_GELU_TANH, "SimpleClassifier": cabi.OP_TANH,
+                 "LargeClassifier": cabi.OP_TANH}
+_ACT_BY_NAME = {"tanh": cabi.OP_TANH, "gelu": cabi.OP_GELU_TANH, "relu": cabi.OP_RELU}
+
+
+def _module_of(state):
+    fn = getattr(state, "apply_fn", None)
+    return getattr(fn, "__self__", None)
+
+
+def _strip(params):
+    tree = {k: v for k, v in dict(params).items() if k not in ("logvar", "batch_stats")}
+    if list(tree.keys()) == ["params"]:  # toy layout (main.py:191-194)
+        tree = dict(tree["params"])
+    return tree
+
+
+def _spec_from(module, params, model_type) -> MLPSpec:
+    """Pattern-match the parameter tree + module class onto the layer program the CUDA library executes.
+    Anything that is not a Dense/activation stack is rejected loudly (no fallback)."""
+    cls = type(module).__name__ if module is not None else None
+    if cls in ("LeNet5", "ResNet1M"):
+        raise NotImplementedError(f"{cls}: conv JVP/VJP kernels are not built yet (SURVEY §8a M3/M4)")
+    act = None
+    if module is not None and isinstance(getattr(module, "activation", None), str):
+        act = _ACT_BY_NAME.get(module.activation)
+    if act is None:
+        act = _ACT_BY_CLASS.get(cls)
+    if act is None:
+        raise ValueError(f"unsupported model for the B200 path: apply_fn of {cls!r}; supported: "
+                         f"{sorted(_ACT_BY_CLASS)} (or a module with .activation in {sorted(_ACT_BY_NAME)})")
+    tree = _strip(params)
+    names = sorted(tree.keys())
+    if not names or any(not re.fullmatch(r"Dense_\d+", n) for n in names):
+        raise ValueError(f"unsupported parameter tree for an MLP: keys {names}")
+    order = sorted(names, key=lambda n: int(n.split("_")[1]))
+    if order != names:
+        raise ValueError("more than 10 Dense layers: flat order (lexicographic) differs from forward order")
+    dims = []
+    for n in order:
+        leaf = tree[n]
+        if sorted(leaf.keys()) != ["bias", "kernel"]:
+            raise ValueError(f"{n}: expected leaves bias, kernel; got {sorted(leaf.keys())}")
+        kin, kout = tuple(leaf["kernel"].shape)
+        if dims and dims[-1] != kin:
+            raise ValueError(f"{n}: kernel in_features {kin} != previous out_features {dims[-1]}")
+        if not dims:
+            dims.append(int(kin))
+        dims.append(int(kout))
+    return MLPSpec(dims, act, model_type)
+
+
+def _logvar_of(params) -> float:
+    p = dict(params)
+    if "logvar" in p:
+        lv = p["logvar"]["logvar"]
+        return float(lv.item() if hasattr(lv, "item") else lv)
+    return 0.0
+
+
+_BIND_CACHE: "OrderedDict[tuple, BoundModel]" = OrderedDict()
+_BIND_CACHE_SIZE = 4
+
+
+def _bind(state, Z, model_type, tensor_path: Optional[bool] = None) -> BoundModel:
+    theta, _ = flatten_nn_params(state.params)
+    Zt = dev_f32(Z)
+    key = (id(state), Zt.data_ptr() if isinstance(Z, torch.Tensor) else id(Z), tuple(Zt.shape),
+           getattr(Z, "_version", 0), model_type, tensor_path, float(theta.double().sum().item()))
+    bm = _BIND_CACHE.get(key)
+    if bm is not None:
+        _BIND_CACHE.move_to_end(key)
+        return bm
+    spec = _spec_from(_module_of(state), state.params, model_type)
+    logvar = _logvar_of(state.params) if model_type == "regressor" else 0.0
+    bm = BoundModel(spec, theta, Zt, logvar, tensor_path)
+    _BIND_CACHE[key] = bm
+    while len(_BIND_CACHE) > _BIND_CACHE_SIZE:
+        _BIND_CACHE.popitem(last=False)
+    return bm
+
+
+def _bind_variables(module, variables, x) -> BoundModel:
+    """Forward pass for Module.apply(variables, x): variables is the toy ({'params': ...}) or scale layout."""
+    mt = getattr(module, "model_type", "classifier")
+    spec = _spec_from(module, variables, mt)
+    theta, _ = flatten_nn_params(variables)
+    return BoundModel(spec, theta, dev_f32(x), 0.0)
+
+
+def _batched(fn, model=None, **attrs):
+    fn._lip_batched = True
+    fn._lip_model = model
+    for k, v in attrs.items():
+        setattr(fn, k, v)
+    return fn
+
+
+# ------------------------------------------------------------------------------------------------------------
+def compute_W_vps(state, Z, model_type, full_set_size=None, blockwise=False, *, tensor_path=None):
+    """ggn.py:9-93.  Returns (Wfun, WTfun) with W = sqrt(N/M) [J_1^T L_1 ... J_M^T L_M]."""
+    bm = _bind(state, Z, model_type, tensor_path)
+    M = bm.M
+    N = full_set_size or M
+    recal = math.sqrt(N / M)
+    K = bm.K
+    reg = model_type == "regressor"
+
+    def WTfun(v):
+        out = bm.wt(v, scale=recal, factor=cabi.FACTOR_SQRT)
+        return out[..., 0] if reg else out          # regressor: (M,) per vector (ggn.py:58,85)
+
+    def Wfun(U):
+        U = dev_f32(U)
+        single = (U.dim() == 1) if reg else (U.dim() == 2)
+        if reg and U.dim() == 2 and U.shape == (M, 1) and M != 1:
+            single = True
+        return bm.w(U, scale=recal, factor=cabi.FACTOR_SQRT, batched=not single)
+
+    _batched(WTfun, bm, _lip_kind="WT", _lip_scale=recal, _lip_transpose=Wfun)
+    _batched(Wfun, bm, _lip_kind="W", _lip_scale=recal, _lip_transpose=WTfun)
+
+    if blockwise:  # ggn.py:79-82 — per-point closures (tests / dead alternating-projection stub only)
+        def W_per_point(i, U_i):
+            U = torch.zeros(M, K, device=bm.device)
+            U[int(i)] = dev_f32(U_i).reshape(K)
+            return bm.w(U, scale=recal, factor=cabi.FACTOR_SQRT, batched=False)
+
+        def WT_per_point(i, v):
+            out = bm.wt(dev_f32(v).reshape(-1), scale=recal, factor=cabi.FACTOR_SQRT)[int(i)]
+            return out[0] if reg else out
+
+        return W_per_point, WT_per_point
+    return Wfun, WTfun
+
+
+def compute_ggn_vp(state, Z, model_type, full_set_size=None, *, tensor_path=None):
+    """ggn.py:97-146.  Returns ggn_vp: v -> (N/M) sum_i J_i^T H_i J_i v  (x exp(-logvar) for regressors)."""
+    bm = _bind(state, Z, model_type, tensor_path)
+    M = bm.M
+    N = full_set_size or M
+    recal = N / M
+    if model_type == "regressor":
+        recal *= math.exp(-bm.logvar)  # ggn.py:112-113
+
+    def ggn_vp(v):
+        return bm.ggn_vp(v, recal, 0.0)
+
+    return _batched(ggn_vp, bm, _lip_kind="GGN", _lip_recal=recal, _lip_alpha=0.0, _lip_transpose=ggn_vp)
+
+
+def compute_ggn_dense(state, Z, model_type, full_set_size=None):
+    """ggn.py:149-193 (debug oracle in the reference).  Built by pushing the identity through ggn_vp, which
+    tests/test_ggn.py:87-131 pins as equal to the explicit sum of J^T H J."""
+    flat_params, unravel_fn = flatten_nn_params(state.params)
+    D = flat_params.numel()
+    vp = compute_ggn_vp(state, Z, model_type, full_set_size)
+    GGN = vp(torch.eye(D, device=flat_params.device))
+    return GGN.T.contiguous(), flat_params, unravel_fn
+
+
+def build_WTW(W, WT, inner_shape, d, *, dtype=torch.float32, block=64):
+    """ggn.py:198-227: dense Gram W^T W (d x d), symmetrised from the upper triangle.
+    When W/WT are this module's closures over one bound model the native lip_gram_wtw runs; otherwise the
+    one-hot blocks are pushed through the given closures (batched when they support it)."""
+    bm = getattr(W, "_lip_model", None)
+    if bm is not None and bm is getattr(WT, "_lip_model", None) and getattr(W, "_lip_kind", "") == "W" \
+            and getattr(WT, "_lip_kind", "") == "WT" and d == bm.M * bm.K:
+        G = bm.gram(scale=W._lip_scale, block=max(int(block), 256))
+        return G.to(dtype) if dtype not in (float, None) and isinstance(dtype, torch.dtype) else G
+    dev = torch.device("cuda", torch.cuda.current_device())
+    G = torch.zeros(d, d, device=dev, dtype=torch.float32)
+    eye = torch.eye(d, device=dev)
+    for start in range(0, d, block):
+        E = eye[start:start + block].reshape((-1,) + tuple(inner_shape))
+        if getattr(W, "_lip_batched", False) and getattr(WT, "_lip_batched", False):
+            cols = WT(W(E)).reshape(E.shape[0], d)
+        else:
+            cols = torch.stack([dev_f32(WT(W(e))).reshape(-1) for e in E])
+        G[:, start:start + cols.shape[0]] = cols.T
+    return torch.triu(G) + torch.triu(G, 1).T
+
+
+def build_WTWz(WT, W_z, inner_shape_z, *, d, dtype=torch.float32, block=64):
+    """ggn.py:233-272 (cross-Gram W^T W_z, used only by the dead '_scalable_exact' objective)."""
+    d_z = int(np.prod(inner_shape_z))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    G = torch.zeros(d, d_z, device=dev)
+    eye = torch.eye(d_z, device=dev)
+    for start in range(0, d_z, block):
+        E = eye[start:start + block].reshape((-1,) + tuple(inner_shape_z))
+        if getattr(W_z, "_lip_batched", False) and getattr(WT, "_lip_batched", False):
+            cols = WT(W_z(E)).reshape(E.shape[0], d)
+        else:
+            cols = torch.stack([dev_f32(WT(W_z(e))).reshape(-1) for e in E])
+        G[:, start:start + cols.shape[0]] = cols.T
+    return G
+
+
+def ensure_symmetry(Mx, jitter=1e-8):
+    """ggn.py:277"""
+    return 0.5 * (Mx + Mx.T) + jitter * torch.eye(Mx.shape[0], device=Mx.device, dtype=Mx.dtype)

@@ -1,0 +1,163 @@
+"""Drop-in mirror of /root/reference/src/stochtrace.py on the B200 path.
+
+Same names and argument meaning.  `seed` is an int / torch.Generator (JAX's threefry keys cannot be reproduced
+without JAX; SURVEY §2.1: probes are inputs) and every estimator also takes `eps=` to supply the probe matrix
+explicitly, which is how the parity tests feed identical probes to this path and to the oracle.
+Probe batching: where the reference vmaps `Xfun` over probe rows, closures flagged `_lip_batched` receive the
+whole [B, n] block in one call.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._runtime import _require_cuda, dev_f32
+from .matfree import _generator, cg
+
+
+def vmap(fn, in_axes=0, out_axes=0):
+    """jax.vmap for matvec closures: batched closures get the whole block, others are looped."""
+
+    def mapped(X):
+        X = dev_f32(X)
+        Xr = X if in_axes == 0 else X.transpose(0, 1)
+        if getattr(fn, "_lip_batched", False):
+            Y = fn(Xr.contiguous())
+        else:
+            Y = torch.stack([dev_f32(fn(x)) for x in Xr])
+        return Y if out_axes == 0 else Y.transpose(0, 1)
+
+    return mapped
+
+
+def _rademacher(seed, shape):
+    g = _generator(seed)
+    return torch.randint(0, 2, shape, generator=g, device=g.device, dtype=torch.int8).float() * 2 - 1
+
+
+def _normal(seed, shape):
+    g = _generator(seed)
+    return torch.randn(*shape, generator=g, device=g.device)
+
+
+def stochastic_trace_estimator_dense(X, seed, num_samples=1_000, *, eps=None):
+    """stochtrace.py:7-19"""
+    X = dev_f32(X)
+    Eps = dev_f32(eps) if eps is not None else _rademacher(seed, (num_samples, X.shape[0]))
+    return ((Eps @ X.T) * Eps).sum(1).mean()
+
+
+def stochastic_trace_estimator_mvp(Xfun, D, seed, num_samples=1_000, dtype=torch.float32, *, eps=None):
+    """stochtrace.py:22-34: mean_b eps_b . X eps_b with Rademacher probes."""
+    Eps = dev_f32(eps) if eps is not None else _rademacher(seed, (num_samples, D))
+    Y = vmap(Xfun)(Eps)
+    return (Eps * Y).sum(1).mean()
+
+
+def _project_out(Q, Mx):
+    """(I - Q Q^T) Mx without the n x n projector of stochtrace.py:47,65,96."""
+    return Mx - Q @ (Q.T @ Mx)
+
+
+def hutchpp_dense(X, seed, num_samples=10, *, eps=None):
+    """stochtrace.py:37-49"""
+    X = dev_f32(X)
+    e = dev_f32(eps) if eps is not None else _normal(seed, (num_samples * 2, X.shape[0]))
+    ns = e.shape[0] // 2
+    S, G = e[:ns], e[ns:]
+    Q, _ = torch.linalg.qr(X @ S.T)
+    PG = _project_out(Q, G.T)
+    return torch.trace(Q.T @ X @ Q) + torch.trace(PG.T @ X @ PG) / ns
+
+
+def hutchpp_mvp(Xfun, D, seed, num_samples=10, *, eps=None):
+    """stochtrace.py:52-79; Xfun maps a MATRIX [D,k] -> [D,k] (:64,74)."""
+    e = dev_f32(eps) if eps is not None else _normal(seed, (num_samples * 2, D))
+    ns = e.shape[0] // 2
+    S, G = e[:ns], e[ns:]
+    Q, _ = torch.linalg.qr(dev_f32(Xfun(S.T.contiguous())))
+
+    def quad_term(Mx):
+        return Mx.T @ dev_f32(Xfun(Mx.contiguous()))
+
+    return torch.trace(quad_term(Q)) + torch.trace(quad_term(_project_out(Q, G.T))) / ns
+
+
+def hutchpp(Xfun, sampler):
+    """stochtrace.py:82-111; Xfun maps a vector; NB the residual term divides by the FULL probe count (:84,109)."""
+    e = dev_f32(sampler(...))
+    num_samples = e.shape[0]
+    S, G = e[:num_samples // 2], e[num_samples // 2:]
+    Q, _ = torch.linalg.qr(vmap(Xfun, in_axes=0, out_axes=1)(S), mode="reduced")
+
+    def quad_term(Mx):
+        Y = vmap(Xfun, in_axes=1, out_axes=1)(Mx)
+        return Mx.T @ Y
+
+    return torch.trace(quad_term(Q)) + torch.trace(quad_term(_project_out(Q, G.T))) / num_samples
+
+
+def apply_X(Xfun, Mx):
+    """stochtrace.py:113-114: rows of Mx are probes; result columns are X @ probe."""
+    return vmap(Xfun, in_axes=0, out_axes=1)(Mx)
+
+
+def hutchpp_v2(Xfun, sampler, *, s1, s2):
+    """stochtrace.py:118-135"""
+    e = dev_f32(sampler(...))
+    S, G = e[:s1], e[s1:]
+    Y = apply_X(Xfun, S)                                  # (n, s1)
+    Q, _ = torch.linalg.qr(Y, mode="reduced")
+    XQ = apply_X(Xfun, Q.T)
+    low_rank = (XQ * Q).sum()                             # tr(Q^T X Q)
+    G_perp = G - (G @ Q) @ Q.T
+    XGp = apply_X(Xfun, G_perp)
+    resid = (G_perp.T * XGp).sum() / s2                   # tr(G_perp X G_perp^T)
+    return low_rank + resid
+
+
+def _cg_matrix(Xfun):
+    """Xinv for the *_inv_mvp estimators: CG on every column of a [D,k] block (stochtrace.py:144-147,189-193)."""
+
+    def Xinv(Mx):
+        Mx = dev_f32(Mx)
+        if Mx.dim() == 1:
+            return cg(Xfun, Mx)[0]
+        return cg(Xfun, Mx.T.contiguous())[0].T
+
+    return Xinv
+
+
+def hutchpp_inv_mvp(Xfun, D, seed, num_samples=10, *, eps=None):
+    """stochtrace.py:138-148"""
+    return hutchpp_mvp(_cg_matrix(Xfun), D, seed, num_samples=num_samples, eps=eps)
+
+
+def na_hutchpp_dense(X, seed, num_samples=10, *, eps=None):
+    """stochtrace.py:151-163"""
+    X = dev_f32(X)
+    c3 = 0.25
+    e = dev_f32(eps) if eps is not None else _rademacher(seed, (num_samples * 4, X.shape[0]))
+    ns = e.shape[0] // 4
+    S, R, G = e[:ns], e[ns:3 * ns], e[3 * ns:]
+    W = X @ S.T
+    Zm = X @ R.T
+    pin = torch.linalg.pinv(S @ Zm)
+    return torch.trace(pin @ (W.T @ Zm)) + (torch.trace(G @ X @ G.T) - torch.trace(G @ Zm @ pin @ W.T @ G.T)) / (c3 * 4 * ns)
+
+
+def na_hutchpp_mvp(Xfun, D, seed, num_samples=10, dtype=torch.float32, *, eps=None):
+    """stochtrace.py:166-180; Xfun maps a matrix."""
+    c3 = 0.25
+    e = dev_f32(eps) if eps is not None else _rademacher(seed, (num_samples * 4, D))
+    ns = e.shape[0] // 4
+    S, R, G = e[:ns], e[ns:3 * ns], e[3 * ns:]
+    W = dev_f32(Xfun(S.T.contiguous()))
+    Zm = dev_f32(Xfun(R.T.contiguous()))
+    pin = torch.linalg.pinv(S @ Zm)
+    XG = dev_f32(Xfun(G.T.contiguous()))
+    return torch.trace(pin @ (W.T @ Zm)) + (torch.trace(G @ XG) - torch.trace(G @ Zm @ pin @ W.T @ G.T)) / (c3 * 4 * ns)
+
+
+def na_hutchpp_inv_mvp(Xfun, D, seed, num_samples=10, *, eps=None):
+    """stochtrace.py:183-194"""
+    return na_hutchpp_mvp(_cg_matrix(Xfun), D, seed, num_samples=num_samples, eps=eps)

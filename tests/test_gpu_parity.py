@@ -1,0 +1,311 @@
+"""GPU parity: the CUDA path (through the C ABI) against the float64 CPU oracle on identical weights, points
+and probe matrices.  Tolerances are BASELINE.json's: GGN-vector products <= 1e-5 relative (fp32),
+trace / logdet / CG <= 1e-4 relative."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_pair, rel_err
+from oracle import lip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_GGN = 1e-5
+TOL_EST = 1e-4
+
+CONFIGS = {
+    # name: (kind, hidden, n_out, in_dim, M, N, logvar)
+    "C1_toy_sine": ("regressor", [8, 8, 8, 8], 1, 1, 40, 240, 0.0),
+    "C2_xor": ("classifier", [16, 16], 2, 2, 32, 800, 0.0),
+    "C3a_subset89": ("classifier", [32, 32, 32], 2, 2, 96, 10000, 0.0),
+    "mlp_ragged": ("large", [37, 129, 20], 7, 45, 133, 1000, 0.0),
+    "reg_logvar": ("regressor", [9], 1, 3, 17, 170, 0.4),
+    "linear": ("regressor", [], 1, 1, 4, 4, 0.07),
+}
+
+
+def _setup(name, seed=0):
+    kind, hidden, n_out, in_dim, M, N, logvar = CONFIGS[name]
+    ost, lst = make_pair(kind, hidden=hidden, n_out=n_out, in_dim=in_dim, seed=100 + seed, logvar=logvar)
+    rng = np.random.default_rng(1000 + seed)
+    Z = rng.standard_normal((M, in_dim)).astype(np.float32)
+    mt = "regressor" if kind == "regressor" else "classifier"
+    return ost, lst, Z, mt, N
+
+
+def cu(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32, device="cuda")
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_ggn_vp_matches_oracle(name):
+    from lip_b200 import ggn, lla
+    ost, lst, Z, mt, N = _setup(name)
+    D = ost.flat()[0].size
+    rng = np.random.default_rng(5)
+    V = rng.choice([-1.0, 1.0], size=(6, D)).astype(np.float32)
+    V[3:] = rng.standard_normal((3, D)).astype(np.float32)
+    ref_vp = O.compute_ggn_vp(ost, Z, mt, full_set_size=N)
+    ref = np.stack([ref_vp(v) for v in V.astype(np.float64)])
+    vp = ggn.compute_ggn_vp(lst, cu(Z), mt, full_set_size=N)
+    got = vp(cu(V)).cpu().numpy()
+    assert got.shape == (6, D)
+    assert rel_err(got, ref) < TOL_GGN
+    single = vp(cu(V[0])).cpu().numpy()          # the reference's un-batched signature
+    assert single.shape == (D,) and rel_err(single, ref[0]) < TOL_GGN
+    alpha = 0.37
+    cvp = lla.compute_curvature_approx(lst, cu(Z), mt, alpha, full_set_size=N)
+    assert rel_err(cvp(cu(V)).cpu().numpy(), ref + alpha * V) < TOL_GGN
+
+
+def test_G1_golden_linear_model():
+    """tests/test_ggn.py:87-102 / fixtures.py:24: GGN = e^{-logvar} [[n, sum x],[sum x, sum x^2]] in (bias, kernel) order."""
+    from lip_b200 import ggn
+    ost, lst, _, mt, _ = _setup("linear")
+    X = np.array([[-1.0], [0.0], [1.1], [3.5]], dtype=np.float32)
+    G, flat, _ = ggn.compute_ggn_dense(lst, cu(X), "regressor")
+    expect = math.exp(-0.07) * np.array([[4.0, 3.6], [3.6, 14.46]])
+    np.testing.assert_allclose(G.cpu().numpy(), expect, rtol=2e-6, atol=1e-6)
+    Wfun, WTfun = ggn.compute_W_vps(lst, cu(X), "regressor")
+    WT_out = WTfun(torch.eye(2, device="cuda"))
+    assert WT_out.shape == (2, 4)                  # regressor: (M,) per vector
+    comp = Wfun(WT_out)
+    np.testing.assert_allclose(comp.cpu().numpy(), expect, rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["C1_toy_sine", "C2_xor", "mlp_ragged", "reg_logvar"])
+def test_W_WT_match_oracle(name):
+    from lip_b200 import ggn
+    ost, lst, Z, mt, N = _setup(name)
+    D = ost.flat()[0].size
+    rng = np.random.default_rng(6)
+    V = rng.standard_normal((4, D)).astype(np.float32)
+    Wo, WTo = O.compute_W_vps(ost, Z, mt, full_set_size=N)
+    Wg, WTg = ggn.compute_W_vps(lst, cu(Z), mt, full_set_size=N)
+    ref_wt = np.stack([WTo(v) for v in V.astype(np.float64)])
+    got_wt = WTg(cu(V)).cpu().numpy()
+    assert got_wt.shape == ref_wt.shape
+    assert rel_err(got_wt, ref_wt) < TOL_GGN
+    U = rng.standard_normal(ref_wt.shape).astype(np.float32)
+    ref_w = np.stack([Wo(u) for u in U.astype(np.float64)])
+    got_w = Wg(cu(U)).cpu().numpy()
+    assert rel_err(got_w, ref_w) < TOL_GGN
+    assert rel_err(Wg(cu(U[0])).cpu().numpy(), ref_w[0]) < TOL_GGN
+    # identity W(W^T v) == GGN v  (tests/test_sample.py:19-49)
+    vp = ggn.compute_ggn_vp(lst, cu(Z), mt, full_set_size=N)
+    assert rel_err(Wg(WTg(cu(V))).cpu().numpy(), vp(cu(V)).cpu().numpy()) < 2e-5
+    # blockwise closures (ggn.py:79-82)
+    Wb, WTb = ggn.compute_W_vps(lst, cu(Z), mt, full_set_size=N, blockwise=True)
+    Wob, WTob = O.compute_W_vps(ost, Z, mt, full_set_size=N, blockwise=True)
+    assert rel_err(WTb(3, cu(V[0])).cpu().numpy(), WTob(3, V[0].astype(np.float64))) < TOL_GGN
+
+
+def test_gram_matches_oracle():
+    from lip_b200 import ggn
+    ost, lst, Z, mt, N = _setup("C2_xor")
+    Wo, WTo = O.compute_W_vps(ost, Z, mt)
+    d = Z.shape[0] * 2
+    ref = O.build_WTW(Wo, WTo, (Z.shape[0], 2), d)
+    Wg, WTg = ggn.compute_W_vps(lst, cu(Z), mt)
+    got = ggn.build_WTW(Wg, WTg, (Z.shape[0], 2), d, dtype=torch.float32, block=2).cpu().numpy()
+    assert rel_err(got, ref) < TOL_GGN
+    np.testing.assert_array_equal(got, got.T)
+    # generic (closure-pushing) path gives the same matrix
+    plainW = lambda U: Wg(U)
+    got2 = ggn.build_WTW(plainW, WTg, (Z.shape[0], 2), d, dtype=torch.float32, block=16).cpu().numpy()
+    assert rel_err(got2, ref) < TOL_GGN
+
+
+def test_forward_outputs_match_oracle():
+    from lip_b200 import ggn
+    for name in ("C1_toy_sine", "mlp_ragged"):
+        ost, lst, Z, mt, N = _setup(name)
+        bm = ggn._bind(lst, cu(Z), mt)
+        assert rel_err(bm.outputs().cpu().numpy(), O.model_outputs(ost, Z)) < 2e-6
+
+
+# --------------------------------------------------------------------------------- vector stage
+def test_cg_matches_oracle():
+    from lip_b200 import matfree
+    rng = np.random.default_rng(3)
+    n = 300
+    G = rng.standard_normal((n, n))
+    A = (G @ G.T / n + np.eye(n)).astype(np.float32)
+    Bv = rng.standard_normal((5, n)).astype(np.float32)
+    At = cu(A)
+    mv = matfree.batched(lambda X: X @ At)
+    x, iters = matfree.cg(mv, cu(Bv))
+    for b in range(5):
+        xo, ko = O.cg(lambda v: A.astype(np.float64) @ v, Bv[b].astype(np.float64))
+        assert rel_err(x[b].cpu().numpy(), xo) < TOL_EST
+        assert abs(int(iters[b]) - ko) <= 1
+    x1, _ = matfree.cg(lambda v: At @ v, cu(Bv[0]))        # un-batched closure, single vector
+    assert rel_err(x1.cpu().numpy(), O.cg(lambda v: A.astype(np.float64) @ v, Bv[0].astype(np.float64))[0]) < TOL_EST
+
+
+def test_tridiag_funm_vs_eigh():
+    from lip_b200 import matfree
+    rng = np.random.default_rng(8)
+    for k in (1, 2, 5, 40, 300):
+        d = (rng.random((3, k)) * 3 + 0.5).astype(np.float32)
+        e = (rng.standard_normal((3, max(k - 1, 0))) * 0.7).astype(np.float32)
+        for fn, f, clip in (("log", np.log, None), ("invsqrt", lambda x: 1 / np.sqrt(x), 1.0), ("inv", lambda x: 1 / x, None)):
+            dd = d.copy() + 3.0   # diagonally dominant -> SPD
+            Ts = [np.diag(dd[b].astype(np.float64)) + np.diag(e[b].astype(np.float64), 1) + np.diag(e[b].astype(np.float64), -1)
+                  for b in range(3)]
+            df = matfree.DenseFunm(fn, clip)
+            q = df.quad_e1(cu(dd), cu(e)).cpu().numpy()
+            fe = df.apply_e1(cu(dd), cu(e)).cpu().numpy()
+            for b in range(3):
+                w, V = np.linalg.eigh(Ts[b])
+                if clip is not None:
+                    w = np.clip(w, clip, None)
+                fT = V @ np.diag(f(w)) @ V.T
+                assert abs(q[b] - fT[0, 0]) <= 2e-6 * max(1.0, abs(fT[0, 0]))
+                assert rel_err(fe[b], fT[:, 0]) < 5e-6
+
+
+def test_G2_lanczos_invsqrt_golden_and_oracle():
+    """tests/test_sample.py:334-355 on the GPU path, and against the oracle's Lanczos."""
+    from lip_b200 import matfree
+    D = 100
+    diag = np.arange(1, D + 1, dtype=np.float64) / D
+    dg = cu(diag)
+    invsqrt = matfree.dense_funm_sym_eigh(lambda x: 1.0 / torch.sqrt(x))
+    f = matfree.funm_lanczos_sym(invsqrt, matfree.decomp.tridiag_sym(20))
+    res = f(lambda v: dg * v, torch.ones(D, device="cuda")).cpu().numpy()
+    np.testing.assert_allclose(res, 1.0 / np.sqrt(diag), rtol=1e-1)
+    fo = O.funm_lanczos_sym(O.dense_funm_sym_eigh(lambda x: 1.0 / np.sqrt(x), clip_min=None), O.tridiag_sym(20))
+    assert rel_err(res, fo(lambda v: diag * v, np.ones(D))) < TOL_EST
+
+
+def test_lanczos_slq_and_gkl_logdet_match_oracle():
+    from lip_b200 import ggn, lla, matfree, matfree_monkeypatch
+    ost, lst, Z, mt, N = _setup("C2_xor")
+    D = ost.flat()[0].size
+    alpha = 1.7
+    rng = np.random.default_rng(12)
+    probes = rng.choice([-1.0, 1.0], size=(3, D)).astype(np.float32)
+    # Lanczos form with the patched (clipped) integrand, operator = curvature_vp
+    cvp_o = O.compute_curvature_approx(ost, Z, mt, alpha, full_set_size=N)
+    ref = O.slq_logdet_lanczos(cvp_o, probes.astype(np.float64), 25, clip_min=1.0)
+    cvp = lla.compute_curvature_approx(lst, cu(Z), mt, alpha, full_set_size=N)
+    integrand = matfree_monkeypatch.integrand_funm_sym_logdet(matfree.decomp.tridiag_sym(25))
+    est = matfree.stochtrace.estimator(integrand, sampler=lambda _: cu(probes))
+    got = float(est(cvp, 0))
+    assert abs(got - ref) <= TOL_EST * abs(ref)
+    # GKL product form (train_inducing.py:148-171)
+    ref2 = O.slq_logdet_gkl(ost, Z, mt, alpha, probes.astype(np.float64), 25)
+    Wz, WzT = ggn.compute_W_vps(lst, cu(Z), mt, full_set_size=None)
+    sa = math.sqrt(alpha)
+    d = Z.shape[0] * 2
+
+    @matfree.batched
+    def bidiag_target(v):
+        v = v.reshape(-1, D)
+        return torch.cat([sa * v, WzT(v).reshape(v.shape[0], d)], dim=1)
+
+    @matfree.batched
+    def bidiag_target_T(u):
+        u = u.reshape(-1, D + d)
+        return sa * u[:, :D] + Wz(u[:, D:].reshape(-1, Z.shape[0], 2))
+
+    problem = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(25))
+    est2 = matfree.stochtrace.estimator(lambda Av, s: problem(Av, s, bidiag_target_T), sampler=lambda _: cu(probes))
+    est2_fn = matfree.stochtrace.estimator(matfree.batched(lambda Av, s: problem(Av, s, bidiag_target_T)),
+                                           sampler=lambda _: cu(probes))
+    got2 = float(est2_fn(bidiag_target, 0))
+    assert abs(got2 - ref2) <= TOL_EST * abs(ref2)
+    assert abs(float(est2(bidiag_target, 0)) - ref2) <= TOL_EST * abs(ref2)
+
+
+# --------------------------------------------------------------------------------- estimators
+def test_estimators_match_oracle_with_identical_probes():
+    from lip_b200 import lla, stochtrace
+    ost, lst, Z, mt, N = _setup("C2_xor")
+    D = ost.flat()[0].size
+    alpha = 0.9
+    cvp_o = O.compute_curvature_approx(ost, Z, mt, alpha, full_set_size=N)
+    cvp = lla.compute_curvature_approx(lst, cu(Z), mt, alpha, full_set_size=N)
+    rng = np.random.default_rng(2)
+    eps = rng.choice([-1.0, 1.0], size=(64, D)).astype(np.float32)
+    ref = O.stochastic_trace_estimator_mvp(cvp_o, eps.astype(np.float64))
+    got = float(stochtrace.stochastic_trace_estimator_mvp(cvp, D, 0, eps=cu(eps)))
+    assert abs(got - ref) <= TOL_EST * abs(ref)
+    ref2 = O.hutchpp_v2(cvp_o, eps.astype(np.float64), s1=48, s2=16)
+    got2 = float(stochtrace.hutchpp_v2(cvp, lambda _: cu(eps), s1=48, s2=16))
+    assert abs(got2 - ref2) <= TOL_EST * abs(ref2)
+    g = rng.standard_normal((40, D)).astype(np.float32)
+    ref3 = O.hutchpp(cvp_o, g.astype(np.float64))
+    got3 = float(stochtrace.hutchpp(cvp, lambda _: cu(g)))
+    assert abs(got3 - ref3) <= TOL_EST * abs(ref3)
+
+
+def test_G3_golden_traces_on_gpu():
+    """tests/fixtures.py:201-209, tests/test_stochtrace.py:90-97: hutchpp_v2 exact when s1 >= n."""
+    from lip_b200 import stochtrace
+    A = np.array([[1.0, 4, 50], [-30, 4.0, 16], [12, 6, 5.0]])
+    rng = np.random.default_rng(3)
+    for Mx, tr in ((np.diag([1.0, 2.0, 3.0]), 6.0), (A @ A.T, 3894.0)):
+        Mt = cu(Mx)
+        eps = cu(rng.choice([-1.0, 1.0], size=(8, 3)))
+        est = float(stochtrace.hutchpp_v2(lambda v: Mt @ v, lambda _: eps, s1=4, s2=4))
+        assert abs(est - tr) <= 2e-5 * tr
+        est_d = float(stochtrace.stochastic_trace_estimator_dense(Mt, 0, eps=eps))
+        assert abs(est_d - O.stochastic_trace_estimator_dense(Mx, eps.cpu().numpy().astype(np.float64))) <= 1e-4 * tr
+    n = 150
+    G = rng.standard_normal((n, n))
+    M3 = G @ G.T
+    M3t = cu(M3)
+    g = rng.standard_normal((60, n)).astype(np.float32)
+    mat = lambda Mx: M3t @ Mx
+    assert abs(float(stochtrace.hutchpp_mvp(mat, n, 0, eps=cu(g))) - O.hutchpp_mvp(lambda Mx: M3 @ Mx, g.astype(np.float64))) \
+        <= 1e-4 * np.trace(M3)
+    r = rng.choice([-1.0, 1.0], size=(80, n)).astype(np.float32)
+    assert abs(float(stochtrace.na_hutchpp_mvp(mat, n, 0, eps=cu(r))) - O.na_hutchpp_mvp(lambda Mx: M3 @ Mx, r.astype(np.float64))) \
+        <= 5e-4 * np.trace(M3)
+    X = A @ A.T
+    Xt = cu(X)
+    g3 = rng.standard_normal((20, 3)).astype(np.float32)
+    ref = O.hutchpp_inv_mvp(lambda v: X @ v, g3.astype(np.float64))
+    got = float(stochtrace.hutchpp_inv_mvp(lambda v: Xt @ v, 3, 0, eps=cu(g3)))
+    assert abs(got - ref) <= 2e-3 * abs(ref)
+
+
+# --------------------------------------------------------------------------------- sampler + predictive
+def test_sampler_and_predictive_match_oracle():
+    from lip_b200 import lla, sample as S
+    ost, lst, Z, mt, N = _setup("C2_xor")
+    Z = Z[:12]
+    D = ost.flat()[0].size
+    alpha = 2.5
+    rng = np.random.default_rng(4)
+    Eps = rng.standard_normal((3, D)).astype(np.float32)
+    ref = O.sample(ost, Z, D, alpha, Eps.astype(np.float64), mt, full_set_size=N)
+    got = S.sample(lst, cu(Z), D, alpha, 0, mt, num_samples=3, full_set_size=N, eps=cu(Eps)).cpu().numpy()
+    assert got.shape == (3, D)
+    assert rel_err(got, ref) < TOL_EST
+    Xnew = rng.standard_normal((9, 2)).astype(np.float32)
+    refp = O.predict_lla_scalable(ost, Xnew, Z, mt, alpha, Eps.astype(np.float64), full_set_size=N)
+    gotp = lla.predict_lla_scalable(lst, cu(Xnew), cu(Z), mt, alpha, full_set_size=N, num_samples=3, eps=cu(Eps)).cpu().numpy()
+    assert gotp.shape == (3, 9, 2)
+    assert rel_err(gotp, refp) < TOL_EST
+
+
+def test_unsupported_models_fail_loudly():
+    from lip_b200 import ggn, scalemodels
+    st = scalemodels.TrainState(params={"Conv_0": {"kernel": np.zeros((5, 5, 1, 6), np.float32)}},
+                                apply_fn=scalemodels.LeNet5().apply)
+    with pytest.raises(NotImplementedError):
+        ggn.compute_ggn_vp(st, torch.zeros(2, 28, 28, 1, device="cuda"), "classifier")
+
+    class Weird:
+        def apply(self, *a, **k):
+            return None
+
+    st2 = scalemodels.TrainState(params={"Dense_0": {"bias": np.zeros(2, np.float32), "kernel": np.zeros((3, 2), np.float32)}},
+                                 apply_fn=Weird().apply)
+    with pytest.raises(ValueError):
+        ggn.compute_ggn_vp(st2, torch.zeros(2, 3, device="cuda"), "classifier")
