@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: probe-batched GGN-vector products/s (+ SLQ logdet time) on the MNIST-MLP
+configuration C3b of BASELINE.md (LargeClassifier 784-1024-512-256-128-10, D=1,494,154, M=512 inducing points,
+N=60,000, alpha=1e-3), synthetic weights / points / Rademacher probes.
+
+  python bench.py --gpus N --steps K --warmup W            # B200 path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on the host CPU cores
+
+One "step" = one Hutchinson trace-estimator pass (src/stochtrace.py:22-34) over this rank's B probes:
+curvature_vp(V) (src/lla.py:19-23 -> src/ggn.py:133-144) for all probes in ONE lip_ggn_vp call, the per-probe
+quadratic forms v.(Gv) (lip_dot), and — for N>1 — one NCCL all-reduce of the trace accumulator.  Probes are
+sharded over ranks (weak scaling: B per GPU fixed), weights/points/activation cache replicated.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DIMS = [784, 1024, 512, 256, 128, 10]
+M_POINTS, N_FULL, ALPHA = 512, 60_000, 1e-3
+SIGMA_ALL = sum(DIMS[i] * DIMS[i + 1] for i in range(len(DIMS) - 1))
+SIGMA_GE2 = sum(DIMS[i] * DIMS[i + 1] for i in range(1, len(DIMS) - 1))
+FLOP_PER_PRODUCT = M_POINTS * (4 * SIGMA_ALL + 4 * SIGMA_GE2)      # 4.468 GFLOP
+WORKLOAD = "C3b MNIST-MLP 784-1024-512-256-128-10 (D=1494154), M=512, N=60000, alpha=1e-3"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--probes", type=int, default=256, help="probes per GPU per step")
+    ap.add_argument("--slq-k", type=int, default=64)
+    ap.add_argument("--slq-probes", type=int, default=4)
+    ap.add_argument("--cpu-probes", type=int, default=2, help="products in the CPU-baseline sample")
+    ap.add_argument("--no-slq", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tensor-path", type=int, default=-1, help="-1 auto, 0 SIMT fp32, 1 tcgen05 3xTF32")
+    return ap.parse_args()
+
+
+def build_states(seed=1003):
+    import numpy as np
+    from helpers import make_pair
+    ost, lst = make_pair("large", hidden=DIMS[1:-1], n_out=DIMS[-1], in_dim=DIMS[0], seed=seed, in_shape=(28, 28, 1))
+    rng = np.random.default_rng(seed + 1)
+    Z = rng.random((M_POINTS, DIMS[0]), dtype=np.float32)
+    return ost, lst, Z
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                return
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return None
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measure_tf32_peak(torch):
+    """cuBLAS TF32 8192^3, best of 10 (the way MEASURED_PEAKS.json measures bf16) — the tensor roofline denominator."""
+    n = 8192
+    a = torch.randn(n, n, device="cuda")
+    b = torch.randn(n, n, device="cuda")
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    best = float("inf")
+    for _ in range(3):
+        torch.matmul(a, b)
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return 2 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_reference_products_per_s(ost, Z, n_products, steps=1, warmup=0):
+    """The reference's algorithm (src/ggn.py:133-144: sequential loop over the M points, per-point jvp, redundant
+    forward, closed-form Hessian, per-point vjp) restated in torch fp32 on the host cores (oracle/, kind 'port':
+    JAX is not installed in this image so /root/reference cannot run)."""
+    import numpy as np
+    import torch
+    from oracle import lip_oracle as O
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    vp = O.compute_curvature_approx(ost, Z, "classifier", ALPHA, full_set_size=N_FULL, sequential=True,
+                                    dtype=torch.float32)
+    D = ost.flat()[0].size
+    rng = np.random.default_rng(7)
+    V = rng.choice([-1.0, 1.0], size=(n_products, D)).astype(np.float32)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for v in V:
+            vp(v)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return n_products * len(times) / total, cores, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ost, _, Z = build_states()
+    # bounded sample: ONE product (all 512 points) per step so that --steps 10 --warmup 3 ends within minutes
+    args.cpu_probes = 1
+    pps, cores, sec = cpu_reference_products_per_s(ost, Z, args.cpu_probes, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    sample = f"{args.cpu_probes} products (all {M_POINTS} points each) per step, torch fp32 restatement of src/ggn.py:133-144"
+    line = {"impl": "reference", "metric": "ggn_vec_products_per_s", "value": pps, "unit": "products/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "probes_per_step": args.cpu_probes},
+            "cpu_baseline": {"value": pps, "unit": "products/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": pps, "unit": "products/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as entry
+    entry.build()
+    import lip_b200  # noqa: F401
+    from lip_b200 import _cabi, lla, matfree, ggn
+    from lip_b200._runtime import ptr, scratch, stream
+    L = _cabi.lib()
+
+    ost, lst, Z = build_states()
+    D = ost.flat()[0].size
+    B = args.probes
+    dev = torch.device("cuda", local)
+    Zd = torch.as_tensor(Z, device=dev)
+    tp = None if args.tensor_path < 0 else bool(args.tensor_path)
+    cvp = lla.compute_curvature_approx(lst, Zd, "classifier", ALPHA, full_set_size=N_FULL, tensor_path=tp)
+    bm = cvp._lip_model
+    path = bm.path_name() if hasattr(bm, "path_name") else "simt-fp32"
+
+    rng = np.random.default_rng(2000 + rank)
+    host_i8 = torch.from_numpy(rng.integers(0, 2, size=(B, D), dtype=np.int8) * 2 - 1).pin_memory()
+    V = host_i8.to(dev).float()
+    q = torch.empty(B, device=dev)
+    acc = torch.zeros(1, device=dev)
+    sc, _ = scratch(L.lip_dot_scratch_bytes(D, B))
+
+    def step(Vin):
+        Y = cvp(Vin)                                                  # [B, D]: one lip_ggn_vp call
+        _cabi.check(L.lip_dot(ptr(Vin), ptr(Y), ptr(q), D, B, D, D, sc, stream()))
+        part = q.sum(0, keepdim=True)
+        if world > 1:
+            dist.all_reduce(part)                                     # trace accumulator (probe-sharded Hutchinson)
+        acc.add_(part)
+        return Y
+
+    for _ in range(args.warmup):
+        step(V)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = L.lip_launch_count()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step(V)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = L.lip_launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+    trace_est = float(acc.item()) / (B * world * (args.steps + args.warmup))
+
+    # ---- end to end through the public API with HOST probes (pinned int8 +-1), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        bufs = [torch.empty(B, D, dtype=torch.int8, device=dev) for _ in range(2)]
+        evs = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                bufs[i % 2].copy_(host_i8, non_blocking=True)
+                evs[i % 2].record(copy_stream)
+
+        def e2e_run(nsteps):
+            res = []
+            prefetch(0)
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    copy_stream.wait_stream(torch.cuda.current_stream())   # buffer (i+1)%2 is free once step i-1 is done
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(evs[i % 2])
+                step(bufs[i % 2].float())
+                res.append(q.cpu())                                        # D2H of the step's result (B floats)
+            return res
+
+        e2e_run(2)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e2e_run(args.steps)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * args.steps / float(dt.item()), "unit": "products/s",
+               "h2d_bytes_per_step": B * D, "d2h_bytes_per_step": B * 4,
+               "note": "pinned int8 +-1 probes -> lla.compute_curvature_approx(...)(V) -> v.(Gv) read back; H2D double-buffered"}
+
+    # ---- SLQ logdet (GKL form, src/train_inducing.py:148-171), probes sharded over ranks ----
+    slq = None
+    if not args.no_slq:
+        k, ns = args.slq_k, args.slq_probes
+        Wz, WzT = ggn.compute_W_vps(lst, Zd, "classifier", full_set_size=None, tensor_path=tp)
+        sa = math.sqrt(ALPHA)
+        d = M_POINTS * DIMS[-1]
+
+        @matfree.batched
+        def Av(v):
+            v = v.reshape(-1, D)
+            return torch.cat([sa * v, WzT(v).reshape(v.shape[0], d)], dim=1)
+
+        @matfree.batched
+        def vA(u):
+            u = u.reshape(-1, D + d)
+            return Wz(u[:, D:].reshape(-1, M_POINTS, DIMS[-1])) .add_(u[:, :D], alpha=sa)
+
+        problem = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(k))
+        mine = list(range(rank, ns, world))
+        probes = V[:ns][mine] if mine else None
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        part = problem(Av, probes, vA).sum().reshape(1) if mine else torch.zeros(1, device=dev)
+        if world > 1:
+            dist.all_reduce(part)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        slq = {"seconds": float(dt.item()), "k": k, "probes": ns, "logdet_estimate": float(part.item()) / ns,
+               "form": "GKL bidiag on [sqrt(alpha) I; Wz^T]"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    tf32_peak = measure_tf32_peak(torch)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    achieved = FLOP_PER_PRODUCT * B / (ms_step * 1e-3) / 1e12
+    peak = tf32_peak / 3.0
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "kernel": "all GEMM launches of one lip_ggn_vp call (JVP + VJP sweeps)",
+                "peak_source": f"cuBLAS TF32 8192^3 best-of-10 measured in this run = {tf32_peak:.1f} TFLOP/s, divided by 3 "
+                               f"(3xTF32 emulated fp32); bf16 of MEASURED_PEAKS.json = {peaks.get('bf16_tflops')}",
+                "algorithmic_flop_per_launch_group": FLOP_PER_PRODUCT * B}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        pps, cores, sec = cpu_reference_products_per_s(ost, Z, args.cpu_probes)
+        cpu = {"value": pps, "unit": "products/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_probes} products, torch fp32 restatement of src/ggn.py:133-144 (JAX not installed), {sec:.1f} s"}
+    line = {"metric": "ggn_vec_products_per_s", "value": value, "unit": "products/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "probes_per_gpu": B, "path": path,
+                       "l2": "inputs larger than L2 (V and out are %.2f GB each per GPU)" % (B * D * 4 / 1e9),
+                       "parallelism": f"probe-sharded x{world}"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "slq_logdet": slq, "hutchinson_trace_estimate": trace_est}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,8 @@ typedef enum {
 
 const char* lip_last_error(void);
 int lip_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+int64_t lip_launch_count(void);
 /* 1 if the current device is sm_100 (tcgen05 path usable), 0 otherwise, <0 on error */
 int lip_device_is_sm100(void);
 

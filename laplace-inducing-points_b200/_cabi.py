@@ -27,6 +27,7 @@ _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_
 SIGNATURES = {
     "lip_last_error": (C.c_char_p, []),
     "lip_version": (C.c_int, []),
+    "lip_launch_count": (_I64, []),
     "lip_device_is_sm100": (C.c_int, []),
     "lip_model_create": (C.c_int, [C.POINTER(LayerDesc), _I32, _I32, _I64, C.POINTER(_P)]),
     "lip_model_destroy": (C.c_int, [_P]),

@@ -20,7 +20,9 @@ def _require_cuda() -> torch.device:
 def dev_f32(x, device=None) -> torch.Tensor:
     device = device or _require_cuda()
     if isinstance(x, torch.Tensor):
-        return x.to(device=device, dtype=torch.float32).contiguous()
+        if x.device != device:   # move first (possibly a narrow dtype from pinned host memory), cast on the device
+            x = x.to(device=device, non_blocking=True)
+        return x.to(dtype=torch.float32).contiguous()
     import numpy as np
     return torch.as_tensor(np.asarray(x), dtype=torch.float32).to(device).contiguous()
 

@@ -1,5 +1,5 @@
 // lip_api.cu — error reporting and device queries of the C ABI.
-#include <mutex>
+#include <atomic>
 
 #include "lip_common.cuh"
 
@@ -16,6 +16,10 @@ void set_error(const char* fmt, ...) {
 
 const char* get_error() { return g_err; }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 }  // namespace lip
 
 extern "C" {
@@ -23,6 +27,8 @@ extern "C" {
 const char* lip_last_error(void) { return lip::get_error(); }
 
 int lip_version(void) { return 100; }
+
+int64_t lip_launch_count(void) { return (int64_t)lip::launches(); }
 
 int lip_device_is_sm100(void) {
   int dev = 0;

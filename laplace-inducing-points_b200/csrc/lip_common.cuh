@@ -12,6 +12,7 @@ namespace lip {
 
 void set_error(const char* fmt, ...);
 const char* get_error();
+long long launches();
 
 #define LIP_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -31,7 +32,13 @@ const char* get_error();
     }                                                                                     \
   } while (0)
 
-#define LIP_LAUNCH_CHECK() LIP_CHECK_CUDA(cudaGetLastError())
+void count_launch();
+// every kernel launch in the library is followed by this macro: it checks the launch and counts it
+#define LIP_LAUNCH_CHECK()                    \
+  do {                                        \
+    ::lip::count_launch();                    \
+    LIP_CHECK_CUDA(cudaGetLastError());       \
+  } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -77,7 +84,7 @@ struct TcOperand {
   int64_t cols = 0;    // extent of the contiguous index
 };
 struct TcGemmProblem {
-  int64_t M = 0, N = 0, K = 0, batch = 1;
+  int64_t M = 0, N = 0, K = 0, K2 = 0, batch = 1;
   TcOperand A1, B1, A2, B2;   // second pair optional
   int a_batched = 1, b_batched = 1, a2_batched = 1, b2_batched = 1;
   float* C = nullptr; int64_t c_sz = 0, c_sm = 0;

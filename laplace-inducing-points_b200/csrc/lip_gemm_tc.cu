@@ -1,19 +1,574 @@
-// lip_gemm_tc.cu — tcgen05 3xTF32 GEMM (placeholder until the tensor-core kernel lands; SIMT path is used).
+// lip_gemm_tc.cu — tcgen05 (5th-gen tensor core) batched GEMM with 3xTF32 fp32 emulation for sm_100a.
+//
+// The hot GEMMs of the GGN-vector product (see lip_model.cu) in fp32-faithful arithmetic on the tensor cores:
+//   D = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi            (x = hi + lo, hi = tf32(x), lo = tf32(x - hi))
+// accumulated in fp32 in TMEM.  Operands are pre-split (hi, lo) fp32 arrays in HBM (weights / activations are
+// split once at bind time, intermediates are split by the producing kernel's epilogue, probe blocks by
+// tf32_split), staged by TMA into 128B-swizzled shared-memory tiles, and consumed by tcgen05.mma.kind::tf32
+// issued by one thread.  Three operand-major combinations cover the JVP, weight-gradient and delta-backprop
+// GEMMs without any transposition pass:
+//   JVP    : A K-major  (activations [M,K]),  B MN-major (tangent weights [K,N])      (+ a second A/B pair)
+//   WGRAD  : A MN-major (activations^T),      B MN-major (deltas [K,N])
+//   DGRAD  : A K-major  (deltas [M,K]),       B K-major  (weights [N,K])
+// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-7 = epilogue (TMEM -> registers -> fused epilogue -> global).  All mbarrier waits are bounded: a
+// deadlock traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+#include <stdlib.h>
+
 #include "lip_common.cuh"
 
 namespace lip {
-bool tc_available() { return false; }
-int gemm_tc(const TcGemmProblem&, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return LIP_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int TBM = 128;       // CTA tile rows (UMMA M)
+constexpr int TBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;      // tf32
+constexpr int TC_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int tf32_split(const float*, int64_t, float*, float*, int64_t, int64_t, int64_t, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return LIP_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a broken pipeline traps (-> cudaErrorLaunchFailure) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ---------------------------------------------------
+// shared-memory matrix descriptor, sm100 version field = 1.
+// layout_type 2 = SWIZZLE_128B (16-byte swizzle atoms; K-major operands),
+//             1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms, 4-row K groups): the ONLY layout tcgen05 accepts
+//                 for MN-major 32-bit (tf32) operands (cutlass sm100_common.inl:92).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);             // [0,14)  start address >> 4
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // [16,30) leading byte offset >> 4
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // [32,46) stride byte offset >> 4
+  d |= (uint64_t)1 << 46;                              // [46,48) version = 1 (Blackwell)
+  d |= (uint64_t)layout_type << 61;                    // [61,64) layout type
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4)                        // c_format = F32
+         | (2u << 7)                      // a_format = TF32
+         | (2u << 10)                     // b_format = TF32
+         | ((a_mn ? 1u : 0u) << 15)       // a_major: 0 = K, 1 = MN
+         | ((b_mn ? 1u : 0u) << 16)       // b_major
+         | ((uint32_t)(N >> 3) << 17)     // n_dim
+         | ((uint32_t)(M >> 4) << 24);    // m_dim
+}
+
+struct TcParams {
+  int M, N, K1, K2;
+  int a1_batched, b1_batched, a2_batched, b2_batched;
+  float* C; float* C_lo;
+  long long c_sz, c_sm;
+  float scale;
+  const float* bias; long long bias_sz;
+  const float* mask; long long mask_sm;
+  const float* add; long long add_sz; float add_scale;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_TILE = TBM * TBK * 4;   // 16 KB
+  static constexpr int B_TILE = BN * TBK * 4;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = (BN <= 128) ? 3 : 2;
+  static constexpr int BYTES = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// One operand tile load (ROWS = TBM or BN rows of the tile's non-contraction index).
+//   K-major : 3D map {K, rows, batch},  ONE box {32 k, ROWS rows, 1}: smem [row][32 k] (128 B rows, 8-row swizzle groups)
+//   MN-major: 3D map {cols, K, batch},  ROWS/32 boxes {32 cols, 32 k, 1}, 4 KB each: smem [chunk][k][32 cols]
+// Out-of-range rows / columns / k are zero-filled by TMA.
+template <bool KMAJOR, int ROWS>
+__device__ __forceinline__ void load_operand(uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0, int row0, int z) {
+  if (KMAJOR) {
+    tma_load_3d(dst, map, bar, k0, row0, z);
+  } else {
+#pragma unroll
+    for (int c = 0; c < ROWS / 32; ++c) tma_load_3d(dst + c * (TBK * 128), map, bar, row0 + 32 * c, k0, z);
+  }
+}
+
+template <int BN, bool A_K, bool B_K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
+               const __grid_constant__ CUtensorMap mB1h, const __grid_constant__ CUtensorMap mB1l,
+               const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
+               const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, TcParams p) {
+  using SL = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + SL::STAGES * SL::STAGE;
+  // barriers: full[STAGES], empty[STAGES], tmem_full; then the TMEM base address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SL::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * SL::STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SL::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN, z = blockIdx.z;
+  const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
+  const int nk = nk1 + nk2;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < SL::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % SL::STAGES;
+        const uint32_t ph = (kb / SL::STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t st = smem_base + s * SL::STAGE;
+        mbar_arrive_expect_tx(full_bar(s), SL::STAGE);
+        const bool second = kb >= nk1;
+        const int k0 = (second ? kb - nk1 : kb) * TBK;
+        const CUtensorMap* ah = second ? &mA2h : &mA1h;
+        const CUtensorMap* al = second ? &mA2l : &mA1l;
+        const CUtensorMap* bh = second ? &mB2h : &mB1h;
+        const CUtensorMap* bl = second ? &mB2l : &mB1l;
+        const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
+        const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
+        load_operand<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
+        load_operand<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
+        load_operand<B_K, BN>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb);
+        load_operand<B_K, BN>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TBM, BN, !A_K, !B_K);
+      // K-major SW128: 8-row groups 1024 B apart (SBO); k sub-step (8 tf32) = +32 B inside the 128 B row.
+      // MN-major SW128_BASE32B: 32-element MN chunks TBK*128 B apart (LBO), 4-row k groups 512 B apart (SBO);
+      //   k sub-step (8 rows) = +1024 B.
+      constexpr uint32_t A_LBO = A_K ? 16 : TBK * 128, B_LBO = B_K ? 16 : TBK * 128;
+      constexpr uint32_t A_SBO = A_K ? 1024 : 512, B_SBO = B_K ? 1024 : 512;
+      constexpr uint32_t A_LT = A_K ? 2 : 1, B_LT = B_K ? 2 : 1;
+      constexpr uint32_t A_KSTEP = A_K ? 32 : 1024, B_KSTEP = B_K ? 32 : 1024;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % SL::STAGES;
+        const uint32_t ph = (kb / SL::STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * SL::STAGE;
+        const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE, b_lo = b_hi + SL::B_TILE;
+#pragma unroll
+        for (int j = 0; j < TBK / UMMA_K; ++j) {
+          const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+          const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+          const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+          const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+          // small terms first, the dominant hi*hi term last
+          umma_tf32(tmem_base, dal, dbh, idesc, (kb | j) != 0);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1);
+        }
+        umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);             // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: TMEM -> registers -> fused epilogue -> global =================
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    const long long crow = (long long)z * p.c_sz + (long long)m * p.c_sm;
+    const float* bias = p.bias ? p.bias + (long long)z * p.bias_sz : nullptr;
+    const float* mask = p.mask ? p.mask + (long long)m * p.mask_sm : nullptr;
+    const float* add = p.add ? p.add + (long long)z * p.add_sz + (long long)m * p.c_sm : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= p.N) continue;
+      const int nvalid = (p.N - nb) < 32 ? (p.N - nb) : 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nvalid) {
+          float x = p.scale * v[i];
+          if (bias) x += __ldg(bias + nb + i);
+          if (mask) x *= __ldg(mask + nb + i);
+          if (add) x += p.add_scale * __ldg(add + nb + i);
+          v[i] = x;
+        }
+      }
+      float* cp = p.C + crow + nb;
+      if (p.C_lo) {
+        float* lp = p.C_lo + crow + nb;
+        if (nvalid == 32 && (((uintptr_t)cp | (uintptr_t)lp) & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 h, l;
+            h.x = tf32_rna(v[i]); h.y = tf32_rna(v[i + 1]); h.z = tf32_rna(v[i + 2]); h.w = tf32_rna(v[i + 3]);
+            l.x = tf32_rna(v[i] - h.x); l.y = tf32_rna(v[i + 1] - h.y); l.z = tf32_rna(v[i + 2] - h.z);
+            l.w = tf32_rna(v[i + 3] - h.w);
+            *reinterpret_cast<float4*>(cp + i) = h;
+            *reinterpret_cast<float4*>(lp + i) = l;
+          }
+        } else {
+          for (int i = 0; i < nvalid; ++i) {
+            float h = tf32_rna(v[i]);
+            cp[i] = h;
+            lp[i] = tf32_rna(v[i] - h);
+          }
+        }
+      } else if (nvalid == 32 && ((uintptr_t)cp & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else if (nvalid == 32 && ((uintptr_t)cp & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) *reinterpret_cast<float2*>(cp + i) = make_float2(v[i], v[i + 1]);
+      } else {
+        for (int i = 0; i < nvalid; ++i) cp[i] = v[i];
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+  }
+}
+
+// ---- TF32 hi/lo split --------------------------------------------------------------------------------------
+__global__ void tf32_split_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ hi,
+                                  float* __restrict__ lo, long long ld_dst, long long rows, long long cols) {
+  const long long r = blockIdx.y;
+  const float* s = src + r * ld_src;
+  float* h = hi + r * ld_dst;
+  float* l = lo + r * ld_dst;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ld_dst; c += (long long)gridDim.x * blockDim.x) {
+    float x = c < cols ? s[c] : 0.f;
+    float xh = tf32_rna(x);
+    h[c] = xh;
+    l[c] = tf32_rna(x - xh);
+  }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// kmajor: element (row r, k) at ptr + r*ld + k;  box {32 k, box_rows rows, 1}
+// mn-major: element (k, col c) at ptr + k*ld + c; box {32 cols, 32 k, 1} (one box per 32-column chunk)
+int make_map(CUtensorMap* map, const float* ptr, bool kmajor, int64_t rows_or_cols, int64_t K, int64_t ld, int64_t sz,
+             int64_t batch, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LIP_ERR_UNSUPPORTED; }
+  LIP_REQUIRE(((uintptr_t)ptr & 15) == 0 && ld % 4 == 0 && sz % 4 == 0, "gemm_tc: operand not 16-byte aligned (ld=%lld sz=%lld)",
+              (long long)ld, (long long)sz);
+  CUresult r;
+  const cuuint64_t bstride = (cuuint64_t)(batch > 1 ? sz : (kmajor ? rows_or_cols * ld : K * ld)) * 4;
+  if (kmajor) {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows_or_cols, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, bstride ? bstride : 16};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[3] = {(cuuint64_t)rows_or_cols, (cuuint64_t)K, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, bstride ? bstride : 16};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): kmajor=%d rows=%lld K=%lld ld=%lld sz=%lld batch=%lld", (int)r, (int)kmajor,
+              (long long)rows_or_cols, (long long)K, (long long)ld, (long long)sz, (long long)batch);
+    return LIP_ERR_CUDA;
+  }
+  return LIP_OK;
+}
+
+template <int BN, bool A_K, bool B_K>
+int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
+  CUtensorMap maps[8];
+  const TcOperand* ops[4] = {&g.A1, &g.B1, &g.A2, &g.B2};
+  const int batched[4] = {g.a_batched, g.b_batched, g.a2_batched, g.b2_batched};
+  const bool dual = g.A2.hi != nullptr;
+  for (int i = 0; i < 4; ++i) {
+    const TcOperand& o = *ops[(i >= 2 && !dual) ? i - 2 : i];
+    const int bt = batched[(i >= 2 && !dual) ? i - 2 : i];
+    const bool is_a = (i % 2 == 0);
+    const bool km = is_a ? A_K : B_K;
+    const int64_t K = (i >= 2 && dual) ? g.K2 : g.K;
+    const int64_t rows = is_a ? g.M : g.N;
+    int rc = make_map(&maps[2 * i], o.hi, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, is_a ? TBM : BN);
+    if (rc) return rc;
+    rc = make_map(&maps[2 * i + 1], o.lo, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, is_a ? TBM : BN);
+    if (rc) return rc;
+  }
+  TcParams p;
+  p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0;
+  p.a1_batched = g.a_batched; p.b1_batched = g.b_batched; p.a2_batched = g.a2_batched; p.b2_batched = g.b2_batched;
+  p.C = g.C; p.C_lo = g.C_lo; p.c_sz = g.c_sz; p.c_sm = g.c_sm;
+  p.scale = g.epi.scale;
+  p.bias = g.epi.bias; p.bias_sz = g.epi.bias_sz;
+  p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
+  p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
+  using SL = SmemLayout<BN>;
+  auto kern = gemm_tc_kernel<BN, A_K, B_K>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES));
+    attr_set = true;
+  }
+  const int64_t zmax = 65535;
+  LIP_REQUIRE(g.batch <= zmax, "gemm_tc: batch %lld exceeds %lld", (long long)g.batch, (long long)zmax);
+  dim3 grid((unsigned)ceil_div(g.M, TBM), (unsigned)ceil_div(g.N, BN), (unsigned)g.batch);
+  kern<<<grid, TC_THREADS, SL::BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+}  // namespace
+
+bool tc_available() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cached = (major == 10 && minor == 0 && get_encode() != nullptr) ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return LIP_OK;
+  LIP_REQUIRE(g.A1.hi && g.A1.lo && g.B1.hi && g.B1.lo && g.C, "gemm_tc: null operand");
+  LIP_REQUIRE(g.epi.act < 0 && g.epi.dphi_out == nullptr, "gemm_tc: activation epilogue is SIMT-only");
+  const bool a_k = g.A1.major_k != 0, b_k = g.B1.major_k != 0;
+  if (g.A2.hi) LIP_REQUIRE((g.A2.major_k != 0) == a_k && (g.B2.major_k != 0) == b_k, "gemm_tc: second pair must share majors");
+  if (a_k && !b_k) return launch_tc<128, true, false>(g, st);
+  if (!a_k && !b_k) return launch_tc<128, false, false>(g, st);
+  if (a_k && b_k) return launch_tc<128, true, true>(g, st);
+  set_error("gemm_tc: unsupported operand majors (A MN-major with B K-major)");
+  return LIP_ERR_INVALID;
+}
+
+int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows, int64_t cols,
+               cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return LIP_OK;
+  LIP_REQUIRE(rows <= 65535 * 1024LL, "tf32_split: too many rows");
+  int64_t gx = ceil_div(ld_dst, 256);
+  if (gx > 1024) gx = 1024;
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    int64_t rc = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid((unsigned)gx, (unsigned)rc);
+    tf32_split_kernel<<<grid, 256, 0, st>>>(src + r0 * ld_src, ld_src, hi + r0 * ld_dst, lo + r0 * ld_dst, ld_dst, rc, cols);
+    LIP_LAUNCH_CHECK();
+  }
+  return LIP_OK;
+}
+
 }  // namespace lip
 
-extern "C" int lip_selftest_tc_gemm(int32_t, int64_t, int64_t, int64_t, int64_t, float*, lip_stream_t) {
-  lip::set_error("tcgen05 GEMM not built");
-  return LIP_ERR_UNSUPPORTED;
+// ---- self test: tensor-core GEMM vs the exact SIMT GEMM on random data ---------------------------------------
+namespace {
+__global__ void fill_random_kernel(float* x, long long n, unsigned seed, float scale) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned s = (unsigned)(i * 2654435761u) ^ seed;
+  s ^= s >> 16; s *= 0x7feb352du; s ^= s >> 15; s *= 0x846ca68bu; s ^= s >> 16;
+  x[i] = scale * ((float)(s & 0xFFFFFF) / 8388608.f - 1.f);
+}
+__global__ void max_rel_err_kernel(const float* a, const float* b, long long n, float* num, float* den) {
+  __shared__ float sn[256], sd[256];
+  float ln = 0.f, ld = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = a[i] - b[i];
+    ln += d * d;
+    ld += b[i] * b[i];
+  }
+  sn[threadIdx.x] = ln; sd[threadIdx.x] = ld;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sn[threadIdx.x] += sn[threadIdx.x + o]; sd[threadIdx.x] += sd[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { atomicAdd(num, sn[0]); atomicAdd(den, sd[0]); }
+}
+}  // namespace
+
+extern "C" int lip_selftest_tc_gemm(int32_t variant, int64_t M, int64_t N, int64_t K, int64_t batch, float* max_rel_err,
+                                    lip_stream_t stream) {
+  using namespace lip;
+  LIP_REQUIRE(variant >= 0 && variant <= 2 && M > 0 && N > 0 && K > 0 && batch > 0 && max_rel_err, "selftest: bad argument");
+  if (!tc_available()) { set_error("selftest: tcgen05 path unavailable on this device"); return LIP_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  auto pad = [](int64_t x) { return (x + 31) / 32 * 32; };
+  // logical operands: A [M x K], B [K x N] per batch (A shared for variant 0/1, B shared for variant 2)
+  const bool a_k = (variant != 1), b_k = (variant == 2);
+  const bool a_batched = (variant == 2), b_batched = (variant != 2);
+  const int64_t a_rows = a_k ? M : K, a_cols = a_k ? K : M;   // memory layout rows x cols (cols contiguous)
+  const int64_t b_rows = b_k ? N : K, b_cols = b_k ? K : N;
+  const int64_t lda = pad(a_cols), ldb = pad(b_cols);
+  const int64_t a_sz = a_rows * lda, b_sz = b_rows * ldb;
+  const int64_t na = (a_batched ? batch : 1) * a_sz + 64, nb = (b_batched ? batch : 1) * b_sz + 64;
+  float *A, *Ah, *Al, *Bm, *Bh, *Bl, *C0, *C1, *mask, *stats;
+  LIP_CHECK_CUDA(cudaMalloc(&A, 4 * na)); LIP_CHECK_CUDA(cudaMalloc(&Ah, 4 * na)); LIP_CHECK_CUDA(cudaMalloc(&Al, 4 * na));
+  LIP_CHECK_CUDA(cudaMalloc(&Bm, 4 * nb)); LIP_CHECK_CUDA(cudaMalloc(&Bh, 4 * nb)); LIP_CHECK_CUDA(cudaMalloc(&Bl, 4 * nb));
+  const int64_t nc = batch * M * N;
+  LIP_CHECK_CUDA(cudaMalloc(&C0, 4 * nc)); LIP_CHECK_CUDA(cudaMalloc(&C1, 4 * nc));
+  LIP_CHECK_CUDA(cudaMalloc(&mask, 4 * M * N)); LIP_CHECK_CUDA(cudaMalloc(&stats, 8));
+  fill_random_kernel<<<(unsigned)ceil_div(na, 256), 256, 0, st>>>(A, na, 11u, 1.f);
+  fill_random_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, st>>>(Bm, nb, 23u, 1.f);
+  fill_random_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>(mask, M * N, 37u, 1.f);
+  int rc = tf32_split(A, lda, Ah, Al, lda, (a_batched ? batch : 1) * a_rows, lda, st);
+  if (!rc) rc = tf32_split(Bm, ldb, Bh, Bl, ldb, (b_batched ? batch : 1) * b_rows, ldb, st);
+  GemmProblem sp;
+  sp.M = M; sp.N = N; sp.K = K; sp.batch = batch;
+  sp.A1 = {A, a_batched ? a_sz : 0, a_k ? lda : 1, a_k ? 1 : lda};
+  sp.B1 = {Bm, b_batched ? b_sz : 0, b_k ? 1 : ldb, b_k ? ldb : 1};
+  sp.C = C0; sp.c_sz = M * N; sp.c_sm = N;
+  sp.epi.scale = 0.5f; sp.epi.mask = mask; sp.epi.mask_sm = N;
+  if (!rc) rc = gemm_simt(sp, st);
+  TcGemmProblem tp;
+  tp.M = M; tp.N = N; tp.K = K; tp.batch = batch;
+  tp.A1.hi = Ah; tp.A1.lo = Al; tp.A1.sz = a_sz; tp.A1.ld = lda; tp.A1.major_k = a_k;
+  tp.B1.hi = Bh; tp.B1.lo = Bl; tp.B1.sz = b_sz; tp.B1.ld = ldb; tp.B1.major_k = b_k;
+  tp.a_batched = a_batched; tp.b_batched = b_batched;
+  tp.C = C1; tp.c_sz = M * N; tp.c_sm = N;
+  tp.epi = sp.epi;
+  if (!rc) rc = gemm_tc(tp, st);
+  float h[2] = {0.f, 0.f};
+  if (!rc && getenv("LIP_TC_DEBUG")) {
+    // structured probe: A = 1 for k == kd (else 0), B[k][n] = n + 1000 k  ->  C[m][n] = 0.5 * mask * (n + 1000 kd)
+    cudaStreamSynchronize(st);
+    std::vector<float> c0(64), c1(64);
+    for (int row : {0, 1, 33}) {
+      cudaMemcpy(c0.data(), C0 + (size_t)row * N, 4 * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(c1.data(), C1 + (size_t)row * N, 4 * 8, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "  row %d simt:", row);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.4f", c0[i]);
+      fprintf(stderr, "\n  row %d tc  :", row);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %9.4f", c1[i]);
+      fprintf(stderr, "\n");
+    }
+  }
+  if (!rc) {
+    cudaMemsetAsync(stats, 0, 8, st);
+    max_rel_err_kernel<<<256, 256, 0, st>>>(C1, C0, nc, stats, stats + 1);
+    cudaError_t e = cudaMemcpyAsync(h, stats, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("selftest: %s", cudaGetErrorString(e)); rc = LIP_ERR_CUDA; }
+  }
+  cudaFree(A); cudaFree(Ah); cudaFree(Al); cudaFree(Bm); cudaFree(Bh); cudaFree(Bl); cudaFree(C0); cudaFree(C1);
+  cudaFree(mask); cudaFree(stats);
+  if (rc) return rc;
+  *max_rel_err = h[1] > 0.f ? sqrtf(h[0] / h[1]) : (h[0] > 0.f ? 1e30f : 0.f);
+  return LIP_OK;
 }

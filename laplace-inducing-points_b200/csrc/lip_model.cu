@@ -463,7 +463,8 @@ int lip_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale
     if (factor == LIP_FACTOR_SQRT) s *= expf(-0.5f * m->logvar);
     int64_t n = B * m->M * m->K;
     scale_copy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(U, w.buf[0], n, 1.f);
-    rc = (cudaGetLastError() == cudaSuccess) ? LIP_OK : LIP_ERR_CUDA;
+    LIP_LAUNCH_CHECK();
+    rc = LIP_OK;
   }
   if (rc) return rc;
   return vjp_sweep(m, w.buf[0], w.buf[1], B, out, s, add, add_scale, st);

@@ -287,7 +287,6 @@ class OracleState:
 
     def f_theta(self, theta: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         """Model output [n, K] as a differentiable function of the flat float64 parameter vector."""
-        _, unravel = self.flat()
         tree = _unravel_torch(theta, self.params)
         bs = _tree_to_torch(self.batch_stats)
         return self.model.forward(tree, x, bs)
