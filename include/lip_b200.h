@@ -76,6 +76,8 @@ int64_t lip_model_num_outputs(const lip_model* m);
 int64_t lip_model_num_points(const lip_model* m);
 /* 0: SIMT fp32 only; 1: tcgen05 3xTF32 for qualifying layers (default when the device is sm_100) */
 int lip_model_set_tensor_path(lip_model* m, int32_t enable);
+/* number of dense layers whose GEMMs run on the tcgen05 path for the current binding (0 = SIMT only) */
+int lip_model_tensor_layers(const lip_model* m);
 
 /* Bind weights theta[D] (flat, reference order) and points Z[M, in_features]; runs and caches the forward
  * pass (activations, activation derivatives, softmax p and sqrt p).  Replaces the per-call forward passes of

@@ -35,6 +35,7 @@ SIGNATURES = {
     "lip_model_num_outputs": (_I64, [_P]),
     "lip_model_num_points": (_I64, [_P]),
     "lip_model_set_tensor_path": (C.c_int, [_P, _I32]),
+    "lip_model_tensor_layers": (C.c_int, [_P]),
     "lip_model_bind": (C.c_int, [_P, _P, _P, _I64, _F, _P]),
     "lip_model_outputs": (C.c_int, [_P, _P, _P]),
     "lip_workspace_bytes": (_SZ, [_P, _I64]),

@@ -114,6 +114,11 @@ class BoundModel:
         self._ws = Scratch()
         self.launches = 0
 
+    def path_name(self) -> str:
+        n = cabi.lib().lip_model_tensor_layers(self._h)
+        total = len(self.spec.layers)
+        return f"tcgen05-3xtf32 ({n}/{total} layers) + simt-fp32" if n else "simt-fp32"
+
     # ---- helpers ----
     def _workspace(self, B: int):
         need = cabi.lib().lip_workspace_bytes(self._h, B)

@@ -61,6 +61,7 @@ struct GemmEpilogue {
   const float* add = nullptr;   int64_t add_sz = 0; float add_scale = 0.f;  // same m/n strides as C
   int act = -1;                 // -1 none, else lip_op activation
   float* dphi_out = nullptr;    // same layout as C (only with act >= 0)
+  float* C_lo = nullptr;        // SIMT path: if set, C receives tf32(v) and C_lo the tf32 remainder (feeds a tcgen05 GEMM)
 };
 
 struct GemmProblem {
@@ -96,6 +97,14 @@ int gemm_tc(const TcGemmProblem& p, cudaStream_t stream);
 // x -> (hi, lo) TF32 split into a padded destination: dst[r*ld_dst + c] for r<rows, c<cols
 int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows,
                int64_t cols, cudaStream_t stream);
+// batched form: element (z, r, c) at z*sz + r*ld + c
+int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, float* lo, int64_t sz_dst,
+                int64_t ld_dst, int64_t batch, int64_t rows, int64_t cols, cudaStream_t stream);
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 __device__ __forceinline__ float act_apply(int act, float h, float* dphi) {
   float a, d;

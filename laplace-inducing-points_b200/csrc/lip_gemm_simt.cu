@@ -28,6 +28,7 @@ struct DevGemm {
   const float* add;  long long add_sz; float add_scale;
   int act;
   float* dphi_out;
+  float* C_lo;
 };
 
 template <bool KC>  // KC: the contraction index is the contiguous one for this operand
@@ -137,7 +138,13 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
       }
       if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
       if (g.add) v += g.add_scale * __ldg(g.add + (long long)z * g.add_sz + (long long)m * g.c_sm + n);
-      g.C[co] = v;
+      if (g.C_lo) {
+        const float h = tf32_round(v);
+        g.C[co] = h;
+        g.C_lo[co] = tf32_round(v - h);
+      } else {
+        g.C[co] = v;
+      }
     }
   }
 }
@@ -165,7 +172,7 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
   g.bias = p.epi.bias; g.bias_sz = p.epi.bias_sz;
   g.mask = p.epi.mask; g.mask_sm = p.epi.mask_sm;
   g.add = p.epi.add; g.add_sz = p.epi.add_sz; g.add_scale = p.epi.add_scale;
-  g.act = p.epi.act; g.dphi_out = p.epi.dphi_out;
+  g.act = p.epi.act; g.dphi_out = p.epi.dphi_out; g.C_lo = p.epi.C_lo;
 
   dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM), 1);
   // gridDim.z is limited to 65535: chunk the batch.
@@ -179,6 +186,7 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     if (gz.bias) gz.bias += z0 * g.bias_sz;
     if (gz.add) gz.add += z0 * g.add_sz;
     if (gz.dphi_out) gz.dphi_out += z0 * g.c_sz;
+    if (gz.C_lo) gz.C_lo += z0 * g.c_sz;
     grid.z = (unsigned)zc;
     if (a_kc && !b_kc) gemm_simt_kernel<true, false><<<grid, NT, 0, stream>>>(gz);
     else if (!a_kc && !b_kc) gemm_simt_kernel<false, false><<<grid, NT, 0, stream>>>(gz);

@@ -29,6 +29,11 @@ constexpr int TBM = 128;       // CTA tile rows (UMMA M)
 constexpr int TBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;      // tf32
 constexpr int TC_THREADS = 256;
+// fp32 accumulation in TMEM rounds toward zero, a bias that grows with the number of accumulation steps.
+// Two measures keep 3xTF32 inside the 1e-5 budget: the two cross terms (2^-11 smaller) accumulate in their own
+// TMEM tile so they never truncate the main sum, and the hi*hi terms are dealt round-robin to NACC main tiles
+// that are added in round-to-nearest fp32 by the epilogue.
+constexpr int NACC = 3;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,6 +177,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
                const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
                const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, TcParams p) {
   using SL = SmemLayout<BN>;
+  constexpr int TMEM_COLS = (NACC + 1) * BN <= 32 ? 32 : (NACC + 1) * BN <= 64 ? 64 : (NACC + 1) * BN <= 128 ? 128
+                            : (NACC + 1) * BN <= 256 ? 256 : 512;
+  static_assert((NACC + 1) * BN <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + SL::STAGES * SL::STAGE;
@@ -193,7 +201,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -249,10 +258,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
           const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
           const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
           const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-          // small terms first, the dominant hi*hi term last
-          umma_tf32(tmem_base, dal, dbh, idesc, (kb | j) != 0);
+          const int g = kb * (TBK / UMMA_K) + j;       // global k sub-step
+          // columns [0,BN): cross terms; columns [(1+i)*BN, (2+i)*BN): main accumulator i
+          umma_tf32(tmem_base, dal, dbh, idesc, g != 0);
           umma_tf32(tmem_base, dah, dbl, idesc, 1);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1);
+          umma_tf32(tmem_base + (uint32_t)((1 + g % NACC) * BN), dah, dbh, idesc, g >= NACC);
         }
         umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
       }
@@ -272,7 +282,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      tmem_ld32(tl, v);                                   // cross terms
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        float w[32];
+        tmem_ld32(tl + (uint32_t)((1 + a) * BN), w);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += w[i];
+      }
       const int nb = n0 + c * 32;
       if (!row_ok || nb >= p.N) continue;
       const int nvalid = (p.N - nb) < 32 ? (p.N - nb) : 32;
@@ -321,17 +339,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
   }
 }
 
 // ---- TF32 hi/lo split --------------------------------------------------------------------------------------
-__global__ void tf32_split_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ hi,
-                                  float* __restrict__ lo, long long ld_dst, long long rows, long long cols) {
-  const long long r = blockIdx.y;
-  const float* s = src + r * ld_src;
-  float* h = hi + r * ld_dst;
-  float* l = lo + r * ld_dst;
+// src element (z, r, c) at src + z*sz_src + r*ld_src + c  ->  hi/lo (z, r, c) at z*sz_dst + r*ld_dst + c, c < ld_dst
+// (columns in [cols, ld_dst) are zero-filled)
+__global__ void tf32_split_kernel(const float* __restrict__ src, long long sz_src, long long ld_src,
+                                  float* __restrict__ hi, float* __restrict__ lo, long long sz_dst, long long ld_dst,
+                                  long long cols) {
+  const long long r = blockIdx.y, z = blockIdx.z;
+  const float* s = src + z * sz_src + r * ld_src;
+  float* h = hi + z * sz_dst + r * ld_dst;
+  float* l = lo + z * sz_dst + r * ld_dst;
   for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ld_dst; c += (long long)gridDim.x * blockDim.x) {
     float x = c < cols ? s[c] : 0.f;
     float xh = tf32_rna(x);
@@ -459,19 +480,27 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   return LIP_ERR_INVALID;
 }
 
-int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows, int64_t cols,
-               cudaStream_t st) {
-  if (rows <= 0 || cols <= 0) return LIP_OK;
-  LIP_REQUIRE(rows <= 65535 * 1024LL, "tf32_split: too many rows");
+int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, float* lo, int64_t sz_dst, int64_t ld_dst,
+                int64_t batch, int64_t rows, int64_t cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return LIP_OK;
   int64_t gx = ceil_div(ld_dst, 256);
-  if (gx > 1024) gx = 1024;
-  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
-    int64_t rc = rows - r0 < 65535 ? rows - r0 : 65535;
-    dim3 grid((unsigned)gx, (unsigned)rc);
-    tf32_split_kernel<<<grid, 256, 0, st>>>(src + r0 * ld_src, ld_src, hi + r0 * ld_dst, lo + r0 * ld_dst, ld_dst, rc, cols);
-    LIP_LAUNCH_CHECK();
+  if (gx > 64) gx = 64;
+  for (int64_t z0 = 0; z0 < batch; z0 += 65535) {
+    const int64_t zc = batch - z0 < 65535 ? batch - z0 : 65535;
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+      const int64_t rc = rows - r0 < 65535 ? rows - r0 : 65535;
+      dim3 grid((unsigned)gx, (unsigned)rc, (unsigned)zc);
+      tf32_split_kernel<<<grid, 256, 0, st>>>(src + z0 * sz_src + r0 * ld_src, sz_src, ld_src, hi + z0 * sz_dst + r0 * ld_dst,
+                                              lo + z0 * sz_dst + r0 * ld_dst, sz_dst, ld_dst, cols);
+      LIP_LAUNCH_CHECK();
+    }
   }
   return LIP_OK;
+}
+
+int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows, int64_t cols,
+               cudaStream_t st) {
+  return tf32_split3(src, 0, ld_src, hi, lo, 0, ld_dst, 1, rows, cols, st);
 }
 
 }  // namespace lip

@@ -36,10 +36,14 @@ struct lip_model {
   float* logits = nullptr;   // [M, K]
   float* P = nullptr;        // softmax(logits)
   float* S = nullptr;        // sqrt(P)
-  int use_tc = -1;           // -1 auto
-  // tcgen05 operands: TF32 hi/lo splits in padded buffers (ld multiple of 32)
+  int use_tc = -1;           // -1 auto (tcgen05 when the device is sm_100), 0 SIMT only, 1 tcgen05
+  bool tc_on = false;        // decided at bind time
+  // tcgen05 operands: TF32 hi/lo splits of the cached activations and of the weights (ld padded to 4)
   std::vector<float*> A_hi, A_lo, W_hi, W_lo;
   std::vector<int64_t> A_ld, W_ld;
+  std::vector<char> tc_layer;   // layer l runs its three GEMMs on the tensor cores
+  int64_t max_split = 0;        // max over tc layers of in * ldw (floats per probe of the split tangent block)
+  int ldmax = 0;                // widest padded intermediate row
 
   void free_cache() {
     for (auto p : A) if (p) cudaFree(p);
@@ -49,6 +53,7 @@ struct lip_model {
     for (auto p : W_hi) if (p) cudaFree(p);
     for (auto p : W_lo) if (p) cudaFree(p);
     A.clear(); dphi.clear(); A_hi.clear(); A_lo.clear(); W_hi.clear(); W_lo.clear(); A_ld.clear(); W_ld.clear();
+    tc_layer.clear(); tc_on = false; max_split = 0;
     if (logits) cudaFree(logits);
     if (P) cudaFree(P);
     if (S) cudaFree(S);
@@ -107,21 +112,27 @@ __global__ void scale_copy_kernel(const float* __restrict__ in, float* __restric
   if (i < n) out[i] = scale * in[i];
 }
 
-// gb[b][j] = scale * sum_m Delta[b][m][j] + add_scale * add[b][j]
-__global__ void bias_grad_kernel(const float* __restrict__ Delta, int64_t M, int n, float* __restrict__ out,
-                                 int64_t out_sz, float scale, const float* __restrict__ add, int64_t add_sz,
-                                 float add_scale) {
+// gb[b][j] = scale * sum_m (Delta[b][m][j] (+ Delta_lo[b][m][j])) + add_scale * add[b][j];  Delta rows have stride ld
+__global__ void bias_grad_kernel(const float* __restrict__ Delta, const float* __restrict__ Delta_lo, int64_t M, int n,
+                                 int64_t ld, float* __restrict__ out, int64_t out_sz, float scale,
+                                 const float* __restrict__ add, int64_t add_sz, float add_scale) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const float* d = Delta + (int64_t)b * M * n + j;
+  const float* d = Delta + (int64_t)b * M * ld + j;
   float acc = 0.f;
   int64_t m = 0;
   for (; m + 4 <= M; m += 4) {
-    float a0 = d[(m + 0) * n], a1 = d[(m + 1) * n], a2 = d[(m + 2) * n], a3 = d[(m + 3) * n];
+    float a0 = d[(m + 0) * ld], a1 = d[(m + 1) * ld], a2 = d[(m + 2) * ld], a3 = d[(m + 3) * ld];
     acc += (a0 + a1) + (a2 + a3);
   }
-  for (; m < M; ++m) acc += d[m * n];
+  for (; m < M; ++m) acc += d[m * ld];
+  if (Delta_lo) {
+    const float* e = Delta_lo + (int64_t)b * M * ld + j;
+    float acc2 = 0.f;
+    for (m = 0; m < M; ++m) acc2 += e[m * ld];
+    acc += acc2;
+  }
   float v = scale * acc;
   if (add) v += add_scale * add[(int64_t)b * add_sz + j];
   out[(int64_t)b * out_sz + j] = v;
@@ -161,15 +172,21 @@ int launch_factor(const float* in, float* out, const lip_model* m, int64_t B, in
   return LIP_OK;
 }
 
+static inline int pad4(int x) { return (x + 3) / 4 * 4; }
+
 struct Workspace {
-  float* buf[2];
-  size_t per_buf;  // floats
+  float* hi[2];     // intermediate ping-pong (plain fp32, or the tf32-hi part when the consumer is a tcgen05 GEMM)
+  float* lo[2];     // tf32-lo parts (tensor path only)
+  float* vs_hi;     // split tangent-weight block of the current layer, [B][in][ldw]
+  float* vs_lo;
+  size_t per_buf;   // floats
 };
 
 size_t ws_bytes(const lip_model* m, int64_t B) {
-  size_t per = (size_t)B * (size_t)m->M * (size_t)m->maxw;
-  per = align_up(per, 64);
-  return 2 * per * sizeof(float) + 256;
+  size_t per = align_up((size_t)B * (size_t)m->M * (size_t)(m->tc_on ? m->ldmax : m->maxw), 64);
+  size_t total = 2 * per;
+  if (m->tc_on) total += 2 * per + 2 * align_up((size_t)B * (size_t)m->max_split, 64);
+  return total * sizeof(float) + 256;
 }
 
 int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
@@ -178,59 +195,117 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
     set_error("workspace too small: need %zu bytes, got %zu", need, bytes);
     return LIP_ERR_WORKSPACE;
   }
-  uintptr_t base = align_up((uintptr_t)ws, 256);
-  size_t per = align_up((size_t)B * (size_t)m->M * (size_t)m->maxw, 64);
-  w->buf[0] = (float*)base;
-  w->buf[1] = w->buf[0] + per;
+  float* base = (float*)align_up((uintptr_t)ws, 256);
+  size_t per = align_up((size_t)B * (size_t)m->M * (size_t)(m->tc_on ? m->ldmax : m->maxw), 64);
   w->per_buf = per;
+  w->hi[0] = base; w->hi[1] = base + per;
+  w->lo[0] = w->lo[1] = w->vs_hi = w->vs_lo = nullptr;
+  if (m->tc_on) {
+    w->lo[0] = base + 2 * per; w->lo[1] = base + 3 * per;
+    size_t vs = align_up((size_t)B * (size_t)m->max_split, 64);
+    w->vs_hi = base + 4 * per; w->vs_lo = w->vs_hi + vs;
+  }
   return LIP_OK;
 }
 
+// leading dimension of the intermediate produced by layer l (its output width), padded on the tensor path
+static inline int ld_of(const lip_model* m, int width) { return m->tc_on ? pad4(width) : width; }
+
 // ---- JVP sweep: V[B,D] -> dlogits written to `dst` ([B,M,K], contiguous).  Intermediates ping-pong in ws.
-int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float* dst, float out_scale,
-              cudaStream_t st) {
+int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float* dst, cudaStream_t st) {
   const int nL = (int)m->L.size();
-  const float* prev = nullptr;
+  const float* prev_hi = nullptr;
+  const float* prev_lo = nullptr;
+  int prev_ld = 0;
   for (int l = 0; l < nL; ++l) {
     const DenseLayer& Ld = m->L[l];
     const bool last = (l == nL - 1);
-    float* out = last ? dst : w.buf[l & 1];
-    GemmProblem p;
-    p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = B;
-    p.A1 = {m->A[l], 0, Ld.in, 1};
-    p.B1 = {V + Ld.woff, m->D, Ld.out, 1};
-    if (l > 0) {
-      p.A2 = {prev, m->M * (int64_t)Ld.in, Ld.in, 1};
-      p.B2 = {m->theta + Ld.woff, 0, Ld.out, 1};
-      p.K2 = Ld.in;
+    const bool tc = m->tc_on && m->tc_layer[l];
+    const bool next_tc = m->tc_on && !last && m->tc_layer[l + 1];   // consumer of this layer's output
+    float* out_hi = last ? dst : w.hi[l & 1];
+    float* out_lo = (!last && next_tc) ? w.lo[l & 1] : nullptr;
+    const int out_ld = last ? Ld.out : ld_of(m, Ld.out);
+    if (tc) {
+      const int64_t ldw = m->W_ld[l];
+      int rc = tf32_split3(V + Ld.woff, m->D, Ld.out, w.vs_hi, w.vs_lo, (int64_t)Ld.in * ldw, ldw, B, Ld.in, Ld.out, st);
+      if (rc) return rc;
+      TcGemmProblem p;
+      p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = B;
+      p.A1.hi = m->A_hi[l]; p.A1.lo = m->A_lo[l]; p.A1.ld = m->A_ld[l]; p.A1.sz = m->M * m->A_ld[l]; p.A1.major_k = 1;
+      p.a_batched = 0;
+      p.B1.hi = w.vs_hi; p.B1.lo = w.vs_lo; p.B1.ld = ldw; p.B1.sz = (int64_t)Ld.in * ldw; p.B1.major_k = 0;
+      p.b_batched = 1;
+      if (l > 0) {
+        p.A2.hi = prev_hi; p.A2.lo = prev_lo; p.A2.ld = prev_ld; p.A2.sz = m->M * (int64_t)prev_ld; p.A2.major_k = 1;
+        p.a2_batched = 1;
+        p.B2.hi = m->W_hi[l]; p.B2.lo = m->W_lo[l]; p.B2.ld = ldw; p.B2.sz = (int64_t)Ld.in * ldw; p.B2.major_k = 0;
+        p.b2_batched = 0;
+        p.K2 = Ld.in;
+      }
+      p.C = out_hi; p.C_lo = out_lo; p.c_sz = m->M * (int64_t)out_ld; p.c_sm = out_ld;
+      p.epi.bias = V + Ld.boff; p.epi.bias_sz = m->D;
+      if (!last) { p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out; }
+      rc = gemm_tc(p, st);
+      if (rc) return rc;
+    } else {
+      GemmProblem p;
+      p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = B;
+      p.A1 = {m->A[l], 0, Ld.in, 1};
+      p.B1 = {V + Ld.woff, m->D, Ld.out, 1};
+      if (l > 0) {
+        // a SIMT layer always reads a plain fp32 intermediate (its producer saw next_tc == false)
+        p.A2 = {prev_hi, m->M * (int64_t)prev_ld, prev_ld, 1};
+        p.B2 = {m->theta + Ld.woff, 0, Ld.out, 1};
+        p.K2 = Ld.in;
+      }
+      p.C = out_hi; p.c_sz = m->M * (int64_t)out_ld; p.c_sm = out_ld;
+      p.epi.C_lo = out_lo;
+      p.epi.bias = V + Ld.boff; p.epi.bias_sz = m->D;
+      if (!last) { p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out; }
+      int rc = gemm_simt(p, st);
+      if (rc) return rc;
     }
-    p.C = out; p.c_sz = m->M * (int64_t)Ld.out; p.c_sm = Ld.out;
-    p.epi.bias = V + Ld.boff; p.epi.bias_sz = m->D;
-    if (!last) { p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out; }
-    // NB epilogue order is scale*acc + bias, then mask: out_scale only applies on the last layer (no mask),
-    // where scale*(acc) + bias would mis-scale the bias -> apply out_scale separately when != 1.
-    int rc = gemm_simt(p, st);
-    if (rc) return rc;
-    prev = out;
+    prev_hi = out_hi; prev_lo = out_lo; prev_ld = out_ld;
   }
-  (void)out_scale;
   return LIP_OK;
 }
 
-// ---- VJP sweep: Delta_L in `delta` ([B,M,K]); writes out[B,D] = scale * J^T delta + add_scale * add.
-// `delta` lives in (or is copied to) a workspace buffer; the other buffer is used for ping-pong.
-int vjp_sweep(lip_model* m, float* delta, float* other, int64_t B, float* out, float scale, const float* add,
+// ---- VJP sweep: Delta_L (plain fp32, [B,M,K] contiguous) in w.hi[src]; writes out[B,D] = scale * J^T delta + add_scale * add.
+int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, float scale, const float* add,
               float add_scale, cudaStream_t st) {
   const int nL = (int)m->L.size();
-  float* cur = delta;
-  float* nxt = other;
+  int cur = src;
+  int cur_ld = m->K;
+  bool cur_split = false;
+  if (m->tc_on && m->tc_layer[nL - 1]) {
+    // the top layer runs on the tensor cores: re-lay Delta_L as padded hi/lo
+    const int ldp = pad4(m->K);
+    int rc = tf32_split(w.hi[cur], m->K, w.hi[cur ^ 1], w.lo[cur ^ 1], ldp, B * m->M, m->K, st);
+    if (rc) return rc;
+    cur ^= 1; cur_ld = ldp; cur_split = true;
+  }
   for (int l = nL - 1; l >= 0; --l) {
     const DenseLayer& Ld = m->L[l];
-    {  // weight gradient: [in x out] = A_l^T [in x M] * Delta [M x out]
+    const bool tc = m->tc_on && m->tc_layer[l];
+    const float* d_hi = w.hi[cur];
+    const float* d_lo = cur_split ? w.lo[cur] : nullptr;
+    if (tc) {  // weight gradient [in x out] = A_l^T [in x M] * Delta [M x out]
+      TcGemmProblem p;
+      p.M = Ld.in; p.N = Ld.out; p.K = m->M; p.batch = B;
+      p.A1.hi = m->A_hi[l]; p.A1.lo = m->A_lo[l]; p.A1.ld = m->A_ld[l]; p.A1.sz = m->M * m->A_ld[l]; p.A1.major_k = 0;
+      p.a_batched = 0;
+      p.B1.hi = d_hi; p.B1.lo = d_lo; p.B1.ld = cur_ld; p.B1.sz = m->M * (int64_t)cur_ld; p.B1.major_k = 0;
+      p.b_batched = 1;
+      p.C = out + Ld.woff; p.c_sz = m->D; p.c_sm = Ld.out;
+      p.epi.scale = scale;
+      if (add) { p.epi.add = add + Ld.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+      int rc = gemm_tc(p, st);
+      if (rc) return rc;
+    } else {
       GemmProblem p;
       p.M = Ld.in; p.N = Ld.out; p.K = m->M; p.batch = B;
       p.A1 = {m->A[l], 0, 1, Ld.in};
-      p.B1 = {cur, m->M * (int64_t)Ld.out, Ld.out, 1};
+      p.B1 = {d_hi, m->M * (int64_t)cur_ld, cur_ld, 1};
       p.C = out + Ld.woff; p.c_sz = m->D; p.c_sm = Ld.out;
       p.epi.scale = scale;
       if (add) { p.epi.add = add + Ld.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
@@ -239,20 +314,37 @@ int vjp_sweep(lip_model* m, float* delta, float* other, int64_t B, float* out, f
     }
     {  // bias gradient
       dim3 grid((unsigned)ceil_div(Ld.out, 128), (unsigned)B);
-      bias_grad_kernel<<<grid, 128, 0, st>>>(cur, m->M, Ld.out, out + Ld.boff, m->D, scale,
+      bias_grad_kernel<<<grid, 128, 0, st>>>(d_hi, d_lo, m->M, Ld.out, cur_ld, out + Ld.boff, m->D, scale,
                                              add ? add + Ld.boff : nullptr, m->D, add_scale);
       LIP_LAUNCH_CHECK();
     }
     if (l > 0) {  // Delta_{l-1} = (Delta_l W_l^T) * phi'_{l-1}
-      GemmProblem p;
-      p.M = m->M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
-      p.A1 = {cur, m->M * (int64_t)Ld.out, Ld.out, 1};
-      p.B1 = {m->theta + Ld.woff, 0, 1, Ld.out};
-      p.C = nxt; p.c_sz = m->M * (int64_t)Ld.in; p.c_sm = Ld.in;
-      p.epi.mask = m->dphi[l - 1]; p.epi.mask_sm = Ld.in;
-      int rc = gemm_simt(p, st);
-      if (rc) return rc;
-      float* t = cur; cur = nxt; nxt = t;
+      const bool next_split = m->tc_on && m->tc_layer[l - 1];
+      const int nxt = cur ^ 1;
+      const int nxt_ld = ld_of(m, Ld.in);
+      if (tc) {
+        TcGemmProblem p;
+        p.M = m->M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
+        p.A1.hi = d_hi; p.A1.lo = d_lo; p.A1.ld = cur_ld; p.A1.sz = m->M * (int64_t)cur_ld; p.A1.major_k = 1;
+        p.a_batched = 1;
+        p.B1.hi = m->W_hi[l]; p.B1.lo = m->W_lo[l]; p.B1.ld = m->W_ld[l]; p.B1.sz = (int64_t)Ld.in * m->W_ld[l];
+        p.B1.major_k = 1; p.b_batched = 0;
+        p.C = w.hi[nxt]; p.C_lo = next_split ? w.lo[nxt] : nullptr; p.c_sz = m->M * (int64_t)nxt_ld; p.c_sm = nxt_ld;
+        p.epi.mask = m->dphi[l - 1]; p.epi.mask_sm = Ld.in;
+        int rc = gemm_tc(p, st);
+        if (rc) return rc;
+      } else {
+        GemmProblem p;
+        p.M = m->M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
+        p.A1 = {d_hi, m->M * (int64_t)cur_ld, cur_ld, 1};
+        p.B1 = {m->theta + Ld.woff, 0, 1, Ld.out};
+        p.C = w.hi[nxt]; p.c_sz = m->M * (int64_t)nxt_ld; p.c_sm = nxt_ld;
+        p.epi.C_lo = next_split ? w.lo[nxt] : nullptr;
+        p.epi.mask = m->dphi[l - 1]; p.epi.mask_sm = Ld.in;
+        int rc = gemm_simt(p, st);
+        if (rc) return rc;
+      }
+      cur = nxt; cur_ld = nxt_ld; cur_split = next_split;
     }
   }
   return LIP_OK;
@@ -343,6 +435,13 @@ int64_t lip_model_num_params(const lip_model* m) { return m ? m->D : -1; }
 int64_t lip_model_num_outputs(const lip_model* m) { return m ? m->K : -1; }
 int64_t lip_model_num_points(const lip_model* m) { return (m && m->bound) ? m->M : -1; }
 
+int lip_model_tensor_layers(const lip_model* m) {
+  if (!m || !m->bound || !m->tc_on) return 0;
+  int n = 0;
+  for (char c : m->tc_layer) n += c ? 1 : 0;
+  return n;
+}
+
 int lip_model_set_tensor_path(lip_model* m, int32_t enable) {
   LIP_REQUIRE(m != nullptr, "null model");
   m->use_tc = enable ? 1 : 0;
@@ -389,6 +488,43 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
     softmax_rows_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(m->logits, m->P, m->S, M, m->K);
     LIP_LAUNCH_CHECK();
   }
+  // ---- tensor-core path: decide per layer, split the shared operands once ----
+  m->tc_on = false;
+  m->tc_layer.assign(nL, 0);
+  m->ldmax = 0;
+  for (auto& Ld : m->L) m->ldmax = pad4(Ld.out) > m->ldmax ? pad4(Ld.out) : m->ldmax;
+  if (m->use_tc != 0) {
+    const bool avail = tc_available();
+    if (m->use_tc == 1 && !avail) {
+      set_error("lip_model_bind: tensor path requested but the device is not sm_100 / TMA encode unavailable");
+      return LIP_ERR_UNSUPPORTED;
+    }
+    if (avail) {
+      for (int l = 0; l < nL; ++l)
+        m->tc_layer[l] = (m->L[l].in >= 64 && m->L[l].out >= 64 && M >= 64 && (m->L[l].out % 4 == 0)) ? 1 : 0;
+      for (int l = 0; l < nL; ++l) m->tc_on = m->tc_on || m->tc_layer[l];
+    }
+  }
+  if (m->tc_on) {
+    m->A_hi.assign(nL, nullptr); m->A_lo.assign(nL, nullptr); m->W_hi.assign(nL, nullptr); m->W_lo.assign(nL, nullptr);
+    m->A_ld.assign(nL, 0); m->W_ld.assign(nL, 0);
+    m->max_split = 0;
+    for (int l = 0; l < nL; ++l) {
+      if (!m->tc_layer[l]) continue;
+      const DenseLayer& Ld = m->L[l];
+      const int64_t lda = pad4(Ld.in), ldw = pad4(Ld.out);
+      m->A_ld[l] = lda; m->W_ld[l] = ldw;
+      LIP_CHECK_CUDA(cudaMalloc(&m->A_hi[l], sizeof(float) * (size_t)M * lda + 256));
+      LIP_CHECK_CUDA(cudaMalloc(&m->A_lo[l], sizeof(float) * (size_t)M * lda + 256));
+      LIP_CHECK_CUDA(cudaMalloc(&m->W_hi[l], sizeof(float) * (size_t)Ld.in * ldw + 256));
+      LIP_CHECK_CUDA(cudaMalloc(&m->W_lo[l], sizeof(float) * (size_t)Ld.in * ldw + 256));
+      int rc = tf32_split(m->A[l], Ld.in, m->A_hi[l], m->A_lo[l], lda, M, Ld.in, st);
+      if (rc) return rc;
+      rc = tf32_split(theta + Ld.woff, Ld.out, m->W_hi[l], m->W_lo[l], ldw, Ld.in, Ld.out, st);
+      if (rc) return rc;
+      if ((int64_t)Ld.in * ldw > m->max_split) m->max_split = (int64_t)Ld.in * ldw;
+    }
+  }
   m->bound = true;
   return LIP_OK;
 }
@@ -417,14 +553,15 @@ int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal,
   if (rc) return rc;
   const int nL = (int)m->L.size();
   // dlogits land in the buffer the last hidden layer did NOT use, so the VJP can ping-pong from it
-  float* dl = w.buf[(nL - 1) & 1];
-  rc = jvp_sweep(m, V, B, w, dl, 1.f, st);
+  const int src = (nL - 1) & 1;
+  float* dl = w.hi[src];
+  rc = jvp_sweep(m, V, B, w, dl, st);
   if (rc) return rc;
   if (m->model_type == LIP_CLASSIFIER) {
     rc = launch_factor(dl, dl, m, B, 0, 1.f, st);
     if (rc) return rc;
   }
-  return vjp_sweep(m, dl, w.buf[nL & 1], B, out, recal, alpha != 0.f ? V : nullptr, alpha, st);
+  return vjp_sweep(m, src, B, w, out, recal, alpha != 0.f ? V : nullptr, alpha, st);
 }
 
 int lip_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scale, int32_t factor,
@@ -435,7 +572,7 @@ int lip_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scal
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
-  rc = jvp_sweep(m, V, B, w, out, 1.f, st);
+  rc = jvp_sweep(m, V, B, w, out, st);
   if (rc) return rc;
   float s = scale;
   if (factor == LIP_FACTOR_SQRT && m->model_type == LIP_REGRESSOR) s *= expf(-0.5f * m->logvar);
@@ -458,16 +595,16 @@ int lip_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale
   if (rc) return rc;
   float s = scale;
   if (factor == LIP_FACTOR_SQRT && m->model_type == LIP_CLASSIFIER) {
-    rc = launch_factor(U, w.buf[0], m, B, 2, 1.f, st);
+    rc = launch_factor(U, w.hi[0], m, B, 2, 1.f, st);
   } else {
     if (factor == LIP_FACTOR_SQRT) s *= expf(-0.5f * m->logvar);
     int64_t n = B * m->M * m->K;
-    scale_copy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(U, w.buf[0], n, 1.f);
+    scale_copy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(U, w.hi[0], n, 1.f);
     LIP_LAUNCH_CHECK();
     rc = LIP_OK;
   }
   if (rc) return rc;
-  return vjp_sweep(m, w.buf[0], w.buf[1], B, out, s, add, add_scale, st);
+  return vjp_sweep(m, 0, B, w, out, s, add, add_scale, st);
 }
 
 size_t lip_gram_workspace_bytes(const lip_model* m, int64_t block) {

@@ -309,3 +309,72 @@ def test_unsupported_models_fail_loudly():
                                  apply_fn=Weird().apply)
     with pytest.raises(ValueError):
         ggn.compute_ggn_vp(st2, torch.zeros(2, 3, device="cuda"), "classifier")
+
+
+# --------------------------------------------------------------------------------- tensor-core path
+TC_CONFIGS = {
+    # name: (hidden, n_out, in_dim, M, N)
+    "tc_small": ([128, 64], 10, 96, 128, 5000),
+    "tc_ragged": ([200, 72, 136], 7, 100, 150, 900),
+}
+
+
+@pytest.mark.parametrize("name", list(TC_CONFIGS))
+def test_tensor_core_path_matches_oracle(name):
+    """The tcgen05 3xTF32 path (layers with in,out,M >= 64) against the float64 oracle and against the SIMT path."""
+    from lip_b200 import ggn, lla
+    hidden, n_out, in_dim, M, N = TC_CONFIGS[name]
+    ost, lst = make_pair("large", hidden=hidden, n_out=n_out, in_dim=in_dim, seed=77)
+    rng = np.random.default_rng(78)
+    Z = rng.random((M, in_dim)).astype(np.float32)
+    D = ost.flat()[0].size
+    V = rng.choice([-1.0, 1.0], size=(5, D)).astype(np.float32)
+    V[3:] = rng.standard_normal((2, D)).astype(np.float32)
+    alpha = 0.01
+    ref_vp = O.compute_curvature_approx(ost, Z, "classifier", alpha, full_set_size=N)
+    ref = np.stack([ref_vp(v) for v in V.astype(np.float64)])
+    cvp = lla.compute_curvature_approx(lst, cu(Z), "classifier", alpha, full_set_size=N, tensor_path=True)
+    assert "tcgen05" in cvp._lip_model.path_name()
+    got = cvp(cu(V)).cpu().numpy()
+    simt = lla.compute_curvature_approx(lst, cu(Z), "classifier", alpha, full_set_size=N, tensor_path=False)(cu(V)).cpu().numpy()
+    e_tc, e_simt = rel_err(got, ref), rel_err(simt, ref)
+    print(f"{name}: tc rel err {e_tc:.2e}, simt rel err {e_simt:.2e}")
+    assert e_simt < TOL_GGN
+    assert e_tc < TOL_GGN
+    Wo, WTo = O.compute_W_vps(ost, Z, "classifier", full_set_size=N)
+    Wg, WTg = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=N, tensor_path=True)
+    ref_wt = np.stack([WTo(v) for v in V.astype(np.float64)])
+    assert rel_err(WTg(cu(V)).cpu().numpy(), ref_wt) < TOL_GGN
+    U = rng.standard_normal(ref_wt.shape).astype(np.float32)
+    assert rel_err(Wg(cu(U)).cpu().numpy(), np.stack([Wo(u) for u in U.astype(np.float64)])) < TOL_GGN
+
+
+def test_tensor_core_gemm_selftest():
+    import ctypes as C
+    from lip_b200 import _cabi
+    L = _cabi.lib()
+    for variant in (0, 1, 2):
+        for (M, N, K, b) in [(128, 128, 32, 1), (256, 256, 128, 3), (100, 96, 72, 2), (512, 256, 1024, 2)]:
+            err = C.c_float(-1)
+            _cabi.check(L.lip_selftest_tc_gemm(variant, M, N, K, b, C.byref(err), None), "selftest")
+            assert err.value < 4e-6, (variant, M, N, K, b, err.value)
+
+
+def test_headline_config_matches_oracle():
+    """C3b (MNIST MLP 784-1024-512-256-128-10, M=512) at full size: curvature_vp for 2 probes vs the float64 oracle."""
+    from lip_b200 import lla
+    ost, lst = make_pair("large", hidden=[1024, 512, 256, 128], n_out=10, in_dim=784, seed=1003, in_shape=(28, 28, 1))
+    rng = np.random.default_rng(1004)
+    Z = rng.random((512, 784)).astype(np.float32)
+    D = ost.flat()[0].size
+    assert D == 1494154
+    V = rng.choice([-1.0, 1.0], size=(2, D)).astype(np.float32)
+    V[1] = rng.standard_normal(D).astype(np.float32)
+    ref_vp = O.compute_curvature_approx(ost, Z, "classifier", 1e-3, full_set_size=60000)
+    ref = np.stack([ref_vp(v) for v in V.astype(np.float64)])
+    for tp in (True, False):
+        cvp = lla.compute_curvature_approx(lst, cu(Z), "classifier", 1e-3, full_set_size=60000, tensor_path=tp)
+        got = cvp(cu(V)).cpu().numpy()
+        errs = [rel_err(got[i], ref[i]) for i in range(2)]
+        print(f"C3b tensor_path={tp} ({cvp._lip_model.path_name()}): rel err {errs}")
+        assert max(errs) < TOL_GGN
