@@ -10,9 +10,12 @@
 //   JVP    : A K-major  (activations [M,K]),  B MN-major (tangent weights [K,N])      (+ a second A/B pair)
 //   WGRAD  : A MN-major (activations^T),      B MN-major (deltas [K,N])
 //   DGRAD  : A K-major  (deltas [M,K]),       B K-major  (weights [N,K])
-// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps4-7 = epilogue (TMEM -> registers -> fused epilogue -> global).  All mbarrier waits are bounded: a
-// deadlock traps instead of hanging the GPU.
+// Persistent CTAs (one per SM) walk a static tile schedule.  Warp roles (256 threads): warp0 = TMA producer,
+// warp1 = MMA issuer, warp2 = TMEM allocator, warps4-7 = accumulator drain + epilogue.  The K loop is cut into
+// chunks of KC k-blocks; chunks alternate between two TMEM buffers, and the drain warps add each finished chunk
+// into fp32 REGISTER accumulators (round-to-nearest) while the tensor core works on the next chunk / next tile.
+// The tile epilogue transposes through shared memory so that mask/add reads and the stores are 128-byte coalesced.
+// All mbarrier waits are bounded: a deadlock traps instead of hanging the GPU.
 #include <cuda.h>
 
 #include <mutex>
@@ -28,12 +31,13 @@ namespace {
 constexpr int TBM = 128;       // CTA tile rows (UMMA M)
 constexpr int TBK = 32;        // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;      // tf32
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // 4 control warps + 8 drain/epilogue warps
 // fp32 accumulation in TMEM rounds toward zero, a bias that grows with the number of accumulation steps.
 // Two measures keep 3xTF32 inside the 1e-5 budget: the two cross terms (2^-11 smaller) accumulate in their own
-// TMEM tile so they never truncate the main sum, and the hi*hi terms are dealt round-robin to NACC main tiles
-// that are added in round-to-nearest fp32 by the epilogue.
-constexpr int NACC = 3;
+// TMEM tile so they never truncate the main sum, and no TMEM accumulator lives longer than KC k-blocks
+// (32 tf32 MMAs) before it is folded into the register accumulators in round-to-nearest.
+constexpr int KC = 8;          // k-blocks per TMEM chunk (256 fp32 of K)
+constexpr int STG_LD = 33;     // padded row of the epilogue staging tile
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,7 +141,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
 }
 
 struct TcParams {
-  int M, N, K1, K2;
+  int M, N, K1, K2, batch;
   int a1_batched, b1_batched, a2_batched, b2_batched;
   float* C; float* C_lo;
   long long c_sz, c_sm;
@@ -153,7 +157,8 @@ struct SmemLayout {
   static constexpr int B_TILE = BN * TBK * 4;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = (BN <= 128) ? 3 : 2;
-  static constexpr int BYTES = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING = 8 * 32 * STG_LD * 4;   // one 32x32 (padded) transpose tile per drain warp
+  static constexpr int BYTES = STAGES * STAGE + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // One operand tile load (ROWS = TBM or BN rows of the tile's non-contraction index).
@@ -177,26 +182,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
                const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
                const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, TcParams p) {
   using SL = SmemLayout<BN>;
-  constexpr int TMEM_COLS = (NACC + 1) * BN <= 32 ? 32 : (NACC + 1) * BN <= 64 ? 64 : (NACC + 1) * BN <= 128 ? 128
-                            : (NACC + 1) * BN <= 256 ? 256 : 512;
-  static_assert((NACC + 1) * BN <= 512, "accumulators exceed TMEM");
+  static_assert(BN == 128, "register accumulators are sized for BN = 128");
+  constexpr int TMEM_COLS = 512;          // 2 buffers x (cross-term tile + main tile) x BN columns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + SL::STAGES * SL::STAGE;
-  // barriers: full[STAGES], empty[STAGES], tmem_full; then the TMEM base address slot
+  const uint32_t stg_base = smem_base + SL::STAGES * SL::STAGE;
+  const uint32_t bar_base = stg_base + SL::STAGING;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (SL::STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * SL::STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * SL::STAGES + 1);
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * SL::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SL::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SL::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN, z = blockIdx.z;
   const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
   const int nk = nk1 + nk2;
+  const int nchunks = (nk + KC - 1) / KC;
+  const int mt = (p.M + TBM - 1) / TBM, nt = (p.N + BN - 1) / BN;
+  const long long ntiles = (long long)mt * nt * p.batch;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < SL::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -214,24 +221,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % SL::STAGES;
-        const uint32_t ph = (kb / SL::STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t st = smem_base + s * SL::STAGE;
-        mbar_arrive_expect_tx(full_bar(s), SL::STAGE);
-        const bool second = kb >= nk1;
-        const int k0 = (second ? kb - nk1 : kb) * TBK;
-        const CUtensorMap* ah = second ? &mA2h : &mA1h;
-        const CUtensorMap* al = second ? &mA2l : &mA1l;
-        const CUtensorMap* bh = second ? &mB2h : &mB1h;
-        const CUtensorMap* bl = second ? &mB2l : &mB1l;
-        const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
-        const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
-        load_operand<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
-        load_operand<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
-        load_operand<B_K, BN>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb);
-        load_operand<B_K, BN>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb);
+      uint32_t it = 0;   // k-block counter across all tiles of this CTA
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (int)(t % mt) * TBM, n0 = (int)((t / mt) % nt) * BN, z = (int)(t / ((long long)mt * nt));
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % SL::STAGES;
+          const uint32_t ph = (it / SL::STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t st = smem_base + s * SL::STAGE;
+          mbar_arrive_expect_tx(full_bar(s), SL::STAGE);
+          const bool second = kb >= nk1;
+          const int k0 = (second ? kb - nk1 : kb) * TBK;
+          const CUtensorMap* ah = second ? &mA2h : &mA1h;
+          const CUtensorMap* al = second ? &mA2l : &mA1l;
+          const CUtensorMap* bh = second ? &mB2h : &mB1h;
+          const CUtensorMap* bl = second ? &mB2l : &mB1l;
+          const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
+          const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
+          load_operand<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
+          load_operand<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
+          load_operand<B_K, BN>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb);
+          load_operand<B_K, BN>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb);
+        }
       }
     }
   } else if (warp == 1) {
@@ -245,97 +256,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
       constexpr uint32_t A_SBO = A_K ? 1024 : 512, B_SBO = B_K ? 1024 : 512;
       constexpr uint32_t A_LT = A_K ? 2 : 1, B_LT = B_K ? 2 : 1;
       constexpr uint32_t A_KSTEP = A_K ? 32 : 1024, B_KSTEP = B_K ? 32 : 1024;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % SL::STAGES;
-        const uint32_t ph = (kb / SL::STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t st = smem_base + s * SL::STAGE;
-        const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE, b_lo = b_hi + SL::B_TILE;
+      uint32_t it = 0, ck = 0;   // k-block / chunk counters across all tiles
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c, ++ck) {
+          const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
+          mbar_wait(tempty_bar(buf), cph ^ 1);           // drain warps have emptied this TMEM buffer
+          tc_fence_after();
+          const uint32_t t_small = tmem_base + buf * (2 * BN), t_main = t_small + BN;
+          const int kb_end = (c + 1) * KC < nk ? (c + 1) * KC : nk;
+          for (int kb = c * KC; kb < kb_end; ++kb, ++it) {
+            const int s = it % SL::STAGES;
+            const uint32_t ph = (it / SL::STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t st = smem_base + s * SL::STAGE;
+            const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE, b_lo = b_hi + SL::B_TILE;
 #pragma unroll
-        for (int j = 0; j < TBK / UMMA_K; ++j) {
-          const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
-          const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
-          const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-          const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-          const int g = kb * (TBK / UMMA_K) + j;       // global k sub-step
-          // columns [0,BN): cross terms; columns [(1+i)*BN, (2+i)*BN): main accumulator i
-          umma_tf32(tmem_base, dal, dbh, idesc, g != 0);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1);
-          umma_tf32(tmem_base + (uint32_t)((1 + g % NACC) * BN), dah, dbh, idesc, g >= NACC);
+            for (int j = 0; j < TBK / UMMA_K; ++j) {
+              const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+              const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+              const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+              const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+              const uint32_t acc = (kb != c * KC || j != 0) ? 1u : 0u;   // first MMA of a chunk overwrites
+              umma_tf32(t_small, dal, dbh, idesc, acc);
+              umma_tf32(t_small, dah, dbl, idesc, 1);
+              umma_tf32(t_main, dah, dbh, idesc, acc);
+            }
+            umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
+          }
+          umma_commit(tfull_bar(buf));            // chunk complete
         }
-        umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
       }
-      umma_commit(tmem_full_bar);             // accumulator complete
     }
   } else if (warp >= 4) {
-    // ================= epilogue: TMEM -> registers -> fused epilogue -> global =================
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
-    const long long crow = (long long)z * p.c_sz + (long long)m * p.c_sm;
-    const float* bias = p.bias ? p.bias + (long long)z * p.bias_sz : nullptr;
-    const float* mask = p.mask ? p.mask + (long long)m * p.mask_sm : nullptr;
-    const float* add = p.add ? p.add + (long long)z * p.add_sz + (long long)m * p.c_sm : nullptr;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-      tmem_ld32(tl, v);                                   // cross terms
+    // ================= drain + epilogue warps (8): warp -> TMEM lane quarter q, column half h =================
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
+    const int h = (warp - 4) >> 2;            // which 64-column half of the tile this warp owns
+    constexpr int HC = BN / 2;                // 64 columns per warp
+    float* stg = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw))) + (warp - 4) * 32 * STG_LD;
+    uint32_t ck = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int m0 = (int)(t % mt) * TBM, n0 = (int)((t / mt) % nt) * BN, z = (int)(t / ((long long)mt * nt));
+      float acc[HC];
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) {
-        float w[32];
-        tmem_ld32(tl + (uint32_t)((1 + a) * BN), w);
+      for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++ck) {
+        const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
+        mbar_wait(tfull_bar(buf), cph);
+        tc_fence_after();
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + h * HC;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += w[i];
-      }
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= p.N) continue;
-      const int nvalid = (p.N - nb) < 32 ? (p.N - nb) : 32;
+        for (int cc = 0; cc < HC / 32; ++cc) {
+          float w[32];
+          tmem_ld32(tl + (uint32_t)(cc * 32), w);              // cross terms
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nvalid) {
-          float x = p.scale * v[i];
-          if (bias) x += __ldg(bias + nb + i);
-          if (mask) x *= __ldg(mask + nb + i);
-          if (add) x += p.add_scale * __ldg(add + nb + i);
-          v[i] = x;
+          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+          tmem_ld32(tl + (uint32_t)(BN + cc * 32), w);         // main terms
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));           // buffer may be overwritten by the next chunk
       }
-      float* cp = p.C + crow + nb;
-      if (p.C_lo) {
-        float* lp = p.C_lo + crow + nb;
-        if (nvalid == 32 && (((uintptr_t)cp | (uintptr_t)lp) & 15) == 0) {
+      // ---- tile epilogue: registers -> smem (own 32x32 block) -> coalesced fused epilogue + store ----
+      const float* bias = p.bias ? p.bias + (long long)z * p.bias_sz : nullptr;
+      const long long zc = (long long)z * p.c_sz, za = (long long)z * p.add_sz;
+      const int mrow0 = m0 + q * 32;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 h, l;
-            h.x = tf32_rna(v[i]); h.y = tf32_rna(v[i + 1]); h.z = tf32_rna(v[i + 2]); h.w = tf32_rna(v[i + 3]);
-            l.x = tf32_rna(v[i] - h.x); l.y = tf32_rna(v[i + 1] - h.y); l.z = tf32_rna(v[i + 2] - h.z);
-            l.w = tf32_rna(v[i + 3] - h.w);
-            *reinterpret_cast<float4*>(cp + i) = h;
-            *reinterpret_cast<float4*>(lp + i) = l;
-          }
-        } else {
-          for (int i = 0; i < nvalid; ++i) {
-            float h = tf32_rna(v[i]);
-            cp[i] = h;
-            lp[i] = tf32_rna(v[i] - h);
+      for (int cc = 0; cc < HC / 32; ++cc) {
+        const int n = n0 + h * HC + cc * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
+        __syncwarp();
+        if (n < p.N) {
+          const float bv = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+          for (int rb = 0; rb < 32; rb += 16) {
+            float mv[16], av[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {       // issue all loads of this row block first (memory-level parallelism)
+              const int m = mrow0 + rb + r;
+              const bool ok = m < p.M;
+              mv[r] = (p.mask && ok) ? __ldg(p.mask + (long long)m * p.mask_sm + n) : 1.f;
+              av[r] = (p.add && ok) ? __ldg(p.add + za + (long long)m * p.c_sm + n) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int m = mrow0 + rb + r;
+              if (m < p.M) {
+                const float x = (p.scale * stg[(rb + r) * STG_LD + lane] + bv) * mv[r] + p.add_scale * av[r];
+                const long long co = zc + (long long)m * p.c_sm + n;
+                if (p.C_lo) {
+                  const float hh = tf32_rna(x);
+                  p.C[co] = hh;
+                  p.C_lo[co] = tf32_rna(x - hh);
+                } else {
+                  p.C[co] = x;
+                }
+              }
+            }
           }
         }
-      } else if (nvalid == 32 && ((uintptr_t)cp & 15) == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      } else if (nvalid == 32 && ((uintptr_t)cp & 7) == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) *reinterpret_cast<float2*>(cp + i) = make_float2(v[i], v[i + 1]);
-      } else {
-        for (int i = 0; i < nvalid; ++i) cp[i] = v[i];
+        __syncwarp();
       }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
@@ -431,7 +458,7 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
     if (rc) return rc;
   }
   TcParams p;
-  p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0;
+  p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0; p.batch = (int)g.batch;
   p.a1_batched = g.a_batched; p.b1_batched = g.b_batched; p.a2_batched = g.a2_batched; p.b2_batched = g.b2_batched;
   p.C = g.C; p.C_lo = g.C_lo; p.c_sz = g.c_sz; p.c_sm = g.c_sm;
   p.scale = g.epi.scale;
@@ -445,9 +472,14 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
     LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES));
     attr_set = true;
   }
-  const int64_t zmax = 65535;
-  LIP_REQUIRE(g.batch <= zmax, "gemm_tc: batch %lld exceeds %lld", (long long)g.batch, (long long)zmax);
-  dim3 grid((unsigned)ceil_div(g.M, TBM), (unsigned)ceil_div(g.N, BN), (unsigned)g.batch);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LIP_CHECK_CUDA(cudaGetDevice(&dev));
+    LIP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t ntiles = ceil_div(g.M, TBM) * ceil_div(g.N, BN) * g.batch;
+  dim3 grid((unsigned)(ntiles < num_sms ? ntiles : num_sms));
   kern<<<grid, TC_THREADS, SL::BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
