@@ -76,6 +76,33 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -89,6 +116,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -162,20 +194,35 @@ struct SmemLayout {
 };
 
 // One operand tile load (ROWS = TBM or BN rows of the tile's non-contraction index).
-//   K-major : 3D map {K, rows, batch},  ONE box {32 k, ROWS rows, 1}: smem [row][32 k] (128 B rows, 8-row swizzle groups)
+//   K-major : 3D map {K, rows, batch},  box {32 k, ROWS (or ROWS/2) rows, 1}: smem [row][32 k] (128 B rows)
 //   MN-major: 3D map {cols, K, batch},  ROWS/32 boxes {32 cols, 32 k, 1}, 4 KB each: smem [chunk][k][32 cols]
 // Out-of-range rows / columns / k are zero-filled by TMA.
-template <bool KMAJOR, int ROWS>
-__device__ __forceinline__ void load_operand(uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0, int row0, int z) {
-  if (KMAJOR) {
-    tma_load_3d(dst, map, bar, k0, row0, z);
-  } else {
+// CL == 4 (2x2 cluster): this CTA fetches only half `half` of the tile and multicasts it to the CTAs in `mask`
+// (the partner fetches the other half), so every tile is read from L2 once per CTA pair.
+template <bool KMAJOR, int ROWS, int CL>
+__device__ __forceinline__ void load_operand(uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0, int row0, int z,
+                                             int half, uint16_t mask) {
+  if (CL == 1) {
+    if (KMAJOR) {
+      tma_load_3d(dst, map, bar, k0, row0, z);
+    } else {
 #pragma unroll
-    for (int c = 0; c < ROWS / 32; ++c) tma_load_3d(dst + c * (TBK * 128), map, bar, row0 + 32 * c, k0, z);
+      for (int c = 0; c < ROWS / 32; ++c) tma_load_3d(dst + c * (TBK * 128), map, bar, row0 + 32 * c, k0, z);
+    }
+  } else {
+    if (KMAJOR) {
+      tma_load_3d_mc(dst + half * (ROWS / 2) * 128, map, bar, k0, row0 + half * (ROWS / 2), z, mask);
+    } else {
+#pragma unroll
+      for (int c = 0; c < ROWS / 64; ++c) {
+        const int ch = half * (ROWS / 64) + c;
+        tma_load_3d_mc(dst + ch * (TBK * 128), map, bar, row0 + 32 * ch, k0, z, mask);
+      }
+    }
   }
 }
 
-template <int BN, bool A_K, bool B_K>
+template <int BN, bool A_K, bool B_K, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
                const __grid_constant__ CUtensorMap mB1h, const __grid_constant__ CUtensorMap mB1l,
@@ -199,10 +246,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   const int nk = nk1 + nk2;
   const int nchunks = (nk + KC - 1) / KC;
   const int mt = (p.M + TBM - 1) / TBM, nt = (p.N + BN - 1) / BN;
-  const long long ntiles = (long long)mt * nt * p.batch;
+  // Tile schedule.  CL == 1: CTA-granular, tile t = blockIdx.x + i * gridDim.x, m fastest.
+  // CL == 4: a 2x2 cluster walks 2x2 super-tiles; rank r -> (ci = r >> 1 along M, cj = r & 1 along N).
+  const uint32_t crank = (CL == 1) ? 0u : cluster_ctarank();
+  const int ci = (int)(crank >> 1), cj = (int)(crank & 1);
+  const int smt = (CL == 1) ? mt : (mt + 1) / 2, snt = (CL == 1) ? nt : (nt + 1) / 2;
+  const long long ntiles = (long long)smt * snt * p.batch;
+  const long long t_first = (CL == 1) ? (long long)blockIdx.x : (long long)cluster_id_x();
+  const long long t_step = (CL == 1) ? (long long)gridDim.x : (long long)num_clusters_x();
+  auto tile_coords = [&](long long t, int& m0, int& n0, int& z) {
+    const int tm = (int)(t % smt), tn = (int)((t / smt) % snt);
+    z = (int)(t / ((long long)smt * snt));
+    m0 = ((CL == 1) ? tm : 2 * tm + ci) * TBM;
+    n0 = ((CL == 1) ? tn : 2 * tn + cj) * BN;
+  };
+  // multicast masks: A tile is shared by the two CTAs with the same ci, B tile by the two with the same cj
+  const uint16_t a_mask = (uint16_t)(0x3u << (2 * ci)), b_mask = (uint16_t)((1u << cj) | (1u << (cj + 2)));
+  const uint16_t e_mask = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < SL::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // a stage is written by this CTA and (CL == 4) by its A- and B-partners: all three consumers must release it
+    for (int s = 0; s < SL::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL == 1 ? 1 : 3); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -214,6 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL != 1) cluster_sync_all();          // partner barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -222,8 +287,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;   // k-block counter across all tiles of this CTA
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int m0 = (int)(t % mt) * TBM, n0 = (int)((t / mt) % nt) * BN, z = (int)(t / ((long long)mt * nt));
+      for (long long t = t_first; t < ntiles; t += t_step) {
+        int m0, n0, z;
+        tile_coords(t, m0, n0, z);
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % SL::STAGES;
           const uint32_t ph = (it / SL::STAGES) & 1;
@@ -238,10 +304,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
           const CUtensorMap* bl = second ? &mB2l : &mB1l;
           const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
           const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
-          load_operand<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
-          load_operand<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
-          load_operand<B_K, BN>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb);
-          load_operand<B_K, BN>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb);
+          load_operand<A_K, TBM, CL>(st, ah, full_bar(s), k0, m0, za, cj, a_mask);
+          load_operand<A_K, TBM, CL>(st + SL::A_TILE, al, full_bar(s), k0, m0, za, cj, a_mask);
+          load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb, ci, b_mask);
+          load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb, ci, b_mask);
         }
       }
     }
@@ -257,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
       constexpr uint32_t A_LT = A_K ? 2 : 1, B_LT = B_K ? 2 : 1;
       constexpr uint32_t A_KSTEP = A_K ? 32 : 1024, B_KSTEP = B_K ? 32 : 1024;
       uint32_t it = 0, ck = 0;   // k-block / chunk counters across all tiles
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (long long t = t_first; t < ntiles; t += t_step) {
         for (int c = 0; c < nchunks; ++c, ++ck) {
           const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
           mbar_wait(tempty_bar(buf), cph ^ 1);           // drain warps have emptied this TMEM buffer
@@ -282,7 +348,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
               umma_tf32(t_small, dah, dbl, idesc, 1);
               umma_tf32(t_main, dah, dbh, idesc, acc);
             }
-            umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
+            // frees the smem stage when these MMAs retire (for every CTA that writes into it)
+            if (CL == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), e_mask);
           }
           umma_commit(tfull_bar(buf));            // chunk complete
         }
@@ -295,8 +362,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
     constexpr int HC = BN / 2;                // 64 columns per warp
     float* stg = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw))) + (warp - 4) * 32 * STG_LD;
     uint32_t ck = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int m0 = (int)(t % mt) * TBM, n0 = (int)((t / mt) % nt) * BN, z = (int)(t / ((long long)mt * nt));
+    for (long long t = t_first; t < ntiles; t += t_step) {
+      int m0, n0, z;
+      tile_coords(t, m0, n0, z);
       float acc[HC];
 #pragma unroll
       for (int i = 0; i < HC; ++i) acc[i] = 0.f;
@@ -364,6 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL != 1) cluster_sync_all();          // no multicast write / remote arrive may target a CTA that has exited
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
@@ -439,7 +508,7 @@ int make_map(CUtensorMap* map, const float* ptr, bool kmajor, int64_t rows_or_co
   return LIP_OK;
 }
 
-template <int BN, bool A_K, bool B_K>
+template <int BN, bool A_K, bool B_K, int CL>
 int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
   CUtensorMap maps[8];
   const TcOperand* ops[4] = {&g.A1, &g.B1, &g.A2, &g.B2};
@@ -452,9 +521,10 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
     const bool km = is_a ? A_K : B_K;
     const int64_t K = (i >= 2 && dual) ? g.K2 : g.K;
     const int64_t rows = is_a ? g.M : g.N;
-    int rc = make_map(&maps[2 * i], o.hi, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, is_a ? TBM : BN);
+    const int box_rows = (is_a ? TBM : BN) / (CL == 1 ? 1 : 2);   // cluster mode: each CTA fetches half a tile
+    int rc = make_map(&maps[2 * i], o.hi, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, box_rows);
     if (rc) return rc;
-    rc = make_map(&maps[2 * i + 1], o.lo, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, is_a ? TBM : BN);
+    rc = make_map(&maps[2 * i + 1], o.lo, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, box_rows);
     if (rc) return rc;
   }
   TcParams p;
@@ -466,7 +536,7 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
   p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
   p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
   using SL = SmemLayout<BN>;
-  auto kern = gemm_tc_kernel<BN, A_K, B_K>;
+  auto kern = gemm_tc_kernel<BN, A_K, B_K, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES));
@@ -478,9 +548,26 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
     LIP_CHECK_CUDA(cudaGetDevice(&dev));
     LIP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int64_t ntiles = ceil_div(g.M, TBM) * ceil_div(g.N, BN) * g.batch;
-  dim3 grid((unsigned)(ntiles < num_sms ? ntiles : num_sms));
-  kern<<<grid, TC_THREADS, SL::BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+  const int64_t mt = ceil_div(g.M, TBM), nt = ceil_div(g.N, BN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SL::BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (CL == 1) {
+    const int64_t ntiles = mt * nt * g.batch;
+    cfg.gridDim = dim3((unsigned)(ntiles < num_sms ? ntiles : num_sms));
+    cfg.numAttrs = 0;
+  } else {
+    const int64_t nsuper = ceil_div(mt, 2) * ceil_div(nt, 2) * g.batch;
+    const int64_t max_clusters = num_sms / CL;
+    cfg.gridDim = dim3((unsigned)((nsuper < max_clusters ? nsuper : max_clusters) * CL));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  LIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p));
   LIP_LAUNCH_CHECK();
   return LIP_OK;
 }
@@ -505,9 +592,19 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   LIP_REQUIRE(g.epi.act < 0 && g.epi.dphi_out == nullptr, "gemm_tc: activation epilogue is SIMT-only");
   const bool a_k = g.A1.major_k != 0, b_k = g.B1.major_k != 0;
   if (g.A2.hi) LIP_REQUIRE((g.A2.major_k != 0) == a_k && (g.B2.major_k != 0) == b_k, "gemm_tc: second pair must share majors");
-  if (a_k && !b_k) return launch_tc<128, true, false>(g, st);
-  if (!a_k && !b_k) return launch_tc<128, false, false>(g, st);
-  if (a_k && b_k) return launch_tc<128, true, true>(g, st);
+  // 2x2 clusters with TMA multicast halve the L2 reads per CTA; worth it once there are enough tiles per cluster
+  static const int force_cl = getenv("LIP_TC_CLUSTER") ? atoi(getenv("LIP_TC_CLUSTER")) : -1;
+  // (measured on B200: correct, but the lock-step coupling costs more than the L2 saving -> off by default)
+  const bool cl4 = force_cl == 4;
+  if (cl4) {
+    if (a_k && !b_k) return launch_tc<128, true, false, 4>(g, st);
+    if (!a_k && !b_k) return launch_tc<128, false, false, 4>(g, st);
+    if (a_k && b_k) return launch_tc<128, true, true, 4>(g, st);
+  } else {
+    if (a_k && !b_k) return launch_tc<128, true, false, 1>(g, st);
+    if (!a_k && !b_k) return launch_tc<128, false, false, 1>(g, st);
+    if (a_k && b_k) return launch_tc<128, true, true, 1>(g, st);
+  }
   set_error("gemm_tc: unsupported operand majors (A MN-major with B K-major)");
   return LIP_ERR_INVALID;
 }
