@@ -181,6 +181,12 @@ int lip_bidiag_to_tridiag(const float* alphas, const float* betas, float* tdiag,
 int lip_selftest_tc_gemm(int32_t variant, int64_t Mrows, int64_t N, int64_t K, int64_t batch,
                          float* max_rel_err, lip_stream_t stream);
 
+/* Microbenchmark of the tensor-core GEMM (zero operands, same variants as the self test): average ms per launch
+ * over `iters` launches.  dbg knobs (diagnosis only; results are then meaningless): 1 = skip the epilogue's global
+ * traffic, 2 = issue only the hi*hi MMA, 4 = skip the TMA loads.  two_cta: 0 = 1-CTA kernel, 1 = cta_group::2. */
+int lip_bench_tc_gemm(int32_t variant, int64_t Mrows, int64_t N, int64_t K, int64_t batch, int32_t iters,
+                      int32_t dbg, int32_t two_cta, float* ms_per_iter, lip_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,7 @@ SIGNATURES = {
     "lip_tridiag_scratch_bytes": (_SZ, [_I64, _I64, _I32]),
     "lip_tridiag_funm": (C.c_int, [_P, _P, _I64, _I64, _I32, _F, _P, _P, _P, _P, _P]),
     "lip_bidiag_to_tridiag": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
+    "lip_bench_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, _I32, _I32, _I32, C.POINTER(_F), _P]),
     "lip_selftest_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, C.POINTER(_F), _P]),
 }
 

@@ -70,6 +70,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
+// One lane of a converged warp.  The role loops below run warp-uniformly and gate only the asynchronous issue with
+// this predicate: operands then live in uniform registers and each UTCHMMA / UTMALDG is a single instruction
+// (under `if (lane == 0)` the compiler wraps every one in a VOTEU/ELECT/R2UR.BROADCAST divergence loop, which
+// costs more than the 64-cycle tf32 MMA itself).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -123,6 +138,35 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
                ::"r"(bar), "h"(mask) : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) forms ----------------------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the pair-rank bit of a shared::cluster address -> even CTA
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  // executed by both CTAs of the pair: data lands in the executing CTA's smem, bytes are credited to the LEADER's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -172,8 +216,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
          | ((uint32_t)(M >> 4) << 24);    // m_dim
 }
 
+static int g_tc_dbg = 0;      // set only by lip_bench_tc_gemm
+static int g_tc_force2 = -1;  // -1: environment / default, 0: 1-CTA kernel, 1: 2-CTA kernel
+
 struct TcParams {
   int M, N, K1, K2, batch;
+  int dbg;   // microbenchmark knobs: 1 = skip epilogue global traffic, 2 = issue only the hi*hi MMA, 4 = skip TMA loads
   int a1_batched, b1_batched, a2_batched, b2_batched;
   float* C; float* C_lo;
   long long c_sz, c_sm;
@@ -241,7 +289,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SL::STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * SL::STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
   const int nk = nk1 + nk2;
   const int nchunks = (nk + KC - 1) / KC;
@@ -284,8 +333,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
+    {
       uint32_t it = 0;   // k-block counter across all tiles of this CTA
       for (long long t = t_first; t < ntiles; t += t_step) {
         int m0, n0, z;
@@ -295,25 +344,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
           const uint32_t ph = (it / SL::STAGES) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t st = smem_base + s * SL::STAGE;
-          mbar_arrive_expect_tx(full_bar(s), SL::STAGE);
-          const bool second = kb >= nk1;
-          const int k0 = (second ? kb - nk1 : kb) * TBK;
-          const CUtensorMap* ah = second ? &mA2h : &mA1h;
-          const CUtensorMap* al = second ? &mA2l : &mA1l;
-          const CUtensorMap* bh = second ? &mB2h : &mB1h;
-          const CUtensorMap* bl = second ? &mB2l : &mB1l;
-          const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
-          const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
-          load_operand<A_K, TBM, CL>(st, ah, full_bar(s), k0, m0, za, cj, a_mask);
-          load_operand<A_K, TBM, CL>(st + SL::A_TILE, al, full_bar(s), k0, m0, za, cj, a_mask);
-          load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb, ci, b_mask);
-          load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb, ci, b_mask);
+          if (elect_one()) {
+            if (p.dbg & 4) {
+              mbar_arrive(full_bar(s));
+            } else {
+              mbar_arrive_expect_tx(full_bar(s), SL::STAGE);
+              const bool second = kb >= nk1;
+              const int k0 = (second ? kb - nk1 : kb) * TBK;
+              const CUtensorMap* ah = second ? &mA2h : &mA1h;
+              const CUtensorMap* al = second ? &mA2l : &mA1l;
+              const CUtensorMap* bh = second ? &mB2h : &mB1h;
+              const CUtensorMap* bl = second ? &mB2l : &mB1l;
+              const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
+              const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
+              load_operand<A_K, TBM, CL>(st, ah, full_bar(s), k0, m0, za, cj, a_mask);
+              load_operand<A_K, TBM, CL>(st + SL::A_TILE, al, full_bar(s), k0, m0, za, cj, a_mask);
+              load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb, ci, b_mask);
+              load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb, ci, b_mask);
+            }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+    {
       constexpr uint32_t idesc = make_idesc(TBM, BN, !A_K, !B_K);
       // K-major SW128: 8-row groups 1024 B apart (SBO); k sub-step (8 tf32) = +32 B inside the 128 B row.
       // MN-major SW128_BASE32B: 32-element MN chunks TBK*128 B apart (LBO), 4-row k groups 512 B apart (SBO);
@@ -337,21 +393,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
             tc_fence_after();
             const uint32_t st = smem_base + s * SL::STAGE;
             const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE, b_lo = b_hi + SL::B_TILE;
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < TBK / UMMA_K; ++j) {
-              const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
-              const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
-              const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-              const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-              const uint32_t acc = (kb != c * KC || j != 0) ? 1u : 0u;   // first MMA of a chunk overwrites
-              umma_tf32(t_small, dal, dbh, idesc, acc);
-              umma_tf32(t_small, dah, dbl, idesc, 1);
-              umma_tf32(t_main, dah, dbh, idesc, acc);
+              for (int j = 0; j < TBK / UMMA_K; ++j) {
+                const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                const uint32_t acc = (kb != c * KC || j != 0) ? 1u : 0u;   // first MMA of a chunk overwrites
+                if (!(p.dbg & 2)) {
+                  umma_tf32(t_small, dal, dbh, idesc, acc);
+                  umma_tf32(t_small, dah, dbl, idesc, 1);
+                }
+                umma_tf32(t_main, dah, dbh, idesc, acc);
+              }
+              // frees the smem stage when these MMAs retire (for every CTA that writes into it)
+              if (CL == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), e_mask);
             }
-            // frees the smem stage when these MMAs retire (for every CTA that writes into it)
-            if (CL == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), e_mask);
+            __syncwarp();
           }
-          umma_commit(tfull_bar(buf));            // chunk complete
+          if (elect_one()) umma_commit(tfull_bar(buf));            // chunk complete
+          __syncwarp();
         }
       }
     }
@@ -397,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
         __syncwarp();
-        if (n < p.N) {
+        if (n < p.N && !(p.dbg & 1)) {
           const float bv = bias ? __ldg(bias + n) : 0.f;
 #pragma unroll
           for (int rb = 0; rb < 32; rb += 16) {
@@ -436,6 +498,256 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
+// ============================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair computes a 256 x BN2 tile.  Each CTA stages its own 128 A rows and HALF
+// of the B tile (BN2/2 rows); the tensor core of the pair reads B halves from both shared memories, so per-CTA
+// shared-memory operand traffic drops from 8 KB to 6 KB per MMA and TMA fill from 64 KB to 48 KB per k-block
+// (the 1-CTA kernel saturates the 128 B/clk shared-memory port at ~60 % tensor utilisation).
+// MMAs are issued by the leader CTA (rank 0) only; TMA loads of both CTAs credit the leader's full barrier; the
+// leader's commits are multicast to both CTAs' empty / tmem-full barriers; the peer's drain warps release the
+// TMEM buffers on the leader's tmem-empty barrier.  Everything else (chunked drain, epilogue) is per-CTA as above.
+// ============================================================================================================
+template <int BN2>
+struct SmemLayout2 {
+  static constexpr int A_TILE = TBM * TBK * 4;          // 16 KB
+  static constexpr int B_TILE = (BN2 / 2) * TBK * 4;    // half of the B tile
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = 4;
+  static constexpr int STAGING = 8 * 32 * STG_LD * 4;
+  static constexpr int BYTES = STAGES * STAGE + STAGING + 1024 + 256;
+};
+
+template <bool KMAJOR, int ROWS>
+__device__ __forceinline__ void load_operand_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int k0, int row0, int z) {
+  if (KMAJOR) {
+    tma_load_3d_2sm(dst, map, bar, k0, row0, z);
+  } else {
+#pragma unroll
+    for (int c = 0; c < ROWS / 32; ++c) tma_load_3d_2sm(dst + c * (TBK * 128), map, bar, row0 + 32 * c, k0, z);
+  }
+}
+
+template <int BN2, bool A_K, bool B_K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
+                const __grid_constant__ CUtensorMap mB1h, const __grid_constant__ CUtensorMap mB1l,
+                const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
+                const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, TcParams p) {
+  using SL = SmemLayout2<BN2>;
+  static_assert(BN2 == 128, "drain register accumulators are sized for 128 output columns per CTA");
+  constexpr int BN = BN2;                 // output columns per CTA
+  constexpr int TMEM_COLS = 512;          // 2 buffers x (cross-term tile + main tile) x BN columns
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = smem_base + SL::STAGES * SL::STAGE;
+  const uint32_t bar_base = stg_base + SL::STAGING;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SL::STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * SL::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SL::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SL::STAGES + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // 0 = leader
+  const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
+  const int nk = nk1 + nk2;
+  const int nchunks = (nk + KC - 1) / KC;
+  const int mpt = (p.M + 2 * TBM - 1) / (2 * TBM), nt = (p.N + BN - 1) / BN;
+  const long long ntiles = (long long)mpt * nt * p.batch;
+  const long long t_first = (long long)cluster_id_x(), t_step = (long long)num_clusters_x();
+  auto tile_coords = [&](long long t, int& m0, int& n0, int& z) {
+    z = (int)(t / ((long long)mpt * nt));
+    m0 = ((int)(t % mpt) * 2 + (int)crank) * TBM;
+    n0 = (int)((t / mpt) % nt) * BN;
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < SL::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // tmem-full: one multicast commit from the leader; tmem-empty (used on the leader): 8 drain warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs; warp-uniform loop, one elected lane issues) =================
+    {
+      uint32_t it = 0;
+      for (long long t = t_first; t < ntiles; t += t_step) {
+        int m0, n0, z;
+        tile_coords(t, m0, n0, z);
+        const int nb0 = n0 + (int)crank * (BN / 2);       // this CTA stages B rows [nb0, nb0 + BN/2)
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % SL::STAGES;
+          const uint32_t ph = (it / SL::STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t st = smem_base + s * SL::STAGE;
+          if (elect_one()) {
+            if (p.dbg & 4) {
+              if (crank == 0) mbar_arrive(full_bar(s));
+            } else {
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SL::STAGE);   // bytes of BOTH CTAs
+              const bool second = kb >= nk1;
+              const int k0 = (second ? kb - nk1 : kb) * TBK;
+              const CUtensorMap* ah = second ? &mA2h : &mA1h;
+              const CUtensorMap* al = second ? &mA2l : &mA1l;
+              const CUtensorMap* bh = second ? &mB2h : &mB1h;
+              const CUtensorMap* bl = second ? &mB2l : &mB1l;
+              const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
+              const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
+              load_operand_2sm<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
+              load_operand_2sm<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
+              load_operand_2sm<B_K, BN / 2>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, nb0, zb);
+              load_operand_2sm<B_K, BN / 2>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, nb0, zb);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: LEADER CTA only (warp-uniform loop, one elected lane issues) =================
+    if (crank == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * TBM, BN, !A_K, !B_K);
+      constexpr uint32_t A_LBO = A_K ? 16 : TBK * 128, B_LBO = B_K ? 16 : TBK * 128;
+      constexpr uint32_t A_SBO = A_K ? 1024 : 512, B_SBO = B_K ? 1024 : 512;
+      constexpr uint32_t A_LT = A_K ? 2 : 1, B_LT = B_K ? 2 : 1;
+      constexpr uint32_t A_KSTEP = A_K ? 32 : 1024, B_KSTEP = B_K ? 32 : 1024;
+      uint32_t it = 0, ck = 0;
+      for (long long t = t_first; t < ntiles; t += t_step) {
+        for (int c = 0; c < nchunks; ++c, ++ck) {
+          const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
+          mbar_wait(tempty_bar(buf), cph ^ 1);           // both CTAs' drain warps have emptied this TMEM buffer
+          tc_fence_after();
+          const uint32_t t_small = tmem_base + buf * (2 * BN), t_main = t_small + BN;
+          const int kb_end = (c + 1) * KC < nk ? (c + 1) * KC : nk;
+          for (int kb = c * KC; kb < kb_end; ++kb, ++it) {
+            const int s = it % SL::STAGES;
+            const uint32_t ph = (it / SL::STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t st = smem_base + s * SL::STAGE;
+            const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE, b_lo = b_hi + SL::B_TILE;
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < TBK / UMMA_K; ++j) {
+                const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                const uint32_t acc = (kb != c * KC || j != 0) ? 1u : 0u;
+                if (!(p.dbg & 2)) {
+                  umma_tf32_2sm(t_small, dal, dbh, idesc, acc);
+                  umma_tf32_2sm(t_small, dah, dbl, idesc, 1);
+                }
+                umma_tf32_2sm(t_main, dah, dbh, idesc, acc);
+              }
+              umma_commit_2sm(empty_bar(s), 0x3);     // stage free in both CTAs
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit_2sm(tfull_bar(buf), 0x3);     // chunk complete: wake both CTAs' drain warps
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= drain + epilogue warps (per CTA: its own 128 rows x BN columns) =================
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    constexpr int HC = BN / 2;
+    float* stg = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw))) + (warp - 4) * 32 * STG_LD;
+    uint32_t ck = 0;
+    for (long long t = t_first; t < ntiles; t += t_step) {
+      int m0, n0, z;
+      tile_coords(t, m0, n0, z);
+      float acc[HC];
+#pragma unroll
+      for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++ck) {
+        const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
+        mbar_wait(tfull_bar(buf), cph);
+        tc_fence_after();
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + h * HC;
+#pragma unroll
+        for (int cc = 0; cc < HC / 32; ++cc) {
+          float w[32];
+          tmem_ld32(tl + (uint32_t)(cc * 32), w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+          tmem_ld32(tl + (uint32_t)(BN + cc * 32), w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (crank == 0) mbar_arrive(tempty_bar(buf)); else mbar_arrive_remote(tempty_bar(buf), 0);
+        }
+      }
+      const float* bias = p.bias ? p.bias + (long long)z * p.bias_sz : nullptr;
+      const long long zc = (long long)z * p.c_sz, za = (long long)z * p.add_sz;
+      const int mrow0 = m0 + q * 32;
+#pragma unroll
+      for (int cc = 0; cc < HC / 32; ++cc) {
+        const int n = n0 + h * HC + cc * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
+        __syncwarp();
+        if (n < p.N && !(p.dbg & 1)) {
+          const float bv = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+          for (int rb = 0; rb < 32; rb += 16) {
+            float mv[16], av[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int m = mrow0 + rb + r;
+              const bool ok = m < p.M;
+              mv[r] = (p.mask && ok) ? __ldg(p.mask + (long long)m * p.mask_sm + n) : 1.f;
+              av[r] = (p.add && ok) ? __ldg(p.add + za + (long long)m * p.c_sm + n) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int m = mrow0 + rb + r;
+              if (m < p.M) {
+                const float x = (p.scale * stg[(rb + r) * STG_LD + lane] + bv) * mv[r] + p.add_scale * av[r];
+                const long long co = zc + (long long)m * p.c_sm + n;
+                if (p.C_lo) {
+                  const float hh = tf32_rna(x);
+                  p.C[co] = hh;
+                  p.C_lo[co] = tf32_rna(x - hh);
+                } else {
+                  p.C[co] = x;
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
   }
 }
 
@@ -529,6 +841,7 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
   }
   TcParams p;
   p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0; p.batch = (int)g.batch;
+  p.dbg = g_tc_dbg;
   p.a1_batched = g.a_batched; p.b1_batched = g.b_batched; p.a2_batched = g.a2_batched; p.b2_batched = g.b2_batched;
   p.C = g.C; p.C_lo = g.C_lo; p.c_sz = g.c_sz; p.c_sm = g.c_sm;
   p.scale = g.epi.scale;
@@ -572,6 +885,64 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
   return LIP_OK;
 }
 
+template <int BN2, bool A_K, bool B_K>
+int launch_tc2(const TcGemmProblem& g, cudaStream_t st) {
+  CUtensorMap maps[8];
+  const TcOperand* ops[4] = {&g.A1, &g.B1, &g.A2, &g.B2};
+  const int batched[4] = {g.a_batched, g.b_batched, g.a2_batched, g.b2_batched};
+  const bool dual = g.A2.hi != nullptr;
+  for (int i = 0; i < 4; ++i) {
+    const TcOperand& o = *ops[(i >= 2 && !dual) ? i - 2 : i];
+    const int bt = batched[(i >= 2 && !dual) ? i - 2 : i];
+    const bool is_a = (i % 2 == 0);
+    const bool km = is_a ? A_K : B_K;
+    const int64_t K = (i >= 2 && dual) ? g.K2 : g.K;
+    const int64_t rows = is_a ? g.M : g.N;
+    const int box_rows = is_a ? TBM : BN2 / 2;        // each CTA of the pair stages half of the B tile
+    int rc = make_map(&maps[2 * i], o.hi, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, box_rows);
+    if (rc) return rc;
+    rc = make_map(&maps[2 * i + 1], o.lo, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, box_rows);
+    if (rc) return rc;
+  }
+  TcParams p;
+  p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0; p.batch = (int)g.batch;
+  p.dbg = g_tc_dbg;
+  p.a1_batched = g.a_batched; p.b1_batched = g.b_batched; p.a2_batched = g.a2_batched; p.b2_batched = g.b2_batched;
+  p.C = g.C; p.C_lo = g.C_lo; p.c_sz = g.c_sz; p.c_sm = g.c_sm;
+  p.scale = g.epi.scale;
+  p.bias = g.epi.bias; p.bias_sz = g.epi.bias_sz;
+  p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
+  p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
+  using SL = SmemLayout2<BN2>;
+  auto kern = gemm_tc2_kernel<BN2, A_K, B_K>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LIP_CHECK_CUDA(cudaGetDevice(&dev));
+    LIP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t npairs = ceil_div(g.M, 2 * TBM) * ceil_div(g.N, BN2) * g.batch;
+  const int64_t max_clusters = num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SL::BYTES;
+  cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)((npairs < max_clusters ? npairs : max_clusters) * 2));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p));
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
 }  // namespace
 
 bool tc_available() {
@@ -596,6 +967,16 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   static const int force_cl = getenv("LIP_TC_CLUSTER") ? atoi(getenv("LIP_TC_CLUSTER")) : -1;
   // (measured on B200: correct, but the lock-step coupling costs more than the L2 saving -> off by default)
   const bool cl4 = force_cl == 4;
+  static const int two_cta = getenv("LIP_TC_2CTA") ? atoi(getenv("LIP_TC_2CTA")) : 0;
+  static const bool verbose = getenv("LIP_TC_VERBOSE") != nullptr;
+  if (verbose) fprintf(stderr, "[lip] gemm_tc M=%lld N=%lld K=%lld K2=%lld batch=%lld a_k=%d b_k=%d two_cta=%d cl4=%d\n", (long long)g.M,
+                       (long long)g.N, (long long)g.K, (long long)g.K2, (long long)g.batch, (int)a_k, (int)b_k, two_cta, (int)cl4);
+  const bool use2 = g_tc_force2 >= 0 ? (g_tc_force2 == 1) : (two_cta != 0);
+  if (use2 && g.M > TBM) {
+    if (a_k && !b_k) return launch_tc2<128, true, false>(g, st);
+    if (!a_k && !b_k) return launch_tc2<128, false, false>(g, st);
+    if (a_k && b_k) return launch_tc2<128, true, true>(g, st);
+  }
   if (cl4) {
     if (a_k && !b_k) return launch_tc<128, true, false, 4>(g, st);
     if (!a_k && !b_k) return launch_tc<128, false, false, 4>(g, st);
@@ -660,6 +1041,49 @@ __global__ void max_rel_err_kernel(const float* a, const float* b, long long n, 
   if (threadIdx.x == 0) { atomicAdd(num, sn[0]); atomicAdd(den, sd[0]); }
 }
 }  // namespace
+
+extern "C" int lip_bench_tc_gemm(int32_t variant, int64_t M, int64_t N, int64_t K, int64_t batch, int32_t iters, int32_t dbg,
+                                 int32_t two_cta, float* ms_per_iter, lip_stream_t stream) {
+  using namespace lip;
+  LIP_REQUIRE(variant >= 0 && variant <= 2 && M > 0 && N > 0 && K > 0 && batch > 0 && iters > 0 && ms_per_iter, "bench: bad argument");
+  if (!tc_available()) { set_error("bench: tcgen05 path unavailable"); return LIP_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  auto pad = [](int64_t x) { return (x + 31) / 32 * 32; };
+  const bool a_k = (variant != 1), b_k = (variant == 2);
+  const bool a_batched = (variant == 2), b_batched = (variant != 2);
+  const int64_t a_rows = a_k ? M : K, a_cols = a_k ? K : M, b_rows = b_k ? N : K, b_cols = b_k ? K : N;
+  const int64_t lda = pad(a_cols), ldb = pad(b_cols), a_sz = a_rows * lda, b_sz = b_rows * ldb;
+  const int64_t na = (a_batched ? batch : 1) * a_sz + 64, nb = (b_batched ? batch : 1) * b_sz + 64, nc = batch * M * N;
+  float *Ah, *Al, *Bh, *Bl, *C;
+  LIP_CHECK_CUDA(cudaMalloc(&Ah, 4 * na)); LIP_CHECK_CUDA(cudaMalloc(&Al, 4 * na));
+  LIP_CHECK_CUDA(cudaMalloc(&Bh, 4 * nb)); LIP_CHECK_CUDA(cudaMalloc(&Bl, 4 * nb)); LIP_CHECK_CUDA(cudaMalloc(&C, 4 * nc));
+  cudaMemsetAsync(Ah, 0, 4 * na, st); cudaMemsetAsync(Al, 0, 4 * na, st);
+  cudaMemsetAsync(Bh, 0, 4 * nb, st); cudaMemsetAsync(Bl, 0, 4 * nb, st);
+  TcGemmProblem tp;
+  tp.M = M; tp.N = N; tp.K = K; tp.batch = batch;
+  tp.A1.hi = Ah; tp.A1.lo = Al; tp.A1.sz = a_sz; tp.A1.ld = lda; tp.A1.major_k = a_k;
+  tp.B1.hi = Bh; tp.B1.lo = Bl; tp.B1.sz = b_sz; tp.B1.ld = ldb; tp.B1.major_k = b_k;
+  tp.a_batched = a_batched; tp.b_batched = b_batched;
+  tp.C = C; tp.c_sz = M * N; tp.c_sm = N;
+  g_tc_dbg = dbg; g_tc_force2 = two_cta;
+  int rc = gemm_tc(tp, st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  if (!rc) {
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < iters && !rc; ++i) rc = gemm_tc(tp, st);
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { set_error("bench: %s", cudaGetErrorString(e)); rc = LIP_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_iter = ms / iters;
+  }
+  g_tc_dbg = 0; g_tc_force2 = -1;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl); cudaFree(C);
+  return rc;
+}
 
 extern "C" int lip_selftest_tc_gemm(int32_t variant, int64_t M, int64_t N, int64_t K, int64_t batch, float* max_rel_err,
                                     lip_stream_t stream) {
