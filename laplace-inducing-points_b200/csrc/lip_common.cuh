@@ -74,15 +74,15 @@ struct GemmProblem {
 
 int gemm_simt(const GemmProblem& p, cudaStream_t stream);
 
-// tcgen05 3xTF32 path (lip_gemm_tc.cu).  Operands are pre-split TF32 hi/lo pairs in padded buffers.
+// tcgen05 3xTF32 path (lip_gemm_tc.cu).  x = hi + lo with hi, lo TF32-representable.  `hi` may also be the raw
+// fp32 array (the tensor core ignores the 13 low mantissa bits, i.e. truncates) when `lo` was computed against
+// that truncation (tf32_lo_trunc below).  lo == nullptr means "identically zero" (operand exactly TF32).
 struct TcOperand {
   const float* hi = nullptr;
   const float* lo = nullptr;
   int64_t sz = 0;      // batch stride (elements), multiple of 4
   int64_t ld = 0;      // leading dimension (elements), multiple of 4
   int major_k = 1;     // 1: contraction index contiguous ("K-major"), 0: M/N index contiguous
-  int64_t rows = 0;    // extent of the non-contiguous index
-  int64_t cols = 0;    // extent of the contiguous index
 };
 struct TcGemmProblem {
   int64_t M = 0, N = 0, K = 0, K2 = 0, batch = 1;
@@ -90,16 +90,19 @@ struct TcGemmProblem {
   int a_batched = 1, b_batched = 1, a2_batched = 1, b2_batched = 1;
   float* C = nullptr; int64_t c_sz = 0, c_sm = 0;
   float* C_lo = nullptr;      // optional: C receives tf32-hi(v), C_lo the remainder (feeds the next GEMM)
-  GemmEpilogue epi;
+  GemmEpilogue epi;           // scale, mask OR add (and bias on the single-CTA kernel); no activation
 };
 bool tc_available();
 int gemm_tc(const TcGemmProblem& p, cudaStream_t stream);
-// x -> (hi, lo) TF32 split into a padded destination: dst[r*ld_dst + c] for r<rows, c<cols
+// x -> (hi, lo) TF32 split (round-to-nearest hi) into a padded destination: dst[r*ld_dst + c] for r<rows, c<cols
 int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows,
                int64_t cols, cudaStream_t stream);
 // batched form: element (z, r, c) at z*sz + r*ld + c
 int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, float* lo, int64_t sz_dst,
                 int64_t ld_dst, int64_t batch, int64_t rows, int64_t cols, cudaStream_t stream);
+// lo[r*ld + c] = tf32_rna(x - trunc_tf32(x)) for a [rows x cols] block with row pitch ld (same pitch in and out):
+// the low-order part that pairs with the RAW array used as the high-order operand.  float4-vectorised (ld % 4 == 0).
+int tf32_lo_trunc(const float* src, float* lo, int64_t ld, int64_t rows, int64_t cols, cudaStream_t stream);
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

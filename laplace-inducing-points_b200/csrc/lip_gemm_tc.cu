@@ -221,6 +221,7 @@ static int g_tc_force2 = -1;  // -1: environment / default, 0: 1-CTA kernel, 1: 
 
 struct TcParams {
   int M, N, K1, K2, batch;
+  int kc, merge;   // experiment knobs: k-blocks per TMEM chunk; cross terms share the main accumulator
   int dbg;   // microbenchmark knobs: 1 = skip epilogue global traffic, 2 = issue only the hi*hi MMA, 4 = skip TMA loads
   int a1_batched, b1_batched, a2_batched, b2_batched;
   float* C; float* C_lo;
@@ -293,7 +294,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
   const int nk = nk1 + nk2;
-  const int nchunks = (nk + KC - 1) / KC;
+  const int KCr = p.kc;
+  const int nchunks = (nk + KCr - 1) / KCr;
   const int mt = (p.M + TBM - 1) / TBM, nt = (p.N + BN - 1) / BN;
   // Tile schedule.  CL == 1: CTA-granular, tile t = blockIdx.x + i * gridDim.x, m fastest.
   // CL == 4: a 2x2 cluster walks 2x2 super-tiles; rank r -> (ci = r >> 1 along M, cj = r & 1 along N).
@@ -385,8 +387,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
           mbar_wait(tempty_bar(buf), cph ^ 1);           // drain warps have emptied this TMEM buffer
           tc_fence_after();
           const uint32_t t_small = tmem_base + buf * (2 * BN), t_main = t_small + BN;
-          const int kb_end = (c + 1) * KC < nk ? (c + 1) * KC : nk;
-          for (int kb = c * KC; kb < kb_end; ++kb, ++it) {
+          const int kb_end = (c + 1) * KCr < nk ? (c + 1) * KCr : nk;
+          for (int kb = c * KCr; kb < kb_end; ++kb, ++it) {
             const int s = it % SL::STAGES;
             const uint32_t ph = (it / SL::STAGES) & 1;
             mbar_wait(full_bar(s), ph);
@@ -400,12 +402,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
                 const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
                 const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
                 const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-                const uint32_t acc = (kb != c * KC || j != 0) ? 1u : 0u;   // first MMA of a chunk overwrites
-                if (!(p.dbg & 2)) {
-                  umma_tf32(t_small, dal, dbh, idesc, acc);
-                  umma_tf32(t_small, dah, dbl, idesc, 1);
+                const uint32_t acc = (kb != c * KCr || j != 0) ? 1u : 0u;   // first MMA of a chunk overwrites
+                if (p.merge) {
+                  umma_tf32(t_main, dal, dbh, idesc, acc);
+                  umma_tf32(t_main, dah, dbl, idesc, 1);
+                  umma_tf32(t_main, dah, dbh, idesc, 1);
+                } else {
+                  if (!(p.dbg & 2)) {
+                    umma_tf32(t_small, dal, dbh, idesc, acc);
+                    umma_tf32(t_small, dah, dbl, idesc, 1);
+                  }
+                  umma_tf32(t_main, dah, dbh, idesc, acc);
                 }
-                umma_tf32(t_main, dah, dbh, idesc, acc);
               }
               // frees the smem stage when these MMAs retire (for every CTA that writes into it)
               if (CL == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), e_mask);
@@ -438,9 +446,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
 #pragma unroll
         for (int cc = 0; cc < HC / 32; ++cc) {
           float w[32];
-          tmem_ld32(tl + (uint32_t)(cc * 32), w);              // cross terms
+          if (!p.merge) {
+            tmem_ld32(tl + (uint32_t)(cc * 32), w);              // cross terms
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+            for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+          }
           tmem_ld32(tl + (uint32_t)(BN + cc * 32), w);         // main terms
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
@@ -555,7 +565,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
   const uint32_t crank = cluster_ctarank();          // 0 = leader
   const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
   const int nk = nk1 + nk2;
-  const int nchunks = (nk + KC - 1) / KC;
+  const int KCr = p.kc;
+  const int nchunks = (nk + KCr - 1) / KCr;
   const int mpt = (p.M + 2 * TBM - 1) / (2 * TBM), nt = (p.N + BN - 1) / BN;
   const long long ntiles = (long long)mpt * nt * p.batch;
   const long long t_first = (long long)cluster_id_x(), t_step = (long long)num_clusters_x();
@@ -635,8 +646,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
           mbar_wait(tempty_bar(buf), cph ^ 1);           // both CTAs' drain warps have emptied this TMEM buffer
           tc_fence_after();
           const uint32_t t_small = tmem_base + buf * (2 * BN), t_main = t_small + BN;
-          const int kb_end = (c + 1) * KC < nk ? (c + 1) * KC : nk;
-          for (int kb = c * KC; kb < kb_end; ++kb, ++it) {
+          const int kb_end = (c + 1) * KCr < nk ? (c + 1) * KCr : nk;
+          for (int kb = c * KCr; kb < kb_end; ++kb, ++it) {
             const int s = it % SL::STAGES;
             const uint32_t ph = (it / SL::STAGES) & 1;
             mbar_wait(full_bar(s), ph);
@@ -650,12 +661,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
                 const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
                 const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
                 const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-                const uint32_t acc = (kb != c * KC || j != 0) ? 1u : 0u;
-                if (!(p.dbg & 2)) {
-                  umma_tf32_2sm(t_small, dal, dbh, idesc, acc);
-                  umma_tf32_2sm(t_small, dah, dbl, idesc, 1);
+                const uint32_t acc = (kb != c * KCr || j != 0) ? 1u : 0u;
+                if (p.merge) {
+                  umma_tf32_2sm(t_main, dal, dbh, idesc, acc);
+                  umma_tf32_2sm(t_main, dah, dbl, idesc, 1);
+                  umma_tf32_2sm(t_main, dah, dbh, idesc, 1);
+                } else {
+                  if (!(p.dbg & 2)) {
+                    umma_tf32_2sm(t_small, dal, dbh, idesc, acc);
+                    umma_tf32_2sm(t_small, dah, dbl, idesc, 1);
+                  }
+                  umma_tf32_2sm(t_main, dah, dbh, idesc, acc);
                 }
-                umma_tf32_2sm(t_main, dah, dbh, idesc, acc);
               }
               umma_commit_2sm(empty_bar(s), 0x3);     // stage free in both CTAs
             }
@@ -687,9 +704,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
 #pragma unroll
         for (int cc = 0; cc < HC / 32; ++cc) {
           float w[32];
-          tmem_ld32(tl + (uint32_t)(cc * 32), w);
+          if (!p.merge) {
+            tmem_ld32(tl + (uint32_t)(cc * 32), w);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+            for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+          }
           tmem_ld32(tl + (uint32_t)(BN + cc * 32), w);
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
@@ -842,6 +861,8 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
   TcParams p;
   p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0; p.batch = (int)g.batch;
   p.dbg = g_tc_dbg;
+  p.kc = getenv("LIP_TC_KC") ? atoi(getenv("LIP_TC_KC")) : KC;
+  p.merge = getenv("LIP_TC_MERGE") ? atoi(getenv("LIP_TC_MERGE")) : 0;
   p.a1_batched = g.a_batched; p.b1_batched = g.b_batched; p.a2_batched = g.a2_batched; p.b2_batched = g.b2_batched;
   p.C = g.C; p.C_lo = g.C_lo; p.c_sz = g.c_sz; p.c_sm = g.c_sm;
   p.scale = g.epi.scale;
@@ -907,6 +928,8 @@ int launch_tc2(const TcGemmProblem& g, cudaStream_t st) {
   TcParams p;
   p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0; p.batch = (int)g.batch;
   p.dbg = g_tc_dbg;
+  p.kc = getenv("LIP_TC_KC") ? atoi(getenv("LIP_TC_KC")) : KC;
+  p.merge = getenv("LIP_TC_MERGE") ? atoi(getenv("LIP_TC_MERGE")) : 0;
   p.a1_batched = g.a_batched; p.b1_batched = g.b_batched; p.a2_batched = g.a2_batched; p.b2_batched = g.b2_batched;
   p.C = g.C; p.C_lo = g.C_lo; p.c_sz = g.c_sz; p.c_sm = g.c_sm;
   p.scale = g.epi.scale;
