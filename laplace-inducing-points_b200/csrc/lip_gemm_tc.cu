@@ -232,6 +232,79 @@ struct TcParams {
   const float* add; long long add_sz; float add_scale;
 };
 
+
+// ---- tile epilogue shared by both kernels ---------------------------------------------------------------------------
+// A drain warp owns 32 tile rows (one TMEM lane quarter; lane <-> row) x 64 columns in `acc`.  Each 32x32 block is
+// transposed through the warp's padded staging tile so that lane <-> column for the global accesses (128-byte
+// coalesced rows), then  x = (scale * acc + bias[n]) * mask[m][n] + add_scale * add[m][n]  is stored as fp32 or as a
+// TF32 (hi, lo) pair.  The row loops use hoisted base pointers and 8-row batches (loads first): the per-element
+// instruction count, not memory bandwidth, was the cost of the first version of this epilogue (ncu: `no_inst`).
+template <bool HAS_LO>
+__device__ __forceinline__ void store_block_rows(const TcParams& p, const float* __restrict__ sp, float* __restrict__ cp,
+                                                 float* __restrict__ lp, const float* __restrict__ mp,
+                                                 const float* __restrict__ ap, float bv, int nrows) {
+  const float sc = p.scale, asc = p.add_scale;
+  const long long cs = p.c_sm, ms = p.mask_sm;
+  int r0 = 0;
+  for (; r0 + 8 <= nrows; r0 += 8) {
+    float mv[8], av[8], xv[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      mv[r] = mp ? __ldg(mp + (r0 + r) * ms) : 1.f;
+      av[r] = ap ? __ldg(ap + (r0 + r) * cs) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) xv[r] = fmaf(asc, av[r], fmaf(sc, sp[(r0 + r) * STG_LD], bv) * mv[r]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (HAS_LO) {
+        const float hh = tf32_rna(xv[r]);
+        cp[(r0 + r) * cs] = hh;
+        lp[(r0 + r) * cs] = tf32_rna(xv[r] - hh);
+      } else {
+        cp[(r0 + r) * cs] = xv[r];
+      }
+    }
+  }
+  for (; r0 < nrows; ++r0) {
+    const float mv = mp ? __ldg(mp + r0 * ms) : 1.f;
+    const float av = ap ? __ldg(ap + r0 * cs) : 0.f;
+    const float x = fmaf(asc, av, fmaf(sc, sp[r0 * STG_LD], bv) * mv);
+    if (HAS_LO) {
+      const float hh = tf32_rna(x);
+      cp[r0 * cs] = hh;
+      lp[r0 * cs] = tf32_rna(x - hh);
+    } else {
+      cp[r0 * cs] = x;
+    }
+  }
+}
+
+// acc: the warp's 32 x 64 block (row = lane), m0/n0: tile origin, q: lane quarter, h: column half
+__device__ __forceinline__ void tile_epilogue(const TcParams& p, float (&acc)[64], float* stg, int m0, int n0, int z, int q,
+                                              int h, int lane) {
+  const int mrow0 = m0 + q * 32;
+  int nrows = p.M - mrow0;
+  nrows = nrows > 32 ? 32 : nrows;
+  const long long zc = (long long)z * p.c_sz + (long long)mrow0 * p.c_sm;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int n = n0 + h * 64 + cc * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
+    __syncwarp();
+    if (n < p.N && nrows > 0 && !(p.dbg & 1)) {
+      const float bv = p.bias ? __ldg(p.bias + (long long)z * p.bias_sz + n) : 0.f;
+      float* cp = p.C + zc + n;
+      const float* mp = p.mask ? p.mask + (long long)mrow0 * p.mask_sm + n : nullptr;
+      const float* ap = p.add ? p.add + (long long)z * p.add_sz + (long long)mrow0 * p.c_sm + n : nullptr;
+      if (p.C_lo) store_block_rows<true>(p, stg + lane, cp, p.C_lo + zc + n, mp, ap, bv, nrows);
+      else store_block_rows<false>(p, stg + lane, cp, nullptr, mp, ap, bv, nrows);
+    }
+    __syncwarp();
+  }
+}
+
 template <int BN>
 struct SmemLayout {
   static constexpr int A_TILE = TBM * TBK * 4;   // 16 KB
@@ -459,47 +532,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(buf));           // buffer may be overwritten by the next chunk
       }
-      // ---- tile epilogue: registers -> smem (own 32x32 block) -> coalesced fused epilogue + store ----
-      const float* bias = p.bias ? p.bias + (long long)z * p.bias_sz : nullptr;
-      const long long zc = (long long)z * p.c_sz, za = (long long)z * p.add_sz;
-      const int mrow0 = m0 + q * 32;
-#pragma unroll
-      for (int cc = 0; cc < HC / 32; ++cc) {
-        const int n = n0 + h * HC + cc * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
-        __syncwarp();
-        if (n < p.N && !(p.dbg & 1)) {
-          const float bv = bias ? __ldg(bias + n) : 0.f;
-#pragma unroll
-          for (int rb = 0; rb < 32; rb += 16) {
-            float mv[16], av[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {       // issue all loads of this row block first (memory-level parallelism)
-              const int m = mrow0 + rb + r;
-              const bool ok = m < p.M;
-              mv[r] = (p.mask && ok) ? __ldg(p.mask + (long long)m * p.mask_sm + n) : 1.f;
-              av[r] = (p.add && ok) ? __ldg(p.add + za + (long long)m * p.c_sm + n) : 0.f;
-            }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-              const int m = mrow0 + rb + r;
-              if (m < p.M) {
-                const float x = (p.scale * stg[(rb + r) * STG_LD + lane] + bv) * mv[r] + p.add_scale * av[r];
-                const long long co = zc + (long long)m * p.c_sm + n;
-                if (p.C_lo) {
-                  const float hh = tf32_rna(x);
-                  p.C[co] = hh;
-                  p.C_lo[co] = tf32_rna(x - hh);
-                } else {
-                  p.C[co] = x;
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
+      // ---- tile epilogue: registers -> smem (own 32x32 blocks) -> coalesced fused epilogue + store ----
+      tile_epilogue(p, acc, stg, m0, n0, z, q, h, lane);
     }
   }
   tc_fence_before();
@@ -719,46 +753,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
           if (crank == 0) mbar_arrive(tempty_bar(buf)); else mbar_arrive_remote(tempty_bar(buf), 0);
         }
       }
-      const float* bias = p.bias ? p.bias + (long long)z * p.bias_sz : nullptr;
-      const long long zc = (long long)z * p.c_sz, za = (long long)z * p.add_sz;
-      const int mrow0 = m0 + q * 32;
-#pragma unroll
-      for (int cc = 0; cc < HC / 32; ++cc) {
-        const int n = n0 + h * HC + cc * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
-        __syncwarp();
-        if (n < p.N && !(p.dbg & 1)) {
-          const float bv = bias ? __ldg(bias + n) : 0.f;
-#pragma unroll
-          for (int rb = 0; rb < 32; rb += 16) {
-            float mv[16], av[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-              const int m = mrow0 + rb + r;
-              const bool ok = m < p.M;
-              mv[r] = (p.mask && ok) ? __ldg(p.mask + (long long)m * p.mask_sm + n) : 1.f;
-              av[r] = (p.add && ok) ? __ldg(p.add + za + (long long)m * p.c_sm + n) : 0.f;
-            }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-              const int m = mrow0 + rb + r;
-              if (m < p.M) {
-                const float x = (p.scale * stg[(rb + r) * STG_LD + lane] + bv) * mv[r] + p.add_scale * av[r];
-                const long long co = zc + (long long)m * p.c_sm + n;
-                if (p.C_lo) {
-                  const float hh = tf32_rna(x);
-                  p.C[co] = hh;
-                  p.C_lo[co] = tf32_rna(x - hh);
-                } else {
-                  p.C[co] = x;
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
+      tile_epilogue(p, acc, stg, m0, n0, z, q, h, lane);
     }
   }
   tc_fence_before();
@@ -785,6 +780,35 @@ __global__ void tf32_split_kernel(const float* __restrict__ src, long long sz_sr
     float xh = tf32_rna(x);
     h[c] = xh;
     l[c] = tf32_rna(x - xh);
+  }
+}
+
+// Contiguous blocks (ld_src == ld_dst == cols, the probe blocks V[b, woff : woff + in*out]): one flat grid-stride pass
+// per batch entry, 4 independent coalesced loads in flight per thread (the source is only 4-byte aligned: b*D + woff).
+__global__ void __launch_bounds__(256) tf32_split_flat_kernel(const float* __restrict__ src, long long sz_src,
+                                                              float* __restrict__ hi, float* __restrict__ lo,
+                                                              long long sz_dst, long long n) {
+  const long long z = blockIdx.y;
+  const float* s = src + z * sz_src;
+  float* h = hi + z * sz_dst;
+  float* l = lo + z * sz_dst;
+  const long long stride = (long long)gridDim.x * 256;
+  long long i = blockIdx.x * 256ll + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = __ldg(s + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float xh = tf32_rna(x[u]);
+      h[i + u * stride] = xh;
+      l[i + u * stride] = tf32_rna(x[u] - xh);
+    }
+  }
+  for (; i < n; i += stride) {
+    const float x = __ldg(s + i), xh = tf32_rna(x);
+    h[i] = xh;
+    l[i] = tf32_rna(x - xh);
   }
 }
 
@@ -1016,6 +1040,17 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
 int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, float* lo, int64_t sz_dst, int64_t ld_dst,
                 int64_t batch, int64_t rows, int64_t cols, cudaStream_t st) {
   if (rows <= 0 || cols <= 0 || batch <= 0) return LIP_OK;
+  if (ld_src == cols && ld_dst == cols && batch <= 65535) {
+    const int64_t n = rows * cols;
+    int64_t g = ceil_div(n, 256 * 8);
+    const int64_t cap = ceil_div((int64_t)148 * 16, batch);      // ~16 resident CTAs' worth of blocks per SM overall
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    dim3 grid((unsigned)g, (unsigned)batch);
+    tf32_split_flat_kernel<<<grid, 256, 0, st>>>(src, sz_src, hi, lo, sz_dst, n);
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
   int64_t gx = ceil_div(ld_dst, 256);
   if (gx > 64) gx = 64;
   for (int64_t z0 = 0; z0 < batch; z0 += 65535) {
