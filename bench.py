@@ -38,11 +38,11 @@ WORKLOAD = "C3b MNIST-MLP 784-1024-512-256-128-10 (D=1494154), M=512, N=60000, a
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--probes", type=int, default=256, help="probes per GPU per step")
-    ap.add_argument("--slq-k", type=int, default=64)
+    ap.add_argument("--slq-k", type=int, default=409, help="GKL depth; int(0.8*M) as train_inducing.py:148")
     ap.add_argument("--slq-probes", type=int, default=4)
     ap.add_argument("--cpu-probes", type=int, default=2, help="products in the CPU-baseline sample")
     ap.add_argument("--no-slq", action="store_true")
@@ -62,34 +62,59 @@ def build_states(seed=1003):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons DURING the timed region (NVML; nvidia-smi as the fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        bits = [getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        return [str(mhz), str(self.max_mhz)] + ["Active" if (r & b) else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    time.sleep(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
                 if len(parts) >= 6:
                     self.samples.append(parts)
             except Exception:
+                if self.nvml is not None:
+                    self.nvml = None       # fall back to nvidia-smi
+                    continue
                 return
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
             return None
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        reasons = sorted({self.NAMES[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measure_tf32_peak(torch):
@@ -270,37 +295,55 @@ def run_b200(args):
     # ---- SLQ logdet (GKL form, src/train_inducing.py:148-171), probes sharded over ranks ----
     slq = None
     if not args.no_slq:
+        from lip_b200 import _dist
         k, ns = args.slq_k, args.slq_probes
         Wz, WzT = ggn.compute_W_vps(lst, Zd, "classifier", full_set_size=None, tensor_path=tp)
         sa = math.sqrt(ALPHA)
         d = M_POINTS * DIMS[-1]
 
         @matfree.batched
-        def Av(v):
+        def Av(v):                                    # bidiag_target: v -> [sqrt(alpha) v ; Wz^T v]   (train_inducing.py:166-169)
             v = v.reshape(-1, D)
             return torch.cat([sa * v, WzT(v).reshape(v.shape[0], d)], dim=1)
 
         @matfree.batched
-        def vA(u):
+        def vA(u):                                    # its transpose (jax.vjp in the reference)
             u = u.reshape(-1, D + d)
-            return Wz(u[:, D:].reshape(-1, M_POINTS, DIMS[-1])) .add_(u[:, :D], alpha=sa)
+            return Wz(u[:, D:].reshape(-1, M_POINTS, DIMS[-1])).add_(u[:, :D], alpha=sa)
 
-        problem = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(k))
-        mine = list(range(rank, ns, world))
-        probes = V[:ns][mine] if mine else None
+        integrand = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(k))
+        quad = matfree.batched(lambda mv, E: integrand(mv, E, vA))
+        # identical probe matrix on every rank (probes are inputs); rank r runs rows probe_slice(ns)
+        gp = torch.Generator(device=dev)
+        gp.manual_seed(4242)
+        slq_probes = torch.randint(0, 2, (ns, D), generator=gp, device=dev, dtype=torch.int8).float() * 2 - 1
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        part = problem(Av, probes, vA).sum().reshape(1) if mine else torch.zeros(1, device=dev)
-        if world > 1:
-            dist.all_reduce(part)
+        est = _dist.slq_sharded(quad, Av, slq_probes)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        slq = {"seconds": float(dt.item()), "k": k, "probes": ns, "logdet_estimate": float(part.item()) / ns,
-               "form": "GKL bidiag on [sqrt(alpha) I; Wz^T]"}
+        sl = _dist.probe_slice(ns, rank, world)
+        n_loc = max(sl.stop - sl.start, (ns + world - 1) // world)
+        # algorithmic re-orthogonalisation traffic of the slowest rank: step i reads i rows of U (n = D + d) and i + 1
+        # rows of V (n = D) twice each (project, subtract); SURVEY 8d
+        reorth_bytes = n_loc * 4 * sum(2 * i * (D + d) + 2 * (i + 1) * D for i in range(k))
+        secs = float(dt.item())
+        hbm = None
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        slq = {"seconds": secs, "k": k, "probes": ns, "probes_per_gpu": n_loc, "logdet_estimate": float(est.item()),
+               "form": "GKL bidiag on [sqrt(alpha) I; Wz^T], full re-orthogonalisation",
+               "roofline": {"bound": "hbm", "achieved": reorth_bytes / secs / 1e9, "peak": hbm, "unit": "GB/s",
+                            "frac": (reorth_bytes / secs / 1e9 / hbm) if hbm else None,
+                            "algorithmic_bytes": reorth_bytes,
+                            "note": "re-orthogonalisation bytes only, divided by the WHOLE logdet wall time (mat-vecs, "
+                                    "eigensolve and host orchestration included)"}}
 
     if rank != 0:
         if world > 1:

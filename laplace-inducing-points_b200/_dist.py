@@ -1,0 +1,89 @@
+"""Probe sharding across the GPUs of one box (the reference is single-device, src/data.py:90-93).
+
+Every estimator on the hot path is a mean / sum over independent probe columns (stochtrace.py:19,34; matfree's
+`estimator` mean; sample.py:155 independent samples).  One process per GPU: weights, points and the activation
+cache are replicated, rank r owns a contiguous slice of the probe rows and runs its own Krylov recurrences; the
+only communication is ONE all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests) of the partial
+accumulators — a few floats per estimator call.  Nothing here touches the data path.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) of the initialised default process group, (0, 1) without one."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).
+    Returns (rank, world_size, local_rank).  A single-process run (WORLD_SIZE unset or 1) needs no group."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, ws, local
+
+
+def probe_slice(num_probes: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> slice:
+    """Contiguous, balanced slice of the probe rows owned by `rank` (sizes differ by at most one; the first
+    num_probes % world_size ranks get the extra row; a rank may own zero rows when num_probes < world_size)."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    if num_probes < 0 or world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"bad shard request: num_probes={num_probes} rank={rank} world_size={world_size}")
+    base, extra = divmod(num_probes, world_size)
+    start = rank * base + min(rank, extra)
+    return slice(start, start + base + (1 if rank < extra else 0))
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """In-place sum over ranks (no-op without a process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def sharded_mean(per_probe_fn: Callable[[torch.Tensor], torch.Tensor], probes: torch.Tensor) -> torch.Tensor:
+    """mean_b per_probe_fn(probes)[b] over ALL probe rows, each rank evaluating only its slice.
+    `probes` is the full [B, n] probe matrix (identical on every rank: probes are inputs);
+    `per_probe_fn` maps a [b_loc, n] block to b_loc per-probe values.  Returns the global mean on every rank."""
+    B = probes.shape[0]
+    mine = probes[probe_slice(B)]
+    acc = torch.zeros(1, dtype=torch.float64, device=probes.device)
+    if mine.shape[0] > 0:
+        acc += per_probe_fn(mine).double().sum()
+    allreduce_sum_(acc)
+    return (acc / B).to(torch.float32)[0]
+
+
+def hutchinson_sharded(Xfun: Callable, probes: torch.Tensor) -> torch.Tensor:
+    """stochastic_trace_estimator_mvp (stochtrace.py:22-34) with the probe rows sharded over ranks."""
+    def quad(E):
+        Y = Xfun(E) if getattr(Xfun, "_lip_batched", False) else torch.stack([Xfun(e) for e in E])
+        return (E * Y.reshape(E.shape)).sum(1)
+    return sharded_mean(quad, probes)
+
+
+def slq_sharded(integrand: Callable, matvec, probes: torch.Tensor, *parameters) -> torch.Tensor:
+    """matfree.stochtrace.estimator(integrand, sampler)(matvec, key) with the sampler's rows sharded over ranks:
+    the mean over all probes of integrand(matvec, probe) (train_inducing.py:156-163)."""
+    def quad(E):
+        if getattr(integrand, "_lip_batched", False):
+            return integrand(matvec, E, *parameters).reshape(-1)
+        return torch.stack([integrand(matvec, e, *parameters) for e in E]).reshape(-1)
+    return sharded_mean(quad, probes)

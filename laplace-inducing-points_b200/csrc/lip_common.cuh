@@ -90,6 +90,9 @@ struct TcGemmProblem {
   int a_batched = 1, b_batched = 1, a2_batched = 1, b2_batched = 1;
   float* C = nullptr; int64_t c_sz = 0, c_sm = 0;
   float* C_lo = nullptr;      // optional: C receives tf32-hi(v), C_lo the remainder (feeds the next GEMM)
+  // optional: column sums of the stored values per 32-row block, colsum[z*colsum_sz + (m/32)*colsum_ld + n]
+  // (ceil(M/128)*4 slots per z; fuses the bias gradient into the delta-backprop epilogue)
+  float* colsum = nullptr; int64_t colsum_sz = 0, colsum_ld = 0;
   GemmEpilogue epi;           // scale, mask OR add (and bias on the single-CTA kernel); no activation
 };
 bool tc_available();

@@ -149,6 +149,80 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
   }
 }
 
+// ---- skinny variant: N <= 16 (the K-logit head layer, every layer of the toy models) -------------------------------
+// The 128x128 tile above wastes > 87 % of its FMAs when N = 10.  Here a CTA owns 64 rows x all (<= 16) columns;
+// thread (row r, column group cg) keeps 4 accumulators; A tile [32 k][64 m] and B tile [32 k][16 n] in shared memory.
+constexpr int SB_M = 64, SB_K = 32, SB_N = 16;
+
+template <bool A_KC>
+__global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
+  __shared__ float As[SB_K][SB_M + 1];
+  __shared__ __align__(16) float Bs[SB_K][SB_N];
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.y * SB_M;
+  const int tid = threadIdx.x;
+  const int r = tid >> 2, cg = tid & 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int npairs = g.A2.ptr ? 2 : 1;
+  for (int pair = 0; pair < npairs; ++pair) {
+    const DevOperand& A = pair ? g.A2 : g.A1;
+    const DevOperand& B = pair ? g.B2 : g.B1;
+    const int K = pair ? g.K2 : g.K1;
+    const float* Ap = A.ptr + (long long)z * A.sz;
+    const float* Bp = B.ptr + (long long)z * B.sz;
+    for (int k0 = 0; k0 < K; k0 += SB_K) {
+#pragma unroll
+      for (int i = 0; i < (SB_M * SB_K) / NT; ++i) {
+        const int idx = tid + NT * i;
+        int k, rr;
+        if (A_KC) { k = idx % SB_K; rr = idx / SB_K; } else { rr = idx % SB_M; k = idx / SB_M; }
+        const int gm = m0 + rr, gk = k0 + k;
+        As[k][rr] = (gm < g.M && gk < K) ? __ldg(Ap + (long long)gm * A.s0 + (long long)gk * A.s1) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < (SB_K * SB_N) / NT; ++i) {
+        const int idx = tid + NT * i;
+        const int n = idx % SB_N, k = idx / SB_N;
+        const int gk = k0 + k;
+        Bs[k][n] = (n < g.N && gk < K) ? __ldg(Bp + (long long)gk * B.s0 + (long long)n * B.s1) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < SB_K; ++k) {
+        const float a = As[k][r];
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][cg * 4]);
+        acc[0] = fmaf(a, b.x, acc[0]); acc[1] = fmaf(a, b.y, acc[1]);
+        acc[2] = fmaf(a, b.z, acc[2]); acc[3] = fmaf(a, b.w, acc[3]);
+      }
+      __syncthreads();
+    }
+  }
+  const int m = m0 + r;
+  if (m >= g.M) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = cg * 4 + j;
+    if (n >= g.N) continue;
+    float v = g.scale * acc[j];
+    if (g.bias) v += __ldg(g.bias + (long long)z * g.bias_sz + n);
+    const long long co = (long long)z * g.c_sz + (long long)m * g.c_sm + n;
+    if (g.act >= 0) {
+      float d;
+      v = act_apply(g.act, v, &d);
+      if (g.dphi_out) g.dphi_out[co] = d;
+    }
+    if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
+    if (g.add) v += g.add_scale * __ldg(g.add + (long long)z * g.add_sz + (long long)m * g.c_sm + n);
+    if (g.C_lo) {
+      const float h = tf32_round(v);
+      g.C[co] = h;
+      g.C_lo[co] = tf32_round(v - h);
+    } else {
+      g.C[co] = v;
+    }
+  }
+}
+
 }  // namespace
 
 int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
@@ -188,6 +262,13 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     if (gz.dphi_out) gz.dphi_out += z0 * g.c_sz;
     if (gz.C_lo) gz.C_lo += z0 * g.c_sz;
     grid.z = (unsigned)zc;
+    if (p.N <= SB_N) {
+      dim3 sg(1, (unsigned)ceil_div(p.M, SB_M), (unsigned)zc);
+      if (a_kc) gemm_skinny_kernel<true><<<sg, NT, 0, stream>>>(gz);
+      else gemm_skinny_kernel<false><<<sg, NT, 0, stream>>>(gz);
+      LIP_LAUNCH_CHECK();
+      continue;
+    }
     if (a_kc && !b_kc) gemm_simt_kernel<true, false><<<grid, NT, 0, stream>>>(gz);
     else if (!a_kc && !b_kc) gemm_simt_kernel<false, false><<<grid, NT, 0, stream>>>(gz);
     else if (a_kc && b_kc) gemm_simt_kernel<true, true><<<grid, NT, 0, stream>>>(gz);

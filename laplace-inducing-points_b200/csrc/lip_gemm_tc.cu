@@ -230,6 +230,7 @@ struct TcParams {
   const float* bias; long long bias_sz;
   const float* mask; long long mask_sm;
   const float* add; long long add_sz; float add_scale;
+  float* colsum; long long colsum_sz, colsum_ld;
 };
 
 
@@ -240,11 +241,12 @@ struct TcParams {
 // TF32 (hi, lo) pair.  The row loops use hoisted base pointers and 8-row batches (loads first): the per-element
 // instruction count, not memory bandwidth, was the cost of the first version of this epilogue (ncu: `no_inst`).
 template <bool HAS_LO>
-__device__ __forceinline__ void store_block_rows(const TcParams& p, const float* __restrict__ sp, float* __restrict__ cp,
+__device__ __forceinline__ float store_block_rows(const TcParams& p, const float* __restrict__ sp, float* __restrict__ cp,
                                                  float* __restrict__ lp, const float* __restrict__ mp,
                                                  const float* __restrict__ ap, float bv, int nrows) {
   const float sc = p.scale, asc = p.add_scale;
   const long long cs = p.c_sm, ms = p.mask_sm;
+  float colsum = 0.f;
   int r0 = 0;
   for (; r0 + 8 <= nrows; r0 += 8) {
     float mv[8], av[8], xv[8];
@@ -255,6 +257,7 @@ __device__ __forceinline__ void store_block_rows(const TcParams& p, const float*
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) xv[r] = fmaf(asc, av[r], fmaf(sc, sp[(r0 + r) * STG_LD], bv) * mv[r]);
+    colsum += ((xv[0] + xv[1]) + (xv[2] + xv[3])) + ((xv[4] + xv[5]) + (xv[6] + xv[7]));
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       if (HAS_LO) {
@@ -270,6 +273,7 @@ __device__ __forceinline__ void store_block_rows(const TcParams& p, const float*
     const float mv = mp ? __ldg(mp + r0 * ms) : 1.f;
     const float av = ap ? __ldg(ap + r0 * cs) : 0.f;
     const float x = fmaf(asc, av, fmaf(sc, sp[r0 * STG_LD], bv) * mv);
+    colsum += x;
     if (HAS_LO) {
       const float hh = tf32_rna(x);
       cp[r0 * cs] = hh;
@@ -278,6 +282,7 @@ __device__ __forceinline__ void store_block_rows(const TcParams& p, const float*
       cp[r0 * cs] = x;
     }
   }
+  return colsum;
 }
 
 // acc: the warp's 32 x 64 block (row = lane), m0/n0: tile origin, q: lane quarter, h: column half
@@ -293,13 +298,17 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& p, float (&acc)[64
 #pragma unroll
     for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
     __syncwarp();
-    if (n < p.N && nrows > 0 && !(p.dbg & 1)) {
-      const float bv = p.bias ? __ldg(p.bias + (long long)z * p.bias_sz + n) : 0.f;
-      float* cp = p.C + zc + n;
-      const float* mp = p.mask ? p.mask + (long long)mrow0 * p.mask_sm + n : nullptr;
-      const float* ap = p.add ? p.add + (long long)z * p.add_sz + (long long)mrow0 * p.c_sm + n : nullptr;
-      if (p.C_lo) store_block_rows<true>(p, stg + lane, cp, p.C_lo + zc + n, mp, ap, bv, nrows);
-      else store_block_rows<false>(p, stg + lane, cp, nullptr, mp, ap, bv, nrows);
+    if (n < p.N && !(p.dbg & 1)) {
+      float csum = 0.f;
+      if (nrows > 0) {
+        const float bv = p.bias ? __ldg(p.bias + (long long)z * p.bias_sz + n) : 0.f;
+        float* cp = p.C + zc + n;
+        const float* mp = p.mask ? p.mask + (long long)mrow0 * p.mask_sm + n : nullptr;
+        const float* ap = p.add ? p.add + (long long)z * p.add_sz + (long long)mrow0 * p.c_sm + n : nullptr;
+        if (p.C_lo) csum = store_block_rows<true>(p, stg + lane, cp, p.C_lo + zc + n, mp, ap, bv, nrows);
+        else csum = store_block_rows<false>(p, stg + lane, cp, nullptr, mp, ap, bv, nrows);
+      }
+      if (p.colsum) p.colsum[(long long)z * p.colsum_sz + (long long)(mrow0 >> 5) * p.colsum_ld + n] = csum;
     }
     __syncwarp();
   }
@@ -893,6 +902,7 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
   p.bias = g.epi.bias; p.bias_sz = g.epi.bias_sz;
   p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
   p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
+  p.colsum = g.colsum; p.colsum_sz = g.colsum_sz; p.colsum_ld = g.colsum_ld;
   using SL = SmemLayout<BN>;
   auto kern = gemm_tc_kernel<BN, A_K, B_K, CL>;
   static bool attr_set = false;
@@ -960,6 +970,7 @@ int launch_tc2(const TcGemmProblem& g, cudaStream_t st) {
   p.bias = g.epi.bias; p.bias_sz = g.epi.bias_sz;
   p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
   p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
+  p.colsum = g.colsum; p.colsum_sz = g.colsum_sz; p.colsum_ld = g.colsum_ld;
   using SL = SmemLayout2<BN2>;
   auto kern = gemm_tc2_kernel<BN2, A_K, B_K>;
   static bool attr_set = false;
@@ -1014,11 +1025,15 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   static const int force_cl = getenv("LIP_TC_CLUSTER") ? atoi(getenv("LIP_TC_CLUSTER")) : -1;
   // (measured on B200: correct, but the lock-step coupling costs more than the L2 saving -> off by default)
   const bool cl4 = force_cl == 4;
-  static const int two_cta = getenv("LIP_TC_2CTA") ? atoi(getenv("LIP_TC_2CTA")) : 0;
+  // cta_group::2 policy: -1 (default) = CTA pairs for the JVP-type GEMMs (K-major A, MN-major B) whose M fills whole
+  // 256-row pair tiles - measured faster there (profiles/r01_launches_*), slower for the short-K weight-gradient /
+  // delta-backprop GEMMs; 0 = never; 1 = always (when M > 128)
+  static const int two_cta = getenv("LIP_TC_2CTA") ? atoi(getenv("LIP_TC_2CTA")) : -1;
   static const bool verbose = getenv("LIP_TC_VERBOSE") != nullptr;
   if (verbose) fprintf(stderr, "[lip] gemm_tc M=%lld N=%lld K=%lld K2=%lld batch=%lld a_k=%d b_k=%d two_cta=%d cl4=%d\n", (long long)g.M,
                        (long long)g.N, (long long)g.K, (long long)g.K2, (long long)g.batch, (int)a_k, (int)b_k, two_cta, (int)cl4);
-  const bool use2 = g_tc_force2 >= 0 ? (g_tc_force2 == 1) : (two_cta != 0);
+  const bool auto2 = a_k && !b_k && (g.M % (2 * TBM) == 0);
+  const bool use2 = g_tc_force2 >= 0 ? (g_tc_force2 == 1) : (two_cta < 0 ? auto2 : two_cta != 0);
   if (use2 && g.M > TBM) {
     if (a_k && !b_k) return launch_tc2<128, true, false>(g, st);
     if (!a_k && !b_k) return launch_tc2<128, false, false>(g, st);

@@ -179,13 +179,17 @@ struct Workspace {
   float* lo[2];     // tf32-lo parts (tensor path only)
   float* vs_hi;     // split tangent-weight block of the current layer, [B][in][ldw]
   float* vs_lo;
+  float* colsum;    // per-32-row-block column sums of the delta written by a tcgen05 delta-backprop GEMM: [B][nslots][ldmax]
   size_t per_buf;   // floats
 };
+
+static inline int64_t colsum_slots(const lip_model* m) { return ceil_div(m->M, 128) * 4; }
 
 size_t ws_bytes(const lip_model* m, int64_t B) {
   size_t per = align_up((size_t)B * (size_t)m->M * (size_t)(m->tc_on ? m->ldmax : m->maxw), 64);
   size_t total = 2 * per;
-  if (m->tc_on) total += 2 * per + 2 * align_up((size_t)B * (size_t)m->max_split, 64);
+  if (m->tc_on) total += 2 * per + 2 * align_up((size_t)B * (size_t)m->max_split, 64) +
+                        align_up((size_t)B * (size_t)colsum_slots(m) * (size_t)m->ldmax, 64);
   return total * sizeof(float) + 256;
 }
 
@@ -199,11 +203,12 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
   size_t per = align_up((size_t)B * (size_t)m->M * (size_t)(m->tc_on ? m->ldmax : m->maxw), 64);
   w->per_buf = per;
   w->hi[0] = base; w->hi[1] = base + per;
-  w->lo[0] = w->lo[1] = w->vs_hi = w->vs_lo = nullptr;
+  w->lo[0] = w->lo[1] = w->vs_hi = w->vs_lo = w->colsum = nullptr;
   if (m->tc_on) {
     w->lo[0] = base + 2 * per; w->lo[1] = base + 3 * per;
     size_t vs = align_up((size_t)B * (size_t)m->max_split, 64);
     w->vs_hi = base + 4 * per; w->vs_lo = w->vs_hi + vs;
+    w->colsum = w->vs_lo + vs;
   }
   return LIP_OK;
 }
@@ -277,6 +282,8 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
   int cur = src;
   int cur_ld = m->K;
   bool cur_split = false;
+  bool cur_colsum = false;   // w.colsum holds the column sums of the current delta (written by the GEMM that produced it)
+  const int64_t nslots = colsum_slots(m);
   if (m->tc_on && m->tc_layer[nL - 1]) {
     // the top layer runs on the tensor cores: re-lay Delta_L as padded hi/lo
     const int ldp = pad4(m->K);
@@ -312,10 +319,14 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
       int rc = gemm_simt(p, st);
       if (rc) return rc;
     }
-    {  // bias gradient
+    {  // bias gradient: column sums of Delta_l (from the producing GEMM's epilogue when it was a tcgen05 GEMM)
       dim3 grid((unsigned)ceil_div(Ld.out, 128), (unsigned)B);
-      bias_grad_kernel<<<grid, 128, 0, st>>>(d_hi, d_lo, m->M, Ld.out, cur_ld, out + Ld.boff, m->D, scale,
-                                             add ? add + Ld.boff : nullptr, m->D, add_scale);
+      if (cur_colsum)
+        bias_grad_kernel<<<grid, 128, 0, st>>>(w.colsum, nullptr, nslots, Ld.out, cur_ld, out + Ld.boff, m->D, scale,
+                                               add ? add + Ld.boff : nullptr, m->D, add_scale);
+      else
+        bias_grad_kernel<<<grid, 128, 0, st>>>(d_hi, d_lo, m->M, Ld.out, cur_ld, out + Ld.boff, m->D, scale,
+                                               add ? add + Ld.boff : nullptr, m->D, add_scale);
       LIP_LAUNCH_CHECK();
     }
     if (l > 0) {  // Delta_{l-1} = (Delta_l W_l^T) * phi'_{l-1}
@@ -331,6 +342,7 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
         p.B1.major_k = 1; p.b_batched = 0;
         p.C = w.hi[nxt]; p.C_lo = next_split ? w.lo[nxt] : nullptr; p.c_sz = m->M * (int64_t)nxt_ld; p.c_sm = nxt_ld;
         p.epi.mask = m->dphi[l - 1]; p.epi.mask_sm = Ld.in;
+        p.colsum = w.colsum; p.colsum_ld = nxt_ld; p.colsum_sz = nslots * (int64_t)nxt_ld;
         int rc = gemm_tc(p, st);
         if (rc) return rc;
       } else {
@@ -344,7 +356,7 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
         int rc = gemm_simt(p, st);
         if (rc) return rc;
       }
-      cur = nxt; cur_ld = nxt_ld; cur_split = next_split;
+      cur = nxt; cur_ld = nxt_ld; cur_split = next_split; cur_colsum = tc;
     }
   }
   return LIP_OK;

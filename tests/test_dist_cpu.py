@@ -1,0 +1,95 @@
+"""Host-side multi-GPU logic on CPU: probe sharding + the single all-reduce of the accumulators,
+exercised with world_size 2 over gloo.  The operator is a CPU stand-in (a dense symmetric matrix) — the sharding
+layer treats the matvec as opaque, exactly as the estimators treat `Xfun`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import lip_b200  # noqa: F401
+from lip_b200 import _dist
+
+
+def test_probe_slice_partitions_every_row_once():
+    for B in (0, 1, 2, 5, 64, 257):
+        for ws in (1, 2, 3, 8):
+            rows = []
+            sizes = []
+            for r in range(ws):
+                s = _dist.probe_slice(B, r, ws)
+                rows += list(range(B))[s]
+                sizes.append(s.stop - s.start)
+            assert rows == list(range(B))
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        _dist.probe_slice(4, 2, 2)
+
+
+def test_single_process_is_a_plain_mean():
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(12, 12, generator=g)
+    A = A @ A.T
+    E = torch.randint(0, 2, (10, 12), generator=g).float() * 2 - 1
+    got = _dist.hutchinson_sharded(lambda v: A @ v, E)
+    ref = torch.stack([e @ (A @ e) for e in E]).mean()
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, ws, port, B, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = _dist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, ws) and _dist.world() == (rank, ws)
+    g = torch.Generator().manual_seed(1)               # identical inputs on every rank (probes are inputs)
+    A = torch.randn(40, 40, generator=g)
+    A = A @ A.T + 40 * torch.eye(40)
+    E = torch.randint(0, 2, (B, 40), generator=g).float() * 2 - 1
+    calls = []
+
+    def Xfun(V):                                        # batched closure: sees only this rank's rows
+        calls.append(V.shape[0])
+        return V @ A
+    Xfun._lip_batched = True
+    tr = _dist.hutchinson_sharded(Xfun, E)
+
+    def integrand(matvec, V):                           # an SLQ-like per-probe scalar: v . log-ish quadratic form
+        return (V * matvec(V)).sum(1).log()
+    integrand._lip_batched = True
+    lq = _dist.slq_sharded(integrand, Xfun, E)
+    out[rank] = (float(tr), float(lq), sum(calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [7, 1])
+def test_world_size_2_gloo_matches_single_process(B):
+    ws = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(ws, port, B, out), nprocs=ws, join=True)
+        res = dict(out)
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(40, 40, generator=g)
+    A = A @ A.T + 40 * torch.eye(40)
+    E = torch.randint(0, 2, (B, 40), generator=g).float() * 2 - 1
+    quad = (E * (E @ A)).sum(1)
+    ref_tr, ref_lq = float(quad.mean()), float(quad.log().mean())
+    for r in range(ws):
+        tr, lq, _ = res[r]
+        assert abs(tr - ref_tr) <= 1e-5 * abs(ref_tr)
+        assert abs(lq - ref_lq) <= 1e-5 * abs(ref_lq)
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]       # every rank holds the same global estimate
+    # each estimator call pushes a rank's own rows once: 2 calls x rows owned
+    owned = [(_dist.probe_slice(B, r, ws).stop - _dist.probe_slice(B, r, ws).start) for r in range(ws)]
+    assert [res[r][2] for r in range(ws)] == [2 * o for o in owned]
