@@ -34,21 +34,29 @@ typedef enum {
   LIP_ERR_NOT_BOUND = -5
 } lip_status;
 
-/* layer program ops.  Round 1 executes DENSE + activations (models M1/M2 of SURVEY.md 8a:
- * src/toymodels.py:4-37, src/scalemodels.py:52-67); the conv ops are reserved for M3/M4. */
+/* layer program ops.  Dense/activation chains are models M1/M2 of SURVEY.md 8a (src/toymodels.py:4-37,
+ * src/scalemodels.py:52-67); INPUT/ZEROPAD/CONV2D/AVGPOOL2/FLATTEN add model M3, LeNet5 (src/scalemodels.py:11-49).
+ * Images are NHWC, conv kernels HWIO (flax), stride 1, VALID after the explicit ZEROPAD. */
 typedef enum {
   LIP_OP_DENSE = 0,      /* y = x @ kernel[in,out] + bias[out]   (flax nn.Dense) */
   LIP_OP_TANH = 1,
   LIP_OP_GELU_TANH = 2,  /* flax nn.gelu(approximate=True) */
-  LIP_OP_RELU = 3
+  LIP_OP_RELU = 3,
+  LIP_OP_CONV2D = 4,     /* y = conv(x, kernel[kh,kw,cin,cout]) + bias[cout], stride 1, VALID (flax nn.Conv) */
+  LIP_OP_AVGPOOL2 = 5,   /* nn.avg_pool(window (2,2), strides (2,2)) */
+  LIP_OP_ZEROPAD = 6,    /* jnp.pad(x, ((0,0),(p,p),(p,p),(0,0))) */
+  LIP_OP_FLATTEN = 7,    /* x.reshape(batch, -1) of an NHWC image (a no-op on the memory layout) */
+  LIP_OP_INPUT = 8       /* declares an image input: kh = height, kw = width, in_features = channels (first op) */
 } lip_op;
 
 typedef struct {
   int32_t op;            /* lip_op */
-  int32_t in_features;   /* DENSE only */
-  int32_t out_features;  /* DENSE only */
-  int64_t bias_offset;   /* DENSE: offset of bias[out] in the flat parameter vector */
-  int64_t kernel_offset; /* DENSE: offset of kernel[in,out] in the flat parameter vector */
+  int32_t in_features;   /* DENSE: in; CONV2D: cin; INPUT: channels */
+  int32_t out_features;  /* DENSE: out; CONV2D: cout */
+  int64_t bias_offset;   /* DENSE / CONV2D: offset of bias[out] in the flat parameter vector */
+  int64_t kernel_offset; /* DENSE: offset of kernel[in,out]; CONV2D: of kernel[kh,kw,cin,cout] */
+  int32_t kh, kw;        /* CONV2D: kernel height / width; INPUT: image height / width */
+  int32_t stride, pad;   /* CONV2D: stride (1); ZEROPAD: zero rows / columns added on each side */
 } lip_layer_desc;
 
 typedef enum { LIP_REGRESSOR = 0, LIP_CLASSIFIER = 1 } lip_model_type;

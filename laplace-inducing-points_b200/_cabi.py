@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "liblip_b200.so")
 LIP_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOT_BOUND = -1, -2, -3, -4, -5
 OP_DENSE, OP_TANH, OP_GELU_TANH, OP_RELU = 0, 1, 2, 3
+OP_CONV2D, OP_AVGPOOL2, OP_ZEROPAD, OP_FLATTEN, OP_INPUT = 4, 5, 6, 7, 8
 REGRESSOR, CLASSIFIER = 0, 1
 FACTOR_NONE, FACTOR_SQRT = 0, 1
 FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY = 0, 1, 2, 3
@@ -18,7 +19,8 @@ FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY = 0, 1, 2, 3
 
 class LayerDesc(C.Structure):
     _fields_ = [("op", C.c_int32), ("in_features", C.c_int32), ("out_features", C.c_int32),
-                ("bias_offset", C.c_int64), ("kernel_offset", C.c_int64)]
+                ("bias_offset", C.c_int64), ("kernel_offset", C.c_int64),
+                ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t

@@ -81,6 +81,71 @@ class MLPSpec:
         return arr, len(out)
 
 
+class ConvProgramSpec:
+    """A conv stage program (INPUT, ZEROPAD, CONV2D, act, AVGPOOL2, FLATTEN, DENSE ...) with parameter offsets taken
+    from the reference's flat order (sorted module names: Conv_i before Dense_i; inside a module bias before kernel).
+
+    ops: list of tuples
+        ("input", H, W, C) | ("pad", p) | ("conv", module_name, kh, kw, cin, cout) | ("act", op) | ("pool",) |
+        ("flatten",) | ("dense", module_name, nin, nout)
+    """
+
+    def __init__(self, ops, model_type: str, name: str = "conv"):
+        self.ops = list(ops)
+        self.model_type = model_type
+        self.name = name
+        sizes = {}
+        for op in self.ops:
+            if op[0] == "conv":
+                _, mod, kh, kw, cin, cout = op
+                sizes[mod] = (cout, kh * kw * cin * cout)
+            elif op[0] == "dense":
+                _, mod, nin, nout = op
+                sizes[mod] = (nout, nin * nout)
+        self.offsets = {}
+        off = 0
+        for mod in sorted(sizes):                       # ravel_pytree: sorted keys; leaves 'bias' < 'kernel'
+            nb, nk = sizes[mod]
+            self.offsets[mod] = (off, off + nb)
+            off += nb + nk
+        self.num_params = off
+        inp = self.ops[0]
+        if inp[0] != "input":
+            raise ValueError("a conv program starts with ('input', H, W, C)")
+        self.in_shape = tuple(inp[1:4])
+        self.in_features = int(inp[1] * inp[2] * inp[3])
+        last = [op for op in self.ops if op[0] == "dense"][-1]
+        self.num_outputs = int(last[3])
+        self.layers = [op for op in self.ops if op[0] in ("conv", "dense")]
+
+    def descs(self):
+        out = []
+        for op in self.ops:
+            k = op[0]
+            if k == "input":
+                out.append(cabi.LayerDesc(cabi.OP_INPUT, op[3], 0, 0, 0, op[1], op[2], 0, 0))
+            elif k == "pad":
+                out.append(cabi.LayerDesc(cabi.OP_ZEROPAD, 0, 0, 0, 0, 0, 0, 0, op[1]))
+            elif k == "conv":
+                _, mod, kh, kw, cin, cout = op
+                boff, woff = self.offsets[mod]
+                out.append(cabi.LayerDesc(cabi.OP_CONV2D, cin, cout, boff, woff, kh, kw, 1, 0))
+            elif k == "act":
+                out.append(cabi.LayerDesc(op[1], 0, 0, 0, 0))
+            elif k == "pool":
+                out.append(cabi.LayerDesc(cabi.OP_AVGPOOL2, 0, 0, 0, 0))
+            elif k == "flatten":
+                out.append(cabi.LayerDesc(cabi.OP_FLATTEN, 0, 0, 0, 0))
+            elif k == "dense":
+                _, mod, nin, nout = op
+                boff, woff = self.offsets[mod]
+                out.append(cabi.LayerDesc(cabi.OP_DENSE, nin, nout, boff, woff))
+            else:
+                raise ValueError(f"unknown program op {op!r}")
+        arr = (cabi.LayerDesc * len(out))(*out)
+        return arr, len(out)
+
+
 class BoundModel:
     """lip_model handle bound to (theta, Z): owns the activation cache; exposes the probe-batched operators."""
 
@@ -95,10 +160,11 @@ class BoundModel:
         Zf = dev_f32(Z, self.device)
         self.M = int(Zf.shape[0])
         self.Z = Zf.reshape(self.M, -1)
-        if self.Z.shape[1] != spec.dims[0]:
-            raise ValueError(f"points have {self.Z.shape[1]} features, model expects {spec.dims[0]}")
+        in_features = spec.in_features if hasattr(spec, "in_features") else spec.dims[0]
+        if self.Z.shape[1] != in_features:
+            raise ValueError(f"points have {self.Z.shape[1]} features, model expects {in_features}")
         self.D = spec.num_params
-        self.K = spec.dims[-1]
+        self.K = spec.num_outputs if hasattr(spec, "num_outputs") else spec.dims[-1]
         self.model_type = spec.model_type
         self.logvar = float(logvar)
         arr, n = spec.descs()
@@ -117,6 +183,8 @@ class BoundModel:
     def path_name(self) -> str:
         n = cabi.lib().lip_model_tensor_layers(self._h)
         total = len(self.spec.layers)
+        if isinstance(self.spec, ConvProgramSpec):
+            return f"im2col + simt-fp32 ({total} conv/dense stages)"
         return f"tcgen05-3xtf32 ({n}/{total} layers) + simt-fp32" if n else "simt-fp32"
 
     # ---- helpers ----

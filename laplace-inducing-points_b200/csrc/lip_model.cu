@@ -11,56 +11,9 @@
 #include <new>
 
 #include "lip_common.cuh"
+#include "lip_model.cuh"
 
 using namespace lip;
-
-struct DenseLayer {
-  int in = 0, out = 0;
-  int64_t boff = 0, woff = 0;
-  int act = -1;  // activation applied to this layer's output (-1: none / last layer)
-};
-
-struct lip_model {
-  std::vector<DenseLayer> L;
-  int model_type = LIP_CLASSIFIER;
-  int64_t D = 0;
-  int K = 0;
-  int maxw = 0;  // widest layer output
-  // bound state
-  bool bound = false;
-  int64_t M = 0;
-  const float* theta = nullptr;
-  float logvar = 0.f;
-  std::vector<float*> A;     // A[l]: input of layer l, [M, in_l]   (A[0] = Z)
-  std::vector<float*> dphi;  // dphi[l]: phi'(h_l) at the output of layer l (l < nL-1), [M, out_l]
-  float* logits = nullptr;   // [M, K]
-  float* P = nullptr;        // softmax(logits)
-  float* S = nullptr;        // sqrt(P)
-  int use_tc = -1;           // -1 auto (tcgen05 when the device is sm_100), 0 SIMT only, 1 tcgen05
-  bool tc_on = false;        // decided at bind time
-  // tcgen05 operands: TF32 hi/lo splits of the cached activations and of the weights (ld padded to 4)
-  std::vector<float*> A_hi, A_lo, W_hi, W_lo;
-  std::vector<int64_t> A_ld, W_ld;
-  std::vector<char> tc_layer;   // layer l runs its three GEMMs on the tensor cores
-  int64_t max_split = 0;        // max over tc layers of in * ldw (floats per probe of the split tangent block)
-  int ldmax = 0;                // widest padded intermediate row
-
-  void free_cache() {
-    for (auto p : A) if (p) cudaFree(p);
-    for (auto p : dphi) if (p) cudaFree(p);
-    for (auto p : A_hi) if (p) cudaFree(p);
-    for (auto p : A_lo) if (p) cudaFree(p);
-    for (auto p : W_hi) if (p) cudaFree(p);
-    for (auto p : W_lo) if (p) cudaFree(p);
-    A.clear(); dphi.clear(); A_hi.clear(); A_lo.clear(); W_hi.clear(); W_lo.clear(); A_ld.clear(); W_ld.clear();
-    tc_layer.clear(); tc_on = false; max_split = 0;
-    if (logits) cudaFree(logits);
-    if (P) cudaFree(P);
-    if (S) cudaFree(S);
-    logits = P = S = nullptr;
-    bound = false;
-  }
-};
 
 namespace {
 
@@ -138,6 +91,28 @@ __global__ void bias_grad_kernel(const float* __restrict__ Delta, const float* _
   out[(int64_t)b * out_sz + j] = v;
 }
 
+// Tall-skinny contiguous case (conv stages: rows = points x pixels, n = channels, ld == n): one CTA per batch entry, the
+// thread count is a multiple of n so every thread always sees the same column of the flat [rows * n] array.
+__global__ void colsum_flat_kernel(const float* __restrict__ Delta, long long rows, int n, float* __restrict__ out,
+                                   long long out_sz, float scale, const float* __restrict__ add, long long add_sz,
+                                   float add_scale) {
+  extern __shared__ float sm[];
+  const long long b = blockIdx.x;
+  const float* d = Delta + b * rows * n;
+  const long long total = rows * n;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) acc += __ldg(d + i);
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    float t = 0.f;
+    for (int k = threadIdx.x; k < (int)blockDim.x; k += n) t += sm[k];
+    float v = scale * t;
+    if (add) v += add_scale * add[b * add_sz + threadIdx.x];
+    out[b * out_sz + threadIdx.x] = v;
+  }
+}
+
 __global__ void onehot_rows_kernel(float* __restrict__ U, int64_t d, int64_t start, int64_t blk) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= blk * d) return;
@@ -152,6 +127,39 @@ __global__ void symmetrize_from_lower_kernel(float* __restrict__ G, int64_t d) {
   if (idx >= d * d) return;
   int64_t r = idx / d, c = idx % d;
   if (r < c) G[r * d + c] = G[c * d + r];
+}
+
+}  // namespace
+
+namespace lip {
+int launch_bias_grad(const float* Delta, const float* Delta_lo, int64_t rows, int n, int64_t ld, int64_t B, float* out,
+                     int64_t out_sz, float scale, const float* add, int64_t add_sz, float add_scale, cudaStream_t st) {
+  if (!Delta_lo && ld == n && n <= 64 && rows >= 2048) {
+    const int threads = n * (1024 / n);
+    colsum_flat_kernel<<<(unsigned)B, threads, threads * sizeof(float), st>>>(Delta, rows, n, out, out_sz, scale, add, add_sz,
+                                                                              add_scale);
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
+  for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+    const int64_t bc = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((unsigned)ceil_div(n, 128), (unsigned)bc);
+    bias_grad_kernel<<<grid, 128, 0, st>>>(Delta + b0 * rows * ld, Delta_lo ? Delta_lo + b0 * rows * ld : nullptr, rows, n, ld,
+                                           out + b0 * out_sz, out_sz, scale, add ? add + b0 * add_sz : nullptr, add_sz,
+                                           add_scale);
+    LIP_LAUNCH_CHECK();
+  }
+  return LIP_OK;
+}
+int launch_scale_copy(const float* in, float* out, int64_t n, float scale, cudaStream_t st) {
+  scale_copy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(in, out, n, scale);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+int launch_softmax(const float* logits, float* P, float* S, int64_t M, int K, cudaStream_t st) {
+  softmax_rows_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(logits, P, S, M, K);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
 }
 
 int launch_factor(const float* in, float* out, const lip_model* m, int64_t B, int mode, float scale,
@@ -172,6 +180,9 @@ int launch_factor(const float* in, float* out, const lip_model* m, int64_t B, in
   return LIP_OK;
 }
 
+}  // namespace lip
+
+namespace {
 static inline int pad4(int x) { return (x + 3) / 4 * 4; }
 
 struct Workspace {
@@ -378,6 +389,17 @@ int lip_model_create(const lip_layer_desc* layers, int32_t n_layers, int32_t mod
   LIP_REQUIRE(m != nullptr, "lip_model_create: out of host memory");
   m->model_type = model_type;
   m->D = num_params;
+  if (layers[0].op == LIP_OP_INPUT) {   // conv stage program (lip_cnn.cu)
+    int rc = cnn_parse(m, layers, n_layers, num_params);
+    if (rc) { delete m; return rc; }
+    if (model_type == LIP_REGRESSOR && m->K != 1) {
+      delete m;
+      set_error("lip_model_create: regressors must have one output");
+      return LIP_ERR_INVALID;
+    }
+    *out = m;
+    return LIP_OK;
+  }
   int64_t counted = 0;
   for (int i = 0; i < n_layers; ++i) {
     const lip_layer_desc& d = layers[i];
@@ -468,6 +490,7 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
   m->M = M;
   m->theta = theta;
   m->logvar = logvar;
+  if (m->is_cnn) return cnn_bind(m, theta, Z, M, st);
   const int nL = (int)m->L.size();
   m->A.assign(nL, nullptr);
   m->dphi.assign(nL > 1 ? nL - 1 : 0, nullptr);
@@ -551,7 +574,7 @@ int lip_model_outputs(lip_model* m, float* out, lip_stream_t stream) {
 
 size_t lip_workspace_bytes(const lip_model* m, int64_t B) {
   if (!m || !m->bound || B <= 0) return 0;
-  return ws_bytes(m, B);
+  return m->is_cnn ? cnn_ws_bytes(m, B) : ws_bytes(m, B);
 }
 
 int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* workspace,
@@ -560,6 +583,7 @@ int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal,
   LIP_REQUIRE(V != out, "lip_ggn_vp: in-place operation is not supported");
   if (!m->bound) { set_error("lip_ggn_vp: model not bound"); return LIP_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_cnn) return cnn_ggn_vp(m, V, out, B, recal, alpha, workspace, workspace_bytes, st);
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
@@ -581,6 +605,7 @@ int lip_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scal
   LIP_REQUIRE(m && V && out && B > 0, "lip_wt_apply: null argument or B <= 0");
   if (!m->bound) { set_error("lip_wt_apply: model not bound"); return LIP_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_cnn) return cnn_wt_apply(m, V, out, B, scale, factor, workspace, workspace_bytes, st);
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
@@ -602,6 +627,7 @@ int lip_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale
   LIP_REQUIRE(m && U && out && B > 0, "lip_w_apply: null argument or B <= 0");
   if (!m->bound) { set_error("lip_w_apply: model not bound"); return LIP_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_cnn) return cnn_w_apply(m, U, out, B, scale, factor, add, add_scale, workspace, workspace_bytes, st);
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
@@ -622,7 +648,7 @@ int lip_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale
 size_t lip_gram_workspace_bytes(const lip_model* m, int64_t block) {
   if (!m || !m->bound || block <= 0) return 0;
   size_t d = (size_t)m->M * m->K;
-  return ws_bytes(m, block) + align_up(sizeof(float) * (size_t)block * d, 256) +
+  return (m->is_cnn ? cnn_ws_bytes(m, block) : ws_bytes(m, block)) + align_up(sizeof(float) * (size_t)block * d, 256) +
          align_up(sizeof(float) * (size_t)block * (size_t)m->D, 256) + 512;
 }
 

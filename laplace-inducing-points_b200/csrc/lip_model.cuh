@@ -1,0 +1,98 @@
+// lip_model.cuh — the model handle shared by the MLP path (lip_model.cu) and the conv stage-program path (lip_cnn.cu).
+#pragma once
+#include <vector>
+
+#include "lip_common.cuh"
+
+struct DenseLayer {
+  int in = 0, out = 0;
+  int64_t boff = 0, woff = 0;
+  int act = -1;  // activation applied to this layer's output (-1: none / last layer)
+};
+
+// One affine stage of a conv program: CONV2D (as a GEMM over im2col patches) or DENSE, + activation + optional 2x2 avg-pool.
+struct ConvStage {
+  int type = 0;          // 0 dense, 1 conv
+  int act = -1;          // activation after the affine op (-1 none)
+  int pool = 0;          // 1: nn.avg_pool 2x2 after the activation
+  int Hi = 1, Wi = 1, cin = 0, pad = 0, kh = 1, kw = 1, Ho = 1, Wo = 1, cout = 0, Hp = 1, Wp = 1;
+  int64_t boff = 0, woff = 0;
+  int P = 1;             // GEMM rows per point: Ho*Wo (1 for dense)
+  int Kc = 0;            // contraction length: kh*kw*cin (in_features for dense)
+  float* Aop = nullptr;  // bound cache: [M*P, Kc] im2col patches (conv) or the stage input (dense)
+  float* dphi = nullptr; // bound cache: [M*P, cout] activation derivative (null for the last stage)
+  int64_t out_per_point() const { return pool ? (int64_t)Hp * Wp * cout : (int64_t)P * cout; }
+};
+
+struct lip_model {
+  std::vector<DenseLayer> L;
+  int model_type = LIP_CLASSIFIER;
+  int64_t D = 0;
+  int K = 0;
+  int maxw = 0;  // widest layer output
+  // bound state
+  bool bound = false;
+  int64_t M = 0;
+  const float* theta = nullptr;
+  float logvar = 0.f;
+  std::vector<float*> A;     // A[l]: input of layer l, [M, in_l]   (A[0] = Z)
+  std::vector<float*> dphi;  // dphi[l]: phi'(h_l) at the output of layer l (l < nL-1), [M, out_l]
+  float* logits = nullptr;   // [M, K]
+  float* P = nullptr;        // softmax(logits)
+  float* S = nullptr;        // sqrt(P)
+  int use_tc = -1;           // -1 auto (tcgen05 when the device is sm_100), 0 SIMT only, 1 tcgen05
+  bool tc_on = false;        // decided at bind time
+  // tcgen05 operands: TF32 hi/lo splits of the cached activations and of the weights (ld padded to 4)
+  std::vector<float*> A_hi, A_lo, W_hi, W_lo;
+  std::vector<int64_t> A_ld, W_ld;
+  std::vector<char> tc_layer;   // layer l runs its three GEMMs on the tensor cores
+  int64_t max_split = 0;        // max over tc layers of in * ldw (floats per probe of the split tangent block)
+  int ldmax = 0;                // widest padded intermediate row
+
+  // ---- conv stage programs (LeNet5, src/scalemodels.py:11-49): see lip_cnn.cu ----
+  bool is_cnn = false;
+  int in_h = 0, in_w = 0, in_c = 0;      // NHWC input image
+  std::vector<ConvStage> CS;   // stages of a conv program
+  float* cnn_tmp_out = nullptr;          // bind-time scratch
+  float* cnn_tmp_x = nullptr;
+
+  void free_cnn_cache();
+  void free_cache() {
+    free_cnn_cache();
+    for (auto p : A) if (p) cudaFree(p);
+    for (auto p : dphi) if (p) cudaFree(p);
+    for (auto p : A_hi) if (p) cudaFree(p);
+    for (auto p : A_lo) if (p) cudaFree(p);
+    for (auto p : W_hi) if (p) cudaFree(p);
+    for (auto p : W_lo) if (p) cudaFree(p);
+    A.clear(); dphi.clear(); A_hi.clear(); A_lo.clear(); W_hi.clear(); W_lo.clear(); A_ld.clear(); W_ld.clear();
+    tc_layer.clear(); tc_on = false; max_split = 0;
+    if (logits) cudaFree(logits);
+    if (P) cudaFree(P);
+    if (S) cudaFree(S);
+    logits = P = S = nullptr;
+    bound = false;
+  }
+};
+
+
+namespace lip {
+// small shared launchers (defined in lip_model.cu)
+int launch_factor(const float* in, float* out, const lip_model* m, int64_t B, int mode, float scale, cudaStream_t st);
+// gb[b][j] = scale * sum_{r<rows} Delta[b][r][j] (+ Delta_lo) + add_scale * add[b][j];  Delta rows have stride ld
+int launch_bias_grad(const float* Delta, const float* Delta_lo, int64_t rows, int n, int64_t ld, int64_t B, float* out,
+                     int64_t out_sz, float scale, const float* add, int64_t add_sz, float add_scale, cudaStream_t st);
+int launch_scale_copy(const float* in, float* out, int64_t n, float scale, cudaStream_t st);
+int launch_softmax(const float* logits, float* P, float* S, int64_t M, int K, cudaStream_t st);
+
+// conv stage-program path (lip_cnn.cu)
+int cnn_parse(lip_model* m, const lip_layer_desc* layers, int32_t n_layers, int64_t num_params);
+int cnn_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaStream_t st);
+size_t cnn_ws_bytes(const lip_model* m, int64_t B);
+int cnn_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* ws, size_t bytes,
+               cudaStream_t st);
+int cnn_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scale, int32_t factor, void* ws, size_t bytes,
+                 cudaStream_t st);
+int cnn_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,
+                float add_scale, void* ws, size_t bytes, cudaStream_t st);
+}  // namespace lip

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _cabi as cabi
-from ._runtime import BoundModel, MLPSpec, dev_f32
+from ._runtime import BoundModel, ConvProgramSpec, MLPSpec, dev_f32
 from .utils import flatten_nn_params
 
 _ACT_BY_CLASS = {"SimpleRegressor": cabi.OP_GELU_TANH, "SimpleClassifier": cabi.OP_TANH,
@@ -40,8 +40,10 @@ def _spec_from(module, params, model_type) -> MLPSpec:
     """Pattern-match the parameter tree + module class onto the layer program the CUDA library executes.
     Anything that is not a Dense/activation stack is rejected loudly (no fallback)."""
     cls = type(module).__name__ if module is not None else None
-    if cls in ("LeNet5", "ResNet1M"):
-        raise NotImplementedError(f"{cls}: conv JVP/VJP kernels are not built yet (SURVEY §8a M3/M4)")
+    if cls == "ResNet1M":
+        raise NotImplementedError("ResNet1M: conv/BN/residual JVP/VJP kernels are not built yet (SURVEY §8a M4)")
+    if cls == "LeNet5":
+        return _lenet5_spec(params, model_type)
     act = None
     if module is not None and isinstance(getattr(module, "activation", None), str):
         act = _ACT_BY_NAME.get(module.activation)
@@ -69,6 +71,31 @@ def _spec_from(module, params, model_type) -> MLPSpec:
             dims.append(int(kin))
         dims.append(int(kout))
     return MLPSpec(dims, act, model_type)
+
+
+def _lenet5_spec(params, model_type) -> ConvProgramSpec:
+    """scalemodels.py:11-49: pad 28->32, conv5x5(6) VALID -> relu -> avgpool2, conv5x5(16) -> relu -> avgpool2,
+    flatten (HWC) = 400 -> 120 -> 84 -> 10 with relu.  The parameter tree is checked against that geometry."""
+    tree = _strip(params)
+    expect = {"Conv_0": (5, 5, 1, 6), "Conv_1": (5, 5, 6, 16), "Dense_0": (400, 120), "Dense_1": (120, 84)}
+    if sorted(tree.keys()) != ["Conv_0", "Conv_1", "Dense_0", "Dense_1", "Dense_2"]:
+        raise ValueError(f"LeNet5: unexpected parameter tree keys {sorted(tree.keys())}")
+    for name, shp in expect.items():
+        leaf = tree[name]
+        if sorted(leaf.keys()) != ["bias", "kernel"] or tuple(leaf["kernel"].shape) != shp:
+            raise ValueError(f"LeNet5: {name} must hold bias + kernel{shp}, got "
+                             f"{ {k: tuple(v.shape) for k, v in leaf.items()} }")
+    k2 = tuple(tree["Dense_2"]["kernel"].shape)
+    if k2[0] != 84:
+        raise ValueError(f"LeNet5: Dense_2 kernel {k2}")
+    ops = [("input", 28, 28, 1), ("pad", 2),
+           ("conv", "Conv_0", 5, 5, 1, 6), ("act", cabi.OP_RELU), ("pool",),
+           ("conv", "Conv_1", 5, 5, 6, 16), ("act", cabi.OP_RELU), ("pool",),
+           ("flatten",),
+           ("dense", "Dense_0", 400, 120), ("act", cabi.OP_RELU),
+           ("dense", "Dense_1", 120, 84), ("act", cabi.OP_RELU),
+           ("dense", "Dense_2", 84, int(k2[1]))]
+    return ConvProgramSpec(ops, model_type, name="LeNet5")
 
 
 def _logvar_of(params) -> float:

@@ -1,8 +1,8 @@
 """Architecture descriptors mirroring /root/reference/src/scalemodels.py.
 
-LargeClassifier (scalemodels.py:52-67) runs on the CUDA path.  LeNet5 / ResNet1M (scalemodels.py:11-49,
-70-157) are declared so that configs parse, but the conv JVP/VJP kernels are a later SURVEY §8 row:
-binding them raises NotImplementedError loudly (no fallback)."""
+LargeClassifier (scalemodels.py:52-67) and LeNet5 (scalemodels.py:11-49) run on the CUDA path.  ResNet1M
+(scalemodels.py:70-157) is declared so that configs parse, but its conv/BN/residual JVP/VJP kernels are a later
+SURVEY §8 row: binding it raises NotImplementedError loudly (no fallback)."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field
@@ -30,8 +30,28 @@ class LargeClassifier(_MLPBase):
 
 
 class LeNet5:
-    def apply(self, *a, **k):
-        raise NotImplementedError("LeNet5: conv JVP/VJP kernels are not built yet (SURVEY §8a M3)")
+    """scalemodels.py:11-49.  Runs on the CUDA path as a conv stage program (csrc/lip_cnn.cu)."""
+    model_type = "classifier"
+
+    def init(self, seed, x=None):
+        """Synthetic initialisation (kernel ~ N(0, 1/fan_in), bias ~ N(0, 0.01^2)); flax-style variables."""
+        import math
+        rng = np.random.default_rng(int(seed))
+
+        def conv(kh, kw, ci, co):
+            return {"bias": (0.01 * rng.standard_normal(co)).astype(np.float32),
+                    "kernel": (rng.standard_normal((kh, kw, ci, co)) / math.sqrt(kh * kw * ci)).astype(np.float32)}
+
+        def dense(i, o):
+            return {"bias": (0.01 * rng.standard_normal(o)).astype(np.float32),
+                    "kernel": (rng.standard_normal((i, o)) / math.sqrt(i)).astype(np.float32)}
+
+        return {"params": {"Conv_0": conv(5, 5, 1, 6), "Conv_1": conv(5, 5, 6, 16), "Dense_0": dense(400, 120),
+                           "Dense_1": dense(120, 84), "Dense_2": dense(84, 10)}}
+
+    def apply(self, variables, x, *args, train=False, mutable=False, **kwargs):
+        from .ggn import _bind_variables
+        return _bind_variables(self, variables, x).outputs()
 
 
 @dataclass

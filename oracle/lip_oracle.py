@@ -59,6 +59,12 @@ def model_outputs(state: OracleState, Z) -> np.ndarray:
         return _model_fn(state, Z)(_t(theta)).numpy()
 
 
+def jvp_outputs(state: OracleState, X, w) -> np.ndarray:
+    """lla.py:153: jax.jvp(lambda p: model(p, X), (theta,), (w,))[1]  ->  J_X w, shape [n, K]."""
+    theta, _ = state.flat()
+    return torch.func.jvp(_model_fn(state, X), (_t(theta),), (_t(w),))[1].detach().numpy()
+
+
 def jacobians(state: OracleState, Z) -> np.ndarray:
     """Explicit per-point Jacobians J[i] = d f(z_i;theta)/d theta, shape [M, K, D] (ground truth)."""
     theta, _ = state.flat()

@@ -10,8 +10,8 @@ def rel_err(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def make_pair(kind, *, hidden, n_out, in_dim, seed, logvar=0.0, toy_layout=False, in_shape=None):
-    """kind: 'regressor' | 'classifier' | 'large'.  Returns (oracle_state, lip_state)."""
+def make_pair(kind, *, hidden=(), n_out=10, in_dim=0, seed=0, logvar=0.0, toy_layout=False, in_shape=None):
+    """kind: 'regressor' | 'classifier' | 'large' | 'lenet5'.  Returns (oracle_state, lip_state)."""
     import lip_b200  # noqa: F401
     from lip_b200 import scalemodels, toymodels
 
@@ -25,6 +25,9 @@ def make_pair(kind, *, hidden, n_out, in_dim, seed, logvar=0.0, toy_layout=False
         shp = tuple(in_shape) if in_shape else (in_dim,)
         om = OM.OracleModel("large_classifier", shp, list(hidden), n_out, "classifier")
         mod = scalemodels.LargeClassifier(shp, list(hidden), len(hidden), n_out)
+    elif kind == "lenet5":
+        om = OM.LeNet5()
+        mod = scalemodels.LeNet5()
     else:
         raise ValueError(kind)
     variables = om.init(seed)

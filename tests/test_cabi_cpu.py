@@ -89,3 +89,61 @@ def test_host_spec_and_layout_without_gpu():
     assert (nin, nout, boff, woff) == (1024, 512, 1024 + 784 * 1024, 1024 + 784 * 1024 + 512)
     arr, n = spec.descs()
     assert n == 9 and arr[1].op == cb.OP_TANH and arr[8].op == cb.OP_DENSE
+
+
+def _lenet_program(cabi):
+    import lip_b200  # noqa: F401
+    from lip_b200._runtime import ConvProgramSpec
+    ops = [("input", 28, 28, 1), ("pad", 2),
+           ("conv", "Conv_0", 5, 5, 1, 6), ("act", cabi.OP_RELU), ("pool",),
+           ("conv", "Conv_1", 5, 5, 6, 16), ("act", cabi.OP_RELU), ("pool",), ("flatten",),
+           ("dense", "Dense_0", 400, 120), ("act", cabi.OP_RELU), ("dense", "Dense_1", 120, 84), ("act", cabi.OP_RELU),
+           ("dense", "Dense_2", 84, 10)]
+    return ConvProgramSpec(ops, "classifier", name="LeNet5")
+
+
+def test_conv_program_create_and_layout(cabi):
+    """LeNet5 (scalemodels.py:11-49) as a conv stage program: accepted by lip_model_create (host-only call), D = 61706,
+    and the module offsets follow the reference's flat order (utils.py:12-17), checked against the oracle's flatten."""
+    import ctypes as C
+    from oracle import models as OM
+    L = cabi.lib()
+    spec = _lenet_program(cabi)
+    assert spec.num_params == 61706 and spec.in_features == 784 and spec.num_outputs == 10
+    arr, n = spec.descs()
+    h = C.c_void_p()
+    assert L.lip_model_create(arr, n, cabi.CLASSIFIER, spec.num_params, C.byref(h)) == 0, L.lip_last_error()
+    assert L.lip_model_num_params(h) == 61706 and L.lip_model_num_outputs(h) == 10
+    assert L.lip_model_destroy(h) == 0
+    # offsets vs the oracle's ravel order: fill each leaf with a distinct constant and look it up in the flat vector
+    om = OM.LeNet5()
+    variables = om.init(0)
+    code = {}
+    for i, mod in enumerate(sorted(variables["params"])):
+        for j, leaf in enumerate(sorted(variables["params"][mod])):
+            variables["params"][mod][leaf][...] = 10 * i + j
+            code[(mod, leaf)] = 10 * i + j
+    flat, _ = OM.flatten_nn_params(variables["params"])
+    for mod, (boff, woff) in spec.offsets.items():
+        assert flat[boff] == code[(mod, "bias")] and flat[woff] == code[(mod, "kernel")]
+        assert flat[woff - 1] == code[(mod, "bias")]          # bias block ends where the kernel block starts
+    # malformed programs are rejected with LIP_ERR_INVALID
+    def create(descs, D):
+        a = (cabi.LayerDesc * len(descs))(*descs)
+        hh = C.c_void_p()
+        return L.lip_model_create(a, len(descs), cabi.CLASSIFIER, D, C.byref(hh))
+    inp = cabi.LayerDesc(cabi.OP_INPUT, 1, 0, 0, 0, 8, 8, 0, 0)
+    conv = cabi.LayerDesc(cabi.OP_CONV2D, 1, 2, 0, 2, 3, 3, 1, 0)          # 8x8x1 -> 6x6x2, 18 + 2 params
+    relu = cabi.LayerDesc(cabi.OP_RELU, 0, 0, 0, 0)
+    pool = cabi.LayerDesc(cabi.OP_AVGPOOL2, 0, 0, 0, 0)
+    dense = cabi.LayerDesc(cabi.OP_DENSE, 18, 3, 20, 23)                   # 3x3x2 = 18 -> 3
+    assert create([inp, conv, relu, pool, dense], 20 + 3 + 54) == 0
+    assert create([inp, conv, relu, pool, dense], 99) == cabi.ERR_INVALID                  # parameter count mismatch
+    assert create([inp, conv, pool, dense], 77) == cabi.ERR_INVALID                        # conv stage without activation
+    bad_stride = cabi.LayerDesc(cabi.OP_CONV2D, 1, 2, 0, 2, 3, 3, 2, 0)
+    assert create([inp, bad_stride, relu, pool, dense], 77) == cabi.ERR_INVALID            # stride 2 not built
+    bad_cin = cabi.LayerDesc(cabi.OP_CONV2D, 3, 2, 0, 2, 3, 3, 1, 0)
+    assert create([inp, bad_cin, relu, pool, dense], 77) == cabi.ERR_INVALID
+    assert create([inp, conv, relu, pool], 20) == cabi.ERR_INVALID                         # must end with DENSE
+    odd = cabi.LayerDesc(cabi.OP_INPUT, 1, 0, 0, 0, 7, 7, 0, 0)                            # 7x7 -> 5x5: odd pool
+    assert create([odd, conv, relu, pool, dense], 77) == cabi.ERR_INVALID

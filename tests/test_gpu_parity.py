@@ -298,8 +298,12 @@ def test_unsupported_models_fail_loudly():
     from lip_b200 import ggn, scalemodels
     st = scalemodels.TrainState(params={"Conv_0": {"kernel": np.zeros((5, 5, 1, 6), np.float32)}},
                                 apply_fn=scalemodels.LeNet5().apply)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):              # a LeNet5 whose parameter tree does not have the LeNet geometry
         ggn.compute_ggn_vp(st, torch.zeros(2, 28, 28, 1, device="cuda"), "classifier")
+    st3 = scalemodels.TrainState(params={"Conv_0": {"kernel": np.zeros((3, 3, 3, 32), np.float32)}},
+                                 apply_fn=scalemodels.ResNet1M().apply)
+    with pytest.raises(NotImplementedError):     # conv/BN/residual kernels: SURVEY 8a M4, not built
+        ggn.compute_ggn_vp(st3, torch.zeros(2, 32, 32, 3, device="cuda"), "classifier")
 
     class Weird:
         def apply(self, *a, **k):
@@ -378,3 +382,59 @@ def test_headline_config_matches_oracle():
         errs = [rel_err(got[i], ref[i]) for i in range(2)]
         print(f"C3b tensor_path={tp} ({cvp._lip_model.path_name()}): rel err {errs}")
         assert max(errs) < TOL_GGN
+
+
+# --------------------------------------------------------------------------------- conv stage programs (LeNet5)
+def test_lenet5_operators_match_oracle():
+    """M3 (scalemodels.py:11-49): forward, GGN-vector product, W, W^T and the W W^T == GGN identity against the float64
+    oracle (torch autograd through the restated LeNet5) on identical weights / points / probes."""
+    from lip_b200 import ggn, lla
+    ost, lst = make_pair("lenet5", seed=31)
+    rng = np.random.default_rng(32)
+    M, N = 5, 60000
+    Z = rng.random((M, 28, 28, 1)).astype(np.float32)
+    D = ost.flat()[0].size
+    assert D == 61706
+    bm = ggn._bind(lst, cu(Z), "classifier")
+    assert rel_err(bm.outputs().cpu().numpy(), O.model_outputs(ost, Z)) < 2e-6
+    V = rng.choice([-1.0, 1.0], size=(3, D)).astype(np.float32)
+    V[2] = rng.standard_normal(D).astype(np.float32)
+    ref_vp = O.compute_ggn_vp(ost, Z, "classifier", full_set_size=N)
+    ref = np.stack([ref_vp(v) for v in V.astype(np.float64)])
+    vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=N)
+    got = vp(cu(V)).cpu().numpy()
+    assert rel_err(got, ref) < TOL_GGN
+    alpha = 5e-3
+    cvp = lla.compute_curvature_approx(lst, cu(Z), "classifier", alpha, full_set_size=N)
+    assert rel_err(cvp(cu(V[0])).cpu().numpy(), ref[0] + alpha * V[0]) < TOL_GGN
+    Wo, WTo = O.compute_W_vps(ost, Z, "classifier", full_set_size=N)
+    Wg, WTg = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=N)
+    ref_wt = np.stack([WTo(v) for v in V.astype(np.float64)])
+    assert rel_err(WTg(cu(V)).cpu().numpy(), ref_wt) < TOL_GGN
+    U = rng.standard_normal(ref_wt.shape).astype(np.float32)
+    ref_w = np.stack([Wo(u) for u in U.astype(np.float64)])
+    assert rel_err(Wg(cu(U)).cpu().numpy(), ref_w) < TOL_GGN
+    assert rel_err(Wg(WTg(cu(V))).cpu().numpy(), got) < 2e-5
+
+
+def test_lenet5_hutchinson_and_predictive():
+    """Estimators on top of the conv path: Hutchinson trace with identical probes, batched predictive JVP (lla.py:153)."""
+    from lip_b200 import _cabi, ggn, lla, stochtrace
+    ost, lst = make_pair("lenet5", seed=33)
+    rng = np.random.default_rng(34)
+    Z = rng.random((4, 28, 28, 1)).astype(np.float32)
+    D = ost.flat()[0].size
+    alpha = 5e-3
+    eps = rng.choice([-1.0, 1.0], size=(6, D)).astype(np.float32)
+    cvp_o = O.compute_curvature_approx(ost, Z, "classifier", alpha, full_set_size=1000)
+    ref = O.stochastic_trace_estimator_mvp(cvp_o, eps.astype(np.float64))
+    cvp = lla.compute_curvature_approx(lst, cu(Z), "classifier", alpha, full_set_size=1000)
+    got = float(stochtrace.stochastic_trace_estimator_mvp(cvp, D, 0, eps=cu(eps)))
+    assert abs(got - ref) <= TOL_EST * abs(ref)
+    # plain Jacobian-vector products at new inputs (factor NONE): J_X w
+    Xnew = rng.random((3, 28, 28, 1)).astype(np.float32)
+    w = rng.standard_normal((2, D)).astype(np.float32)
+    bx = ggn._bind(lst, cu(Xnew), "classifier")
+    got_j = bx.wt(cu(w), scale=1.0, factor=_cabi.FACTOR_NONE).cpu().numpy()
+    ref_j = np.stack([O.jvp_outputs(ost, Xnew, wi.astype(np.float64)) for wi in w])
+    assert rel_err(got_j, ref_j) < TOL_GGN
