@@ -8,6 +8,7 @@
 //   VJP   layer l:  gW_l[b] = A_{l-1}^T D_l[b];  gb_l[b] = colsum D_l[b];  D_{l-1}[b] = (D_l[b] W_l^T) * phi'_{l-1}
 // with the output-space Hessian / sqrt-Hessian applied in registers between the two sweeps.
 #include <vector>
+#include <stdlib.h>
 #include <new>
 
 #include "lip_common.cuh"
@@ -199,7 +200,7 @@ static inline int64_t colsum_slots(const lip_model* m) { return ceil_div(m->M, 1
 size_t ws_bytes(const lip_model* m, int64_t B) {
   size_t per = align_up((size_t)B * (size_t)m->M * (size_t)(m->tc_on ? m->ldmax : m->maxw), 64);
   size_t total = 2 * per;
-  if (m->tc_on) total += 2 * per + 2 * align_up((size_t)B * (size_t)m->max_split, 64) +
+  if (m->tc_on) total += 2 * per + 2 * align_up((size_t)B * (size_t)m->sum_split, 64) +
                         align_up((size_t)B * (size_t)colsum_slots(m) * (size_t)m->ldmax, 64);
   return total * sizeof(float) + 256;
 }
@@ -217,7 +218,7 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
   w->lo[0] = w->lo[1] = w->vs_hi = w->vs_lo = w->colsum = nullptr;
   if (m->tc_on) {
     w->lo[0] = base + 2 * per; w->lo[1] = base + 3 * per;
-    size_t vs = align_up((size_t)B * (size_t)m->max_split, 64);
+    size_t vs = align_up((size_t)B * (size_t)m->sum_split, 64);
     w->vs_hi = base + 4 * per; w->vs_lo = w->vs_hi + vs;
     w->colsum = w->vs_lo + vs;
   }
@@ -233,6 +234,40 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
   const float* prev_hi = nullptr;
   const float* prev_lo = nullptr;
   int prev_ld = 0;
+  // TF32 (hi, lo) splits of the probes' weight blocks: HBM-bound, independent of everything but V.  They run on the
+  // model's side stream, layer by layer, while the compute-bound GEMMs of the earlier layers run on `st`; the first
+  // tensor-core layer is additionally cut into probe chunks so that only its first chunk's split is exposed.
+  constexpr int NCH = lip_model::SPLIT_CHUNKS;
+  // Measured on B200 (profiles/r01_split_overlap.txt): no gain - the sustained step is power-capped, so hiding the
+  // HBM-bound splits behind the tensor-bound GEMMs does not shorten it.  Off unless LIP_SPLIT_OVERLAP=1.
+  static const bool overlap = getenv("LIP_SPLIT_OVERLAP") && atoi(getenv("LIP_SPLIT_OVERLAP")) != 0;
+  int first_tc = -1;
+  for (int l = 0; l < nL && m->tc_on; ++l) if (m->tc_layer[l]) { first_tc = l; break; }
+  const int64_t chunk = ceil_div(B, NCH);
+  if (m->tc_on) {
+    cudaStream_t ss = overlap ? m->side : st;
+    if (overlap) {
+      LIP_CHECK_CUDA(cudaEventRecord(m->ev_fork, st));
+      LIP_CHECK_CUDA(cudaStreamWaitEvent(ss, m->ev_fork, 0));
+    }
+    for (int l = 0; l < nL; ++l) {
+      if (!m->tc_layer[l]) continue;
+      const DenseLayer& Ld = m->L[l];
+      const int64_t ldw = m->W_ld[l], bsz = (int64_t)Ld.in * ldw;
+      float* hi = w.vs_hi + B * m->split_off[l];
+      float* lo = w.vs_lo + B * m->split_off[l];
+      const int nch = (l == first_tc && overlap) ? NCH : 1;
+      for (int c = 0; c < nch; ++c) {
+        const int64_t b0 = nch == 1 ? 0 : c * chunk, b1 = nch == 1 ? B : (b0 + chunk < B ? b0 + chunk : B);
+        if (b1 > b0) {
+          int rc = tf32_split3(V + b0 * m->D + Ld.woff, m->D, Ld.out, hi + b0 * bsz, lo + b0 * bsz, bsz, ldw, b1 - b0, Ld.in,
+                               Ld.out, ss);
+          if (rc) return rc;
+        }
+        if (overlap) LIP_CHECK_CUDA(cudaEventRecord(m->ev_split[l * NCH + c], ss));
+      }
+    }
+  }
   for (int l = 0; l < nL; ++l) {
     const DenseLayer& Ld = m->L[l];
     const bool last = (l == nL - 1);
@@ -243,13 +278,13 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
     const int out_ld = last ? Ld.out : ld_of(m, Ld.out);
     if (tc) {
       const int64_t ldw = m->W_ld[l];
-      int rc = tf32_split3(V + Ld.woff, m->D, Ld.out, w.vs_hi, w.vs_lo, (int64_t)Ld.in * ldw, ldw, B, Ld.in, Ld.out, st);
-      if (rc) return rc;
+      const float* vs_hi = w.vs_hi + B * m->split_off[l];
+      const float* vs_lo = w.vs_lo + B * m->split_off[l];
       TcGemmProblem p;
       p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = B;
       p.A1.hi = m->A_hi[l]; p.A1.lo = m->A_lo[l]; p.A1.ld = m->A_ld[l]; p.A1.sz = m->M * m->A_ld[l]; p.A1.major_k = 1;
       p.a_batched = 0;
-      p.B1.hi = w.vs_hi; p.B1.lo = w.vs_lo; p.B1.ld = ldw; p.B1.sz = (int64_t)Ld.in * ldw; p.B1.major_k = 0;
+      p.B1.hi = vs_hi; p.B1.lo = vs_lo; p.B1.ld = ldw; p.B1.sz = (int64_t)Ld.in * ldw; p.B1.major_k = 0;
       p.b_batched = 1;
       if (l > 0) {
         p.A2.hi = prev_hi; p.A2.lo = prev_lo; p.A2.ld = prev_ld; p.A2.sz = m->M * (int64_t)prev_ld; p.A2.major_k = 1;
@@ -261,7 +296,27 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       p.C = out_hi; p.C_lo = out_lo; p.c_sz = m->M * (int64_t)out_ld; p.c_sm = out_ld;
       p.epi.bias = V + Ld.boff; p.epi.bias_sz = m->D;
       if (!last) { p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out; }
-      rc = gemm_tc(p, st);
+      int rc = LIP_OK;
+      if (overlap && l == first_tc && l == 0) {
+        // probe-chunked: chunk c starts as soon as its split has landed
+        for (int c = 0; c < NCH && !rc; ++c) {
+          const int64_t b0 = c * chunk, b1 = b0 + chunk < B ? b0 + chunk : B;
+          LIP_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_split[l * NCH + c], 0));
+          if (b1 <= b0) continue;
+          TcGemmProblem q = p;
+          q.batch = b1 - b0;
+          q.B1.hi += b0 * q.B1.sz; q.B1.lo += b0 * q.B1.sz;
+          q.C += b0 * q.c_sz; if (q.C_lo) q.C_lo += b0 * q.c_sz;
+          q.epi.bias += b0 * q.epi.bias_sz;
+          rc = gemm_tc(q, st);
+        }
+      } else {
+        if (overlap) {
+          const int nch = (l == first_tc) ? NCH : 1;
+          for (int c = 0; c < nch; ++c) LIP_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_split[l * NCH + c], 0));
+        }
+        rc = gemm_tc(p, st);
+      }
       if (rc) return rc;
     } else {
       GemmProblem p;
@@ -461,6 +516,9 @@ int lip_model_create(const lip_layer_desc* layers, int32_t n_layers, int32_t mod
 int lip_model_destroy(lip_model* m) {
   if (!m) return LIP_OK;
   m->free_cache();
+  for (auto e : m->ev_split) cudaEventDestroy(e);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->side) cudaStreamDestroy(m->side);
   delete m;
   return LIP_OK;
 }
@@ -558,6 +616,22 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
       rc = tf32_split(theta + Ld.woff, Ld.out, m->W_hi[l], m->W_lo[l], ldw, Ld.in, Ld.out, st);
       if (rc) return rc;
       if ((int64_t)Ld.in * ldw > m->max_split) m->max_split = (int64_t)Ld.in * ldw;
+    }
+    m->split_off.assign(nL, 0);
+    m->sum_split = 0;
+    for (int l = 0; l < nL; ++l) {
+      if (!m->tc_layer[l]) continue;
+      m->split_off[l] = m->sum_split;
+      m->sum_split += (int64_t)m->L[l].in * m->W_ld[l];
+    }
+    if (!m->side) {
+      LIP_CHECK_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+      LIP_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    }
+    while ((int)m->ev_split.size() < nL * lip_model::SPLIT_CHUNKS) {
+      cudaEvent_t e;
+      LIP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      m->ev_split.push_back(e);
     }
   }
   m->bound = true;

@@ -47,6 +47,13 @@ struct lip_model {
   std::vector<int64_t> A_ld, W_ld;
   std::vector<char> tc_layer;   // layer l runs its three GEMMs on the tensor cores
   int64_t max_split = 0;        // max over tc layers of in * ldw (floats per probe of the split tangent block)
+  int64_t sum_split = 0;        // sum over tc layers of in * ldw
+  std::vector<int64_t> split_off;   // per layer: float offset (per probe) of its block inside the split buffers
+  // side stream that runs the probe-block TF32 splits concurrently with the (compute-bound) JVP GEMMs
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_split;   // [layer * SPLIT_CHUNKS + chunk]
+  static constexpr int SPLIT_CHUNKS = 4;
   int ldmax = 0;                // widest padded intermediate row
 
   // ---- conv stage programs (LeNet5, src/scalemodels.py:11-49): see lip_cnn.cu ----
@@ -66,7 +73,7 @@ struct lip_model {
     for (auto p : W_hi) if (p) cudaFree(p);
     for (auto p : W_lo) if (p) cudaFree(p);
     A.clear(); dphi.clear(); A_hi.clear(); A_lo.clear(); W_hi.clear(); W_lo.clear(); A_ld.clear(); W_ld.clear();
-    tc_layer.clear(); tc_on = false; max_split = 0;
+    tc_layer.clear(); tc_on = false; max_split = 0; sum_split = 0; split_off.clear();
     if (logits) cudaFree(logits);
     if (P) cudaFree(P);
     if (S) cudaFree(S);
