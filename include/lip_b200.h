@@ -46,7 +46,19 @@ typedef enum {
   LIP_OP_AVGPOOL2 = 5,   /* nn.avg_pool(window (2,2), strides (2,2)) */
   LIP_OP_ZEROPAD = 6,    /* jnp.pad(x, ((0,0),(p,p),(p,p),(0,0))) */
   LIP_OP_FLATTEN = 7,    /* x.reshape(batch, -1) of an NHWC image (a no-op on the memory layout) */
-  LIP_OP_INPUT = 8       /* declares an image input: kh = height, kw = width, in_features = channels (first op) */
+  LIP_OP_INPUT = 8,      /* declares an image input: kh = height, kw = width, in_features = channels (first op) */
+  /* residual networks (model M4, ResNet1M: src/scalemodels.py:70-157).  A program is
+   *   INPUT, CONV2D, BATCHNORM, RELU,
+   *   { RES_SAVE, CONV2D, BATCHNORM, RELU, CONV2D, BATCHNORM, [RES_CONV2D, RES_BATCHNORM,] RES_ADD, RELU }*,
+   *   GLOBAL_MEAN, DENSE
+   * with bias-free SAME-padded convs (pad = rows/columns of zeros BEFORE the image, flax/XLA SAME; stride 1 or 2). */
+  LIP_OP_BATCHNORM = 9,      /* eval mode (ggn.py:52): in_features = channels, bias_offset = bias[c], kernel_offset = scale[c]
+                                in theta; running mean/var come from lip_model_set_bn_stats, in program order */
+  LIP_OP_RES_SAVE = 10,      /* remember the current tensor as the block's residual */
+  LIP_OP_RES_CONV2D = 11,    /* CONV2D applied to the saved residual (the 1x1 strided shortcut) */
+  LIP_OP_RES_BATCHNORM = 12, /* BATCHNORM applied to the saved residual */
+  LIP_OP_RES_ADD = 13,       /* x = x + residual */
+  LIP_OP_GLOBAL_MEAN = 14    /* jnp.mean(x, axis=(1, 2)) */
 } lip_op;
 
 typedef struct {
@@ -56,7 +68,7 @@ typedef struct {
   int64_t bias_offset;   /* DENSE / CONV2D: offset of bias[out] in the flat parameter vector */
   int64_t kernel_offset; /* DENSE: offset of kernel[in,out]; CONV2D: of kernel[kh,kw,cin,cout] */
   int32_t kh, kw;        /* CONV2D: kernel height / width; INPUT: image height / width */
-  int32_t stride, pad;   /* CONV2D: stride (1); ZEROPAD: zero rows / columns added on each side */
+  int32_t stride, pad;   /* CONV2D: stride, zero rows / columns before the image; ZEROPAD: zeros added on each side */
 } lip_layer_desc;
 
 typedef enum { LIP_REGRESSOR = 0, LIP_CLASSIFIER = 1 } lip_model_type;
@@ -93,6 +105,10 @@ int lip_model_tensor_layers(const lip_model* m);
  * log-variance (ggn.py:112-113); ignored for classifiers.  Allocates the cache (not a hot call). */
 int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, float logvar,
                    lip_stream_t stream);
+/* BatchNorm running statistics for programs with BATCHNORM ops (state.batch_stats, src/ggn.py:52): device array
+ * [mean_0(c0), var_0(c0), mean_1(c1), var_1(c1), ...] in the order the BATCHNORM / RES_BATCHNORM ops appear; eps is
+ * flax's 1e-5.  Must be called before lip_model_bind; the library keeps its own copy. */
+int lip_model_set_bn_stats(lip_model* m, const float* stats, int64_t n, lip_stream_t stream);
 /* Copies the cached model outputs f(theta, Z) [M,K] (logits / means) to out. */
 int lip_model_outputs(lip_model* m, float* out, lip_stream_t stream);
 

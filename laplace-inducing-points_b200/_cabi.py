@@ -12,6 +12,7 @@ LIP_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOT_BOUND = -1, -2, -3, -4, -5
 OP_DENSE, OP_TANH, OP_GELU_TANH, OP_RELU = 0, 1, 2, 3
 OP_CONV2D, OP_AVGPOOL2, OP_ZEROPAD, OP_FLATTEN, OP_INPUT = 4, 5, 6, 7, 8
+OP_BATCHNORM, OP_RES_SAVE, OP_RES_CONV2D, OP_RES_BATCHNORM, OP_RES_ADD, OP_GLOBAL_MEAN = 9, 10, 11, 12, 13, 14
 REGRESSOR, CLASSIFIER = 0, 1
 FACTOR_NONE, FACTOR_SQRT = 0, 1
 FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY = 0, 1, 2, 3
@@ -39,6 +40,7 @@ SIGNATURES = {
     "lip_model_set_tensor_path": (C.c_int, [_P, _I32]),
     "lip_model_tensor_layers": (C.c_int, [_P]),
     "lip_model_bind": (C.c_int, [_P, _P, _P, _I64, _F, _P]),
+    "lip_model_set_bn_stats": (C.c_int, [_P, _P, _I64, _P]),
     "lip_model_outputs": (C.c_int, [_P, _P, _P]),
     "lip_workspace_bytes": (_SZ, [_P, _I64]),
     "lip_ggn_vp": (C.c_int, [_P, _P, _P, _I64, _F, _F, _P, _SZ, _P]),

@@ -146,6 +146,99 @@ class ConvProgramSpec:
         return arr, len(out)
 
 
+def _tree_walk(tree, prefix=()):
+    if isinstance(tree, dict):
+        for k in sorted(tree.keys()):
+            yield from _tree_walk(tree[k], prefix + (k,))
+    else:
+        yield prefix, tree
+
+
+class ResNetProgramSpec:
+    """ResNet1M (scalemodels.py:70-157) as a residual conv program.  Geometry and parameter offsets are read off the
+    parameter tree itself (flat order = sorted-key DFS, utils.py:12-17): stem Conv_0 + BatchNorm_0, BasicBlock_i with
+    Conv_0/1 (+ Conv_2 = 1x1 shortcut, which is also how the stride-2 blocks are recognised, scalemodels.py:101-109),
+    Dense_0.  BatchNorm running statistics (state.batch_stats) are constants of the program."""
+
+    def __init__(self, tree, batch_stats, in_shape, model_type: str):
+        import numpy as np
+        self.model_type = model_type
+        self.name = "ResNet1M"
+        self.in_shape = tuple(int(x) for x in in_shape)
+        if len(self.in_shape) != 3:
+            raise ValueError(f"ResNet1M expects NHWC images, got per-point shape {self.in_shape}")
+        self.in_features = int(np.prod(self.in_shape))
+        offs, off = {}, 0
+        for path, leaf in _tree_walk(tree):
+            offs[path] = off
+            off += int(np.prod(tuple(leaf.shape))) if len(tuple(leaf.shape)) else 1
+        self.num_params = off
+        stats_tree = dict(batch_stats or {})
+        if list(stats_tree.keys()) == ["batch_stats"]:
+            stats_tree = dict(stats_tree["batch_stats"])
+        H, W, C = self.in_shape
+        self.ops = [cabi.LayerDesc(cabi.OP_INPUT, C, 0, 0, 0, H, W, 0, 0)]
+        self.layers = []
+        stats = []
+
+        def sub(t, path):
+            for k in path:
+                if not isinstance(t, dict) or k not in t:
+                    raise ValueError(f"ResNet1M: missing {'/'.join(path)} in the parameter / batch_stats tree")
+                t = t[k]
+            return t
+
+        def conv_bn(path, conv, bn, cin, hin, stride, op_conv, op_bn):
+            kern = sub(tree, path + (conv, "kernel"))
+            if "bias" in sub(tree, path + (conv,)):
+                raise ValueError(f"ResNet1M: {'/'.join(path + (conv,))} has a bias (use_bias=False expected)")
+            kh, kw, ci, co = (int(x) for x in kern.shape)
+            if ci != cin or kh != kw:
+                raise ValueError(f"ResNet1M: {'/'.join(path + (conv,))} kernel {tuple(kern.shape)} does not fit {cin} input channels")
+            hout = -(-hin // stride)
+            pad = max((hout - 1) * stride + kh - hin, 0) // 2            # XLA 'SAME': the smaller half goes first
+            self.ops.append(cabi.LayerDesc(op_conv, ci, co, -1, offs[path + (conv, "kernel")], kh, kw, stride, pad))
+            bnp = sub(tree, path + (bn,))
+            if tuple(bnp["scale"].shape) != (co,) or tuple(bnp["bias"].shape) != (co,):
+                raise ValueError(f"ResNet1M: {'/'.join(path + (bn,))} does not have {co} channels")
+            self.ops.append(cabi.LayerDesc(op_bn, co, co, offs[path + (bn, "bias")], offs[path + (bn, "scale")]))
+            st = sub(stats_tree, path + (bn,))
+            stats.append(torch.as_tensor(np.asarray(st["mean"], dtype=np.float32)).reshape(-1))
+            stats.append(torch.as_tensor(np.asarray(st["var"], dtype=np.float32)).reshape(-1))
+            self.layers.append(path + (conv,))
+            return co, hout
+
+        if W != H:
+            raise ValueError("ResNet1M: square inputs expected")
+        C, H = conv_bn((), "Conv_0", "BatchNorm_0", C, H, 1, cabi.OP_CONV2D, cabi.OP_BATCHNORM)
+        self.ops.append(cabi.LayerDesc(cabi.OP_RELU, 0, 0, 0, 0))
+        blocks = sorted((k for k in tree if k.startswith("BasicBlock_")), key=lambda k: int(k.split("_")[1]))
+        for name in blocks:
+            blk = tree[name]
+            stride = 2 if "Conv_2" in blk else 1
+            self.ops.append(cabi.LayerDesc(cabi.OP_RES_SAVE, 0, 0, 0, 0))
+            c1, h1 = conv_bn((name,), "Conv_0", "BatchNorm_0", C, H, stride, cabi.OP_CONV2D, cabi.OP_BATCHNORM)
+            self.ops.append(cabi.LayerDesc(cabi.OP_RELU, 0, 0, 0, 0))
+            c2, h2 = conv_bn((name,), "Conv_1", "BatchNorm_1", c1, h1, 1, cabi.OP_CONV2D, cabi.OP_BATCHNORM)
+            if "Conv_2" in blk:
+                conv_bn((name,), "Conv_2", "BatchNorm_2", C, H, stride, cabi.OP_RES_CONV2D, cabi.OP_RES_BATCHNORM)
+            self.ops.append(cabi.LayerDesc(cabi.OP_RES_ADD, 0, 0, 0, 0))
+            self.ops.append(cabi.LayerDesc(cabi.OP_RELU, 0, 0, 0, 0))
+            C, H = c2, h2
+        dk = sub(tree, ("Dense_0", "kernel"))
+        if int(dk.shape[0]) != C:
+            raise ValueError(f"ResNet1M: Dense_0 kernel {tuple(dk.shape)} does not fit {C} channels")
+        self.num_outputs = int(dk.shape[1])
+        self.ops.append(cabi.LayerDesc(cabi.OP_GLOBAL_MEAN, 0, 0, 0, 0))
+        self.ops.append(cabi.LayerDesc(cabi.OP_DENSE, C, self.num_outputs, offs[("Dense_0", "bias")], offs[("Dense_0", "kernel")]))
+        self.layers.append(("Dense_0",))
+        self.bn_stats = torch.cat(stats)
+
+    def descs(self):
+        arr = (cabi.LayerDesc * len(self.ops))(*self.ops)
+        return arr, len(self.ops)
+
+
 class BoundModel:
     """lip_model handle bound to (theta, Z): owns the activation cache; exposes the probe-batched operators."""
 
@@ -175,6 +268,10 @@ class BoundModel:
         self._finalizer = weakref.finalize(self, L.lip_model_destroy, h)
         if tensor_path is not None:
             cabi.check(L.lip_model_set_tensor_path(self._h, 1 if tensor_path else 0))
+        if getattr(spec, "bn_stats", None) is not None:
+            self._bn_stats = dev_f32(spec.bn_stats, self.device)
+            cabi.check(L.lip_model_set_bn_stats(self._h, ptr(self._bn_stats), self._bn_stats.numel(), stream()),
+                       "lip_model_set_bn_stats")
         cabi.check(L.lip_model_bind(self._h, ptr(self.theta), ptr(self.Z), self.M, self.logvar, stream()),
                    "lip_model_bind")
         self._ws = Scratch()
@@ -183,7 +280,7 @@ class BoundModel:
     def path_name(self) -> str:
         n = cabi.lib().lip_model_tensor_layers(self._h)
         total = len(self.spec.layers)
-        if isinstance(self.spec, ConvProgramSpec):
+        if isinstance(self.spec, (ConvProgramSpec, ResNetProgramSpec)):
             return f"im2col + simt-fp32 ({total} conv/dense stages)"
         return f"tcgen05-3xtf32 ({n}/{total} layers) + simt-fp32" if n else "simt-fp32"
 

@@ -30,9 +30,9 @@ void lip_model::free_cnn_cache() {
 
 namespace {
 
-// out[r][(dy*kw + dx)*C + c] = in[mz][y + dy - pad][x + dx - pad][c]   (0 outside), r = (mz*Ho + y)*Wo + x
+// out[r][(dy*kw + dx)*C + c] = in[mz][y*stride + dy - pad_h][x*stride + dx - pad_w][c]   (0 outside), r = (mz*Ho + y)*Wo + x
 __global__ void im2col_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int Hi, int Wi, int C,
-                              int pad, int kh, int kw, int Ho, int Wo) {
+                              int pad_h, int pad_w, int stride, int kh, int kw, int Ho, int Wo) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long t = idx;
     const int c = (int)(t % C); t /= C;
@@ -40,17 +40,17 @@ __global__ void im2col_kernel(const float* __restrict__ in, float* __restrict__ 
     const int dy = (int)(t % kh); t /= kh;
     const int x = (int)(t % Wo); t /= Wo;
     const int y = (int)(t % Ho); t /= Ho;
-    const int yi = y + dy - pad, xi = x + dx - pad;
+    const int yi = y * stride + dy - pad_h, xi = x * stride + dx - pad_w;
     float v = 0.f;
     if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) v = __ldg(in + ((t * Hi + yi) * Wi + xi) * C + c);
     out[idx] = v;
   }
 }
 
-// tin[mz][yi][xi][c] = sum over (dy, dx) with 0 <= y = yi + pad - dy < Ho, 0 <= x = xi + pad - dx < Wo of
-//                      col[(mz*Ho + y)*Wo + x][(dy*kw + dx)*C + c]          (gather form: deterministic, no atomics)
+// tin[mz][yi][xi][c] (+)= sum over (dy, dx) with y*stride = yi + pad_h - dy, x*stride = xi + pad_w - dx, 0 <= y < Ho, 0 <= x < Wo
+//                         of col[(mz*Ho + y)*Wo + x][(dy*kw + dx)*C + c]          (gather form: deterministic, no atomics)
 __global__ void col2im_kernel(const float* __restrict__ col, float* __restrict__ tin, long long total, int Hi, int Wi, int C,
-                              int pad, int kh, int kw, int Ho, int Wo) {
+                              int pad_h, int pad_w, int stride, int kh, int kw, int Ho, int Wo, int accumulate) {
   const int Kc = kh * kw * C;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long t = idx;
@@ -59,15 +59,19 @@ __global__ void col2im_kernel(const float* __restrict__ col, float* __restrict__
     const int yi = (int)(t % Hi); t /= Hi;
     float acc = 0.f;
     for (int dy = 0; dy < kh; ++dy) {
-      const int y = yi + pad - dy;
-      if (y < 0 || y >= Ho) continue;
+      const int ys = yi + pad_h - dy;
+      if (ys < 0 || ys % stride != 0) continue;
+      const int y = ys / stride;
+      if (y >= Ho) continue;
       for (int dx = 0; dx < kw; ++dx) {
-        const int x = xi + pad - dx;
-        if (x < 0 || x >= Wo) continue;
+        const int xs = xi + pad_w - dx;
+        if (xs < 0 || xs % stride != 0) continue;
+        const int x = xs / stride;
+        if (x >= Wo) continue;
         acc += __ldg(col + ((t * Ho + y) * Wo + x) * Kc + (dy * kw + dx) * C + c);
       }
     }
-    tin[idx] = acc;
+    tin[idx] = accumulate ? tin[idx] + acc : acc;
   }
 }
 
@@ -110,18 +114,32 @@ inline unsigned ew_grid(long long total) {
   if (g < 1) g = 1;
   return (unsigned)g;
 }
+}  // namespace
 
-int launch_im2col(const float* in, float* out, int64_t MZ, const ConvStage& s, cudaStream_t st) {
-  const long long total = (long long)MZ * s.P * s.Kc;
-  im2col_kernel<<<ew_grid(total), 256, 0, st>>>(in, out, total, s.Hi, s.Wi, s.cin, s.pad, s.kh, s.kw, s.Ho, s.Wo);
+namespace lip {
+int im2col(const float* in, float* out, int64_t MZ, int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kh, int kw,
+           int Ho, int Wo, cudaStream_t st) {
+  const long long total = (long long)MZ * Ho * Wo * kh * kw * C;
+  im2col_kernel<<<ew_grid(total), 256, 0, st>>>(in, out, total, Hi, Wi, C, pad_h, pad_w, stride, kh, kw, Ho, Wo);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
 }
-int launch_col2im(const float* col, float* tin, int64_t MZ, const ConvStage& s, cudaStream_t st) {
-  const long long total = (long long)MZ * s.Hi * s.Wi * s.cin;
-  col2im_kernel<<<ew_grid(total), 256, 0, st>>>(col, tin, total, s.Hi, s.Wi, s.cin, s.pad, s.kh, s.kw, s.Ho, s.Wo);
+int col2im(const float* col, float* tin, int64_t MZ, int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kh, int kw,
+           int Ho, int Wo, int accumulate, cudaStream_t st) {
+  const long long total = (long long)MZ * Hi * Wi * C;
+  col2im_kernel<<<ew_grid(total), 256, 0, st>>>(col, tin, total, Hi, Wi, C, pad_h, pad_w, stride, kh, kw, Ho, Wo, accumulate);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
+}
+}  // namespace lip
+
+namespace {
+
+int launch_im2col(const float* in, float* out, int64_t MZ, const ConvStage& s, cudaStream_t st) {
+  return im2col(in, out, MZ, s.Hi, s.Wi, s.cin, s.pad, s.pad, 1, s.kh, s.kw, s.Ho, s.Wo, st);
+}
+int launch_col2im(const float* col, float* tin, int64_t MZ, const ConvStage& s, cudaStream_t st) {
+  return col2im(col, tin, MZ, s.Hi, s.Wi, s.cin, s.pad, s.pad, 1, s.kh, s.kw, s.Ho, s.Wo, 0, st);
 }
 int launch_avgpool(const float* in, float* out, int64_t MZ, const ConvStage& s, cudaStream_t st) {
   const long long total = (long long)MZ * s.Hp * s.Wp * s.cout;

@@ -444,8 +444,10 @@ int lip_model_create(const lip_layer_desc* layers, int32_t n_layers, int32_t mod
   LIP_REQUIRE(m != nullptr, "lip_model_create: out of host memory");
   m->model_type = model_type;
   m->D = num_params;
-  if (layers[0].op == LIP_OP_INPUT) {   // conv stage program (lip_cnn.cu)
-    int rc = cnn_parse(m, layers, n_layers, num_params);
+  if (layers[0].op == LIP_OP_INPUT) {   // conv stage program (lip_cnn.cu) or residual conv program (lip_resnet.cu)
+    bool residual = false;
+    for (int i = 0; i < n_layers; ++i) residual = residual || layers[i].op >= LIP_OP_BATCHNORM;
+    int rc = residual ? resnet_parse(m, layers, n_layers, num_params) : cnn_parse(m, layers, n_layers, num_params);
     if (rc) { delete m; return rc; }
     if (model_type == LIP_REGRESSOR && m->K != 1) {
       delete m;
@@ -519,6 +521,7 @@ int lip_model_destroy(lip_model* m) {
   for (auto e : m->ev_split) cudaEventDestroy(e);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->side) cudaStreamDestroy(m->side);
+  if (m->rn_stats) cudaFree(m->rn_stats);
   delete m;
   return LIP_OK;
 }
@@ -548,6 +551,7 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
   m->M = M;
   m->theta = theta;
   m->logvar = logvar;
+  if (m->is_resnet) return resnet_bind(m, theta, Z, M, st);
   if (m->is_cnn) return cnn_bind(m, theta, Z, M, st);
   const int nL = (int)m->L.size();
   m->A.assign(nL, nullptr);
@@ -638,6 +642,15 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
   return LIP_OK;
 }
 
+int lip_model_set_bn_stats(lip_model* m, const float* stats, int64_t n, lip_stream_t stream) {
+  LIP_REQUIRE(m && stats && n > 0, "lip_model_set_bn_stats: null argument");
+  LIP_REQUIRE(m->is_resnet && n == m->rn_nstats, "lip_model_set_bn_stats: the program's BATCHNORM ops need %lld statistics, got %lld",
+              (long long)(m ? m->rn_nstats : 0), (long long)n);
+  if (!m->rn_stats) LIP_CHECK_CUDA(cudaMalloc(&m->rn_stats, sizeof(float) * (size_t)n));
+  LIP_CHECK_CUDA(cudaMemcpyAsync(m->rn_stats, stats, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return LIP_OK;
+}
+
 int lip_model_outputs(lip_model* m, float* out, lip_stream_t stream) {
   LIP_REQUIRE(m && out, "null argument");
   if (!m->bound) { set_error("model not bound"); return LIP_ERR_NOT_BOUND; }
@@ -648,7 +661,7 @@ int lip_model_outputs(lip_model* m, float* out, lip_stream_t stream) {
 
 size_t lip_workspace_bytes(const lip_model* m, int64_t B) {
   if (!m || !m->bound || B <= 0) return 0;
-  return m->is_cnn ? cnn_ws_bytes(m, B) : ws_bytes(m, B);
+  return m->is_resnet ? resnet_ws_bytes(m, B) : (m->is_cnn ? cnn_ws_bytes(m, B) : ws_bytes(m, B));
 }
 
 int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* workspace,
@@ -657,6 +670,7 @@ int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal,
   LIP_REQUIRE(V != out, "lip_ggn_vp: in-place operation is not supported");
   if (!m->bound) { set_error("lip_ggn_vp: model not bound"); return LIP_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_resnet) return resnet_ggn_vp(m, V, out, B, recal, alpha, workspace, workspace_bytes, st);
   if (m->is_cnn) return cnn_ggn_vp(m, V, out, B, recal, alpha, workspace, workspace_bytes, st);
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
@@ -679,6 +693,7 @@ int lip_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scal
   LIP_REQUIRE(m && V && out && B > 0, "lip_wt_apply: null argument or B <= 0");
   if (!m->bound) { set_error("lip_wt_apply: model not bound"); return LIP_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_resnet) return resnet_wt_apply(m, V, out, B, scale, factor, workspace, workspace_bytes, st);
   if (m->is_cnn) return cnn_wt_apply(m, V, out, B, scale, factor, workspace, workspace_bytes, st);
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
@@ -701,6 +716,7 @@ int lip_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale
   LIP_REQUIRE(m && U && out && B > 0, "lip_w_apply: null argument or B <= 0");
   if (!m->bound) { set_error("lip_w_apply: model not bound"); return LIP_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_resnet) return resnet_w_apply(m, U, out, B, scale, factor, add, add_scale, workspace, workspace_bytes, st);
   if (m->is_cnn) return cnn_w_apply(m, U, out, B, scale, factor, add, add_scale, workspace, workspace_bytes, st);
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
@@ -722,7 +738,7 @@ int lip_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale
 size_t lip_gram_workspace_bytes(const lip_model* m, int64_t block) {
   if (!m || !m->bound || block <= 0) return 0;
   size_t d = (size_t)m->M * m->K;
-  return (m->is_cnn ? cnn_ws_bytes(m, block) : ws_bytes(m, block)) + align_up(sizeof(float) * (size_t)block * d, 256) +
+  return (m->is_resnet ? resnet_ws_bytes(m, block) : (m->is_cnn ? cnn_ws_bytes(m, block) : ws_bytes(m, block))) + align_up(sizeof(float) * (size_t)block * d, 256) +
          align_up(sizeof(float) * (size_t)block * (size_t)m->D, 256) + 512;
 }
 

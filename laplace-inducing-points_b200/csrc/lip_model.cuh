@@ -24,6 +24,23 @@ struct ConvStage {
   int64_t out_per_point() const { return pool ? (int64_t)Hp * Wp * cout : (int64_t)P * cout; }
 };
 
+// One conv + BatchNorm(eval) [+ residual add] [+ relu] unit of a residual network (ResNet1M, src/scalemodels.py:70-157):
+//   y = relu?( scale * xhat + beta + skip ),  xhat = (conv(x, W) - mean) * rsqrt(var + eps)
+struct ConvBN {
+  int Hi = 0, Wi = 0, cin = 0, kh = 0, kw = 0, stride = 1, pad_h = 0, pad_w = 0, Ho = 0, Wo = 0, cout = 0;
+  int64_t woff = 0, scale_off = 0, beta_off = 0;   // offsets in theta: kernel[kh,kw,cin,cout], BN scale[c], BN bias[c]
+  int64_t stats_off = 0;                           // offset of [mean(c), var(c)] in the bn-stats array
+  int relu = 0;
+  int src = -2, dst = 0, skip = -1;                // tangent-buffer slots (0..3); src -2 = the network input (data)
+  int accumulate = 0;                              // VJP: the cotangent of `src` already holds another branch's contribution
+  float* Aop = nullptr;    // [M*Ho*Wo, kh*kw*cin] im2col patches of the cached input activation
+  float* xhat = nullptr;   // [M*Ho*Wo, cout]
+  float* mask = nullptr;   // [M*Ho*Wo, cout] relu' of the unit's pre-activation (null without relu)
+  float* g = nullptr;      // [cout] scale * rsqrt(var + eps)
+  int64_t P() const { return (int64_t)Ho * Wo; }
+  int64_t Kc() const { return (int64_t)kh * kw * cin; }
+};
+
 struct lip_model {
   std::vector<DenseLayer> L;
   int model_type = LIP_CLASSIFIER;
@@ -63,9 +80,20 @@ struct lip_model {
   float* cnn_tmp_out = nullptr;          // bind-time scratch
   float* cnn_tmp_x = nullptr;
 
+  // ---- residual conv programs (ResNet1M): see lip_resnet.cu ----
+  bool is_resnet = false;
+  std::vector<ConvBN> RB;                // stem + blocks, in forward order
+  int rn_last_slot = 0, rn_H = 0, rn_W = 0, rn_C = 0;   // the tensor fed to the global mean
+  int64_t rn_dense_boff = 0, rn_dense_woff = 0;
+  float* rn_mean_act = nullptr;          // [M, rn_C] cached global-mean activations (the head's A operand)
+  float* rn_stats = nullptr;             // device copy of the BatchNorm running statistics, [sum 2*c]
+  int64_t rn_nstats = 0;
+  int64_t rn_slot_elems = 0;             // per-point elements of the largest activation tensor
+  void free_resnet_cache();
   void free_cnn_cache();
   void free_cache() {
     free_cnn_cache();
+    free_resnet_cache();
     for (auto p : A) if (p) cudaFree(p);
     for (auto p : dphi) if (p) cudaFree(p);
     for (auto p : A_hi) if (p) cudaFree(p);
@@ -92,6 +120,12 @@ int launch_bias_grad(const float* Delta, const float* Delta_lo, int64_t rows, in
 int launch_scale_copy(const float* in, float* out, int64_t n, float scale, cudaStream_t st);
 int launch_softmax(const float* logits, float* P, float* S, int64_t M, int K, cudaStream_t st);
 
+// NHWC im2col / col2im (lip_cnn.cu): patches [MZ*Ho*Wo, kh*kw*C], column order (dy, dx, c) = flax HWIO kernel rows
+int im2col(const float* in, float* out, int64_t MZ, int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kh, int kw,
+           int Ho, int Wo, cudaStream_t st);
+int col2im(const float* col, float* tin, int64_t MZ, int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kh, int kw,
+           int Ho, int Wo, int accumulate, cudaStream_t st);
+
 // conv stage-program path (lip_cnn.cu)
 int cnn_parse(lip_model* m, const lip_layer_desc* layers, int32_t n_layers, int64_t num_params);
 int cnn_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaStream_t st);
@@ -102,4 +136,14 @@ int cnn_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scal
                  cudaStream_t st);
 int cnn_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,
                 float add_scale, void* ws, size_t bytes, cudaStream_t st);
+// residual conv programs (lip_resnet.cu)
+int resnet_parse(lip_model* m, const lip_layer_desc* layers, int32_t n_layers, int64_t num_params);
+int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaStream_t st);
+size_t resnet_ws_bytes(const lip_model* m, int64_t B);
+int resnet_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* ws, size_t bytes,
+                  cudaStream_t st);
+int resnet_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scale, int32_t factor, void* ws, size_t bytes,
+                    cudaStream_t st);
+int resnet_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,
+                   float add_scale, void* ws, size_t bytes, cudaStream_t st);
 }  // namespace lip

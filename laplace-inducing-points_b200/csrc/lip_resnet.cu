@@ -1,0 +1,524 @@
+// lip_resnet.cu — probe-batched GGN / W / W^T operators for residual conv programs (ResNet1M, src/scalemodels.py:70-157).
+//
+// Same operator semantics as lip_model.cu (src/ggn.py:9-146).  The network is a chain of conv + BatchNorm(eval) units
+//   y = relu?( scale * xhat + beta + skip ),   xhat = (conv(x, W) - mean) * rsqrt(var + eps),   g = scale * rsqrt(var + eps)
+// (stem; per BasicBlock: conv-bn-relu, conv-bn, optional 1x1 strided conv-bn on the residual, add, relu), a global mean and
+// a Dense head.  BatchNorm scale / bias ARE parameters (they are in the flat vector); mean / var are constants (ggn.py:52).
+//   JVP  unit:  dY[b] = mask * ( g * (Aop . dW[b] + col(T_src[b]) . W) + xhat * dscale[b] + dbeta[b] + T_skip[b] )
+//   VJP  unit:  Dy = Dout * mask;  gbeta = colsum Dy;  gscale = colsum (Dy * xhat);  cot[skip] (+)= Dy;  Dh = g * Dy;
+//               gW[b] = Aop^T . Dh[b];  cot[src] (+)= col2im(Dh[b] . W^T)
+// Convs run as GEMMs over im2col patches (Aop cached at bind; col(.) materialised per call), on the fp32 SIMT kernels.
+// Tangents / cotangents live in four rotating [B, M, H, W, C] slots (block input, branch, shortcut, block output).
+#include <new>
+#include <vector>
+
+#include "lip_model.cuh"
+
+using namespace lip;
+
+void lip_model::free_resnet_cache() {
+  for (auto& u : RB) {
+    if (u.Aop) cudaFree(u.Aop);
+    if (u.xhat) cudaFree(u.xhat);
+    if (u.mask) cudaFree(u.mask);
+    if (u.g) cudaFree(u.g);
+    u.Aop = u.xhat = u.mask = u.g = nullptr;
+  }
+  if (rn_mean_act) cudaFree(rn_mean_act);
+  rn_mean_act = nullptr;
+}
+
+namespace {
+
+constexpr float BN_EPS = 1e-5f;   // flax.linen.BatchNorm default epsilon
+
+inline unsigned ew_grid(long long total) {
+  long long g = (total + 255) / 256;
+  if (g > 148ll * 32) g = 148ll * 32;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+// bind time: h = conv output [R, C] -> xhat, g;  y = relu?(scale * xhat + beta + skip) -> out, mask
+__global__ void bn_fwd_kernel(const float* __restrict__ h, const float* __restrict__ mean, const float* __restrict__ var,
+                              const float* __restrict__ scale, const float* __restrict__ beta, const float* __restrict__ skip,
+                              float* __restrict__ xhat, float* __restrict__ mask, float* __restrict__ g, float* __restrict__ out,
+                              long long total, int C, int relu) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const float rstd = rsqrtf(var[c] + BN_EPS);
+    const float xh = (h[idx] - mean[c]) * rstd;
+    xhat[idx] = xh;
+    if (idx < C) g[c] = scale[c] * rstd;
+    float y = fmaf(scale[c], xh, beta[c]);
+    if (skip) y += skip[idx];
+    if (relu) {
+      mask[idx] = y > 0.f ? 1.f : 0.f;
+      y = fmaxf(y, 0.f);
+    }
+    out[idx] = y;
+  }
+}
+
+// dY[b][i] = mask[i] * ( g[c] * dH[b][i] + xhat[i] * dscale[b][c] + dbeta[b][c] + Tskip[b][i] ),  i in [0, per_z)
+__global__ void bn_jvp_kernel(const float* __restrict__ dH, const float* __restrict__ g, const float* __restrict__ xhat,
+                              const float* __restrict__ mask, const float* __restrict__ dscale, const float* __restrict__ dbeta,
+                              long long pstride, const float* __restrict__ tskip, float* __restrict__ out, long long total,
+                              long long per_z, int C) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long z = idx / per_z, i = idx % per_z;
+    const int c = (int)(i % C);
+    float v = fmaf(g[c], dH[idx], fmaf(__ldg(xhat + i), __ldg(dscale + z * pstride + c), __ldg(dbeta + z * pstride + c)));
+    if (tskip) v += tskip[idx];
+    if (mask) v *= __ldg(mask + i);
+    out[idx] = v;
+  }
+}
+
+// Dy = Dout * mask;  cot_skip (+)= Dy;  Dh = g[c] * Dy
+__global__ void bn_vjp_kernel(const float* __restrict__ dout, const float* __restrict__ mask, const float* __restrict__ g,
+                              float* __restrict__ dh, float* cot_skip, int skip_accumulate, long long total, long long per_z,
+                              int C) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx % per_z;
+    const int c = (int)(i % C);
+    float dy = dout[idx];
+    if (mask) dy *= __ldg(mask + i);
+    if (cot_skip) cot_skip[idx] = skip_accumulate ? cot_skip[idx] + dy : dy;
+    dh[idx] = g[c] * dy;
+  }
+}
+
+// one CTA per probe, blockDim.x a multiple of C: every thread sees one column of the flat [R * C] arrays
+//   gbeta[c] = sum_r Dout*mask,  gscale[c] = sum_r Dout*mask*xhat;  out = scale * sum + add_scale * add
+__global__ void bn_param_grad_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
+                                     const float* __restrict__ xhat, long long per_z, int C, float* __restrict__ out_beta,
+                                     float* __restrict__ out_scale, long long out_sz, float scale,
+                                     const float* __restrict__ add_beta, const float* __restrict__ add_scale_p, long long add_sz,
+                                     float add_scale) {
+  extern __shared__ float sm[];
+  float* s1 = sm;
+  float* s2 = sm + blockDim.x;
+  const long long b = blockIdx.x;
+  const float* d = dout + b * per_z;
+  float a1 = 0.f, a2 = 0.f;
+  for (long long i = threadIdx.x; i < per_z; i += blockDim.x) {
+    float dy = __ldg(d + i);
+    if (mask) dy *= __ldg(mask + i);
+    a1 += dy;
+    a2 = fmaf(dy, __ldg(xhat + i), a2);
+  }
+  s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
+  __syncthreads();
+  if ((int)threadIdx.x < C) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int k = threadIdx.x; k < (int)blockDim.x; k += C) { t1 += s1[k]; t2 += s2[k]; }
+    float vb = scale * t1, vs = scale * t2;
+    if (add_beta) { vb += add_scale * add_beta[b * add_sz + threadIdx.x]; vs += add_scale * add_scale_p[b * add_sz + threadIdx.x]; }
+    out_beta[b * out_sz + threadIdx.x] = vb;
+    out_scale[b * out_sz + threadIdx.x] = vs;
+  }
+}
+
+// out[mz][c] = mean over hw of in[mz][hw][c]
+__global__ void global_mean_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int HW, int C) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long mz = idx / C;
+    const int c = (int)(idx % C);
+    const float* p = in + mz * HW * C + c;
+    float acc = 0.f;
+    for (int i = 0; i < HW; ++i) acc += p[(long long)i * C];
+    out[idx] = acc / (float)HW;
+  }
+}
+// cot_in[mz][hw][c] = cot_out[mz][c] / HW
+__global__ void global_mean_bwd_kernel(const float* __restrict__ g, float* __restrict__ out, long long total, int HW, int C) {
+  const float inv = 1.f / (float)HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long mz = idx / ((long long)HW * C);
+    const int c = (int)(idx % C);
+    out[idx] = inv * __ldg(g + mz * C + c);
+  }
+}
+
+struct RnWs {
+  float* slot[4];   // tangent / cotangent tensors [B, M, slot_elems]
+  float* raw;       // conv GEMM output dH / Dh, [B, max R*cout]
+  float* col;       // im2col of a tangent / Dh . W^T, [B, max R*Kc]
+  float* head;      // [B, M, C_last] mean tangent / cotangent  +  [B, M, K] delta at the logits
+  float* dl;
+};
+struct RnSizes { size_t slot, raw, col, head, dl; };
+
+RnSizes rn_sizes(const lip_model* m, int64_t B) {
+  RnSizes z{};
+  z.slot = align_up((size_t)B * m->M * (size_t)m->rn_slot_elems, 64);
+  size_t raw = 0, col = 0;
+  for (const ConvBN& u : m->RB) {
+    const size_t r = (size_t)B * m->M * u.P() * u.cout;
+    raw = r > raw ? r : raw;
+    if (u.src != -2) {
+      const size_t c = (size_t)B * m->M * u.P() * u.Kc();
+      col = c > col ? c : col;
+    }
+  }
+  z.raw = align_up(raw, 64); z.col = align_up(col, 64);
+  z.head = align_up((size_t)B * m->M * m->rn_C, 64);
+  z.dl = align_up((size_t)B * m->M * m->K, 64);
+  return z;
+}
+
+int rn_carve(const lip_model* m, int64_t B, void* ws, size_t bytes, RnWs* w) {
+  const size_t need = resnet_ws_bytes(m, B);
+  if (bytes < need || ws == nullptr) {
+    set_error("workspace too small: need %zu bytes, got %zu", need, bytes);
+    return LIP_ERR_WORKSPACE;
+  }
+  const RnSizes z = rn_sizes(m, B);
+  float* p = (float*)align_up((uintptr_t)ws, 256);
+  for (int i = 0; i < 4; ++i) { w->slot[i] = p; p += z.slot; }
+  w->raw = p; p += z.raw;
+  w->col = p; p += z.col;
+  w->head = p; p += z.head;
+  w->dl = p;
+  return LIP_OK;
+}
+
+// ---- JVP sweep: V[B, D] -> dlogits [B, M, K] in dst --------------------------------------------------------------------
+int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* dst, cudaStream_t st) {
+  for (const ConvBN& u : m->RB) {
+    const int64_t R = m->M * u.P(), Kc = u.Kc();
+    GemmProblem p;
+    p.M = R; p.N = u.cout; p.K = Kc; p.batch = B;
+    p.A1 = {u.Aop, 0, Kc, 1};
+    p.B1 = {V + u.woff, m->D, u.cout, 1};
+    if (u.src != -2) {
+      int rc = im2col(w.slot[u.src], w.col, B * m->M, u.Hi, u.Wi, u.cin, u.pad_h, u.pad_w, u.stride, u.kh, u.kw, u.Ho, u.Wo, st);
+      if (rc) return rc;
+      p.A2 = {w.col, R * Kc, Kc, 1};
+      p.B2 = {m->theta + u.woff, 0, u.cout, 1};
+      p.K2 = Kc;
+    }
+    p.C = w.raw; p.c_sz = R * (int64_t)u.cout; p.c_sm = u.cout;
+    int rc = gemm_simt(p, st);
+    if (rc) return rc;
+    const long long per_z = R * (long long)u.cout, total = per_z * B;
+    bn_jvp_kernel<<<ew_grid(total), 256, 0, st>>>(w.raw, u.g, u.xhat, u.mask, V + u.scale_off, V + u.beta_off, m->D,
+                                                  u.skip >= 0 ? w.slot[u.skip] : nullptr, w.slot[u.dst], total, per_z, u.cout);
+    LIP_LAUNCH_CHECK();
+  }
+  const int HW = m->rn_H * m->rn_W, C = m->rn_C;
+  {
+    const long long total = (long long)B * m->M * C;
+    global_mean_kernel<<<ew_grid(total), 256, 0, st>>>(w.slot[m->rn_last_slot], w.head, total, HW, C);
+    LIP_LAUNCH_CHECK();
+  }
+  GemmProblem p;   // head: dlogits[b] = mean_act . dWd[b] + Tmean[b] . Wd + dbd[b]
+  p.M = m->M; p.N = m->K; p.K = C; p.batch = B;
+  p.A1 = {m->rn_mean_act, 0, C, 1};
+  p.B1 = {V + m->rn_dense_woff, m->D, m->K, 1};
+  p.A2 = {w.head, m->M * (int64_t)C, C, 1};
+  p.B2 = {m->theta + m->rn_dense_woff, 0, m->K, 1};
+  p.K2 = C;
+  p.C = dst; p.c_sz = m->M * (int64_t)m->K; p.c_sm = m->K;
+  p.epi.bias = V + m->rn_dense_boff; p.epi.bias_sz = m->D;
+  return gemm_simt(p, st);
+}
+
+// ---- VJP sweep: dl [B, M, K] -> out[B, D] = scale * J^T dl + add_scale * add ---------------------------------------------
+int rn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const RnWs& w, float* out, float scale, const float* add,
+                 float add_scale, cudaStream_t st) {
+  const int HW = m->rn_H * m->rn_W, C = m->rn_C;
+  {  // head
+    GemmProblem p;
+    p.M = C; p.N = m->K; p.K = m->M; p.batch = B;
+    p.A1 = {m->rn_mean_act, 0, 1, C};
+    p.B1 = {dl, m->M * (int64_t)m->K, m->K, 1};
+    p.C = out + m->rn_dense_woff; p.c_sz = m->D; p.c_sm = m->K;
+    p.epi.scale = scale;
+    if (add) { p.epi.add = add + m->rn_dense_woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+    int rc = gemm_simt(p, st);
+    if (rc) return rc;
+    rc = launch_bias_grad(dl, nullptr, m->M, m->K, m->K, B, out + m->rn_dense_boff, m->D, scale,
+                          add ? add + m->rn_dense_boff : nullptr, m->D, add_scale, st);
+    if (rc) return rc;
+    GemmProblem q;   // cotangent of the mean activations: [M x C] = dl [M x K] . Wd^T
+    q.M = m->M; q.N = C; q.K = m->K; q.batch = B;
+    q.A1 = {dl, m->M * (int64_t)m->K, m->K, 1};
+    q.B1 = {m->theta + m->rn_dense_woff, 0, 1, m->K};
+    q.C = w.head; q.c_sz = m->M * (int64_t)C; q.c_sm = C;
+    rc = gemm_simt(q, st);
+    if (rc) return rc;
+    const long long total = (long long)B * m->M * HW * C;
+    global_mean_bwd_kernel<<<ew_grid(total), 256, 0, st>>>(w.head, w.slot[m->rn_last_slot], total, HW, C);
+    LIP_LAUNCH_CHECK();
+  }
+  for (int i = (int)m->RB.size() - 1; i >= 0; --i) {
+    const ConvBN& u = m->RB[i];
+    const int64_t R = m->M * u.P(), Kc = u.Kc();
+    const long long per_z = R * (long long)u.cout, total = per_z * B;
+    const float* dout = w.slot[u.dst];
+    {  // BatchNorm parameter gradients
+      const int threads = u.cout * (512 / u.cout > 0 ? 512 / u.cout : 1);
+      bn_param_grad_kernel<<<(unsigned)B, threads, 2 * threads * sizeof(float), st>>>(
+          dout, u.mask, u.xhat, per_z, u.cout, out + u.beta_off, out + u.scale_off, m->D, scale,
+          add ? add + u.beta_off : nullptr, add ? add + u.scale_off : nullptr, m->D, add_scale);
+      LIP_LAUNCH_CHECK();
+    }
+    // Dy -> skip cotangent (first contribution to that slot: plain store), Dh = g * Dy
+    bn_vjp_kernel<<<ew_grid(total), 256, 0, st>>>(dout, u.mask, u.g, w.raw, u.skip >= 0 ? w.slot[u.skip] : nullptr, 0, total,
+                                                  per_z, u.cout);
+    LIP_LAUNCH_CHECK();
+    {  // kernel gradient [Kc x cout] = Aop^T . Dh
+      GemmProblem p;
+      p.M = Kc; p.N = u.cout; p.K = R; p.batch = B;
+      p.A1 = {u.Aop, 0, 1, Kc};
+      p.B1 = {w.raw, per_z, u.cout, 1};
+      p.C = out + u.woff; p.c_sz = m->D; p.c_sm = u.cout;
+      p.epi.scale = scale;
+      if (add) { p.epi.add = add + u.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+      int rc = gemm_simt(p, st);
+      if (rc) return rc;
+    }
+    if (u.src == -2) continue;
+    GemmProblem q;   // G [R x Kc] = Dh . W^T, scattered back to the input image
+    q.M = R; q.N = Kc; q.K = u.cout; q.batch = B;
+    q.A1 = {w.raw, per_z, u.cout, 1};
+    q.B1 = {m->theta + u.woff, 0, 1, u.cout};
+    q.C = w.col; q.c_sz = R * Kc; q.c_sm = Kc;
+    int rc = gemm_simt(q, st);
+    if (rc) return rc;
+    rc = col2im(w.col, w.slot[u.src], B * m->M, u.Hi, u.Wi, u.cin, u.pad_h, u.pad_w, u.stride, u.kh, u.kw, u.Ho, u.Wo,
+                u.accumulate, st);
+    if (rc) return rc;
+  }
+  return LIP_OK;
+}
+
+}  // namespace
+
+namespace lip {
+
+int resnet_parse(lip_model* m, const lip_layer_desc* L, int32_t n, int64_t num_params) {
+  m->is_resnet = true;
+  const lip_layer_desc& in = L[0];
+  LIP_REQUIRE(in.kh > 0 && in.kw > 0 && in.in_features > 0, "lip_model_create: INPUT needs height, width, channels > 0");
+  m->in_h = in.kh; m->in_w = in.kw; m->in_c = in.in_features;
+  int H = in.kh, W = in.kw, C = in.in_features;
+  int64_t counted = 0, stats = 0;
+  int64_t max_elems = (int64_t)H * W * C;
+  int i = 1;
+  // conv (+ the BATCHNORM that must follow it) -> one ConvBN unit; (Hs, Ws, Cs) is the unit's input tensor
+  auto conv_bn = [&](int ci, int bi, int Hs, int Ws, int Cs, ConvBN* u) -> int {
+    const lip_layer_desc& c = L[ci];
+    const lip_layer_desc& b = L[bi];
+    LIP_REQUIRE(c.in_features == Cs && c.out_features > 0 && c.kh > 0 && c.kw > 0 && (c.stride == 1 || c.stride == 2) && c.pad >= 0,
+                "lip_model_create: conv at %d: bad shape (cin %d vs %d, stride %d)", ci, c.in_features, Cs, c.stride);
+    LIP_REQUIRE(b.in_features == c.out_features, "lip_model_create: BATCHNORM at %d has %d channels, conv has %d", bi,
+                b.in_features, c.out_features);
+    u->Hi = Hs; u->Wi = Ws; u->cin = Cs; u->kh = c.kh; u->kw = c.kw; u->stride = c.stride; u->pad_h = u->pad_w = c.pad;
+    u->Ho = (Hs + c.stride - 1) / c.stride; u->Wo = (Ws + c.stride - 1) / c.stride;      // SAME
+    u->cout = c.out_features;
+    u->woff = c.kernel_offset; u->scale_off = b.kernel_offset; u->beta_off = b.bias_offset;
+    const int64_t nk = (int64_t)c.kh * c.kw * Cs * c.out_features;
+    LIP_REQUIRE(c.kernel_offset >= 0 && c.kernel_offset + nk <= num_params && b.kernel_offset >= 0 && b.bias_offset >= 0 &&
+                    b.kernel_offset + c.out_features <= num_params && b.bias_offset + c.out_features <= num_params,
+                "lip_model_create: conv/BATCHNORM at %d/%d has an invalid offset", ci, bi);
+    LIP_REQUIRE(c.out_features <= 512, "lip_model_create: conv at %d: more than 512 channels", ci);
+    u->stats_off = stats;
+    stats += 2 * c.out_features;
+    counted += nk + 2 * c.out_features;
+    const int64_t e = (int64_t)u->Ho * u->Wo * u->cout;
+    max_elems = e > max_elems ? e : max_elems;
+    return LIP_OK;
+  };
+  auto is = [&](int k, int op) { return k < n && L[k].op == op; };
+  LIP_REQUIRE(is(1, LIP_OP_CONV2D) && is(2, LIP_OP_BATCHNORM) && is(3, LIP_OP_RELU),
+              "lip_model_create: a residual program starts INPUT, CONV2D, BATCHNORM, RELU");
+  int x = 0;   // slot of the current tensor
+  {
+    ConvBN u;
+    int rc = conv_bn(1, 2, H, W, C, &u);
+    if (rc) return rc;
+    u.relu = 1; u.src = -2; u.dst = x; u.skip = -1;
+    m->RB.push_back(u);
+    H = u.Ho; W = u.Wo; C = u.cout;
+  }
+  i = 4;
+  while (is(i, LIP_OP_RES_SAVE)) {
+    LIP_REQUIRE(is(i + 1, LIP_OP_CONV2D) && is(i + 2, LIP_OP_BATCHNORM) && is(i + 3, LIP_OP_RELU) && is(i + 4, LIP_OP_CONV2D) &&
+                    is(i + 5, LIP_OP_BATCHNORM),
+                "lip_model_create: block at %d must be RES_SAVE, CONV2D, BATCHNORM, RELU, CONV2D, BATCHNORM, ...", i);
+    int free_slots[3], nf = 0;
+    for (int s = 0; s < 4; ++s) if (s != x) free_slots[nf++] = s;
+    const int y = free_slots[0], r = free_slots[1], o = free_slots[2];
+    ConvBN c0, c1;
+    int rc = conv_bn(i + 1, i + 2, H, W, C, &c0);
+    if (rc) return rc;
+    c0.relu = 1; c0.src = x; c0.dst = y; c0.skip = -1; c0.accumulate = 1;   // x's cotangent already holds the skip branch
+    rc = conv_bn(i + 4, i + 5, c0.Ho, c0.Wo, c0.cout, &c1);
+    if (rc) return rc;
+    LIP_REQUIRE(c1.stride == 1, "lip_model_create: second conv of the block at %d must have stride 1", i);
+    int j = i + 6;
+    bool proj = false;
+    ConvBN pj;
+    if (is(j, LIP_OP_RES_CONV2D)) {
+      LIP_REQUIRE(is(j + 1, LIP_OP_RES_BATCHNORM), "lip_model_create: RES_CONV2D at %d must be followed by RES_BATCHNORM", j);
+      rc = conv_bn(j, j + 1, H, W, C, &pj);
+      if (rc) return rc;
+      LIP_REQUIRE(pj.Ho == c1.Ho && pj.Wo == c1.Wo && pj.cout == c1.cout, "lip_model_create: shortcut at %d does not match the branch shape", j);
+      pj.relu = 0; pj.src = x; pj.dst = r; pj.skip = -1; pj.accumulate = 0;
+      proj = true;
+      j += 2;
+    } else {
+      LIP_REQUIRE(c1.Ho == H && c1.Wo == W && c1.cout == C, "lip_model_create: block at %d changes shape but has no shortcut conv", i);
+    }
+    LIP_REQUIRE(is(j, LIP_OP_RES_ADD) && is(j + 1, LIP_OP_RELU), "lip_model_create: block at %d must end with RES_ADD, RELU", i);
+    c1.relu = 1; c1.src = y; c1.dst = o; c1.skip = proj ? r : x; c1.accumulate = 0;
+    m->RB.push_back(c0);
+    if (proj) m->RB.push_back(pj);
+    m->RB.push_back(c1);
+    H = c1.Ho; W = c1.Wo; C = c1.cout;
+    x = o;
+    i = j + 2;
+  }
+  LIP_REQUIRE(is(i, LIP_OP_GLOBAL_MEAN) && is(i + 1, LIP_OP_DENSE) && i + 2 == n,
+              "lip_model_create: a residual program ends with GLOBAL_MEAN, DENSE (op %d of %d)", i, n);
+  const lip_layer_desc& d = L[i + 1];
+  LIP_REQUIRE(d.in_features == C && d.out_features > 0 && d.bias_offset >= 0 && d.kernel_offset >= 0 &&
+                  d.bias_offset + d.out_features <= num_params && d.kernel_offset + (int64_t)C * d.out_features <= num_params,
+              "lip_model_create: DENSE head: in_features %d != %d channels (or bad offset)", d.in_features, C);
+  counted += (int64_t)C * d.out_features + d.out_features;
+  LIP_REQUIRE(counted == num_params, "lip_model_create: layers hold %lld parameters but num_params = %lld", (long long)counted,
+              (long long)num_params);
+  m->rn_last_slot = x; m->rn_H = H; m->rn_W = W; m->rn_C = C;
+  m->rn_dense_boff = d.bias_offset; m->rn_dense_woff = d.kernel_offset;
+  m->rn_nstats = stats;
+  m->rn_slot_elems = max_elems;
+  m->K = d.out_features;
+  return LIP_OK;
+}
+
+int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaStream_t st) {
+  LIP_REQUIRE(m->rn_stats != nullptr, "lip_model_bind: BatchNorm statistics missing (call lip_model_set_bn_stats first)");
+  float* act[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* tmp = nullptr;
+  size_t max_raw = 0;
+  for (const ConvBN& u : m->RB) {
+    const size_t r = (size_t)M * u.P() * u.cout;
+    max_raw = r > max_raw ? r : max_raw;
+  }
+  auto cleanup = [&]() { for (auto& a : act) if (a) cudaFree(a); if (tmp) cudaFree(tmp); };
+  for (auto& a : act) {
+    if (cudaMalloc(&a, sizeof(float) * (size_t)M * m->rn_slot_elems + 256) != cudaSuccess) {
+      cleanup(); set_error("lip_model_bind: out of device memory (activations)"); return LIP_ERR_CUDA;
+    }
+  }
+  if (cudaMalloc(&tmp, sizeof(float) * max_raw + 256) != cudaSuccess) {
+    cleanup(); set_error("lip_model_bind: out of device memory"); return LIP_ERR_CUDA;
+  }
+  int rc = LIP_OK;
+  for (ConvBN& u : m->RB) {
+    const int64_t R = M * u.P(), Kc = u.Kc();
+    if (cudaMalloc(&u.Aop, sizeof(float) * (size_t)R * Kc + 256) != cudaSuccess ||
+        cudaMalloc(&u.xhat, sizeof(float) * (size_t)R * u.cout + 256) != cudaSuccess ||
+        cudaMalloc(&u.g, sizeof(float) * u.cout) != cudaSuccess ||
+        (u.relu && cudaMalloc(&u.mask, sizeof(float) * (size_t)R * u.cout + 256) != cudaSuccess)) {
+      cleanup(); set_error("lip_model_bind: out of device memory (conv cache)"); return LIP_ERR_CUDA;
+    }
+    const float* x = u.src == -2 ? Z : act[u.src];
+    rc = im2col(x, u.Aop, M, u.Hi, u.Wi, u.cin, u.pad_h, u.pad_w, u.stride, u.kh, u.kw, u.Ho, u.Wo, st);
+    if (rc) break;
+    GemmProblem p;
+    p.M = R; p.N = u.cout; p.K = Kc; p.batch = 1;
+    p.A1 = {u.Aop, 0, Kc, 1};
+    p.B1 = {theta + u.woff, 0, u.cout, 1};
+    p.C = tmp; p.c_sz = 0; p.c_sm = u.cout;
+    rc = gemm_simt(p, st);
+    if (rc) break;
+    const long long total = R * (long long)u.cout;
+    bn_fwd_kernel<<<ew_grid(total), 256, 0, st>>>(tmp, m->rn_stats + u.stats_off, m->rn_stats + u.stats_off + u.cout,
+                                                  theta + u.scale_off, theta + u.beta_off, u.skip >= 0 ? act[u.skip] : nullptr,
+                                                  u.xhat, u.mask, u.g, act[u.dst], total, u.cout, u.relu);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) { rc = LIP_ERR_CUDA; set_error("lip_model_bind: bn_fwd launch failed"); break; }
+  }
+  if (!rc) {
+    const int HW = m->rn_H * m->rn_W, C = m->rn_C;
+    if (cudaMalloc(&m->rn_mean_act, sizeof(float) * (size_t)M * C + 256) != cudaSuccess ||
+        cudaMalloc(&m->logits, sizeof(float) * (size_t)M * m->K) != cudaSuccess ||
+        cudaMalloc(&m->P, sizeof(float) * (size_t)M * m->K) != cudaSuccess ||
+        cudaMalloc(&m->S, sizeof(float) * (size_t)M * m->K) != cudaSuccess) {
+      cleanup(); set_error("lip_model_bind: out of device memory (head)"); return LIP_ERR_CUDA;
+    }
+    const long long total = (long long)M * C;
+    global_mean_kernel<<<ew_grid(total), 256, 0, st>>>(act[m->rn_last_slot], m->rn_mean_act, total, HW, C);
+    count_launch();
+    GemmProblem p;
+    p.M = M; p.N = m->K; p.K = C; p.batch = 1;
+    p.A1 = {m->rn_mean_act, 0, C, 1};
+    p.B1 = {theta + m->rn_dense_woff, 0, m->K, 1};
+    p.C = m->logits; p.c_sz = 0; p.c_sm = m->K;
+    p.epi.bias = theta + m->rn_dense_boff; p.epi.bias_sz = 0;
+    rc = gemm_simt(p, st);
+    if (!rc && m->model_type == LIP_CLASSIFIER) rc = launch_softmax(m->logits, m->P, m->S, M, m->K, st);
+  }
+  // the temporaries are read by work queued on `st`: free them only after it has drained (bind is not a hot call)
+  cudaStreamSynchronize(st);
+  cleanup();
+  if (rc) return rc;
+  m->tc_on = false;
+  m->bound = true;
+  return LIP_OK;
+}
+
+size_t resnet_ws_bytes(const lip_model* m, int64_t B) {
+  const RnSizes z = rn_sizes(m, B);
+  return (4 * z.slot + z.raw + z.col + z.head + z.dl) * sizeof(float) + 512;
+}
+
+int resnet_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* ws, size_t bytes,
+                  cudaStream_t st) {
+  RnWs w;
+  int rc = rn_carve(m, B, ws, bytes, &w);
+  if (rc) return rc;
+  rc = rn_jvp_sweep(m, V, B, w, w.dl, st);
+  if (rc) return rc;
+  if (m->model_type == LIP_CLASSIFIER) {
+    rc = launch_factor(w.dl, w.dl, m, B, 0, 1.f, st);
+    if (rc) return rc;
+  }
+  return rn_vjp_sweep(m, w.dl, B, w, out, recal, alpha != 0.f ? V : nullptr, alpha, st);
+}
+
+int resnet_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scale, int32_t factor, void* ws, size_t bytes,
+                    cudaStream_t st) {
+  RnWs w;
+  int rc = rn_carve(m, B, ws, bytes, &w);
+  if (rc) return rc;
+  rc = rn_jvp_sweep(m, V, B, w, out, st);
+  if (rc) return rc;
+  float s = scale;
+  if (factor == LIP_FACTOR_SQRT && m->model_type == LIP_REGRESSOR) s *= expf(-0.5f * m->logvar);
+  if (factor == LIP_FACTOR_SQRT && m->model_type == LIP_CLASSIFIER) return launch_factor(out, out, m, B, 1, s, st);
+  if (s != 1.f) return launch_scale_copy(out, out, B * m->M * m->K, s, st);
+  return LIP_OK;
+}
+
+int resnet_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,
+                   float add_scale, void* ws, size_t bytes, cudaStream_t st) {
+  RnWs w;
+  int rc = rn_carve(m, B, ws, bytes, &w);
+  if (rc) return rc;
+  float s = scale;
+  if (factor == LIP_FACTOR_SQRT && m->model_type == LIP_CLASSIFIER) {
+    rc = launch_factor(U, w.dl, m, B, 2, 1.f, st);
+  } else {
+    if (factor == LIP_FACTOR_SQRT) s *= expf(-0.5f * m->logvar);
+    rc = launch_scale_copy(U, w.dl, B * m->M * m->K, 1.f, st);
+  }
+  if (rc) return rc;
+  return rn_vjp_sweep(m, w.dl, B, w, out, s, add, add_scale, st);
+}
+
+}  // namespace lip

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _cabi as cabi
-from ._runtime import BoundModel, ConvProgramSpec, MLPSpec, dev_f32
+from ._runtime import BoundModel, ConvProgramSpec, MLPSpec, ResNetProgramSpec, dev_f32
 from .utils import flatten_nn_params
 
 _ACT_BY_CLASS = {"SimpleRegressor": cabi.OP_GELU_TANH, "SimpleClassifier": cabi.OP_TANH,
@@ -36,12 +36,12 @@ def _strip(params):
     return tree
 
 
-def _spec_from(module, params, model_type) -> MLPSpec:
+def _spec_from(module, params, model_type, batch_stats=None, in_shape=None) -> MLPSpec:
     """Pattern-match the parameter tree + module class onto the layer program the CUDA library executes.
     Anything that is not a Dense/activation stack is rejected loudly (no fallback)."""
     cls = type(module).__name__ if module is not None else None
     if cls == "ResNet1M":
-        raise NotImplementedError("ResNet1M: conv/BN/residual JVP/VJP kernels are not built yet (SURVEY §8a M4)")
+        return ResNetProgramSpec(_strip(params), batch_stats, in_shape, model_type)
     if cls == "LeNet5":
         return _lenet5_spec(params, model_type)
     act = None
@@ -119,7 +119,10 @@ def _bind(state, Z, model_type, tensor_path: Optional[bool] = None) -> BoundMode
     if bm is not None:
         _BIND_CACHE.move_to_end(key)
         return bm
-    spec = _spec_from(_module_of(state), state.params, model_type)
+    module = _module_of(state)
+    if type(module).__name__ == "ResNet1M" and Zt.dim() == 4 and Zt.shape[-1] == 1:
+        Zt = Zt.repeat(1, 1, 1, 3)                      # scalemodels.py:126-127: grayscale inputs are tiled to 3 channels
+    spec = _spec_from(module, state.params, model_type, getattr(state, "batch_stats", None), tuple(Zt.shape[1:]))
     logvar = _logvar_of(state.params) if model_type == "regressor" else 0.0
     bm = BoundModel(spec, theta, Zt, logvar, tensor_path)
     _BIND_CACHE[key] = bm

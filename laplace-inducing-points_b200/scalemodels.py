@@ -1,8 +1,7 @@
 """Architecture descriptors mirroring /root/reference/src/scalemodels.py.
 
-LargeClassifier (scalemodels.py:52-67) and LeNet5 (scalemodels.py:11-49) run on the CUDA path.  ResNet1M
-(scalemodels.py:70-157) is declared so that configs parse, but its conv/BN/residual JVP/VJP kernels are a later
-SURVEY §8 row: binding it raises NotImplementedError loudly (no fallback)."""
+LargeClassifier (scalemodels.py:52-67), LeNet5 (scalemodels.py:11-49) and ResNet1M (scalemodels.py:70-157, eval-mode
+BatchNorm) run on the CUDA path; anything else raises loudly (no fallback)."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field
@@ -56,10 +55,26 @@ class LeNet5:
 
 @dataclass
 class ResNet1M:
+    """scalemodels.py:112-157 (+ BasicBlock :70-109).  Runs on the CUDA path as a residual conv program
+    (csrc/lip_resnet.cu), BatchNorm in eval mode with the running statistics of `variables['batch_stats']`."""
     num_classes: int = 10
+    model_type = "classifier"
 
-    def apply(self, *a, **k):
-        raise NotImplementedError("ResNet1M: conv/BN JVP/VJP kernels are not built yet (SURVEY §8a M4)")
+    def apply(self, variables, x, *args, train=False, mutable=False, **kwargs):
+        if train:
+            raise NotImplementedError("ResNet1M: only eval-mode BatchNorm (use_running_average) is on the hot path (ggn.py:52)")
+        from ._runtime import BoundModel, ResNetProgramSpec, dev_f32
+        from .ggn import _strip
+        from .utils import flatten_nn_params
+        xt = dev_f32(x)
+        if xt.dim() == 3:
+            xt = xt[None]
+        if xt.shape[-1] == 1:
+            xt = xt.repeat(1, 1, 1, 3)
+        params = {k: v for k, v in dict(variables).items() if k != "batch_stats"}
+        spec = ResNetProgramSpec(_strip(params), dict(variables).get("batch_stats"), tuple(xt.shape[1:]), "classifier")
+        theta, _ = flatten_nn_params(params)
+        return BoundModel(spec, theta, xt, 0.0).outputs()
 
 
 @dataclass

@@ -11,7 +11,7 @@ def rel_err(a, b):
 
 
 def make_pair(kind, *, hidden=(), n_out=10, in_dim=0, seed=0, logvar=0.0, toy_layout=False, in_shape=None):
-    """kind: 'regressor' | 'classifier' | 'large' | 'lenet5'.  Returns (oracle_state, lip_state)."""
+    """kind: 'regressor' | 'classifier' | 'large' | 'lenet5' | 'resnet1m'.  Returns (oracle_state, lip_state)."""
     import lip_b200  # noqa: F401
     from lip_b200 import scalemodels, toymodels
 
@@ -28,9 +28,12 @@ def make_pair(kind, *, hidden=(), n_out=10, in_dim=0, seed=0, logvar=0.0, toy_la
     elif kind == "lenet5":
         om = OM.LeNet5()
         mod = scalemodels.LeNet5()
+    elif kind == "resnet1m":
+        om = OM.ResNet1M(n_out, tuple(in_shape) if in_shape else (32, 32, 3))
+        mod = scalemodels.ResNet1M(n_out)
     else:
         raise ValueError(kind)
     variables = om.init(seed)
     ost = OM.OracleState(om, variables, toy_layout=toy_layout, logvar=logvar)
-    lst = scalemodels.TrainState(params=ost.params, apply_fn=mod.apply, batch_stats={})
+    lst = scalemodels.TrainState(params=ost.params, apply_fn=mod.apply, batch_stats=ost.batch_stats)
     return ost, lst

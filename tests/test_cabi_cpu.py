@@ -147,3 +147,29 @@ def test_conv_program_create_and_layout(cabi):
     assert create([inp, conv, relu, pool], 20) == cabi.ERR_INVALID                         # must end with DENSE
     odd = cabi.LayerDesc(cabi.OP_INPUT, 1, 0, 0, 0, 7, 7, 0, 0)                            # 7x7 -> 5x5: odd pool
     assert create([odd, conv, relu, pool, dense], 77) == cabi.ERR_INVALID
+
+
+def test_resnet_program_create(cabi):
+    """ResNet1M (scalemodels.py:70-157) as a residual conv program built from the parameter tree: accepted by
+    lip_model_create, D = 1,084,586, 21 conv+BatchNorm units -> 2 * 2016 running statistics."""
+    import ctypes as C
+    from oracle import models as OM
+    from lip_b200._runtime import ResNetProgramSpec
+    L = cabi.lib()
+    v = OM.ResNet1M(10, (32, 32, 3)).init(0)
+    spec = ResNetProgramSpec(v["params"], v["batch_stats"], (32, 32, 3), "classifier")
+    assert spec.num_params == 1084586 and spec.num_outputs == 10
+    assert spec.bn_stats.numel() == 2 * (32 * 7 + 64 * 7 + 128 * 7)
+    arr, n = spec.descs()
+    h = C.c_void_p()
+    assert L.lip_model_create(arr, n, cabi.CLASSIFIER, spec.num_params, C.byref(h)) == 0, L.lip_last_error()
+    assert L.lip_model_num_params(h) == 1084586 and L.lip_model_num_outputs(h) == 10
+    assert L.lip_model_destroy(h) == 0
+    # a block that changes shape without a shortcut conv is rejected
+    bad = [d for d in spec.ops if d.op not in (cabi.OP_RES_CONV2D, cabi.OP_RES_BATCHNORM)]
+    a = (cabi.LayerDesc * len(bad))(*bad)
+    assert L.lip_model_create(a, len(bad), cabi.CLASSIFIER, spec.num_params, C.byref(h)) == cabi.ERR_INVALID
+    # missing BatchNorm statistics are a host-side error
+    import pytest
+    with pytest.raises(ValueError):
+        ResNetProgramSpec(v["params"], {}, (32, 32, 3), "classifier")

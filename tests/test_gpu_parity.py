@@ -302,7 +302,7 @@ def test_unsupported_models_fail_loudly():
         ggn.compute_ggn_vp(st, torch.zeros(2, 28, 28, 1, device="cuda"), "classifier")
     st3 = scalemodels.TrainState(params={"Conv_0": {"kernel": np.zeros((3, 3, 3, 32), np.float32)}},
                                  apply_fn=scalemodels.ResNet1M().apply)
-    with pytest.raises(NotImplementedError):     # conv/BN/residual kernels: SURVEY 8a M4, not built
+    with pytest.raises(ValueError):              # a ResNet1M tree without its BatchNorm / blocks / head
         ggn.compute_ggn_vp(st3, torch.zeros(2, 32, 32, 3, device="cuda"), "classifier")
 
     class Weird:
@@ -438,3 +438,46 @@ def test_lenet5_hutchinson_and_predictive():
     got_j = bx.wt(cu(w), scale=1.0, factor=_cabi.FACTOR_NONE).cpu().numpy()
     ref_j = np.stack([O.jvp_outputs(ost, Xnew, wi.astype(np.float64)) for wi in w])
     assert rel_err(got_j, ref_j) < TOL_GGN
+
+
+# --------------------------------------------------------------------------------- residual conv programs (ResNet1M)
+def test_resnet1m_operators_match_oracle():
+    """M4 (scalemodels.py:70-157): stem + 9 BasicBlocks (two of them strided with a 1x1 shortcut) + global mean + Dense,
+    BatchNorm in eval mode with its scale / bias inside the flat parameter vector: forward, GGN-vector product, W^T, W
+    against the float64 oracle (torch autograd through the restated network)."""
+    from lip_b200 import ggn, lla
+    ost, lst = make_pair("resnet1m", n_out=10, seed=41, in_shape=(32, 32, 3))
+    rng = np.random.default_rng(42)
+    M, N = 2, 49000
+    Z = rng.random((M, 32, 32, 3)).astype(np.float32)
+    D = ost.flat()[0].size
+    assert D == 1084586                      # SURVEY 8a M4
+    bm = ggn._bind(lst, cu(Z), "classifier")
+    assert rel_err(bm.outputs().cpu().numpy(), O.model_outputs(ost, Z)) < 5e-6
+    V = rng.choice([-1.0, 1.0], size=(2, D)).astype(np.float32)
+    V[1] = rng.standard_normal(D).astype(np.float32)
+    ref_vp = O.compute_ggn_vp(ost, Z, "classifier", full_set_size=N)
+    ref = np.stack([ref_vp(v) for v in V.astype(np.float64)])
+    vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=N)
+    got = vp(cu(V)).cpu().numpy()
+    assert rel_err(got, ref) < TOL_GGN
+    alpha = 5e-3
+    cvp = lla.compute_curvature_approx(lst, cu(Z), "classifier", alpha, full_set_size=N)
+    assert rel_err(cvp(cu(V[0])).cpu().numpy(), ref[0] + alpha * V[0]) < TOL_GGN
+    Wo, WTo = O.compute_W_vps(ost, Z, "classifier", full_set_size=N)
+    Wg, WTg = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=N)
+    ref_wt = np.stack([WTo(v) for v in V.astype(np.float64)])
+    assert rel_err(WTg(cu(V)).cpu().numpy(), ref_wt) < TOL_GGN
+    U = rng.standard_normal(ref_wt.shape).astype(np.float32)
+    ref_w = np.stack([Wo(u) for u in U.astype(np.float64)])
+    assert rel_err(Wg(cu(U)).cpu().numpy(), ref_w) < TOL_GGN
+
+
+def test_resnet1m_grayscale_inputs_are_tiled():
+    """scalemodels.py:126-127: a 1-channel input is tiled to 3 channels before the stem."""
+    from lip_b200 import ggn
+    ost, lst = make_pair("resnet1m", n_out=10, seed=43, in_shape=(28, 28, 1))
+    rng = np.random.default_rng(44)
+    Z = rng.random((2, 28, 28, 1)).astype(np.float32)
+    bm = ggn._bind(lst, cu(Z), "classifier")
+    assert rel_err(bm.outputs().cpu().numpy(), O.model_outputs(ost, Z)) < 5e-6
