@@ -39,6 +39,10 @@ WORKLOADS = {
                 flop_per_product=512 * (4 * SIGMA_ALL + 4 * SIGMA_GE2)),          # 4.468 GFLOP
     "lenet5": dict(name="C4 LeNet5 (D=61706), M=200, N=60000, alpha=5e-3", M=200, N=60_000, alpha=5e-3, K=10,
                    flop_per_product=200 * (8 * 416_520 - 4 * 117_600)),           # 2,861,760 FLOP / point
+    # C5 shape at the reference's own largest M (config/scale/resnet1-2_cifar10.yml:15, m=100): the conv path
+    # materialises im2col patches, so BASELINE's synthetic M=4096 needs the implicit-GEMM kernel of a later round
+    "resnet1m": dict(name="C5 ResNet1M CIFAR-shaped 32x32x3 (D=1084586), M=100, N=49000, alpha=5e-3", M=100, N=49_000,
+                     alpha=5e-3, K=10, flop_per_product=100 * 1_300_000_000),     # ~1.30 GFLOP / point
 }
 M_POINTS, N_FULL, ALPHA = 512, 60_000, 1e-3
 FLOP_PER_PRODUCT = WORKLOADS["mlp"]["flop_per_product"]
@@ -73,6 +77,10 @@ def build_states(seed=1003, workload="mlp"):
     import numpy as np
     from helpers import make_pair
     rng = np.random.default_rng(seed + 1)
+    if workload == "resnet1m":
+        ost, lst = make_pair("resnet1m", n_out=10, seed=seed, in_shape=(32, 32, 3))
+        Z = rng.random((M_POINTS, 32, 32, 3), dtype=np.float32)
+        return ost, lst, Z
     if workload == "lenet5":
         ost, lst = make_pair("lenet5", seed=seed)
         Z = rng.random((M_POINTS, 28, 28, 1), dtype=np.float32)

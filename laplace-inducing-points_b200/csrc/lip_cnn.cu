@@ -246,6 +246,7 @@ int cnn_jvp_sweep(lip_model* m, const float* V, int64_t B, const CnnWs& w, float
 int cnn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const CnnWs& w, float* out, float scale, const float* add,
                   float add_scale, cudaStream_t st) {
   const int nS = (int)m->CS.size();
+  const size_t col_elems = cnn_sizes(m, B).col;
   const float* d = dl;     // delta w.r.t. the pre-activation of stage i, [B, M*P, cout]
   for (int i = nS - 1; i >= 0; --i) {
     const ConvStage& s = m->CS[i];
@@ -258,6 +259,7 @@ int cnn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const CnnWs& w, floa
       p.C = out + s.woff; p.c_sz = m->D; p.c_sm = s.cout;
       p.epi.scale = scale;
       if (add) { p.epi.add = add + s.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+      p.splitk_ws = w.col; p.splitk_ws_elems = (int64_t)col_elems;      // col is free here (used again by the G GEMM below)
       int rc = gemm_simt(p, st);
       if (rc) return rc;
       rc = launch_bias_grad(d, nullptr, R, s.cout, s.cout, B, out + s.boff, m->D, scale, add ? add + s.boff : nullptr, m->D,

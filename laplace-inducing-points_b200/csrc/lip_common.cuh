@@ -70,6 +70,10 @@ struct GemmProblem {
   int64_t K2 = 0;
   float* C = nullptr; int64_t c_sz = 0, c_sm = 0;  // n stride is 1
   GemmEpilogue epi;
+  // optional split-K scratch (floats): long-K, few-tile problems (per-probe conv weight gradients: K = points x pixels)
+  // are cut into K slices whose partial tiles land here and are reduced, in a fixed order, by a second kernel that
+  // applies the epilogue.  Deterministic (no atomics).  Ignored when the problem already fills the GPU.
+  float* splitk_ws = nullptr; int64_t splitk_ws_elems = 0;
 };
 
 int gemm_simt(const GemmProblem& p, cudaStream_t stream);

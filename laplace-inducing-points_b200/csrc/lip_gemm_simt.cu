@@ -29,18 +29,21 @@ struct DevGemm {
   int act;
   float* dphi_out;
   float* C_lo;
+  int ksplit;          // > 1: blockIdx.y = m_tile * ksplit + slice; raw partial tiles go to `part`
+  float* part;         // [slice][z][M][N]
+  long long part_sz;   // stride between slices = batch * M * N
 };
 
-template <bool KC>  // KC: the contraction index is the contiguous one for this operand
+template <bool KC, int ROWS>  // KC: the contraction index is the contiguous one for this operand; ROWS: tile extent of the other
 __device__ __forceinline__ void load_tile(const DevOperand& op, long long zoff, int row0, int rows, int k0, int K,
-                                          bool is_a, float (&reg)[8]) {
-  // A tile: [BM rows(m)] x [BK k]; B tile: [BK k] x [BN cols(n)].  "row" below = the non-k index.
+                                          bool is_a, float (&reg)[ROWS * BK / NT]) {
+  // A tile: [ROWS rows(m)] x [BK k]; B tile: [BK k] x [ROWS cols(n)].  "row" below = the non-k index.
   const int tid = threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < ROWS * BK / NT; ++i) {
     int idx = tid + NT * i;
     int k, r;
-    if (KC) { k = idx % BK; r = idx / BK; } else { r = idx % BM; k = idx / BM; }
+    if (KC) { k = idx % BK; r = idx / BK; } else { r = idx % ROWS; k = idx / ROWS; }
     int gr = row0 + r, gk = k0 + k;
     float v = 0.f;
     if (gr < rows && gk < K) {
@@ -52,32 +55,38 @@ __device__ __forceinline__ void load_tile(const DevOperand& op, long long zoff, 
   }
 }
 
-template <bool KC>
-__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], const float (&reg)[8]) {
+template <bool KC, int ROWS>
+__device__ __forceinline__ void store_tile(float (*S)[ROWS + PAD], const float (&reg)[ROWS * BK / NT]) {
   const int tid = threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < ROWS * BK / NT; ++i) {
     int idx = tid + NT * i;
     int k, r;
-    if (KC) { k = idx % BK; r = idx / BK; } else { r = idx % BM; k = idx / BM; }
+    if (KC) { k = idx % BK; r = idx / BK; } else { r = idx % ROWS; k = idx / ROWS; }
     S[k][r] = reg[i];
   }
 }
 
-template <bool A_KC, bool B_KC>
+// BNT: tile width (128, or 64 / 32 for narrow outputs such as 32- and 64-channel convs); NJ = BNT / 16 columns per thread
+template <bool A_KC, bool B_KC, int BNT>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
+  constexpr int NJ = BNT / 16;
   __shared__ __align__(16) float As[2][BK][BM + PAD];
-  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BNT + PAD];
 
   const int z = blockIdx.z;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ks = g.ksplit > 1 ? g.ksplit : 1;
+  const int slice = blockIdx.y % ks;
+  const int m0 = (blockIdx.y / ks) * BM, n0 = blockIdx.x * BNT;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  // column j of this thread's micro-tile -> column of the tile
+  auto col_of = [&](int j) { return NJ == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : tx * NJ + j; };
 
-  float acc[8][8];
+  float acc[8][NJ];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
 
   const int npairs = g.A2.ptr ? 2 : 1;
   for (int pair = 0; pair < npairs; ++pair) {
@@ -85,48 +94,74 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
     const DevOperand& B = pair ? g.B2 : g.B1;
     const int K = pair ? g.K2 : g.K1;
     const long long za = (long long)z * A.sz, zb = (long long)z * B.sz;
-    const int nk = (K + BK - 1) / BK;
-    float ra[8], rb[8];
-    load_tile<A_KC>(A, za, m0, g.M, 0, K, true, ra);
-    load_tile<B_KC>(B, zb, n0, g.N, 0, K, false, rb);
-    store_tile<A_KC>(As[0], ra);
-    store_tile<B_KC>(Bs[0], rb);
+    const int nk_all = (K + BK - 1) / BK;
+    const int kt0 = (int)((long long)nk_all * slice / ks), nk = (int)((long long)nk_all * (slice + 1) / ks);
+    if (kt0 >= nk) continue;
+    float ra[8], rb[BNT * BK / NT];
+    load_tile<A_KC, BM>(A, za, m0, g.M, kt0 * BK, K, true, ra);
+    load_tile<B_KC, BNT>(B, zb, n0, g.N, kt0 * BK, K, false, rb);
+    store_tile<A_KC, BM>(As[kt0 & 1], ra);
+    store_tile<B_KC, BNT>(Bs[kt0 & 1], rb);
     __syncthreads();
-    for (int kt = 0; kt < nk; ++kt) {
+    for (int kt = kt0; kt < nk; ++kt) {
       const int cur = kt & 1;
       if (kt + 1 < nk) {
-        load_tile<A_KC>(A, za, m0, g.M, (kt + 1) * BK, K, true, ra);
-        load_tile<B_KC>(B, zb, n0, g.N, (kt + 1) * BK, K, false, rb);
+        load_tile<A_KC, BM>(A, za, m0, g.M, (kt + 1) * BK, K, true, ra);
+        load_tile<B_KC, BNT>(B, zb, n0, g.N, (kt + 1) * BK, K, false, rb);
       }
 #pragma unroll
       for (int k = 0; k < BK; ++k) {
         float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
         float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
-        float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
-        float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
         float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float b[NJ];
+        if (NJ == 8) {
+          float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+          float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+          b[NJ - 4] = b1.x; b[NJ - 3] = b1.y; b[NJ - 2] = b1.z; b[NJ - 1] = b1.w;
+        } else if (NJ == 4) {
+          float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+        } else {
+          float2 b0 = *reinterpret_cast<const float2*>(&Bs[cur][k][tx * 2]);
+          b[0] = b0.x; b[1] = b0.y;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
       if (kt + 1 < nk) {
-        store_tile<A_KC>(As[cur ^ 1], ra);
-        store_tile<B_KC>(Bs[cur ^ 1], rb);
+        store_tile<A_KC, BM>(As[cur ^ 1], ra);
+        store_tile<B_KC, BNT>(Bs[cur ^ 1], rb);
       }
       __syncthreads();
     }
   }
 
+  if (ks > 1) {   // split-K: raw partial tile, reduced (with the epilogue) by splitk_reduce_kernel
+    float* pt = g.part + (long long)slice * g.part_sz + (long long)z * g.M * g.N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (m >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int n = n0 + col_of(j);
+        if (n < g.N) pt[(long long)m * g.N + n] = acc[i][j];
+      }
+    }
+    return;
+  }
   // ---- fused epilogue ----
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (m >= g.M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+    for (int j = 0; j < NJ; ++j) {
+      const int n = n0 + col_of(j);
       if (n >= g.N) continue;
       float v = g.scale * acc[i][j];
       if (g.bias) v += __ldg(g.bias + (long long)z * g.bias_sz + n);
@@ -159,7 +194,9 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
   __shared__ float As[SB_K][SB_M + 1];
   __shared__ __align__(16) float Bs[SB_K][SB_N];
   const int z = blockIdx.z;
-  const int m0 = blockIdx.y * SB_M;
+  const int ks = g.ksplit > 1 ? g.ksplit : 1;
+  const int slice = blockIdx.y % ks;
+  const int m0 = (blockIdx.y / ks) * SB_M;
   const int tid = threadIdx.x;
   const int r = tid >> 2, cg = tid & 3;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -170,7 +207,11 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
     const int K = pair ? g.K2 : g.K1;
     const float* Ap = A.ptr + (long long)z * A.sz;
     const float* Bp = B.ptr + (long long)z * B.sz;
-    for (int k0 = 0; k0 < K; k0 += SB_K) {
+    const int nk_all = (K + SB_K - 1) / SB_K;
+    const int k_begin = (int)((long long)nk_all * slice / ks) * SB_K;
+    const int k_end_t = (int)((long long)nk_all * (slice + 1) / ks) * SB_K;
+    const int k_end = k_end_t < K ? k_end_t : K;
+    for (int k0 = k_begin; k0 < k_end; k0 += SB_K) {
 #pragma unroll
       for (int i = 0; i < (SB_M * SB_K) / NT; ++i) {
         const int idx = tid + NT * i;
@@ -199,6 +240,12 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
   }
   const int m = m0 + r;
   if (m >= g.M) return;
+  if (ks > 1) {
+    float* pt = g.part + (long long)slice * g.part_sz + (long long)z * g.M * g.N + (long long)m * g.N;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (cg * 4 + j < g.N) pt[cg * 4 + j] = acc[j];
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int n = cg * 4 + j;
@@ -213,6 +260,35 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
     }
     if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
     if (g.add) v += g.add_scale * __ldg(g.add + (long long)z * g.add_sz + (long long)m * g.c_sm + n);
+    if (g.C_lo) {
+      const float h = tf32_round(v);
+      g.C[co] = h;
+      g.C_lo[co] = tf32_round(v - h);
+    } else {
+      g.C[co] = v;
+    }
+  }
+}
+
+// C = epilogue( sum_slices part[slice][z][m][n] ), slices summed in a fixed order
+__global__ void splitk_reduce_kernel(DevGemm g, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % g.N);
+    const long long t = idx / g.N;
+    const int m = (int)(t % g.M);
+    const long long z = t / g.M;
+    float acc = 0.f;
+    for (int s = 0; s < g.ksplit; ++s) acc += g.part[(long long)s * g.part_sz + idx];
+    float v = g.scale * acc;
+    if (g.bias) v += __ldg(g.bias + z * g.bias_sz + n);
+    const long long co = z * g.c_sz + (long long)m * g.c_sm + n;
+    if (g.act >= 0) {
+      float d;
+      v = act_apply(g.act, v, &d);
+      if (g.dphi_out) g.dphi_out[co] = d;
+    }
+    if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
+    if (g.add) v += g.add_scale * __ldg(g.add + z * g.add_sz + (long long)m * g.c_sm + n);
     if (g.C_lo) {
       const float h = tf32_round(v);
       g.C[co] = h;
@@ -247,8 +323,25 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
   g.mask = p.epi.mask; g.mask_sm = p.epi.mask_sm;
   g.add = p.epi.add; g.add_sz = p.epi.add_sz; g.add_scale = p.epi.add_scale;
   g.act = p.epi.act; g.dphi_out = p.epi.dphi_out; g.C_lo = p.epi.C_lo;
+  g.ksplit = 1; g.part = nullptr; g.part_sz = 0;
 
-  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM), 1);
+  // split-K decision: few tiles, long K, scratch available, single operand pair, batch in one launch
+  const bool skinny = p.N <= SB_N;
+  const int bnt = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : BN);       // narrow tiles for 32- / 64-wide outputs
+  const int64_t tiles = skinny ? ceil_div(p.M, SB_M) : ceil_div(p.N, bnt) * ceil_div(p.M, BM);
+  const int64_t kstep = skinny ? SB_K : BK;
+  if (p.splitk_ws && !p.A2.ptr && p.batch <= 65535 && tiles * p.batch < 2 * 148 && p.K >= 64 * kstep) {
+    int64_t S = ceil_div(4 * 148, tiles * p.batch);
+    const int64_t smax_k = p.K / (8 * kstep);                       // at least 8 k-tiles per slice
+    const int64_t smax_ws = p.splitk_ws_elems / (p.batch * p.M * p.N);
+    if (S > smax_k) S = smax_k;
+    if (S > smax_ws) S = smax_ws;
+    if (S > 1 && tiles * S <= 65535) {
+      g.ksplit = (int)S; g.part = p.splitk_ws; g.part_sz = p.batch * p.M * p.N;
+    }
+  }
+
+  dim3 grid((unsigned)ceil_div(p.N, bnt), (unsigned)(ceil_div(p.M, BM) * g.ksplit), 1);
   // gridDim.z is limited to 65535: chunk the batch.
   const int64_t zmax = 65535;
   for (int64_t z0 = 0; z0 < p.batch; z0 += zmax) {
@@ -263,17 +356,38 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     if (gz.C_lo) gz.C_lo += z0 * g.c_sz;
     grid.z = (unsigned)zc;
     if (p.N <= SB_N) {
-      dim3 sg(1, (unsigned)ceil_div(p.M, SB_M), (unsigned)zc);
+      dim3 sg(1, (unsigned)(ceil_div(p.M, SB_M) * g.ksplit), (unsigned)zc);
       if (a_kc) gemm_skinny_kernel<true><<<sg, NT, 0, stream>>>(gz);
       else gemm_skinny_kernel<false><<<sg, NT, 0, stream>>>(gz);
       LIP_LAUNCH_CHECK();
+      if (g.ksplit > 1) {
+        const long long total = (long long)p.batch * p.M * p.N;
+        long long rb = (total + 255) / 256;
+        if (rb > 148 * 16) rb = 148 * 16;
+        splitk_reduce_kernel<<<(unsigned)rb, 256, 0, stream>>>(gz, total);
+        LIP_LAUNCH_CHECK();
+      }
       continue;
     }
-    if (a_kc && !b_kc) gemm_simt_kernel<true, false><<<grid, NT, 0, stream>>>(gz);
-    else if (!a_kc && !b_kc) gemm_simt_kernel<false, false><<<grid, NT, 0, stream>>>(gz);
-    else if (a_kc && b_kc) gemm_simt_kernel<true, true><<<grid, NT, 0, stream>>>(gz);
-    else gemm_simt_kernel<false, true><<<grid, NT, 0, stream>>>(gz);
+#define LIP_SIMT_LAUNCH(AK, BK_)                                                                 \
+    do {                                                                                          \
+      if (bnt == 32) gemm_simt_kernel<AK, BK_, 32><<<grid, NT, 0, stream>>>(gz);                   \
+      else if (bnt == 64) gemm_simt_kernel<AK, BK_, 64><<<grid, NT, 0, stream>>>(gz);              \
+      else gemm_simt_kernel<AK, BK_, 128><<<grid, NT, 0, stream>>>(gz);                            \
+    } while (0)
+    if (a_kc && !b_kc) LIP_SIMT_LAUNCH(true, false);
+    else if (!a_kc && !b_kc) LIP_SIMT_LAUNCH(false, false);
+    else if (a_kc && b_kc) LIP_SIMT_LAUNCH(true, true);
+    else LIP_SIMT_LAUNCH(false, true);
+#undef LIP_SIMT_LAUNCH
     LIP_LAUNCH_CHECK();
+    if (g.ksplit > 1) {
+      const long long total = (long long)p.batch * p.M * p.N;
+      long long rb = (total + 255) / 256;
+      if (rb > 148 * 16) rb = 148 * 16;
+      splitk_reduce_kernel<<<(unsigned)rb, 256, 0, stream>>>(gz, total);
+      LIP_LAUNCH_CHECK();
+    }
   }
   return LIP_OK;
 }

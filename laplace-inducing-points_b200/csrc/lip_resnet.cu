@@ -229,6 +229,7 @@ int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* 
 int rn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const RnWs& w, float* out, float scale, const float* add,
                  float add_scale, cudaStream_t st) {
   const int HW = m->rn_H * m->rn_W, C = m->rn_C;
+  const size_t col_elems = rn_sizes(m, B).col;
   {  // head
     GemmProblem p;
     p.M = C; p.N = m->K; p.K = m->M; p.batch = B;
@@ -277,6 +278,7 @@ int rn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const RnWs& w, float*
       p.C = out + u.woff; p.c_sz = m->D; p.c_sm = u.cout;
       p.epi.scale = scale;
       if (add) { p.epi.add = add + u.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+      p.splitk_ws = w.col; p.splitk_ws_elems = (int64_t)col_elems;    // col is free until the G GEMM below
       int rc = gemm_simt(p, st);
       if (rc) return rc;
     }
