@@ -87,3 +87,25 @@ def slq_sharded(integrand: Callable, matvec, probes: torch.Tensor, *parameters) 
             return integrand(matvec, E, *parameters).reshape(-1)
         return torch.stack([integrand(matvec, e, *parameters) for e in E]).reshape(-1)
     return sharded_mean(quad, probes)
+
+
+# ---------------------------------------------------------------------------------------------- point (M) sharding
+def point_slice(num_points: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> slice:
+    """Contiguous, balanced slice of the inducing points owned by `rank` (sharding over M for large
+    point sets).  Same partition rule as probe_slice."""
+    return probe_slice(num_points, rank, world_size)
+
+
+def point_sharded(local_fn: Callable[[torch.Tensor], torch.Tensor]) -> Callable[[torch.Tensor], torch.Tensor]:
+    """GGN(Z) v = sum_g GGN(Z_g) v: wraps a rank-local operator (bound to this rank's points, already scaled with the
+    GLOBAL recalibration N / M) into the global one with ONE all-reduce of the [B, D] result per application.
+    Every rank must call the wrapper with the same `v`."""
+
+    def global_fn(v):
+        out = local_fn(v)
+        return allreduce_sum_(out.contiguous())
+
+    for attr in ("_lip_batched", "_lip_model", "_lip_kind"):
+        if hasattr(local_fn, attr):
+            setattr(global_fn, attr, getattr(local_fn, attr))
+    return global_fn

@@ -294,9 +294,15 @@ class BoundModel:
         cabi.check(cabi.lib().lip_model_outputs(self._h, ptr(out), stream()))
         return out
 
+    @staticmethod
+    def _check_last(t: torch.Tensor, n: int, what: str) -> None:
+        if t.dim() == 0 or t.shape[-1] != n:
+            raise ValueError(f"{what}: last dimension must be {n}, got shape {tuple(t.shape)}")
+
     # ---- operators (all probe-batched: leading dim B) ----
     def ggn_vp(self, V: torch.Tensor, recal: float, alpha: float = 0.0) -> torch.Tensor:
         V = dev_f32(V, self.device)
+        self._check_last(V, self.D, "parameter-space vector")
         single = V.dim() == 1
         Vb = V.reshape(-1, self.D)
         B = Vb.shape[0]
@@ -307,6 +313,7 @@ class BoundModel:
 
     def wt(self, V: torch.Tensor, scale: float = 1.0, factor: int = cabi.FACTOR_SQRT) -> torch.Tensor:
         V = dev_f32(V, self.device)
+        self._check_last(V, self.D, "parameter-space vector")
         single = V.dim() == 1
         Vb = V.reshape(-1, self.D)
         B = Vb.shape[0]
@@ -319,6 +326,8 @@ class BoundModel:
           add_scale: float = 0.0, batched: Optional[bool] = None) -> torch.Tensor:
         U = dev_f32(U, self.device)
         d = self.M * self.K
+        if U.numel() == 0 or U.numel() % d != 0:
+            raise ValueError(f"output-space block: {tuple(U.shape)} is not a multiple of (M, K) = ({self.M}, {self.K})")
         if batched is None:
             batched = U.numel() != d
         Ub = U.reshape(-1, d)

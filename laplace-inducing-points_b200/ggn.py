@@ -185,19 +185,32 @@ def compute_W_vps(state, Z, model_type, full_set_size=None, blockwise=False, *, 
     return Wfun, WTfun
 
 
-def compute_ggn_vp(state, Z, model_type, full_set_size=None, *, tensor_path=None):
-    """ggn.py:97-146.  Returns ggn_vp: v -> (N/M) sum_i J_i^T H_i J_i v  (x exp(-logvar) for regressors)."""
+def compute_ggn_vp(state, Z, model_type, full_set_size=None, *, tensor_path=None, shard_points=False):
+    """ggn.py:97-146.  Returns ggn_vp: v -> (N/M) sum_i J_i^T H_i J_i v  (x exp(-logvar) for regressors).
+
+    shard_points=True (multi-GPU): this rank binds only its slice of the M points; the returned
+    closure sums the partial products with one all-reduce of the [B, D] result (torch.distributed must be initialised,
+    every rank passes the same Z and v)."""
+    M = int(Z.shape[0])
+    if shard_points:
+        from . import _dist
+        Z = dev_f32(Z)[_dist.point_slice(M)].contiguous()
+        if Z.shape[0] == 0:
+            raise ValueError(f"shard_points: fewer points ({M}) than ranks")
     bm = _bind(state, Z, model_type, tensor_path)
-    M = bm.M
     N = full_set_size or M
-    recal = N / M
+    recal = N / M                               # the GLOBAL M: partial sums add up to the reference's product
     if model_type == "regressor":
         recal *= math.exp(-bm.logvar)  # ggn.py:112-113
 
     def ggn_vp(v):
         return bm.ggn_vp(v, recal, 0.0)
 
-    return _batched(ggn_vp, bm, _lip_kind="GGN", _lip_recal=recal, _lip_alpha=0.0, _lip_transpose=ggn_vp)
+    fn = _batched(ggn_vp, bm, _lip_kind="GGN", _lip_recal=recal, _lip_alpha=0.0, _lip_transpose=ggn_vp)
+    if shard_points:
+        fn = _dist.point_sharded(fn)
+        fn._lip_recal, fn._lip_alpha, fn._lip_transpose = recal, 0.0, fn
+    return fn
 
 
 def compute_ggn_dense(state, Z, model_type, full_set_size=None):

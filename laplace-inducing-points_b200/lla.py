@@ -10,11 +10,21 @@ from .sample import sample
 from .utils import flatten_nn_params
 
 
-def compute_curvature_approx(map_state, Z, model_type, alpha, full_set_size=None, *, tensor_path=None):
-    """lla.py:11-23: curvature_vp(v) = ggn_vp(v) + alpha v — one fused call (the +alpha v is the GEMM epilogue)."""
-    ggn_vp = compute_ggn_vp(map_state, Z, model_type=model_type, full_set_size=full_set_size, tensor_path=tensor_path)
+def compute_curvature_approx(map_state, Z, model_type, alpha, full_set_size=None, *, tensor_path=None,
+                             shard_points=False):
+    """lla.py:11-23: curvature_vp(v) = ggn_vp(v) + alpha v — one fused call (the +alpha v is the GEMM epilogue).
+    shard_points=True: points sharded over ranks (see ggn.compute_ggn_vp); each rank adds alpha / world_size of v so
+    the all-reduced sum carries alpha v once."""
+    ggn_vp = compute_ggn_vp(map_state, Z, model_type=model_type, full_set_size=full_set_size, tensor_path=tensor_path,
+                            shard_points=shard_points)
     bm, recal = ggn_vp._lip_model, ggn_vp._lip_recal
     alpha = float(alpha)
+    if shard_points:
+        from . import _dist
+        local_alpha = alpha / _dist.world()[1]
+        fn = _dist.point_sharded(_batched(lambda v: bm.ggn_vp(v, recal, local_alpha), bm, _lip_kind="GGN"))
+        fn._lip_recal, fn._lip_alpha, fn._lip_transpose = recal, alpha, fn
+        return fn
 
     def curvature_vp(v):
         return bm.ggn_vp(v, recal, alpha)

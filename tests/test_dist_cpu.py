@@ -93,3 +93,37 @@ def test_world_size_2_gloo_matches_single_process(B):
     # each estimator call pushes a rank's own rows once: 2 calls x rows owned
     owned = [(_dist.probe_slice(B, r, ws).stop - _dist.probe_slice(B, r, ws).start) for r in range(ws)]
     assert [res[r][2] for r in range(ws)] == [2 * o for o in owned]
+
+
+def _worker_points(rank, ws, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws),
+                      LOCAL_RANK=str(rank))
+    _dist.init_from_env(backend="gloo")
+    g = torch.Generator().manual_seed(3)
+    J = torch.randn(9, 4, 30, generator=g)                 # per-point Jacobians [M, K, D] (identical on every rank)
+    V = torch.randn(5, 30, generator=g)
+    sl = _dist.point_slice(J.shape[0])
+    Jl = J[sl]
+
+    def local(v):                                          # this rank's partial GGN-vector product: sum_i J_i^T J_i v
+        return torch.einsum("mkd,mke,be->bd", Jl, Jl, v)
+    local._lip_batched = True
+    res = _dist.point_sharded(local)(V)
+    out[rank] = res.numpy().copy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_point_sharded_operator_sums_partial_products():
+    """GGN(Z) v = sum over ranks of GGN(Z_rank) v, one all-reduce of the [B, D] block."""
+    ws, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_points, args=(ws, port, out), nprocs=ws, join=True)
+        res = dict(out)
+    g = torch.Generator().manual_seed(3)
+    J = torch.randn(9, 4, 30, generator=g)
+    V = torch.randn(5, 30, generator=g)
+    ref = torch.einsum("mkd,mke,be->bd", J, J, V).numpy()
+    for r in range(ws):
+        np.testing.assert_allclose(res[r], ref, rtol=1e-5, atol=1e-5)

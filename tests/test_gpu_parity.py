@@ -481,3 +481,51 @@ def test_resnet1m_grayscale_inputs_are_tiled():
     Z = rng.random((2, 28, 28, 1)).astype(np.float32)
     bm = ggn._bind(lst, cu(Z), "classifier")
     assert rel_err(bm.outputs().cpu().numpy(), O.model_outputs(ost, Z)) < 5e-6
+
+
+# --------------------------------------------------------------------------------- full-size properties (C3b)
+def test_headline_size_properties():
+    """BASELINE's headline shape (784-1024-512-256-128-10, D = 1,494,154, M = 512) through size-independent properties
+    of the operators (the float64 oracle is only run on 2 probes at this size, in test_headline_config_matches_oracle):
+    symmetry u.(G v) == v.(G u), linearity, W W^T == GGN, positive semi-definiteness, and SIMT == tcgen05."""
+    from lip_b200 import ggn, lla
+    ost, lst = make_pair("large", hidden=[1024, 512, 256, 128], n_out=10, in_dim=784, seed=1003, in_shape=(28, 28, 1))
+    rng = np.random.default_rng(77)
+    Z = cu(rng.random((512, 784)).astype(np.float32))
+    D = ost.flat()[0].size
+    assert D == 1494154
+    N = 60000
+    G = ggn.compute_ggn_vp(lst, Z, "classifier", full_set_size=N)
+    U = cu(rng.standard_normal((3, D)).astype(np.float32))
+    V = cu(rng.choice([-1.0, 1.0], size=(3, D)).astype(np.float32))
+    GU, GV = G(U), G(V)
+    uGv = (U.double() * GV.double()).sum(1)
+    vGu = (V.double() * GU.double()).sum(1)
+    assert torch.all((uGv - vGu).abs() <= 2e-5 * (U.double().norm(dim=1) * GV.double().norm(dim=1)))   # symmetry
+    assert torch.all((V.double() * GV.double()).sum(1) >= 0) and torch.all((U.double() * GU.double()).sum(1) >= 0)   # PSD
+    lin = G(2.0 * U - 0.5 * V)
+    assert rel_err(lin.cpu().numpy(), (2.0 * GU - 0.5 * GV).cpu().numpy()) < 1e-5                      # linearity
+    Wf, WTf = ggn.compute_W_vps(lst, Z, "classifier", full_set_size=N)
+    assert rel_err(Wf(WTf(V)).cpu().numpy(), GV.cpu().numpy()) < 2e-5                                  # W W^T == GGN
+    alpha = 1e-3
+    S = lla.compute_curvature_approx(lst, Z, "classifier", alpha, full_set_size=N)
+    assert rel_err(S(V).cpu().numpy(), (GV + alpha * V).cpu().numpy()) < 1e-5                          # curvature = GGN + alpha I
+    G_simt = ggn.compute_ggn_vp(lst, Z, "classifier", full_set_size=N, tensor_path=False)
+    assert rel_err(GV.cpu().numpy(), G_simt(V).cpu().numpy()) < 1e-5                                   # both arithmetic paths
+    assert rel_err(G(V[0]).cpu().numpy(), GV[0].cpu().numpy()) < 1e-6                                  # un-batched == batched
+
+
+def test_edge_shapes():
+    """One point, one probe, one hidden unit; K = 1 classifier head is rejected for regressors only when K != 1."""
+    from lip_b200 import ggn
+    ost, lst = make_pair("classifier", hidden=[1], n_out=3, in_dim=1, seed=9)
+    Z = np.array([[0.3]], dtype=np.float32)
+    D = ost.flat()[0].size
+    v = np.arange(1, D + 1, dtype=np.float32) / D
+    ref = O.compute_ggn_vp(ost, Z, "classifier", full_set_size=7)(v.astype(np.float64))
+    got = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=7)(cu(v)).cpu().numpy()
+    assert got.shape == (D,) and rel_err(got, ref) < TOL_GGN
+    with pytest.raises(ValueError):
+        ggn.compute_ggn_vp(lst, cu(np.zeros((2, 5), np.float32)), "classifier")          # wrong feature count
+    with pytest.raises(ValueError):
+        ggn.compute_ggn_vp(lst, cu(Z), "classifier")(cu(np.zeros(D + 1, np.float32)))    # wrong vector length
