@@ -399,9 +399,18 @@ def run_b200(args):
     except Exception:
         pass
     achieved = FLOP_PER_PRODUCT * B / (ms_ggn * 1e-3) / 1e12
+    # DRAM bytes of one lip_ggn_vp call from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum summed
+    # over the call's launches); only valid for the configuration it was captured on
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_ggn_vp.json")))
+        if args.workload == "mlp" and B == 256:
+            traffic = tj["traffic_bytes"]
+    except Exception:
+        pass
     peak = tf32_peak / 3.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                "traffic": traffic,
                 "kernel": "one lip_ggn_vp call = the JVP + VJP GEMM sweeps over all probes (tcgen05 gemm_tc*_kernel launches "
                           "+ split / head / bias kernels), timed alone with CUDA events",
                 "ms_per_call": ms_ggn,

@@ -1130,8 +1130,15 @@ extern "C" int lip_bench_tc_gemm(int32_t variant, int64_t M, int64_t N, int64_t 
   float *Ah, *Al, *Bh, *Bl, *C;
   LIP_CHECK_CUDA(cudaMalloc(&Ah, 4 * na)); LIP_CHECK_CUDA(cudaMalloc(&Al, 4 * na));
   LIP_CHECK_CUDA(cudaMalloc(&Bh, 4 * nb)); LIP_CHECK_CUDA(cudaMalloc(&Bl, 4 * nb)); LIP_CHECK_CUDA(cudaMalloc(&C, 4 * nc));
-  cudaMemsetAsync(Ah, 0, 4 * na, st); cudaMemsetAsync(Al, 0, 4 * na, st);
-  cudaMemsetAsync(Bh, 0, 4 * nb, st); cudaMemsetAsync(Bl, 0, 4 * nb, st);
+  if (getenv("LIP_BENCH_RANDOM")) {   // realistic switching activity (power / clocks) instead of all-zero operands
+    fill_random_kernel<<<(unsigned)ceil_div(na, 256), 256, 0, st>>>(Ah, na, 11u, 1.f);
+    fill_random_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, st>>>(Bh, nb, 23u, 1.f);
+    tf32_split(Ah, lda, Ah, Al, lda, (a_batched ? batch : 1) * a_rows, lda, st);
+    tf32_split(Bh, ldb, Bh, Bl, ldb, (b_batched ? batch : 1) * b_rows, ldb, st);
+  } else {
+    cudaMemsetAsync(Ah, 0, 4 * na, st); cudaMemsetAsync(Al, 0, 4 * na, st);
+    cudaMemsetAsync(Bh, 0, 4 * nb, st); cudaMemsetAsync(Bl, 0, 4 * nb, st);
+  }
   TcGemmProblem tp;
   tp.M = M; tp.N = N; tp.K = K; tp.batch = batch;
   tp.A1.hi = Ah; tp.A1.lo = Al; tp.A1.sz = a_sz; tp.A1.ld = lda; tp.A1.major_k = a_k;
