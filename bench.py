@@ -296,16 +296,25 @@ def run_b200(args):
     value = B * world * args.steps / (ms_total * 1e-3)
     trace_est = float(acc.item()) / (B * world * (args.steps + args.warmup))
 
-    # ---- end to end through the public API with HOST probes (pinned int8 +-1), copies inside the timed region ----
+    # ---- end to end through the public API with HOST probes, copies inside the timed region ----
+    # Rademacher probes live in pinned host memory in their packed wire format (1 bit / element, numpy.packbits); every step
+    # copies its probes H2D, unpacks them on the device (lip_unpack_rademacher), runs the public
+    # lla.compute_curvature_approx(...)(V) + quadratic forms, and copies the step's B results back to pinned host memory.
     e2e = None
     if not args.no_e2e:
+        from lip_b200 import stochtrace as st_mod
+        host_bits = torch.from_numpy(st_mod.pack_rademacher(host_i8.numpy())).pin_memory()
+        nbytes_row = host_bits.shape[1]
         copy_stream = torch.cuda.Stream()
-        bufs = [torch.empty(B, D, dtype=torch.int8, device=dev) for _ in range(2)]
+        bufs = [torch.empty(B, nbytes_row, dtype=torch.uint8, device=dev) for _ in range(2)]
+        vbuf = torch.empty(B, D, device=dev)
         evs = [torch.cuda.Event() for _ in range(2)]
+        host_q = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
+        qev = [torch.cuda.Event() for _ in range(2)]
 
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
-                bufs[i % 2].copy_(host_i8, non_blocking=True)
+                bufs[i % 2].copy_(host_bits, non_blocking=True)
                 evs[i % 2].record(copy_stream)
 
         def e2e_run(nsteps):
@@ -316,8 +325,14 @@ def run_b200(args):
                     copy_stream.wait_stream(torch.cuda.current_stream())   # buffer (i+1)%2 is free once step i-1 is done
                     prefetch(i + 1)
                 torch.cuda.current_stream().wait_event(evs[i % 2])
-                step(bufs[i % 2].float())
-                res.append(q.cpu())                                        # D2H of the step's result (B floats)
+                st_mod.unpack_rademacher(bufs[i % 2], D, out=vbuf)
+                step(vbuf)
+                if i >= 2:
+                    qev[i % 2].synchronize()                               # result of step i-2 has landed: consume it
+                    res.append(float(host_q[i % 2].sum()))
+                host_q[i % 2].copy_(q, non_blocking=True)                  # D2H of the step's result (B floats)
+                qev[i % 2].record()
+            torch.cuda.synchronize()
             return res
 
         e2e_run(2)
@@ -331,8 +346,9 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": B * world * args.steps / float(dt.item()), "unit": "products/s",
-               "h2d_bytes_per_step": B * D, "d2h_bytes_per_step": B * 4,
-               "note": "pinned int8 +-1 probes -> lla.compute_curvature_approx(...)(V) -> v.(Gv) read back; H2D double-buffered"}
+               "h2d_bytes_per_step": B * nbytes_row, "d2h_bytes_per_step": B * 4,
+               "note": "pinned bit-packed +-1 probes -> H2D -> lip_unpack_rademacher -> lla.compute_curvature_approx(...)(V) -> "
+                       "v.(Gv) -> pinned host; H2D double-buffered, D2H pipelined two steps deep"}
 
     # ---- SLQ logdet (GKL form, src/train_inducing.py:148-171), probes sharded over ranks ----
     slq = None

@@ -155,6 +155,11 @@ int lip_axpby(const float* a, const float* x, const float* c, float* y, int64_t 
 int lip_scale(const float* s, int32_t invert, const float* x, float* y, int64_t n, int64_t B,
               int64_t ldx, int64_t ldy, lip_stream_t stream);
 
+/* Rademacher probes in their compact wire format: row b of `bits` (ldbits bytes per row, numpy.packbits order: bit
+ * 7 of byte 0 is element 0) -> out[b, j] = bit ? +1 : -1, j < n.  Host probes for Hutchinson / SLQ
+ * (src/stochtrace.py:28, src/train_inducing.py:139) then cross PCIe at 1 bit per element instead of 32. */
+int lip_unpack_rademacher(const uint8_t* bits, int64_t ldbits, float* out, int64_t n, int64_t B, lip_stream_t stream);
+
 /* One CG iteration's vector work for jax.scipy.sparse.linalg.cg semantics (call sites
  * src/stochtrace.py:146,192; src/sample.py:71): given Ap = A p,
  *   a = gamma/(p.Ap); x += a p; r -= a Ap; gamma' = r.r; p = r + (gamma'/gamma) p; gamma = gamma'

@@ -52,6 +52,7 @@ SIGNATURES = {
     "lip_dot": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
     "lip_axpby": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "lip_scale": (C.c_int, [_P, _I32, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "lip_unpack_rademacher": (C.c_int, [_P, _I64, _P, _I64, _I64, _P]),
     "lip_cg_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P]),
     "lip_cg_init": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I64, _I64, _P, _P]),
     "lip_reorth_scratch_bytes": (_SZ, [_I64, _I64, _I64]),

@@ -29,6 +29,28 @@ def vmap(fn, in_axes=0, out_axes=0):
     return mapped
 
 
+def pack_rademacher(eps) -> "np.ndarray":
+    """+-1 probe matrix [B, n] (host) -> packed bits [B, ceil(n/8)] uint8 (numpy.packbits order): the wire format for
+    host-resident Rademacher probes (1 bit per element over PCIe)."""
+    import numpy as np
+    e = np.asarray(eps.cpu() if isinstance(eps, torch.Tensor) else eps)
+    return np.packbits(e > 0, axis=1)
+
+
+def unpack_rademacher(bits, n: int, out=None):
+    """Packed bits [B, ceil(n/8)] (a uint8 CUDA tensor) -> float32 +-1 probes [B, n] on the device (lip_unpack_rademacher)."""
+    from . import _cabi as cabi
+    from ._runtime import ptr, stream
+    if not (isinstance(bits, torch.Tensor) and bits.is_cuda and bits.dtype == torch.uint8 and bits.dim() == 2):
+        raise ValueError("unpack_rademacher: bits must be a 2-D uint8 CUDA tensor")
+    bits = bits.contiguous()
+    B = bits.shape[0]
+    if out is None:
+        out = torch.empty(B, n, device=bits.device, dtype=torch.float32)
+    cabi.check(cabi.lib().lip_unpack_rademacher(ptr(bits), bits.shape[1], ptr(out), n, B, stream()), "lip_unpack_rademacher")
+    return out
+
+
 def _rademacher(seed, shape):
     g = _generator(seed)
     return torch.randint(0, 2, shape, generator=g, device=g.device, dtype=torch.int8).float() * 2 - 1

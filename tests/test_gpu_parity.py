@@ -529,3 +529,17 @@ def test_edge_shapes():
         ggn.compute_ggn_vp(lst, cu(np.zeros((2, 5), np.float32)), "classifier")          # wrong feature count
     with pytest.raises(ValueError):
         ggn.compute_ggn_vp(lst, cu(Z), "classifier")(cu(np.zeros(D + 1, np.float32)))    # wrong vector length
+
+
+def test_packed_rademacher_probes_round_trip():
+    """Bit-exact: pack (host, numpy.packbits) -> unpack (device) reproduces the +-1 probe matrix, ragged n included."""
+    from lip_b200 import stochtrace
+    rng = np.random.default_rng(8)
+    for B, n in ((1, 1), (3, 8), (5, 1003), (2, 61706)):
+        eps = rng.choice([-1.0, 1.0], size=(B, n)).astype(np.float32)
+        bits = stochtrace.pack_rademacher(eps)
+        assert bits.shape == (B, (n + 7) // 8) and bits.dtype == np.uint8
+        got = stochtrace.unpack_rademacher(torch.as_tensor(bits, device="cuda"), n).cpu().numpy()
+        np.testing.assert_array_equal(got, eps)
+    with pytest.raises(ValueError):
+        stochtrace.unpack_rademacher(torch.zeros(2, 3), 24)
