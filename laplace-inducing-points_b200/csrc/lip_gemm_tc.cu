@@ -240,32 +240,31 @@ struct TcParams {
 // coalesced rows), then  x = (scale * acc + bias[n]) * mask[m][n] + add_scale * add[m][n]  is stored as fp32 or as a
 // TF32 (hi, lo) pair.  The row loops use hoisted base pointers and 8-row batches (loads first): the per-element
 // instruction count, not memory bandwidth, was the cost of the first version of this epilogue (ncu: `no_inst`).
-template <bool HAS_LO>
+template <bool HAS_LO, int RB>   // RB: rows per load batch (all mask / add loads of a batch are in flight together)
 __device__ __forceinline__ float store_block_rows(const TcParams& p, const float* __restrict__ sp, float* __restrict__ cp,
-                                                 float* __restrict__ lp, const float* __restrict__ mp,
-                                                 const float* __restrict__ ap, float bv, int nrows) {
+                                                  float* __restrict__ lp, const float* __restrict__ mp,
+                                                  const float* __restrict__ ap, float bv, int nrows) {
   const float sc = p.scale, asc = p.add_scale;
   const long long cs = p.c_sm, ms = p.mask_sm;
   float colsum = 0.f;
   int r0 = 0;
-  for (; r0 + 8 <= nrows; r0 += 8) {
-    float mv[8], av[8], xv[8];
+  for (; r0 + RB <= nrows; r0 += RB) {
+    float mv[RB], av[RB];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < RB; ++r) {
       mv[r] = mp ? __ldg(mp + (r0 + r) * ms) : 1.f;
       av[r] = ap ? __ldg(ap + (r0 + r) * cs) : 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) xv[r] = fmaf(asc, av[r], fmaf(sc, sp[(r0 + r) * STG_LD], bv) * mv[r]);
-    colsum += ((xv[0] + xv[1]) + (xv[2] + xv[3])) + ((xv[4] + xv[5]) + (xv[6] + xv[7]));
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < RB; ++r) {
+      const float x = fmaf(asc, av[r], fmaf(sc, sp[(r0 + r) * STG_LD], bv) * mv[r]);
+      colsum += x;
       if (HAS_LO) {
-        const float hh = tf32_rna(xv[r]);
+        const float hh = tf32_rna(x);
         cp[(r0 + r) * cs] = hh;
-        lp[(r0 + r) * cs] = tf32_rna(xv[r] - hh);
+        lp[(r0 + r) * cs] = tf32_rna(x - hh);
       } else {
-        cp[(r0 + r) * cs] = xv[r];
+        cp[(r0 + r) * cs] = x;
       }
     }
   }
@@ -285,16 +284,17 @@ __device__ __forceinline__ float store_block_rows(const TcParams& p, const float
   return colsum;
 }
 
-// acc: the warp's 32 x 64 block (row = lane), m0/n0: tile origin, q: lane quarter, h: column half
-__device__ __forceinline__ void tile_epilogue(const TcParams& p, float (&acc)[64], float* stg, int m0, int n0, int z, int q,
-                                              int h, int lane) {
+// acc: the warp's 32 x (32 * NBLK) block (row = lane), m0/n0: tile origin, q: lane quarter, h: which column group
+template <int NBLK, int RB>
+__device__ __forceinline__ void tile_epilogue(const TcParams& p, float (&acc)[32 * NBLK], float* stg, int m0, int n0, int z,
+                                              int q, int h, int lane) {
   const int mrow0 = m0 + q * 32;
   int nrows = p.M - mrow0;
   nrows = nrows > 32 ? 32 : nrows;
   const long long zc = (long long)z * p.c_sz + (long long)mrow0 * p.c_sm;
 #pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int n = n0 + h * 64 + cc * 32 + lane;
+  for (int cc = 0; cc < NBLK; ++cc) {
+    const int n = n0 + h * (32 * NBLK) + cc * 32 + lane;
 #pragma unroll
     for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
     __syncwarp();
@@ -305,8 +305,8 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& p, float (&acc)[64
         float* cp = p.C + zc + n;
         const float* mp = p.mask ? p.mask + (long long)mrow0 * p.mask_sm + n : nullptr;
         const float* ap = p.add ? p.add + (long long)z * p.add_sz + (long long)mrow0 * p.c_sm + n : nullptr;
-        if (p.C_lo) csum = store_block_rows<true>(p, stg + lane, cp, p.C_lo + zc + n, mp, ap, bv, nrows);
-        else csum = store_block_rows<false>(p, stg + lane, cp, nullptr, mp, ap, bv, nrows);
+        if (p.C_lo) csum = store_block_rows<true, RB>(p, stg + lane, cp, p.C_lo + zc + n, mp, ap, bv, nrows);
+        else csum = store_block_rows<false, RB>(p, stg + lane, cp, nullptr, mp, ap, bv, nrows);
       }
       if (p.colsum) p.colsum[(long long)z * p.colsum_sz + (long long)(mrow0 >> 5) * p.colsum_ld + n] = csum;
     }
@@ -542,7 +542,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
         if (lane == 0) mbar_arrive(tempty_bar(buf));           // buffer may be overwritten by the next chunk
       }
       // ---- tile epilogue: registers -> smem (own 32x32 blocks) -> coalesced fused epilogue + store ----
-      tile_epilogue(p, acc, stg, m0, n0, z, q, h, lane);
+      tile_epilogue<2, 8>(p, acc, stg, m0, n0, z, q, h, lane);
     }
   }
   tc_fence_before();
@@ -762,7 +762,236 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
           if (crank == 0) mbar_arrive(tempty_bar(buf)); else mbar_arrive_remote(tempty_bar(buf), 0);
         }
       }
-      tile_epilogue(p, acc, stg, m0, n0, z, q, h, lane);
+      tile_epilogue<2, 8>(p, acc, stg, m0, n0, z, q, h, lane);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
+// ============================================================================================================
+// Wide CTA-pair variant: a pair computes a 256 x 256 tile (UMMA 256 x 256 x 8, cta_group::2).  Per CTA and MMA the
+// tensor core reads 4 KB of A and 4 KB of B from shared memory for 128 clk of work: half the operand traffic of the
+// 128-wide tiles, which are operand-fetch bound (tools/mma_probe.cu: 139 clk per MMA here = 3765 FLOP/clk/SM, the nominal
+// TF32 rate, against 3021 for 128 x 128).  The 512 TMEM columns hold ONE cross-term tile and ONE main tile (256 columns
+// each), so there is no TMEM double buffering: the cross terms accumulate over the whole K loop (their truncation error
+// is 2^-11 down), the main terms are folded into fp32 registers every KC k-blocks and the first k-block of the next chunk
+// issues its cross-term MMAs while that drain is in flight.  Drain warps hold 32 x 128 accumulators each, so the kernel
+// re-balances registers between the control warpgroup and the two drain warpgroups with setmaxnreg.
+// ============================================================================================================
+constexpr int WN = 256;                 // pair-tile columns (per CTA: 128 rows x 256 columns of output)
+constexpr int W_REG_CTRL = 40, W_REG_DRAIN = 224;
+
+struct SmemLayoutW {
+  static constexpr int A_TILE = TBM * TBK * 4;          // 16 KB
+  static constexpr int B_TILE = (WN / 2) * TBK * 4;     // half of the 256-column B tile: 16 KB
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE; // 64 KB
+  static constexpr int STAGES = 3;
+  static constexpr int STAGING = 8 * 32 * STG_LD * 4;
+  static constexpr int BYTES = STAGES * STAGE + STAGING + 1024 + 256;
+};
+
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2w_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
+                 const __grid_constant__ CUtensorMap mB1h, const __grid_constant__ CUtensorMap mB1l,
+                 const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
+                 const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, TcParams p) {
+  using SL = SmemLayoutW;
+  constexpr int TMEM_COLS = 512;          // [0, 256): cross terms (whole tile), [256, 512): main terms (one chunk)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = smem_base + SL::STAGES * SL::STAGE;
+  const uint32_t bar_base = stg_base + SL::STAGING;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SL::STAGES + s); };
+  const uint32_t mfull_bar = bar_base + 8u * (2 * SL::STAGES + 0);    // main tile of a chunk complete
+  const uint32_t mempty_bar = bar_base + 8u * (2 * SL::STAGES + 1);   // main tile drained (leader's barrier)
+  const uint32_t cfull_bar = bar_base + 8u * (2 * SL::STAGES + 2);    // cross tile of a tile complete
+  const uint32_t cempty_bar = bar_base + 8u * (2 * SL::STAGES + 3);   // cross tile drained (leader's barrier)
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SL::STAGES + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
+  const int nk = nk1 + nk2;
+  const int KCr = p.kc;
+  const int nchunks = (nk + KCr - 1) / KCr;
+  const int mpt = (p.M + 2 * TBM - 1) / (2 * TBM), nt = (p.N + WN - 1) / WN;
+  const long long ntiles = (long long)mpt * nt * p.batch;
+  const long long t_first = (long long)cluster_id_x(), t_step = (long long)num_clusters_x();
+  auto tile_coords = [&](long long t, int& m0, int& n0, int& z) {
+    z = (int)(t / ((long long)mpt * nt));
+    m0 = ((int)(t % mpt) * 2 + (int)crank) * TBM;
+    n0 = (int)((t / mpt) % nt) * WN;
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < SL::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(mfull_bar, 1); mbar_init(cfull_bar, 1);
+    mbar_init(mempty_bar, 16); mbar_init(cempty_bar, 16);       // 8 drain warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(W_REG_CTRL));
+    if (warp == 0) {
+      // ================= TMA producer (both CTAs) =================
+      uint32_t it = 0;
+      for (long long t = t_first; t < ntiles; t += t_step) {
+        int m0, n0, z;
+        tile_coords(t, m0, n0, z);
+        const int nb0 = n0 + (int)crank * (WN / 2);       // this CTA stages B rows [nb0, nb0 + 128)
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % SL::STAGES;
+          const uint32_t ph = (it / SL::STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t st = smem_base + s * SL::STAGE;
+          if (elect_one()) {
+            if (p.dbg & 4) {
+              if (crank == 0) mbar_arrive(full_bar(s));
+            } else {
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SL::STAGE);
+              const bool second = kb >= nk1;
+              const int k0 = (second ? kb - nk1 : kb) * TBK;
+              const CUtensorMap* ah = second ? &mA2h : &mA1h;
+              const CUtensorMap* al = second ? &mA2l : &mA1l;
+              const CUtensorMap* bh = second ? &mB2h : &mB1h;
+              const CUtensorMap* bl = second ? &mB2l : &mB1l;
+              const int za = (second ? p.a2_batched : p.a1_batched) ? z : 0;
+              const int zb = (second ? p.b2_batched : p.b1_batched) ? z : 0;
+              load_operand_2sm<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
+              load_operand_2sm<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
+              load_operand_2sm<B_K, WN / 2>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, nb0, zb);
+              load_operand_2sm<B_K, WN / 2>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, nb0, zb);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 1 && crank == 0) {
+      // ================= MMA issuer: leader CTA only =================
+      constexpr uint32_t idesc = make_idesc(2 * TBM, WN, !A_K, !B_K);
+      constexpr uint32_t A_LBO = A_K ? 16 : TBK * 128, B_LBO = B_K ? 16 : TBK * 128;
+      constexpr uint32_t A_SBO = A_K ? 1024 : 512, B_SBO = B_K ? 1024 : 512;
+      constexpr uint32_t A_LT = A_K ? 2 : 1, B_LT = B_K ? 2 : 1;
+      constexpr uint32_t A_KSTEP = A_K ? 32 : 1024, B_KSTEP = B_K ? 32 : 1024;
+      const uint32_t t_cross = tmem_base, t_main = tmem_base + WN;
+      uint32_t it = 0, ck = 0, tl = 0;     // k-block / chunk / tile counters
+      for (long long t = t_first; t < ntiles; t += t_step, ++tl) {
+        for (int c = 0; c < nchunks; ++c, ++ck) {
+          const int kb_end = (c + 1) * KCr < nk ? (c + 1) * KCr : nk;
+          for (int kb = c * KCr; kb < kb_end; ++kb, ++it) {
+            const int s = it % SL::STAGES;
+            const uint32_t ph = (it / SL::STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            if (kb == 0) mbar_wait(cempty_bar, (tl & 1) ^ 1);        // previous tile's cross terms have been read out
+            tc_fence_after();
+            const uint32_t st = smem_base + s * SL::STAGE;
+            const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE, b_lo = b_hi + SL::B_TILE;
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < TBK / UMMA_K; ++j) {      // cross terms first: they do not need the main tile
+                const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                if (!(p.dbg & 2)) {
+                  umma_tf32_2sm(t_cross, dal, dbh, idesc, (kb != 0 || j != 0) ? 1u : 0u);
+                  umma_tf32_2sm(t_cross, dah, dbl, idesc, 1);
+                }
+              }
+            }
+            __syncwarp();
+            if (kb == c * KCr) {                                       // the previous chunk's main tile has been folded
+              mbar_wait(mempty_bar, (ck & 1) ^ 1);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < TBK / UMMA_K; ++j) {
+                const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                umma_tf32_2sm(t_main, dah, dbh, idesc, (kb != c * KCr || j != 0) ? 1u : 0u);
+              }
+              umma_commit_2sm(empty_bar(s), 0x3);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma_commit_2sm(mfull_bar, 0x3);
+            if (c == nchunks - 1) umma_commit_2sm(cfull_bar, 0x3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(W_REG_DRAIN));
+    // ================= drain + epilogue warps (per CTA: its own 128 rows x 256 columns) =================
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;            // which 128-column half
+    constexpr int HC = WN / 2;                // 128 columns per warp
+    float* stg = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw))) + (warp - 4) * 32 * STG_LD;
+    uint32_t ck = 0, tl = 0;
+    for (long long t = t_first; t < ntiles; t += t_step, ++tl) {
+      int m0, n0, z;
+      tile_coords(t, m0, n0, z);
+      float acc[HC];
+#pragma unroll
+      for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + h * HC;
+      for (int c = 0; c < nchunks; ++c, ++ck) {
+        mbar_wait(mfull_bar, ck & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < HC / 32; ++cc) {
+          float w[32];
+          tmem_ld32(tbase + (uint32_t)(WN + cc * 32), w);         // main terms of this chunk
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (crank == 0) mbar_arrive(mempty_bar); else mbar_arrive_remote(mempty_bar, 0);
+        }
+      }
+      mbar_wait(cfull_bar, tl & 1);
+      tc_fence_after();
+      if (!(p.dbg & 2)) {
+#pragma unroll
+        for (int cc = 0; cc < HC / 32; ++cc) {
+          float w[32];
+          tmem_ld32(tbase + (uint32_t)(cc * 32), w);               // cross terms of the whole tile
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (crank == 0) mbar_arrive(cempty_bar); else mbar_arrive_remote(cempty_bar, 0);
+      }
+      tile_epilogue<HC / 32, 32>(p, acc, stg, m0, n0, z, q, h, lane);
     }
   }
   tc_fence_before();
@@ -1001,6 +1230,67 @@ int launch_tc2(const TcGemmProblem& g, cudaStream_t st) {
   return LIP_OK;
 }
 
+template <bool A_K, bool B_K>
+int launch_tc2w(const TcGemmProblem& g, cudaStream_t st) {
+  CUtensorMap maps[8];
+  const TcOperand* ops[4] = {&g.A1, &g.B1, &g.A2, &g.B2};
+  const int batched[4] = {g.a_batched, g.b_batched, g.a2_batched, g.b2_batched};
+  const bool dual = g.A2.hi != nullptr;
+  for (int i = 0; i < 4; ++i) {
+    const TcOperand& o = *ops[(i >= 2 && !dual) ? i - 2 : i];
+    const int bt = batched[(i >= 2 && !dual) ? i - 2 : i];
+    const bool is_a = (i % 2 == 0);
+    const bool km = is_a ? A_K : B_K;
+    const int64_t K = (i >= 2 && dual) ? g.K2 : g.K;
+    const int64_t rows = is_a ? g.M : g.N;
+    const int box_rows = is_a ? TBM : WN / 2;
+    int rc = make_map(&maps[2 * i], o.hi, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, box_rows);
+    if (rc) return rc;
+    rc = make_map(&maps[2 * i + 1], o.lo, km, rows, K, o.ld, o.sz, bt ? g.batch : 1, box_rows);
+    if (rc) return rc;
+  }
+  TcParams p;
+  p.M = (int)g.M; p.N = (int)g.N; p.K1 = (int)g.K; p.K2 = dual ? (int)g.K2 : 0; p.batch = (int)g.batch;
+  p.dbg = g_tc_dbg;
+  p.kc = getenv("LIP_TC_KC") ? atoi(getenv("LIP_TC_KC")) : KC;
+  p.merge = 0;
+  p.a1_batched = g.a_batched; p.b1_batched = g.b_batched; p.a2_batched = g.a2_batched; p.b2_batched = g.b2_batched;
+  p.C = g.C; p.C_lo = g.C_lo; p.c_sz = g.c_sz; p.c_sm = g.c_sm;
+  p.scale = g.epi.scale;
+  p.bias = g.epi.bias; p.bias_sz = g.epi.bias_sz;
+  p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
+  p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
+  p.colsum = g.colsum; p.colsum_sz = g.colsum_sz; p.colsum_ld = g.colsum_ld;
+  using SL = SmemLayoutW;
+  auto kern = gemm_tc2w_kernel<A_K, B_K>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LIP_CHECK_CUDA(cudaGetDevice(&dev));
+    LIP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t npairs = ceil_div(g.M, 2 * TBM) * ceil_div(g.N, WN) * g.batch;
+  const int64_t max_clusters = num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SL::BYTES;
+  cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)((npairs < max_clusters ? npairs : max_clusters) * 2));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p));
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
 }  // namespace
 
 bool tc_available() {
@@ -1032,6 +1322,21 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   static const bool verbose = getenv("LIP_TC_VERBOSE") != nullptr;
   if (verbose) fprintf(stderr, "[lip] gemm_tc M=%lld N=%lld K=%lld K2=%lld batch=%lld a_k=%d b_k=%d two_cta=%d cl4=%d\n", (long long)g.M,
                        (long long)g.N, (long long)g.K, (long long)g.K2, (long long)g.batch, (int)a_k, (int)b_k, two_cta, (int)cl4);
+  // wide CTA-pair tiles (256 x 256; measured ~22 % faster per tile than 128-wide tiles, profiles/r01_gemm_microbench_wide.txt):
+  // used when the padded tile area does not grow by more than 10 % over 128 x 128 tiles.  LIP_TC_WIDE: -1 auto (default),
+  // 0 never, 1 whenever M > 128 and N > 128.
+  static const int wide = getenv("LIP_TC_WIDE") ? atoi(getenv("LIP_TC_WIDE")) : -1;
+  {
+    const double area_w = (double)(ceil_div(g.M, 2 * TBM) * 2 * TBM) * (double)(ceil_div(g.N, WN) * WN);
+    const double area_n = (double)(ceil_div(g.M, TBM) * TBM) * (double)(ceil_div(g.N, 128) * 128);
+    const bool fits = area_w <= 1.10 * area_n;
+    const bool use_w = g_tc_force2 == 2 || (g_tc_force2 < 0 && (wide == 1 || (wide < 0 && fits)) && g.M > TBM && g.N > 128);
+    if (use_w) {
+      if (a_k && !b_k) return launch_tc2w<true, false>(g, st);
+      if (!a_k && !b_k) return launch_tc2w<false, false>(g, st);
+      if (a_k && b_k) return launch_tc2w<true, true>(g, st);
+    }
+  }
   const bool auto2 = a_k && !b_k && (g.M % (2 * TBM) == 0);
   const bool use2 = g_tc_force2 >= 0 ? (g_tc_force2 == 1) : (two_cta < 0 ? auto2 : two_cta != 0);
   if (use2 && g.M > TBM) {

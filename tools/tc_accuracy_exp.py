@@ -1,7 +1,7 @@
 """Manual GPU harness: accuracy / speed of the tcgen05 3xTF32 path vs TMEM chunk length and accumulator merging."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 from helpers import make_pair, rel_err
 from oracle import lip_oracle as O

@@ -18,7 +18,7 @@ th = threading.Thread(target=sample, daemon=True); th.start()
 shapes = {"jvp_l1": (0, 512, 512, 2048, 256), "wgrad_l1": (1, 1024, 512, 512, 256), "dgrad_l1": (2, 512, 1024, 512, 256)}
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 for name, (v, M, N, K, b) in shapes.items():
-    for two in (0, 1):
+    for two in (0, 1, 2):
         for dbg in (0, 1, 5, 7):
             ms = C.c_float(0)
             t0 = time.time()
