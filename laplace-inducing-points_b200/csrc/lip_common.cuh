@@ -78,15 +78,17 @@ struct GemmProblem {
 
 int gemm_simt(const GemmProblem& p, cudaStream_t stream);
 
-// tcgen05 3xTF32 path (lip_gemm_tc.cu).  x = hi + lo with hi, lo TF32-representable.  `hi` may also be the raw
-// fp32 array (the tensor core ignores the 13 low mantissa bits, i.e. truncates) when `lo` was computed against
-// that truncation (tf32_lo_trunc below).  lo == nullptr means "identically zero" (operand exactly TF32).
+// tcgen05 3xTF32 path (lip_gemm_tc.cu).  x = hi + lo with hi = tf32_rna(x), lo = tf32_rna(x - hi).
 struct TcOperand {
   const float* hi = nullptr;
   const float* lo = nullptr;
   int64_t sz = 0;      // batch stride (elements), multiple of 4
   int64_t ld = 0;      // leading dimension (elements), multiple of 4
   int major_k = 1;     // 1: contraction index contiguous ("K-major"), 0: M/N index contiguous
+  // optional device flag written by tf32_split*: 0 = every lo element of this operand is zero (the data is exactly
+  // TF32-representable, e.g. +-1 Rademacher probes or one-hot blocks) -> the kernels skip its lo tile loads and the
+  // hi x lo MMAs, an exact saving of one third of the tensor work of that operand pair.  Honoured for B1 only.
+  const int* lo_nz = nullptr;
 };
 struct TcGemmProblem {
   int64_t M = 0, N = 0, K = 0, K2 = 0, batch = 1;
@@ -106,10 +108,7 @@ int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t l
                int64_t cols, cudaStream_t stream);
 // batched form: element (z, r, c) at z*sz + r*ld + c
 int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, float* lo, int64_t sz_dst,
-                int64_t ld_dst, int64_t batch, int64_t rows, int64_t cols, cudaStream_t stream);
-// lo[r*ld + c] = tf32_rna(x - trunc_tf32(x)) for a [rows x cols] block with row pitch ld (same pitch in and out):
-// the low-order part that pairs with the RAW array used as the high-order operand.  float4-vectorised (ld % 4 == 0).
-int tf32_lo_trunc(const float* src, float* lo, int64_t ld, int64_t rows, int64_t cols, cudaStream_t stream);
+                int64_t ld_dst, int64_t batch, int64_t rows, int64_t cols, cudaStream_t stream, int* lo_nz = nullptr);
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

@@ -231,6 +231,7 @@ struct TcParams {
   const float* mask; long long mask_sm;
   const float* add; long long add_sz; float add_scale;
   float* colsum; long long colsum_sz, colsum_ld;
+  const int* b1_lo_nz;   // device flag: 0 -> B1's lo operand is identically zero (skip its loads and MMAs)
 };
 
 
@@ -376,6 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
   const int nk = nk1 + nk2;
+  const bool skip_b1lo = p.b1_lo_nz != nullptr && *reinterpret_cast<const volatile int*>(p.b1_lo_nz) == 0;
   const int KCr = p.kc;
   const int nchunks = (nk + KCr - 1) / KCr;
   const int mt = (p.M + TBM - 1) / TBM, nt = (p.N + BN - 1) / BN;
@@ -432,8 +434,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
             if (p.dbg & 4) {
               mbar_arrive(full_bar(s));
             } else {
-              mbar_arrive_expect_tx(full_bar(s), SL::STAGE);
               const bool second = kb >= nk1;
+              const bool no_blo = skip_b1lo && !second;
+              mbar_arrive_expect_tx(full_bar(s), SL::STAGE - (no_blo ? SL::B_TILE : 0));
               const int k0 = (second ? kb - nk1 : kb) * TBK;
               const CUtensorMap* ah = second ? &mA2h : &mA1h;
               const CUtensorMap* al = second ? &mA2l : &mA1l;
@@ -444,7 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
               load_operand<A_K, TBM, CL>(st, ah, full_bar(s), k0, m0, za, cj, a_mask);
               load_operand<A_K, TBM, CL>(st + SL::A_TILE, al, full_bar(s), k0, m0, za, cj, a_mask);
               load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, n0, zb, ci, b_mask);
-              load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb, ci, b_mask);
+              if (!no_blo) load_operand<B_K, BN, CL>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, n0, zb, ci, b_mask);
             }
           }
           __syncwarp();
@@ -485,14 +488,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
                 const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
                 const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
                 const uint32_t acc = (kb != c * KCr || j != 0) ? 1u : 0u;   // first MMA of a chunk overwrites
+                const bool no_blo = skip_b1lo && kb < nk1;
                 if (p.merge) {
                   umma_tf32(t_main, dal, dbh, idesc, acc);
-                  umma_tf32(t_main, dah, dbl, idesc, 1);
+                  if (!no_blo) umma_tf32(t_main, dah, dbl, idesc, 1);
                   umma_tf32(t_main, dah, dbh, idesc, 1);
                 } else {
                   if (!(p.dbg & 2)) {
                     umma_tf32(t_small, dal, dbh, idesc, acc);
-                    umma_tf32(t_small, dah, dbl, idesc, 1);
+                    if (!no_blo) umma_tf32(t_small, dah, dbl, idesc, 1);
                   }
                   umma_tf32(t_main, dah, dbh, idesc, acc);
                 }
@@ -608,6 +612,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
   const uint32_t crank = cluster_ctarank();          // 0 = leader
   const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
   const int nk = nk1 + nk2;
+  const bool skip_b1lo = p.b1_lo_nz != nullptr && *reinterpret_cast<const volatile int*>(p.b1_lo_nz) == 0;
   const int KCr = p.kc;
   const int nchunks = (nk + KCr - 1) / KCr;
   const int mpt = (p.M + 2 * TBM - 1) / (2 * TBM), nt = (p.N + BN - 1) / BN;
@@ -655,8 +660,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
             if (p.dbg & 4) {
               if (crank == 0) mbar_arrive(full_bar(s));
             } else {
-              if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SL::STAGE);   // bytes of BOTH CTAs
               const bool second = kb >= nk1;
+              const bool no_blo = skip_b1lo && !second;
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (SL::STAGE - (no_blo ? SL::B_TILE : 0)));   // bytes of BOTH CTAs
               const int k0 = (second ? kb - nk1 : kb) * TBK;
               const CUtensorMap* ah = second ? &mA2h : &mA1h;
               const CUtensorMap* al = second ? &mA2l : &mA1l;
@@ -667,7 +673,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
               load_operand_2sm<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
               load_operand_2sm<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
               load_operand_2sm<B_K, BN / 2>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, nb0, zb);
-              load_operand_2sm<B_K, BN / 2>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, nb0, zb);
+              if (!no_blo) load_operand_2sm<B_K, BN / 2>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, nb0, zb);
             }
           }
           __syncwarp();
@@ -705,14 +711,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant_
                 const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
                 const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
                 const uint32_t acc = (kb != c * KCr || j != 0) ? 1u : 0u;
+                const bool no_blo = skip_b1lo && kb < nk1;
                 if (p.merge) {
                   umma_tf32_2sm(t_main, dal, dbh, idesc, acc);
-                  umma_tf32_2sm(t_main, dah, dbl, idesc, 1);
+                  if (!no_blo) umma_tf32_2sm(t_main, dah, dbl, idesc, 1);
                   umma_tf32_2sm(t_main, dah, dbh, idesc, 1);
                 } else {
                   if (!(p.dbg & 2)) {
                     umma_tf32_2sm(t_small, dal, dbh, idesc, acc);
-                    umma_tf32_2sm(t_small, dah, dbl, idesc, 1);
+                    if (!no_blo) umma_tf32_2sm(t_small, dah, dbl, idesc, 1);
                   }
                   umma_tf32_2sm(t_main, dah, dbh, idesc, acc);
                 }
@@ -821,6 +828,7 @@ gemm_tc2w_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant
   const uint32_t crank = cluster_ctarank();
   const int nk1 = (p.K1 + TBK - 1) / TBK, nk2 = (p.K2 + TBK - 1) / TBK;
   const int nk = nk1 + nk2;
+  const bool skip_b1lo = p.b1_lo_nz != nullptr && *reinterpret_cast<const volatile int*>(p.b1_lo_nz) == 0;
   const int KCr = p.kc;
   const int nchunks = (nk + KCr - 1) / KCr;
   const int mpt = (p.M + 2 * TBM - 1) / (2 * TBM), nt = (p.N + WN - 1) / WN;
@@ -869,8 +877,9 @@ gemm_tc2w_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant
             if (p.dbg & 4) {
               if (crank == 0) mbar_arrive(full_bar(s));
             } else {
-              if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SL::STAGE);
               const bool second = kb >= nk1;
+              const bool no_blo = skip_b1lo && !second;
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (SL::STAGE - (no_blo ? SL::B_TILE : 0)));
               const int k0 = (second ? kb - nk1 : kb) * TBK;
               const CUtensorMap* ah = second ? &mA2h : &mA1h;
               const CUtensorMap* al = second ? &mA2l : &mA1l;
@@ -881,7 +890,7 @@ gemm_tc2w_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant
               load_operand_2sm<A_K, TBM>(st, ah, full_bar(s), k0, m0, za);
               load_operand_2sm<A_K, TBM>(st + SL::A_TILE, al, full_bar(s), k0, m0, za);
               load_operand_2sm<B_K, WN / 2>(st + 2 * SL::A_TILE, bh, full_bar(s), k0, nb0, zb);
-              load_operand_2sm<B_K, WN / 2>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, nb0, zb);
+              if (!no_blo) load_operand_2sm<B_K, WN / 2>(st + 2 * SL::A_TILE + SL::B_TILE, bl, full_bar(s), k0, nb0, zb);
             }
           }
           __syncwarp();
@@ -916,7 +925,7 @@ gemm_tc2w_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant
                 const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
                 if (!(p.dbg & 2)) {
                   umma_tf32_2sm(t_cross, dal, dbh, idesc, (kb != 0 || j != 0) ? 1u : 0u);
-                  umma_tf32_2sm(t_cross, dah, dbl, idesc, 1);
+                  if (!(skip_b1lo && kb < nk1)) umma_tf32_2sm(t_cross, dah, dbl, idesc, 1);
                 }
               }
             }
@@ -1008,7 +1017,8 @@ gemm_tc2w_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant
 // (columns in [cols, ld_dst) are zero-filled)
 __global__ void tf32_split_kernel(const float* __restrict__ src, long long sz_src, long long ld_src,
                                   float* __restrict__ hi, float* __restrict__ lo, long long sz_dst, long long ld_dst,
-                                  long long cols) {
+                                  long long cols, int* __restrict__ nz) {
+  int any = 0;
   const long long r = blockIdx.y, z = blockIdx.z;
   const float* s = src + z * sz_src + r * ld_src;
   float* h = hi + z * sz_dst + r * ld_dst;
@@ -1016,16 +1026,20 @@ __global__ void tf32_split_kernel(const float* __restrict__ src, long long sz_sr
   for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ld_dst; c += (long long)gridDim.x * blockDim.x) {
     float x = c < cols ? s[c] : 0.f;
     float xh = tf32_rna(x);
+    const float xl = tf32_rna(x - xh);
     h[c] = xh;
-    l[c] = tf32_rna(x - xh);
+    l[c] = xl;
+    any |= (xl != 0.f);
   }
+  if (nz && __syncthreads_or(any) && threadIdx.x == 0) atomicOr(nz, 1);
 }
 
 // Contiguous blocks (ld_src == ld_dst == cols, the probe blocks V[b, woff : woff + in*out]): one flat grid-stride pass
 // per batch entry, 4 independent coalesced loads in flight per thread (the source is only 4-byte aligned: b*D + woff).
 __global__ void __launch_bounds__(256) tf32_split_flat_kernel(const float* __restrict__ src, long long sz_src,
                                                               float* __restrict__ hi, float* __restrict__ lo,
-                                                              long long sz_dst, long long n) {
+                                                              long long sz_dst, long long n, int* __restrict__ nz) {
+  int any = 0;
   const long long z = blockIdx.y;
   const float* s = src + z * sz_src;
   float* h = hi + z * sz_dst;
@@ -1039,15 +1053,20 @@ __global__ void __launch_bounds__(256) tf32_split_flat_kernel(const float* __res
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float xh = tf32_rna(x[u]);
+      const float xl = tf32_rna(x[u] - xh);
       h[i + u * stride] = xh;
-      l[i + u * stride] = tf32_rna(x[u] - xh);
+      l[i + u * stride] = xl;
+      any |= (xl != 0.f);
     }
   }
   for (; i < n; i += stride) {
     const float x = __ldg(s + i), xh = tf32_rna(x);
+    const float xl = tf32_rna(x - xh);
     h[i] = xh;
-    l[i] = tf32_rna(x - xh);
+    l[i] = xl;
+    any |= (xl != 0.f);
   }
+  if (nz && __syncthreads_or(any) && threadIdx.x == 0) atomicOr(nz, 1);
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------------
@@ -1132,6 +1151,7 @@ int launch_tc(const TcGemmProblem& g, cudaStream_t st) {
   p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
   p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
   p.colsum = g.colsum; p.colsum_sz = g.colsum_sz; p.colsum_ld = g.colsum_ld;
+  p.b1_lo_nz = g.B1.lo_nz;
   using SL = SmemLayout<BN>;
   auto kern = gemm_tc_kernel<BN, A_K, B_K, CL>;
   static bool attr_set = false;
@@ -1200,6 +1220,7 @@ int launch_tc2(const TcGemmProblem& g, cudaStream_t st) {
   p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
   p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
   p.colsum = g.colsum; p.colsum_sz = g.colsum_sz; p.colsum_ld = g.colsum_ld;
+  p.b1_lo_nz = g.B1.lo_nz;
   using SL = SmemLayout2<BN2>;
   auto kern = gemm_tc2_kernel<BN2, A_K, B_K>;
   static bool attr_set = false;
@@ -1261,6 +1282,7 @@ int launch_tc2w(const TcGemmProblem& g, cudaStream_t st) {
   p.mask = g.epi.mask; p.mask_sm = g.epi.mask_sm;
   p.add = g.epi.add; p.add_sz = g.epi.add_sz; p.add_scale = g.epi.add_scale;
   p.colsum = g.colsum; p.colsum_sz = g.colsum_sz; p.colsum_ld = g.colsum_ld;
+  p.b1_lo_nz = g.B1.lo_nz;
   using SL = SmemLayoutW;
   auto kern = gemm_tc2w_kernel<A_K, B_K>;
   static bool attr_set = false;
@@ -1358,7 +1380,7 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
 }
 
 int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, float* lo, int64_t sz_dst, int64_t ld_dst,
-                int64_t batch, int64_t rows, int64_t cols, cudaStream_t st) {
+                int64_t batch, int64_t rows, int64_t cols, cudaStream_t st, int* lo_nz) {
   if (rows <= 0 || cols <= 0 || batch <= 0) return LIP_OK;
   if (ld_src == cols && ld_dst == cols && batch <= 65535) {
     const int64_t n = rows * cols;
@@ -1367,7 +1389,7 @@ int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, flo
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     dim3 grid((unsigned)g, (unsigned)batch);
-    tf32_split_flat_kernel<<<grid, 256, 0, st>>>(src, sz_src, hi, lo, sz_dst, n);
+    tf32_split_flat_kernel<<<grid, 256, 0, st>>>(src, sz_src, hi, lo, sz_dst, n, lo_nz);
     LIP_LAUNCH_CHECK();
     return LIP_OK;
   }
@@ -1379,7 +1401,7 @@ int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, flo
       const int64_t rc = rows - r0 < 65535 ? rows - r0 : 65535;
       dim3 grid((unsigned)gx, (unsigned)rc, (unsigned)zc);
       tf32_split_kernel<<<grid, 256, 0, st>>>(src + z0 * sz_src + r0 * ld_src, sz_src, ld_src, hi + z0 * sz_dst + r0 * ld_dst,
-                                              lo + z0 * sz_dst + r0 * ld_dst, sz_dst, ld_dst, cols);
+                                              lo + z0 * sz_dst + r0 * ld_dst, sz_dst, ld_dst, cols, lo_nz);
       LIP_LAUNCH_CHECK();
     }
   }
@@ -1388,7 +1410,7 @@ int tf32_split3(const float* src, int64_t sz_src, int64_t ld_src, float* hi, flo
 
 int tf32_split(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows, int64_t cols,
                cudaStream_t st) {
-  return tf32_split3(src, 0, ld_src, hi, lo, 0, ld_dst, 1, rows, cols, st);
+  return tf32_split3(src, 0, ld_src, hi, lo, 0, ld_dst, 1, rows, cols, st, nullptr);
 }
 
 }  // namespace lip

@@ -250,6 +250,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       LIP_CHECK_CUDA(cudaEventRecord(m->ev_fork, st));
       LIP_CHECK_CUDA(cudaStreamWaitEvent(ss, m->ev_fork, 0));
     }
+    LIP_CHECK_CUDA(cudaMemsetAsync(m->lo_nz, 0, sizeof(int) * nL, ss));
     for (int l = 0; l < nL; ++l) {
       if (!m->tc_layer[l]) continue;
       const DenseLayer& Ld = m->L[l];
@@ -261,7 +262,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
         const int64_t b0 = nch == 1 ? 0 : c * chunk, b1 = nch == 1 ? B : (b0 + chunk < B ? b0 + chunk : B);
         if (b1 > b0) {
           int rc = tf32_split3(V + b0 * m->D + Ld.woff, m->D, Ld.out, hi + b0 * bsz, lo + b0 * bsz, bsz, ldw, b1 - b0, Ld.in,
-                               Ld.out, ss);
+                               Ld.out, ss, m->lo_nz + l);
           if (rc) return rc;
         }
         if (overlap) LIP_CHECK_CUDA(cudaEventRecord(m->ev_split[l * NCH + c], ss));
@@ -286,6 +287,9 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       p.a_batched = 0;
       p.B1.hi = vs_hi; p.B1.lo = vs_lo; p.B1.ld = ldw; p.B1.sz = (int64_t)Ld.in * ldw; p.B1.major_k = 0;
       p.b_batched = 1;
+      // exactly-TF32 probes (Rademacher +-1, one-hot): the split found no lo part -> skip its loads / MMAs.  Not in the
+      // probe-chunked overlap mode, where a later chunk's split may still be running when the first GEMM starts.
+      if (!(overlap && l == first_tc && l == 0)) p.B1.lo_nz = m->lo_nz + l;
       if (l > 0) {
         p.A2.hi = prev_hi; p.A2.lo = prev_lo; p.A2.ld = prev_ld; p.A2.sz = m->M * (int64_t)prev_ld; p.A2.major_k = 1;
         p.a2_batched = 1;
@@ -522,6 +526,7 @@ int lip_model_destroy(lip_model* m) {
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->side) cudaStreamDestroy(m->side);
   if (m->rn_stats) cudaFree(m->rn_stats);
+  if (m->lo_nz) cudaFree(m->lo_nz);
   delete m;
   return LIP_OK;
 }
@@ -628,6 +633,7 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
       m->split_off[l] = m->sum_split;
       m->sum_split += (int64_t)m->L[l].in * m->W_ld[l];
     }
+    if (!m->lo_nz) LIP_CHECK_CUDA(cudaMalloc(&m->lo_nz, sizeof(int) * (nL > 0 ? nL : 1)));
     if (!m->side) {
       LIP_CHECK_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
       LIP_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));

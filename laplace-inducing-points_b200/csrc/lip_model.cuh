@@ -66,6 +66,7 @@ struct lip_model {
   int64_t max_split = 0;        // max over tc layers of in * ldw (floats per probe of the split tangent block)
   int64_t sum_split = 0;        // sum over tc layers of in * ldw
   std::vector<int64_t> split_off;   // per layer: float offset (per probe) of its block inside the split buffers
+  int* lo_nz = nullptr;             // [layers] device flags: the probe block of layer l has a non-zero TF32 lo part
   // side stream that runs the probe-block TF32 splits concurrently with the (compute-bound) JVP GEMMs
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr;

@@ -543,3 +543,23 @@ def test_packed_rademacher_probes_round_trip():
         np.testing.assert_array_equal(got, eps)
     with pytest.raises(ValueError):
         stochtrace.unpack_rademacher(torch.zeros(2, 3), 24)
+
+
+def test_exact_tf32_probes_take_the_zero_lo_path():
+    """+-1 (Rademacher) and one-hot probe blocks are exactly TF32: the split kernel finds no lo part and the tcgen05 GEMMs
+    skip that operand's lo loads / MMAs.  The result must equal the oracle exactly as for general probes, and a batch that
+    mixes exact and general rows must take the general path."""
+    from lip_b200 import ggn
+    hidden, n_out, in_dim, M, N = TC_CONFIGS["tc_ragged"]
+    ost, lst = make_pair("large", hidden=hidden, n_out=n_out, in_dim=in_dim, seed=300)
+    rng = np.random.default_rng(301)
+    Z = rng.standard_normal((M, in_dim)).astype(np.float32)
+    D = ost.flat()[0].size
+    ref_vp = O.compute_ggn_vp(ost, Z, "classifier", full_set_size=N)
+    vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=N, tensor_path=True)
+    V_pm = rng.choice([-1.0, 1.0], size=(3, D)).astype(np.float32)
+    V_hot = np.zeros((2, D), np.float32); V_hot[0, 5] = 1.0; V_hot[1, D - 3] = -2.0
+    V_mix = V_pm.copy(); V_mix[1] = rng.standard_normal(D).astype(np.float32)
+    for V in (V_pm, V_hot, V_mix):
+        ref = np.stack([ref_vp(v) for v in V.astype(np.float64)])
+        assert rel_err(vp(cu(V)).cpu().numpy(), ref) < TOL_GGN
