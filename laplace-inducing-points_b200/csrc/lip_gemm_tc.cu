@@ -1344,6 +1344,33 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   static const bool verbose = getenv("LIP_TC_VERBOSE") != nullptr;
   if (verbose) fprintf(stderr, "[lip] gemm_tc M=%lld N=%lld K=%lld K2=%lld batch=%lld a_k=%d b_k=%d two_cta=%d cl4=%d\n", (long long)g.M,
                        (long long)g.N, (long long)g.K, (long long)g.K2, (long long)g.batch, (int)a_k, (int)b_k, two_cta, (int)cl4);
+  // Ragged M (e.g. the 784-row weight gradient of the first MNIST layer): run the rows that fill whole 256-row pair tiles
+  // on the wide kernel and the remaining (< 256) rows as a second launch, instead of padding 784 -> 1024 or giving the whole
+  // problem to the 128-wide kernel.
+  static const int split_m = getenv("LIP_TC_SPLIT_M") ? atoi(getenv("LIP_TC_SPLIT_M")) : 1;
+  if (split_m && g_tc_force2 < 0 && g.M > 2 * TBM && g.M % (2 * TBM) != 0 && g.N > 128 && !g.colsum) {
+    const int64_t M0 = g.M / (2 * TBM) * (2 * TBM);
+    auto shift = [&](TcOperand o, bool batched_unused) {
+      (void)batched_unused;
+      if (o.hi) {
+        const int64_t off = o.major_k ? M0 * o.ld : M0;     // K-major: rows are M; MN-major: M is the contiguous index
+        o.hi += off; o.lo += off;
+      }
+      return o;
+    };
+    TcGemmProblem head = g, tail = g;
+    head.M = M0;
+    tail.M = g.M - M0;
+    tail.A1 = shift(g.A1, g.a_batched);
+    tail.A2 = shift(g.A2, g.a2_batched);
+    tail.C = g.C + M0 * g.c_sm;
+    if (g.C_lo) tail.C_lo = g.C_lo + M0 * g.c_sm;
+    if (g.epi.mask) tail.epi.mask = g.epi.mask + M0 * g.epi.mask_sm;
+    if (g.epi.add) tail.epi.add = g.epi.add + M0 * g.c_sm;
+    int rc = gemm_tc(head, st);
+    if (rc) return rc;
+    return gemm_tc(tail, st);
+  }
   // wide CTA-pair tiles (256 x 256; measured ~22 % faster per tile than 128-wide tiles, profiles/r01_gemm_microbench_wide.txt):
   // used when the padded tile area does not grow by more than 10 % over 128 x 128 tiles.  LIP_TC_WIDE: -1 auto (default),
   // 0 never, 1 whenever M > 128 and N > 128.

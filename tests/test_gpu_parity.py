@@ -563,3 +563,36 @@ def test_exact_tf32_probes_take_the_zero_lo_path():
     for V in (V_pm, V_hot, V_mix):
         ref = np.stack([ref_vp(v) for v in V.astype(np.float64)])
         assert rel_err(vp(cu(V)).cpu().numpy(), ref) < TOL_GGN
+
+
+def test_ggn_vp_is_cuda_graph_capturable():
+    """The hot call enqueues asynchronously on the caller's stream with no allocation / host sync inside the library
+    (include/lip_b200.h contract): one lip_ggn_vp call captured into a CUDA graph replays to the same result, on both
+    arithmetic paths, with new probe values written into the captured input buffer."""
+    from lip_b200 import lla
+    hidden, n_out, in_dim, M, N = TC_CONFIGS["tc_small"]
+    ost, lst = make_pair("large", hidden=hidden, n_out=n_out, in_dim=in_dim, seed=310)
+    rng = np.random.default_rng(311)
+    Z = cu(rng.standard_normal((M, in_dim)).astype(np.float32))
+    D = ost.flat()[0].size
+    for tp in (False, True):
+        cvp = lla.compute_curvature_approx(lst, Z, "classifier", 0.25, full_set_size=N, tensor_path=tp)
+        V = cu(rng.standard_normal((6, D)).astype(np.float32))
+        eager = cvp(V).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            cvp(V)                                   # warm-up on the capture stream (workspace growth, attribute setup)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = cvp(V)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert rel_err(out.cpu().numpy(), eager.cpu().numpy()) < 1e-6
+        V2 = cu(rng.choice([-1.0, 1.0], size=(6, D)).astype(np.float32))
+        expect = cvp(V2).clone()
+        V.copy_(V2)                                  # new probes into the captured input buffer
+        graph.replay()
+        torch.cuda.synchronize()
+        assert rel_err(out.cpu().numpy(), expect.cpu().numpy()) < 1e-6
