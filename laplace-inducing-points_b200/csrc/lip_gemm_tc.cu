@@ -1348,7 +1348,8 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   // on the wide kernel and the remaining (< 256) rows as a second launch, instead of padding 784 -> 1024 or giving the whole
   // problem to the 128-wide kernel.
   static const int split_m = getenv("LIP_TC_SPLIT_M") ? atoi(getenv("LIP_TC_SPLIT_M")) : 1;
-  if (split_m && g_tc_force2 < 0 && g.M > 2 * TBM && g.M % (2 * TBM) != 0 && g.N > 128 && !g.colsum) {
+  if (split_m && g_tc_force2 < 0 && g.M > 2 * TBM && g.M % (2 * TBM) != 0 && g.N > 128 && !g.colsum &&
+      (g.M / (2 * TBM)) * ceil_div(g.N, WN) * g.batch >= 74) {
     const int64_t M0 = g.M / (2 * TBM) * (2 * TBM);
     auto shift = [&](TcOperand o, bool batched_unused) {
       (void)batched_unused;
@@ -1378,7 +1379,10 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   {
     const double area_w = (double)(ceil_div(g.M, 2 * TBM) * 2 * TBM) * (double)(ceil_div(g.N, WN) * WN);
     const double area_n = (double)(ceil_div(g.M, TBM) * TBM) * (double)(ceil_div(g.N, 128) * 128);
-    const bool fits = area_w <= 1.10 * area_n;
+    // wide pair tiles only when there are enough of them to fill the 74 CTA pairs (small probe batches, e.g. the 4-probe
+    // mat-vecs inside SLQ, get more parallelism from 128-wide tiles)
+    const int64_t npairs_w = ceil_div(g.M, 2 * TBM) * ceil_div(g.N, WN) * g.batch;
+    const bool fits = area_w <= 1.10 * area_n && npairs_w >= 74;
     const bool use_w = g_tc_force2 == 2 || (g_tc_force2 < 0 && (wide == 1 || (wide < 0 && fits)) && g.M > TBM && g.N > 128);
     if (use_w) {
       if (a_k && !b_k) return launch_tc2w<true, false>(g, st);
@@ -1386,7 +1390,7 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
       if (a_k && b_k) return launch_tc2w<true, true>(g, st);
     }
   }
-  const bool auto2 = a_k && !b_k && (g.M % (2 * TBM) == 0);
+  const bool auto2 = a_k && !b_k && (g.M % (2 * TBM) == 0) && ceil_div(g.M, 2 * TBM) * ceil_div(g.N, 128) * g.batch >= 74;
   const bool use2 = g_tc_force2 >= 0 ? (g_tc_force2 == 1) : (two_cta < 0 ? auto2 : two_cta != 0);
   if (use2 && g.M > TBM) {
     if (a_k && !b_k) return launch_tc2<128, true, false>(g, st);

@@ -114,6 +114,37 @@ __global__ void colsum_flat_kernel(const float* __restrict__ Delta, long long ro
   }
 }
 
+// Delta back-propagation through a narrow head layer (K = out <= 16 logits):
+//   C[r][n] = mask[r % M][n] * sum_k D[r][k] * W[n][k],   r = (probe, point),  W = kernel [in, K] row-major
+// one thread per output element; the whole kernel matrix sits in shared memory.  Replaces a 128x128-tile GEMM whose K loop
+// had a single, mostly padded k-tile (158 us -> HBM-bound).
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ D, const float* __restrict__ W,
+                                                         const float* __restrict__ mask, float* __restrict__ C,
+                                                         float* __restrict__ C_lo, long long rows, long long M, int in, int K,
+                                                         int ld_out) {
+  extern __shared__ float ws[];   // [in][K]
+  for (int i = threadIdx.x; i < in * K; i += blockDim.x) ws[i] = W[i];
+  __syncthreads();
+  const long long total = rows * in;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / in;
+    const int n = (int)(idx - r * in);
+    const float* d = D + r * K;
+    const float* w = ws + n * K;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(__ldg(d + k), w[k], acc);
+    if (mask) acc *= __ldg(mask + (r % M) * in + n);
+    const long long co = r * ld_out + n;
+    if (C_lo) {
+      const float h = tf32_round(acc);
+      C[co] = h;
+      C_lo[co] = tf32_round(acc - h);
+    } else {
+      C[co] = acc;
+    }
+  }
+}
+
 __global__ void onehot_rows_kernel(float* __restrict__ U, int64_t d, int64_t start, int64_t blk) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= blk * d) return;
@@ -415,6 +446,14 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
         p.colsum = w.colsum; p.colsum_ld = nxt_ld; p.colsum_sz = nslots * (int64_t)nxt_ld;
         int rc = gemm_tc(p, st);
         if (rc) return rc;
+      } else if (Ld.out <= 16 && cur_ld == Ld.out && !cur_split && (size_t)Ld.in * Ld.out * sizeof(float) <= 48 * 1024) {
+        const long long rows = B * m->M, total = rows * Ld.in;
+        long long gb = (total + 255) / 256;
+        if (gb > 148 * 16) gb = 148 * 16;
+        head_dgrad_kernel<<<(unsigned)gb, 256, (size_t)Ld.in * Ld.out * sizeof(float), st>>>(
+            d_hi, m->theta + Ld.woff, m->dphi[l - 1], w.hi[nxt], next_split ? w.lo[nxt] : nullptr, rows, m->M, Ld.in, Ld.out,
+            nxt_ld);
+        LIP_LAUNCH_CHECK();
       } else {
         GemmProblem p;
         p.M = m->M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
