@@ -209,7 +209,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "probes_per_step": args.cpu_probes},
             "cpu_baseline": {"value": pps, "unit": "products/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": pps, "unit": "products/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -465,15 +465,31 @@ def run_b200(args):
                        "parallelism": f"probe-sharded x{world}"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "slq_logdet": slq, "hutchinson_trace_estimate": trace_est}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of this run, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in some images) off it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout must carry exactly one JSON line, but NCCL prints its version banner to fd 1 at communicator creation (and other
+    # native libraries may chat too): point fd 1 at stderr for the whole run and keep the original stdout for emit().
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     set_workload(args.workload)
     if args.workload != "mlp":
