@@ -70,6 +70,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--tensor-path", type=int, default=-1, help="-1 auto, 0 SIMT fp32, 1 tcgen05 3xTF32")
     ap.add_argument("--workload", default="mlp", choices=sorted(WORKLOADS), help="mlp = headline C3b; lenet5 = C4 conv path")
+    ap.add_argument("--points", type=int, default=0, help="override the workload's number of inducing points M")
     return ap.parse_args()
 
 
@@ -492,6 +493,11 @@ def main():
     os.dup2(2, 1)
     args = parse_args()
     set_workload(args.workload)
+    if args.points > 0:
+        global M_POINTS, FLOP_PER_PRODUCT, WORKLOAD
+        FLOP_PER_PRODUCT = FLOP_PER_PRODUCT // M_POINTS * args.points
+        WORKLOAD = WORKLOAD.replace(f"M={M_POINTS}", f"M={args.points}")
+        M_POINTS = args.points
     if args.workload != "mlp":
         args.no_slq = True          # the SLQ leg is defined on the headline MLP
     if args.impl == "reference":

@@ -47,11 +47,49 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 //   acc[z][m][n] = sum_k A1[z][m][k] B1[z][k][n]  (+ sum_k A2[z][m][k] B2[z][k][n])
 //   v = scale*acc + bias[z][n];  (act) ;  v *= mask[m][n];  v += add_scale * add[z][m][n]
 //   C[z][m][n] = v;   dphi_out[z][m][n] = act'(pre-activation)   (forward pass only)
+// division by a runtime constant without the integer divider: q = (umulhi(n, mul) + n) >> shift for 0 <= n < 2^31
+struct FastDiv {
+  uint32_t d = 1, mul = 0, shift = 0;
+  FastDiv() {}
+  explicit FastDiv(uint32_t div) : d(div) {
+    shift = 0;
+    while ((1ull << shift) < div) ++shift;
+    mul = (uint32_t)((((1ull << shift) - div) << 32) / div + 1);
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(((uint64_t)__umulhi(n, mul) + n) >> shift);
+#else
+    return n / d;
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
+// Implicit-GEMM view of an NHWC image [*, Hi, Wi, C] as the A operand of a GEMM (no im2col buffer).  patch(r, kc) is the
+// im2col element of output pixel r = (mz, y, x) and patch column kc = (dy, dx, c) (the row order of a flax HWIO kernel):
+//   mode 1:  A[m][k] = patch(r = m, kc = k)                      (conv forward / JVP: rows = output pixels)
+//   mode 2:  A[m][k] = patch(r = k, kc = m)                      (weight gradient: A = patches^T, contraction over pixels)
+//   mode 3:  A[m][k] = D[(mz, y, x), co]  with m = input pixel (mz, yi, xi), k = (dy, dx, co),
+//            y * stride = yi + pad_h - dy, x * stride = xi + pad_w - dx   (delta back-propagation = transposed conv; C = cout
+//            of the source image D [*, Ho, Wo, C])
+// Elements that fall into the zero padding (or between strides) read as 0.
+struct ConvGather {
+  int mode = 0;
+  int Hi = 0, Wi = 0, C = 0, pad_h = 0, pad_w = 0, stride = 1, kh = 1, kw = 1, Ho = 0, Wo = 0;
+  FastDiv dC, dkw, dWo, dHo, dWi, dHi;
+  void finalize() {
+    dC = FastDiv((uint32_t)C); dkw = FastDiv((uint32_t)kw); dWo = FastDiv((uint32_t)Wo); dHo = FastDiv((uint32_t)Ho);
+    dWi = FastDiv((uint32_t)Wi); dHi = FastDiv((uint32_t)Hi);
+  }
+};
+
 struct GemmOperand {
   const float* ptr = nullptr;
   int64_t sz = 0;   // batch stride
   int64_t s0 = 0;   // stride of the row index (m for A, k for B)
   int64_t s1 = 0;   // stride of the col index (k for A, n for B)
+  ConvGather conv;  // A operands only: mode != 0 replaces the (s0, s1) addressing by the patch gather above
 };
 
 struct GemmEpilogue {

@@ -15,7 +15,39 @@ constexpr int BM = 128, BN = 128, BK = 16, NT = 256, PAD = 4;
 struct DevOperand {
   const float* ptr;
   long long sz, s0, s1;
+  ConvGather conv;
 };
+
+// offset of the image element behind A[m][k] of a gathered operand; false = zero padding
+__device__ __forceinline__ bool conv_offset(const ConvGather& c, uint32_t m, uint32_t k, long long* off) {
+  if (c.mode == 3) {
+    uint32_t t, co, dx, dy, xi, yi, mz;
+    c.dC.divmod(k, t, co);
+    c.dkw.divmod(t, dy, dx);
+    c.dWi.divmod(m, t, xi);
+    c.dHi.divmod(t, mz, yi);
+    const int ys = (int)yi + c.pad_h - (int)dy, xs = (int)xi + c.pad_w - (int)dx;
+    if (ys < 0 || xs < 0) return false;
+    int y = ys, x = xs;
+    if (c.stride != 1) {
+      if ((ys % c.stride) | (xs % c.stride)) return false;
+      y = ys / c.stride; x = xs / c.stride;
+    }
+    if (y >= c.Ho || x >= c.Wo) return false;
+    *off = (((long long)mz * c.Ho + y) * c.Wo + x) * c.C + co;
+    return true;
+  }
+  const uint32_t r = c.mode == 1 ? m : k, kc = c.mode == 1 ? k : m;
+  uint32_t t, ch, dx, dy, x, y, mz;
+  c.dC.divmod(kc, t, ch);
+  c.dkw.divmod(t, dy, dx);
+  c.dWo.divmod(r, t, x);
+  c.dHo.divmod(t, mz, y);
+  const int yi = (int)y * c.stride + (int)dy - c.pad_h, xi = (int)x * c.stride + (int)dx - c.pad_w;
+  if (yi < 0 || yi >= c.Hi || xi < 0 || xi >= c.Wi) return false;
+  *off = (((long long)mz * c.Hi + yi) * c.Wi + xi) * c.C + ch;
+  return true;
+}
 
 struct DevGemm {
   int M, N, K1, K2;
@@ -34,7 +66,9 @@ struct DevGemm {
   long long part_sz;   // stride between slices = batch * M * N
 };
 
-template <bool KC, int ROWS>  // KC: the contraction index is the contiguous one for this operand; ROWS: tile extent of the other
+// KC: the contraction index is the contiguous one for this operand; ROWS: tile extent of the other; GATHER: the A operand may
+// be an implicit-GEMM patch gather (compiled out of the plain kernels: the divmod chain costs registers / occupancy)
+template <bool KC, int ROWS, bool GATHER>
 __device__ __forceinline__ void load_tile(const DevOperand& op, long long zoff, int row0, int rows, int k0, int K,
                                           bool is_a, float (&reg)[ROWS * BK / NT]) {
   // A tile: [ROWS rows(m)] x [BK k]; B tile: [BK k] x [ROWS cols(n)].  "row" below = the non-k index.
@@ -47,9 +81,14 @@ __device__ __forceinline__ void load_tile(const DevOperand& op, long long zoff, 
     int gr = row0 + r, gk = k0 + k;
     float v = 0.f;
     if (gr < rows && gk < K) {
-      long long off = is_a ? ((long long)gr * op.s0 + (long long)gk * op.s1)
-                           : ((long long)gk * op.s0 + (long long)gr * op.s1);
-      v = __ldg(op.ptr + zoff + off);
+      if (GATHER && is_a && op.conv.mode) {
+        long long off;
+        if (conv_offset(op.conv, (uint32_t)gr, (uint32_t)gk, &off)) v = __ldg(op.ptr + zoff + off);
+      } else {
+        long long off = is_a ? ((long long)gr * op.s0 + (long long)gk * op.s1)
+                             : ((long long)gk * op.s0 + (long long)gr * op.s1);
+        v = __ldg(op.ptr + zoff + off);
+      }
     }
     reg[i] = v;
   }
@@ -68,7 +107,7 @@ __device__ __forceinline__ void store_tile(float (*S)[ROWS + PAD], const float (
 }
 
 // BNT: tile width (128, or 64 / 32 for narrow outputs such as 32- and 64-channel convs); NJ = BNT / 16 columns per thread
-template <bool A_KC, bool B_KC, int BNT>
+template <bool A_KC, bool B_KC, int BNT, bool GATHER>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
   constexpr int NJ = BNT / 16;
   __shared__ __align__(16) float As[2][BK][BM + PAD];
@@ -98,16 +137,16 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
     const int kt0 = (int)((long long)nk_all * slice / ks), nk = (int)((long long)nk_all * (slice + 1) / ks);
     if (kt0 >= nk) continue;
     float ra[8], rb[BNT * BK / NT];
-    load_tile<A_KC, BM>(A, za, m0, g.M, kt0 * BK, K, true, ra);
-    load_tile<B_KC, BNT>(B, zb, n0, g.N, kt0 * BK, K, false, rb);
+    load_tile<A_KC, BM, GATHER>(A, za, m0, g.M, kt0 * BK, K, true, ra);
+    load_tile<B_KC, BNT, false>(B, zb, n0, g.N, kt0 * BK, K, false, rb);
     store_tile<A_KC, BM>(As[kt0 & 1], ra);
     store_tile<B_KC, BNT>(Bs[kt0 & 1], rb);
     __syncthreads();
     for (int kt = kt0; kt < nk; ++kt) {
       const int cur = kt & 1;
       if (kt + 1 < nk) {
-        load_tile<A_KC, BM>(A, za, m0, g.M, (kt + 1) * BK, K, true, ra);
-        load_tile<B_KC, BNT>(B, zb, n0, g.N, (kt + 1) * BK, K, false, rb);
+        load_tile<A_KC, BM, GATHER>(A, za, m0, g.M, (kt + 1) * BK, K, true, ra);
+        load_tile<B_KC, BNT, false>(B, zb, n0, g.N, (kt + 1) * BK, K, false, rb);
       }
 #pragma unroll
       for (int k = 0; k < BK; ++k) {
@@ -189,7 +228,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
 // thread (row r, column group cg) keeps 4 accumulators; A tile [32 k][64 m] and B tile [32 k][16 n] in shared memory.
 constexpr int SB_M = 64, SB_K = 32, SB_N = 16;
 
-template <bool A_KC>
+template <bool A_KC, bool GATHER>
 __global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
   __shared__ float As[SB_K][SB_M + 1];
   __shared__ __align__(16) float Bs[SB_K][SB_N];
@@ -218,7 +257,16 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
         int k, rr;
         if (A_KC) { k = idx % SB_K; rr = idx / SB_K; } else { rr = idx % SB_M; k = idx / SB_M; }
         const int gm = m0 + rr, gk = k0 + k;
-        As[k][rr] = (gm < g.M && gk < K) ? __ldg(Ap + (long long)gm * A.s0 + (long long)gk * A.s1) : 0.f;
+        float av = 0.f;
+        if (gm < g.M && gk < K) {
+          if (GATHER && A.conv.mode) {
+            long long off;
+            if (conv_offset(A.conv, (uint32_t)gm, (uint32_t)gk, &off)) av = __ldg(Ap + off);
+          } else {
+            av = __ldg(Ap + (long long)gm * A.s0 + (long long)gk * A.s1);
+          }
+        }
+        As[k][rr] = av;
       }
 #pragma unroll
       for (int i = 0; i < (SB_K * SB_N) / NT; ++i) {
@@ -304,18 +352,23 @@ __global__ void splitk_reduce_kernel(DevGemm g, long long total) {
 int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return LIP_OK;
   LIP_REQUIRE(p.A1.ptr && p.B1.ptr && p.C, "gemm_simt: null operand");
-  const bool a_kc = (p.A1.s1 == 1);   // A contiguous along k
+  const bool a_kc = p.A1.conv.mode ? (p.A1.conv.mode != 2) : (p.A1.s1 == 1);   // A contiguous along k
   const bool b_kc = (p.B1.s1 != 1);   // B contiguous along k (else along n)
-  LIP_REQUIRE(a_kc || p.A1.s0 == 1, "gemm_simt: A must be contiguous along m or k");
+  LIP_REQUIRE(p.A1.conv.mode || a_kc || p.A1.s0 == 1, "gemm_simt: A must be contiguous along m or k");
   LIP_REQUIRE(!b_kc || p.B1.s0 == 1, "gemm_simt: B must be contiguous along k or n");
   if (p.A2.ptr) {
     LIP_REQUIRE(p.B2.ptr != nullptr, "gemm_simt: A2 without B2");
-    LIP_REQUIRE(a_kc ? p.A2.s1 == 1 : p.A2.s0 == 1, "gemm_simt: A2 must share A1's contiguous index");
+    LIP_REQUIRE(p.A2.conv.mode ? ((p.A2.conv.mode != 2) == a_kc) : (a_kc ? p.A2.s1 == 1 : p.A2.s0 == 1),
+                "gemm_simt: A2 must share A1's contiguous index");
     LIP_REQUIRE(b_kc ? p.B2.s0 == 1 : p.B2.s1 == 1, "gemm_simt: B2 must share B1's contiguous index");
   }
   DevGemm g;
   g.M = (int)p.M; g.N = (int)p.N; g.K1 = (int)p.K; g.K2 = (int)p.K2;
-  auto cv = [](const GemmOperand& o) { return DevOperand{o.ptr, o.sz, o.s0, o.s1}; };
+  auto cv = [](const GemmOperand& o) {
+    DevOperand d{o.ptr, o.sz, o.s0, o.s1, o.conv};
+    if (d.conv.mode) d.conv.finalize();
+    return d;
+  };
   g.A1 = cv(p.A1); g.B1 = cv(p.B1); g.A2 = cv(p.A2); g.B2 = cv(p.B2);
   g.C = p.C; g.c_sz = p.c_sz; g.c_sm = p.c_sm;
   g.scale = p.epi.scale;
@@ -324,6 +377,7 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
   g.add = p.epi.add; g.add_sz = p.epi.add_sz; g.add_scale = p.epi.add_scale;
   g.act = p.epi.act; g.dphi_out = p.epi.dphi_out; g.C_lo = p.epi.C_lo;
   g.ksplit = 1; g.part = nullptr; g.part_sz = 0;
+  const bool gather = p.A1.conv.mode != 0 || p.A2.conv.mode != 0;
 
   // split-K decision: few tiles, long K, scratch available, single operand pair, batch in one launch
   const bool skinny = p.N <= SB_N;
@@ -357,8 +411,13 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     grid.z = (unsigned)zc;
     if (p.N <= SB_N) {
       dim3 sg(1, (unsigned)(ceil_div(p.M, SB_M) * g.ksplit), (unsigned)zc);
-      if (a_kc) gemm_skinny_kernel<true><<<sg, NT, 0, stream>>>(gz);
-      else gemm_skinny_kernel<false><<<sg, NT, 0, stream>>>(gz);
+      if (gather) {
+        if (a_kc) gemm_skinny_kernel<true, true><<<sg, NT, 0, stream>>>(gz);
+        else gemm_skinny_kernel<false, true><<<sg, NT, 0, stream>>>(gz);
+      } else {
+        if (a_kc) gemm_skinny_kernel<true, false><<<sg, NT, 0, stream>>>(gz);
+        else gemm_skinny_kernel<false, false><<<sg, NT, 0, stream>>>(gz);
+      }
       LIP_LAUNCH_CHECK();
       if (g.ksplit > 1) {
         const long long total = (long long)p.batch * p.M * p.N;
@@ -369,16 +428,21 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
       }
       continue;
     }
+#define LIP_SIMT_LAUNCH_G(AK, BK_, G)                                                            \
+    do {                                                                                          \
+      if (bnt == 32) gemm_simt_kernel<AK, BK_, 32, G><<<grid, NT, 0, stream>>>(gz);                \
+      else if (bnt == 64) gemm_simt_kernel<AK, BK_, 64, G><<<grid, NT, 0, stream>>>(gz);           \
+      else gemm_simt_kernel<AK, BK_, 128, G><<<grid, NT, 0, stream>>>(gz);                         \
+    } while (0)
 #define LIP_SIMT_LAUNCH(AK, BK_)                                                                 \
     do {                                                                                          \
-      if (bnt == 32) gemm_simt_kernel<AK, BK_, 32><<<grid, NT, 0, stream>>>(gz);                   \
-      else if (bnt == 64) gemm_simt_kernel<AK, BK_, 64><<<grid, NT, 0, stream>>>(gz);              \
-      else gemm_simt_kernel<AK, BK_, 128><<<grid, NT, 0, stream>>>(gz);                            \
+      if (gather) LIP_SIMT_LAUNCH_G(AK, BK_, true); else LIP_SIMT_LAUNCH_G(AK, BK_, false);         \
     } while (0)
     if (a_kc && !b_kc) LIP_SIMT_LAUNCH(true, false);
     else if (!a_kc && !b_kc) LIP_SIMT_LAUNCH(false, false);
     else if (a_kc && b_kc) LIP_SIMT_LAUNCH(true, true);
     else LIP_SIMT_LAUNCH(false, true);
+#undef LIP_SIMT_LAUNCH_G
 #undef LIP_SIMT_LAUNCH
     LIP_LAUNCH_CHECK();
     if (g.ksplit > 1) {

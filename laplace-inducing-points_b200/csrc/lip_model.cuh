@@ -33,12 +33,20 @@ struct ConvBN {
   int relu = 0;
   int src = -2, dst = 0, skip = -1;                // tangent-buffer slots (0..3); src -2 = the network input (data)
   int accumulate = 0;                              // VJP: the cotangent of `src` already holds another branch's contribution
-  float* Aop = nullptr;    // [M*Ho*Wo, kh*kw*cin] im2col patches of the cached input activation
+  float* Xin = nullptr;    // [M, Hi, Wi, cin] cached input activation (the conv GEMMs gather their patches from it)
+  float* Wt = nullptr;     // [kh*kw*cout, cin] kernel re-laid for the delta back-propagation (transposed conv) GEMM
   float* xhat = nullptr;   // [M*Ho*Wo, cout]
   float* mask = nullptr;   // [M*Ho*Wo, cout] relu' of the unit's pre-activation (null without relu)
   float* g = nullptr;      // [cout] scale * rsqrt(var + eps)
   int64_t P() const { return (int64_t)Ho * Wo; }
   int64_t Kc() const { return (int64_t)kh * kw * cin; }
+  // gather descriptors (lip_common.cuh: ConvGather) of this conv for the three GEMM roles
+  lip::ConvGather gather(int mode) const {
+    lip::ConvGather cg;
+    cg.mode = mode; cg.Hi = Hi; cg.Wi = Wi; cg.C = (mode == 3) ? cout : cin; cg.pad_h = pad_h; cg.pad_w = pad_w;
+    cg.stride = stride; cg.kh = kh; cg.kw = kw; cg.Ho = Ho; cg.Wo = Wo;
+    return cg;
+  }
 };
 
 struct lip_model {

@@ -4,10 +4,12 @@
 //   y = relu?( scale * xhat + beta + skip ),   xhat = (conv(x, W) - mean) * rsqrt(var + eps),   g = scale * rsqrt(var + eps)
 // (stem; per BasicBlock: conv-bn-relu, conv-bn, optional 1x1 strided conv-bn on the residual, add, relu), a global mean and
 // a Dense head.  BatchNorm scale / bias ARE parameters (they are in the flat vector); mean / var are constants (ggn.py:52).
-//   JVP  unit:  dY[b] = mask * ( g * (Aop . dW[b] + col(T_src[b]) . W) + xhat * dscale[b] + dbeta[b] + T_skip[b] )
+//   JVP  unit:  dY[b] = mask * ( g * (patches(X) . dW[b] + patches(T_src[b]) . W) + xhat * dscale[b] + dbeta[b] + T_skip[b] )
 //   VJP  unit:  Dy = Dout * mask;  gbeta = colsum Dy;  gscale = colsum (Dy * xhat);  cot[skip] (+)= Dy;  Dh = g * Dy;
-//               gW[b] = Aop^T . Dh[b];  cot[src] (+)= col2im(Dh[b] . W^T)
-// Convs run as GEMMs over im2col patches (Aop cached at bind; col(.) materialised per call), on the fp32 SIMT kernels.
+//               gW[b] = patches(X)^T . Dh[b];  cot[src] (+)= transposed_conv(Dh[b], W)
+// Convs run as IMPLICIT GEMMs on the fp32 SIMT kernels: the A operand gathers its im2col patches straight from the NHWC
+// image (ConvGather in lip_common.cuh) - the cached input activation, the probe's tangent image, or (transposed conv) the
+// delta - so no patch buffer, im2col or col2im pass exists and memory stays O(activations).
 // Tangents / cotangents live in four rotating [B, M, H, W, C] slots (block input, branch, shortcut, block output).
 #include <new>
 #include <vector>
@@ -18,11 +20,12 @@ using namespace lip;
 
 void lip_model::free_resnet_cache() {
   for (auto& u : RB) {
-    if (u.Aop) cudaFree(u.Aop);
+    if (u.Xin) cudaFree(u.Xin);
+    if (u.Wt) cudaFree(u.Wt);
     if (u.xhat) cudaFree(u.xhat);
     if (u.mask) cudaFree(u.mask);
     if (u.g) cudaFree(u.g);
-    u.Aop = u.xhat = u.mask = u.g = nullptr;
+    u.Xin = u.Wt = u.xhat = u.mask = u.g = nullptr;
   }
   if (rn_mean_act) cudaFree(rn_mean_act);
   rn_mean_act = nullptr;
@@ -120,6 +123,15 @@ __global__ void bn_param_grad_kernel(const float* __restrict__ dout, const float
   }
 }
 
+// Wt[(tap*cout + co)*cin + ci] = W[(tap*cin + ci)*cout + co]
+__global__ void conv_wt_kernel(const float* __restrict__ W, float* __restrict__ Wt, int taps, int cin, int cout) {
+  const int total = taps * cin * cout;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ci = idx % cin, t = idx / cin, co = t % cout, tap = t / cout;
+    Wt[idx] = W[(tap * cin + ci) * cout + co];
+  }
+}
+
 // out[mz][c] = mean over hw of in[mz][hw][c]
 __global__ void global_mean_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int HW, int C) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -144,7 +156,7 @@ __global__ void global_mean_bwd_kernel(const float* __restrict__ g, float* __res
 struct RnWs {
   float* slot[4];   // tangent / cotangent tensors [B, M, slot_elems]
   float* raw;       // conv GEMM output dH / Dh, [B, max R*cout]
-  float* col;       // im2col of a tangent / Dh . W^T, [B, max R*Kc]
+  float* col;       // split-K scratch of the per-probe kernel-gradient GEMMs
   float* head;      // [B, M, C_last] mean tangent / cotangent  +  [B, M, K] delta at the logits
   float* dl;
 };
@@ -157,10 +169,8 @@ RnSizes rn_sizes(const lip_model* m, int64_t B) {
   for (const ConvBN& u : m->RB) {
     const size_t r = (size_t)B * m->M * u.P() * u.cout;
     raw = r > raw ? r : raw;
-    if (u.src != -2) {
-      const size_t c = (size_t)B * m->M * u.P() * u.Kc();
-      col = c > col ? c : col;
-    }
+    const size_t c = (size_t)B * u.Kc() * u.cout * 8;        // up to 8 K-slices of every probe's [Kc x cout] gradient
+    col = c > col ? c : col;
   }
   z.raw = align_up(raw, 64); z.col = align_up(col, 64);
   z.head = align_up((size_t)B * m->M * m->rn_C, 64);
@@ -190,12 +200,11 @@ int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* 
     const int64_t R = m->M * u.P(), Kc = u.Kc();
     GemmProblem p;
     p.M = R; p.N = u.cout; p.K = Kc; p.batch = B;
-    p.A1 = {u.Aop, 0, Kc, 1};
+    p.A1.ptr = u.Xin; p.A1.sz = 0; p.A1.conv = u.gather(1);                    // patches of the cached activation
     p.B1 = {V + u.woff, m->D, u.cout, 1};
     if (u.src != -2) {
-      int rc = im2col(w.slot[u.src], w.col, B * m->M, u.Hi, u.Wi, u.cin, u.pad_h, u.pad_w, u.stride, u.kh, u.kw, u.Ho, u.Wo, st);
-      if (rc) return rc;
-      p.A2 = {w.col, R * Kc, Kc, 1};
+      p.A2.ptr = w.slot[u.src]; p.A2.sz = m->M * (int64_t)u.Hi * u.Wi * u.cin;  // patches of the probe's tangent image
+      p.A2.conv = u.gather(1);
       p.B2 = {m->theta + u.woff, 0, u.cout, 1};
       p.K2 = Kc;
     }
@@ -270,28 +279,27 @@ int rn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const RnWs& w, float*
     bn_vjp_kernel<<<ew_grid(total), 256, 0, st>>>(dout, u.mask, u.g, w.raw, u.skip >= 0 ? w.slot[u.skip] : nullptr, 0, total,
                                                   per_z, u.cout);
     LIP_LAUNCH_CHECK();
-    {  // kernel gradient [Kc x cout] = Aop^T . Dh
+    {  // kernel gradient [Kc x cout] = patches(X)^T . Dh
       GemmProblem p;
       p.M = Kc; p.N = u.cout; p.K = R; p.batch = B;
-      p.A1 = {u.Aop, 0, 1, Kc};
+      p.A1.ptr = u.Xin; p.A1.sz = 0; p.A1.conv = u.gather(2);
       p.B1 = {w.raw, per_z, u.cout, 1};
       p.C = out + u.woff; p.c_sz = m->D; p.c_sm = u.cout;
       p.epi.scale = scale;
       if (add) { p.epi.add = add + u.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
-      p.splitk_ws = w.col; p.splitk_ws_elems = (int64_t)col_elems;    // col is free until the G GEMM below
+      p.splitk_ws = w.col; p.splitk_ws_elems = (int64_t)col_elems;
       int rc = gemm_simt(p, st);
       if (rc) return rc;
     }
     if (u.src == -2) continue;
-    GemmProblem q;   // G [R x Kc] = Dh . W^T, scattered back to the input image
-    q.M = R; q.N = Kc; q.K = u.cout; q.batch = B;
-    q.A1 = {w.raw, per_z, u.cout, 1};
-    q.B1 = {m->theta + u.woff, 0, 1, u.cout};
-    q.C = w.col; q.c_sz = R * Kc; q.c_sm = Kc;
+    // cotangent of the input image = transposed conv of Dh: one GEMM whose A operand gathers Dh (no col buffer / col2im)
+    GemmProblem q;
+    q.M = m->M * (int64_t)u.Hi * u.Wi; q.N = u.cin; q.K = (int64_t)u.kh * u.kw * u.cout; q.batch = B;
+    q.A1.ptr = w.raw; q.A1.sz = per_z; q.A1.conv = u.gather(3);
+    q.B1 = {u.Wt, 0, u.cin, 1};
+    q.C = w.slot[u.src]; q.c_sz = q.M * (int64_t)u.cin; q.c_sm = u.cin;
+    if (u.accumulate) { q.epi.add = q.C; q.epi.add_sz = q.c_sz; q.epi.add_scale = 1.f; }   // second branch into this slot
     int rc = gemm_simt(q, st);
-    if (rc) return rc;
-    rc = col2im(w.col, w.slot[u.src], B * m->M, u.Hi, u.Wi, u.cin, u.pad_h, u.pad_w, u.stride, u.kh, u.kw, u.Ho, u.Wo,
-                u.accumulate, st);
     if (rc) return rc;
   }
   return LIP_OK;
@@ -422,18 +430,23 @@ int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cud
   int rc = LIP_OK;
   for (ConvBN& u : m->RB) {
     const int64_t R = M * u.P(), Kc = u.Kc();
-    if (cudaMalloc(&u.Aop, sizeof(float) * (size_t)R * Kc + 256) != cudaSuccess ||
+    const size_t xin_elems = (size_t)M * u.Hi * u.Wi * u.cin;
+    if (cudaMalloc(&u.Xin, sizeof(float) * xin_elems + 256) != cudaSuccess ||
+        cudaMalloc(&u.Wt, sizeof(float) * (size_t)Kc * u.cout + 256) != cudaSuccess ||
         cudaMalloc(&u.xhat, sizeof(float) * (size_t)R * u.cout + 256) != cudaSuccess ||
         cudaMalloc(&u.g, sizeof(float) * u.cout) != cudaSuccess ||
         (u.relu && cudaMalloc(&u.mask, sizeof(float) * (size_t)R * u.cout + 256) != cudaSuccess)) {
       cleanup(); set_error("lip_model_bind: out of device memory (conv cache)"); return LIP_ERR_CUDA;
     }
     const float* x = u.src == -2 ? Z : act[u.src];
-    rc = im2col(x, u.Aop, M, u.Hi, u.Wi, u.cin, u.pad_h, u.pad_w, u.stride, u.kh, u.kw, u.Ho, u.Wo, st);
-    if (rc) break;
+    if (cudaMemcpyAsync(u.Xin, x, sizeof(float) * xin_elems, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      cleanup(); set_error("lip_model_bind: activation copy failed"); return LIP_ERR_CUDA;
+    }
+    conv_wt_kernel<<<(unsigned)ceil_div(Kc * u.cout, 256), 256, 0, st>>>(theta + u.woff, u.Wt, u.kh * u.kw, u.cin, u.cout);
+    count_launch();
     GemmProblem p;
     p.M = R; p.N = u.cout; p.K = Kc; p.batch = 1;
-    p.A1 = {u.Aop, 0, Kc, 1};
+    p.A1.ptr = u.Xin; p.A1.sz = 0; p.A1.conv = u.gather(1);
     p.B1 = {theta + u.woff, 0, u.cout, 1};
     p.C = tmp; p.c_sz = 0; p.c_sm = u.cout;
     rc = gemm_simt(p, st);
