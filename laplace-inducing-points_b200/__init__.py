@@ -1,7 +1,7 @@
 """lip_b200 â€” B200-native (sm_100a) drop-in for the matrix-free linearized-Laplace hot path of
 nrholm1/Laplace-Inducing-Points.  Module names mirror the reference's `src/` package:
 
-    ggn, lla, stochtrace, sample, matfree_monkeypatch, utils, toymodels, scalemodels
+    ggn, lla, stochtrace, sample, matfree_monkeypatch, utils, toymodels, scalemodels, train_inducing (forward objective)
     matfree  (replacements for the third-party matfree / jax.scipy.sparse.linalg.cg routines)
 
 All compute runs in liblip_b200.so (hand-written CUDA behind the C ABI of include/lip_b200.h); importing this
@@ -10,7 +10,7 @@ package without the built library, or calling it without a CUDA device, raises â
 from . import _cabi  # noqa: F401
 
 __all__ = ["ggn", "lla", "stochtrace", "sample", "matfree", "matfree_monkeypatch", "utils", "toymodels",
-           "scalemodels"]
+           "scalemodels", "train_inducing"]
 
 
 def __getattr__(name):

@@ -574,6 +574,35 @@ def slq_logdet_gkl(state, Z, model_type, alpha, probes, num_matvecs):
     return estimator(integrand, probes)(Av, vA)
 
 
+def alternative_objective_scalable(Z, X, state, alpha, model_type, probes, full_set_size=None, st_samples=None,
+                                   slq_samples=2, slq_num_matvecs=None):
+    """train_inducing.py:87-173 (forward value): tr(S_X S_Z^{-1}) by hutchpp_v2 on the Woodbury inverse + the GKL logdet.
+    `probes` [st_samples, D] replaces the matfree Rademacher sampler (:138-142; the same probes feed both terms)."""
+    import scipy.linalg as sla
+    probes = np.asarray(probes, dtype=np.float64)
+    st_samples = probes.shape[0] if st_samples is None else st_samples
+    N = full_set_size
+    M = np.asarray(Z).shape[0]
+    beta = N / M
+    S_vp = compute_curvature_approx(state, X, model_type, alpha, full_set_size=N)                # :108-110
+    Wz, WzT = compute_W_vps(state, Z, model_type, full_set_size=None)                            # :114-116
+    D = state.flat()[0].size
+    inner = np.asarray(WzT(np.zeros(D))).shape
+    d_z = int(np.prod(inner))
+    WzTWz = build_WTW(Wz, WzT, inner, d_z, block=1)                                              # :126
+    Kmat = np.eye(d_z) / beta + WzTWz / alpha
+
+    def Sz_inv(v):                                                                               # :127-132
+        u = np.asarray(WzT(v)).reshape(d_z)
+        x = sla.solve(Kmat, u)
+        return v / alpha - Wz(x.reshape(inner)) / alpha ** 2
+
+    trace_term = hutchpp_v2(lambda v: S_vp(Sz_inv(v)), probes[:st_samples], s1=st_samples - 16, s2=16)   # :144-145
+    k = slq_num_matvecs if slq_num_matvecs is not None else int(M * 0.8)                         # :148
+    logdet_term = slq_logdet_gkl(state, Z, model_type, alpha, probes[:slq_samples], k)           # :156-171
+    return logdet_term + trace_term
+
+
 def slq_logdet_lanczos(matvec, probes, num_matvecs, *, clip_min=1.0):
     """train_inducing.py:152-153 (commented 'old tridiagonal formulation') / tests/test_variational.py:126-150."""
     integrand = integrand_funm_sym_logdet(tridiag_sym(num_matvecs), clip_min=clip_min)

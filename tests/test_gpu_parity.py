@@ -596,3 +596,29 @@ def test_ggn_vp_is_cuda_graph_capturable():
         graph.replay()
         torch.cuda.synchronize()
         assert rel_err(out.cpu().numpy(), expect.cpu().numpy()) < 1e-6
+
+
+# --------------------------------------------------------------------------------- the production caller
+@pytest.mark.parametrize("kind", ["classifier", "regressor"])
+def test_scalable_kl_objective_forward_matches_oracle(kind):
+    """train_inducing.py:87-173 (forward value): Hutch++ v2 trace of S_X S_Z^{-1} (Woodbury) + GKL logdet, with identical
+    probes, against the float64 restatement."""
+    from lip_b200 import train_inducing
+    if kind == "classifier":
+        ost, lst = make_pair("classifier", hidden=[16, 16], n_out=2, in_dim=2, seed=50)
+        M, k = 32, None
+    else:
+        ost, lst = make_pair("regressor", hidden=[8, 8], n_out=1, in_dim=1, seed=51, logvar=0.3)
+        M, k = 30, 20
+    in_dim = 2 if kind == "classifier" else 1
+    rng = np.random.default_rng(52)
+    Z = rng.standard_normal((M, in_dim)).astype(np.float32)
+    X = rng.standard_normal((48, in_dim)).astype(np.float32)
+    D = ost.flat()[0].size
+    probes = rng.choice([-1.0, 1.0], size=(40, D)).astype(np.float32)
+    alpha, N = 0.9, 800
+    ref = O.alternative_objective_scalable(Z, X, ost, alpha, kind, probes.astype(np.float64), full_set_size=N, slq_samples=2,
+                                           slq_num_matvecs=k)
+    got = float(train_inducing.alternative_objective_scalable(cu(Z), cu(X), lst, alpha, kind, 0, full_set_size=N, st_samples=40,
+                                                              slq_samples=2, slq_num_matvecs=k, probes=cu(probes)))
+    assert abs(got - ref) <= TOL_EST * abs(ref), (got, ref)
