@@ -395,6 +395,8 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     }
   }
 
+  LIP_REQUIRE((skinny ? ceil_div(p.M, SB_M) : ceil_div(p.M, BM)) * g.ksplit <= 65535 && ceil_div(p.N, bnt) <= 2147483647LL,
+              "gemm_simt: %lld rows exceed the grid limit of this kernel (tile rows x K slices <= 65535)", (long long)p.M);
   dim3 grid((unsigned)ceil_div(p.N, bnt), (unsigned)(ceil_div(p.M, BM) * g.ksplit), 1);
   // gridDim.z is limited to 65535: chunk the batch.
   const int64_t zmax = 65535;
