@@ -400,6 +400,19 @@ def run_b200(args):
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        # the Lanczos form (integrand_funm_sym_logdet of src/matfree_monkeypatch.py:25-41, eigenvalues clipped to >= 1;
+        # train_inducing.py:152-153) on the curvature operator itself, same probes and depth
+        from lip_b200 import matfree_monkeypatch
+        lz = matfree_monkeypatch.integrand_funm_sym_logdet(matfree.decomp.tridiag_sym(k))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        est_lz = _dist.slq_sharded(lz, cvp, slq_probes)
+        torch.cuda.synchronize()
+        dt_lz = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt_lz, op=dist.ReduceOp.MAX)
         sl = _dist.probe_slice(ns, rank, world)
         n_loc = max(sl.stop - sl.start, (ns + world - 1) // world)
         # algorithmic re-orthogonalisation traffic of the slowest rank: step i reads i rows of U (n = D + d) and i + 1
@@ -411,7 +424,12 @@ def run_b200(args):
             hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
         except Exception:
             pass
+        lz_bytes = n_loc * 4 * sum(2 * (i + 1) * D * 2 for i in range(k))      # CGS2: two passes over i + 1 rows of Q
         slq = {"seconds": secs, "k": k, "probes": ns, "probes_per_gpu": n_loc, "logdet_estimate": float(est.item()),
+               "lanczos_form": {"seconds": float(dt_lz.item()), "logdet_estimate_clip1": float(est_lz.item()),
+                                "form": "Lanczos tridiag_sym(k) on curvature_vp, full re-orthogonalisation (2 passes), "
+                                        "log(clip(eig, 1)) quadrature",
+                                "reorth_GBps": lz_bytes / float(dt_lz.item()) / 1e9},
                "form": "GKL bidiag on [sqrt(alpha) I; Wz^T], full re-orthogonalisation",
                "roofline": {"bound": "hbm", "achieved": reorth_bytes / secs / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": (reorth_bytes / secs / 1e9 / hbm) if hbm else None,

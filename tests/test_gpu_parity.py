@@ -622,3 +622,22 @@ def test_scalable_kl_objective_forward_matches_oracle(kind):
     got = float(train_inducing.alternative_objective_scalable(cu(Z), cu(X), lst, alpha, kind, 0, full_set_size=N, st_samples=40,
                                                               slq_samples=2, slq_num_matvecs=k, probes=cu(probes)))
     assert abs(got - ref) <= TOL_EST * abs(ref), (got, ref)
+
+
+def test_materialize_covariance_probes_an_operator():
+    """lla.py:160-217: diagonal / full matrix of a linear operator by unit-vector probing (float64 buffers)."""
+    from lip_b200 import lla
+    rng = np.random.default_rng(60)
+    N, out_dim = 5, 3
+    A = rng.standard_normal((N * out_dim, N * out_dim))
+    Cov = A @ A.T
+    Ct = torch.as_tensor(Cov, device="cuda", dtype=torch.float64)
+    f = lambda e: (Ct @ e.reshape(-1).double()).reshape(N, out_dim)
+    diag = lla.materialize_covariance(f, N, out_dim, mode="diag").cpu().numpy()
+    np.testing.assert_allclose(diag, np.diag(Cov).reshape(N, out_dim), rtol=1e-12)
+    full = lla.materialize_covariance(f, N, out_dim, mode="full").cpu().numpy()
+    np.testing.assert_allclose(full, Cov, rtol=1e-12)
+    ref_diag = O.materialize_covariance(lambda e: Cov @ np.asarray(e).reshape(-1), N, out_dim, mode="diag")
+    np.testing.assert_allclose(diag, np.asarray(ref_diag).reshape(N, out_dim), rtol=1e-12)
+    with pytest.raises(ValueError):
+        lla.materialize_covariance(f, N, out_dim, mode="banana")
