@@ -195,6 +195,21 @@ def cpu_reference_products_per_s(ost, Z, n_products, steps=1, warmup=0):
     return n_products * len(times) / total, cores, total / len(times)
 
 
+def reference_import_status():
+    """The unmodified reference (pip-installed from /root/reference into baseline/_ref) is pure Python on top
+    of JAX / flax / matfree.  Returns None when it can be imported, else the reason it cannot (then the oracle port runs)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        return "baseline/_ref/src missing (reference not installed in this tree)"
+    try:
+        import importlib
+        for mod in ("jax", "flax", "matfree"):
+            importlib.import_module(mod)
+    except Exception as e:          # noqa: BLE001
+        return f"{type(e).__name__}: {e}"
+    return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -203,7 +218,9 @@ def run_reference(args):
     # bounded sample: ONE product (all 512 points) per step so that --steps 10 --warmup 3 ends within minutes
     args.cpu_probes = 1
     pps, cores, sec = cpu_reference_products_per_s(ost, Z, args.cpu_probes, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-    sample = f"{args.cpu_probes} products (all {M_POINTS} points each) per step, torch fp32 restatement of src/ggn.py:133-144"
+    why = reference_import_status()
+    sample = (f"{args.cpu_probes} products (all {M_POINTS} points each) per step, torch fp32 restatement of src/ggn.py:133-144 "
+              f"(oracle port; the installed reference itself is not runnable here: {why})")
     line = {"impl": "reference", "metric": "ggn_vec_products_per_s", "value": pps, "unit": "products/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
