@@ -43,13 +43,37 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if not force and not needs_build():
                 return LIB
             tmp = LIB + f".tmp{os.getpid()}"
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
-                  [os.path.join(CSRC, s) for s in SOURCES]
-            res = subprocess.run(cmd, capture_output=True, text=True)
+            # one nvcc -c per source, in parallel (the two GEMM files dominate), then one link
+            from concurrent.futures import ThreadPoolExecutor
+            objdir = os.path.join(HERE, "build")
+            os.makedirs(objdir, exist_ok=True)
+            nvcc = _nvcc()
+            cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+            def compile_one(src):
+                obj = os.path.join(objdir, os.path.splitext(src)[0] + f".{os.getpid()}.o")
+                r = subprocess.run([nvcc] + cflags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+                return src, obj, r
+
+            with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+                results = list(pool.map(compile_one, SOURCES))
+            log = "".join(r.stderr for _, _, r in results)
+            failed = [(src, r) for src, _, r in results if r.returncode != 0]
+            if failed:
+                for _, obj, _ in results:
+                    if os.path.exists(obj):
+                        os.remove(obj)
+                raise RuntimeError("nvcc failed:\n" + "".join(r.stdout + r.stderr for _, r in failed))
+            objs = [obj for _, obj, _ in results]
+            res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs,
+                                 capture_output=True, text=True)
+            for obj in objs:
+                os.remove(obj)
+            res.stderr = log + res.stderr
             if res.returncode != 0:
                 if os.path.exists(tmp):
                     os.remove(tmp)
-                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+                raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
             os.replace(tmp, LIB)
             if verbose:
                 sys.stderr.write(res.stderr)

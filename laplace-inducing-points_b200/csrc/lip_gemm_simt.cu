@@ -94,6 +94,91 @@ __device__ __forceinline__ void load_tile(const DevOperand& op, long long zoff, 
   }
 }
 
+// Per-thread state of a gathered A tile (128 rows x BK, 8 elements per thread).  The decomposition of the part of the index that
+// does not change over the K loop is hoisted: in the k-contiguous layout (modes 1, 3) a thread's 8 elements sit in 8 fixed tile
+// rows and share one k, so the rows' image coordinates are computed once per tile and each k-tile costs a single
+// (dy, dx, channel) decomposition; in the m-contiguous layout (mode 2) the thread's patch column kc is fixed instead.
+template <bool KC>
+struct GatherTile {
+  int y0[8], x0[8];           // KC: per row  (mode 1: y*stride - pad, x*stride - pad;  mode 3: yi + pad, xi + pad)
+  int base[8];                // KC: per row image offset of (mz, 0, 0, 0) (< 2^31: one probe's image);  !KC: unused
+  int dy, dx, ch;             // !KC: the fixed patch column
+  bool rowok[8], kcok;
+
+  __device__ __forceinline__ void init(const ConvGather& c, int m0, int M) {
+    const int tid = threadIdx.x;
+    if (KC) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t gr = (uint32_t)(m0 + (tid + NT * i) / BK);
+        rowok[i] = (int)gr < M;
+        uint32_t t, x, y, mz;
+        if (c.mode == 3) {
+          c.dWi.divmod(gr, t, x);
+          c.dHi.divmod(t, mz, y);
+          y0[i] = (int)y + c.pad_h; x0[i] = (int)x + c.pad_w;
+          base[i] = (int)(mz * (uint32_t)(c.Ho * c.Wo * c.C));
+        } else {
+          c.dWo.divmod(gr, t, x);
+          c.dHo.divmod(t, mz, y);
+          y0[i] = (int)y * c.stride - c.pad_h; x0[i] = (int)x * c.stride - c.pad_w;
+          base[i] = (int)(mz * (uint32_t)(c.Hi * c.Wi * c.C));
+        }
+      }
+    } else {
+      const uint32_t kc = (uint32_t)(m0 + tid % BM);
+      kcok = (int)kc < M;
+      uint32_t t, c_, dx_, dy_;
+      c.dC.divmod(kc, t, c_);
+      c.dkw.divmod(t, dy_, dx_);
+      dy = (int)dy_; dx = (int)dx_; ch = (int)c_;
+    }
+  }
+
+  __device__ __forceinline__ void load(const DevOperand& op, long long zoff, int k0, int K, float (&reg)[8]) const {
+    const ConvGather& c = op.conv;
+    const int tid = threadIdx.x;
+    const float* p = op.ptr + zoff;
+    if (KC) {
+      const uint32_t gk = (uint32_t)(k0 + tid % BK);
+      uint32_t t, c_, dx_, dy_;
+      c.dC.divmod(gk, t, c_);
+      c.dkw.divmod(t, dy_, dx_);
+      const bool kok = (int)gk < K;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = 0.f;
+        if (kok && rowok[i]) {
+          if (c.mode == 3) {
+            int ys = y0[i] - (int)dy_, xs = x0[i] - (int)dx_;
+            bool ok = ys >= 0 && xs >= 0;
+            if (ok && c.stride != 1) { ok = (ys % c.stride == 0) && (xs % c.stride == 0); ys /= c.stride; xs /= c.stride; }
+            if (ok && ys < c.Ho && xs < c.Wo) v = __ldg(p + (base[i] + (ys * c.Wo + xs) * c.C + (int)c_));
+          } else {
+            const int yi = y0[i] + (int)dy_, xi = x0[i] + (int)dx_;
+            if (yi >= 0 && yi < c.Hi && xi >= 0 && xi < c.Wi) v = __ldg(p + (base[i] + (yi * c.Wi + xi) * c.C + (int)c_));
+          }
+        }
+        reg[i] = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t r = (uint32_t)(k0 + (tid + NT * i) / BM);
+        float v = 0.f;
+        if (kcok && (int)r < K) {
+          uint32_t t, x, y, mz;
+          c.dWo.divmod(r, t, x);
+          c.dHo.divmod(t, mz, y);
+          const int yi = (int)y * c.stride + dy - c.pad_h, xi = (int)x * c.stride + dx - c.pad_w;
+          if (yi >= 0 && yi < c.Hi && xi >= 0 && xi < c.Wi) v = __ldg(p + (((long long)mz * c.Hi + yi) * c.Wi + xi) * c.C + ch);
+        }
+        reg[i] = v;
+      }
+    }
+  }
+};
+
 template <bool KC, int ROWS>
 __device__ __forceinline__ void store_tile(float (*S)[ROWS + PAD], const float (&reg)[ROWS * BK / NT]) {
   const int tid = threadIdx.x;
@@ -137,7 +222,11 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
     const int kt0 = (int)((long long)nk_all * slice / ks), nk = (int)((long long)nk_all * (slice + 1) / ks);
     if (kt0 >= nk) continue;
     float ra[8], rb[BNT * BK / NT];
-    load_tile<A_KC, BM, GATHER>(A, za, m0, g.M, kt0 * BK, K, true, ra);
+    GatherTile<A_KC> gt;
+    const bool gathered = GATHER && A.conv.mode != 0;
+    if (gathered) gt.init(A.conv, m0, g.M);
+    if (gathered) gt.load(A, za, kt0 * BK, K, ra);
+    else load_tile<A_KC, BM, false>(A, za, m0, g.M, kt0 * BK, K, true, ra);
     load_tile<B_KC, BNT, false>(B, zb, n0, g.N, kt0 * BK, K, false, rb);
     store_tile<A_KC, BM>(As[kt0 & 1], ra);
     store_tile<B_KC, BNT>(Bs[kt0 & 1], rb);
@@ -145,7 +234,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(DevGemm g) {
     for (int kt = kt0; kt < nk; ++kt) {
       const int cur = kt & 1;
       if (kt + 1 < nk) {
-        load_tile<A_KC, BM, GATHER>(A, za, m0, g.M, (kt + 1) * BK, K, true, ra);
+        if (gathered) gt.load(A, za, (kt + 1) * BK, K, ra);
+        else load_tile<A_KC, BM, false>(A, za, m0, g.M, (kt + 1) * BK, K, true, ra);
         load_tile<B_KC, BNT, false>(B, zb, n0, g.N, (kt + 1) * BK, K, false, rb);
       }
 #pragma unroll

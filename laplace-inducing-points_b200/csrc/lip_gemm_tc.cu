@@ -1333,17 +1333,15 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
   LIP_REQUIRE(g.epi.act < 0 && g.epi.dphi_out == nullptr, "gemm_tc: activation epilogue is SIMT-only");
   const bool a_k = g.A1.major_k != 0, b_k = g.B1.major_k != 0;
   if (g.A2.hi) LIP_REQUIRE((g.A2.major_k != 0) == a_k && (g.B2.major_k != 0) == b_k, "gemm_tc: second pair must share majors");
-  // 2x2 clusters with TMA multicast halve the L2 reads per CTA; worth it once there are enough tiles per cluster
-  static const int force_cl = getenv("LIP_TC_CLUSTER") ? atoi(getenv("LIP_TC_CLUSTER")) : -1;
-  // (measured on B200: correct, but the lock-step coupling costs more than the L2 saving -> off by default)
-  const bool cl4 = force_cl == 4;
+  // (the kernel template also has a 2x2-cluster TMA-multicast mode, CL == 4: correct on B200 but the lock-step coupling cost more
+  // than the L2 saving, so it is not instantiated)
   // cta_group::2 policy: -1 (default) = CTA pairs for the JVP-type GEMMs (K-major A, MN-major B) whose M fills whole
   // 256-row pair tiles - measured faster there (profiles/r01_launches_*), slower for the short-K weight-gradient /
   // delta-backprop GEMMs; 0 = never; 1 = always (when M > 128)
   static const int two_cta = getenv("LIP_TC_2CTA") ? atoi(getenv("LIP_TC_2CTA")) : -1;
   static const bool verbose = getenv("LIP_TC_VERBOSE") != nullptr;
-  if (verbose) fprintf(stderr, "[lip] gemm_tc M=%lld N=%lld K=%lld K2=%lld batch=%lld a_k=%d b_k=%d two_cta=%d cl4=%d\n", (long long)g.M,
-                       (long long)g.N, (long long)g.K, (long long)g.K2, (long long)g.batch, (int)a_k, (int)b_k, two_cta, (int)cl4);
+  if (verbose) fprintf(stderr, "[lip] gemm_tc M=%lld N=%lld K=%lld K2=%lld batch=%lld a_k=%d b_k=%d two_cta=%d\n", (long long)g.M,
+                       (long long)g.N, (long long)g.K, (long long)g.K2, (long long)g.batch, (int)a_k, (int)b_k, two_cta);
   // Ragged M (e.g. the 784-row weight gradient of the first MNIST layer): run the rows that fill whole 256-row pair tiles
   // on the wide kernel and the remaining (< 256) rows as a second launch, instead of padding 784 -> 1024 or giving the whole
   // problem to the 128-wide kernel.
@@ -1397,15 +1395,9 @@ int gemm_tc(const TcGemmProblem& g, cudaStream_t st) {
     if (!a_k && !b_k) return launch_tc2<128, false, false>(g, st);
     if (a_k && b_k) return launch_tc2<128, true, true>(g, st);
   }
-  if (cl4) {
-    if (a_k && !b_k) return launch_tc<128, true, false, 4>(g, st);
-    if (!a_k && !b_k) return launch_tc<128, false, false, 4>(g, st);
-    if (a_k && b_k) return launch_tc<128, true, true, 4>(g, st);
-  } else {
-    if (a_k && !b_k) return launch_tc<128, true, false, 1>(g, st);
-    if (!a_k && !b_k) return launch_tc<128, false, false, 1>(g, st);
-    if (a_k && b_k) return launch_tc<128, true, true, 1>(g, st);
-  }
+  if (a_k && !b_k) return launch_tc<128, true, false, 1>(g, st);
+  if (!a_k && !b_k) return launch_tc<128, false, false, 1>(g, st);
+  if (a_k && b_k) return launch_tc<128, true, true, 1>(g, st);
   set_error("gemm_tc: unsupported operand majors (A MN-major with B K-major)");
   return LIP_ERR_INVALID;
 }
