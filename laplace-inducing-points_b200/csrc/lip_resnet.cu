@@ -92,20 +92,22 @@ __global__ void bn_vjp_kernel(const float* __restrict__ dout, const float* __res
   }
 }
 
-// one CTA per probe, blockDim.x a multiple of C: every thread sees one column of the flat [R * C] arrays
-//   gbeta[c] = sum_r Dout*mask,  gscale[c] = sum_r Dout*mask*xhat;  out = scale * sum + add_scale * add
-__global__ void bn_param_grad_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
-                                     const float* __restrict__ xhat, long long per_z, int C, float* __restrict__ out_beta,
-                                     float* __restrict__ out_scale, long long out_sz, float scale,
-                                     const float* __restrict__ add_beta, const float* __restrict__ add_scale_p, long long add_sz,
-                                     float add_scale) {
+// BatchNorm parameter gradients, two stages (deterministic, no atomics).  Stage 1: grid (chunks, probes), blockDim.x a multiple
+// of C so that every thread sees one column of the flat [R * C] arrays; each CTA reduces its slice of rows:
+//   part[b][chunk][0][c] = sum_r Dout*mask,   part[b][chunk][1][c] = sum_r Dout*mask*xhat
+__global__ void bn_param_grad_partial_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
+                                             const float* __restrict__ xhat, long long per_z, int C, float* __restrict__ part) {
   extern __shared__ float sm[];
   float* s1 = sm;
   float* s2 = sm + blockDim.x;
-  const long long b = blockIdx.x;
+  const long long b = blockIdx.y;
+  const int nch = gridDim.x;
   const float* d = dout + b * per_z;
+  // slices are multiples of blockDim.x (itself a multiple of C): the thread <-> column mapping is the same in every slice
+  const long long per_chunk = ((per_z + nch - 1) / nch + blockDim.x - 1) / blockDim.x * blockDim.x;
+  const long long lo = blockIdx.x * per_chunk, hi = lo + per_chunk < per_z ? lo + per_chunk : per_z;
   float a1 = 0.f, a2 = 0.f;
-  for (long long i = threadIdx.x; i < per_z; i += blockDim.x) {
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     float dy = __ldg(d + i);
     if (mask) dy *= __ldg(mask + i);
     a1 += dy;
@@ -116,11 +118,28 @@ __global__ void bn_param_grad_kernel(const float* __restrict__ dout, const float
   if ((int)threadIdx.x < C) {
     float t1 = 0.f, t2 = 0.f;
     for (int k = threadIdx.x; k < (int)blockDim.x; k += C) { t1 += s1[k]; t2 += s2[k]; }
-    float vb = scale * t1, vs = scale * t2;
-    if (add_beta) { vb += add_scale * add_beta[b * add_sz + threadIdx.x]; vs += add_scale * add_scale_p[b * add_sz + threadIdx.x]; }
-    out_beta[b * out_sz + threadIdx.x] = vb;
-    out_scale[b * out_sz + threadIdx.x] = vs;
+    float* p = part + ((b * nch + blockIdx.x) * 2) * C;
+    p[threadIdx.x] = t1;
+    p[C + threadIdx.x] = t2;
   }
+}
+// Stage 2: gbeta[b][c] / gscale[b][c] = scale * sum_chunk part + add_scale * add
+__global__ void bn_param_grad_reduce_kernel(const float* __restrict__ part, int nch, int C, float* __restrict__ out_beta,
+                                            float* __restrict__ out_scale, long long out_sz, float scale,
+                                            const float* __restrict__ add_beta, const float* __restrict__ add_scale_p,
+                                            long long add_sz, float add_scale) {
+  const long long b = blockIdx.x;
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  float t1 = 0.f, t2 = 0.f;
+  for (int k = 0; k < nch; ++k) {
+    const float* p = part + ((b * nch + k) * 2) * C;
+    t1 += p[c]; t2 += p[C + c];
+  }
+  float vb = scale * t1, vs = scale * t2;
+  if (add_beta) { vb += add_scale * add_beta[b * add_sz + c]; vs += add_scale * add_scale_p[b * add_sz + c]; }
+  out_beta[b * out_sz + c] = vb;
+  out_scale[b * out_sz + c] = vs;
 }
 
 // Wt[(tap*cout + co)*cin + ci] = W[(tap*cin + ci)*cout + co]
@@ -268,11 +287,19 @@ int rn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const RnWs& w, float*
     const int64_t R = m->M * u.P(), Kc = u.Kc();
     const long long per_z = R * (long long)u.cout, total = per_z * B;
     const float* dout = w.slot[u.dst];
-    {  // BatchNorm parameter gradients
+    {  // BatchNorm parameter gradients (partials land in the split-K scratch, which the kernel-gradient GEMM reuses afterwards)
       const int threads = u.cout * (512 / u.cout > 0 ? 512 / u.cout : 1);
-      bn_param_grad_kernel<<<(unsigned)B, threads, 2 * threads * sizeof(float), st>>>(
-          dout, u.mask, u.xhat, per_z, u.cout, out + u.beta_off, out + u.scale_off, m->D, scale,
-          add ? add + u.beta_off : nullptr, add ? add + u.scale_off : nullptr, m->D, add_scale);
+      int nch = (int)(per_z / (threads * 64));
+      if (nch > 64) nch = 64;
+      const long long cap = (long long)(col_elems / ((size_t)B * 2 * u.cout));
+      if (nch > cap) nch = (int)cap;
+      if (nch < 1) nch = 1;
+      dim3 grid((unsigned)nch, (unsigned)B);
+      bn_param_grad_partial_kernel<<<grid, threads, 2 * threads * sizeof(float), st>>>(dout, u.mask, u.xhat, per_z, u.cout, w.col);
+      LIP_LAUNCH_CHECK();
+      bn_param_grad_reduce_kernel<<<(unsigned)B, u.cout <= 32 ? 32 : (u.cout + 31) / 32 * 32, 0, st>>>(
+          w.col, nch, u.cout, out + u.beta_off, out + u.scale_off, m->D, scale, add ? add + u.beta_off : nullptr,
+          add ? add + u.scale_off : nullptr, m->D, add_scale);
       LIP_LAUNCH_CHECK();
     }
     // Dy -> skip cotangent (first contribution to that slot: plain store), Dh = g * Dy
