@@ -193,7 +193,7 @@ __device__ __forceinline__ void store_tile(float (*S)[ROWS + PAD], const float (
 
 // BNT: tile width (128, or 64 / 32 for narrow outputs such as 32- and 64-channel convs); NJ = BNT / 16 columns per thread
 template <bool A_KC, bool B_KC, int BNT, bool GATHER>
-__global__ void __launch_bounds__(NT, GATHER ? 2 : 1) gemm_simt_kernel(DevGemm g) {
+__global__ void __launch_bounds__(NT, 2) gemm_simt_kernel(DevGemm g) {
   constexpr int NJ = BNT / 16;
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BNT + PAD];
