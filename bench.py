@@ -301,34 +301,8 @@ def run_b200(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     ms_step = ms_total / args.steps
-    # the dominant kernel group on its own: ONE lip_ggn_vp call (all JVP / VJP GEMM launches) under CUDA events on the
-    # launching stream, same inputs, no quadratic form / all-reduce around it -> roofline.achieved
-    k0, k1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    torch.cuda.synchronize()
-    k0.record()
-    for _ in range(args.steps):
-        cvp(V)
-    k1.record()
-    torch.cuda.synchronize()
-    ms_ggn = torch.tensor([k0.elapsed_time(k1) / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_ggn, op=dist.ReduceOp.MAX)
-    ms_ggn = float(ms_ggn.item())
     value = B * world * args.steps / (ms_total * 1e-3)
     trace_est = float(acc.item()) / (B * world * (args.steps + args.warmup))
-    # the same call on GENERAL (Gaussian) vectors - CG / Lanczos iterates are not exactly TF32, so the zero-lo shortcut
-    # that +-1 probes enjoy does not apply: reported beside the headline
-    Vg = torch.randn(B, D, device=dev)
-    cvp(Vg)
-    torch.cuda.synchronize()
-    k0.record()
-    for _ in range(args.steps):
-        cvp(Vg)
-    k1.record()
-    torch.cuda.synchronize()
-    ms_gauss = k0.elapsed_time(k1) / args.steps
-    del Vg
-
     # ---- end to end through the public API with HOST probes, copies inside the timed region ----
     # Rademacher probes live in pinned host memory in their packed wire format (1 bit / element, numpy.packbits); every step
     # copies its probes H2D, unpacks them on the device (lip_unpack_rademacher), runs the public
@@ -382,6 +356,32 @@ def run_b200(args):
                "h2d_bytes_per_step": B * nbytes_row, "d2h_bytes_per_step": B * 4,
                "note": "pinned bit-packed +-1 probes -> H2D -> lip_unpack_rademacher -> lla.compute_curvature_approx(...)(V) -> "
                        "v.(Gv) -> pinned host; H2D double-buffered, D2H pipelined two steps deep"}
+
+    # the dominant kernel group on its own: ONE lip_ggn_vp call (all JVP / VJP GEMM launches) under CUDA events on the
+    # launching stream, same inputs, no quadratic form / all-reduce around it -> roofline.achieved
+    k0, k1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        cvp(V)
+    k1.record()
+    torch.cuda.synchronize()
+    ms_ggn = torch.tensor([k0.elapsed_time(k1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_ggn, op=dist.ReduceOp.MAX)
+    ms_ggn = float(ms_ggn.item())
+    # the same call on GENERAL (Gaussian) vectors - CG / Lanczos iterates are not exactly TF32, so the zero-lo shortcut
+    # that +-1 probes enjoy does not apply: reported beside the headline
+    Vg = torch.randn(B, D, device=dev)
+    cvp(Vg)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        cvp(Vg)
+    k1.record()
+    torch.cuda.synchronize()
+    ms_gauss = k0.elapsed_time(k1) / args.steps
+    del Vg
 
     # ---- SLQ logdet (GKL form, src/train_inducing.py:148-171), probes sharded over ranks ----
     slq = None

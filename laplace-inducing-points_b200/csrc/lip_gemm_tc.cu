@@ -10,12 +10,17 @@
 //   JVP    : A K-major  (activations [M,K]),  B MN-major (tangent weights [K,N])      (+ a second A/B pair)
 //   WGRAD  : A MN-major (activations^T),      B MN-major (deltas [K,N])
 //   DGRAD  : A K-major  (deltas [M,K]),       B K-major  (weights [N,K])
-// Persistent CTAs (one per SM) walk a static tile schedule.  Warp roles (256 threads): warp0 = TMA producer,
-// warp1 = MMA issuer, warp2 = TMEM allocator, warps4-7 = accumulator drain + epilogue.  The K loop is cut into
-// chunks of KC k-blocks; chunks alternate between two TMEM buffers, and the drain warps add each finished chunk
-// into fp32 REGISTER accumulators (round-to-nearest) while the tensor core works on the next chunk / next tile.
+// Three kernels share the PTX wrappers, the tile epilogue and the host-side tensor-map code:
+//   gemm_tc_kernel   128 x 128 tiles, one CTA per SM                         (ragged tails, small problems)
+//   gemm_tc2_kernel  256 x 128 tiles on CTA pairs (cta_group::2)             (JVP GEMMs with N = 128)
+//   gemm_tc2w_kernel 256 x 256 tiles on CTA pairs, setmaxnreg re-balancing    (everything that fills them; see its header)
+// Persistent CTAs walk a static tile schedule.  Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4-11 = accumulator drain + epilogue.  fp32 accumulation in TMEM truncates, so the K loop is
+// cut into chunks of KC k-blocks whose TMEM accumulators the drain warps fold, round-to-nearest, into fp32 REGISTER
+// accumulators (two alternating TMEM buffers in the 128-wide kernels); the cross terms have their own TMEM tile.
 // The tile epilogue transposes through shared memory so that mask/add reads and the stores are 128-byte coalesced.
 // All mbarrier waits are bounded: a deadlock traps instead of hanging the GPU.
+// LIP_TC_KC / LIP_TC_MERGE are experiment knobs (tools/tc_accuracy_exp.py -> profiles/r01_tc_accuracy*.txt).
 #include <cuda.h>
 
 #include <mutex>
