@@ -63,6 +63,8 @@ SIGNATURES = {
     "lip_bidiag_to_tridiag": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
     "lip_bench_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, _I32, _I32, _I32, C.POINTER(_F), _P]),
     "lip_selftest_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, C.POINTER(_F), _P]),
+    "lip_selftest_conv_tc": (C.c_int, [_I32, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I64, _I32, C.POINTER(_F), C.POINTER(_F),
+                                       C.POINTER(_F), _P]),
 }
 
 _lib = None

@@ -277,9 +277,15 @@ class BoundModel:
         self._ws = Scratch()
         self.launches = 0
 
+    def tensor_layers(self) -> int:
+        """Number of layers / conv units whose GEMMs run on the tcgen05 path (0 = everything on the fp32 SIMT kernels)."""
+        return int(cabi.lib().lip_model_tensor_layers(self._h))
+
     def path_name(self) -> str:
         n = cabi.lib().lip_model_tensor_layers(self._h)
         total = len(self.spec.layers)
+        if isinstance(self.spec, ResNetProgramSpec) and n:
+            return f"implicit-GEMM conv: tcgen05-3xtf32 ({n} conv units) + simt-fp32 ({total} conv/dense stages in all)"
         if isinstance(self.spec, (ConvProgramSpec, ResNetProgramSpec)):
             return f"im2col + simt-fp32 ({total} conv/dense stages)"
         return f"tcgen05-3xtf32 ({n}/{total} layers) + simt-fp32" if n else "simt-fp32"

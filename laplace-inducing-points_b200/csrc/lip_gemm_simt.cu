@@ -474,8 +474,8 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
   const int bnt = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : BN);       // narrow tiles for 32- / 64-wide outputs
   const int64_t tiles = skinny ? ceil_div(p.M, SB_M) : ceil_div(p.N, bnt) * ceil_div(p.M, BM);
   const int64_t kstep = skinny ? SB_K : BK;
-  if (p.splitk_ws && !p.A2.ptr && p.batch <= 65535 && tiles * p.batch < 2 * 148 && p.K >= 64 * kstep) {
-    int64_t S = ceil_div(4 * 148, tiles * p.batch);
+  if (p.splitk_ws && !p.A2.ptr && p.batch <= 65535 && tiles * p.batch < 16 * 148 && p.K >= 64 * kstep) {
+    int64_t S = ceil_div(32 * 148, tiles * p.batch);       // enough CTAs in flight to hide the latency of the long K stream
     const int64_t smax_k = p.K / (8 * kstep);                       // at least 8 k-tiles per slice
     const int64_t smax_ws = p.splitk_ws_elems / (p.batch * p.M * p.N);
     if (S > smax_k) S = smax_k;

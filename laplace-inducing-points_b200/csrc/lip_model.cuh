@@ -38,6 +38,9 @@ struct ConvBN {
   float* xhat = nullptr;   // [M*Ho*Wo, cout]
   float* mask = nullptr;   // [M*Ho*Wo, cout] relu' of the unit's pre-activation (null without relu)
   float* g = nullptr;      // [cout] scale * rsqrt(var + eps)
+  // tcgen05 implicit-GEMM path (lip_conv_tc.cu): TF32 (hi, lo) splits of the cached image and of the two kernel layouts
+  bool tc = false;
+  float *Xh = nullptr, *Xl = nullptr, *Wh = nullptr, *Wl = nullptr, *Wth = nullptr, *Wtl = nullptr;
   int64_t P() const { return (int64_t)Ho * Wo; }
   int64_t Kc() const { return (int64_t)kh * kw * cin; }
   // gather descriptors (lip_common.cuh: ConvGather) of this conv for the three GEMM roles

@@ -7,14 +7,17 @@
 //   JVP  unit:  dY[b] = mask * ( g * (patches(X) . dW[b] + patches(T_src[b]) . W) + xhat * dscale[b] + dbeta[b] + T_skip[b] )
 //   VJP  unit:  Dy = Dout * mask;  gbeta = colsum Dy;  gscale = colsum (Dy * xhat);  cot[skip] (+)= Dy;  Dh = g * Dy;
 //               gW[b] = patches(X)^T . Dh[b];  cot[src] (+)= transposed_conv(Dh[b], W)
-// Convs run as IMPLICIT GEMMs on the fp32 SIMT kernels: the A operand gathers its im2col patches straight from the NHWC
-// image (ConvGather in lip_common.cuh) - the cached input activation, the probe's tangent image, or (transposed conv) the
-// delta - so no patch buffer, im2col or col2im pass exists and memory stays O(activations).
+// Convs run as IMPLICIT GEMMs: the A operand gathers its im2col patches straight from the NHWC image - the cached input
+// activation, the probe's tangent image, or (transposed conv) the delta - so no patch buffer, im2col or col2im pass exists and
+// memory stays O(activations).  Stride-1 convs with >= 32 channels run on the tensor cores (tcgen05 3xTF32, TMA box loads
+// from the image, lip_conv_tc.cu); the 3-channel stem and the strided convs on the fp32 SIMT kernels (ConvGather in
+// lip_common.cuh).
 // Tangents / cotangents live in four rotating [B, M, H, W, C] slots (block input, branch, shortcut, block output).
 #include <new>
 #include <vector>
 
 #include "lip_model.cuh"
+#include "lip_conv_tc.cuh"
 
 using namespace lip;
 
@@ -25,7 +28,10 @@ void lip_model::free_resnet_cache() {
     if (u.xhat) cudaFree(u.xhat);
     if (u.mask) cudaFree(u.mask);
     if (u.g) cudaFree(u.g);
+    for (float* q : {u.Xh, u.Xl, u.Wh, u.Wl, u.Wth, u.Wtl}) if (q) cudaFree(q);
     u.Xin = u.Wt = u.xhat = u.mask = u.g = nullptr;
+    u.Xh = u.Xl = u.Wh = u.Wl = u.Wth = u.Wtl = nullptr;
+    u.tc = false;
   }
   if (rn_mean_act) cudaFree(rn_mean_act);
   rn_mean_act = nullptr;
@@ -80,15 +86,22 @@ __global__ void bn_jvp_kernel(const float* __restrict__ dH, const float* __restr
 
 // Dy = Dout * mask;  cot_skip (+)= Dy;  Dh = g[c] * Dy
 __global__ void bn_vjp_kernel(const float* __restrict__ dout, const float* __restrict__ mask, const float* __restrict__ g,
-                              float* __restrict__ dh, float* cot_skip, int skip_accumulate, long long total, long long per_z,
-                              int C) {
+                              float* __restrict__ dh, float* __restrict__ dh_lo, float* cot_skip, int skip_accumulate,
+                              long long total, long long per_z, int C) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long i = idx % per_z;
     const int c = (int)(i % C);
     float dy = dout[idx];
     if (mask) dy *= __ldg(mask + i);
     if (cot_skip) cot_skip[idx] = skip_accumulate ? cot_skip[idx] + dy : dy;
-    dh[idx] = g[c] * dy;
+    const float v = g[c] * dy;
+    if (dh_lo) {               // TF32 (hi, lo) pair for the tcgen05 conv GEMMs
+      const float hh = tf32_round(v);
+      dh[idx] = hh;
+      dh_lo[idx] = tf32_round(v - hh);
+    } else {
+      dh[idx] = v;
+    }
   }
 }
 
@@ -175,23 +188,42 @@ __global__ void global_mean_bwd_kernel(const float* __restrict__ g, float* __res
 struct RnWs {
   float* slot[4];   // tangent / cotangent tensors [B, M, slot_elems]
   float* raw;       // conv GEMM output dH / Dh, [B, max R*cout]
+  float* raw_lo;    // tensor path: TF32 lo part of Dh (raw then holds the hi part)
+  float* img_h;     // tensor path: TF32 (hi, lo) split of the tangent image a conv reads, [B, M, slot_elems] each
+  float* img_l;
+  float* vh;        // tensor path: TF32 (hi, lo) split of one unit's tangent kernels, [B, max Kc*cout] each
+  float* vl;
   float* col;       // split-K scratch of the per-probe kernel-gradient GEMMs
   float* head;      // [B, M, C_last] mean tangent / cotangent  +  [B, M, K] delta at the logits
   float* dl;
 };
-struct RnSizes { size_t slot, raw, col, head, dl; };
+struct RnSizes { size_t slot, raw, col, head, dl, raw_lo, img, vsplit; };
 
 RnSizes rn_sizes(const lip_model* m, int64_t B) {
   RnSizes z{};
   z.slot = align_up((size_t)B * m->M * (size_t)m->rn_slot_elems, 64);
-  size_t raw = 0, col = 0;
+  size_t raw = 0, col = 0, vs = 0, img = (size_t)B * m->M * (size_t)m->rn_slot_elems;
+  bool any_tc = false;
   for (const ConvBN& u : m->RB) {
     const size_t r = (size_t)B * m->M * u.P() * u.cout;
     raw = r > raw ? r : raw;
-    const size_t c = (size_t)B * u.Kc() * u.cout * 8;        // up to 8 K-slices of every probe's [Kc x cout] gradient
+    size_t slices = 8;                                       // up to 8 K-slices of every probe's [Kc x cout] gradient (SIMT)
+    if (u.tc) {
+      any_tc = true;
+      const size_t s = (size_t)conv_wgrad_tc_splits(m->M, u.Ho, u.Wo, u.cin, u.cout, u.kh, u.kw, B);
+      slices = s > slices ? s : slices;
+      const size_t v = (size_t)B * u.Kc() * u.cout;
+      vs = v > vs ? v : vs;
+      // a strided unit back-propagates through the zero-upsampled delta image [B, M, Hi, Wi, cout]
+      if (u.stride == 2) { const size_t e = (size_t)B * m->M * u.Hi * u.Wi * u.cout; img = e > img ? e : img; }
+    }
+    const size_t c = (size_t)B * u.Kc() * u.cout * slices;
     col = c > col ? c : col;
   }
   z.raw = align_up(raw, 64); z.col = align_up(col, 64);
+  z.raw_lo = any_tc ? z.raw : 0;
+  z.img = any_tc ? align_up(img, 64) : 0;
+  z.vsplit = align_up(vs, 64);
   z.head = align_up((size_t)B * m->M * m->rn_C, 64);
   z.dl = align_up((size_t)B * m->M * m->K, 64);
   return z;
@@ -209,26 +241,52 @@ int rn_carve(const lip_model* m, int64_t B, void* ws, size_t bytes, RnWs* w) {
   w->raw = p; p += z.raw;
   w->col = p; p += z.col;
   w->head = p; p += z.head;
-  w->dl = p;
+  w->dl = p; p += z.dl;
+  w->raw_lo = p; p += z.raw_lo;
+  w->img_h = p; p += z.img;
+  w->img_l = p; p += z.img;
+  w->vh = p; p += z.vsplit;
+  w->vl = p;
   return LIP_OK;
 }
 
 // ---- JVP sweep: V[B, D] -> dlogits [B, M, K] in dst --------------------------------------------------------------------
 int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* dst, cudaStream_t st) {
+  if (m->lo_nz) LIP_CHECK_CUDA(cudaMemsetAsync(m->lo_nz, 0, sizeof(int) * m->RB.size(), st));
   for (const ConvBN& u : m->RB) {
     const int64_t R = m->M * u.P(), Kc = u.Kc();
-    GemmProblem p;
-    p.M = R; p.N = u.cout; p.K = Kc; p.batch = B;
-    p.A1.ptr = u.Xin; p.A1.sz = 0; p.A1.conv = u.gather(1);                    // patches of the cached activation
-    p.B1 = {V + u.woff, m->D, u.cout, 1};
-    if (u.src != -2) {
-      p.A2.ptr = w.slot[u.src]; p.A2.sz = m->M * (int64_t)u.Hi * u.Wi * u.cin;  // patches of the probe's tangent image
-      p.A2.conv = u.gather(1);
-      p.B2 = {m->theta + u.woff, 0, u.cout, 1};
-      p.K2 = Kc;
+    int rc;
+    if (u.tc) {
+      // tensor path: split the probe's tangent kernels and tangent image into TF32 (hi, lo), then one dual-K implicit GEMM
+      const int64_t img_elems = m->M * (int64_t)u.Hi * u.Wi * u.cin;
+      int* nz = m->lo_nz + (&u - m->RB.data());
+      rc = tf32_split3(V + u.woff, m->D, Kc * u.cout, w.vh, w.vl, Kc * u.cout, Kc * u.cout, B, 1, Kc * u.cout, st, nz);
+      if (rc) return rc;
+      rc = tf32_split3(w.slot[u.src], 0, B * img_elems, w.img_h, w.img_l, 0, B * img_elems, 1, 1, B * img_elems, st);
+      if (rc) return rc;
+      ConvTcProblem c;
+      c.imgs = m->M; c.batch = B; c.H = u.Hi; c.W = u.Wi; c.C = u.cin; c.N = u.cout; c.kh = u.kh; c.kw = u.kw; c.pad = u.pad_h;
+      c.stride = u.stride;
+      c.A1.hi = u.Xh; c.A1.lo = u.Xl; c.A1.batched = 0;
+      c.B1.hi = w.vh; c.B1.lo = w.vl; c.B1.sz = Kc * u.cout; c.B1.ld = u.cout; c.B1.major_k = 0; c.B1.lo_nz = nz; c.b1_batched = 1;
+      c.A2.hi = w.img_h; c.A2.lo = w.img_l; c.A2.batched = 1;
+      c.B2.hi = u.Wh; c.B2.lo = u.Wl; c.B2.sz = 0; c.B2.ld = u.cout; c.B2.major_k = 0; c.b2_batched = 0;
+      c.C_out = w.raw; c.c_sz = R * (int64_t)u.cout; c.c_sm = u.cout;
+      rc = conv_tc(c, st);
+    } else {
+      GemmProblem p;
+      p.M = R; p.N = u.cout; p.K = Kc; p.batch = B;
+      p.A1.ptr = u.Xin; p.A1.sz = 0; p.A1.conv = u.gather(1);                    // patches of the cached activation
+      p.B1 = {V + u.woff, m->D, u.cout, 1};
+      if (u.src != -2) {
+        p.A2.ptr = w.slot[u.src]; p.A2.sz = m->M * (int64_t)u.Hi * u.Wi * u.cin;  // patches of the probe's tangent image
+        p.A2.conv = u.gather(1);
+        p.B2 = {m->theta + u.woff, 0, u.cout, 1};
+        p.K2 = Kc;
+      }
+      p.C = w.raw; p.c_sz = R * (int64_t)u.cout; p.c_sm = u.cout;
+      rc = gemm_simt(p, st);
     }
-    p.C = w.raw; p.c_sz = R * (int64_t)u.cout; p.c_sm = u.cout;
-    int rc = gemm_simt(p, st);
     if (rc) return rc;
     const long long per_z = R * (long long)u.cout, total = per_z * B;
     bn_jvp_kernel<<<ew_grid(total), 256, 0, st>>>(w.raw, u.g, u.xhat, u.mask, V + u.scale_off, V + u.beta_off, m->D,
@@ -303,9 +361,37 @@ int rn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const RnWs& w, float*
       LIP_LAUNCH_CHECK();
     }
     // Dy -> skip cotangent (first contribution to that slot: plain store), Dh = g * Dy
-    bn_vjp_kernel<<<ew_grid(total), 256, 0, st>>>(dout, u.mask, u.g, w.raw, u.skip >= 0 ? w.slot[u.skip] : nullptr, 0, total,
-                                                  per_z, u.cout);
+    bn_vjp_kernel<<<ew_grid(total), 256, 0, st>>>(dout, u.mask, u.g, w.raw, u.tc ? w.raw_lo : nullptr,
+                                                  u.skip >= 0 ? w.slot[u.skip] : nullptr, 0, total, per_z, u.cout);
     LIP_LAUNCH_CHECK();
+    if (u.tc) {
+      ConvWgradTcProblem c;   // kernel gradient [Kc x cout] = patches(X)^T . Dh on the tensor cores (split-K)
+      c.imgs = m->M; c.batch = B; c.H = u.Hi; c.W = u.Wi; c.C = u.cin; c.N = u.cout; c.kh = u.kh; c.kw = u.kw; c.pad = u.pad_h;
+      c.stride = u.stride;
+      c.X_hi = u.Xh; c.X_lo = u.Xl;
+      c.D.hi = w.raw; c.D.lo = w.raw_lo; c.D.sz = per_z; c.D.ld = u.cout; c.D.major_k = 0;
+      c.C_out = out + u.woff; c.c_sz = m->D; c.c_sm = u.cout;
+      c.epi.scale = scale;
+      if (add) { c.epi.add = add + u.woff; c.epi.add_sz = m->D; c.epi.add_scale = add_scale; }
+      c.ws = w.col; c.ws_elems = (int64_t)col_elems;
+      int rc = conv_wgrad_tc(c, st);
+      if (rc) return rc;
+      ConvTcProblem q;        // cotangent of the input image = transposed conv of Dh (zero-upsampled first for a strided unit)
+      q.imgs = m->M; q.batch = B; q.H = u.Hi; q.W = u.Wi; q.C = u.cout; q.N = u.cin; q.kh = u.kh; q.kw = u.kw; q.pad = u.pad_h;
+      q.transposed = 1;
+      q.A1.hi = w.raw; q.A1.lo = w.raw_lo; q.A1.batched = 1;
+      if (u.stride == 2) {
+        rc = conv_tc_upsample2(w.raw, w.raw_lo, w.img_h, w.img_l, B * m->M, u.Ho, u.Wo, u.cout, st);
+        if (rc) return rc;
+        q.A1.hi = w.img_h; q.A1.lo = w.img_l;
+      }
+      q.B1.hi = u.Wth; q.B1.lo = u.Wtl; q.B1.sz = 0; q.B1.ld = u.cin; q.B1.major_k = 0; q.b1_batched = 0;
+      q.C_out = w.slot[u.src]; q.c_sz = m->M * (int64_t)u.Hi * u.Wi * u.cin; q.c_sm = u.cin;
+      if (u.accumulate) { q.epi.add = q.C_out; q.epi.add_sz = q.c_sz; q.epi.add_scale = 1.f; }
+      rc = conv_tc(q, st);
+      if (rc) return rc;
+      continue;
+    }
     {  // kernel gradient [Kc x cout] = patches(X)^T . Dh
       GemmProblem p;
       p.M = Kc; p.N = u.cout; p.K = R; p.batch = B;
@@ -455,6 +541,11 @@ int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cud
     cleanup(); set_error("lip_model_bind: out of device memory"); return LIP_ERR_CUDA;
   }
   int rc = LIP_OK;
+  bool any_tc = false;
+  if (m->use_tc == 1 && !tc_available()) {
+    cleanup(); set_error("lip_model_bind: tensor path requested but the device is not sm_100 / TMA encode unavailable");
+    return LIP_ERR_UNSUPPORTED;
+  }
   for (ConvBN& u : m->RB) {
     const int64_t R = M * u.P(), Kc = u.Kc();
     const size_t xin_elems = (size_t)M * u.Hi * u.Wi * u.cin;
@@ -471,6 +562,22 @@ int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cud
     }
     conv_wt_kernel<<<(unsigned)ceil_div(Kc * u.cout, 256), 256, 0, st>>>(theta + u.woff, u.Wt, u.kh * u.kw, u.cin, u.cout);
     count_launch();
+    u.tc = m->use_tc != 0 && u.src != -2 && u.pad_h == u.pad_w &&
+           conv_tc_supported(u.Hi, u.Wi, u.cin, u.cout, u.kh, u.kw, u.stride, u.pad_h);
+    if (u.tc) {   // TF32 (hi, lo) splits of the cached image and of both kernel layouts
+      const size_t wk = (size_t)Kc * u.cout;
+      if (cudaMalloc(&u.Xh, sizeof(float) * xin_elems + 256) != cudaSuccess ||
+          cudaMalloc(&u.Xl, sizeof(float) * xin_elems + 256) != cudaSuccess ||
+          cudaMalloc(&u.Wh, sizeof(float) * wk + 256) != cudaSuccess || cudaMalloc(&u.Wl, sizeof(float) * wk + 256) != cudaSuccess ||
+          cudaMalloc(&u.Wth, sizeof(float) * wk + 256) != cudaSuccess || cudaMalloc(&u.Wtl, sizeof(float) * wk + 256) != cudaSuccess) {
+        cleanup(); set_error("lip_model_bind: out of device memory (tensor-path conv cache)"); return LIP_ERR_CUDA;
+      }
+      rc = tf32_split(u.Xin, (int64_t)xin_elems, u.Xh, u.Xl, (int64_t)xin_elems, 1, (int64_t)xin_elems, st);
+      if (!rc) rc = tf32_split(theta + u.woff, (int64_t)wk, u.Wh, u.Wl, (int64_t)wk, 1, (int64_t)wk, st);
+      if (!rc) rc = tf32_split(u.Wt, (int64_t)wk, u.Wth, u.Wtl, (int64_t)wk, 1, (int64_t)wk, st);
+      if (rc) break;
+      any_tc = true;
+    }
     GemmProblem p;
     p.M = R; p.N = u.cout; p.K = Kc; p.batch = 1;
     p.A1.ptr = u.Xin; p.A1.sz = 0; p.A1.conv = u.gather(1);
@@ -509,14 +616,19 @@ int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cud
   cudaStreamSynchronize(st);
   cleanup();
   if (rc) return rc;
-  m->tc_on = false;
+  if (any_tc && !m->lo_nz && cudaMalloc(&m->lo_nz, sizeof(int) * m->RB.size()) != cudaSuccess) {
+    set_error("lip_model_bind: out of device memory (flags)"); return LIP_ERR_CUDA;
+  }
+  m->tc_on = any_tc;
+  m->tc_layer.assign(m->RB.size(), 0);
+  for (size_t i = 0; i < m->RB.size(); ++i) m->tc_layer[i] = m->RB[i].tc ? 1 : 0;
   m->bound = true;
   return LIP_OK;
 }
 
 size_t resnet_ws_bytes(const lip_model* m, int64_t B) {
   const RnSizes z = rn_sizes(m, B);
-  return (4 * z.slot + z.raw + z.col + z.head + z.dl) * sizeof(float) + 512;
+  return (4 * z.slot + z.raw + z.col + z.head + z.dl + z.raw_lo + 2 * z.img + 2 * z.vsplit) * sizeof(float) + 512;
 }
 
 int resnet_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* ws, size_t bytes,

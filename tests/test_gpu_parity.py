@@ -453,6 +453,7 @@ def test_resnet1m_operators_match_oracle():
     D = ost.flat()[0].size
     assert D == 1084586
     bm = ggn._bind(lst, cu(Z), "classifier")
+    assert bm.tensor_layers() == 20          # every conv unit but the 3-channel stem runs on the tcgen05 implicit GEMM
     assert rel_err(bm.outputs().cpu().numpy(), O.model_outputs(ost, Z)) < 5e-6
     V = rng.choice([-1.0, 1.0], size=(2, D)).astype(np.float32)
     V[1] = rng.standard_normal(D).astype(np.float32)
@@ -471,6 +472,55 @@ def test_resnet1m_operators_match_oracle():
     U = rng.standard_normal(ref_wt.shape).astype(np.float32)
     ref_w = np.stack([Wo(u) for u in U.astype(np.float64)])
     assert rel_err(Wg(cu(U)).cpu().numpy(), ref_w) < TOL_GGN
+
+
+def test_resnet1m_tensor_core_convs_match_simt_and_oracle():
+    """The convs with >= 32 channels (stride 1 and 2) run as tcgen05 implicit GEMMs (lip_conv_tc.cu): same operators as the fp32
+    SIMT implicit GEMM (tensor_path=False), on a point count that leaves ragged 128-pixel tiles (M = 3 at 8x8 = 1.5 tiles) and
+    with Gaussian as well as exactly-TF32 (Rademacher) probes.  Both paths share the bind-time fp32 forward pass, hence the
+    ReLU masks; the float64-oracle parity of the tensor path is test_resnet1m_operators_match_oracle (a piecewise-linear
+    network at a seed where no pre-activation sits within fp32 rounding of a ReLU kink; at this test's seed one does, and
+    the oracle itself moves by 7e-5 under a 1e-7 perturbation of the inputs)."""
+    from lip_b200 import ggn
+    ost, lst = make_pair("resnet1m", n_out=10, seed=45, in_shape=(32, 32, 3))
+    rng = np.random.default_rng(46)
+    M, N = 3, 49000
+    Z = rng.random((M, 32, 32, 3)).astype(np.float32)
+    D = ost.flat()[0].size
+    V = rng.choice([-1.0, 1.0], size=(3, D)).astype(np.float32)
+    V[1] = rng.standard_normal(D).astype(np.float32)
+    V[2, : D // 2] = 0.0
+    tc = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=N, tensor_path=True)
+    assert tc._lip_model.tensor_layers() >= 14, tc._lip_model.path_name()
+    simt = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=N, tensor_path=False)
+    assert simt._lip_model.tensor_layers() == 0
+    got_tc, got_simt = tc(cu(V)).cpu().numpy(), simt(cu(V)).cpu().numpy()
+    for b in range(3):
+        assert rel_err(got_tc[b], got_simt[b]) < TOL_GGN, b
+    Wg, WTg = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=N, tensor_path=True)
+    Ws, WTs = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=N, tensor_path=False)
+    wt = WTg(cu(V))
+    assert rel_err(wt.cpu().numpy(), WTs(cu(V)).cpu().numpy()) < TOL_GGN
+    U = rng.standard_normal(tuple(wt.shape)).astype(np.float32)
+    w_tc = Wg(cu(U)).cpu().numpy()
+    assert rel_err(w_tc, Ws(cu(U)).cpu().numpy()) < TOL_GGN
+
+
+def test_conv_tensor_core_selftest():
+    """lip_selftest_conv_tc: the three tcgen05 implicit-GEMM conv roles against the SIMT implicit GEMM on random data."""
+    import ctypes as C
+    from lip_b200 import _cabi
+    L = _cabi.lib()
+    # (images, H, W, cin, cout, kernel size, stride, probes)
+    shapes = [(4, 32, 32, 32, 32, 3, 1, 2), (3, 16, 16, 64, 64, 3, 1, 2), (5, 8, 8, 128, 128, 3, 1, 3), (4, 16, 16, 32, 64, 1, 1, 2),
+              (2, 32, 32, 64, 32, 3, 1, 1), (7, 8, 8, 32, 32, 3, 1, 2), (40, 16, 16, 64, 64, 3, 1, 4),
+              (3, 32, 32, 32, 64, 3, 2, 2), (5, 16, 16, 64, 128, 3, 2, 2), (3, 32, 32, 32, 64, 1, 2, 2), (5, 16, 16, 64, 128, 1, 2, 3)]
+    for role in (0, 1, 2):
+        for (n, H, W, ci, co, k, sd, b) in shapes:
+            err, t1, t2 = C.c_float(-1), C.c_float(0), C.c_float(0)
+            _cabi.check(L.lip_selftest_conv_tc(role, n, H, W, ci, co, k, sd, b, 0, C.byref(err), C.byref(t1), C.byref(t2), None),
+                        "conv selftest")
+            assert err.value < 5e-6, (role, n, H, W, ci, co, k, sd, b, err.value)
 
 
 def test_resnet1m_grayscale_inputs_are_tiled():
