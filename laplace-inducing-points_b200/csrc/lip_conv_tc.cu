@@ -47,6 +47,64 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// Fused BatchNorm-JVP epilogue (ConvBnEpilogue in lip_conv_tc.cuh); same staging / coalescing scheme as tile_epilogue.
+template <int NBLK, int RB>
+__device__ __forceinline__ void bn_tile_epilogue(const TcParams& p, const ConvBnEpilogue& e, float (&acc)[32 * NBLK], float* stg,
+                                                 int m0, int n0, int z, int q, int h, int lane) {
+  const int mrow0 = m0 + q * 32;
+  int nrows = p.M - mrow0;
+  nrows = nrows > 32 ? 32 : nrows;
+  const long long i0 = (long long)mrow0 * p.c_sm;              // offset inside one batch entry
+  const long long zc = (long long)z * p.c_sz + i0;
+#pragma unroll
+  for (int cc = 0; cc < NBLK; ++cc) {
+    const int n = n0 + h * (32 * NBLK) + cc * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = acc[cc * 32 + i];
+    __syncwarp();
+    if (n < p.N && nrows > 0) {
+      const float gv = __ldg(e.g + n);
+      const float ds = __ldg(e.dscale + (long long)z * e.pstride + n), db = __ldg(e.dbeta + (long long)z * e.pstride + n);
+      const float* xp = e.xhat + i0 + n;
+      const float* mp = e.mask ? e.mask + i0 + n : nullptr;
+      const float* sh = e.skip_hi ? e.skip_hi + zc + n : nullptr;
+      const float* sl = e.skip_hi ? e.skip_lo + zc + n : nullptr;
+      float* ch = p.C + zc + n;
+      float* cl = p.C_lo + zc + n;
+      const float* sp = stg + lane;
+      const long long cs = p.c_sm;
+      int r0 = 0;
+      for (; r0 + RB <= nrows; r0 += RB) {
+        float xv[RB], mv[RB], s1[RB], s2[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          xv[r] = __ldg(xp + (r0 + r) * cs);
+          mv[r] = mp ? __ldg(mp + (r0 + r) * cs) : 1.f;
+          s1[r] = sh ? __ldg(sh + (r0 + r) * cs) : 0.f;
+          s2[r] = sh ? __ldg(sl + (r0 + r) * cs) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          float v = fmaf(gv, sp[(r0 + r) * STG_LD], fmaf(xv[r], ds, db));
+          v = (v + (s1[r] + s2[r])) * mv[r];
+          const float hh = tf32_rna(v);
+          ch[(r0 + r) * cs] = hh;
+          cl[(r0 + r) * cs] = tf32_rna(v - hh);
+        }
+      }
+      for (; r0 < nrows; ++r0) {
+        float v = fmaf(gv, sp[r0 * STG_LD], fmaf(__ldg(xp + r0 * cs), ds, db));
+        if (sh) v += __ldg(sh + r0 * cs) + __ldg(sl + r0 * cs);
+        if (mp) v *= __ldg(mp + r0 * cs);
+        const float hh = tf32_rna(v);
+        ch[r0 * cs] = hh;
+        cl[r0 * cs] = tf32_rna(v - hh);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int NB>
 struct ConvSmem {
   static constexpr int A_TILE = TBM * TBK * 4;   // 16 KB
@@ -62,7 +120,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
                const __grid_constant__ CUtensorMap mB1h, const __grid_constant__ CUtensorMap mB1l,
                const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
-               const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, TcParams p0, ConvGeo g) {
+               const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, TcParams p0, ConvGeo g,
+               ConvBnEpilogue bn) {
   using SL = ConvSmem<NB>;
   constexpr bool A_K = (AMODE == 1);
   constexpr int TMEM_COLS = 512;          // 2 buffers x (cross-term tile + main tile) x 128 columns (NB of them used)
@@ -282,7 +341,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(buf));
       }
-      if (h * HC < NB) tile_epilogue<2, 8>(p, acc, stg, m0, n0, zs, q, h, lane);
+      if (h * HC < NB) {
+        if (AMODE == 1 && bn.on) bn_tile_epilogue<2, 8>(p, bn, acc, stg, m0, n0, zs, q, h, lane);
+        else tile_epilogue<2, 8>(p, acc, stg, m0, n0, zs, q, h, lane);
+      }
     }
   }
   tc_fence_before();
@@ -355,7 +417,8 @@ int num_sms() {
 }
 
 template <int NB, int AMODE>
-int launch_conv(const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, int64_t ntiles, cudaStream_t st) {
+int launch_conv(const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, const ConvBnEpilogue& bn, int64_t ntiles,
+                cudaStream_t st) {
   using SL = ConvSmem<NB>;
   auto kern = conv_tc_kernel<NB, AMODE>;
   static bool attr_set = false;
@@ -365,16 +428,17 @@ int launch_conv(const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, in
   }
   const int sms = num_sms();
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, TC_THREADS, SL::BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p, g);
+  kern<<<grid, TC_THREADS, SL::BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p, g, bn);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
 }
 
 template <int AMODE>
-int dispatch_conv(int nb, const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, int64_t ntiles, cudaStream_t st) {
-  if (nb == 32) return launch_conv<32, AMODE>(maps, p, g, ntiles, st);
-  if (nb == 64) return launch_conv<64, AMODE>(maps, p, g, ntiles, st);
-  return launch_conv<128, AMODE>(maps, p, g, ntiles, st);
+int dispatch_conv(int nb, const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, const ConvBnEpilogue& bn, int64_t ntiles,
+                  cudaStream_t st) {
+  if (nb == 32) return launch_conv<32, AMODE>(maps, p, g, bn, ntiles, st);
+  if (nb == 64) return launch_conv<64, AMODE>(maps, p, g, bn, ntiles, st);
+  return launch_conv<128, AMODE>(maps, p, g, bn, ntiles, st);
 }
 
 inline int tile_width(int64_t N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
@@ -438,7 +502,11 @@ int conv_tc(const ConvTcProblem& c, cudaStream_t st) {
   g.imgs = (int)c.imgs; g.Kc = (int)Kc; g.ksplit = 1; g.kb_per = 0;
   const int nb = tile_width(c.N);
   const int64_t ntiles = ceil_div(R, TBM) * ceil_div(c.N, nb) * c.batch;
-  return dispatch_conv<1>(nb, maps, p, g, ntiles, st);
+  if (c.bn.on) {
+    LIP_REQUIRE(c.C_lo && c.c_sm == c.N && c.bn.g && c.bn.xhat && c.bn.dscale && c.bn.dbeta && (!c.bn.skip_hi || c.bn.skip_lo),
+                "conv_tc: the fused BatchNorm epilogue needs a (hi, lo) output with dense rows and all of g / xhat / dscale / dbeta");
+  }
+  return dispatch_conv<1>(nb, maps, p, g, c.bn, ntiles, st);
 }
 
 int64_t conv_wgrad_tc_splits(int64_t imgs, int Ho, int Wo, int C, int N, int kh, int kw, int64_t batch) {
@@ -488,7 +556,7 @@ int conv_wgrad_tc(const ConvWgradTcProblem& c, cudaStream_t st) {
   g.imgs = (int)c.imgs; g.Kc = (int)Kc; g.ksplit = (int)S; g.kb_per = (int)per;
   const int nb = tile_width(c.N);
   const int64_t ntiles = ceil_div(Kc, TBM) * ceil_div(c.N, nb) * c.batch * S;
-  rc = dispatch_conv<2>(nb, maps, p, g, ntiles, st);
+  rc = dispatch_conv<2>(nb, maps, p, g, ConvBnEpilogue(), ntiles, st);
   if (rc || S == 1) return rc;
   const long long MN = Kc * c.N, total = MN * c.batch;
   long long grid = (total + 255) / 256;

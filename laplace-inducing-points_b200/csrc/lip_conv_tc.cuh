@@ -16,6 +16,19 @@ struct ConvTcImage {
   int batched = 0;          // 1: one image stack per batch entry (probe), 0: shared by all batch entries
 };
 
+// Fused BatchNorm(eval)-JVP epilogue of a conv unit (lip_resnet.cu header): with acc = the dual-K conv sum and i = (row, n),
+//   v = mask[i] * ( g[n] * acc + xhat[i] * dscale[z][n] + dbeta[z][n] + skip_hi[z][i] + skip_lo[z][i] )
+// stored as the TF32 pair (C_out, C_lo) that the next conv's TMA reads directly.  xhat / mask: [rows, N]; skip: layout of C.
+struct ConvBnEpilogue {
+  int on = 0;
+  const float* g = nullptr;
+  const float* xhat = nullptr;
+  const float* mask = nullptr;                                   // optional (units without relu)
+  const float* dscale = nullptr; const float* dbeta = nullptr;   // [z * pstride + n]
+  long long pstride = 0;
+  const float* skip_hi = nullptr; const float* skip_lo = nullptr;   // optional
+};
+
 // out[z][(img, y, x)][n] = sum_{dy,dx,c} A1[z?][img, y + s(dy), x + s(dx), c] * B1[z?][(dy,dx,c)][n]   (+ the same with A2, B2)
 //   s(d) = d - pad   (conv forward / JVP)        or        s(d) = pad - d   (transposed = delta back-propagation)
 struct ConvTcProblem {
@@ -28,6 +41,7 @@ struct ConvTcProblem {
   float* C_out = nullptr; int64_t c_sz = 0, c_sm = 0;
   float* C_lo = nullptr;              // optional (hi, lo) output
   GemmEpilogue epi;                   // scale, bias, mask, add
+  ConvBnEpilogue bn;                  // bn.on: replaces `epi` (needs C_lo, c_sm == N)
 };
 int conv_tc(const ConvTcProblem& p, cudaStream_t stream);
 

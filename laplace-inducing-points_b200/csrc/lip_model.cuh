@@ -101,6 +101,7 @@ struct lip_model {
   float* rn_stats = nullptr;             // device copy of the BatchNorm running statistics, [sum 2*c]
   int64_t rn_nstats = 0;
   int64_t rn_slot_elems = 0;             // per-point elements of the largest activation tensor
+  bool rn_pairs = false;                 // every unit but the stem is on the tcgen05 path: JVP tangents live as TF32 (hi, lo) pairs
   void free_resnet_cache();
   void free_cnn_cache();
   void free_cache() {

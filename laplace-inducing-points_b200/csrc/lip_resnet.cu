@@ -13,6 +13,8 @@
 // from the image, lip_conv_tc.cu); the 3-channel stem and the strided convs on the fp32 SIMT kernels (ConvGather in
 // lip_common.cuh).
 // Tangents / cotangents live in four rotating [B, M, H, W, C] slots (block input, branch, shortcut, block output).
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -70,17 +72,24 @@ __global__ void bn_fwd_kernel(const float* __restrict__ h, const float* __restri
 }
 
 // dY[b][i] = mask[i] * ( g[c] * dH[b][i] + xhat[i] * dscale[b][c] + dbeta[b][c] + Tskip[b][i] ),  i in [0, per_z)
+// out_lo != null: the result is stored as a TF32 (hi, lo) pair (and Tskip read as one) for the tcgen05 conv GEMMs
 __global__ void bn_jvp_kernel(const float* __restrict__ dH, const float* __restrict__ g, const float* __restrict__ xhat,
                               const float* __restrict__ mask, const float* __restrict__ dscale, const float* __restrict__ dbeta,
-                              long long pstride, const float* __restrict__ tskip, float* __restrict__ out, long long total,
-                              long long per_z, int C) {
+                              long long pstride, const float* __restrict__ tskip, const float* __restrict__ tskip_lo,
+                              float* __restrict__ out, float* __restrict__ out_lo, long long total, long long per_z, int C) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long z = idx / per_z, i = idx % per_z;
     const int c = (int)(i % C);
     float v = fmaf(g[c], dH[idx], fmaf(__ldg(xhat + i), __ldg(dscale + z * pstride + c), __ldg(dbeta + z * pstride + c)));
-    if (tskip) v += tskip[idx];
+    if (tskip) v += tskip_lo ? tskip[idx] + tskip_lo[idx] : tskip[idx];
     if (mask) v *= __ldg(mask + i);
-    out[idx] = v;
+    if (out_lo) {
+      const float hh = tf32_round(v);
+      out[idx] = hh;
+      out_lo[idx] = tf32_round(v - hh);
+    } else {
+      out[idx] = v;
+    }
   }
 }
 
@@ -165,13 +174,20 @@ __global__ void conv_wt_kernel(const float* __restrict__ W, float* __restrict__ 
 }
 
 // out[mz][c] = mean over hw of in[mz][hw][c]
-__global__ void global_mean_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int HW, int C) {
+__global__ void global_mean_kernel(const float* __restrict__ in, const float* __restrict__ in_lo, float* __restrict__ out,
+                                   long long total, int HW, int C) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long mz = idx / C;
     const int c = (int)(idx % C);
     const float* p = in + mz * HW * C + c;
     float acc = 0.f;
     for (int i = 0; i < HW; ++i) acc += p[(long long)i * C];
+    if (in_lo) {                    // TF32 (hi, lo) pair: add the lo parts
+      const float* q = in_lo + mz * HW * C + c;
+      float acc2 = 0.f;
+      for (int i = 0; i < HW; ++i) acc2 += q[(long long)i * C];
+      acc += acc2;
+    }
     out[idx] = acc / (float)HW;
   }
 }
@@ -187,6 +203,7 @@ __global__ void global_mean_bwd_kernel(const float* __restrict__ g, float* __res
 
 struct RnWs {
   float* slot[4];   // tangent / cotangent tensors [B, M, slot_elems]
+  float* slot_lo[4];// pairs mode (lip_model::rn_pairs): TF32 lo parts of the JVP tangents (slot[] then holds the hi parts)
   float* raw;       // conv GEMM output dH / Dh, [B, max R*cout]
   float* raw_lo;    // tensor path: TF32 lo part of Dh (raw then holds the hi part)
   float* img_h;     // tensor path: TF32 (hi, lo) split of the tangent image a conv reads, [B, M, slot_elems] each
@@ -197,7 +214,7 @@ struct RnWs {
   float* head;      // [B, M, C_last] mean tangent / cotangent  +  [B, M, K] delta at the logits
   float* dl;
 };
-struct RnSizes { size_t slot, raw, col, head, dl, raw_lo, img, vsplit; };
+struct RnSizes { size_t slot, raw, col, head, dl, raw_lo, img, vsplit, slot_lo; };
 
 RnSizes rn_sizes(const lip_model* m, int64_t B) {
   RnSizes z{};
@@ -224,6 +241,7 @@ RnSizes rn_sizes(const lip_model* m, int64_t B) {
   z.raw_lo = any_tc ? z.raw : 0;
   z.img = any_tc ? align_up(img, 64) : 0;
   z.vsplit = align_up(vs, 64);
+  z.slot_lo = m->rn_pairs ? z.slot : 0;
   z.head = align_up((size_t)B * m->M * m->rn_C, 64);
   z.dl = align_up((size_t)B * m->M * m->K, 64);
   return z;
@@ -246,32 +264,47 @@ int rn_carve(const lip_model* m, int64_t B, void* ws, size_t bytes, RnWs* w) {
   w->img_h = p; p += z.img;
   w->img_l = p; p += z.img;
   w->vh = p; p += z.vsplit;
-  w->vl = p;
+  w->vl = p; p += z.vsplit;
+  for (int i = 0; i < 4; ++i) { w->slot_lo[i] = p; p += z.slot_lo; }
   return LIP_OK;
 }
 
 // ---- JVP sweep: V[B, D] -> dlogits [B, M, K] in dst --------------------------------------------------------------------
 int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* dst, cudaStream_t st) {
   if (m->lo_nz) LIP_CHECK_CUDA(cudaMemsetAsync(m->lo_nz, 0, sizeof(int) * m->RB.size(), st));
+  const bool pairs = m->rn_pairs;
   for (const ConvBN& u : m->RB) {
     const int64_t R = m->M * u.P(), Kc = u.Kc();
     int rc;
     if (u.tc) {
-      // tensor path: split the probe's tangent kernels and tangent image into TF32 (hi, lo), then one dual-K implicit GEMM
+      // tensor path: split the probe's tangent kernels (and, outside pairs mode, the tangent image) into TF32 (hi, lo), then
+      // one dual-K implicit GEMM; in pairs mode its epilogue is the whole BatchNorm-JVP and writes the next (hi, lo) tangent
       const int64_t img_elems = m->M * (int64_t)u.Hi * u.Wi * u.cin;
       int* nz = m->lo_nz + (&u - m->RB.data());
       rc = tf32_split3(V + u.woff, m->D, Kc * u.cout, w.vh, w.vl, Kc * u.cout, Kc * u.cout, B, 1, Kc * u.cout, st, nz);
       if (rc) return rc;
-      rc = tf32_split3(w.slot[u.src], 0, B * img_elems, w.img_h, w.img_l, 0, B * img_elems, 1, 1, B * img_elems, st);
-      if (rc) return rc;
+      if (!pairs) {
+        rc = tf32_split3(w.slot[u.src], 0, B * img_elems, w.img_h, w.img_l, 0, B * img_elems, 1, 1, B * img_elems, st);
+        if (rc) return rc;
+      }
       ConvTcProblem c;
       c.imgs = m->M; c.batch = B; c.H = u.Hi; c.W = u.Wi; c.C = u.cin; c.N = u.cout; c.kh = u.kh; c.kw = u.kw; c.pad = u.pad_h;
       c.stride = u.stride;
       c.A1.hi = u.Xh; c.A1.lo = u.Xl; c.A1.batched = 0;
       c.B1.hi = w.vh; c.B1.lo = w.vl; c.B1.sz = Kc * u.cout; c.B1.ld = u.cout; c.B1.major_k = 0; c.B1.lo_nz = nz; c.b1_batched = 1;
-      c.A2.hi = w.img_h; c.A2.lo = w.img_l; c.A2.batched = 1;
+      c.A2.hi = pairs ? w.slot[u.src] : w.img_h; c.A2.lo = pairs ? w.slot_lo[u.src] : w.img_l; c.A2.batched = 1;
       c.B2.hi = u.Wh; c.B2.lo = u.Wl; c.B2.sz = 0; c.B2.ld = u.cout; c.B2.major_k = 0; c.b2_batched = 0;
-      c.C_out = w.raw; c.c_sz = R * (int64_t)u.cout; c.c_sm = u.cout;
+      c.c_sz = R * (int64_t)u.cout; c.c_sm = u.cout;
+      if (pairs) {
+        c.C_out = w.slot[u.dst]; c.C_lo = w.slot_lo[u.dst];
+        c.bn.on = 1; c.bn.g = u.g; c.bn.xhat = u.xhat; c.bn.mask = u.mask;
+        c.bn.dscale = V + u.scale_off; c.bn.dbeta = V + u.beta_off; c.bn.pstride = m->D;
+        if (u.skip >= 0) { c.bn.skip_hi = w.slot[u.skip]; c.bn.skip_lo = w.slot_lo[u.skip]; }
+        rc = conv_tc(c, st);
+        if (rc) return rc;
+        continue;
+      }
+      c.C_out = w.raw;
       rc = conv_tc(c, st);
     } else {
       GemmProblem p;
@@ -290,13 +323,16 @@ int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* 
     if (rc) return rc;
     const long long per_z = R * (long long)u.cout, total = per_z * B;
     bn_jvp_kernel<<<ew_grid(total), 256, 0, st>>>(w.raw, u.g, u.xhat, u.mask, V + u.scale_off, V + u.beta_off, m->D,
-                                                  u.skip >= 0 ? w.slot[u.skip] : nullptr, w.slot[u.dst], total, per_z, u.cout);
+                                                  u.skip >= 0 ? w.slot[u.skip] : nullptr,
+                                                  (pairs && u.skip >= 0) ? w.slot_lo[u.skip] : nullptr, w.slot[u.dst],
+                                                  pairs ? w.slot_lo[u.dst] : nullptr, total, per_z, u.cout);
     LIP_LAUNCH_CHECK();
   }
   const int HW = m->rn_H * m->rn_W, C = m->rn_C;
   {
     const long long total = (long long)B * m->M * C;
-    global_mean_kernel<<<ew_grid(total), 256, 0, st>>>(w.slot[m->rn_last_slot], w.head, total, HW, C);
+    global_mean_kernel<<<ew_grid(total), 256, 0, st>>>(w.slot[m->rn_last_slot], pairs ? w.slot_lo[m->rn_last_slot] : nullptr, w.head,
+                                                       total, HW, C);
     LIP_LAUNCH_CHECK();
   }
   GemmProblem p;   // head: dlogits[b] = mean_act . dWd[b] + Tmean[b] . Wd + dbd[b]
@@ -601,7 +637,7 @@ int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cud
       cleanup(); set_error("lip_model_bind: out of device memory (head)"); return LIP_ERR_CUDA;
     }
     const long long total = (long long)M * C;
-    global_mean_kernel<<<ew_grid(total), 256, 0, st>>>(act[m->rn_last_slot], m->rn_mean_act, total, HW, C);
+    global_mean_kernel<<<ew_grid(total), 256, 0, st>>>(act[m->rn_last_slot], nullptr, m->rn_mean_act, total, HW, C);
     count_launch();
     GemmProblem p;
     p.M = M; p.N = m->K; p.K = C; p.batch = 1;
@@ -620,6 +656,9 @@ int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cud
     set_error("lip_model_bind: out of device memory (flags)"); return LIP_ERR_CUDA;
   }
   m->tc_on = any_tc;
+  static const int no_fuse = getenv("LIP_CONV_TC_FUSE") ? (atoi(getenv("LIP_CONV_TC_FUSE")) == 0) : 0;
+  m->rn_pairs = any_tc && !no_fuse;
+  for (const ConvBN& u : m->RB) if (u.src != -2 && !u.tc) m->rn_pairs = false;
   m->tc_layer.assign(m->RB.size(), 0);
   for (size_t i = 0; i < m->RB.size(); ++i) m->tc_layer[i] = m->RB[i].tc ? 1 : 0;
   m->bound = true;
@@ -628,7 +667,7 @@ int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cud
 
 size_t resnet_ws_bytes(const lip_model* m, int64_t B) {
   const RnSizes z = rn_sizes(m, B);
-  return (4 * z.slot + z.raw + z.col + z.head + z.dl + z.raw_lo + 2 * z.img + 2 * z.vsplit) * sizeof(float) + 512;
+  return (4 * z.slot + z.raw + z.col + z.head + z.dl + z.raw_lo + 2 * z.img + 2 * z.vsplit + 4 * z.slot_lo) * sizeof(float) + 512;
 }
 
 int resnet_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* ws, size_t bytes,
