@@ -219,7 +219,8 @@ int lip_bench_tc_gemm(int32_t variant, int64_t Mrows, int64_t N, int64_t K, int6
 /* Self test / microbenchmark of the tcgen05 implicit-GEMM convolutions (lip_conv_tc.cu) against the fp32 SIMT implicit GEMM
  * on random data, for a SAME ksz x ksz conv (stride 1 or 2) on `imgs` images [H, W, cin] -> cout and `batch` probes.
  * role: 0 = JVP (shared image x per-probe kernels + per-probe image x shared kernel), 1 = per-probe kernel gradient,
- * 2 = delta back-propagation (transposed conv).  *rel_err = relative L2 error; with iters > 0, *ms_tc / *ms_simt = mean
+ * 2 = delta back-propagation (transposed conv), 3 = the first JVP term alone with the probes folded into the tile width.
+ * *rel_err = relative L2 error; with iters > 0, *ms_tc / *ms_simt = mean
  * time of one tensor-core / one SIMT call. */
 int lip_selftest_conv_tc(int32_t role, int64_t imgs, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksz,
                          int32_t stride, int64_t batch, int32_t iters, float* rel_err, float* ms_tc, float* ms_simt, lip_stream_t stream);

@@ -38,6 +38,8 @@ struct ConvGeo {
   int imgs;                  // images per batch entry (points M)
   int Kc;                    // AMODE 2: patch columns = taps * C (rows of the output)
   int ksplit, kb_per;        // AMODE 2: K slices and k-blocks per slice
+  int merge;                 // 1: one N = 2*NB MMA computes A_hi x [B_hi | B_lo] (see the MMA issuer); 0: three N = NB MMAs
+  int fold, cpb;             // fold > 1: a 128-column tile = `fold` probes x N columns (cpb = N / 32 chunks each); A is shared
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -69,15 +71,17 @@ __device__ __forceinline__ void bn_tile_epilogue(const TcParams& p, const ConvBn
       const float* mp = e.mask ? e.mask + i0 + n : nullptr;
       const float* sh = e.skip_hi ? e.skip_hi + zc + n : nullptr;
       const float* sl = e.skip_hi ? e.skip_lo + zc + n : nullptr;
+      const float* pp = e.pre ? e.pre + zc + n : nullptr;
       float* ch = p.C + zc + n;
       float* cl = p.C_lo + zc + n;
       const float* sp = stg + lane;
       const long long cs = p.c_sm;
       int r0 = 0;
       for (; r0 + RB <= nrows; r0 += RB) {
-        float xv[RB], mv[RB], s1[RB], s2[RB];
+        float xv[RB], mv[RB], s1[RB], s2[RB], pv[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
+          pv[r] = pp ? __ldg(pp + (r0 + r) * cs) : 0.f;
           xv[r] = __ldg(xp + (r0 + r) * cs);
           mv[r] = mp ? __ldg(mp + (r0 + r) * cs) : 1.f;
           s1[r] = sh ? __ldg(sh + (r0 + r) * cs) : 0.f;
@@ -85,7 +89,7 @@ __device__ __forceinline__ void bn_tile_epilogue(const TcParams& p, const ConvBn
         }
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
-          float v = fmaf(gv, sp[(r0 + r) * STG_LD], fmaf(xv[r], ds, db));
+          float v = fmaf(gv, sp[(r0 + r) * STG_LD] + pv[r], fmaf(xv[r], ds, db));
           v = (v + (s1[r] + s2[r])) * mv[r];
           const float hh = tf32_rna(v);
           ch[(r0 + r) * cs] = hh;
@@ -93,7 +97,7 @@ __device__ __forceinline__ void bn_tile_epilogue(const TcParams& p, const ConvBn
         }
       }
       for (; r0 < nrows; ++r0) {
-        float v = fmaf(gv, sp[r0 * STG_LD], fmaf(__ldg(xp + r0 * cs), ds, db));
+        float v = fmaf(gv, sp[r0 * STG_LD] + (pp ? __ldg(pp + r0 * cs) : 0.f), fmaf(__ldg(xp + r0 * cs), ds, db));
         if (sh) v += __ldg(sh + r0 * cs) + __ldg(sl + r0 * cs);
         if (mp) v *= __ldg(mp + r0 * cs);
         const float hh = tf32_rna(v);
@@ -115,7 +119,8 @@ struct ConvSmem {
   static constexpr int BYTES = STAGES * STAGE + STAGING + 1024 + 256;
 };
 
-template <int NB, int AMODE>
+// EPI: 0 = plain fused epilogue (tile_epilogue), 1 = BatchNorm-JVP epilogue (AMODE 1), 2 = probes folded into the tile width
+template <int NB, int AMODE, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
                const __grid_constant__ CUtensorMap mB1h, const __grid_constant__ CUtensorMap mB1l,
@@ -143,21 +148,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
   const bool skip_b1lo = p0.b1_lo_nz != nullptr && *reinterpret_cast<const volatile int*>(p0.b1_lo_nz) == 0;
   const int KCr = p0.kc;
   const int S = (AMODE == 2) ? g.ksplit : 1;
-  const int mt = (p0.M + TBM - 1) / TBM, nt = (p0.N + NB - 1) / NB;
-  const long long ntiles = (long long)mt * nt * p0.batch * S;
-  // tile t -> (m tile, n tile, batch entry z, K slice s): m fastest, slices of one output tile far apart
-  auto tile_coords = [&](long long t, int& m0, int& n0, int& z, int& kb_lo, int& kb_hi) {
+  const int G = (EPI == 2) ? g.fold : 1;      // probes folded into the N dimension of one tile (1: none)
+  const int mt = (p0.M + TBM - 1) / TBM, nt = G > 1 ? 1 : (p0.N + NB - 1) / NB;
+  const int nz = G > 1 ? (p0.batch + G - 1) / G : p0.batch;      // batch entries, or groups of G probes
+  const long long ntiles = (long long)mt * nt * nz * S;
+  // tile t -> (m tile, n tile, batch entry or probe group z, K slice s): m fastest, slices of one output tile far apart
+  auto tile_coords = [&](long long t, int& m0, int& n0, int& z, int& s, int& kb_lo, int& kb_hi) {
     const int tm = (int)(t % mt);
     long long r = t / mt;
     const int tn = (int)(r % nt);
     r /= nt;
-    z = (int)(r % p0.batch);
-    const int s = (int)(r / p0.batch);
+    z = (int)(r % nz);
+    s = (int)(r / nz);
     m0 = tm * TBM; n0 = tn * NB;
     if (AMODE == 2) {
       kb_lo = s * g.kb_per;
       kb_hi = kb_lo + g.kb_per < nk ? kb_lo + g.kb_per : nk;
-      z = z * S + s;          // slot index of the partial tile; the producer recovers the batch entry as z / S
     } else {
       kb_lo = 0; kb_hi = nk;
     }
@@ -184,9 +190,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
     // ================= TMA producer =================
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      int m0, n0, zs, kb_lo, kb_hi;
-      tile_coords(t, m0, n0, zs, kb_lo, kb_hi);
-      const int z = (AMODE == 2) ? zs / S : zs;
+      int m0, n0, z, ks, kb_lo, kb_hi;
+      tile_coords(t, m0, n0, z, ks, kb_lo, kb_hi);
       // AMODE 1: the tile's 128 pixel rows start at (img0, h0, w0) of batch entry z
       int img0 = 0, h0 = 0, w0 = 0;
       // AMODE 2: the four 32-column chunks of the A tile are four (tap, channel block) pairs
@@ -221,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
           const CUtensorMap* al = second ? &mA2l : &mA1l;
           const CUtensorMap* bh = second ? &mB2h : &mB1h;
           const CUtensorMap* bl = second ? &mB2l : &mB1l;
-          const int za = (second ? p0.a2_batched : p0.a1_batched) ? z : 0;
+          const int za = (second ? p0.a2_batched : p0.a1_batched) ? z : 0;      // (fold mode: A is shared)
           const int zb = (second ? p0.b2_batched : p0.b1_batched) ? z : 0;
           if (AMODE == 1) {
             const int tap = kk / g.cblocks, cb = kk - tap * g.cblocks;
@@ -246,8 +251,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
           const int k0b = kk * TBK;
 #pragma unroll
           for (int c = 0; c < NB / 32; ++c) {
-            tma_load_3d(st + 2 * SL::A_TILE + c * (TBK * 128), bh, full_bar(s), n0 + 32 * c, k0b, zb);
-            if (!no_blo) tma_load_3d(st + 2 * SL::A_TILE + SL::B_TILE + c * (TBK * 128), bl, full_bar(s), n0 + 32 * c, k0b, zb);
+            // fold mode: chunk c = 32 columns of probe z*G + c/cpb (a probe index past the batch is an all-zero box)
+            const int bn0 = G > 1 ? (c % g.cpb) * 32 : n0 + 32 * c;
+            const int bz = G > 1 ? z * G + c / g.cpb : zb;
+            tma_load_3d(st + 2 * SL::A_TILE + c * (TBK * 128), bh, full_bar(s), bn0, k0b, bz);
+            if (!no_blo) tma_load_3d(st + 2 * SL::A_TILE + SL::B_TILE + c * (TBK * 128), bl, full_bar(s), bn0, k0b, bz);
           }
         }
         __syncwarp();
@@ -255,22 +263,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    // The B tile is MN-major: 32-column chunks 4 KB apart, and its lo chunks directly follow its hi chunks.  One N = 2*NB MMA
+    // therefore computes A_hi x [B_hi | B_lo]: main term in TMEM columns [0, NB), first cross term in [NB, 2NB); the second
+    // cross term A_lo x B_hi accumulates on top of the first.  A_hi is read from shared memory once instead of twice - the
+    // narrow-N kernels are bound by exactly those reads.
     constexpr uint32_t idesc = make_idesc(TBM, NB, !A_K, true);
+    constexpr uint32_t idesc2 = make_idesc(TBM, 2 * NB, !A_K, true);
     constexpr uint32_t A_LBO = A_K ? 16 : TBK * 128, B_LBO = TBK * 128;
     constexpr uint32_t A_SBO = A_K ? 1024 : 512, B_SBO = 512;
     constexpr uint32_t A_LT = A_K ? 2 : 1, B_LT = 1;
     constexpr uint32_t A_KSTEP = A_K ? 32 : 1024, B_KSTEP = 1024;
     uint32_t it = 0, ck = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      int m0, n0, zs, kb_lo, kb_hi;
-      tile_coords(t, m0, n0, zs, kb_lo, kb_hi);
+      int m0, n0, z, ks, kb_lo, kb_hi;
+      tile_coords(t, m0, n0, z, ks, kb_lo, kb_hi);
       const int nkt = kb_hi - kb_lo;
       const int nchunks = (nkt + KCr - 1) / KCr;
       for (int c = 0; c < nchunks; ++c, ++ck) {
         const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
         mbar_wait(tempty_bar(buf), cph ^ 1);
         tc_fence_after();
-        const uint32_t t_small = tmem_base + buf * (2 * TSTRIDE), t_main = t_small + TSTRIDE;
+        const uint32_t t_main = tmem_base + buf * (2 * TSTRIDE), t_cross = t_main + (g.merge == 2 ? TSTRIDE : NB);
         const int kq_end = (c + 1) * KCr < nkt ? (c + 1) * KCr : nkt;
         for (int kq = c * KCr; kq < kq_end; ++kq, ++it) {
           const int s = it % SL::STAGES;
@@ -278,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t st = smem_base + s * SL::STAGE;
-          const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE, b_lo = b_hi + SL::B_TILE;
+          const uint32_t a_hi = st, a_lo = st + SL::A_TILE, b_hi = st + 2 * SL::A_TILE;
           if (elect_one()) {
             const bool no_blo = skip_b1lo && (kb_lo + kq) < nk1;
 #pragma unroll
@@ -286,11 +299,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
               const uint64_t dah = make_smem_desc(a_hi + j * A_KSTEP, A_LBO, A_SBO, A_LT);
               const uint64_t dal = make_smem_desc(a_lo + j * A_KSTEP, A_LBO, A_SBO, A_LT);
               const uint64_t dbh = make_smem_desc(b_hi + j * B_KSTEP, B_LBO, B_SBO, B_LT);
-              const uint64_t dbl = make_smem_desc(b_lo + j * B_KSTEP, B_LBO, B_SBO, B_LT);
               const uint32_t acc = (kq != c * KCr || j != 0) ? 1u : 0u;
-              umma_tf32(t_small, dal, dbh, idesc, acc);
-              if (!no_blo) umma_tf32(t_small, dah, dbl, idesc, 1);
-              umma_tf32(t_main, dah, dbh, idesc, acc);
+              if (no_blo) {      // exactly-TF32 B (lo identically zero, its tile not loaded): main and one cross term
+                umma_tf32(t_main, dah, dbh, idesc, acc);
+                umma_tf32(t_cross, dal, dbh, idesc, acc);
+              } else if (g.merge != 1) {
+                const uint64_t dbl = make_smem_desc(b_hi + SL::B_TILE + j * B_KSTEP, B_LBO, B_SBO, B_LT);
+                umma_tf32(t_cross, dal, dbh, idesc, acc);
+                umma_tf32(t_cross, dah, dbl, idesc, 1);
+                umma_tf32(t_main, dah, dbh, idesc, acc);
+              } else {
+                umma_tf32(t_main, dah, dbh, idesc2, acc);       // [main | A_hi x B_lo]
+                umma_tf32(t_cross, dal, dbh, idesc, 1);         // += A_lo x B_hi
+              }
             }
             umma_commit(empty_bar(s));
           }
@@ -314,12 +335,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
     p.colsum = nullptr;
     uint32_t ck = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      int m0, n0, zs, kb_lo, kb_hi;
-      tile_coords(t, m0, n0, zs, kb_lo, kb_hi);
+      int m0, n0, z, ks, kb_lo, kb_hi;
+      tile_coords(t, m0, n0, z, ks, kb_lo, kb_hi);
       const int nchunks = (kb_hi - kb_lo + KCr - 1) / KCr;
       float acc[HC];
 #pragma unroll
       for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+      if (EPI == 0 && p.add != nullptr) {
+        // the epilogue reads add[m][n] (the cotangent already in the slot) in four dependent 8-row batches: pull this warp's
+        // 32 x 64 block into L2 now, while the tensor core still works on the tile (lane <-> row, one 128-byte line per group)
+        const int row = m0 + q * 32 + lane;
+        if (row < p.M) {
+          const float* a = p.add + (long long)(z * S + ks) * p.add_sz + (long long)row * p.c_sm + n0 + h * HC;
+#pragma unroll
+          for (int cc = 0; cc < HC / 32; ++cc)
+            if (h * HC + cc * 32 < NB && n0 + h * HC + cc * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + cc * 32));
+        }
+      }
       for (int c = 0; c < nchunks; ++c, ++ck) {
         const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
         mbar_wait(tfull_bar(buf), cph);
@@ -329,10 +361,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
         for (int cc = 0; cc < HC / 32; ++cc) {
           if (h * HC + cc * 32 < NB) {
             float w[32];
-            tmem_ld32(tl + (uint32_t)(cc * 32), w);
+            tmem_ld32(tl + (uint32_t)((g.merge == 2 ? TSTRIDE : NB) + cc * 32), w);            // cross terms
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
-            tmem_ld32(tl + (uint32_t)(TSTRIDE + cc * 32), w);
+            tmem_ld32(tl + (uint32_t)(cc * 32), w);                 // main term
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += w[i];
           }
@@ -341,8 +373,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(buf));
       }
-      if (h * HC < NB) {
-        if (AMODE == 1 && bn.on) bn_tile_epilogue<2, 8>(p, bn, acc, stg, m0, n0, zs, q, h, lane);
+      if (EPI == 2) {
+        // fold mode: each 32-column group of the tile belongs to one probe (output slot probe*S + slice)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int grp = h * 2 + cc;
+          const int probe = z * G + grp / g.cpb;
+          if (probe < p0.batch)
+            tile_epilogue<1, 8>(p, reinterpret_cast<float(&)[32]>(acc[cc * 32]), stg, m0, (grp % g.cpb) * 32, probe * S + ks, q, 0,
+                                lane);
+        }
+      } else if (h * HC < NB) {
+        const int zs = z * S + ks;
+        if (EPI == 1) bn_tile_epilogue<2, 8>(p, bn, acc, stg, m0, n0, zs, q, h, lane);
         else tile_epilogue<2, 8>(p, acc, stg, m0, n0, zs, q, h, lane);
       }
     }
@@ -416,11 +459,11 @@ int num_sms() {
   return n;
 }
 
-template <int NB, int AMODE>
+template <int NB, int AMODE, int EPI>
 int launch_conv(const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, const ConvBnEpilogue& bn, int64_t ntiles,
                 cudaStream_t st) {
   using SL = ConvSmem<NB>;
-  auto kern = conv_tc_kernel<NB, AMODE>;
+  auto kern = conv_tc_kernel<NB, AMODE, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES));
@@ -436,12 +479,29 @@ int launch_conv(const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, co
 template <int AMODE>
 int dispatch_conv(int nb, const CUtensorMap* maps, const TcParams& p, const ConvGeo& g, const ConvBnEpilogue& bn, int64_t ntiles,
                   cudaStream_t st) {
-  if (nb == 32) return launch_conv<32, AMODE>(maps, p, g, bn, ntiles, st);
-  if (nb == 64) return launch_conv<64, AMODE>(maps, p, g, bn, ntiles, st);
-  return launch_conv<128, AMODE>(maps, p, g, bn, ntiles, st);
+  if (g.fold > 1) return launch_conv<128, AMODE, 2>(maps, p, g, bn, ntiles, st);
+  if (AMODE == 1 && bn.on) {
+    if (nb == 32) return launch_conv<32, 1, 1>(maps, p, g, bn, ntiles, st);
+    if (nb == 64) return launch_conv<64, 1, 1>(maps, p, g, bn, ntiles, st);
+    return launch_conv<128, 1, 1>(maps, p, g, bn, ntiles, st);
+  }
+  if (nb == 32) return launch_conv<32, AMODE, 0>(maps, p, g, bn, ntiles, st);
+  if (nb == 64) return launch_conv<64, AMODE, 0>(maps, p, g, bn, ntiles, st);
+  return launch_conv<128, AMODE, 0>(maps, p, g, bn, ntiles, st);
 }
 
 inline int tile_width(int64_t N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+// probes folded into one 128-column tile when the A operand is shared by all probes (N = 32 -> 4, N = 64 -> 2)
+inline int fold_of(int64_t N, int64_t batch) {
+  static const int off = getenv("LIP_CONV_TC_FOLD") ? (atoi(getenv("LIP_CONV_TC_FOLD")) == 0) : 0;
+  if (off || batch < 2 || (N != 32 && N != 64)) return 1;
+  return (int)(128 / N);
+}
+
+int merge_default() {
+  static const int m = getenv("LIP_CONV_TC_MERGE") ? atoi(getenv("LIP_CONV_TC_MERGE")) : 1;
+  return m;
+}
 
 void fill_params(TcParams* p, int64_t M, int64_t N, int64_t K1, int64_t K2, int64_t batch) {
   memset(p, 0, sizeof(*p));
@@ -500,8 +560,13 @@ int conv_tc(const ConvTcProblem& c, cudaStream_t st) {
   g.sgn = c.transposed ? -1 : 1;
   g.off_h = c.transposed ? c.pad : -c.pad; g.off_w = g.off_h;
   g.imgs = (int)c.imgs; g.Kc = (int)Kc; g.ksplit = 1; g.kb_per = 0;
-  const int nb = tile_width(c.N);
-  const int64_t ntiles = ceil_div(R, TBM) * ceil_div(c.N, nb) * c.batch;
+  g.fold = 1; g.cpb = (int)(c.N / 32); g.merge = merge_default();
+  if (c.fold_probes) {
+    LIP_REQUIRE(!dual && !c.A1.batched && c.b1_batched && !c.bn.on && !c.C_lo, "conv_tc: probe folding needs one shared image");
+    g.fold = fold_of(c.N, c.batch);
+  }
+  const int nb = g.fold > 1 ? 128 : tile_width(c.N);
+  const int64_t ntiles = g.fold > 1 ? ceil_div(R, TBM) * ceil_div(c.batch, g.fold) : ceil_div(R, TBM) * ceil_div(c.N, nb) * c.batch;
   if (c.bn.on) {
     LIP_REQUIRE(c.C_lo && c.c_sm == c.N && c.bn.g && c.bn.xhat && c.bn.dscale && c.bn.dbeta && (!c.bn.skip_hi || c.bn.skip_lo),
                 "conv_tc: the fused BatchNorm epilogue needs a (hi, lo) output with dense rows and all of g / xhat / dscale / dbeta");
@@ -511,7 +576,9 @@ int conv_tc(const ConvTcProblem& c, cudaStream_t st) {
 
 int64_t conv_wgrad_tc_splits(int64_t imgs, int Ho, int Wo, int C, int N, int kh, int kw, int64_t batch) {
   const int64_t nk = ceil_div(imgs * (int64_t)Ho * Wo, TBK);
-  const int64_t tiles = ceil_div((int64_t)kh * kw * C, TBM) * ceil_div(N, tile_width(N)) * batch;
+  const int fold = fold_of(N, batch);
+  const int64_t tiles = fold > 1 ? ceil_div((int64_t)kh * kw * C, TBM) * ceil_div(batch, fold)
+                                 : ceil_div((int64_t)kh * kw * C, TBM) * ceil_div(N, tile_width(N)) * batch;
   int64_t S = ceil_div(2 * (int64_t)num_sms(), tiles);
   const int64_t smax = nk / 16 > 1 ? nk / 16 : 1;     // at least 16 k-blocks (two TMEM chunks) per slice
   if (S > smax) S = smax;
@@ -554,8 +621,9 @@ int conv_wgrad_tc(const ConvWgradTcProblem& c, cudaStream_t st) {
   g.W = Wo; g.H = Ho; g.P = (int)P; g.stride = sd; g.C = c.C; g.cblocks = c.C / 32; g.kw = c.kw;
   g.sgn = 1; g.off_h = -c.pad; g.off_w = -c.pad;
   g.imgs = (int)c.imgs; g.Kc = (int)Kc; g.ksplit = (int)S; g.kb_per = (int)per;
-  const int nb = tile_width(c.N);
-  const int64_t ntiles = ceil_div(Kc, TBM) * ceil_div(c.N, nb) * c.batch * S;
+  g.fold = fold_of(c.N, c.batch); g.cpb = (int)(c.N / 32); g.merge = merge_default();
+  const int nb = g.fold > 1 ? 128 : tile_width(c.N);
+  const int64_t ntiles = (g.fold > 1 ? ceil_div(Kc, TBM) * ceil_div(c.batch, g.fold) : ceil_div(Kc, TBM) * ceil_div(c.N, nb) * c.batch) * S;
   rc = dispatch_conv<2>(nb, maps, p, g, ConvBnEpilogue(), ntiles, st);
   if (rc || S == 1) return rc;
   const long long MN = Kc * c.N, total = MN * c.batch;
@@ -632,7 +700,7 @@ extern "C" int lip_selftest_conv_tc(int32_t role, int64_t imgs, int32_t H, int32
                                     int32_t stride, int64_t batch, int32_t iters, float* rel_err, float* ms_tc, float* ms_simt,
                                     lip_stream_t stream) {
   using namespace lip;
-  LIP_REQUIRE(role >= 0 && role <= 2 && imgs > 0 && batch > 0 && rel_err && (stride == 1 || stride == 2),
+  LIP_REQUIRE(role >= 0 && role <= 3 && imgs > 0 && batch > 0 && rel_err && (stride == 1 || stride == 2),
               "conv selftest: bad argument");
   const int pad = stride == 1 ? (ksz - 1) / 2 : 0;      // XLA 'SAME' (smaller half first)
   if (!conv_tc_supported(H, W, cin, cout, ksz, ksz, stride, pad)) {
@@ -646,7 +714,7 @@ extern "C" int lip_selftest_conv_tc(int32_t role, int64_t imgs, int32_t H, int32
   // buffers: X [imgs,H,W,cin] shared image, T [batch,imgs,H,W,cin] per-probe image, Wk [Kc,cout] shared kernel,
   // dW [batch,Kc,cout] per-probe kernels, Dh [batch,R,cout] deltas, Wt [Kt,cin] re-laid kernel
   const int64_t nX = Ri * cin, nT = batch * Ri * cin, nW = Kc * cout, ndW = batch * Kc * cout, nD = batch * R * cout, nWt = Kt * cin;
-  const int64_t nOut = role == 0 ? nD : (role == 1 ? ndW : nT);
+  const int64_t nOut = (role == 0 || role == 3) ? nD : (role == 1 ? ndW : nT);
   const int64_t nUp = stride == 2 ? batch * Ri * cout : 1;
   const int64_t S = conv_wgrad_tc_splits(imgs, Ho, Wo, cin, cout, ksz, ksz, batch);
   const int64_t nws = batch * S * Kc * cout;
@@ -681,7 +749,7 @@ extern "C" int lip_selftest_conv_tc(int32_t role, int64_t imgs, int32_t H, int32
   GemmProblem sp;
   ConvTcProblem tp;
   ConvWgradTcProblem wp;
-  if (role == 0) {
+  if (role == 0 || role == 3) {
     cg.mode = 1; cg.C = cin;
     sp.M = R; sp.N = cout; sp.K = Kc; sp.batch = batch;
     sp.A1.ptr = X; sp.A1.sz = 0; sp.A1.conv = cg;
@@ -697,6 +765,11 @@ extern "C" int lip_selftest_conv_tc(int32_t role, int64_t imgs, int32_t H, int32
     tp.A2 = {Th, Tl, 1};
     tp.B2.hi = Wh; tp.B2.lo = Wl; tp.B2.sz = 0; tp.B2.ld = cout; tp.B2.major_k = 0; tp.b2_batched = 0;
     tp.C_out = C1; tp.c_sz = R * cout; tp.c_sm = cout;
+    if (role == 3) {          // first JVP term alone, probes folded into the tile width
+      sp.A2 = GemmOperand(); sp.B2 = GemmOperand(); sp.K2 = 0;
+      tp.A2 = ConvTcImage(); tp.B2 = TcOperand();
+      tp.fold_probes = 1;
+    }
   } else if (role == 1) {
     cg.mode = 2; cg.C = cin;
     sp.M = Kc; sp.N = cout; sp.K = R; sp.batch = batch;
@@ -724,6 +797,7 @@ extern "C" int lip_selftest_conv_tc(int32_t role, int64_t imgs, int32_t H, int32
     if (stride == 2) tp.A1 = {Uh, Ul, 1}; else tp.A1 = {Dhh, Dhl, 1};
     tp.B1.hi = Wth; tp.B1.lo = Wtl; tp.B1.sz = 0; tp.B1.ld = cin; tp.B1.major_k = 0; tp.b1_batched = 0;
     tp.C_out = C1; tp.c_sz = Ri * cin; tp.c_sm = cin;
+    if (getenv("LIP_SELFTEST_NOADD")) { sp.epi.add = nullptr; sp.epi.add_scale = 0.f; }
     tp.epi = sp.epi;
   }
   sp.epi.C_lo = nullptr;

@@ -17,7 +17,7 @@ struct ConvTcImage {
 };
 
 // Fused BatchNorm(eval)-JVP epilogue of a conv unit (lip_resnet.cu header): with acc = the dual-K conv sum and i = (row, n),
-//   v = mask[i] * ( g[n] * acc + xhat[i] * dscale[z][n] + dbeta[z][n] + skip_hi[z][i] + skip_lo[z][i] )
+//   v = mask[i] * ( g[n] * (acc + pre[z][i]) + xhat[i] * dscale[z][n] + dbeta[z][n] + skip_hi[z][i] + skip_lo[z][i] )
 // stored as the TF32 pair (C_out, C_lo) that the next conv's TMA reads directly.  xhat / mask: [rows, N]; skip: layout of C.
 struct ConvBnEpilogue {
   int on = 0;
@@ -27,6 +27,7 @@ struct ConvBnEpilogue {
   const float* dscale = nullptr; const float* dbeta = nullptr;   // [z * pstride + n]
   long long pstride = 0;
   const float* skip_hi = nullptr; const float* skip_lo = nullptr;   // optional
+  const float* pre = nullptr;      // optional fp32 [layout of C]: added to acc (the probe-folded first JVP term)
 };
 
 // out[z][(img, y, x)][n] = sum_{dy,dx,c} A1[z?][img, y + s(dy), x + s(dx), c] * B1[z?][(dy,dx,c)][n]   (+ the same with A2, B2)
@@ -42,6 +43,9 @@ struct ConvTcProblem {
   float* C_lo = nullptr;              // optional (hi, lo) output
   GemmEpilogue epi;                   // scale, bias, mask, add
   ConvBnEpilogue bn;                  // bn.on: replaces `epi` (needs C_lo, c_sm == N)
+  // 1: A1 is shared and B1 per probe (no second pair): 128 / N probes share one 128-column tile, so the image tile is
+  // staged and read once for all of them (N = 32 / 64; the narrow-N kernels are bound by the A operand's shared-memory reads)
+  int fold_probes = 0;
 };
 int conv_tc(const ConvTcProblem& p, cudaStream_t stream);
 

@@ -296,6 +296,19 @@ int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* 
       c.B2.hi = u.Wh; c.B2.lo = u.Wl; c.B2.sz = 0; c.B2.ld = u.cout; c.B2.major_k = 0; c.b2_batched = 0;
       c.c_sz = R * (int64_t)u.cout; c.c_sm = u.cout;
       if (pairs) {
+        if (u.cout <= 64 && B >= 2) {
+          // narrow layers are bound by the image tile's shared-memory reads: the first term (shared image x per-probe kernels)
+          // runs with 128 / cout probes folded into one tile -> raw, the second term adds it in its BatchNorm epilogue
+          ConvTcProblem f = c;
+          f.A2 = ConvTcImage(); f.B2 = TcOperand();
+          f.fold_probes = 1;
+          f.C_out = w.raw;
+          rc = conv_tc(f, st);
+          if (rc) return rc;
+          c.A1 = c.A2; c.B1 = c.B2; c.b1_batched = 0;
+          c.A2 = ConvTcImage(); c.B2 = TcOperand();
+          c.bn.pre = w.raw;
+        }
         c.C_out = w.slot[u.dst]; c.C_lo = w.slot_lo[u.dst];
         c.bn.on = 1; c.bn.g = u.g; c.bn.xhat = u.xhat; c.bn.mask = u.mask;
         c.bn.dscale = V + u.scale_off; c.bn.dbeta = V + u.beta_off; c.bn.pstride = m->D;

@@ -515,7 +515,7 @@ def test_conv_tensor_core_selftest():
     shapes = [(4, 32, 32, 32, 32, 3, 1, 2), (3, 16, 16, 64, 64, 3, 1, 2), (5, 8, 8, 128, 128, 3, 1, 3), (4, 16, 16, 32, 64, 1, 1, 2),
               (2, 32, 32, 64, 32, 3, 1, 1), (7, 8, 8, 32, 32, 3, 1, 2), (40, 16, 16, 64, 64, 3, 1, 4),
               (3, 32, 32, 32, 64, 3, 2, 2), (5, 16, 16, 64, 128, 3, 2, 2), (3, 32, 32, 32, 64, 1, 2, 2), (5, 16, 16, 64, 128, 1, 2, 3)]
-    for role in (0, 1, 2):
+    for role in (0, 1, 2, 3):
         for (n, H, W, ci, co, k, sd, b) in shapes:
             err, t1, t2 = C.c_float(-1), C.c_float(0), C.c_float(0)
             _cabi.check(L.lip_selftest_conv_tc(role, n, H, W, ci, co, k, sd, b, 0, C.byref(err), C.byref(t1), C.byref(t2), None),

@@ -11,6 +11,7 @@ L = _cabi.lib()
 torch.cuda.init()
 torch.zeros(1, device="cuda")
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+only_big = len(sys.argv) > 2 and sys.argv[2] == "big"
 # (imgs, H, W, cin, cout, ksz, stride, batch)
 shapes = [(4, 32, 32, 32, 32, 3, 1, 2), (3, 16, 16, 64, 64, 3, 1, 2), (5, 8, 8, 128, 128, 3, 1, 3), (4, 16, 16, 32, 64, 1, 1, 2),
           (2, 32, 32, 64, 32, 3, 1, 1), (7, 8, 8, 32, 32, 3, 1, 2), (3, 32, 32, 32, 64, 3, 2, 2), (5, 16, 16, 64, 128, 3, 2, 2),
@@ -18,8 +19,10 @@ shapes = [(4, 32, 32, 32, 32, 3, 1, 2), (3, 16, 16, 64, 64, 3, 1, 2), (5, 8, 8, 
 if iters > 0:
     shapes += [(100, 32, 32, 32, 32, 3, 1, 32), (100, 16, 16, 64, 64, 3, 1, 32), (100, 8, 8, 128, 128, 3, 1, 32),
                (100, 32, 32, 32, 64, 3, 2, 32), (100, 16, 16, 64, 128, 3, 2, 32)]
+if only_big:
+    shapes = [sh for sh in shapes if sh[0] == 100]
 ok = True
-for role in (0, 1, 2):
+for role in (0, 1, 2, 3):
     for (n, H, W, ci, co, k, sd, b) in shapes:
         err, t1, t2 = C.c_float(-1), C.c_float(0), C.c_float(0)
         rc = L.lip_selftest_conv_tc(role, n, H, W, ci, co, k, sd, b, iters, C.byref(err), C.byref(t1), C.byref(t2), None)
