@@ -352,6 +352,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mA1h, const __grid_constant__
             if (h * HC + cc * 32 < NB && n0 + h * HC + cc * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + cc * 32));
         }
       }
+      if (EPI == 1) {
+        // same for the BatchNorm-JVP epilogue's operands (xhat, mask, first-term sum, skip pair)
+        const int row = m0 + q * 32 + lane;
+        if (row < p.M) {
+          const long long i0 = (long long)row * p.c_sm + n0 + h * HC, zi = (long long)z * p.c_sz + i0;
+#pragma unroll
+          for (int cc = 0; cc < HC / 32; ++cc) {
+            if (h * HC + cc * 32 < NB && n0 + h * HC + cc * 32 < p.N) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(bn.xhat + i0 + cc * 32));
+              if (bn.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(bn.mask + i0 + cc * 32));
+              if (bn.pre) asm volatile("prefetch.global.L2 [%0];" ::"l"(bn.pre + zi + cc * 32));
+              if (bn.skip_hi) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(bn.skip_hi + zi + cc * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(bn.skip_lo + zi + cc * 32));
+              }
+            }
+          }
+        }
+      }
       for (int c = 0; c < nchunks; ++c, ++ck) {
         const uint32_t buf = ck & 1, cph = (ck >> 1) & 1;
         mbar_wait(tfull_bar(buf), cph);

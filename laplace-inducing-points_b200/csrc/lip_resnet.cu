@@ -93,47 +93,68 @@ __global__ void bn_jvp_kernel(const float* __restrict__ dH, const float* __restr
   }
 }
 
-// Dy = Dout * mask;  cot_skip (+)= Dy;  Dh = g[c] * Dy
-__global__ void bn_vjp_kernel(const float* __restrict__ dout, const float* __restrict__ mask, const float* __restrict__ g,
-                              float* __restrict__ dh, float* __restrict__ dh_lo, float* cot_skip, int skip_accumulate,
-                              long long total, long long per_z, int C) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long i = idx % per_z;
-    const int c = (int)(i % C);
-    float dy = dout[idx];
-    if (mask) dy *= __ldg(mask + i);
-    if (cot_skip) cot_skip[idx] = skip_accumulate ? cot_skip[idx] + dy : dy;
-    const float v = g[c] * dy;
-    if (dh_lo) {               // TF32 (hi, lo) pair for the tcgen05 conv GEMMs
-      const float hh = tf32_round(v);
-      dh[idx] = hh;
-      dh_lo[idx] = tf32_round(v - hh);
-    } else {
-      dh[idx] = v;
-    }
-  }
-}
-
-// BatchNorm parameter gradients, two stages (deterministic, no atomics).  Stage 1: grid (chunks, probes), blockDim.x a multiple
-// of C so that every thread sees one column of the flat [R * C] arrays; each CTA reduces its slice of rows:
-//   part[b][chunk][0][c] = sum_r Dout*mask,   part[b][chunk][1][c] = sum_r Dout*mask*xhat
-__global__ void bn_param_grad_partial_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
-                                             const float* __restrict__ xhat, long long per_z, int C, float* __restrict__ part) {
+// BatchNorm backward of one unit in ONE pass over Dout (deterministic, no atomics).  Grid (chunks, probes), blockDim.x a multiple
+// of C so that every thread sees one column of the flat [R * C] arrays; each CTA owns a slice of rows:
+//   Dy = Dout * mask;   cot_skip (+)= Dy;   Dh = g[c] * Dy  (fp32, or a TF32 (hi, lo) pair for the tcgen05 conv GEMMs)
+//   part[b][chunk][0][c] = sum_r Dy,   part[b][chunk][1][c] = sum_r Dy * xhat       (stage 1 of the parameter gradients)
+__global__ void bn_backward_kernel(const float* __restrict__ dout, const float* __restrict__ mask, const float* __restrict__ xhat,
+                                   const float* __restrict__ g, float* __restrict__ dh, float* __restrict__ dh_lo, float* cot_skip,
+                                   long long per_z, int C, float* __restrict__ part) {
   extern __shared__ float sm[];
   float* s1 = sm;
   float* s2 = sm + blockDim.x;
   const long long b = blockIdx.y;
   const int nch = gridDim.x;
   const float* d = dout + b * per_z;
+  float* oh = dh + b * per_z;
+  float* ol = dh_lo ? dh_lo + b * per_z : nullptr;
+  float* os = cot_skip ? cot_skip + b * per_z : nullptr;
   // slices are multiples of blockDim.x (itself a multiple of C): the thread <-> column mapping is the same in every slice
   const long long per_chunk = ((per_z + nch - 1) / nch + blockDim.x - 1) / blockDim.x * blockDim.x;
   const long long lo = blockIdx.x * per_chunk, hi = lo + per_chunk < per_z ? lo + per_chunk : per_z;
+  const float gc = g[threadIdx.x % C];
   float a1 = 0.f, a2 = 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+  constexpr int U = 4;
+  long long i = lo + threadIdx.x;
+  for (; i + (U - 1) * (long long)blockDim.x < hi; i += U * (long long)blockDim.x) {
+    float dy[U], xh[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long j = i + u * (long long)blockDim.x;
+      dy[u] = __ldg(d + j);
+      if (mask) dy[u] *= __ldg(mask + j);
+      xh[u] = __ldg(xhat + j);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long j = i + u * (long long)blockDim.x;
+      a1 += dy[u];
+      a2 = fmaf(dy[u], xh[u], a2);
+      if (os) os[j] = dy[u];
+      const float v = gc * dy[u];
+      if (ol) {
+        const float hh = tf32_round(v);
+        oh[j] = hh;
+        ol[j] = tf32_round(v - hh);
+      } else {
+        oh[j] = v;
+      }
+    }
+  }
+  for (; i < hi; i += blockDim.x) {
     float dy = __ldg(d + i);
     if (mask) dy *= __ldg(mask + i);
     a1 += dy;
     a2 = fmaf(dy, __ldg(xhat + i), a2);
+    if (os) os[i] = dy;
+    const float v = gc * dy;
+    if (ol) {
+      const float hh = tf32_round(v);
+      oh[i] = hh;
+      ol[i] = tf32_round(v - hh);
+    } else {
+      oh[i] = v;
+    }
   }
   s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
   __syncthreads();
@@ -394,25 +415,25 @@ int rn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const RnWs& w, float*
     const int64_t R = m->M * u.P(), Kc = u.Kc();
     const long long per_z = R * (long long)u.cout, total = per_z * B;
     const float* dout = w.slot[u.dst];
-    {  // BatchNorm parameter gradients (partials land in the split-K scratch, which the kernel-gradient GEMM reuses afterwards)
+    {  // BatchNorm backward in one pass: Dy -> skip cotangent (first contribution to that slot: plain store), Dh = g * Dy, and
+       // the parameter-gradient partials (they land in the split-K scratch, which the kernel-gradient GEMM reuses afterwards)
       const int threads = u.cout * (512 / u.cout > 0 ? 512 / u.cout : 1);
-      int nch = (int)(per_z / (threads * 64));
-      if (nch > 64) nch = 64;
+      int nch = (int)(per_z / (threads * 16));
+      if (nch > 128) nch = 128;
       const long long cap = (long long)(col_elems / ((size_t)B * 2 * u.cout));
       if (nch > cap) nch = (int)cap;
       if (nch < 1) nch = 1;
       dim3 grid((unsigned)nch, (unsigned)B);
-      bn_param_grad_partial_kernel<<<grid, threads, 2 * threads * sizeof(float), st>>>(dout, u.mask, u.xhat, per_z, u.cout, w.col);
+      bn_backward_kernel<<<grid, threads, 2 * threads * sizeof(float), st>>>(dout, u.mask, u.xhat, u.g, w.raw,
+                                                                            u.tc ? w.raw_lo : nullptr,
+                                                                            u.skip >= 0 ? w.slot[u.skip] : nullptr, per_z, u.cout,
+                                                                            w.col);
       LIP_LAUNCH_CHECK();
       bn_param_grad_reduce_kernel<<<(unsigned)B, u.cout <= 32 ? 32 : (u.cout + 31) / 32 * 32, 0, st>>>(
           w.col, nch, u.cout, out + u.beta_off, out + u.scale_off, m->D, scale, add ? add + u.beta_off : nullptr,
           add ? add + u.scale_off : nullptr, m->D, add_scale);
       LIP_LAUNCH_CHECK();
     }
-    // Dy -> skip cotangent (first contribution to that slot: plain store), Dh = g * Dy
-    bn_vjp_kernel<<<ew_grid(total), 256, 0, st>>>(dout, u.mask, u.g, w.raw, u.tc ? w.raw_lo : nullptr,
-                                                  u.skip >= 0 ? w.slot[u.skip] : nullptr, 0, total, per_z, u.cout);
-    LIP_LAUNCH_CHECK();
     if (u.tc) {
       ConvWgradTcProblem c;   // kernel gradient [Kc x cout] = patches(X)^T . Dh on the tensor cores (split-K)
       c.imgs = m->M; c.batch = B; c.H = u.Hi; c.W = u.Wi; c.C = u.cin; c.N = u.cout; c.kh = u.kh; c.kw = u.kw; c.pad = u.pad_h;
