@@ -141,6 +141,30 @@ int lip_gram_wtw(lip_model* m, float* G, float scale, int64_t block,
                  void* workspace, size_t workspace_bytes, lip_stream_t stream);
 size_t lip_gram_workspace_bytes(const lip_model* m, int64_t block);
 
+/* Cross Gram  Gt = scale_x * scale_z * (W_x^T W_z)^T  [d_z, d_x] row-major (row j = W_x^T W_z e_j), d_x = M_x*K, d_z = M_z*K:
+ * the same layer program bound at two point sets (mx at X, mz at Z; both handles share theta).  Replaces build_WTWz
+ * (src/ggn.py:233-272), whose result [d_x, d_z] is the transpose view of Gt.  The workspace must satisfy
+ * lip_gram_cross_workspace_bytes. */
+int lip_gram_cross(lip_model* mx, lip_model* mz, float* Gt, float scale_x, float scale_z, int64_t block,
+                   void* workspace, size_t workspace_bytes, lip_stream_t stream);
+size_t lip_gram_cross_workspace_bytes(const lip_model* mx, const lip_model* mz, int64_t block);
+
+/* ---- gradients with respect to the bound points Z ---------------------------------------------
+ * The reference obtains dObjective/dZ by jax.value_and_grad THROUGH ggn_vp / Wfun / WTfun (src/train_inducing.py:195-232,
+ * src/ggn.py:9-146).  These are the VJP-with-respect-to-Z rules a jax.custom_vjp around the entry points above needs
+ * (the rule with respect to the vector argument is the operator itself / its adjoint).  With probes b < B, points i < M:
+ *   LIP_ZGRAD_GGN : d/dZ sum_b X1[b]^T ( scale * sum_i J_i^T H_i J_i X2[b] )          X1 = cotangent [B,D], X2 = v [B,D]
+ *   LIP_ZGRAD_WT  : d/dZ sum_b sum_i X2[b,i] . ( scale * L_i^T J_i X1[b] )            X1 = v [B,D], X2 = cotangent [B,M,K]
+ *   LIP_ZGRAD_W   : d/dZ sum_b X1[b]^T ( scale * sum_i J_i^T L_i X2[b,i] )            X1 = cotangent [B,D], X2 = U [B,M,K]
+ *   LIP_ZGRAD_JVP : d/dZ sum_b sum_i X2[b,i] . ( scale * J_i X1[b] )                  X1 = v [B,D], X2 = cotangent [B,M,K]
+ * `scale` has the meaning of lip_ggn_vp's recal / lip_w(t)_apply's scale with factor = SQRT (NONE for LIP_ZGRAD_JVP).
+ * out: [M, in] (per_probe = 0, summed over probes: what differentiating a vmapped closure yields) or [B, M, in] (per_probe = 1).
+ * Dense programs (models M1 / M2) only; conv programs return LIP_ERR_UNSUPPORTED. */
+typedef enum { LIP_ZGRAD_GGN = 0, LIP_ZGRAD_WT = 1, LIP_ZGRAD_W = 2, LIP_ZGRAD_JVP = 3 } lip_zgrad_mode;
+int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, float* out, int64_t B, float scale,
+              int32_t per_probe, void* workspace, size_t workspace_bytes, lip_stream_t stream);
+size_t lip_zgrad_workspace_bytes(const lip_model* m, int32_t mode, int64_t B);
+
 /* ---- vector stage (CG / Lanczos / GKL building blocks; all batched over B independent columns) --------
  * Vectors are [B, n] row-major.  Scalars stay on the device (no host readback). */
 

@@ -15,6 +15,7 @@ OP_CONV2D, OP_AVGPOOL2, OP_ZEROPAD, OP_FLATTEN, OP_INPUT = 4, 5, 6, 7, 8
 OP_BATCHNORM, OP_RES_SAVE, OP_RES_CONV2D, OP_RES_BATCHNORM, OP_RES_ADD, OP_GLOBAL_MEAN = 9, 10, 11, 12, 13, 14
 REGRESSOR, CLASSIFIER = 0, 1
 FACTOR_NONE, FACTOR_SQRT = 0, 1
+ZGRAD_GGN, ZGRAD_WT, ZGRAD_W, ZGRAD_JVP = 0, 1, 2, 3
 FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY = 0, 1, 2, 3
 
 
@@ -48,6 +49,10 @@ SIGNATURES = {
     "lip_w_apply": (C.c_int, [_P, _P, _P, _I64, _F, _I32, _P, _F, _P, _SZ, _P]),
     "lip_gram_wtw": (C.c_int, [_P, _P, _F, _I64, _P, _SZ, _P]),
     "lip_gram_workspace_bytes": (_SZ, [_P, _I64]),
+    "lip_gram_cross": (C.c_int, [_P, _P, _P, _F, _F, _I64, _P, _SZ, _P]),
+    "lip_gram_cross_workspace_bytes": (_SZ, [_P, _P, _I64]),
+    "lip_zgrad": (C.c_int, [_P, _I32, _P, _P, _P, _I64, _F, _I32, _P, _SZ, _P]),
+    "lip_zgrad_workspace_bytes": (_SZ, [_P, _I32, _I64]),
     "lip_dot_scratch_bytes": (_SZ, [_I64, _I64]),
     "lip_dot": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
     "lip_axpby": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),

@@ -355,3 +355,41 @@ class BoundModel:
         ws, nb = self._ws.get(need)
         cabi.check(cabi.lib().lip_gram_wtw(self._h, ptr(G), scale, block, ws, nb, stream()), "lip_gram_wtw")
         return G
+
+    def gram_cross(self, other: "BoundModel", scale_self: float = 1.0, scale_other: float = 1.0, block: int = 256) -> torch.Tensor:
+        """W_self^T W_other as a [d_self, d_other] view (lip_gram_cross; build_WTWz of ggn.py:233-272)."""
+        d_o = other.M * other.K
+        d_s = self.M * self.K
+        block = max(1, min(int(block), d_o))
+        Gt = torch.empty(d_o, d_s, device=self.device, dtype=torch.float32)
+        need = cabi.lib().lip_gram_cross_workspace_bytes(self._h, other._h, block)
+        ws, nb = self._ws.get(need)
+        cabi.check(cabi.lib().lip_gram_cross(self._h, other._h, ptr(Gt), scale_self, scale_other, block, ws, nb, stream()),
+                   "lip_gram_cross")
+        return Gt.T
+
+    def zgrad(self, mode: int, X1: torch.Tensor, X2: torch.Tensor, scale: float = 1.0, per_probe: bool = False) -> torch.Tensor:
+        """d/dZ of <cotangent, operator(vector)> (lip_zgrad, include/lip_b200.h): the VJP-with-respect-to-Z rule of
+        ggn_vp / WTfun / Wfun / the plain batched JVP.  Returns [M, in] (summed over probes) or [B, M, in]."""
+        X1 = dev_f32(X1, self.device)
+        X2 = dev_f32(X2, self.device)
+        self._check_last(X1, self.D, "parameter-space vector")
+        X1b = X1.reshape(-1, self.D)
+        B = X1b.shape[0]
+        d = self.M * self.K
+        if mode == cabi.ZGRAD_GGN:
+            self._check_last(X2, self.D, "parameter-space vector")
+            X2b = X2.reshape(-1, self.D)
+        else:
+            if X2.numel() != B * d:
+                raise ValueError(f"output-space block: {tuple(X2.shape)} does not hold {B} x (M, K) = ({self.M}, {self.K}) entries")
+            X2b = X2.reshape(B, d)
+        if X2b.shape[0] != B:
+            raise ValueError(f"zgrad: {B} cotangents against {X2b.shape[0]} vectors")
+        in_features = self.Z.shape[1]
+        out = torch.empty((B, self.M, in_features) if per_probe else (self.M, in_features), device=self.device, dtype=torch.float32)
+        need = cabi.lib().lip_zgrad_workspace_bytes(self._h, mode, B)
+        ws, nb = self._ws.get(need)
+        cabi.check(cabi.lib().lip_zgrad(self._h, mode, ptr(X1b), ptr(X2b), ptr(out), B, scale, 1 if per_probe else 0, ws, nb,
+                                        stream()), "lip_zgrad")
+        return out

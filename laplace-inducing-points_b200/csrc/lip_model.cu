@@ -819,4 +819,48 @@ int lip_gram_wtw(lip_model* m, float* G, float scale, int64_t block, void* works
   return LIP_OK;
 }
 
+size_t lip_gram_cross_workspace_bytes(const lip_model* mx, const lip_model* mz, int64_t block) {
+  if (!mx || !mz || !mx->bound || !mz->bound || block <= 0) return 0;
+  auto inner = [&](const lip_model* m) {
+    return m->is_resnet ? resnet_ws_bytes(m, block) : (m->is_cnn ? cnn_ws_bytes(m, block) : ws_bytes(m, block));
+  };
+  size_t in_x = inner(mx), in_z = inner(mz);
+  size_t dz = (size_t)mz->M * mz->K;
+  return (in_x > in_z ? in_x : in_z) + align_up(sizeof(float) * (size_t)block * dz, 256) +
+         align_up(sizeof(float) * (size_t)block * (size_t)mz->D, 256) + 512;
+}
+
+int lip_gram_cross(lip_model* mx, lip_model* mz, float* Gt, float scale_x, float scale_z, int64_t block, void* workspace,
+                   size_t workspace_bytes, lip_stream_t stream) {
+  LIP_REQUIRE(mx && mz && Gt && block > 0, "lip_gram_cross: null argument or block <= 0");
+  if (!mx->bound || !mz->bound) { set_error("lip_gram_cross: model not bound"); return LIP_ERR_NOT_BOUND; }
+  LIP_REQUIRE(mx->D == mz->D && mx->K == mz->K && mx->model_type == mz->model_type,
+              "lip_gram_cross: the two handles must hold the same layer program (D %lld vs %lld, K %d vs %d)",
+              (long long)mx->D, (long long)mz->D, mx->K, mz->K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t dz = mz->M * mz->K, dx = mx->M * mx->K;
+  size_t need = lip_gram_cross_workspace_bytes(mx, mz, block);
+  if (workspace_bytes < need || !workspace) {
+    set_error("lip_gram_cross: workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    return LIP_ERR_WORKSPACE;
+  }
+  uintptr_t base = align_up((uintptr_t)workspace, 256);
+  float* U = (float*)base;
+  base += align_up(sizeof(float) * (size_t)block * dz, 256);
+  float* T = (float*)base;
+  base += align_up(sizeof(float) * (size_t)block * (size_t)mz->D, 256);
+  void* inner = (void*)base;
+  size_t inner_bytes = workspace_bytes - (base - (uintptr_t)workspace);
+  for (int64_t start = 0; start < dz; start += block) {
+    int64_t blk = dz - start < block ? dz - start : block;
+    onehot_rows_kernel<<<(unsigned)ceil_div(blk * dz, 256), 256, 0, st>>>(U, dz, start, blk);
+    LIP_LAUNCH_CHECK();
+    int rc = lip_w_apply(mz, U, T, blk, scale_z, LIP_FACTOR_SQRT, nullptr, 0.f, inner, inner_bytes, stream);
+    if (rc) return rc;
+    rc = lip_wt_apply(mx, T, Gt + start * dx, blk, scale_x, LIP_FACTOR_SQRT, inner, inner_bytes, stream);
+    if (rc) return rc;
+  }
+  return LIP_OK;
+}
+
 }  // extern "C"

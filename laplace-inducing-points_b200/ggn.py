@@ -168,8 +168,16 @@ def compute_W_vps(state, Z, model_type, full_set_size=None, blockwise=False, *, 
             single = True
         return bm.w(U, scale=recal, factor=cabi.FACTOR_SQRT, batched=not single)
 
-    _batched(WTfun, bm, _lip_kind="WT", _lip_scale=recal, _lip_transpose=Wfun)
-    _batched(Wfun, bm, _lip_kind="W", _lip_scale=recal, _lip_transpose=WTfun)
+    def WT_zgrad(Ybar, v, per_probe=False):
+        """d/dZ of <Ybar, WTfun(v)> (the VJP-with-respect-to-Z rule of WTfun)."""
+        return bm.zgrad(cabi.ZGRAD_WT, v, Ybar, scale=recal, per_probe=per_probe)
+
+    def W_zgrad(ubar, U, per_probe=False):
+        """d/dZ of <ubar, Wfun(U)>."""
+        return bm.zgrad(cabi.ZGRAD_W, ubar, U, scale=recal, per_probe=per_probe)
+
+    _batched(WTfun, bm, _lip_kind="WT", _lip_scale=recal, _lip_transpose=Wfun, zgrad=WT_zgrad)
+    _batched(Wfun, bm, _lip_kind="W", _lip_scale=recal, _lip_transpose=WTfun, zgrad=W_zgrad)
 
     if blockwise:  # ggn.py:79-82 — per-point closures (tests / dead alternating-projection stub only)
         def W_per_point(i, U_i):
@@ -206,7 +214,12 @@ def compute_ggn_vp(state, Z, model_type, full_set_size=None, *, tensor_path=None
     def ggn_vp(v):
         return bm.ggn_vp(v, recal, 0.0)
 
-    fn = _batched(ggn_vp, bm, _lip_kind="GGN", _lip_recal=recal, _lip_alpha=0.0, _lip_transpose=ggn_vp)
+    def ggn_vp_zgrad(ubar, v, per_probe=False):
+        """d/dZ of <ubar, ggn_vp(v)>: what jax.grad through the reference's ggn_vp yields for Z (train_inducing.py:195-232);
+        with ubar = v it is the gradient of the quadratic form v^T GGN(Z) v."""
+        return bm.zgrad(cabi.ZGRAD_GGN, ubar, v, scale=recal, per_probe=per_probe)
+
+    fn = _batched(ggn_vp, bm, _lip_kind="GGN", _lip_recal=recal, _lip_alpha=0.0, _lip_transpose=ggn_vp, zgrad=ggn_vp_zgrad)
     if shard_points:
         fn = _dist.point_sharded(fn)
         fn._lip_recal, fn._lip_alpha, fn._lip_transpose = recal, 0.0, fn
@@ -246,8 +259,13 @@ def build_WTW(W, WT, inner_shape, d, *, dtype=torch.float32, block=64):
 
 
 def build_WTWz(WT, W_z, inner_shape_z, *, d, dtype=torch.float32, block=64):
-    """ggn.py:233-272 (cross-Gram W^T W_z, used only by the dead '_scalable_exact' objective)."""
+    """ggn.py:233-272: cross-Gram W^T W_z [d, d_z] (the '_scalable_exact' objective, train_inducing.py:26-84).
+    Native lip_gram_cross when both closures come from this module, else the one-hot blocks go through the closures."""
     d_z = int(np.prod(inner_shape_z))
+    bx, bz = getattr(WT, "_lip_model", None), getattr(W_z, "_lip_model", None)
+    if bx is not None and bz is not None and getattr(WT, "_lip_kind", "") == "WT" and getattr(W_z, "_lip_kind", "") == "W" \
+            and d == bx.M * bx.K and d_z == bz.M * bz.K:
+        return bx.gram_cross(bz, WT._lip_scale, W_z._lip_scale, block=max(int(block), 256))     # native lip_gram_cross
     dev = torch.device("cuda", torch.cuda.current_device())
     G = torch.zeros(d, d_z, device=dev)
     eye = torch.eye(d_z, device=dev)

@@ -29,7 +29,9 @@ def compute_curvature_approx(map_state, Z, model_type, alpha, full_set_size=None
     def curvature_vp(v):
         return bm.ggn_vp(v, recal, alpha)
 
-    return _batched(curvature_vp, bm, _lip_kind="GGN", _lip_recal=recal, _lip_alpha=alpha, _lip_transpose=curvature_vp)
+    # d/dZ <ubar, curvature_vp(v)>: the alpha v term does not depend on Z
+    return _batched(curvature_vp, bm, _lip_kind="GGN", _lip_recal=recal, _lip_alpha=alpha, _lip_transpose=curvature_vp,
+                    zgrad=ggn_vp.zgrad)
 
 
 def predict_lla_scalable(map_state, Xnew, Z, model_type, alpha, key=None, full_set_size=None, num_samples=1, *,

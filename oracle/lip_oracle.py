@@ -683,3 +683,104 @@ def predict_lla_scalable(map_state, Xnew, Z, model_type, alpha, Eps, full_set_si
     fmu = f(th).detach().numpy()
     dys = np.stack([torch.func.jvp(f, (th,), (_t(w),))[1].detach().numpy() for w in w_samples])
     return fmu[None] + dys
+
+
+# ======================================================================================
+# gradients with respect to the inducing points Z
+# ======================================================================================
+# The reference obtains them with jax.value_and_grad THROUGH the closures of src/ggn.py (train_inducing.py:195-232).
+# Restated literally: the operators below are written in differentiable torch (float64) exactly as ggn.py composes
+# them (jvp -> output-space factor -> vjp) and torch.func.grad differentiates the scalar <cotangent, operator(vector)>
+# with respect to Z.  No hand-derived adjoint appears here, so this checks the CUDA path's hand-written reverse pass.
+def _softmax_t(f):
+    return torch.softmax(f, dim=-1)
+
+
+def _ggn_vp_t(state, Zt, th, model_type, recal, v):
+    """ggn.py:133-144 batched over points, differentiable in Zt."""
+    f = lambda p: state.f_theta(p, Zt)
+    fz, jv = torch.func.jvp(f, (th,), (v,))
+    if model_type == "classifier":
+        p = _softmax_t(fz)
+        hv = p * jv - p * (p * jv).sum(-1, keepdim=True)      # ggn.py:125-131
+    else:
+        hv = jv
+    _, vjp_fn = torch.func.vjp(f, th)
+    return recal * vjp_fn(hv)[0]
+
+
+def _wt_t(state, Zt, th, model_type, recal, lv, v):
+    """ggn.py:54-62,84-85 + sqrt_Hi_apply (ggn.py:29-39)."""
+    f = lambda p: state.f_theta(p, Zt)
+    fz, jv = torch.func.jvp(f, (th,), (v,))
+    if model_type == "regressor":
+        return recal * math.sqrt(math.exp(-lv)) * jv
+    p = _softmax_t(fz)
+    s = torch.sqrt(p)
+    return recal * (s * jv - (p * jv).sum(-1, keepdim=True) * s)
+
+
+def _w_t(state, Zt, th, model_type, recal, lv, U):
+    """ggn.py:64-76,87-91 + sqrt_Hi_apply_T (ggn.py:16-27)."""
+    f = lambda p: state.f_theta(p, Zt)
+    fz, vjp_fn = torch.func.vjp(f, th)
+    if model_type == "regressor":
+        h = math.sqrt(math.exp(-lv)) * U.reshape(fz.shape)
+    else:
+        p = _softmax_t(fz)
+        s = torch.sqrt(p)
+        h = s * U - (s * U).sum(-1, keepdim=True) * p
+    return recal * vjp_fn(h)[0]
+
+
+def ggn_vp_zgrad(state: OracleState, Z, model_type, Ubar, V, full_set_size=None, per_probe=False) -> np.ndarray:
+    """d/dZ sum_b <Ubar[b], ggn_vp_Z(V[b])>  -> [M, ...] (or [B, M, ...])."""
+    theta, _ = state.flat()
+    th = _t(theta)
+    Zt = _t(Z)
+    M = Zt.shape[0]
+    recal = (full_set_size or M) / M
+    if model_type == "regressor":
+        recal *= math.exp(-state.logvar)
+    Ub, Vb = _t(Ubar).reshape(-1, th.numel()), _t(V).reshape(-1, th.numel())
+    grads = []
+    for u, v in zip(Ub, Vb):
+        grads.append(torch.func.grad(lambda Zv: (u * _ggn_vp_t(state, Zv, th, model_type, recal, v)).sum())(Zt).numpy())
+    g = np.stack(grads)
+    return g if per_probe else g.sum(0)
+
+
+def W_vps_zgrad(state: OracleState, Z, model_type, full_set_size=None):
+    """Returns (W_zgrad(ubar [B,D], U [B,M,K]), WT_zgrad(Ybar [B,M,K], v [B,D])): d/dZ of <ubar, Wfun(U)> and <Ybar, WTfun(v)>."""
+    theta, _ = state.flat()
+    th = _t(theta)
+    Zt = _t(Z)
+    M = Zt.shape[0]
+    recal = math.sqrt((full_set_size or M) / M)
+    lv = state.logvar
+    D = th.numel()
+
+    def W_zgrad(ubar, U):
+        ub = _t(ubar).reshape(-1, D)
+        Ub = _t(U).reshape(ub.shape[0], M, -1)
+        return sum(torch.func.grad(lambda Zv: (u * _w_t(state, Zv, th, model_type, recal, lv, Uu)).sum())(Zt).numpy()
+                   for u, Uu in zip(ub, Ub))
+
+    def WT_zgrad(Ybar, v):
+        vb = _t(v).reshape(-1, D)
+        Yb = _t(Ybar).reshape(vb.shape[0], M, -1)
+        return sum(torch.func.grad(lambda Zv: (Y * _wt_t(state, Zv, th, model_type, recal, lv, vv)).sum())(Zt).numpy()
+                   for Y, vv in zip(Yb, vb))
+
+    return W_zgrad, WT_zgrad
+
+
+def jvp_zgrad(state: OracleState, Z, Cbar, V) -> np.ndarray:
+    """d/dZ sum_b <Cbar[b], J_Z V[b]>   (the plain batched JVP of lla.py:153)."""
+    theta, _ = state.flat()
+    th = _t(theta)
+    Zt = _t(Z)
+    vb = _t(V).reshape(-1, th.numel())
+    Cb = _t(Cbar).reshape(vb.shape[0], Zt.shape[0], -1)
+    return sum(torch.func.grad(lambda Zv: (Cm * torch.func.jvp(lambda p: state.f_theta(p, Zv), (th,), (vv,))[1]).sum())(Zt).numpy()
+               for Cm, vv in zip(Cb, vb))
