@@ -1,9 +1,16 @@
-"""Forward value of the reference's scalable KL objective on the B200 path (/root/reference/src/train_inducing.py:87-173).
+"""The reference's inducing-point objectives and their gradients with respect to Z on the B200 path
+(/root/reference/src/train_inducing.py).
 
-This is the production CALLER of the hot path (SURVEY §8f row f2): every heavy step is one of the package's operators —
-curvature_vp over the data minibatch, W_z / W_z^T, the dense Gram, Hutch++ v2, the GKL logdet.  Only the forward value is
-provided: differentiating it w.r.t. Z (train_inducing.py:196, row f1) is not built, so this is an evaluation / monitoring
-entry point, not a training step.
+This is the production CALLER of the hot path (SURVEY §8f rows f1-f3): every heavy step is one of the package's operators —
+curvature_vp over the data minibatch, W_z / W_z^T, the dense / cross Gram, Hutch++ v2, the GKL logdet — and the Z-gradients
+are assembled from lip_zgrad (the VJP-with-respect-to-Z rules of those operators; csrc/lip_zgrad.cu).
+
+  alternative_objective_scalable        :87-173   forward value (Hutch++ v2 + GKL logdet)
+  alternative_objective_scalable_exact  :26-84    value;  variational_grad_scalable_exact -> (value, dZ)   [deterministic]
+  alternative_objective_dense           :175-192  value;  variational_grad_dense          -> (value, dZ)   [deterministic]
+  variational_grad_scalable             :195      (value, dZ) with a Hutchinson estimate of the gradient (see its docstring:
+                                                  NOT the reference's autodiff-through-the-estimators, same expectation)
+  optimize_step                         :198-232  one optimiser step on Z
 """
 from __future__ import annotations
 
@@ -13,7 +20,7 @@ import torch
 
 from . import matfree
 from ._runtime import dev_f32
-from .ggn import build_WTW, compute_W_vps
+from .ggn import build_WTW, build_WTWz, compute_W_vps
 from .lla import compute_curvature_approx
 from .stochtrace import hutchpp_v2
 from .utils import flatten_nn_params
@@ -80,3 +87,193 @@ def alternative_objective_scalable(Z, X, state, alpha, model_type, key, full_set
     problem = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(k))               # :156-157
     logdet_term = problem(bidiag_target, probes[:slq_samples], bidiag_target_T).mean()           # :159-163
     return logdet_term + trace_term
+
+
+# ============================================================================================================
+# deterministic objectives with gradients (rows f1 / f3)
+# ============================================================================================================
+def _f64(x):
+    return x.to(torch.float64)
+
+
+def _probe_block(D: int, want: int) -> int:
+    """how many [D]-vectors to push through the operators at once (bounded scratch)"""
+    return max(1, min(int(want), (1 << 28) // max(D, 1)))
+
+
+def _exact_parts(Z, X, state, alpha, model_type, full_set_size):
+    N = full_set_size
+    Zt, Xt = dev_f32(Z), dev_f32(X)
+    M, Kx = int(Zt.shape[0]), int(Xt.shape[0])
+    flat, _ = flatten_nn_params(state.params)
+    D = int(flat.numel())                                                                  # :37-39 (logvar is not in D)
+    Wz, WzT = compute_W_vps(state, Zt, model_type, full_set_size=None)                     # :48-50
+    W, WT = compute_W_vps(state, Xt, model_type, full_set_size=None)                       # :51-53
+    bz, bx = Wz._lip_model, W._lip_model
+    inner_shape = (M,) if model_type == "regressor" else (M, bz.K)
+    d_z, d = M * bz.K, Kx * bx.K
+    WzTWz = _f64(build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1))       # :60
+    WTWz = _f64(build_WTWz(WT, Wz, inner_shape, d=d, dtype=torch.float32, block=1))        # :67
+    return dict(N=N, M=M, Kx=Kx, D=D, Wz=Wz, W=W, bz=bz, bx=bx, inner_shape=inner_shape, d_z=d_z, d=d, G=WzTWz, C=WTWz,
+                beta=N / M, gamma=N / Kx, alpha=float(alpha))
+
+
+def _exact_value(p):
+    alpha, beta, gamma, G, C, d_z = p["alpha"], p["beta"], p["gamma"], p["G"], p["C"], p["d_z"]
+    eye = torch.eye(d_z, device=G.device, dtype=torch.float64)
+    logdet_term = torch.linalg.slogdet(eye + beta / alpha * G)[1] + p["D"] * math.log(alpha)    # :62-63
+    Mm = eye / beta + G / alpha                                                            # :69
+    L = torch.linalg.cholesky(Mm)                                                          # :70
+    S1 = torch.cholesky_solve(G, L)                                                        # :71
+    S2 = torch.cholesky_solve(C.T.contiguous(), L)                                         # :72
+    trace1 = torch.trace(S1)                                                               # :74
+    trace2 = (C * S2.T).sum()                                                              # :75
+    return logdet_term - trace1 / alpha - gamma / alpha ** 2 * trace2, L                   # :76-78
+
+
+def alternative_objective_scalable_exact(Z, X, state, alpha, model_type, key=None, full_set_size=None, st_samples=256,
+                                         slq_samples=2, slq_num_matvecs=None):
+    """train_inducing.py:26-84: the KL objective through the dense Grams W_z^T W_z and W^T W_z (identity of
+    src/Untitled-1.md:1-2), exact traces and slogdet.  The Grams come from lip_gram_wtw / lip_gram_cross; the d_z x d_z
+    Cholesky / slogdet are library calls in float64, as the reference hands them to jnp.linalg."""
+    return _exact_value(_exact_parts(Z, X, state, alpha, model_type, full_set_size))[0].float()
+
+
+def variational_grad_scalable_exact(Z, X, state, alpha, model_type, key=None, full_set_size=None, **_):
+    """jax.value_and_grad of alternative_objective_scalable_exact with respect to Z -> (loss, dZ).
+
+    With Mm = I/beta + G/alpha (G = W_z^T W_z, C = W^T W_z):  dL/dG = Mm^-1 G Mm^-1 / alpha^2 + gamma Mm^-1 C^T C Mm^-1 / alpha^3,
+    dL/dC = -2 gamma C Mm^-1 / alpha^2, and  dL/dZ = sum_k d/dZ < 2 W_z (dL/dG)[:, k] + W (dL/dC)[:, k],  W_z e_k >  — one
+    lip_zgrad(W mode) call per block of one-hot columns."""
+    p = _exact_parts(Z, X, state, alpha, model_type, full_set_size)
+    value, L = _exact_value(p)
+    alpha, gamma, G, C, d_z, D = p["alpha"], p["gamma"], p["G"], p["C"], p["d_z"], p["D"]
+    eye = torch.eye(d_z, device=G.device, dtype=torch.float64)
+    Minv = torch.cholesky_solve(eye, L)
+    Gbar = (Minv @ G @ Minv) / alpha ** 2 + gamma / alpha ** 3 * (Minv @ (C.T @ C) @ Minv)
+    Cbar = -2.0 * gamma / alpha ** 2 * (C @ Minv)
+    Wz, W, bz = p["Wz"], p["W"], p["bz"]
+    blk = _probe_block(D, 256)
+    dZ = torch.zeros(p["M"], bz.Z.shape[1], device=G.device, dtype=torch.float32)
+    onehot = torch.eye(d_z, device=G.device, dtype=torch.float32)
+    for k0 in range(0, d_z, blk):
+        k1 = min(d_z, k0 + blk)
+        nb = k1 - k0
+        ub = W._lip_model.w(Cbar[:, k0:k1].T.float().contiguous(), scale=W._lip_scale, batched=True)         # W Cbar[:, k]
+        ub = bz.w((2.0 * Gbar[:, k0:k1]).T.float().contiguous(), scale=Wz._lip_scale, add=ub, add_scale=1.0, batched=True)
+        dZ += Wz.zgrad(ub, onehot[k0:k1].reshape(nb, d_z))
+    return value.float(), dZ.reshape(dev_f32(Z).shape)
+
+
+def _dense_parts(Z, X, state, alpha, model_type, full_set_size):
+    from .ggn import compute_ggn_dense
+    Zt, Xt = dev_f32(Z), dev_f32(X)
+    S, flat, _ = compute_ggn_dense(state, Xt, model_type, full_set_size)                   # lla.py compute_curvature_approx_dense
+    S_z, _, _ = compute_ggn_dense(state, Zt, model_type, full_set_size)
+    D = int(flat.numel())
+    eye = torch.eye(D, device=S.device, dtype=torch.float64)
+    S = _f64(S) + alpha * eye
+    S_z = _f64(S_z) + alpha * eye
+    S_z_inv = torch.linalg.inv(S_z)                                                        # :184
+    return S, S_z_inv, D
+
+
+def alternative_objective_dense(Z, X, state, alpha, model_type, key=None, full_set_size=None):
+    """train_inducing.py:175-192: tr(S S_z^-1) - logdet(S_z^-1) with the D x D matrices materialised (toy sizes)."""
+    S, S_z_inv, _ = _dense_parts(Z, X, state, float(alpha), model_type, full_set_size)
+    return (torch.trace(S @ S_z_inv) - torch.linalg.slogdet(S_z_inv)[1]).float()
+
+
+def variational_grad_dense(Z, X, state, alpha, model_type, key=None, full_set_size=None, **_):
+    """train_inducing.py:194: jax.value_and_grad(alternative_objective_dense) -> (loss, dZ).
+    dL/dS_z = S_z^-1 - S_z^-1 S S_z^-1;  dL/dZ = sum_k d/dZ < (dL/dS_z)[:, k], GGN(Z) e_k >  (lip_zgrad, GGN mode)."""
+    from .ggn import compute_ggn_vp
+    alpha = float(alpha)
+    S, S_z_inv, D = _dense_parts(Z, X, state, alpha, model_type, full_set_size)
+    value = torch.trace(S @ S_z_inv) - torch.linalg.slogdet(S_z_inv)[1]
+    Sbar = S_z_inv - S_z_inv @ S @ S_z_inv
+    Sbar = 0.5 * (Sbar + Sbar.T)
+    Zt = dev_f32(Z)
+    vp = compute_ggn_vp(state, Zt, model_type, full_set_size)
+    eye = torch.eye(D, device=Zt.device, dtype=torch.float32)
+    blk = _probe_block(D, 512)
+    dZ = torch.zeros(Zt.shape[0], vp._lip_model.Z.shape[1], device=Zt.device, dtype=torch.float32)
+    for k0 in range(0, D, blk):
+        k1 = min(D, k0 + blk)
+        dZ += vp.zgrad(Sbar[:, k0:k1].T.float().contiguous(), eye[k0:k1])
+    return value.float(), dZ.reshape(Zt.shape)
+
+
+def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size=None, st_samples=256, slq_samples=2,
+                              slq_num_matvecs=None, *, probes=None):
+    """(loss, dZ) for the scalable objective (train_inducing.py:195).
+
+    The loss is alternative_objective_scalable (Hutch++ v2 + GKL logdet on the given probes).  The reference differentiates
+    THROUGH those estimators (QR, Golub-Kahan recurrences, SVD); here dZ is the Hutchinson estimate of the exact gradient
+        d/dZ [ tr(S_X S_Z^-1) + logdet S_Z ] = tr( (S_Z^-1 - S_Z^-1 S_X S_Z^-1) dS_Z )
+                                             ~ mean_b d/dZ < S_Z^-1 eps_b ,  GGN(Z) (eps_b - S_Z^-1 S_X eps_b) >
+    on the same Rademacher probes, with S_Z^-1 applied exactly through the Woodbury identity (:127-132): ONE lip_zgrad call.
+    Same expectation as the reference's gradient when its estimators converge, NOT the same number for a finite probe set —
+    parity is claimed for the deterministic forms above only."""
+    from .ggn import compute_ggn_vp
+    N = full_set_size
+    Zt, Xt = dev_f32(Z), dev_f32(X)
+    M = int(Zt.shape[0])
+    alpha = float(alpha)
+    flat, _ = flatten_nn_params(state.params)
+    D = int(flat.numel())
+    if probes is None:
+        probes = matfree.sampler_rademacher(torch.ones(D), num=st_samples)(key)
+    probes = dev_f32(probes)
+    loss = alternative_objective_scalable(Zt, Xt, state, alpha, model_type, key, full_set_size=N, st_samples=st_samples,
+                                          slq_samples=slq_samples, slq_num_matvecs=slq_num_matvecs, probes=probes)
+    S_vp = compute_curvature_approx(state, Xt, model_type, alpha, full_set_size=N)
+    Sz_vp = compute_curvature_approx(state, Zt, model_type, alpha, full_set_size=N)
+    Sz_inv = woodbury_inverse(state, Zt, model_type, alpha, N)
+    a = Sz_inv(probes)                                    # S_Z^-1 eps
+    b = probes - Sz_inv(S_vp(probes))                     # eps - S_Z^-1 S_X eps
+    dZ = Sz_vp.zgrad(a, b) / probes.shape[0]
+    return loss, dZ.reshape(Zt.shape)
+
+
+def woodbury_inverse(state, Z, model_type, alpha, full_set_size):
+    """S_Z^-1 v = v/alpha - alpha^-2 W_z (beta^-1 I + alpha^-1 W_z^T W_z)^-1 W_z^T v   (train_inducing.py:127-132), batched."""
+    Zt = dev_f32(Z)
+    M = int(Zt.shape[0])
+    beta = full_set_size / M
+    alpha = float(alpha)
+    Wz, WzT = compute_W_vps(state, Zt, model_type, full_set_size=None)
+    bm = Wz._lip_model
+    inner_shape = (M,) if model_type == "regressor" else (M, bm.K)
+    d_z = M * bm.K
+    D = bm.D
+    WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)
+    Kmat = torch.eye(d_z, device=WzTWz.device, dtype=torch.float64) / beta + WzTWz.double() / alpha
+    LU, piv = torch.linalg.lu_factor(Kmat)
+
+    @matfree.batched
+    def Sz_inv(V):
+        V = dev_f32(V).reshape(-1, D)
+        u = WzT(V).reshape(V.shape[0], d_z)
+        x = torch.linalg.lu_solve(LU, piv, u.double().T).T.float()
+        return bm.w(x.reshape((V.shape[0],) + inner_shape), scale=Wz._lip_scale, add=V, add_scale=-alpha,
+                    batched=True).mul_(-1.0 / alpha ** 2)
+
+    return Sz_inv
+
+
+def optimize_step(Z, X, map_model_state, alpha, opt_state, rng, zoptimizer, num_mc_samples=None, model_type="classifier",
+                  full_set_size=None, scalable=True, st_samples=256, slq_samples=2, slq_num_matvecs=None, *, exact=False):
+    """train_inducing.py:198-232: one optimiser step on Z.  `zoptimizer` follows the optax protocol the reference uses
+    (`update(grads, opt_state, params) -> (updates, new_opt_state)`, updates are ADDED: optax.apply_updates); utils.adam / utils.sgd
+    are minimal stand-ins (optax is not in this image).  scalable=False -> variational_grad_dense (:212-222);
+    scalable=True -> variational_grad_scalable (Hutchinson gradient, see there) or, with exact=True, the exact-Gram form."""
+    if not scalable:
+        loss, grads = variational_grad_dense(Z, X, map_model_state, alpha, model_type, rng, full_set_size=full_set_size)
+    elif exact:
+        loss, grads = variational_grad_scalable_exact(Z, X, map_model_state, alpha, model_type, rng, full_set_size=full_set_size)
+    else:
+        loss, grads = variational_grad_scalable(Z, X, map_model_state, alpha, model_type, rng, full_set_size=full_set_size,
+                                                st_samples=st_samples, slq_samples=slq_samples, slq_num_matvecs=slq_num_matvecs)
+    updates, new_opt_state = zoptimizer.update(grads, opt_state, dev_f32(Z))
+    return dev_f32(Z) + updates, new_opt_state, loss

@@ -48,3 +48,36 @@ def flatten_nn_params(params) -> Tuple[torch.Tensor, Callable]:
 def count_model_params(params) -> int:
     """utils.py:84"""
     return int(sum(int(np.prod(tuple(l.shape))) if hasattr(l, "shape") else 1 for _, l in _walk(dict(params))))
+
+
+# ---- minimal optax-protocol optimisers (optax is not in this image; train_inducing.optimize_step / train_alpha.update_alpha
+# accept any object with init(params) and update(grads, state, params) -> (updates, new_state); updates are added) ----
+class sgd:
+    def __init__(self, learning_rate: float):
+        self.lr = float(learning_rate)
+
+    def init(self, params):
+        return ()
+
+    def update(self, grads, state, params=None):
+        return -self.lr * grads, state
+
+
+class adam:
+    """optax.adam(lr, b1=0.9, b2=0.999, eps=1e-8) restated (bias-corrected moments)."""
+
+    def __init__(self, learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), b1, b2, eps
+
+    def init(self, params):
+        z = torch.zeros_like(torch.as_tensor(params, dtype=torch.float32))
+        return (0, z, z.clone())
+
+    def update(self, grads, state, params=None):
+        t, m, v = state
+        t = t + 1
+        m = self.b1 * m + (1 - self.b1) * grads
+        v = self.b2 * v + (1 - self.b2) * grads * grads
+        mhat = m / (1 - self.b1 ** t)
+        vhat = v / (1 - self.b2 ** t)
+        return -self.lr * mhat / (torch.sqrt(vhat) + self.eps), (t, m, v)

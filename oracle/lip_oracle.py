@@ -784,3 +784,109 @@ def jvp_zgrad(state: OracleState, Z, Cbar, V) -> np.ndarray:
     Cb = _t(Cbar).reshape(vb.shape[0], Zt.shape[0], -1)
     return sum(torch.func.grad(lambda Zv: (Cm * torch.func.jvp(lambda p: state.f_theta(p, Zv), (th,), (vv,))[1]).sum())(Zt).numpy()
                for Cm, vv in zip(Cb, vb))
+
+
+# ======================================================================================
+# deterministic objectives and their gradients with respect to Z (train_inducing.py:26-84,175-192; train_alpha.py:13-44)
+# ======================================================================================
+def _jac_t(state, Zt, th):
+    """J[i] = d f(z_i; theta) / d theta, [M, K, D], differentiable in Zt."""
+    return torch.func.jacrev(lambda p: state.f_theta(p, Zt))(th)
+
+
+def _ggn_dense_t(state, Zt, th, model_type, full_set_size):
+    """ggn.py:149-193 (compute_ggn_dense) in differentiable torch."""
+    M = Zt.shape[0]
+    recal = (full_set_size or M) / M
+    J = _jac_t(state, Zt, th)
+    if model_type == "classifier":
+        p = _softmax_t(state.f_theta(th, Zt))
+        H = torch.diag_embed(p) - p[:, :, None] * p[:, None, :]
+        return recal * torch.einsum("ikd,ikl,ile->de", J, H, J)
+    return recal * math.exp(-state.logvar) * torch.einsum("ikd,ike->de", J, J)
+
+
+def _w_dense_t(state, Zt, th, model_type):
+    """The matrix W = [J_1^T L_1 ... J_M^T L_M] in R^{D x MK} (ggn.py:79-93, full_set_size=None), differentiable in Zt."""
+    J = _jac_t(state, Zt, th)
+    M, K, D = J.shape
+    if model_type == "classifier":
+        p = _softmax_t(state.f_theta(th, Zt))
+        r = torch.sqrt(p)
+        L = torch.diag_embed(r) - p[:, :, None] * r[:, None, :]          # L u = r*u - (r.u) p   (ggn.py:23-27)
+        return torch.einsum("ikd,ikl->dil", J, L).reshape(D, M * K)
+    return math.sqrt(math.exp(-state.logvar)) * J.permute(2, 0, 1).reshape(D, M * K)
+
+
+def _objective_dense_t(state, Zt, Xt, th, alpha, model_type, full_set_size):
+    """train_inducing.py:175-192 (alternative_objective_dense)."""
+    D = th.numel()
+    eye = torch.eye(D, dtype=F64)
+    S = _ggn_dense_t(state, Xt, th, model_type, full_set_size) + alpha * eye              # lla.py compute_curvature_approx_dense
+    S_z = _ggn_dense_t(state, Zt, th, model_type, full_set_size) + alpha * eye
+    S_z_inv = torch.linalg.inv(S_z)
+    trace_term = torch.trace(S @ S_z_inv)
+    return -torch.linalg.slogdet(S_z_inv)[1] + trace_term
+
+
+def _objective_exact_t(state, Zt, Xt, th, alpha, model_type, full_set_size):
+    """train_inducing.py:26-84 (alternative_objective_scalable_exact)."""
+    N = full_set_size
+    M, Kx = Zt.shape[0], Xt.shape[0]
+    beta, gamma = N / M, N / Kx
+    D = th.numel()
+    Wz = _w_dense_t(state, Zt, th, model_type)
+    Wx = _w_dense_t(state, Xt, th, model_type)
+    WzTWz = Wz.T @ Wz                                                                     # :60
+    d_z = WzTWz.shape[0]
+    eye = torch.eye(d_z, dtype=F64)
+    logdet_term = torch.linalg.slogdet(eye + beta / alpha * WzTWz)[1] + D * math.log(alpha)   # :62-63
+    WTWz = Wx.T @ Wz                                                                      # :67
+    Mm = eye / beta + WzTWz / alpha                                                       # :69
+    L = torch.linalg.cholesky(Mm)
+    S1 = torch.cholesky_solve(WzTWz, L)                                                   # :71
+    S2 = torch.cholesky_solve(WTWz.T, L)                                                  # :72
+    trace1 = torch.trace(S1)
+    trace2 = (WTWz * S2.T).sum()                                                          # :75
+    return logdet_term - trace1 / alpha - gamma / alpha ** 2 * trace2                     # :76-78
+
+
+def _value_and_zgrad(fn, state, Z, X, alpha, model_type, full_set_size):
+    theta, _ = state.flat()
+    th = _t(theta)
+    Zt, Xt = _t(Z), _t(X)
+    g, v = torch.func.grad_and_value(lambda Zv: fn(state, Zv, Xt, th, alpha, model_type, full_set_size))(Zt)
+    return float(v), g.numpy()
+
+
+def variational_grad_dense(Z, X, state, alpha, model_type, full_set_size=None):
+    """jax.value_and_grad(alternative_objective_dense) (train_inducing.py:194) -> (loss, dLoss/dZ)."""
+    return _value_and_zgrad(_objective_dense_t, state, Z, X, alpha, model_type, full_set_size)
+
+
+def variational_grad_scalable_exact(Z, X, state, alpha, model_type, full_set_size=None):
+    """value and Z-gradient of alternative_objective_scalable_exact (train_inducing.py:26-84)."""
+    return _value_and_zgrad(_objective_exact_t, state, Z, X, alpha, model_type, full_set_size)
+
+
+def log_marginal_likelihood(alpha, X, state, model_type, full_set_size=None):
+    """train_alpha.py:13-44 -> (log p(D|alpha) up to constants, d/d log(alpha) of it) (update_alpha differentiates in log alpha)."""
+    theta, _ = state.flat()
+    th = _t(theta)
+    Xt = _t(X)
+    N = full_set_size or Xt.shape[0]
+    rescale = N / Xt.shape[0]
+    D = th.numel()
+    W = _w_dense_t(state, Xt, th, model_type).detach()
+    WTW = W.T @ W
+    d = WTW.shape[0]
+
+    def lml(log_alpha):
+        a = torch.exp(log_alpha)
+        logdet_term = torch.linalg.slogdet(torch.eye(d, dtype=F64) + rescale / a * WTW)[1] + D * torch.log(a)
+        log_prior = -0.5 * a * (th @ th) + 0.5 * D * torch.log(a)
+        return log_prior - 0.5 * logdet_term
+
+    la = torch.tensor(math.log(alpha), dtype=F64)
+    g, v = torch.func.grad_and_value(lml)(la)
+    return float(v), float(g)
