@@ -641,8 +641,11 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
       return LIP_ERR_UNSUPPORTED;
     }
     if (avail) {
+      // fewest bound points for which the 128-row MMA tiles still beat the fp32 SIMT kernels: measured 3x faster than SIMT
+      // down to M = 16 at the MNIST-MLP widths (tools/tc_small_m.py, profiles/r01_tc_small_m.txt); LIP_TC_MIN_M overrides
+      static const int64_t min_m = getenv("LIP_TC_MIN_M") ? atoll(getenv("LIP_TC_MIN_M")) : 16;
       for (int l = 0; l < nL; ++l)
-        m->tc_layer[l] = (m->L[l].in >= 64 && m->L[l].out >= 64 && M >= 64 && (m->L[l].out % 4 == 0)) ? 1 : 0;
+        m->tc_layer[l] = (m->L[l].in >= 64 && m->L[l].out >= 64 && M >= min_m && (m->L[l].out % 4 == 0)) ? 1 : 0;
       for (int l = 0; l < nL; ++l) m->tc_on = m->tc_on || m->tc_layer[l];
     }
   }

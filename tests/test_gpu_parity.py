@@ -320,12 +320,15 @@ TC_CONFIGS = {
     # name: (hidden, n_out, in_dim, M, N)
     "tc_small": ([128, 64], 10, 96, 128, 5000),
     "tc_ragged": ([200, 72, 136], 7, 100, 150, 900),
+    # fewer bound points than one 128-row MMA tile (the reference's mlp_mnist.yml trains m = 50 inducing points)
+    "tc_m50": ([256, 128, 64], 10, 784, 50, 60000),
+    "tc_m17": ([136, 72], 5, 100, 17, 300),
 }
 
 
 @pytest.mark.parametrize("name", list(TC_CONFIGS))
 def test_tensor_core_path_matches_oracle(name):
-    """The tcgen05 3xTF32 path (layers with in,out,M >= 64) against the float64 oracle and against the SIMT path."""
+    """The tcgen05 3xTF32 path (layers with in,out >= 64 and M >= 16) against the float64 oracle and against the SIMT path."""
     from lip_b200 import ggn, lla
     hidden, n_out, in_dim, M, N = TC_CONFIGS[name]
     ost, lst = make_pair("large", hidden=hidden, n_out=n_out, in_dim=in_dim, seed=77)
