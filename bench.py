@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--no-slq", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the Z-gradient / inducing-point training-step leg")
     ap.add_argument("--tensor-path", type=int, default=-1, help="-1 auto, 0 SIMT fp32, 1 tcgen05 3xTF32")
     ap.add_argument("--workload", default="mlp", choices=sorted(WORKLOADS), help="mlp = headline C3b; lenet5 = C4 conv path")
     ap.add_argument("--points", type=int, default=0, help="override the workload's number of inducing points M")
@@ -454,6 +455,42 @@ def run_b200(args):
                             "note": "re-orthogonalisation bytes only, divided by the WHOLE logdet wall time (mat-vecs, "
                                     "eigensolve and host orchestration included)"}}
 
+    # ---- gradient with respect to Z (lip_zgrad) and one inducing-point training step ----
+    train = None
+    if not args.no_train_step and world == 1 and args.workload == "mlp":
+        from lip_b200 import train_inducing, utils as lip_utils
+        nb = 64
+        Pz = (torch.randint(0, 2, (nb, D), device=dev, generator=torch.Generator(device=dev).manual_seed(5)).float() * 2 - 1)
+        cvp_z = lla.compute_curvature_approx(lst, Zd, "classifier", ALPHA, full_set_size=N_FULL, tensor_path=tp)
+        cvp_z.zgrad(Pz, Pz)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            cvp_z.zgrad(Pz, Pz)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_z = e0.elapsed_time(e1) / 3
+        # the reference's own training configuration (config/scale/mlp_mnist.yml: m = 50 inducing points, batch 256, 64 probes)
+        m_ref, k_ref = 50, 40
+        Zs = Zd[:m_ref].contiguous()
+        Xb = torch.rand(256, *Zd.shape[1:], device=dev, generator=torch.Generator(device=dev).manual_seed(6))
+        opt = lip_utils.adam(1e-3)
+        ost_z = opt.init(Zs)
+        times = []
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            Zs, ost_z, loss_z = train_inducing.optimize_step(Zs, Xb, lst, ALPHA, ost_z, it, opt, None, "classifier", full_set_size=N_FULL,
+                                                             scalable=True, st_samples=nb, slq_samples=2, slq_num_matvecs=k_ref)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        train = {"zgrad_ms": ms_z, "zgrad_probe_pairs": nb, "zgrad_points": M_POINTS,
+                 "zgrad_note": "lip_zgrad GGN mode, cotangent = vector = 64 Rademacher probes: d/dZ of their quadratic forms (fp32 SIMT GEMMs)",
+                 "optimize_step_seconds": min(times[1:]), "optimize_step_loss": float(loss_z),
+                 "optimize_step_config": f"train_inducing.optimize_step, scalable objective + Hutchinson dZ + Adam: m={m_ref} inducing points, "
+                                         f"|X|=256, st_samples={nb}, slq k={k_ref} x 2 probes (config/scale/mlp_mnist.yml sizes)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -500,7 +537,7 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (V and out are %.2f GB each per GPU)" % (B * D * 4 / 1e9),
                        "parallelism": f"probe-sharded x{world}"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "slq_logdet": slq, "hutchinson_trace_estimate": trace_est}
+            "cpu_baseline": cpu, "slq_logdet": slq, "train_step": train, "hutchinson_trace_estimate": trace_est}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
