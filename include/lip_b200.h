@@ -165,6 +165,15 @@ int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, floa
               int32_t per_probe, void* workspace, size_t workspace_bytes, lip_stream_t stream);
 size_t lip_zgrad_workspace_bytes(const lip_model* m, int32_t mode, int64_t B);
 
+/* ---- evaluation consumer ---------------------------------------------------------------------
+ * Monte-Carlo softmax predictive from the S logit samples of predict_lla_scalable, as batch_nll computes it
+ * (scale_experiments/evaluate.py:126-142):
+ *   log_avg_prob[b] = logsumexp_s log_softmax(logits[s,b,:])[labels[b]] - log S     (NaN for labels outside [0, C))
+ *   mean_probs[b,c] = mean_s softmax(logits[s,b,:])[c]
+ * logits: [S, B, C] row-major; labels: int32 [B]; either output may be NULL (labels may be NULL without log_avg_prob). C <= 64. */
+int lip_mc_softmax_predictive(const float* logits, const int32_t* labels, float* log_avg_prob, float* mean_probs,
+                              int64_t S, int64_t B, int32_t C, lip_stream_t stream);
+
 /* ---- vector stage (CG / Lanczos / GKL building blocks; all batched over B independent columns) --------
  * Vectors are [B, n] row-major.  Scalars stay on the device (no host readback). */
 

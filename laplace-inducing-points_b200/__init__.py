@@ -10,7 +10,7 @@ package without the built library, or calling it without a CUDA device, raises â
 from . import _cabi  # noqa: F401
 
 __all__ = ["ggn", "lla", "stochtrace", "sample", "matfree", "matfree_monkeypatch", "utils", "toymodels",
-           "scalemodels", "train_inducing", "train_alpha"]
+           "scalemodels", "train_inducing", "train_alpha", "evaluate"]
 
 
 def __getattr__(name):

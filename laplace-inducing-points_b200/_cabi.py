@@ -53,6 +53,7 @@ SIGNATURES = {
     "lip_gram_cross_workspace_bytes": (_SZ, [_P, _P, _I64]),
     "lip_zgrad": (C.c_int, [_P, _I32, _P, _P, _P, _I64, _F, _I32, _P, _SZ, _P]),
     "lip_zgrad_workspace_bytes": (_SZ, [_P, _I32, _I64]),
+    "lip_mc_softmax_predictive": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I32, _P]),
     "lip_dot_scratch_bytes": (_SZ, [_I64, _I64]),
     "lip_dot": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
     "lip_axpby": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),

@@ -35,14 +35,23 @@ def compute_curvature_approx(map_state, Z, model_type, alpha, full_set_size=None
 
 
 def predict_lla_scalable(map_state, Xnew, Z, model_type, alpha, key=None, full_set_size=None, num_samples=1, *,
-                         eps=None):
+                         eps=None, sampler=None):
     """lla.py:133-156: f(theta*, X) + J_X w_s for posterior samples w_s = A^{-1/2} eps_s; returns [S, Bt, K].
-    The S sequential batch-JVPs of lla.py:153-154 are one lip_wt_apply(factor=NONE) over all samples."""
+    The S sequential batch-JVPs of lla.py:153-154 are one lip_wt_apply(factor=NONE) over all samples.
+    `sampler` (an inv_matsqrt_vp closure for the same state / Z / alpha) lets a caller that predicts on many test batches
+    (evaluate.eval_dataset) build the Gram factorisation once instead of once per batch (sample.py:77 inside evaluate.py:98-111)."""
     flat_params, _ = flatten_nn_params(map_state.params)
     D = flat_params.numel()
     key = key if key is not None else 123
-    w_samples = sample(map_state, Z, D, alpha=alpha, key=key, model_type=model_type, num_samples=num_samples,
-                       full_set_size=full_set_size, eps=eps)
+    if sampler is not None:
+        if eps is None:
+            from .matfree import _generator
+            g = _generator(key)
+            eps = torch.randn(num_samples, D, generator=g, device=g.device)
+        w_samples = sampler(dev_f32(eps).reshape(-1, D))
+    else:
+        w_samples = sample(map_state, Z, D, alpha=alpha, key=key, model_type=model_type, num_samples=num_samples,
+                           full_set_size=full_set_size, eps=eps)
     bx = _bind(map_state, Xnew, model_type)
     fmu = bx.outputs()
     dys = bx.wt(w_samples.reshape(-1, D), scale=1.0, factor=cabi.FACTOR_NONE)

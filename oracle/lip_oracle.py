@@ -890,3 +890,49 @@ def log_marginal_likelihood(alpha, X, state, model_type, full_set_size=None):
     la = torch.tensor(math.log(alpha), dtype=F64)
     g, v = torch.func.grad_and_value(lml)(la)
     return float(v), float(g)
+
+
+# ======================================================================================
+# evaluation consumer (scale_experiments/evaluate.py:40-152)
+# ======================================================================================
+def mc_softmax_predictive(logit_samples, y):
+    """evaluate.py:119-142: (log( 1/S sum_s softmax(l_s)[y] ) per example, mean_s softmax(l_s))."""
+    ls = np.asarray(logit_samples, dtype=np.float64)
+    y = np.asarray(y).reshape(-1).astype(np.int64)
+    sh = ls - ls.max(axis=-1, keepdims=True)
+    logp = sh - np.log(np.exp(sh).sum(axis=-1, keepdims=True))                 # log_softmax, (S,B,C)
+    lpt = np.take_along_axis(logp, y[None, :, None], axis=-1)[..., 0]          # (S,B)
+    mx = lpt.max(axis=0)
+    log_avg = mx + np.log(np.exp(lpt - mx).sum(axis=0)) - math.log(ls.shape[0])
+    return log_avg, np.exp(logp).mean(axis=0)
+
+
+def batch_nll(state, x, y, Z, *, alpha, full_set_size, model_type, Eps):
+    """evaluate.py:98-152 with the posterior noise Eps [S, D] as an input -> (nll, acc, mean probs)."""
+    logits = predict_lla_scalable(state, x, Z, model_type, alpha, Eps, full_set_size=full_set_size)
+    log_avg, mean = mc_softmax_predictive(logits, y)
+    acc = float((mean.argmax(-1) == np.asarray(y).reshape(-1)).mean())
+    return float(-log_avg.mean()), acc, mean
+
+
+def brier_score(probs, labels):
+    """evaluate.py:40-43."""
+    probs = np.asarray(probs, dtype=np.float64)
+    onehot = np.zeros_like(probs)
+    onehot[np.arange(len(labels)), np.asarray(labels).astype(int)] = 1.0
+    return float(((probs - onehot) ** 2).sum(axis=1).mean())
+
+
+def ece(probs, labels, n_bins=15):
+    """evaluate.py:45-63 (half-open bins [lo, hi) on linspace edges)."""
+    probs = np.asarray(probs)
+    labels = np.asarray(labels).reshape(-1)
+    conf, pred = probs.max(1), probs.argmax(1)
+    hit = pred == labels
+    edges = np.linspace(0.0, 1.0, n_bins + 1)
+    out = 0.0
+    for b in range(n_bins):
+        m = (conf >= edges[b]) & (conf < edges[b + 1])
+        if m.any():
+            out += abs(conf[m].mean() - hit[m].mean()) * m.mean()
+    return float(out)
