@@ -89,6 +89,33 @@ def slq_sharded(integrand: Callable, matvec, probes: torch.Tensor, *parameters) 
     return sharded_mean(quad, probes)
 
 
+def zgrad_sharded(zgrad_fn: Callable, cotangents: torch.Tensor, vectors: torch.Tensor) -> torch.Tensor:
+    """Probe-sharded gradient with respect to Z (SURVEY §8 rows e / f1): sum_b d/dZ <cotangents[b], operator(vectors[b])> with each
+    rank pushing only its slice of the probe pairs through `zgrad_fn` (a closure's .zgrad: lip_zgrad summed over its probes) and ONE
+    all-reduce of the [M, in] result — the Z-gradient is tiny next to the [B, D] probe blocks, so nothing else crosses NVLink.
+    Both arguments are the full [B, ...] blocks, identical on every rank; returns the global sum on every rank."""
+    B = cotangents.shape[0]
+    if vectors.shape[0] != B:
+        raise ValueError(f"zgrad_sharded: {B} cotangents against {vectors.shape[0]} vectors")
+    sl = probe_slice(B)
+    out = None
+    if sl.stop > sl.start:
+        out = zgrad_fn(cotangents[sl], vectors[sl]).contiguous()
+    # a rank that owns no probe still takes part in the all-reduce; it learns the shape from a size exchange
+    shape = torch.zeros(8, dtype=torch.int64, device=cotangents.device)
+    if out is not None:
+        shape[0] = out.dim()
+        shape[1:1 + out.dim()] = torch.tensor(out.shape, dtype=torch.int64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(shape, op=dist.ReduceOp.MAX)
+    if out is None:
+        nd = int(shape[0])
+        if nd == 0:
+            raise ValueError("zgrad_sharded: no rank owns a probe")
+        out = torch.zeros(tuple(int(v) for v in shape[1:1 + nd]), dtype=torch.float32, device=cotangents.device)
+    return allreduce_sum_(out)
+
+
 # ---------------------------------------------------------------------------------------------- point (M) sharding
 def point_slice(num_points: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> slice:
     """Contiguous, balanced slice of the inducing points owned by `rank` (sharding over M for large

@@ -230,9 +230,15 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
     S_vp = compute_curvature_approx(state, Xt, model_type, alpha, full_set_size=N)
     Sz_vp = compute_curvature_approx(state, Zt, model_type, alpha, full_set_size=N)
     Sz_inv = woodbury_inverse(state, Zt, model_type, alpha, N)
-    a = Sz_inv(probes)                                    # S_Z^-1 eps
-    b = probes - Sz_inv(S_vp(probes))                     # eps - S_Z^-1 S_X eps
-    dZ = Sz_vp.zgrad(a, b) / probes.shape[0]
+    from . import _dist
+
+    def local(E, _):                                      # this rank's probe rows (all of them without a process group)
+        a = Sz_inv(E)                                     # S_Z^-1 eps
+        b = E - Sz_inv(S_vp(E))                           # eps - S_Z^-1 S_X eps
+        return Sz_vp.zgrad(a, b)
+
+    # probes shard over ranks: one all-reduce of the [M, in] gradient
+    dZ = _dist.zgrad_sharded(local, probes, probes) / probes.shape[0]
     return loss, dZ.reshape(Zt.shape)
 
 

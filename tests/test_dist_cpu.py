@@ -127,3 +127,41 @@ def test_point_sharded_operator_sums_partial_products():
     ref = torch.einsum("mkd,mke,be->bd", J, J, V).numpy()
     for r in range(ws):
         np.testing.assert_allclose(res[r], ref, rtol=1e-5, atol=1e-5)
+
+
+def _worker_zgrad(rank, ws, port, B, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws),
+                      LOCAL_RANK=str(rank))
+    _dist.init_from_env(backend="gloo")
+    g = torch.Generator().manual_seed(5)
+    T = torch.randn(6, 3, 20, 20, generator=g)             # a bilinear "Z-gradient" tensor: dZ[m, i] = sum_b u_b^T T[m, i] v_b
+    U = torch.randn(B, 20, generator=g)
+    V = torch.randn(B, 20, generator=g)
+    seen = []
+
+    def zgrad(u, v):                                       # stands in for closure.zgrad: sums over the probes it is given
+        seen.append(u.shape[0])
+        return torch.einsum("bd,mide,be->mi", u, T, v)
+    res = _dist.zgrad_sharded(zgrad, U, V)
+    out[rank] = (res.numpy().copy(), sum(seen))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [5, 1])
+def test_zgrad_sharded_sums_probe_slices(B):
+    """the Z-gradient of a probe-averaged quantity shards over probes with one all-reduce of [M, in]
+    (B = 1: one rank owns no probe and still joins the reduction)."""
+    ws, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_zgrad, args=(ws, port, B, out), nprocs=ws, join=True)
+        res = dict(out)
+    g = torch.Generator().manual_seed(5)
+    T = torch.randn(6, 3, 20, 20, generator=g)
+    U = torch.randn(B, 20, generator=g)
+    V = torch.randn(B, 20, generator=g)
+    ref = torch.einsum("bd,mide,be->mi", U, T, V).numpy()
+    for r in range(ws):
+        np.testing.assert_allclose(res[r][0], ref, rtol=1e-5, atol=1e-5)
+    assert sum(res[r][1] for r in range(ws)) == B          # every probe pair is pushed exactly once
