@@ -4,6 +4,8 @@
 // pass at bind time, and the reference result the tcgen05 3xTF32 kernel is self-tested against.
 // 128x128x16 CTA tile, 256 threads, 8x8 register micro-tile (split 4+4 so shared-memory reads are
 // conflict-free float4), register-prefetch double buffering.
+#include <stdlib.h>
+
 #include "lip_common.cuh"
 
 namespace lip {
@@ -16,6 +18,10 @@ struct DevOperand {
   const float* ptr;
   long long sz, s0, s1;
   ConvGather conv;
+  // B operands only, nin > 0: the column index is a folded (batch entry, column) pair, n' = q * nin + r  ->  q * fold_sz + r * s1
+  int nin;
+  FastDiv dnin;
+  long long fold_sz;
 };
 
 // offset of the image element behind A[m][k] of a gathered operand; false = zero padding
@@ -61,10 +67,22 @@ struct DevGemm {
   int act;
   float* dphi_out;
   float* C_lo;
+  int nin;             // > 0: batch folded into N (see gemm_simt): C / add column n' = q * nin + r lives at q * c_sz (add_sz) + m * c_sm + r
+  FastDiv dnin;
   int ksplit;          // > 1: blockIdx.y = m_tile * ksplit + slice; raw partial tiles go to `part`
   float* part;         // [slice][z][M][N]
   long long part_sz;   // stride between slices = batch * M * N
 };
+
+// offset of output element (z, m, n) in an array with batch stride zs (C: c_sz, add: add_sz)
+__device__ __forceinline__ long long out_offset(const DevGemm& g, long long z, int m, int n, long long zs) {
+  if (g.nin) {
+    uint32_t q, r;
+    g.dnin.divmod((uint32_t)n, q, r);
+    return (long long)q * zs + (long long)m * g.c_sm + r;
+  }
+  return z * zs + (long long)m * g.c_sm + n;
+}
 
 // KC: the contraction index is the contiguous one for this operand; ROWS: tile extent of the other; GATHER: the A operand may
 // be an implicit-GEMM patch gather (compiled out of the plain kernels: the divmod chain costs registers / occupancy)
@@ -85,8 +103,16 @@ __device__ __forceinline__ void load_tile(const DevOperand& op, long long zoff, 
         long long off;
         if (conv_offset(op.conv, (uint32_t)gr, (uint32_t)gk, &off)) v = __ldg(op.ptr + zoff + off);
       } else {
-        long long off = is_a ? ((long long)gr * op.s0 + (long long)gk * op.s1)
-                             : ((long long)gk * op.s0 + (long long)gr * op.s1);
+        long long off;
+        if (is_a) {
+          off = (long long)gr * op.s0 + (long long)gk * op.s1;
+        } else if (op.nin) {
+          uint32_t q, r;
+          op.dnin.divmod((uint32_t)gr, q, r);
+          off = (long long)gk * op.s0 + (long long)q * op.fold_sz + (long long)r * op.s1;
+        } else {
+          off = (long long)gk * op.s0 + (long long)gr * op.s1;
+        }
         v = __ldg(op.ptr + zoff + off);
       }
     }
@@ -294,14 +320,14 @@ __global__ void __launch_bounds__(NT, 2) gemm_simt_kernel(DevGemm g) {
       if (n >= g.N) continue;
       float v = g.scale * acc[i][j];
       if (g.bias) v += __ldg(g.bias + (long long)z * g.bias_sz + n);
-      const long long co = (long long)z * g.c_sz + (long long)m * g.c_sm + n;
+      const long long co = out_offset(g, z, m, n, g.c_sz);
       if (g.act >= 0) {
         float d;
         v = act_apply(g.act, v, &d);
         if (g.dphi_out) g.dphi_out[co] = d;
       }
       if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
-      if (g.add) v += g.add_scale * __ldg(g.add + (long long)z * g.add_sz + (long long)m * g.c_sm + n);
+      if (g.add) v += g.add_scale * __ldg(g.add + out_offset(g, z, m, n, g.add_sz));
       if (g.C_lo) {
         const float h = tf32_round(v);
         g.C[co] = h;
@@ -408,6 +434,117 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(DevGemm g) {
   }
 }
 
+// Row-per-thread form of the skinny GEMM (N <= 16): a thread owns RPT whole output rows (16 accumulators each), so one A element
+// from shared memory feeds 16 FMAs and the 16-wide B row is a warp-uniform broadcast (4 LDS.128) - FMA-bound instead of
+// shared-memory-bound (the 64 x 16 tile above does 4 FMAs per 2 shared loads).  Tile: RT_K k-steps x (NT * RPT) rows.
+constexpr int RT_K = 16;
+
+template <bool A_KC, bool GATHER, int RPT>
+__global__ void __launch_bounds__(NT) gemm_rowthread_kernel(DevGemm g) {
+  constexpr int TM = NT * RPT;
+  __shared__ float As[RT_K][TM + 1];
+  __shared__ __align__(16) float Bs[RT_K][SB_N];
+  const int z = blockIdx.z;
+  const int ks = g.ksplit > 1 ? g.ksplit : 1;
+  const int slice = blockIdx.y % ks;
+  const int m0 = (blockIdx.y / ks) * TM;
+  const int tid = threadIdx.x;
+  float acc[RPT][SB_N];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int n = 0; n < SB_N; ++n) acc[r][n] = 0.f;
+  const int npairs = g.A2.ptr ? 2 : 1;
+  for (int pair = 0; pair < npairs; ++pair) {
+    const DevOperand& A = pair ? g.A2 : g.A1;
+    const DevOperand& B = pair ? g.B2 : g.B1;
+    const int K = pair ? g.K2 : g.K1;
+    const float* Ap = A.ptr + (long long)z * A.sz;
+    const float* Bp = B.ptr + (long long)z * B.sz;
+    const int nk_all = (K + RT_K - 1) / RT_K;
+    const int k_begin = (int)((long long)nk_all * slice / ks) * RT_K;
+    const int k_end_t = (int)((long long)nk_all * (slice + 1) / ks) * RT_K;
+    const int k_end = k_end_t < K ? k_end_t : K;
+    for (int k0 = k_begin; k0 < k_end; k0 += RT_K) {
+#pragma unroll 4
+      for (int i = 0; i < (TM * RT_K) / NT; ++i) {
+        const int idx = tid + NT * i;
+        int k, rr;
+        if (A_KC) { k = idx % RT_K; rr = idx / RT_K; } else { rr = idx % TM; k = idx / TM; }
+        const int gm = m0 + rr, gk = k0 + k;
+        float av = 0.f;
+        if (gm < g.M && gk < K) {
+          if (GATHER && A.conv.mode) {
+            long long off;
+            if (conv_offset(A.conv, (uint32_t)gm, (uint32_t)gk, &off)) av = __ldg(Ap + off);
+          } else {
+            av = __ldg(Ap + (long long)gm * A.s0 + (long long)gk * A.s1);
+          }
+        }
+        As[k][rr] = av;
+      }
+      {
+        const int n = tid % SB_N, k = tid / SB_N;          // NT == RT_K * SB_N: one element per thread
+        const int gk = k0 + k;
+        Bs[k][n] = (n < g.N && gk < K) ? __ldg(Bp + (long long)gk * B.s0 + (long long)n * B.s1) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < RT_K; ++k) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][0]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][4]);
+        const float4 b2 = *reinterpret_cast<const float4*>(&Bs[k][8]);
+        const float4 b3 = *reinterpret_cast<const float4*>(&Bs[k][12]);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          const float a = As[k][tid + r * NT];
+          acc[r][0] = fmaf(a, b0.x, acc[r][0]);   acc[r][1] = fmaf(a, b0.y, acc[r][1]);
+          acc[r][2] = fmaf(a, b0.z, acc[r][2]);   acc[r][3] = fmaf(a, b0.w, acc[r][3]);
+          acc[r][4] = fmaf(a, b1.x, acc[r][4]);   acc[r][5] = fmaf(a, b1.y, acc[r][5]);
+          acc[r][6] = fmaf(a, b1.z, acc[r][6]);   acc[r][7] = fmaf(a, b1.w, acc[r][7]);
+          acc[r][8] = fmaf(a, b2.x, acc[r][8]);   acc[r][9] = fmaf(a, b2.y, acc[r][9]);
+          acc[r][10] = fmaf(a, b2.z, acc[r][10]); acc[r][11] = fmaf(a, b2.w, acc[r][11]);
+          acc[r][12] = fmaf(a, b3.x, acc[r][12]); acc[r][13] = fmaf(a, b3.y, acc[r][13]);
+          acc[r][14] = fmaf(a, b3.z, acc[r][14]); acc[r][15] = fmaf(a, b3.w, acc[r][15]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int m = m0 + tid + r * NT;
+    if (m >= g.M) continue;
+    if (ks > 1) {
+      float* pt = g.part + (long long)slice * g.part_sz + (long long)z * g.M * g.N + (long long)m * g.N;
+#pragma unroll
+      for (int n = 0; n < SB_N; ++n) if (n < g.N) pt[n] = acc[r][n];
+      continue;
+    }
+#pragma unroll
+    for (int n = 0; n < SB_N; ++n) {
+      if (n >= g.N) continue;
+      float v = g.scale * acc[r][n];
+      if (g.bias) v += __ldg(g.bias + (long long)z * g.bias_sz + n);
+      const long long co = (long long)z * g.c_sz + (long long)m * g.c_sm + n;
+      if (g.act >= 0) {
+        float d;
+        v = act_apply(g.act, v, &d);
+        if (g.dphi_out) g.dphi_out[co] = d;
+      }
+      if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
+      if (g.add) v += g.add_scale * __ldg(g.add + (long long)z * g.add_sz + (long long)m * g.c_sm + n);
+      if (g.C_lo) {
+        const float h = tf32_round(v);
+        g.C[co] = h;
+        g.C_lo[co] = tf32_round(v - h);
+      } else {
+        g.C[co] = v;
+      }
+    }
+  }
+}
+
 // C = epilogue( sum_slices part[slice][z][m][n] ), slices summed in a fixed order
 __global__ void splitk_reduce_kernel(DevGemm g, long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -419,14 +556,14 @@ __global__ void splitk_reduce_kernel(DevGemm g, long long total) {
     for (int s = 0; s < g.ksplit; ++s) acc += g.part[(long long)s * g.part_sz + idx];
     float v = g.scale * acc;
     if (g.bias) v += __ldg(g.bias + z * g.bias_sz + n);
-    const long long co = z * g.c_sz + (long long)m * g.c_sm + n;
+    const long long co = out_offset(g, z, m, n, g.c_sz);
     if (g.act >= 0) {
       float d;
       v = act_apply(g.act, v, &d);
       if (g.dphi_out) g.dphi_out[co] = d;
     }
     if (g.mask) v *= __ldg(g.mask + (long long)m * g.mask_sm + n);
-    if (g.add) v += g.add_scale * __ldg(g.add + z * g.add_sz + (long long)m * g.c_sm + n);
+    if (g.add) v += g.add_scale * __ldg(g.add + out_offset(g, z, m, n, g.add_sz));
     if (g.C_lo) {
       const float h = tf32_round(v);
       g.C[co] = h;
@@ -439,9 +576,25 @@ __global__ void splitk_reduce_kernel(DevGemm g, long long total) {
 
 }  // namespace
 
-int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
-  if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return LIP_OK;
-  LIP_REQUIRE(p.A1.ptr && p.B1.ptr && p.C, "gemm_simt: null operand");
+int gemm_simt(const GemmProblem& p_in, cudaStream_t stream) {
+  if (p_in.M <= 0 || p_in.N <= 0 || p_in.batch <= 0) return LIP_OK;
+  LIP_REQUIRE(p_in.A1.ptr && p_in.B1.ptr && p_in.C, "gemm_simt: null operand");
+  // Batch folding: a skinny (N <= 16) batched problem whose A operand is SHARED by the batch entries (the per-probe weight
+  // gradients of narrow layers: A = cached activations / patches, B = the probe's deltas) is one wide GEMM
+  //   C[m, (z, n)] = sum_k A[m, k] B[z][k, n]
+  // with the batch folded into the column index: the 128 x 128 tiles reuse each A element 128 times instead of <= 16 and the
+  // shared operand is staged once per 128 / N probes.  LIP_FOLD_N=0 disables it.
+  static const bool fold_on = !(getenv("LIP_FOLD_N") && atoi(getenv("LIP_FOLD_N")) == 0);
+  GemmProblem p = p_in;
+  int fold_nin = 0;
+  long long fold_bsz = 0;
+  if (fold_on && p.N <= 16 && p.batch >= 8 && p.A1.sz == 0 && !p.A2.ptr && !p.A1.conv.mode && p.B1.s1 == 1 && !p.epi.bias &&
+      !p.epi.mask && p.epi.act < 0 && !p.epi.C_lo && !p.epi.dphi_out && p.batch * p.N < (1LL << 30) && p.K >= 64) {
+    fold_nin = (int)p.N;
+    fold_bsz = p.B1.sz;
+    p.N = p.batch * p.N;
+    p.batch = 1;
+  }
   const bool a_kc = p.A1.conv.mode ? (p.A1.conv.mode != 2) : (p.A1.s1 == 1);   // A contiguous along k
   const bool b_kc = (p.B1.s1 != 1);   // B contiguous along k (else along n)
   LIP_REQUIRE(p.A1.conv.mode || a_kc || p.A1.s0 == 1, "gemm_simt: A must be contiguous along m or k");
@@ -455,11 +608,16 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
   DevGemm g;
   g.M = (int)p.M; g.N = (int)p.N; g.K1 = (int)p.K; g.K2 = (int)p.K2;
   auto cv = [](const GemmOperand& o) {
-    DevOperand d{o.ptr, o.sz, o.s0, o.s1, o.conv};
+    DevOperand d{o.ptr, o.sz, o.s0, o.s1, o.conv, 0, FastDiv(), 0};
     if (d.conv.mode) d.conv.finalize();
     return d;
   };
   g.A1 = cv(p.A1); g.B1 = cv(p.B1); g.A2 = cv(p.A2); g.B2 = cv(p.B2);
+  g.nin = fold_nin;
+  if (fold_nin) {
+    g.dnin = FastDiv((uint32_t)fold_nin);
+    g.B1.nin = fold_nin; g.B1.dnin = g.dnin; g.B1.fold_sz = fold_bsz;
+  }
   g.C = p.C; g.c_sz = p.c_sz; g.c_sm = p.c_sm;
   g.scale = p.epi.scale;
   g.bias = p.epi.bias; g.bias_sz = p.epi.bias_sz;
@@ -471,9 +629,13 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
 
   // split-K decision: few tiles, long K, scratch available, single operand pair, batch in one launch
   const bool skinny = p.N <= SB_N;
+  // skinny form: row-per-thread kernel (LIP_SKINNY_ROWTHREAD=0 restores the 64 x 16 tile kernel); 2 rows per thread for tall problems
+  static const bool rowthread = !(getenv("LIP_SKINNY_ROWTHREAD") && atoi(getenv("LIP_SKINNY_ROWTHREAD")) == 0);
+  const int rpt = p.M >= 4 * NT ? 2 : 1;
+  const int sb_m = rowthread ? NT * rpt : SB_M;
   const int bnt = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : BN);       // narrow tiles for 32- / 64-wide outputs
-  const int64_t tiles = skinny ? ceil_div(p.M, SB_M) : ceil_div(p.N, bnt) * ceil_div(p.M, BM);
-  const int64_t kstep = skinny ? SB_K : BK;
+  const int64_t tiles = skinny ? ceil_div(p.M, sb_m) : ceil_div(p.N, bnt) * ceil_div(p.M, BM);
+  const int64_t kstep = skinny ? (rowthread ? RT_K : SB_K) : BK;
   if (p.splitk_ws && !p.A2.ptr && p.batch <= 65535 && tiles * p.batch < 16 * 148 && p.K >= 64 * kstep) {
     int64_t S = ceil_div(32 * 148, tiles * p.batch);       // enough CTAs in flight to hide the latency of the long K stream
     const int64_t smax_k = p.K / (8 * kstep);                       // at least 8 k-tiles per slice
@@ -485,7 +647,7 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     }
   }
 
-  LIP_REQUIRE((skinny ? ceil_div(p.M, SB_M) : ceil_div(p.M, BM)) * g.ksplit <= 65535 && ceil_div(p.N, bnt) <= 2147483647LL,
+  LIP_REQUIRE((skinny ? ceil_div(p.M, sb_m) : ceil_div(p.M, BM)) * g.ksplit <= 65535 && ceil_div(p.N, bnt) <= 2147483647LL,
               "gemm_simt: %lld rows exceed the grid limit of this kernel (tile rows x K slices <= 65535)", (long long)p.M);
   dim3 grid((unsigned)ceil_div(p.N, bnt), (unsigned)(ceil_div(p.M, BM) * g.ksplit), 1);
   // gridDim.z is limited to 65535: chunk the batch.
@@ -502,8 +664,17 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     if (gz.C_lo) gz.C_lo += z0 * g.c_sz;
     grid.z = (unsigned)zc;
     if (p.N <= SB_N) {
-      dim3 sg(1, (unsigned)(ceil_div(p.M, SB_M) * g.ksplit), (unsigned)zc);
-      if (gather) {
+      dim3 sg(1, (unsigned)(ceil_div(p.M, sb_m) * g.ksplit), (unsigned)zc);
+      if (rowthread) {
+#define LIP_RT_LAUNCH(AK, G)                                                                     \
+        do {                                                                                      \
+          if (rpt == 2) gemm_rowthread_kernel<AK, G, 2><<<sg, NT, 0, stream>>>(gz);               \
+          else gemm_rowthread_kernel<AK, G, 1><<<sg, NT, 0, stream>>>(gz);                        \
+        } while (0)
+        if (gather) { if (a_kc) LIP_RT_LAUNCH(true, true); else LIP_RT_LAUNCH(false, true); }
+        else { if (a_kc) LIP_RT_LAUNCH(true, false); else LIP_RT_LAUNCH(false, false); }
+#undef LIP_RT_LAUNCH
+      } else if (gather) {
         if (a_kc) gemm_skinny_kernel<true, true><<<sg, NT, 0, stream>>>(gz);
         else gemm_skinny_kernel<false, true><<<sg, NT, 0, stream>>>(gz);
       } else {
