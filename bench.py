@@ -486,7 +486,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
         train = {"zgrad_ms": ms_z, "zgrad_probe_pairs": nb, "zgrad_points": M_POINTS,
-                 "zgrad_note": "lip_zgrad GGN mode, cotangent = vector = 64 Rademacher probes: d/dZ of their quadratic forms (fp32 SIMT GEMMs)",
+                 "zgrad_note": "lip_zgrad GGN mode, cotangent = vector = 64 Rademacher probes: d/dZ of their quadratic forms (tcgen05 3xTF32 GEMMs for the wide layers)",
                  "optimize_step_seconds": min(times[1:]), "optimize_step_loss": float(loss_z),
                  "optimize_step_config": f"train_inducing.optimize_step, scalable objective + Hutchinson dZ + Adam: m={m_ref} inducing points, "
                                          f"|X|=256, st_samples={nb}, slq k={k_ref} x 2 probes (config/scale/mlp_mnist.yml sizes)"}

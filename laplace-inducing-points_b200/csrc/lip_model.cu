@@ -260,7 +260,10 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
 static inline int ld_of(const lip_model* m, int width) { return m->tc_on ? pad4(width) : width; }
 
 // ---- JVP sweep: V[B,D] -> dlogits written to `dst` ([B,M,K], contiguous).  Intermediates ping-pong in ws.
-int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float* dst, cudaStream_t st) {
+// keep_hi / keep_lo (optional, [nL - 1] pointers): layer l < nL - 1 writes its masked tangent dA_{l+1} there instead of into the
+// ping-pong buffers, so a later reverse pass (lip_zgrad.cu) can read every layer's tangent.
+int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float* dst, cudaStream_t st,
+              float* const* keep_hi = nullptr, float* const* keep_lo = nullptr) {
   const int nL = (int)m->L.size();
   const float* prev_hi = nullptr;
   const float* prev_lo = nullptr;
@@ -305,8 +308,8 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
     const bool last = (l == nL - 1);
     const bool tc = m->tc_on && m->tc_layer[l];
     const bool next_tc = m->tc_on && !last && m->tc_layer[l + 1];   // consumer of this layer's output
-    float* out_hi = last ? dst : w.hi[l & 1];
-    float* out_lo = (!last && next_tc) ? w.lo[l & 1] : nullptr;
+    float* out_hi = last ? dst : (keep_hi ? keep_hi[l] : w.hi[l & 1]);
+    float* out_lo = (!last && next_tc) ? (keep_lo ? keep_lo[l] : w.lo[l & 1]) : nullptr;
     const int out_ld = last ? Ld.out : ld_of(m, Ld.out);
     if (tc) {
       const int64_t ldw = m->W_ld[l];
@@ -472,6 +475,22 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
 }
 
 }  // namespace
+
+namespace lip {
+// ---- MLP sweep pieces shared with lip_zgrad.cu ----
+size_t mlp_ws_bytes(const lip_model* m, int64_t B) { return ws_bytes(m, B); }
+int mlp_ld(const lip_model* m, int width) { return ld_of(m, width); }
+// forward tangent sweep keeping every hidden layer's masked tangent; reports where the probes' split weight blocks live
+int mlp_jvp_keep(lip_model* m, const float* V, int64_t B, void* ws, size_t bytes, float* dl, float* const* keep_hi,
+                 float* const* keep_lo, const float** vs_hi, const float** vs_lo, cudaStream_t st) {
+  Workspace w;
+  int rc = carve(m, B, ws, bytes, &w);
+  if (rc) return rc;
+  if (vs_hi) *vs_hi = w.vs_hi;
+  if (vs_lo) *vs_lo = w.vs_lo;
+  return jvp_sweep(m, V, B, w, dl, st, keep_hi, keep_lo);
+}
+}  // namespace lip
 
 // ============================================================================================================
 // C ABI

@@ -133,6 +133,12 @@ int launch_bias_grad(const float* Delta, const float* Delta_lo, int64_t rows, in
 int launch_scale_copy(const float* in, float* out, int64_t n, float scale, cudaStream_t st);
 int launch_softmax(const float* logits, float* P, float* S, int64_t M, int K, cudaStream_t st);
 
+// MLP sweep pieces shared with lip_zgrad.cu (defined in lip_model.cu)
+size_t mlp_ws_bytes(const lip_model* m, int64_t B);
+int mlp_ld(const lip_model* m, int width);
+int mlp_jvp_keep(lip_model* m, const float* V, int64_t B, void* ws, size_t bytes, float* dl, float* const* keep_hi,
+                 float* const* keep_lo, const float** vs_hi, const float** vs_lo, cudaStream_t st);
+
 // NHWC im2col / col2im (lip_cnn.cu): patches [MZ*Ho*Wo, kh*kw*C], column order (dy, dx, c) = flax HWIO kernel rows
 int im2col(const float* in, float* out, int64_t MZ, int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kh, int kw,
            int Ho, int Wo, cudaStream_t st);

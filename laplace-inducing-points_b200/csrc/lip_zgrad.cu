@@ -23,7 +23,14 @@
 //   LIP_ZGRAD_W     s = ubar^T (scale * sum_i J_i^T L_i U_i)                       X1 = ubar [B,D], X2 = U [B,M,K]
 //   LIP_ZGRAD_JVP   s = sum_i C_i . (scale * J_i v)   (factor NONE, lla.py:153)    X1 = v [B,D],   X2 = C [B,M,K]
 // Dense programs (models M1 / M2) only; conv programs return LIP_ERR_UNSUPPORTED.
+//
+// Two executions of the same recurrences: zgrad_simt (fp32 FMA GEMMs, any activation, any width) and zgrad_tc, which runs the
+// layers the model already has on the tcgen05 path (lip_model.cu: in, out >= 64) through the 3xTF32 tensor-core GEMMs
+// (lip_gemm_tc.cu): the forward tangent pass IS the JVP sweep (keeping every layer's masked tangent dA as a TF32 (hi, lo) pair),
+// X = e W^T is the delta-backprop instance, and q_{l-1} is ONE dual-K GEMM [e_l | q_l] x [dW_l^T ; W_l^T] whose epilogue applies
+// the phi' mask and adds T = (phi''/phi') * dA * X (for tanh phi''/phi' = -2 tanh(h); relu: 0 - zgrad_tc is used for those two).
 #include <math.h>
+#include <stdlib.h>
 
 #include "lip_model.cuh"
 
@@ -192,6 +199,247 @@ void zg_carve(const lip_model* m, int64_t nb, void* ws, ZWs* w) {
 
 inline unsigned blocks(int64_t n) { return (unsigned)ceil_div(n, 256); }
 
+// rho = phi'' / phi' at the bound points (0 where phi' vanishes: tanh saturated in fp32 / relu off, where phi'' * dh is 0 too)
+__global__ void rho_kernel(float* __restrict__ ddphi, const float* __restrict__ dphi, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float d = dphi[i];
+    ddphi[i] = d != 0.f ? ddphi[i] / d : 0.f;
+  }
+}
+
+// rows x cols block with leading dimension ld (X, dA, e, T) against [M, cols] point-wise factors:
+//   e = phi' * X  (as a TF32 (hi, lo) pair when e_lo != nullptr),   T = rho * (dA_hi + dA_lo) * X
+__global__ void reverse_act_tc_kernel(const float* __restrict__ X, const float* __restrict__ dA_hi, const float* __restrict__ dA_lo,
+                                      const float* __restrict__ dphi, const float* __restrict__ rho, float* __restrict__ e_hi,
+                                      float* __restrict__ e_lo, float* __restrict__ T, int64_t rows, int64_t M, int cols, int ld) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols;
+  const int c = (int)(i - r * cols);
+  const int64_t o = r * ld + c, pm = (r % M) * cols + c;
+  const float x = X[o];
+  float da = dA_hi[o];
+  if (dA_lo) da += dA_lo[o];
+  T[o] = __ldg(rho + pm) * da * x;
+  const float e = __ldg(dphi + pm) * x;
+  if (e_lo) {
+    const float h = tf32_round(e);
+    e_hi[o] = h;
+    e_lo[o] = tf32_round(e - h);
+  } else {
+    e_hi[o] = e;
+  }
+}
+
+static inline int64_t pad4l(int64_t x) { return (x + 3) / 4 * 4; }
+
+bool zg_tc_ok(const lip_model* m) {
+  static const bool on = !(getenv("LIP_ZGRAD_TC") && atoi(getenv("LIP_ZGRAD_TC")) == 0);
+  if (!on || !m->tc_on) return false;
+  for (size_t l = 0; l + 1 < m->L.size(); ++l)
+    if (m->L[l].act != LIP_OP_TANH && m->L[l].act != LIP_OP_RELU) return false;
+  return true;
+}
+
+int64_t zg_tc_wld(const lip_model* m) {
+  int64_t w = pad4l(m->L[0].in);
+  for (auto& L : m->L) w = pad4l(L.out) > w ? pad4l(L.out) : w;
+  return w;
+}
+
+struct ZTcSizes {
+  size_t mlp, keep, eq, small, tmp, rho, total;
+};
+
+ZTcSizes zg_tc_sizes(const lip_model* m, int64_t B, int nseg) {
+  ZTcSizes z;
+  const int nL = (int)m->L.size();
+  z.mlp = align_up(mlp_ws_bytes(m, B), 256);
+  size_t keep = 0, rho = 0;
+  for (int l = 0; l + 1 < nL; ++l) {
+    keep += 2 * align_up(sizeof(float) * (size_t)B * m->M * mlp_ld(m, m->L[l].out), 256);
+    rho += align_up(sizeof(float) * (size_t)m->M * m->L[l].out, 256);
+  }
+  z.keep = keep;
+  z.rho = rho;
+  z.eq = align_up(sizeof(float) * (size_t)B * m->M * zg_tc_wld(m), 256);         // one of the 10 e / q / X / T buffers
+  z.small = align_up(sizeof(float) * (size_t)nseg * B * m->M * m->K, 256);       // dl, Cc, Gf
+  z.tmp = align_up(sizeof(float) * (size_t)nseg * B * m->M * m->L[0].in, 256);
+  z.total = nseg * (z.mlp + z.keep) + 10 * z.eq + 3 * z.small + z.tmp + z.rho + 512;
+  return z;
+}
+
+int zgrad_tc(lip_model* m, int32_t mode, const float* X1, const float* X2, float* out, int64_t B, float scale, int32_t per_probe,
+             void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int nL = (int)m->L.size();
+  const int64_t M = m->M;
+  const int nseg = mode == LIP_ZGRAD_GGN ? 2 : 1;
+  const int64_t nb = nseg * B;
+  const ZTcSizes sz = zg_tc_sizes(m, B, nseg);
+  if (!workspace || workspace_bytes < sz.total) {
+    set_error("lip_zgrad: workspace too small: need %zu bytes, got %zu", sz.total, workspace_bytes);
+    return LIP_ERR_WORKSPACE;
+  }
+  char* base = (char*)align_up((uintptr_t)workspace, 256);
+  auto take = [&](size_t bytes) { char* p = base; base += bytes; return (float*)p; };
+  float* mlp_ws[2] = {nullptr, nullptr};
+  std::vector<float*> keep_hi[2], keep_lo[2];
+  for (int sg = 0; sg < nseg; ++sg) {
+    mlp_ws[sg] = take(sz.mlp);
+    keep_hi[sg].assign(nL, nullptr); keep_lo[sg].assign(nL, nullptr);
+    for (int l = 0; l + 1 < nL; ++l) {
+      const size_t b = align_up(sizeof(float) * (size_t)B * M * mlp_ld(m, m->L[l].out), 256);
+      keep_hi[sg][l] = take(b);
+      keep_lo[sg][l] = take(b);
+    }
+  }
+  float* eq[10];
+  for (int i = 0; i < 10; ++i) eq[i] = take(sz.eq);
+  float* dl = take(sz.small);
+  float* Cc = take(sz.small);
+  float* Gf = take(sz.small);
+  float* tmp = take(sz.tmp);
+  std::vector<float*> rho(nL, nullptr);
+  for (int l = 0; l + 1 < nL; ++l) rho[l] = take(align_up(sizeof(float) * (size_t)M * m->L[l].out, 256));
+  const float* Vseg[2] = {X1, mode == LIP_ZGRAD_GGN ? X2 : nullptr};
+  const bool classifier = m->model_type == LIP_CLASSIFIER;
+
+  // ---- rho = phi''/phi' at the bound points ----
+  for (int l = 0; l + 1 < nL; ++l) {
+    const DenseLayer& Ld = m->L[l];
+    GemmProblem p;
+    p.M = M; p.N = Ld.out; p.K = Ld.in; p.batch = 1;
+    p.A1 = {m->A[l], 0, Ld.in, 1};
+    p.B1 = {m->theta + Ld.woff, 0, Ld.out, 1};
+    p.C = rho[l]; p.c_sz = 0; p.c_sm = Ld.out;
+    p.epi.bias = m->theta + Ld.boff; p.epi.bias_sz = 0;
+    int rc = gemm_simt(p, st);
+    if (rc) return rc;
+    act_second_kernel<<<blocks(M * Ld.out), 256, 0, st>>>(rho[l], M * Ld.out, Ld.act);
+    LIP_LAUNCH_CHECK();
+    rho_kernel<<<blocks(M * Ld.out), 256, 0, st>>>(rho[l], m->dphi[l], M * Ld.out);
+    LIP_LAUNCH_CHECK();
+  }
+
+  // ---- forward tangent pass = the JVP sweep, every layer's masked tangent kept ----
+  const float* vs_hi[2] = {nullptr, nullptr};
+  const float* vs_lo[2] = {nullptr, nullptr};
+  for (int sg = 0; sg < nseg; ++sg) {
+    int rc = mlp_jvp_keep(m, Vseg[sg], B, mlp_ws[sg], sz.mlp, dl + (int64_t)sg * B * M * m->K, keep_hi[sg].data(), keep_lo[sg].data(),
+                          &vs_hi[sg], &vs_lo[sg], st);
+    if (rc) return rc;
+  }
+
+  // ---- output-space rows ----
+  float s = scale;
+  if (!classifier && (mode == LIP_ZGRAD_WT || mode == LIP_ZGRAD_W)) s *= expf(-0.5f * m->logvar);
+  zgrad_rows_kernel<<<(unsigned)ceil_div(B * M, 128), 128, 0, st>>>(mode, classifier ? 1 : 0, dl, X2, m->P, m->S, Cc, Gf, B, M, m->K, s);
+  LIP_LAUNCH_CHECK();
+
+  // ---- reverse pass, one segment at a time ----
+  float* X = eq[8];
+  float* T = eq[9];
+  for (int sg = 0; sg < nseg; ++sg) {
+    const float* e_hi = Cc + (int64_t)sg * B * M * m->K;
+    const float* q_hi = Gf + (int64_t)sg * B * M * m->K;
+    const float* e_lo = nullptr;
+    const float* q_lo = nullptr;
+    int cur_ld = m->K;
+    int flip = 0;     // next e / q pairs go to eq[flip .. flip + 3]
+    for (int l = nL - 1; l >= 0; --l) {
+      const DenseLayer& Ld = m->L[l];
+      const bool tc = m->tc_layer[l] != 0;
+      if (tc && !e_lo) {   // a tensor-core top layer: re-lay the fp32 rows as padded (hi, lo) pairs
+        const int ldp = (int)pad4l(cur_ld);
+        int rc = tf32_split(e_hi, cur_ld, eq[flip], eq[flip + 1], ldp, B * M, Ld.out, st);
+        if (rc) return rc;
+        rc = tf32_split(q_hi, cur_ld, eq[flip + 2], eq[flip + 3], ldp, B * M, Ld.out, st);
+        if (rc) return rc;
+        e_hi = eq[flip]; e_lo = eq[flip + 1]; q_hi = eq[flip + 2]; q_lo = eq[flip + 3];
+        cur_ld = ldp; flip ^= 4;
+      }
+      const int in_ld = l > 0 ? mlp_ld(m, Ld.in) : Ld.in;
+      const bool next_pair = l > 0 && m->tc_layer[l - 1] != 0;
+      const int64_t per_in = M * (int64_t)in_ld, per_out = M * (int64_t)cur_ld;
+      float* en_hi = eq[flip];
+      float* en_lo = next_pair ? eq[flip + 1] : nullptr;
+      float* qn_hi = l > 0 ? eq[flip + 2] : tmp + (int64_t)sg * B * M * Ld.in;
+      float* qn_lo = next_pair ? eq[flip + 3] : nullptr;
+      if (l > 0) {   // X = e_l W_l^T
+        if (tc) {
+          TcGemmProblem p;
+          p.M = M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
+          p.A1.hi = e_hi; p.A1.lo = e_lo; p.A1.ld = cur_ld; p.A1.sz = per_out; p.A1.major_k = 1; p.a_batched = 1;
+          p.B1.hi = m->W_hi[l]; p.B1.lo = m->W_lo[l]; p.B1.ld = m->W_ld[l]; p.B1.sz = (int64_t)Ld.in * m->W_ld[l]; p.B1.major_k = 1;
+          p.b_batched = 0;
+          p.C = X; p.c_sz = per_in; p.c_sm = in_ld;
+          int rc = gemm_tc(p, st);
+          if (rc) return rc;
+        } else {
+          GemmProblem p;
+          p.M = M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
+          p.A1 = {e_hi, per_out, cur_ld, 1};
+          p.B1 = {m->theta + Ld.woff, 0, 1, Ld.out};
+          p.C = X; p.c_sz = per_in; p.c_sm = in_ld;
+          int rc = gemm_simt(p, st);
+          if (rc) return rc;
+        }
+        reverse_act_tc_kernel<<<blocks(B * M * Ld.in), 256, 0, st>>>(X, keep_hi[sg][l - 1], tc ? keep_lo[sg][l - 1] : nullptr,   // dA_l has a lo part iff its consumer (layer l) is a tensor-core layer
+                                                                    
+                                                                     m->dphi[l - 1], rho[l - 1], en_hi, en_lo, T, B * M, M, Ld.in, in_ld);
+        LIP_LAUNCH_CHECK();
+      }
+      // q_{l-1} = phi' * (e_l dW_l^T + q_l W_l^T) + T        (l = 0: dZ[b] = e_0 dW_0^T + q_0 W_0^T, no epilogue)
+      if (tc) {
+        const int64_t ldw = m->W_ld[l];
+        TcGemmProblem p;
+        p.M = M; p.N = Ld.in; p.K = Ld.out; p.K2 = Ld.out; p.batch = B;
+        p.A1.hi = e_hi; p.A1.lo = e_lo; p.A1.ld = cur_ld; p.A1.sz = per_out; p.A1.major_k = 1; p.a_batched = 1;
+        p.B1.hi = vs_hi[sg] + B * m->split_off[l]; p.B1.lo = vs_lo[sg] + B * m->split_off[l]; p.B1.ld = ldw;
+        p.B1.sz = (int64_t)Ld.in * ldw; p.B1.major_k = 1; p.b_batched = 1;
+        p.A2.hi = q_hi; p.A2.lo = q_lo; p.A2.ld = cur_ld; p.A2.sz = per_out; p.A2.major_k = 1; p.a2_batched = 1;
+        p.B2.hi = m->W_hi[l]; p.B2.lo = m->W_lo[l]; p.B2.ld = ldw; p.B2.sz = (int64_t)Ld.in * ldw; p.B2.major_k = 1; p.b2_batched = 0;
+        p.C = qn_hi; p.C_lo = qn_lo; p.c_sz = per_in; p.c_sm = in_ld;
+        if (l > 0) {
+          p.epi.mask = m->dphi[l - 1]; p.epi.mask_sm = Ld.in;
+          p.epi.add = T; p.epi.add_sz = per_in; p.epi.add_scale = 1.f;
+        }
+        int rc = gemm_tc(p, st);
+        if (rc) return rc;
+      } else {
+        GemmProblem p;
+        p.M = M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
+        p.A1 = {e_hi, per_out, cur_ld, 1};
+        p.B1 = {Vseg[sg] + Ld.woff, m->D, 1, Ld.out};
+        p.A2 = {q_hi, per_out, cur_ld, 1};
+        p.B2 = {m->theta + Ld.woff, 0, 1, Ld.out};
+        p.K2 = Ld.out;
+        p.C = qn_hi; p.c_sz = per_in; p.c_sm = in_ld;
+        p.epi.C_lo = qn_lo;
+        if (l > 0) {
+          p.epi.mask = m->dphi[l - 1]; p.epi.mask_sm = Ld.in;
+          p.epi.add = T; p.epi.add_sz = per_in; p.epi.add_scale = 1.f;
+        }
+        int rc = gemm_simt(p, st);
+        if (rc) return rc;
+      }
+      e_hi = en_hi; e_lo = en_lo; q_hi = qn_hi; q_lo = qn_lo;
+      cur_ld = in_ld; flip ^= 4;
+    }
+  }
+  const int64_t per0 = M * (int64_t)m->L[0].in;
+  if (!per_probe) {
+    batch_sum_kernel<<<blocks(per0), 256, 0, st>>>(tmp, out, per0, nb, 1.f);
+  } else if (mode == LIP_ZGRAD_GGN) {
+    batch_sum_kernel<<<blocks(B * per0), 256, 0, st>>>(tmp, out, B * per0, 2, 1.f);
+  } else {
+    batch_sum_kernel<<<blocks(B * per0), 256, 0, st>>>(tmp, out, B * per0, 1, 1.f);
+  }
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
 }  // namespace
 }  // namespace lip
 
@@ -201,6 +449,7 @@ extern "C" {
 
 size_t lip_zgrad_workspace_bytes(const lip_model* m, int32_t mode, int64_t B) {
   if (!m || !m->bound || B <= 0 || m->is_cnn || m->is_resnet) return 0;
+  if (zg_tc_ok(m)) return zg_tc_sizes(m, B, mode == LIP_ZGRAD_GGN ? 2 : 1).total;
   return zg_bytes(m, mode == LIP_ZGRAD_GGN ? 2 * B : B);
 }
 
@@ -214,6 +463,7 @@ int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, floa
     return LIP_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (zg_tc_ok(m)) return zgrad_tc(m, mode, X1, X2, out, B, scale, per_probe, workspace, workspace_bytes, st);
   const int nL = (int)m->L.size();
   const int64_t M = m->M;
   const int64_t nb = mode == LIP_ZGRAD_GGN ? 2 * B : B;

@@ -56,6 +56,41 @@ def test_W_WT_zgrad_match_oracle(name):
     assert rel_err(WTfun.zgrad(cu(Y), cu(V)).cpu().numpy(), WTz_ref(Y, V)) < TOL
 
 
+TC_ZCONFIGS = {
+    # name: (hidden, n_out, in_dim, M, N, activation model)
+    "tc_ragged": ([200, 72, 136], 7, 100, 150, 900),
+    "tc_m50": ([256, 128, 64], 10, 784, 50, 60000),
+}
+
+
+@pytest.mark.parametrize("name", list(TC_ZCONFIGS))
+def test_zgrad_tensor_core_path_matches_oracle_and_simt(name):
+    """lip_zgrad on the tcgen05 path (layers with in, out >= 64: JVP sweep forward, delta-backprop + dual-K GEMMs with the
+    mask + add epilogue in reverse) against the float64 autograd oracle and against the fp32 SIMT execution of the same recurrences."""
+    from lip_b200 import ggn
+    hidden, n_out, in_dim, M, N = TC_ZCONFIGS[name]
+    ost, lst = make_pair("large", hidden=hidden, n_out=n_out, in_dim=in_dim, seed=77)
+    rng = np.random.default_rng(79)
+    Z = rng.random((M, in_dim)).astype(np.float32)
+    D = ost.flat()[0].size
+    U, V = _probes(D, 2, 80)
+    Y = rng.standard_normal((2, M, n_out)).astype(np.float32)
+    ref = O.ggn_vp_zgrad(ost, Z, "classifier", U, V, full_set_size=N, per_probe=True)
+    tc = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=N, tensor_path=True)
+    assert "tcgen05" in tc._lip_model.path_name()
+    simt = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=N, tensor_path=False)
+    g_tc = tc.zgrad(cu(U), cu(V), per_probe=True).cpu().numpy()
+    g_simt = simt.zgrad(cu(U), cu(V), per_probe=True).cpu().numpy()
+    e_tc, e_simt = rel_err(g_tc, ref), rel_err(g_simt, ref)
+    print(f"{name}: zgrad GGN tc rel err {e_tc:.2e}, simt rel err {e_simt:.2e}")
+    assert e_simt < TOL and e_tc < TOL
+    assert rel_err(tc.zgrad(cu(U), cu(V)).cpu().numpy(), ref.sum(0)) < TOL
+    Wz_ref, WTz_ref = O.W_vps_zgrad(ost, Z, "classifier", full_set_size=N)
+    Wf, WTf = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=N, tensor_path=True)
+    assert rel_err(Wf.zgrad(cu(U), cu(Y)).cpu().numpy(), Wz_ref(U, Y)) < TOL
+    assert rel_err(WTf.zgrad(cu(Y), cu(V)).cpu().numpy(), WTz_ref(Y, V)) < TOL
+
+
 def test_jvp_zgrad_matches_oracle():
     from lip_b200 import _cabi, ggn
     ost, lst, Z, mt, N = _setup("mlp_ragged")
@@ -93,6 +128,8 @@ def test_zgrad_headline_shape_runs_and_matches_finite_difference():
     V *= 1e-2
     vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=60000, tensor_path=False)
     g = vp.zgrad(cu(U), cu(V)).double().cpu().numpy()
+    g_tc = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=60000, tensor_path=True).zgrad(cu(U), cu(V)).double().cpu().numpy()
+    assert rel_err(g_tc, g) < 2e-5          # tcgen05 3xTF32 execution against the fp32 SIMT execution at the headline shape
     dZ = rng.standard_normal(Z.shape)
     eps = 1e-2
 

@@ -29,7 +29,7 @@ for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g = cvp.zgrad(probes, probes); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"lip_zgrad GGN mode: M={M} B={B} D={D}: {ms:.2f} ms  ({B / ms * 1e3:.0f} probe-gradients/s, {flop / ms / 1e9:.1f} TFLOP/s fp32 SIMT) "
+    print(f"lip_zgrad GGN mode: M={M} B={B} D={D}: {ms:.2f} ms  ({B / ms * 1e3:.0f} probe-gradients/s, {flop / ms / 1e9:.1f} TFLOP/s algorithmic, {cvp._lip_model.path_name()}) "
           f"launches={L.lip_launch_count() - l0} |dZ|={float(g.norm()):.4g}", flush=True)
 rng = np.random.default_rng(9)
 X = torch.as_tensor(rng.random((batch, 784), dtype=np.float32), device=dev)
