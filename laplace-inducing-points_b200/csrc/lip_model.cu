@@ -705,6 +705,10 @@ int lip_model_bind(lip_model* m, const float* theta, const float* Z, int64_t M, 
       m->ev_split.push_back(e);
     }
   }
+  {
+    int rc = zgrad_prepare(m, st);
+    if (rc) return rc;
+  }
   m->bound = true;
   return LIP_OK;
 }

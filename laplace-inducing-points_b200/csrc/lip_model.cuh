@@ -65,6 +65,8 @@ struct lip_model {
   float logvar = 0.f;
   std::vector<float*> A;     // A[l]: input of layer l, [M, in_l]   (A[0] = Z)
   std::vector<float*> dphi;  // dphi[l]: phi'(h_l) at the output of layer l (l < nL-1), [M, out_l]
+  std::vector<float*> ddphi; // ddphi[l]: phi''(h_l), and rho[l] = phi''/phi' (0 where phi' = 0): second-order factors of lip_zgrad
+  std::vector<float*> rho;
   float* logits = nullptr;   // [M, K]
   float* P = nullptr;        // softmax(logits)
   float* S = nullptr;        // sqrt(P)
@@ -109,6 +111,9 @@ struct lip_model {
     free_resnet_cache();
     for (auto p : A) if (p) cudaFree(p);
     for (auto p : dphi) if (p) cudaFree(p);
+    for (auto p : ddphi) if (p) cudaFree(p);
+    for (auto p : rho) if (p) cudaFree(p);
+    ddphi.clear(); rho.clear();
     for (auto p : A_hi) if (p) cudaFree(p);
     for (auto p : A_lo) if (p) cudaFree(p);
     for (auto p : W_hi) if (p) cudaFree(p);
@@ -133,6 +138,8 @@ int launch_bias_grad(const float* Delta, const float* Delta_lo, int64_t rows, in
 int launch_scale_copy(const float* in, float* out, int64_t n, float scale, cudaStream_t st);
 int launch_softmax(const float* logits, float* P, float* S, int64_t M, int K, cudaStream_t st);
 
+// bind-time part of lip_zgrad (lip_zgrad.cu): phi'' and phi''/phi' at the bound points of a dense program
+int zgrad_prepare(lip_model* m, cudaStream_t st);
 // MLP sweep pieces shared with lip_zgrad.cu (defined in lip_model.cu)
 size_t mlp_ws_bytes(const lip_model* m, int64_t B);
 int mlp_ld(const lip_model* m, int width);

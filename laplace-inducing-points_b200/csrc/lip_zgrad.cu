@@ -159,7 +159,6 @@ struct Seg { const float* V; int64_t b0, nb; };   // probes [b0, b0 + nb) of the
 
 struct ZWs {
   std::vector<float*> dh;      // [nb, M, out_l], l < L
-  std::vector<float*> ddphi;   // [M, out_l], l < L
   float* buf[6];               // e / q ping-pong, X, T   (each [nb, M, wmax])
   float* dl;                   // [nb, M, K]
   float* Cc;                   // [nb, M, K]
@@ -175,7 +174,7 @@ int64_t zg_wmax(const lip_model* m) {
 size_t zg_bytes(const lip_model* m, int64_t nb) {
   const int nL = (int)m->L.size();
   size_t fl = 0;
-  for (int l = 0; l + 1 < nL; ++l) fl += align_up((size_t)nb * m->M * m->L[l].out, 64) + align_up((size_t)m->M * m->L[l].out, 64);
+  for (int l = 0; l + 1 < nL; ++l) fl += align_up((size_t)nb * m->M * m->L[l].out, 64);
   fl += 6 * align_up((size_t)nb * m->M * zg_wmax(m), 64);
   fl += 3 * align_up((size_t)nb * m->M * m->K, 64);
   return fl * sizeof(float) + 512;
@@ -184,10 +183,9 @@ size_t zg_bytes(const lip_model* m, int64_t nb) {
 void zg_carve(const lip_model* m, int64_t nb, void* ws, ZWs* w) {
   const int nL = (int)m->L.size();
   float* base = (float*)align_up((uintptr_t)ws, 256);
-  w->dh.assign(nL, nullptr); w->ddphi.assign(nL, nullptr);
+  w->dh.assign(nL, nullptr);
   for (int l = 0; l + 1 < nL; ++l) {
     w->dh[l] = base; base += align_up((size_t)nb * m->M * m->L[l].out, 64);
-    w->ddphi[l] = base; base += align_up((size_t)m->M * m->L[l].out, 64);
   }
   const size_t per = align_up((size_t)nb * m->M * zg_wmax(m), 64);
   for (int i = 0; i < 6; ++i) { w->buf[i] = base; base += per; }
@@ -249,24 +247,20 @@ int64_t zg_tc_wld(const lip_model* m) {
 }
 
 struct ZTcSizes {
-  size_t mlp, keep, eq, small, tmp, rho, total;
+  size_t mlp, keep, eq, small, tmp, total;
 };
 
 ZTcSizes zg_tc_sizes(const lip_model* m, int64_t B, int nseg) {
   ZTcSizes z;
   const int nL = (int)m->L.size();
   z.mlp = align_up(mlp_ws_bytes(m, B), 256);
-  size_t keep = 0, rho = 0;
-  for (int l = 0; l + 1 < nL; ++l) {
-    keep += 2 * align_up(sizeof(float) * (size_t)B * m->M * mlp_ld(m, m->L[l].out), 256);
-    rho += align_up(sizeof(float) * (size_t)m->M * m->L[l].out, 256);
-  }
+  size_t keep = 0;
+  for (int l = 0; l + 1 < nL; ++l) keep += 2 * align_up(sizeof(float) * (size_t)B * m->M * mlp_ld(m, m->L[l].out), 256);
   z.keep = keep;
-  z.rho = rho;
   z.eq = align_up(sizeof(float) * (size_t)B * m->M * zg_tc_wld(m), 256);         // one of the 10 e / q / X / T buffers
   z.small = align_up(sizeof(float) * (size_t)nseg * B * m->M * m->K, 256);       // dl, Cc, Gf
   z.tmp = align_up(sizeof(float) * (size_t)nseg * B * m->M * m->L[0].in, 256);
-  z.total = nseg * (z.mlp + z.keep) + 10 * z.eq + 3 * z.small + z.tmp + z.rho + 512;
+  z.total = nseg * (z.mlp + z.keep) + 10 * z.eq + 3 * z.small + z.tmp + 512;
   return z;
 }
 
@@ -300,27 +294,8 @@ int zgrad_tc(lip_model* m, int32_t mode, const float* X1, const float* X2, float
   float* Cc = take(sz.small);
   float* Gf = take(sz.small);
   float* tmp = take(sz.tmp);
-  std::vector<float*> rho(nL, nullptr);
-  for (int l = 0; l + 1 < nL; ++l) rho[l] = take(align_up(sizeof(float) * (size_t)M * m->L[l].out, 256));
   const float* Vseg[2] = {X1, mode == LIP_ZGRAD_GGN ? X2 : nullptr};
   const bool classifier = m->model_type == LIP_CLASSIFIER;
-
-  // ---- rho = phi''/phi' at the bound points ----
-  for (int l = 0; l + 1 < nL; ++l) {
-    const DenseLayer& Ld = m->L[l];
-    GemmProblem p;
-    p.M = M; p.N = Ld.out; p.K = Ld.in; p.batch = 1;
-    p.A1 = {m->A[l], 0, Ld.in, 1};
-    p.B1 = {m->theta + Ld.woff, 0, Ld.out, 1};
-    p.C = rho[l]; p.c_sz = 0; p.c_sm = Ld.out;
-    p.epi.bias = m->theta + Ld.boff; p.epi.bias_sz = 0;
-    int rc = gemm_simt(p, st);
-    if (rc) return rc;
-    act_second_kernel<<<blocks(M * Ld.out), 256, 0, st>>>(rho[l], M * Ld.out, Ld.act);
-    LIP_LAUNCH_CHECK();
-    rho_kernel<<<blocks(M * Ld.out), 256, 0, st>>>(rho[l], m->dphi[l], M * Ld.out);
-    LIP_LAUNCH_CHECK();
-  }
 
   // ---- forward tangent pass = the JVP sweep, every layer's masked tangent kept ----
   const float* vs_hi[2] = {nullptr, nullptr};
@@ -387,7 +362,7 @@ int zgrad_tc(lip_model* m, int32_t mode, const float* X1, const float* X2, float
         }
         reverse_act_tc_kernel<<<blocks(B * M * Ld.in), 256, 0, st>>>(X, keep_hi[sg][l - 1], tc ? keep_lo[sg][l - 1] : nullptr,   // dA_l has a lo part iff its consumer (layer l) is a tensor-core layer
                                                                     
-                                                                     m->dphi[l - 1], rho[l - 1], en_hi, en_lo, T, B * M, M, Ld.in, in_ld);
+                                                                     m->dphi[l - 1], m->rho[l - 1], en_hi, en_lo, T, B * M, M, Ld.in, in_ld);
         LIP_LAUNCH_CHECK();
       }
       // q_{l-1} = phi' * (e_l dW_l^T + q_l W_l^T) + T        (l = 0: dZ[b] = e_0 dW_0^T + q_0 W_0^T, no epilogue)
@@ -443,6 +418,36 @@ int zgrad_tc(lip_model* m, int32_t mode, const float* X1, const float* X2, float
 }  // namespace
 }  // namespace lip
 
+namespace lip {
+// Bind-time: phi''(h_l) and rho_l = phi''/phi' at the bound points (they depend on Z and theta only).  The pre-activations are
+// recomputed (the forward pass keeps phi(h) and phi'(h), not h).
+int zgrad_prepare(lip_model* m, cudaStream_t st) {
+  const int nL = (int)m->L.size();
+  m->ddphi.assign(nL > 1 ? nL - 1 : 0, nullptr);
+  m->rho.assign(nL > 1 ? nL - 1 : 0, nullptr);
+  for (int l = 0; l + 1 < nL; ++l) {
+    const DenseLayer& Ld = m->L[l];
+    const int64_t n = m->M * (int64_t)Ld.out;
+    LIP_CHECK_CUDA(cudaMalloc(&m->ddphi[l], sizeof(float) * (size_t)n + 256));
+    LIP_CHECK_CUDA(cudaMalloc(&m->rho[l], sizeof(float) * (size_t)n + 256));
+    GemmProblem p;
+    p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = 1;
+    p.A1 = {m->A[l], 0, Ld.in, 1};
+    p.B1 = {m->theta + Ld.woff, 0, Ld.out, 1};
+    p.C = m->ddphi[l]; p.c_sz = 0; p.c_sm = Ld.out;
+    p.epi.bias = m->theta + Ld.boff; p.epi.bias_sz = 0;
+    int rc = gemm_simt(p, st);
+    if (rc) return rc;
+    act_second_kernel<<<blocks(n), 256, 0, st>>>(m->ddphi[l], n, Ld.act);
+    LIP_LAUNCH_CHECK();
+    LIP_CHECK_CUDA(cudaMemcpyAsync(m->rho[l], m->ddphi[l], sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    rho_kernel<<<blocks(n), 256, 0, st>>>(m->rho[l], m->dphi[l], n);
+    LIP_LAUNCH_CHECK();
+  }
+  return LIP_OK;
+}
+}  // namespace lip
+
 using namespace lip;
 
 extern "C" {
@@ -479,21 +484,6 @@ int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, floa
   segs[0] = {X1, 0, B};
   if (mode == LIP_ZGRAD_GGN) { segs[1] = {X2, B, B}; nseg = 2; }
   const bool classifier = m->model_type == LIP_CLASSIFIER;
-
-  // ---- phi'' at the bound points: recompute the pre-activations h_l = A_l W_l + b_l (shared by all probes) ----
-  for (int l = 0; l + 1 < nL; ++l) {
-    const DenseLayer& Ld = m->L[l];
-    GemmProblem p;
-    p.M = M; p.N = Ld.out; p.K = Ld.in; p.batch = 1;
-    p.A1 = {m->A[l], 0, Ld.in, 1};
-    p.B1 = {m->theta + Ld.woff, 0, Ld.out, 1};
-    p.C = w.ddphi[l]; p.c_sz = 0; p.c_sm = Ld.out;
-    p.epi.bias = m->theta + Ld.boff; p.epi.bias_sz = 0;
-    int rc = gemm_simt(p, st);
-    if (rc) return rc;
-    act_second_kernel<<<blocks(M * Ld.out), 256, 0, st>>>(w.ddphi[l], M * Ld.out, Ld.act);
-    LIP_LAUNCH_CHECK();
-  }
 
   // ---- forward tangent pass, raw dh_l kept for every hidden layer ----
   float* dA = w.buf[0];   // phi' * dh of the previous layer
@@ -552,7 +542,7 @@ int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, floa
       }
       float* e_next = w.buf[flip];
       float* q_next = w.buf[flip + 1];
-      reverse_act_kernel<<<blocks(nb * per_in), 256, 0, st>>>(X, w.dh[l - 1], m->dphi[l - 1], w.ddphi[l - 1], e_next, T, per_in,
+      reverse_act_kernel<<<blocks(nb * per_in), 256, 0, st>>>(X, w.dh[l - 1], m->dphi[l - 1], m->ddphi[l - 1], e_next, T, per_in,
                                                               nb * per_in);
       LIP_LAUNCH_CHECK();
       for (int sgi = 0; sgi < nseg; ++sgi) {   // q_{l-1} = phi' * (e_l dW_l^T + q_l W_l^T) + T
