@@ -27,7 +27,7 @@ from .utils import flatten_nn_params
 
 
 def alternative_objective_scalable(Z, X, state, alpha, model_type, key, full_set_size=None, st_samples=256, slq_samples=2,
-                                   slq_num_matvecs=None, *, probes=None):
+                                   slq_num_matvecs=None, *, probes=None, _parts=None):
     """KL[q(theta|Z) || q(theta|data)] up to constants = tr(S_X S_Z^{-1}) + logdet(S_Z)   (train_inducing.py:87-173).
 
     Same arguments as the reference; `key` seeds the Rademacher probes (int / torch.Generator) unless `probes`
@@ -35,31 +35,15 @@ def alternative_objective_scalable(Z, X, state, alpha, model_type, key, full_set
     N = full_set_size
     Zt, Xt = dev_f32(Z), dev_f32(X)
     M = int(Zt.shape[0])
-    beta = N / M
     alpha = float(alpha)
-    alpha_inv, beta_inv = 1.0 / alpha, 1.0 / beta
     flat, _ = flatten_nn_params(state.params)          # D excludes logvar, as :104-106
     D = int(flat.numel())
 
-    S_vp = compute_curvature_approx(state, Xt, model_type, alpha, full_set_size=N)               # :108-110
-    # (the reference also builds Sz_vp over Z, :111-113, and never uses it)
-    Wz, WzT = compute_W_vps(state, Zt, model_type, full_set_size=None)                           # :114-116
-    bm = Wz._lip_model
-    inner_shape = (M,) if model_type == "regressor" else (M, bm.K)
-    d_z = M * bm.K
-    WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)                   # :126
-    # Woodbury: S_Z^{-1} v = v/alpha - alpha^-2 Wz (beta^-1 I + alpha^-1 WzTWz)^-1 WzT v   (:127-132); the d_z x d_z system is
-    # factorised once (float64 LU, library call) instead of once per matvec
-    Kmat = beta_inv * torch.eye(d_z, device=WzTWz.device, dtype=torch.float64) + alpha_inv * WzTWz.double()
-    LU, piv = torch.linalg.lu_factor(Kmat)
-
-    @matfree.batched
-    def Sz_inv(V):
-        V = dev_f32(V).reshape(-1, D)
-        u = WzT(V).reshape(V.shape[0], d_z)
-        x = torch.linalg.lu_solve(LU, piv, u.double().T).T.float()
-        return bm.w(x.reshape((V.shape[0],) + inner_shape), scale=Wz._lip_scale, add=V, add_scale=-alpha,
-                    batched=True).mul_(-alpha_inv ** 2)      # -(1/alpha^2) (Wz x - alpha v) = v/alpha - Wz x / alpha^2
+    # S_vp over the minibatch (:108-110), W_z / W_z^T (:114-116), the dense Gram (:126) and the Woodbury inverse (:127-132); the d_z x d_z
+    # system is factorised once (float64 LU, library call) instead of once per matvec.  (The reference also builds Sz_vp over Z,
+    # :111-113, and never uses it.)
+    parts = _parts if _parts is not None else _scalable_parts(Zt, Xt, state, alpha, model_type, N)
+    S_vp, Wz, WzT, Sz_inv, inner_shape, d_z = (parts[k] for k in ("S_vp", "Wz", "WzT", "Sz_inv", "inner_shape", "d_z"))
 
     @matfree.batched
     def composite_vp(V):                                                                         # :134-135
@@ -225,11 +209,11 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
     if probes is None:
         probes = matfree.sampler_rademacher(torch.ones(D), num=st_samples)(key)
     probes = dev_f32(probes)
+    parts = _scalable_parts(Zt, Xt, state, alpha, model_type, N)
     loss = alternative_objective_scalable(Zt, Xt, state, alpha, model_type, key, full_set_size=N, st_samples=st_samples,
-                                          slq_samples=slq_samples, slq_num_matvecs=slq_num_matvecs, probes=probes)
-    S_vp = compute_curvature_approx(state, Xt, model_type, alpha, full_set_size=N)
+                                          slq_samples=slq_samples, slq_num_matvecs=slq_num_matvecs, probes=probes, _parts=parts)
+    S_vp, Sz_inv = parts["S_vp"], parts["Sz_inv"]
     Sz_vp = compute_curvature_approx(state, Zt, model_type, alpha, full_set_size=N)
-    Sz_inv = woodbury_inverse(state, Zt, model_type, alpha, N)
     from . import _dist
 
     def local(E, _):                                      # this rank's probe rows (all of them without a process group)
@@ -242,30 +226,36 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
     return loss, dZ.reshape(Zt.shape)
 
 
-def woodbury_inverse(state, Z, model_type, alpha, full_set_size):
-    """S_Z^-1 v = v/alpha - alpha^-2 W_z (beta^-1 I + alpha^-1 W_z^T W_z)^-1 W_z^T v   (train_inducing.py:127-132), batched."""
-    Zt = dev_f32(Z)
+def _scalable_parts(Zt, Xt, state, alpha, model_type, N):
+    """The operators the scalable objective and its gradient share: S_vp over the minibatch (:108-110), W_z / W_z^T (:114-116) and
+    S_Z^-1 through the Woodbury identity (:127-132) — built once per step."""
     M = int(Zt.shape[0])
-    beta = full_set_size / M
-    alpha = float(alpha)
+    beta = N / M
+    S_vp = compute_curvature_approx(state, Xt, model_type, alpha, full_set_size=N)
     Wz, WzT = compute_W_vps(state, Zt, model_type, full_set_size=None)
     bm = Wz._lip_model
     inner_shape = (M,) if model_type == "regressor" else (M, bm.K)
     d_z = M * bm.K
     D = bm.D
-    WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)
+    WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)                   # :126
     Kmat = torch.eye(d_z, device=WzTWz.device, dtype=torch.float64) / beta + WzTWz.double() / alpha
     LU, piv = torch.linalg.lu_factor(Kmat)
 
     @matfree.batched
-    def Sz_inv(V):
+    def Sz_inv(V):   # S_Z^-1 v = v/alpha - alpha^-2 W_z (beta^-1 I + alpha^-1 W_z^T W_z)^-1 W_z^T v
         V = dev_f32(V).reshape(-1, D)
         u = WzT(V).reshape(V.shape[0], d_z)
         x = torch.linalg.lu_solve(LU, piv, u.double().T).T.float()
         return bm.w(x.reshape((V.shape[0],) + inner_shape), scale=Wz._lip_scale, add=V, add_scale=-alpha,
-                    batched=True).mul_(-1.0 / alpha ** 2)
+                    batched=True).mul_(-1.0 / alpha ** 2)      # -(1/alpha^2) (Wz x - alpha v) = v/alpha - Wz x / alpha^2
 
-    return Sz_inv
+    return dict(S_vp=S_vp, Wz=Wz, WzT=WzT, Sz_inv=Sz_inv, inner_shape=inner_shape, d_z=d_z)
+
+
+def woodbury_inverse(state, Z, model_type, alpha, full_set_size, X=None):
+    """S_Z^-1 as a batched closure (train_inducing.py:127-132)."""
+    Zt = dev_f32(Z)
+    return _scalable_parts(Zt, Zt if X is None else dev_f32(X), state, float(alpha), model_type, full_set_size)["Sz_inv"]
 
 
 def optimize_step(Z, X, map_model_state, alpha, opt_state, rng, zoptimizer, num_mc_samples=None, model_type="classifier",
