@@ -31,6 +31,14 @@ for name, kw, zshape in (("mlp", dict(kind="large", hidden=[256, 128], n_out=10,
     if rank == 0:
         print(f"{name}: world={world} point-sharded curvature_vp rel_err={e1:.2e}  probe-sharded Hutchinson rel_err={e2:.2e}", flush=True)
     ok = ok and e1 < 1e-5 and e2 < 1e-5
+    if name == "mlp":   # probe-sharded Z-gradient (SURVEY 8 rows e / f1): one all-reduce of the [M, in] result
+        U = torch.as_tensor(rng.standard_normal((8, D)).astype(np.float32), device="cuda")
+        g_full = cvp.zgrad(U, V)
+        g_shard = _dist.zgrad_sharded(cvp.zgrad, U, V)
+        e3 = rel_err(g_shard.cpu().numpy(), g_full.cpu().numpy())
+        if rank == 0:
+            print(f"{name}: world={world} probe-sharded lip_zgrad rel_err={e3:.2e}", flush=True)
+        ok = ok and e3 < 1e-5
 if world > 1:
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
