@@ -159,7 +159,9 @@ size_t lip_gram_cross_workspace_bytes(const lip_model* mx, const lip_model* mz, 
  *   LIP_ZGRAD_JVP : d/dZ sum_b sum_i X2[b,i] . ( scale * J_i X1[b] )                  X1 = v [B,D], X2 = cotangent [B,M,K]
  * `scale` has the meaning of lip_ggn_vp's recal / lip_w(t)_apply's scale with factor = SQRT (NONE for LIP_ZGRAD_JVP).
  * out: [M, in] (per_probe = 0, summed over probes: what differentiating a vmapped closure yields) or [B, M, in] (per_probe = 1).
- * Dense programs (models M1 / M2) only; conv programs return LIP_ERR_UNSUPPORTED. */
+ * Built for dense programs (models M1 / M2: tcgen05 3xTF32 GEMMs for the layers on the tensor path when the activations are
+ * tanh / relu, fp32 SIMT GEMMs otherwise) and for relu conv stage programs (model M3, LeNet5: Z = the input images);
+ * residual programs (M4) return LIP_ERR_UNSUPPORTED. */
 typedef enum { LIP_ZGRAD_GGN = 0, LIP_ZGRAD_WT = 1, LIP_ZGRAD_W = 2, LIP_ZGRAD_JVP = 3 } lip_zgrad_mode;
 int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, float* out, int64_t B, float scale,
               int32_t per_probe, void* workspace, size_t workspace_bytes, lip_stream_t stream);

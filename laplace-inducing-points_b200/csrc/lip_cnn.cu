@@ -477,6 +477,128 @@ int cnn_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scal
   return LIP_OK;
 }
 
+// ---- gradients with respect to the input images Z (lip_zgrad for conv stage programs) ---------------------------
+// Recurrences of lip_zgrad.cu with phi = relu, so phi'' = 0 and no tangent has to be kept:
+//     e_{i-1} = phi'_{i-1} * pool^T( col2im( e_i W_i^T ) )
+//     q_{i-1} = phi'_{i-1} * pool^T( col2im( e_i dW_i[b]^T + q_i W_i^T ) )
+//     dZ      = col2im_0( sum_probes  e_0 dW_0[b]^T + q_0 W_0^T )
+// i.e. two delta back-propagations (the second with a dual-K GEMM that also reads the probe's own kernel block in place),
+// continued through stage 0 down to the input image.
+struct CnnZSizes { size_t raw, fin, sum, small, total; };
+
+static CnnZSizes cnn_zsizes(const lip_model* m, int nseg, int64_t B, int per_probe) {
+  CnnZSizes z;
+  const CnnSizes c = cnn_sizes(m, B);
+  const ConvStage& s0 = m->CS[0];
+  z.raw = c.raw;
+  z.fin = align_up((size_t)nseg * B * m->M * (size_t)s0.P * s0.Kc, 64);
+  z.sum = align_up((size_t)(per_probe ? B : 1) * m->M * (size_t)s0.P * s0.Kc, 64);
+  z.small = align_up((size_t)nseg * B * m->M * m->K, 64);
+  z.total = align_up(cnn_ws_bytes(m, B), 256) + (2 * z.raw + z.fin + z.sum + 3 * z.small) * sizeof(float) + 512;
+  return z;
+}
+
+size_t cnn_zgrad_ws_bytes(const lip_model* m, int32_t mode, int64_t B) {
+  return cnn_zsizes(m, mode == LIP_ZGRAD_GGN ? 2 : 1, B, 1).total;
+}
+
+int cnn_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, float* out, int64_t B, float scale, int32_t per_probe,
+              void* ws, size_t bytes, cudaStream_t st) {
+  const int nS = (int)m->CS.size();
+  for (int i = 0; i + 1 < nS; ++i)
+    if (m->CS[i].act != LIP_OP_RELU) {
+      set_error("lip_zgrad: conv stage programs need relu activations (stage %d has op %d)", i, m->CS[i].act);
+      return LIP_ERR_UNSUPPORTED;
+    }
+  const int nseg = mode == LIP_ZGRAD_GGN ? 2 : 1;
+  const CnnZSizes z = cnn_zsizes(m, nseg, B, 1);
+  if (!ws || bytes < z.total) {
+    set_error("lip_zgrad: workspace too small: need %zu bytes, got %zu", z.total, bytes);
+    return LIP_ERR_WORKSPACE;
+  }
+  CnnWs w;
+  const size_t inner = align_up(cnn_ws_bytes(m, B), 256);
+  int rc = cnn_carve(m, B, ws, inner, &w);
+  if (rc) return rc;
+  float* base = (float*)align_up((uintptr_t)ws + inner, 256);
+  float* qbuf[2] = {base, base + z.raw};
+  float* fin = base + 2 * z.raw;
+  float* sum = fin + z.fin;
+  float* dl = sum + z.sum;
+  float* Cc = dl + z.small;
+  float* Gf = Cc + z.small;
+  float* ebuf[2] = {w.raw, w.raw2};
+  const float* Vseg[2] = {X1, mode == LIP_ZGRAD_GGN ? X2 : nullptr};
+  const int64_t M = m->M;
+  const int64_t small_seg = B * M * m->K;
+
+  for (int sg = 0; sg < nseg; ++sg) {   // forward tangent pass: only the tangent logits are needed (relu: phi'' = 0)
+    rc = cnn_jvp_sweep(m, Vseg[sg], B, w, dl + sg * small_seg, st);
+    if (rc) return rc;
+  }
+  rc = launch_zgrad_rows(mode, m, dl, X2, Cc, Gf, B, scale, st);
+  if (rc) return rc;
+
+  const ConvStage& s0 = m->CS[0];
+  const int64_t fin_seg = B * M * (int64_t)s0.P * s0.Kc;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const float* e = Cc + sg * small_seg;
+    const float* q = Gf + sg * small_seg;
+    int pp = 0;
+    for (int i = nS - 1; i >= 0; --i) {
+      const ConvStage& s = m->CS[i];
+      const int64_t R = M * (int64_t)s.P;
+      for (int which = 0; which < 2; ++which) {      // 0: the e path (shared kernel), 1: the q path (dual-K with the probe's kernel)
+        if (i == 0 && which == 0) continue;          // stage 0 needs only  e_0 dW_0^T + q_0 W_0^T
+        float* G = (i == 0) ? fin + sg * fin_seg : ((s.type == 1) ? w.col : w.t[0]);
+        GemmProblem p;
+        p.M = R; p.N = s.Kc; p.K = s.cout; p.batch = B;
+        p.A1 = {e, R * (int64_t)s.cout, s.cout, 1};
+        if (which == 0) {
+          p.B1 = {m->theta + s.woff, 0, 1, s.cout};
+        } else {
+          p.B1 = {Vseg[sg] + s.woff, m->D, 1, s.cout};
+          p.A2 = {q, R * (int64_t)s.cout, s.cout, 1};
+          p.B2 = {m->theta + s.woff, 0, 1, s.cout};
+          p.K2 = s.cout;
+        }
+        p.C = G; p.c_sz = R * (int64_t)s.Kc; p.c_sm = s.Kc;
+        rc = gemm_simt(p, st);
+        if (rc) return rc;
+        if (i == 0) break;
+        const ConvStage& sp = m->CS[i - 1];
+        const float* tin = G;     // gradient w.r.t. the output of stage i-1, [B, M, out_per_point(i-1)]
+        if (s.type == 1) {
+          rc = launch_col2im(w.col, w.t[0], B * M, s, st);
+          if (rc) return rc;
+          tin = w.t[0];
+        }
+        rc = launch_unpool_mask(tin, which == 0 ? ebuf[pp] : qbuf[pp], B, M, sp, st);
+        if (rc) return rc;
+      }
+      if (i > 0) { e = ebuf[pp]; q = qbuf[pp]; pp ^= 1; }
+    }
+  }
+  // sum over probes (per probe in GGN mode: the two halves), then back to the image through stage 0's patches
+  const int64_t per0 = M * (int64_t)s0.P * s0.Kc;
+  const float* src = fin;
+  int64_t images = M;
+  if (!per_probe) {
+    rc = launch_batch_sum(fin, sum, per0, (int64_t)nseg * B, st);
+    if (rc) return rc;
+    src = sum;
+  } else {
+    images = B * M;
+    if (nseg == 2) {
+      rc = launch_batch_sum(fin, sum, B * per0, 2, st);
+      if (rc) return rc;
+      src = sum;
+    }
+  }
+  if (s0.type == 1) return launch_col2im(src, out, images, s0, st);
+  return launch_scale_copy(src, out, images * (int64_t)s0.Kc, 1.f, st);
+}
+
 int cnn_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,
                 float add_scale, void* ws, size_t bytes, cudaStream_t st) {
   CnnWs w;

@@ -138,6 +138,14 @@ int launch_bias_grad(const float* Delta, const float* Delta_lo, int64_t rows, in
 int launch_scale_copy(const float* in, float* out, int64_t n, float scale, cudaStream_t st);
 int launch_softmax(const float* logits, float* P, float* S, int64_t M, int K, cudaStream_t st);
 
+// pieces of lip_zgrad shared with the conv stage programs (lip_zgrad.cu)
+int launch_zgrad_rows(int mode, const lip_model* m, const float* dl, const float* X2, float* Cc, float* Gf, int64_t B, float scale,
+                      cudaStream_t st);
+int launch_batch_sum(const float* x, float* out, int64_t per, int64_t nb, cudaStream_t st);
+// gradients with respect to Z for conv stage programs with relu activations (lip_cnn.cu)
+size_t cnn_zgrad_ws_bytes(const lip_model* m, int32_t mode, int64_t B);
+int cnn_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, float* out, int64_t B, float scale, int32_t per_probe,
+              void* ws, size_t bytes, cudaStream_t st);
 // bind-time part of lip_zgrad (lip_zgrad.cu): phi'' and phi''/phi' at the bound points of a dense program
 int zgrad_prepare(lip_model* m, cudaStream_t st);
 // MLP sweep pieces shared with lip_zgrad.cu (defined in lip_model.cu)

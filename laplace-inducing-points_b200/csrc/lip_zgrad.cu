@@ -22,7 +22,8 @@
 //   LIP_ZGRAD_WT    s = sum_i Ybar_i . (scale * L_i^T J_i v)                       X1 = v [B,D],   X2 = Ybar [B,M,K]
 //   LIP_ZGRAD_W     s = ubar^T (scale * sum_i J_i^T L_i U_i)                       X1 = ubar [B,D], X2 = U [B,M,K]
 //   LIP_ZGRAD_JVP   s = sum_i C_i . (scale * J_i v)   (factor NONE, lla.py:153)    X1 = v [B,D],   X2 = C [B,M,K]
-// Dense programs (models M1 / M2) only; conv programs return LIP_ERR_UNSUPPORTED.
+// Dense programs (models M1 / M2) here; relu conv stage programs (LeNet5, M3) in lip_cnn.cu (cnn_zgrad); residual programs return
+// LIP_ERR_UNSUPPORTED.
 //
 // Two executions of the same recurrences: zgrad_simt (fp32 FMA GEMMs, any activation, any width) and zgrad_tc, which runs the
 // layers the model already has on the tcgen05 path (lip_model.cu: in, out >= 64) through the 3xTF32 tensor-core GEMMs
@@ -419,6 +420,22 @@ int zgrad_tc(lip_model* m, int32_t mode, const float* X1, const float* X2, float
 }  // namespace lip
 
 namespace lip {
+int launch_zgrad_rows(int mode, const lip_model* m, const float* dl, const float* X2, float* Cc, float* Gf, int64_t B, float scale,
+                      cudaStream_t st) {
+  const bool classifier = m->model_type == LIP_CLASSIFIER;
+  float s = scale;
+  if (!classifier && (mode == LIP_ZGRAD_WT || mode == LIP_ZGRAD_W)) s *= expf(-0.5f * m->logvar);   // as lip_w(t)_apply, factor SQRT
+  zgrad_rows_kernel<<<(unsigned)ceil_div(B * m->M, 128), 128, 0, st>>>(mode, classifier ? 1 : 0, dl, X2, m->P, m->S, Cc, Gf, B, m->M,
+                                                                      m->K, s);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+int launch_batch_sum(const float* x, float* out, int64_t per, int64_t nb, cudaStream_t st) {
+  batch_sum_kernel<<<blocks(per), 256, 0, st>>>(x, out, per, nb, 1.f);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
 // Bind-time: phi''(h_l) and rho_l = phi''/phi' at the bound points (they depend on Z and theta only).  The pre-activations are
 // recomputed (the forward pass keeps phi(h) and phi'(h), not h).
 int zgrad_prepare(lip_model* m, cudaStream_t st) {
@@ -453,7 +470,8 @@ using namespace lip;
 extern "C" {
 
 size_t lip_zgrad_workspace_bytes(const lip_model* m, int32_t mode, int64_t B) {
-  if (!m || !m->bound || B <= 0 || m->is_cnn || m->is_resnet) return 0;
+  if (!m || !m->bound || B <= 0 || m->is_resnet) return 0;
+  if (m->is_cnn) return cnn_zgrad_ws_bytes(m, mode, B);
   if (zg_tc_ok(m)) return zg_tc_sizes(m, B, mode == LIP_ZGRAD_GGN ? 2 : 1).total;
   return zg_bytes(m, mode == LIP_ZGRAD_GGN ? 2 * B : B);
 }
@@ -463,11 +481,12 @@ int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, floa
   LIP_REQUIRE(m && X1 && X2 && out && B > 0, "lip_zgrad: null argument or B <= 0");
   LIP_REQUIRE(mode >= LIP_ZGRAD_GGN && mode <= LIP_ZGRAD_JVP, "lip_zgrad: bad mode %d", mode);
   if (!m->bound) { set_error("lip_zgrad: model not bound"); return LIP_ERR_NOT_BOUND; }
-  if (m->is_cnn || m->is_resnet) {
-    set_error("lip_zgrad: gradients with respect to Z are built for dense programs only (conv programs: not yet)");
+  if (m->is_resnet) {
+    set_error("lip_zgrad: gradients with respect to Z are built for dense programs and relu conv stage programs (residual programs: not yet)");
     return LIP_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_cnn) return cnn_zgrad(m, mode, X1, X2, out, B, scale, per_probe, workspace, workspace_bytes, st);
   if (zg_tc_ok(m)) return zgrad_tc(m, mode, X1, X2, out, B, scale, per_probe, workspace, workspace_bytes, st);
   const int nL = (int)m->L.size();
   const int64_t M = m->M;

@@ -142,11 +142,31 @@ def test_zgrad_headline_shape_runs_and_matches_finite_difference():
     assert abs(fd - an) <= 2e-2 * max(abs(an), 1e-12), (fd, an)
 
 
-def test_zgrad_rejects_conv_programs_and_bad_shapes():
+def test_lenet5_zgrad_matches_oracle():
+    """lip_zgrad for relu conv stage programs (LeNet5, src/scalemodels.py:11-49): d/dZ with respect to the input IMAGES."""
+    from lip_b200 import ggn
+    ost, lst = make_pair("lenet5", seed=1)
+    rng = np.random.default_rng(2)
+    Z = rng.random((3, 28, 28, 1)).astype(np.float32)
+    D = ost.flat()[0].size
+    U, V = _probes(D, 2, 19)
+    Y = rng.standard_normal((2, 3, 10)).astype(np.float32)
+    ref = O.ggn_vp_zgrad(ost, Z, "classifier", U, V, full_set_size=600, per_probe=True)
+    vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=600)
+    got = vp.zgrad(cu(U), cu(V), per_probe=True).cpu().numpy().reshape(ref.shape)
+    assert rel_err(got, ref) < TOL
+    assert rel_err(vp.zgrad(cu(U), cu(V)).cpu().numpy().reshape(Z.shape), ref.sum(0)) < TOL
+    Wz_ref, WTz_ref = O.W_vps_zgrad(ost, Z, "classifier", full_set_size=600)
+    Wf, WTf = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=600)
+    assert rel_err(Wf.zgrad(cu(U), cu(Y)).cpu().numpy().reshape(Z.shape), Wz_ref(U, Y)) < TOL
+    assert rel_err(WTf.zgrad(cu(Y), cu(V)).cpu().numpy().reshape(Z.shape), WTz_ref(Y, V)) < TOL
+
+
+def test_zgrad_rejects_residual_programs_and_bad_shapes():
     from lip_b200 import ggn
     from lip_b200._cabi import LipError
-    ost, lst = make_pair("lenet5", seed=1)
-    Z = np.random.default_rng(2).random((3, 28, 28, 1)).astype(np.float32)
+    ost, lst = make_pair("resnet1m", n_out=10, in_shape=(8, 8, 3), seed=1)
+    Z = np.random.default_rng(2).random((2, 8, 8, 3)).astype(np.float32)
     vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier")
     D = ost.flat()[0].size
     with pytest.raises((LipError, ValueError, RuntimeError)):
