@@ -488,7 +488,7 @@ def run_b200(args):
         train = {"zgrad_ms": ms_z, "zgrad_probe_pairs": nb, "zgrad_points": M_POINTS,
                  "zgrad_note": "lip_zgrad GGN mode, cotangent = vector = 64 Rademacher probes: d/dZ of their quadratic forms (tcgen05 3xTF32 GEMMs for the wide layers)",
                  "optimize_step_seconds": min(times[1:]), "optimize_step_loss": float(loss_z),
-                 "optimize_step_config": f"train_inducing.optimize_step, scalable objective + Hutchinson dZ + Adam: m={m_ref} inducing points, "
+                 "optimize_step_config": f"train_inducing.optimize_step, scalable objective + exact dZ + Adam: m={m_ref} inducing points, "
                                          f"|X|=256, st_samples={nb}, slq k={k_ref} x 2 probes (config/scale/mlp_mnist.yml sizes)"}
 
     if rank != 0:

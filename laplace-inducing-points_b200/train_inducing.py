@@ -8,8 +8,8 @@ are assembled from lip_zgrad (the VJP-with-respect-to-Z rules of those operators
   alternative_objective_scalable        :87-173   forward value (Hutch++ v2 + GKL logdet)
   alternative_objective_scalable_exact  :26-84    value;  variational_grad_scalable_exact -> (value, dZ)   [deterministic]
   alternative_objective_dense           :175-192  value;  variational_grad_dense          -> (value, dZ)   [deterministic]
-  variational_grad_scalable             :195      (value, dZ) with a Hutchinson estimate of the gradient (see its docstring:
-                                                  NOT the reference's autodiff-through-the-estimators, same expectation)
+  variational_grad_scalable             :195      (stochastic loss value, EXACT dZ of the quantity it estimates; see its docstring:
+                                                  NOT the reference's autodiff-through-the-estimators)
   optimize_step                         :198-232  one optimiser step on Z
 """
 from __future__ import annotations
@@ -85,18 +85,25 @@ def _probe_block(D: int, want: int) -> int:
     return max(1, min(int(want), (1 << 28) // max(D, 1)))
 
 
-def _exact_parts(Z, X, state, alpha, model_type, full_set_size):
+def _exact_parts(Z, X, state, alpha, model_type, full_set_size, zside=None):
+    """zside: optional (Wz, WzT, WzTWz) already built for the same state / Z (the scalable objective's parts)"""
     N = full_set_size
     Zt, Xt = dev_f32(Z), dev_f32(X)
     M, Kx = int(Zt.shape[0]), int(Xt.shape[0])
     flat, _ = flatten_nn_params(state.params)
     D = int(flat.numel())                                                                  # :37-39 (logvar is not in D)
-    Wz, WzT = compute_W_vps(state, Zt, model_type, full_set_size=None)                     # :48-50
+    if zside is not None:
+        Wz, WzT, WzTWz = zside
+    else:
+        Wz, WzT = compute_W_vps(state, Zt, model_type, full_set_size=None)                 # :48-50
+        WzTWz = None
     W, WT = compute_W_vps(state, Xt, model_type, full_set_size=None)                       # :51-53
     bz, bx = Wz._lip_model, W._lip_model
     inner_shape = (M,) if model_type == "regressor" else (M, bz.K)
     d_z, d = M * bz.K, Kx * bx.K
-    WzTWz = _f64(build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1))       # :60
+    if WzTWz is None:
+        WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)         # :60
+    WzTWz = _f64(WzTWz)
     WTWz = _f64(build_WTWz(WT, Wz, inner_shape, d=d, dtype=torch.float32, block=1))        # :67
     return dict(N=N, M=M, Kx=Kx, D=D, Wz=Wz, W=W, bz=bz, bx=bx, inner_shape=inner_shape, d_z=d_z, d=d, G=WzTWz, C=WTWz,
                 beta=N / M, gamma=N / Kx, alpha=float(alpha))
@@ -107,9 +114,12 @@ def _exact_value(p):
     eye = torch.eye(d_z, device=G.device, dtype=torch.float64)
     logdet_term = torch.linalg.slogdet(eye + beta / alpha * G)[1] + p["D"] * math.log(alpha)    # :62-63
     Mm = eye / beta + G / alpha                                                            # :69
-    L = torch.linalg.cholesky(Mm)                                                          # :70
-    S1 = torch.cholesky_solve(G, L)                                                        # :71
-    S2 = torch.cholesky_solve(C.T.contiguous(), L)                                         # :72
+    # :70-72 factorise Mm by Cholesky.  G is the Gram of a rank-deficient factor (each softmax L_i drops one direction), so Mm's
+    # smallest eigenvalues are exactly 1/beta and the fp32 rounding noise of G, amplified by 1/alpha, can push them below zero at the
+    # scale configs (jnp.linalg.cholesky would return NaN there); an LU factorisation solves the same systems without that failure.
+    L = torch.linalg.lu_factor(Mm)
+    S1 = torch.linalg.lu_solve(*L, G)                                                      # :71
+    S2 = torch.linalg.lu_solve(*L, C.T.contiguous())                                       # :72
     trace1 = torch.trace(S1)                                                               # :74
     trace2 = (C * S2.T).sum()                                                              # :75
     return logdet_term - trace1 / alpha - gamma / alpha ** 2 * trace2, L                   # :76-78
@@ -130,10 +140,16 @@ def variational_grad_scalable_exact(Z, X, state, alpha, model_type, key=None, fu
     dL/dC = -2 gamma C Mm^-1 / alpha^2, and  dL/dZ = sum_k d/dZ < 2 W_z (dL/dG)[:, k] + W (dL/dC)[:, k],  W_z e_k >  — one
     lip_zgrad(W mode) call per block of one-hot columns."""
     p = _exact_parts(Z, X, state, alpha, model_type, full_set_size)
+    value, dZ = _exact_value_and_zgrad(p)
+    return value.float(), dZ.reshape(dev_f32(Z).shape)
+
+
+def _exact_value_and_zgrad(p):
     value, L = _exact_value(p)
     alpha, gamma, G, C, d_z, D = p["alpha"], p["gamma"], p["G"], p["C"], p["d_z"], p["D"]
     eye = torch.eye(d_z, device=G.device, dtype=torch.float64)
-    Minv = torch.cholesky_solve(eye, L)
+    Minv = torch.linalg.lu_solve(*L, eye)
+    Minv = 0.5 * (Minv + Minv.T)
     Gbar = (Minv @ G @ Minv) / alpha ** 2 + gamma / alpha ** 3 * (Minv @ (C.T @ C) @ Minv)
     Cbar = -2.0 * gamma / alpha ** 2 * (C @ Minv)
     Wz, W, bz = p["Wz"], p["W"], p["bz"]
@@ -146,7 +162,7 @@ def variational_grad_scalable_exact(Z, X, state, alpha, model_type, key=None, fu
         ub = W._lip_model.w(Cbar[:, k0:k1].T.float().contiguous(), scale=W._lip_scale, batched=True)         # W Cbar[:, k]
         ub = bz.w((2.0 * Gbar[:, k0:k1]).T.float().contiguous(), scale=Wz._lip_scale, add=ub, add_scale=1.0, batched=True)
         dZ += Wz.zgrad(ub, onehot[k0:k1].reshape(nb, d_z))
-    return value.float(), dZ.reshape(dev_f32(Z).shape)
+    return value, dZ
 
 
 def _dense_parts(Z, X, state, alpha, model_type, full_set_size):
@@ -189,20 +205,25 @@ def variational_grad_dense(Z, X, state, alpha, model_type, key=None, full_set_si
 
 
 def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size=None, st_samples=256, slq_samples=2,
-                              slq_num_matvecs=None, *, probes=None):
+                              slq_num_matvecs=None, *, probes=None, gradient="exact"):
     """(loss, dZ) for the scalable objective (train_inducing.py:195).
 
     The loss is alternative_objective_scalable (Hutch++ v2 + GKL logdet on the given probes).  The reference differentiates
-    THROUGH those estimators (QR, Golub-Kahan recurrences, SVD); here dZ is the Hutchinson estimate of the exact gradient
-        d/dZ [ tr(S_X S_Z^-1) + logdet S_Z ] = tr( (S_Z^-1 - S_Z^-1 S_X S_Z^-1) dS_Z )
-                                             ~ mean_b d/dZ < S_Z^-1 eps_b ,  GGN(Z) (eps_b - S_Z^-1 S_X eps_b) >
-    on the same Rademacher probes, with S_Z^-1 applied exactly through the Woodbury identity (:127-132): ONE lip_zgrad call.
-    Same expectation as the reference's gradient when its estimators converge, NOT the same number for a finite probe set —
-    parity is claimed for the deterministic forms above only."""
+    THROUGH those estimators (QR, Golub-Kahan recurrences, SVD) and so gets a noisy gradient of a noisy loss; here dZ is the gradient
+    of the quantity they estimate, tr(S_X S_Z^-1) + logdet S_Z:
+
+      gradient="exact" (default): S_Z depends on Z only through the D x d_z factor W_z, so dL = tr(A dS_Z) with
+        A = S_Z^-1 - S_Z^-1 S_X S_Z^-1 is a finite sum over the d_z columns of W_z: dL/dZ = sum_k d/dZ < 2 beta A W_z e_k, W_z e_k >, with A applied
+        through the Woodbury inverse — d_z columns through lip_zgrad(W mode), deterministic, no probe variance.  It equals the gradient of
+        the exact-Gram form (variational_grad_scalable_exact; the two objectives differ by a Z-independent constant).
+      gradient="hutchinson": mean_b d/dZ < S_Z^-1 eps_b , GGN(Z) (eps_b - S_Z^-1 S_X eps_b) > on the loss's probes (ONE lip_zgrad call,
+        probes sharded over ranks).  Unbiased but, for D ~ 1e6 and tens of probes, dominated by its variance
+        (tools/descent_check.py: |estimate| ~ 1e5 x |true gradient| at the mlp_mnist.yml sizes) — kept for small models / many probes.
+
+    Parity with the reference is claimed for the deterministic forms (oracle: float64 autograd of train_inducing.py:26-84,175-192)."""
     from .ggn import compute_ggn_vp
     N = full_set_size
     Zt, Xt = dev_f32(Z), dev_f32(X)
-    M = int(Zt.shape[0])
     alpha = float(alpha)
     flat, _ = flatten_nn_params(state.params)
     D = int(flat.numel())
@@ -212,6 +233,25 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
     parts = _scalable_parts(Zt, Xt, state, alpha, model_type, N)
     loss = alternative_objective_scalable(Zt, Xt, state, alpha, model_type, key, full_set_size=N, st_samples=st_samples,
                                           slq_samples=slq_samples, slq_num_matvecs=slq_num_matvecs, probes=probes, _parts=parts)
+    if gradient == "exact":
+        # dL = tr(A dS_Z), A = S_Z^-1 - S_Z^-1 S_X S_Z^-1, S_Z = alpha I + beta W_z W_z^T   =>   dL/dZ = sum_k d/dZ < 2 beta A W_z e_k , W_z e_k >.
+        # A is applied to the D-vectors W_z e_k through the Woodbury closure: every (beta^-1 I + alpha^-1 G)^-1 solve sits between
+        # W_z^T and W_z, which annihilate the Gram's null directions (one per softmax point) where that solve is dominated by the
+        # fp32 rounding noise of G at the scale configs.  (The Gram-space form, variational_grad_scalable_exact, applies that inverse
+        # to one-hot columns directly and loses accuracy there when alpha / beta is below the Gram's rounding noise.)
+        Wz, Sz_inv, S_vp, d_z = parts["Wz"], parts["Sz_inv"], parts["S_vp"], parts["d_z"]
+        beta = N / int(Zt.shape[0])
+        blk = _probe_block(D, 256)
+        onehot = torch.eye(d_z, device=Zt.device, dtype=torch.float32)
+        dZ = torch.zeros(int(Zt.shape[0]), Wz._lip_model.Z.shape[1], device=Zt.device, dtype=torch.float32)
+        for k0 in range(0, d_z, blk):
+            E = onehot[k0:min(d_z, k0 + blk)]
+            y = Sz_inv(Wz(E.reshape((-1,) + parts["inner_shape"])).reshape(E.shape[0], D))       # S_Z^-1 W_z e_k
+            y = y - Sz_inv(S_vp(y))                                                               # A W_z e_k
+            dZ += Wz.zgrad(y.mul_(2.0 * beta), E)
+        return loss, dZ.reshape(Zt.shape)
+    if gradient != "hutchinson":
+        raise ValueError(f"gradient must be 'exact' or 'hutchinson', got {gradient!r}")
     S_vp, Sz_inv = parts["S_vp"], parts["Sz_inv"]
     Sz_vp = compute_curvature_approx(state, Zt, model_type, alpha, full_set_size=N)
     from . import _dist
@@ -249,7 +289,7 @@ def _scalable_parts(Zt, Xt, state, alpha, model_type, N):
         return bm.w(x.reshape((V.shape[0],) + inner_shape), scale=Wz._lip_scale, add=V, add_scale=-alpha,
                     batched=True).mul_(-1.0 / alpha ** 2)      # -(1/alpha^2) (Wz x - alpha v) = v/alpha - Wz x / alpha^2
 
-    return dict(S_vp=S_vp, Wz=Wz, WzT=WzT, Sz_inv=Sz_inv, inner_shape=inner_shape, d_z=d_z)
+    return dict(S_vp=S_vp, Wz=Wz, WzT=WzT, Sz_inv=Sz_inv, inner_shape=inner_shape, d_z=d_z, WzTWz=WzTWz)
 
 
 def woodbury_inverse(state, Z, model_type, alpha, full_set_size, X=None):
@@ -263,7 +303,7 @@ def optimize_step(Z, X, map_model_state, alpha, opt_state, rng, zoptimizer, num_
     """train_inducing.py:198-232: one optimiser step on Z.  `zoptimizer` follows the optax protocol the reference uses
     (`update(grads, opt_state, params) -> (updates, new_opt_state)`, updates are ADDED: optax.apply_updates); utils.adam / utils.sgd
     are minimal stand-ins (optax is not in this image).  scalable=False -> variational_grad_dense (:212-222);
-    scalable=True -> variational_grad_scalable (Hutchinson gradient, see there) or, with exact=True, the exact-Gram form."""
+    scalable=True -> variational_grad_scalable (stochastic loss, exact gradient; see there) or, with exact=True, the exact-Gram form for both."""
     if not scalable:
         loss, grads = variational_grad_dense(Z, X, map_model_state, alpha, model_type, rng, full_set_size=full_set_size)
     elif exact:

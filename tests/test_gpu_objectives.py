@@ -70,23 +70,30 @@ def test_optimize_step_dense_and_exact_agree_with_oracle_gradient_step():
     np.testing.assert_allclose(Znew.cpu().numpy() - Z, -1e-2 * np.sign(ref_g), atol=1e-4)
 
 
-def test_scalable_gradient_estimator_is_the_exact_gradient_in_expectation():
-    """variational_grad_scalable: Hutchinson estimate of dL/dZ on the objective's probes.  With the probe set sqrt(D) e_1 .. sqrt(D) e_D
-    the Hutchinson average IS the trace, so the estimator must reproduce the deterministic gradient; with Rademacher probes it
-    is checked loosely (statistical)."""
+def test_scalable_gradient_is_exact_and_hutchinson_form_agrees_in_expectation():
+    """variational_grad_scalable: the loss is the stochastic estimate, dZ the exact gradient of tr(S_X S_Z^-1) + logdet S_Z (default), which
+    must equal the deterministic oracle gradient.  gradient="hutchinson": with the probe set sqrt(D) e_1 .. sqrt(D) e_D the Hutchinson
+    average IS the trace, so it must reproduce the same gradient; with Rademacher probes it is checked loosely (statistical)."""
     from lip_b200 import train_inducing as TI
     ost, lst, Z, X, mt, N, alpha = _case("xor")
     _, ref_g = O.variational_grad_dense(Z, X, ost, alpha, mt, full_set_size=N)
     D = ost.flat()[0].size
-    basis = (math.sqrt(D) * np.eye(D)).astype(np.float32)
-    loss, g = TI.variational_grad_scalable(cu(Z), cu(X), lst, alpha, mt, 0, full_set_size=N, slq_num_matvecs=8, probes=cu(basis))
-    assert rel_err(g.cpu().numpy(), ref_g) < 2e-3
+    probes = np.random.default_rng(33).choice([-1.0, 1.0], size=(64, D)).astype(np.float32)
+    loss, g = TI.variational_grad_scalable(cu(Z), cu(X), lst, alpha, mt, 0, full_set_size=N, slq_num_matvecs=8, probes=cu(probes))
+    assert g.shape == Z.shape and rel_err(g.cpu().numpy(), ref_g) < 2e-3      # every S_Z^-1 application is an fp32 Woodbury solve
     assert math.isfinite(float(loss))
+    basis = (math.sqrt(D) * np.eye(D)).astype(np.float32)
+    _, g = TI.variational_grad_scalable(cu(Z), cu(X), lst, alpha, mt, 0, full_set_size=N, slq_num_matvecs=8, probes=cu(basis),
+                                        gradient="hutchinson")
+    assert rel_err(g.cpu().numpy(), ref_g) < 2e-3
     probes = np.random.default_rng(33).choice([-1.0, 1.0], size=(4096, D)).astype(np.float32)
-    _, g = TI.variational_grad_scalable(cu(Z), cu(X), lst, alpha, mt, 0, full_set_size=N, slq_num_matvecs=8, probes=cu(probes))
+    _, g = TI.variational_grad_scalable(cu(Z), cu(X), lst, alpha, mt, 0, full_set_size=N, slq_num_matvecs=8, probes=cu(probes),
+                                        gradient="hutchinson")
     g = g.cpu().numpy()
     cos = float((g * ref_g).sum() / (np.linalg.norm(g) * np.linalg.norm(ref_g)))
     assert cos > 0.9, (cos, rel_err(g, ref_g))
+    with pytest.raises(ValueError):
+        TI.variational_grad_scalable(cu(Z), cu(X), lst, alpha, mt, 0, full_set_size=N, slq_num_matvecs=8, probes=cu(probes[:32]), gradient="x")
 
 
 @pytest.mark.parametrize("name", ["xor", "sine"])

@@ -41,5 +41,5 @@ for rep in range(3):
     Zc, state, loss = train_inducing.optimize_step(Zc, X, lst, bench.ALPHA, state, rep, opt, None, "classifier", full_set_size=bench.N_FULL,
                                                    scalable=True, st_samples=B, slq_samples=2, slq_num_matvecs=k)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(f"optimize_step (scalable objective + Hutchinson dZ): M={M} |X|={batch} st_samples={B} slq k={k}: loss={float(loss):.6g} {dt:.3f} s "
+    print(f"optimize_step (scalable objective + exact dZ): M={M} |X|={batch} st_samples={B} slq k={k}: loss={float(loss):.6g} {dt:.3f} s "
           f"launches={L.lip_launch_count() - l0} |dZ step|={float((Zc - Zt).norm()):.4g}", flush=True)
