@@ -85,6 +85,21 @@ def _probe_block(D: int, want: int) -> int:
     return max(1, min(int(want), (1 << 28) // max(D, 1)))
 
 
+_PSD_MAX = 4096
+
+
+def _psd_part(G):
+    """G = W_z^T W_z is positive semi-definite with one exact null direction per softmax point, but arrives with fp32 rounding noise
+    (~1e-6 |G|) of either sign.  (I/beta + G/alpha)^-1 amplifies a negative noise eigenvalue without bound once it approaches
+    -alpha/beta (the scale configs: alpha/beta ~ 1e-6), so the float64 small-matrix algebra works on the PSD part of the symmetrised
+    Gram (eigenvalues clamped at 0: the inverse is then bounded by beta in every direction).  d_z <= 4096; larger Grams are used as is."""
+    G = 0.5 * (G + G.T)
+    if G.shape[0] > _PSD_MAX:
+        return G
+    lam, V = torch.linalg.eigh(G)
+    return (V * lam.clamp_min(0.0)) @ V.T
+
+
 def _exact_parts(Z, X, state, alpha, model_type, full_set_size, zside=None):
     """zside: optional (Wz, WzT, WzTWz) already built for the same state / Z (the scalable objective's parts)"""
     N = full_set_size
@@ -103,7 +118,7 @@ def _exact_parts(Z, X, state, alpha, model_type, full_set_size, zside=None):
     d_z, d = M * bz.K, Kx * bx.K
     if WzTWz is None:
         WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)         # :60
-    WzTWz = _f64(WzTWz)
+    WzTWz = _psd_part(_f64(WzTWz))
     WTWz = _f64(build_WTWz(WT, Wz, inner_shape, d=d, dtype=torch.float32, block=1))        # :67
     return dict(N=N, M=M, Kx=Kx, D=D, Wz=Wz, W=W, bz=bz, bx=bx, inner_shape=inner_shape, d_z=d_z, d=d, G=WzTWz, C=WTWz,
                 beta=N / M, gamma=N / Kx, alpha=float(alpha))
@@ -212,13 +227,14 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
     THROUGH those estimators (QR, Golub-Kahan recurrences, SVD) and so gets a noisy gradient of a noisy loss; here dZ is the gradient
     of the quantity they estimate, tr(S_X S_Z^-1) + logdet S_Z:
 
-      gradient="exact" (default): S_Z depends on Z only through the D x d_z factor W_z, so dL = tr(A dS_Z) with
-        A = S_Z^-1 - S_Z^-1 S_X S_Z^-1 is a finite sum over the d_z columns of W_z: dL/dZ = sum_k d/dZ < 2 beta A W_z e_k, W_z e_k >, with A applied
-        through the Woodbury inverse — d_z columns through lip_zgrad(W mode), deterministic, no probe variance.  It equals the gradient of
-        the exact-Gram form (variational_grad_scalable_exact; the two objectives differ by a Z-independent constant).
+      gradient="exact" (default): the Gram-space formulas of variational_grad_scalable_exact (the two objectives differ by a Z-independent
+        constant) on the Grams already built for the Woodbury inverse: float64 small-matrix algebra on the PSD part of the fp32 Grams,
+        d_z one-hot columns through lip_zgrad(W mode).  Deterministic, no probe variance.
+      gradient="woodbury": S_Z depends on Z only through the D x d_z factor W_z, so dL = tr(A dS_Z), A = S_Z^-1 - S_Z^-1 S_X S_Z^-1, is
+        sum_k d/dZ < 2 beta A W_z e_k, W_z e_k > with A pushed through the fp32 Woodbury inverse (no cross-Gram needed; ~50x more rounding error).
       gradient="hutchinson": mean_b d/dZ < S_Z^-1 eps_b , GGN(Z) (eps_b - S_Z^-1 S_X eps_b) > on the loss's probes (ONE lip_zgrad call,
-        probes sharded over ranks).  Unbiased but, for D ~ 1e6 and tens of probes, dominated by its variance
-        (tools/descent_check.py: |estimate| ~ 1e5 x |true gradient| at the mlp_mnist.yml sizes) — kept for small models / many probes.
+        probes sharded over ranks).  Unbiased but, for D ~ 1e6 and tens of probes, dominated by its variance.
+      All three lose accuracy as beta / alpha grows (profiles/r01_descent_check.txt, tools/grad_conditioning.py).
 
     Parity with the reference is claimed for the deterministic forms (oracle: float64 autograd of train_inducing.py:26-84,175-192)."""
     from .ggn import compute_ggn_vp
@@ -234,6 +250,12 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
     loss = alternative_objective_scalable(Zt, Xt, state, alpha, model_type, key, full_set_size=N, st_samples=st_samples,
                                           slq_samples=slq_samples, slq_num_matvecs=slq_num_matvecs, probes=probes, _parts=parts)
     if gradient == "exact":
+        # Gram-space form (float64 small-matrix algebra on the PSD part of the fp32 Grams): 50x less rounding error than pushing A
+        # through fp32 Woodbury solves (tools/grad_conditioning.py: 2.7e-3 vs 1.0e-1 relative at alpha = 1e-3, beta = 500 on a toy model)
+        p = _exact_parts(Zt, Xt, state, alpha, model_type, N, zside=(parts["Wz"], parts["WzT"], parts["WzTWz"]))
+        _, dZ = _exact_value_and_zgrad(p)
+        return loss, dZ.reshape(Zt.shape)
+    if gradient == "woodbury":
         # dL = tr(A dS_Z), A = S_Z^-1 - S_Z^-1 S_X S_Z^-1, S_Z = alpha I + beta W_z W_z^T   =>   dL/dZ = sum_k d/dZ < 2 beta A W_z e_k , W_z e_k >.
         # A is applied to the D-vectors W_z e_k through the Woodbury closure: every (beta^-1 I + alpha^-1 G)^-1 solve sits between
         # W_z^T and W_z, which annihilate the Gram's null directions (one per softmax point) where that solve is dominated by the
@@ -251,7 +273,7 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
             dZ += Wz.zgrad(y.mul_(2.0 * beta), E)
         return loss, dZ.reshape(Zt.shape)
     if gradient != "hutchinson":
-        raise ValueError(f"gradient must be 'exact' or 'hutchinson', got {gradient!r}")
+        raise ValueError(f"gradient must be 'exact', 'woodbury' or 'hutchinson', got {gradient!r}")
     S_vp, Sz_inv = parts["S_vp"], parts["Sz_inv"]
     Sz_vp = compute_curvature_approx(state, Zt, model_type, alpha, full_set_size=N)
     from . import _dist
