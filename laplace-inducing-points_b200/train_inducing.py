@@ -86,6 +86,37 @@ def _probe_block(D: int, want: int) -> int:
 
 
 _PSD_MAX = 4096
+_ACCURATE_MAX_ELEMS = 12 * (1 << 30)     # floats of the materialised factor W_z (48 GB of the 180 GB HBM)
+
+
+def _grams_from_factors(Wz, W, inner_shape_z, inner_shape_x, d_z, d, D):
+    """G = W_z^T W_z and C = W^T W_z as float64 products of the MATERIALISED fp32 factors (rows W e_k from lip_w_apply).
+    lip_gram_wtw returns fl32(W^T (W e_k)): its rounding error (~1e-6 |G|, either sign) lands directly on G's null / small eigenvalues.
+    The float64 Gram of the rounded factor W~ is the exact Gram of a nearby matrix instead: positive semi-definite by construction, and
+    its null directions are perturbed only to second order (|W~ n|^2 ~ 1e-12 |W|^2).  Measured (tools/grad_conditioning.py): 7x smaller
+    gradient error at benign beta/alpha (3.8e-5 -> 5.3e-6), no gain at beta/alpha ~ 1e6, where the fp32 operators downstream of the
+    Grams dominate - so it is an option (accurate_grams=True), not the default.
+    The products are D-chunked float64 GEMMs (library calls, like the d_z x d_z factorisations next to them)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    blk = _probe_block(D, 256)
+    eye_z = torch.eye(d_z, device=dev, dtype=torch.float32)
+    Wz_rows = torch.empty(d_z, D, device=dev, dtype=torch.float32)
+    for k0 in range(0, d_z, blk):
+        E = eye_z[k0:min(d_z, k0 + blk)]
+        Wz_rows[k0:k0 + E.shape[0]] = Wz(E.reshape((-1,) + tuple(inner_shape_z))).reshape(E.shape[0], D)
+    chunk = 1 << 18
+    G = torch.zeros(d_z, d_z, device=dev, dtype=torch.float64)
+    for c0 in range(0, D, chunk):
+        A = Wz_rows[:, c0:c0 + chunk].double()
+        G += A @ A.T
+    C = torch.zeros(d, d_z, device=dev, dtype=torch.float64)
+    eye_x = torch.eye(d, device=dev, dtype=torch.float32)
+    for k0 in range(0, d, blk):
+        E = eye_x[k0:min(d, k0 + blk)]
+        Wx_rows = W(E.reshape((-1,) + tuple(inner_shape_x))).reshape(E.shape[0], D)
+        for c0 in range(0, D, chunk):
+            C[k0:k0 + E.shape[0]] += Wx_rows[:, c0:c0 + chunk].double() @ Wz_rows[:, c0:c0 + chunk].double().T
+    return G, C
 
 
 def _psd_part(G):
@@ -100,7 +131,7 @@ def _psd_part(G):
     return (V * lam.clamp_min(0.0)) @ V.T
 
 
-def _exact_parts(Z, X, state, alpha, model_type, full_set_size, zside=None):
+def _exact_parts(Z, X, state, alpha, model_type, full_set_size, zside=None, accurate=False):
     """zside: optional (Wz, WzT, WzTWz) already built for the same state / Z (the scalable objective's parts)"""
     N = full_set_size
     Zt, Xt = dev_f32(Z), dev_f32(X)
@@ -116,10 +147,14 @@ def _exact_parts(Z, X, state, alpha, model_type, full_set_size, zside=None):
     bz, bx = Wz._lip_model, W._lip_model
     inner_shape = (M,) if model_type == "regressor" else (M, bz.K)
     d_z, d = M * bz.K, Kx * bx.K
-    if WzTWz is None:
-        WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)         # :60
-    WzTWz = _psd_part(_f64(WzTWz))
-    WTWz = _f64(build_WTWz(WT, Wz, inner_shape, d=d, dtype=torch.float32, block=1))        # :67
+    if accurate and (d_z + 256) * D <= _ACCURATE_MAX_ELEMS:
+        WzTWz, WTWz = _grams_from_factors(Wz, W, inner_shape, (Kx,) if model_type == "regressor" else (Kx, bx.K), d_z, d, D)
+    else:
+        if WzTWz is None:
+            WzTWz = build_WTW(Wz, WzT, inner_shape, d_z, dtype=torch.float32, block=1)     # :60
+        WzTWz = _f64(WzTWz)
+        WTWz = _f64(build_WTWz(WT, Wz, inner_shape, d=d, dtype=torch.float32, block=1))    # :67
+    WzTWz = _psd_part(WzTWz)
     return dict(N=N, M=M, Kx=Kx, D=D, Wz=Wz, W=W, bz=bz, bx=bx, inner_shape=inner_shape, d_z=d_z, d=d, G=WzTWz, C=WTWz,
                 beta=N / M, gamma=N / Kx, alpha=float(alpha))
 
@@ -148,13 +183,13 @@ def alternative_objective_scalable_exact(Z, X, state, alpha, model_type, key=Non
     return _exact_value(_exact_parts(Z, X, state, alpha, model_type, full_set_size))[0].float()
 
 
-def variational_grad_scalable_exact(Z, X, state, alpha, model_type, key=None, full_set_size=None, **_):
+def variational_grad_scalable_exact(Z, X, state, alpha, model_type, key=None, full_set_size=None, *, accurate_grams=False, **_):
     """jax.value_and_grad of alternative_objective_scalable_exact with respect to Z -> (loss, dZ).
 
     With Mm = I/beta + G/alpha (G = W_z^T W_z, C = W^T W_z):  dL/dG = Mm^-1 G Mm^-1 / alpha^2 + gamma Mm^-1 C^T C Mm^-1 / alpha^3,
     dL/dC = -2 gamma C Mm^-1 / alpha^2, and  dL/dZ = sum_k d/dZ < 2 W_z (dL/dG)[:, k] + W (dL/dC)[:, k],  W_z e_k >  — one
     lip_zgrad(W mode) call per block of one-hot columns."""
-    p = _exact_parts(Z, X, state, alpha, model_type, full_set_size)
+    p = _exact_parts(Z, X, state, alpha, model_type, full_set_size, accurate=accurate_grams)
     value, dZ = _exact_value_and_zgrad(p)
     return value.float(), dZ.reshape(dev_f32(Z).shape)
 

@@ -17,5 +17,6 @@ for alpha, N in ((0.05, 800), (1e-2, 6000), (1e-3, 6000), (1e-3, 60000)):
     _, ref_g = O.variational_grad_dense(Z, X, ost, alpha, "classifier", full_set_size=N)
     _, g = TI.variational_grad_scalable(cu(Z), cu(X), lst, alpha, "classifier", 0, full_set_size=N, slq_num_matvecs=4, probes=cu(probes), gradient="woodbury")
     _, g2 = TI.variational_grad_scalable_exact(cu(Z), cu(X), lst, alpha, "classifier", 0, full_set_size=N)
-    g = g.cpu().numpy(); g2 = g2.cpu().numpy()
-    print(f"alpha={alpha} N={N} beta={N/12:.0f}: |g_ref|={np.linalg.norm(ref_g):.3e}  woodbury-form rel err {rel_err(g, ref_g):.2e}  gram-form rel err {rel_err(g2, ref_g):.2e}")
+    _, g3 = TI.variational_grad_scalable_exact(cu(Z), cu(X), lst, alpha, "classifier", 0, full_set_size=N, accurate_grams=True)
+    g = g.cpu().numpy(); g2 = g2.cpu().numpy(); g3 = g3.cpu().numpy()
+    print(f"alpha={alpha} N={N} beta={N/12:.0f}: |g_ref|={np.linalg.norm(ref_g):.3e}  woodbury-form rel err {rel_err(g, ref_g):.2e}  gram-form rel err {rel_err(g2, ref_g):.2e}  gram-form with f64 Grams of the fp32 factors {rel_err(g3, ref_g):.2e}")
