@@ -212,22 +212,54 @@ __global__ void rho_kernel(float* __restrict__ ddphi, const float* __restrict__ 
 __global__ void reverse_act_tc_kernel(const float* __restrict__ X, const float* __restrict__ dA_hi, const float* __restrict__ dA_lo,
                                       const float* __restrict__ dphi, const float* __restrict__ rho, float* __restrict__ e_hi,
                                       float* __restrict__ e_lo, float* __restrict__ T, int64_t rows, int64_t M, int cols, int ld) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= rows * cols) return;
-  const int64_t r = i / cols;
-  const int c = (int)(i - r * cols);
-  const int64_t o = r * ld + c, pm = (r % M) * cols + c;
-  const float x = X[o];
-  float da = dA_hi[o];
-  if (dA_lo) da += dA_lo[o];
-  T[o] = __ldg(rho + pm) * da * x;
-  const float e = __ldg(dphi + pm) * x;
-  if (e_lo) {
-    const float h = tf32_round(e);
-    e_hi[o] = h;
-    e_lo[o] = tf32_round(e - h);
-  } else {
-    e_hi[o] = e;
+  // blockIdx.y strides over rows (no per-element division), threadIdx.x over 4-column groups (ld and the buffers are 16-byte aligned)
+  const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c4 >= cols) return;
+  const bool full = c4 + 4 <= cols;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const int64_t o = r * ld + c4, pm = (r % M) * cols + c4;
+    float x[4], da[4], ph[4], rh[4];
+    if (full) {
+      *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(X + o);
+      *reinterpret_cast<float4*>(da) = *reinterpret_cast<const float4*>(dA_hi + o);
+      if (dA_lo) {
+        const float4 l = *reinterpret_cast<const float4*>(dA_lo + o);
+        da[0] += l.x; da[1] += l.y; da[2] += l.z; da[3] += l.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = c4 + j < cols;
+        x[j] = ok ? X[o + j] : 0.f;
+        da[j] = ok ? dA_hi[o + j] + (dA_lo ? dA_lo[o + j] : 0.f) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {            // [M, cols] factors: cols need not be a multiple of 4
+      const bool ok = c4 + j < cols;
+      ph[j] = ok ? __ldg(dphi + pm + j) : 0.f;
+      rh[j] = ok ? __ldg(rho + pm + j) : 0.f;
+    }
+    float t[4], eh[4], el[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      t[j] = rh[j] * da[j] * x[j];
+      const float e = ph[j] * x[j];
+      if (e_lo) { eh[j] = tf32_round(e); el[j] = tf32_round(e - eh[j]); } else { eh[j] = e; el[j] = 0.f; }
+    }
+    if (full) {
+      *reinterpret_cast<float4*>(T + o) = *reinterpret_cast<const float4*>(t);
+      *reinterpret_cast<float4*>(e_hi + o) = *reinterpret_cast<const float4*>(eh);
+      if (e_lo) *reinterpret_cast<float4*>(e_lo + o) = *reinterpret_cast<const float4*>(el);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c4 + j < cols) {
+          T[o + j] = t[j];
+          e_hi[o + j] = eh[j];
+          if (e_lo) e_lo[o + j] = el[j];
+        }
+    }
   }
 }
 
@@ -361,7 +393,8 @@ int zgrad_tc(lip_model* m, int32_t mode, const float* X1, const float* X2, float
           int rc = gemm_simt(p, st);
           if (rc) return rc;
         }
-        reverse_act_tc_kernel<<<blocks(B * M * Ld.in), 256, 0, st>>>(X, keep_hi[sg][l - 1], tc ? keep_lo[sg][l - 1] : nullptr,   // dA_l has a lo part iff its consumer (layer l) is a tensor-core layer
+        const dim3 rgrid((unsigned)ceil_div(ceil_div(Ld.in, 4), 128), (unsigned)(B * M < 16384 ? B * M : 16384));
+        reverse_act_tc_kernel<<<rgrid, 128, 0, st>>>(X, keep_hi[sg][l - 1], tc ? keep_lo[sg][l - 1] : nullptr,   // dA_l has a lo part iff its consumer (layer l) is a tensor-core layer
                                                                     
                                                                      m->dphi[l - 1], m->rho[l - 1], en_hi, en_lo, T, B * M, M, Ld.in, in_ld);
         LIP_LAUNCH_CHECK();
