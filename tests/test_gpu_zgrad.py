@@ -91,6 +91,21 @@ def test_zgrad_tensor_core_path_matches_oracle_and_simt(name):
     assert rel_err(WTf.zgrad(cu(Y), cu(V)).cpu().numpy(), WTz_ref(Y, V)) < TOL
 
 
+def test_zgrad_gelu_model_on_the_tensor_path_falls_back_to_simt():
+    """A GELU regressor wide enough for the tcgen05 path: phi''/phi' is unbounded at GELU's stationary point, so lip_zgrad keeps dh and
+    runs the fp32 SIMT recurrences even though the model's operators are on the tensor cores.  Single probe (B = 1) as well."""
+    from lip_b200 import ggn
+    ost, lst = make_pair("regressor", hidden=[128, 128], n_out=1, in_dim=96, seed=88, logvar=0.2)
+    rng = np.random.default_rng(89)
+    Z = rng.standard_normal((70, 96)).astype(np.float32)
+    D = ost.flat()[0].size
+    U, V = _probes(D, 1, 90)
+    vp = ggn.compute_ggn_vp(lst, cu(Z), "regressor", full_set_size=700)
+    assert "tcgen05" in vp._lip_model.path_name()
+    ref = O.ggn_vp_zgrad(ost, Z, "regressor", U, V, full_set_size=700)
+    assert rel_err(vp.zgrad(cu(U[0]), cu(V[0])).cpu().numpy(), ref) < TOL
+
+
 def test_jvp_zgrad_matches_oracle():
     from lip_b200 import _cabi, ggn
     ost, lst, Z, mt, N = _setup("mlp_ragged")
