@@ -106,6 +106,38 @@ def test_zgrad_gelu_model_on_the_tensor_path_falls_back_to_simt():
     assert rel_err(vp.zgrad(cu(U[0]), cu(V[0])).cpu().numpy(), ref) < TOL
 
 
+def test_zgrad_is_cuda_graph_capturable():
+    """lip_zgrad keeps the hot-call contract of include/lip_b200.h (no allocation / host sync inside the library; phi'' and phi''/phi'
+    are bind-time state): one call captured into a CUDA graph replays to the same result on both executions."""
+    from lip_b200 import ggn
+    hidden, n_out, in_dim, M, N = TC_ZCONFIGS["tc_ragged"]
+    ost, lst = make_pair("large", hidden=hidden, n_out=n_out, in_dim=in_dim, seed=77)
+    rng = np.random.default_rng(91)
+    Z = cu(rng.random((M, in_dim)).astype(np.float32))
+    D = ost.flat()[0].size
+    for tp in (False, True):
+        vp = ggn.compute_ggn_vp(lst, Z, "classifier", full_set_size=N, tensor_path=tp)
+        U, V = (cu(x) for x in _probes(D, 3, 92))
+        eager = vp.zgrad(U, V).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            vp.zgrad(U, V)                              # warm-up on the capture stream (workspace growth)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = vp.zgrad(U, V)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert rel_err(out.cpu().numpy(), eager.cpu().numpy()) < 1e-6
+        V2 = cu(_probes(D, 3, 93)[1])
+        expect = vp.zgrad(U, V2).clone()
+        V.copy_(V2)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert rel_err(out.cpu().numpy(), expect.cpu().numpy()) < 1e-6
+
+
 def test_jvp_zgrad_matches_oracle():
     from lip_b200 import _cabi, ggn
     ost, lst, Z, mt, N = _setup("mlp_ragged")
