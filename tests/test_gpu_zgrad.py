@@ -60,6 +60,8 @@ TC_ZCONFIGS = {
     # name: (hidden, n_out, in_dim, M, N, activation model)
     "tc_ragged": ([200, 72, 136], 7, 100, 150, 900),
     "tc_m50": ([256, 128, 64], 10, 784, 50, 60000),
+    "tc_simt_bottom": ([128, 64], 5, 45, 70, 500),      # first layer (in = 45) and head on SIMT, a tensor-core layer between them
+    "tc_top": ([128], 64, 96, 80, 800),                 # the logit layer itself on the tensor cores (K = 64 outputs)
 }
 
 
