@@ -583,13 +583,14 @@ int gemm_simt(const GemmProblem& p_in, cudaStream_t stream) {
   // gradients of narrow layers: A = cached activations / patches, B = the probe's deltas) is one wide GEMM
   //   C[m, (z, n)] = sum_k A[m, k] B[z][k, n]
   // with the batch folded into the column index: the 128 x 128 tiles reuse each A element 128 times instead of <= 16 and the
-  // shared operand is staged once per 128 / N probes.  LIP_FOLD_N=0 disables it.
+  // shared operand is staged once per 128 / N probes.  Long contractions only (conv weight gradients, K = points x pixels): for the
+  // K = 512 head layer of the MNIST MLP the 256 skinny GEMMs were measured 1 % faster per lip_ggn_vp call.  LIP_FOLD_N=0 disables it.
   static const bool fold_on = !(getenv("LIP_FOLD_N") && atoi(getenv("LIP_FOLD_N")) == 0);
   GemmProblem p = p_in;
   int fold_nin = 0;
   long long fold_bsz = 0;
   if (fold_on && p.N <= 16 && p.batch >= 8 && p.A1.sz == 0 && !p.A2.ptr && !p.A1.conv.mode && p.B1.s1 == 1 && !p.epi.bias &&
-      !p.epi.mask && p.epi.act < 0 && !p.epi.C_lo && !p.epi.dphi_out && p.batch * p.N < (1LL << 30) && p.K >= 64) {
+      !p.epi.mask && p.epi.act < 0 && !p.epi.C_lo && !p.epi.dphi_out && p.batch * p.N < (1LL << 30) && p.K >= 2048) {
     fold_nin = (int)p.N;
     fold_bsz = p.B1.sz;
     p.N = p.batch * p.N;
