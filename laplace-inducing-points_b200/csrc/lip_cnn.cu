@@ -47,6 +47,30 @@ __global__ void im2col_kernel(const float* __restrict__ in, float* __restrict__ 
   }
 }
 
+// Same result, one image per blockIdx.y step: the element index inside an image fits 32 bits, so the (pixel, tap, channel)
+// decomposition is four multiply-shift divisions (FastDiv) instead of five 64-bit divisions per element - the 64-bit form was
+// integer-bound at 0.9 TB/s of patch writes (profiles/r01_launches_lenet5_summary.txt).
+__global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict__ in, float* __restrict__ out, long long MZ, int per_img,
+                                                         int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kw, int Ho, int Wo,
+                                                         lip::FastDiv dKc, lip::FastDiv dRow, lip::FastDiv dC, lip::FastDiv dWo) {
+  (void)Ho;
+  for (long long mz = blockIdx.y; mz < MZ; mz += gridDim.y) {
+    const float* img = in + mz * (long long)Hi * Wi * C;
+    float* o = out + mz * (long long)per_img;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < (uint32_t)per_img; e += gridDim.x * blockDim.x) {
+      uint32_t r, kc, dy, j, dx, c, y, x;
+      dKc.divmod(e, r, kc);        // output pixel, patch column
+      dRow.divmod(kc, dy, j);      // tap row, (dx, c)
+      dC.divmod(j, dx, c);
+      dWo.divmod(r, y, x);
+      const int yi = (int)y * stride + (int)dy - pad_h, xi = (int)x * stride + (int)dx - pad_w;
+      float v = 0.f;
+      if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) v = __ldg(img + ((long long)yi * Wi + xi) * C + c);
+      o[e] = v;
+    }
+  }
+}
+
 // tin[mz][yi][xi][c] (+)= sum over (dy, dx) with y*stride = yi + pad_h - dy, x*stride = xi + pad_w - dx, 0 <= y < Ho, 0 <= x < Wo
 //                         of col[(mz*Ho + y)*Wo + x][(dy*kw + dx)*C + c]          (gather form: deterministic, no atomics)
 __global__ void col2im_kernel(const float* __restrict__ col, float* __restrict__ tin, long long total, int Hi, int Wi, int C,
@@ -120,6 +144,19 @@ namespace lip {
 int im2col(const float* in, float* out, int64_t MZ, int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kh, int kw,
            int Ho, int Wo, cudaStream_t st) {
   const long long total = (long long)MZ * Ho * Wo * kh * kw * C;
+  const long long per_img = (long long)Ho * Wo * kh * kw * C;
+  if (per_img < (1LL << 31) && MZ > 0) {
+    const int Kc = kh * kw * C;
+    long long gx = (per_img + 255) / 256;
+    if (gx > 64) gx = 64;
+    long long gy = MZ < 148 * 32 / gx + 1 ? MZ : 148 * 32 / gx + 1;
+    if (gy > 65535) gy = 65535;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    im2col_img_kernel<<<grid, 256, 0, st>>>(in, out, MZ, (int)per_img, Hi, Wi, C, pad_h, pad_w, stride, kw, Ho, Wo, FastDiv((uint32_t)Kc),
+                                            FastDiv((uint32_t)(kw * C)), FastDiv((uint32_t)C), FastDiv((uint32_t)Wo));
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
   im2col_kernel<<<ew_grid(total), 256, 0, st>>>(in, out, total, Hi, Wi, C, pad_h, pad_w, stride, kh, kw, Ho, Wo);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
