@@ -132,6 +132,26 @@ __global__ void unpool_mask_kernel(const float* __restrict__ tin, const float* _
   }
 }
 
+// 32-bit form: blockIdx.y strides over the batch entries z, the element index inside one entry (per_z < 2^31) is decomposed with
+// multiply-shift divisions
+__global__ void __launch_bounds__(256) unpool_mask_z_kernel(const float* __restrict__ tin, const float* __restrict__ dphi,
+                                                            float* __restrict__ d, long long B, int per_z, long long tin_per_z,
+                                                            int Ho, int Wo, int C, lip::FastDiv dC, lip::FastDiv dWo, lip::FastDiv dHo) {
+  const int Hp = Ho / 2, Wp = Wo / 2;
+  for (long long z = blockIdx.y; z < B; z += gridDim.y) {
+    const float* ti = tin + z * tin_per_z;
+    float* dz = d + z * (long long)per_z;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < (uint32_t)per_z; e += gridDim.x * blockDim.x) {
+      uint32_t t, c, x, y, m;
+      dC.divmod(e, t, c);
+      dWo.divmod(t, t, x);
+      dHo.divmod(t, m, y);
+      const float v = 0.25f * __ldg(ti + (((long long)m * Hp + (y >> 1)) * Wp + (x >> 1)) * C + c);
+      dz[e] = v * __ldg(dphi + e);
+    }
+  }
+}
+
 inline unsigned ew_grid(long long total) {
   long long g = (total + 255) / 256;
   if (g > 148ll * 32) g = 148ll * 32;
@@ -187,6 +207,17 @@ int launch_avgpool(const float* in, float* out, int64_t MZ, const ConvStage& s, 
 // d (gradient w.r.t. the pre-activation of stage s, [B, M*P, cout]) from tin (gradient w.r.t. the stage's output)
 int launch_unpool_mask(const float* tin, float* d, int64_t B, int64_t M, const ConvStage& s, cudaStream_t st) {
   const long long per_z = (long long)M * s.P * s.cout, total = per_z * B;
+  if (s.pool && per_z < (1LL << 31)) {
+    long long gx = (per_z + 255) / 256;
+    if (gx > 296) gx = 296;
+    long long gy = B < 148 * 32 / gx + 1 ? B : 148 * 32 / gx + 1;
+    if (gy > 65535) gy = 65535;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    unpool_mask_z_kernel<<<grid, 256, 0, st>>>(tin, s.dphi, d, B, (int)per_z, (long long)M * s.Hp * s.Wp * s.cout, s.Ho, s.Wo, s.cout,
+                                               FastDiv((uint32_t)s.cout), FastDiv((uint32_t)s.Wo), FastDiv((uint32_t)s.Ho));
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
   unpool_mask_kernel<<<ew_grid(total), 256, 0, st>>>(tin, s.dphi, d, total, per_z, s.Ho, s.Wo, s.cout, s.pool);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
