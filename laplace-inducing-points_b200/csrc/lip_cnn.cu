@@ -99,6 +99,36 @@ __global__ void col2im_kernel(const float* __restrict__ col, float* __restrict__
   }
 }
 
+// stride-1 form with one image per blockIdx.y step and multiply-shift index decomposition (no division in the tap loop)
+__global__ void __launch_bounds__(256) col2im_s1_kernel(const float* __restrict__ col, float* __restrict__ tin, long long MZ, int per_img,
+                                                        int Hi, int Wi, int C, int pad_h, int pad_w, int kh, int kw, int Ho, int Wo,
+                                                        int accumulate, lip::FastDiv dC, lip::FastDiv dWi) {
+  (void)Hi;
+  const int Kc = kh * kw * C;
+  for (long long mz = blockIdx.y; mz < MZ; mz += gridDim.y) {
+    const float* cimg = col + mz * (long long)Ho * Wo * Kc;
+    float* o = tin + mz * (long long)per_img;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < (uint32_t)per_img; e += gridDim.x * blockDim.x) {
+      uint32_t t, c, yi, xi;
+      dC.divmod(e, t, c);
+      dWi.divmod(t, yi, xi);
+      float acc = 0.f;
+      const int dy0 = (int)yi + pad_h - (Ho - 1) > 0 ? (int)yi + pad_h - (Ho - 1) : 0;
+      const int dy1 = (int)yi + pad_h < kh - 1 ? (int)yi + pad_h : kh - 1;
+      const int dx0 = (int)xi + pad_w - (Wo - 1) > 0 ? (int)xi + pad_w - (Wo - 1) : 0;
+      const int dx1 = (int)xi + pad_w < kw - 1 ? (int)xi + pad_w : kw - 1;
+      for (int dy = dy0; dy <= dy1; ++dy) {
+        const int y = (int)yi + pad_h - dy;
+        for (int dx = dx0; dx <= dx1; ++dx) {
+          const int x = (int)xi + pad_w - dx;
+          acc += __ldg(cimg + ((long long)y * Wo + x) * Kc + (dy * kw + dx) * C + c);
+        }
+      }
+      o[e] = accumulate ? o[e] + acc : acc;
+    }
+  }
+}
+
 // out[mz][yp][xp][c] = mean of the 2x2 window of in[mz][.][.][c]   (in: Ho x Wo, out: Ho/2 x Wo/2)
 __global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int Ho, int Wo, int C) {
   const int Hp = Ho / 2, Wp = Wo / 2;
@@ -184,6 +214,18 @@ int im2col(const float* in, float* out, int64_t MZ, int Hi, int Wi, int C, int p
 int col2im(const float* col, float* tin, int64_t MZ, int Hi, int Wi, int C, int pad_h, int pad_w, int stride, int kh, int kw,
            int Ho, int Wo, int accumulate, cudaStream_t st) {
   const long long total = (long long)MZ * Hi * Wi * C;
+  const long long per_img = (long long)Hi * Wi * C;
+  if (stride == 1 && per_img < (1LL << 31) && MZ > 0) {
+    long long gx = (per_img + 255) / 256;
+    if (gx > 64) gx = 64;
+    long long gy = MZ < 148 * 32 / gx + 1 ? MZ : 148 * 32 / gx + 1;
+    if (gy > 65535) gy = 65535;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    col2im_s1_kernel<<<grid, 256, 0, st>>>(col, tin, MZ, (int)per_img, Hi, Wi, C, pad_h, pad_w, kh, kw, Ho, Wo, accumulate,
+                                           FastDiv((uint32_t)C), FastDiv((uint32_t)Wi));
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
   col2im_kernel<<<ew_grid(total), 256, 0, st>>>(col, tin, total, Hi, Wi, C, pad_h, pad_w, stride, kh, kw, Ho, Wo, accumulate);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
