@@ -545,6 +545,59 @@ __global__ void __launch_bounds__(NT) gemm_rowthread_kernel(DevGemm g) {
   }
 }
 
+// Short-contraction form (K <= 32, both operands k-contiguous, 32 <= N <= 1024): C[m][n] = sum_k A[m][k] B[n][k] is write-bound
+// (the delta back-propagation of a narrow conv layer: K = cout = 16, N = kh*kw*cin = 150, 3 GB of patch gradients per call), so the
+// whole B sits transposed in shared memory, a thread owns 4 consecutive columns of a row and a warp's stores cover consecutive
+// addresses; the 128 x 128 tile kernel reached 0.3 TB/s on it (half-empty second column tile, strided epilogue stores).
+constexpr int SK_ROWS = 256;
+
+__global__ void __launch_bounds__(NT) gemm_smallk_kernel(DevGemm g) {
+  extern __shared__ __align__(16) float sk_B[];      // [K][Np]
+  const int K = g.K1, N = g.N, Np = (N + 3) & ~3;
+  const long long z = blockIdx.z;
+  const float* Ap = g.A1.ptr + z * g.A1.sz;
+  const float* Bp = g.B1.ptr + z * g.B1.sz;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * Np; i += NT) {
+    const int k = i / Np, n = i - k * Np;
+    sk_B[i] = n < N ? __ldg(Bp + (long long)k * g.B1.s0 + (long long)n * g.B1.s1) : 0.f;
+  }
+  __syncthreads();
+  const int ng = Np >> 2;
+  const int rif = NT / ng;                 // rows in flight per block (>= 1: N <= 1024)
+  const int cgp = tid % ng, rl = tid / ng;
+  if (rl >= rif) return;
+  const int n0 = cgp << 2;
+  const long long r_end = (long long)(blockIdx.x + 1) * SK_ROWS < g.M ? (long long)(blockIdx.x + 1) * SK_ROWS : g.M;
+  float* Cz = g.C + z * g.c_sz;
+  const bool pair_ok = ((g.c_sm & 1) == 0) && ((g.c_sz & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 7) == 0);
+  for (long long r = (long long)blockIdx.x * SK_ROWS + rl; r < r_end; r += rif) {
+    const float* a = Ap + r * g.A1.s0;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+      const float av = __ldg(a + k);
+      const float4 b = *reinterpret_cast<const float4*>(&sk_B[k * Np + n0]);
+      acc0 = fmaf(av, b.x, acc0); acc1 = fmaf(av, b.y, acc1); acc2 = fmaf(av, b.z, acc2); acc3 = fmaf(av, b.w, acc3);
+    }
+    float v[4] = {g.scale * acc0, g.scale * acc1, g.scale * acc2, g.scale * acc3};
+    if (g.mask) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < N) v[j] *= __ldg(g.mask + r * g.mask_sm + n0 + j);
+    }
+    float* c = Cz + r * g.c_sm + n0;
+    if (pair_ok && n0 + 3 < N) {
+      *reinterpret_cast<float2*>(c) = make_float2(v[0], v[1]);
+      *reinterpret_cast<float2*>(c + 2) = make_float2(v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < N) c[j] = v[j];
+    }
+  }
+}
+
 // C = epilogue( sum_slices part[slice][z][m][n] ), slices summed in a fixed order
 __global__ void splitk_reduce_kernel(DevGemm g, long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -627,6 +680,16 @@ int gemm_simt(const GemmProblem& p_in, cudaStream_t stream) {
   g.act = p.epi.act; g.dphi_out = p.epi.dphi_out; g.C_lo = p.epi.C_lo;
   g.ksplit = 1; g.part = nullptr; g.part_sz = 0;
   const bool gather = p.A1.conv.mode != 0 || p.A2.conv.mode != 0;
+
+  if (!p.A2.ptr && !gather && a_kc && b_kc && p.K <= 32 && p.N >= 32 && p.N <= 1024 && !p.epi.bias && p.epi.act < 0 && !p.epi.add &&
+      !p.epi.C_lo && !p.epi.dphi_out && !fold_nin && p.batch <= 65535 && p.A1.s1 == 1) {
+    const size_t smem = sizeof(float) * (size_t)p.K * (size_t)((p.N + 3) & ~3);
+    if (smem > 48 * 1024) LIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_smallk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    dim3 kg((unsigned)ceil_div(p.M, SK_ROWS), 1, (unsigned)p.batch);
+    gemm_smallk_kernel<<<kg, NT, smem, stream>>>(g);
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
 
   // split-K decision: few tiles, long K, scratch available, single operand pair, batch in one launch
   const bool skinny = p.N <= SB_N;
