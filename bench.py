@@ -393,15 +393,9 @@ def run_b200(args):
         sa = math.sqrt(ALPHA)
         d = M_POINTS * DIMS[-1]
 
-        @matfree.batched
-        def Av(v):                                    # bidiag_target: v -> [sqrt(alpha) v ; Wz^T v]   (train_inducing.py:166-169)
-            v = v.reshape(-1, D)
-            return torch.cat([sa * v, WzT(v).reshape(v.shape[0], d)], dim=1)
-
-        @matfree.batched
-        def vA(u):                                    # its transpose (jax.vjp in the reference)
-            u = u.reshape(-1, D + d)
-            return Wz(u[:, D:].reshape(-1, M_POINTS, DIMS[-1])).add_(u[:, :D], alpha=sa)
+        # bidiag_target v -> [sqrt(alpha) v ; Wz^T v] (train_inducing.py:166-169) and its transpose (jax.vjp in the reference)
+        Av = matfree.gkl_target(WzT, Wz, ALPHA)
+        vA = Av._lip_transpose
 
         integrand = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(k))
         quad = matfree.batched(lambda mv, E: integrand(mv, E, vA))

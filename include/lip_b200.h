@@ -239,6 +239,88 @@ int lip_tridiag_funm(const float* diag, const float* off, int64_t k, int64_t B, 
 int lip_bidiag_to_tridiag(const float* alphas, const float* betas, float* tdiag, float* toff, int64_t k,
                           int64_t B, lip_stream_t stream);
 
+/* ---- composite Krylov entry points -------------------------------------------------------------------------------
+ * ONE call enqueues a whole recurrence on the caller's stream: no host synchronisation (lip_cg_solve: optional), no
+ * allocation (caller workspace, lip_krylov_workspace_bytes), every scalar on the device, CUDA-graph capturable for the
+ * built-in operator kinds.  These are what an XLA custom call would bind for matfree.decomp.tridiag_sym / decomp.bidiag /
+ * funm.* and jax.scipy.sparse.linalg.cg at the reference's call sites (src/sample.py:71,113-115; src/train_inducing.py:156-163;
+ * src/stochtrace.py:146,192; src/matfree_monkeypatch.py:25-41). */
+
+/* A linear operator for the Krylov routines. */
+typedef enum {
+  LIP_LINOP_GGN = 0,        /* v[D] -> scale * sum_i J_i^T H_i J_i v + alpha v   (curvature_vp, src/lla.py:19-23; symmetric) */
+  LIP_LINOP_GKL = 1,        /* v[D] -> [sqrt(alpha) v ; scale * W^T v] in R^{D+d}  (bidiag_target, src/train_inducing.py:166-169);
+                               transpose u -> sqrt(alpha) u[:D] + scale * W u[D:]  (what jax.vjp derives inside matfree) */
+  LIP_LINOP_DENSE_SYM = 2,  /* u[n] -> alpha u + beta * G u, G [n,n] symmetric, row-major (inner_fun_flat, src/sample.py:120-125) */
+  LIP_LINOP_CALLBACK = 3    /* a caller function (any other composition, e.g. S_X S_Z^{-1} of src/train_inducing.py:134-135) */
+} lip_linop_kind;
+
+/* CALLBACK protocol: the library copies the operator's input to cb_in ([B, n] contiguous; transpose: cb_in_t [B, n_out]), calls
+ * fn(ctx, transpose, B, stream), and reads the result from cb_out ([B, n_out]; transpose: cb_out_t [B, n]).  fn enqueues its
+ * work on `stream` and returns 0, or non-zero to abort the recurrence.  symmetric != 0: fn is never called with transpose = 1. */
+typedef int (*lip_matvec_fn)(void* ctx, int32_t transpose, int64_t B, lip_stream_t stream);
+
+typedef struct {
+  int32_t kind;          /* lip_linop_kind */
+  int32_t symmetric;     /* CALLBACK: 1 if A = A^T */
+  lip_model* model;      /* GGN, GKL: a bound model */
+  float scale;           /* GGN: recal = N/M (x exp(-logvar));  GKL: the scale of W (sqrt(N/M); 1 at the reference's call site) */
+  float alpha;           /* GGN: + alpha v;  GKL: alpha (its square root is taken inside);  DENSE_SYM: alpha */
+  float beta;            /* DENSE_SYM */
+  const float* dense;    /* DENSE_SYM: G, device */
+  int64_t n;             /* DENSE_SYM, CALLBACK: input dimension (model kinds: D) */
+  int64_t n_out;         /* CALLBACK: output dimension */
+  lip_matvec_fn fn;      /* CALLBACK */
+  void* ctx;
+  float *cb_in, *cb_out, *cb_in_t, *cb_out_t;   /* CALLBACK: device buffers, see above (the _t pair may be NULL when symmetric) */
+} lip_linop;
+
+typedef enum {
+  LIP_KRYLOV_LANCZOS = 0, LIP_KRYLOV_GKL = 1, LIP_KRYLOV_SLQ_LANCZOS = 2, LIP_KRYLOV_SLQ_GKL = 3, LIP_KRYLOV_FUNM = 4,
+  LIP_KRYLOV_CG = 5, LIP_KRYLOV_HUTCHPP = 6, LIP_KRYLOV_APPLY = 7
+} lip_krylov_routine;
+/* workspace bytes of the routine below for depth k (CG, APPLY: ignored; HUTCHPP: s1) and B columns */
+size_t lip_krylov_workspace_bytes(const lip_linop* op, int32_t routine, int64_t k, int64_t B);
+
+/* out = A in (transpose = 0: in [B, n] -> out [B, n_out]) or A^T in (transpose = 1), both contiguous: the operator on its own. */
+int lip_linop_apply(const lip_linop* op, const float* in, float* out, int64_t B, int32_t transpose, void* workspace,
+                    size_t workspace_bytes, lip_stream_t stream);
+
+/* matfree.decomp.tridiag_sym(k) with full re-orthogonalisation (passes = 2: CGS2, what the Python mirror used; 1: CGS), batched:
+ * q_0 = v0/|v0|; for i < k: w = A q_i; h = Q^T w (first pass = Arnoldi column); w -= Q h [twice]; q_{i+1} = w/|w|.
+ * diag[B,k], off[B,k-1] receive T = (H + H^T)/2 on its three diagonals; norm0[B] (optional) = |v0|.
+ * Q [B, k, ldq] is the caller-owned basis (16-byte aligned, ldq % 4 == 0, rows zero-padded).  v0: [B, ldv0]. */
+int lip_lanczos_tridiag(const lip_linop* op, const float* v0, int64_t ldv0, int64_t k, int64_t B, int32_t passes, float* Q,
+                        int64_t ldq, float* diag, float* off, float* norm0, void* workspace, size_t workspace_bytes,
+                        lip_stream_t stream);
+
+/* matfree.decomp.bidiag(k): Golub-Kahan-Lanczos with full re-orthogonalisation of both bases, batched.  alphas[B,k] (diagonal),
+ * betas[B,k] (betas[:,0] = 0; betas[:,i] = super-diagonal entry (i-1, i)).  Us [B,k,ldu], Vs [B,k,ldv] caller-owned bases. */
+int lip_gkl_bidiag(const lip_linop* op, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* Us, int64_t ldu, float* Vs,
+                   int64_t ldv, float* alphas, float* betas, float* norm0, void* workspace, size_t workspace_bytes,
+                   lip_stream_t stream);
+
+/* Stochastic-Lanczos-quadrature integrand for every probe row: quad_out[b] = |v_b|^2 e1^T f(T_b) e1.
+ * form LIP_SLQ_LANCZOS: T from lip_lanczos_tridiag (matfree funm.integrand_funm_sym; with fn = log, clip_min = 1 the patched
+ *   integrand_funm_sym_logdet of src/matfree_monkeypatch.py:25-41);
+ * form LIP_SLQ_GKL: T = B^T B from lip_gkl_bidiag (funm.integrand_funm_product_logdet, src/train_inducing.py:156-157).
+ * fn / clip_min as lip_tridiag_funm.  The mean over probes (matfree stochtrace.estimator) is the caller's (and, sharded over
+ * GPUs, one all-reduce of B floats). */
+typedef enum { LIP_SLQ_LANCZOS = 0, LIP_SLQ_GKL = 1 } lip_slq_form;
+int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form, int32_t fn,
+                       float clip_min, float* quad_out, void* workspace, size_t workspace_bytes, lip_stream_t stream);
+
+/* matfree.funm.funm_lanczos_sym: out[b,:] = |v_b| Q_b f(T_b) e1 ~= f(A) v_b   (src/sample.py:113-115: f = 1/sqrt, clip_min = 1). */
+int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv, int64_t k, int64_t B, int32_t fn, float clip_min,
+                     float* out, int64_t ldo, void* workspace, size_t workspace_bytes, lip_stream_t stream);
+
+/* jax.scipy.sparse.linalg.cg(A, b): x0 = 0, stop when r.r <= max(tol^2 b.b, atol^2) or after maxiter iterations (< 0: 10 n).
+ * b, x: [B, n] contiguous.  check_every > 0: the host polls a pinned flag every check_every iterations and stops enqueueing once
+ * every column has converged (it synchronises with the stream before returning); check_every = 0: exactly maxiter masked
+ * iterations are enqueued and the call never waits (graph-capturable).  iters_out: int32 [B] device, optional. */
+int lip_cg_solve(const lip_linop* op, const float* b, float* x, int64_t B, float tol, float atol, int64_t maxiter,
+                 int32_t check_every, int32_t* iters_out, void* workspace, size_t workspace_bytes, lip_stream_t stream);
+
 /* ---- self test of the tensor-core GEMM (3xTF32 tcgen05) against the SIMT fp32 GEMM; returns max rel err
  * through *max_rel_err.  variant: 0 = JVP-type (A K-major, B N-major), 1 = weight-grad type (both MN-major),
  * 2 = delta-backprop type (both K-major). */

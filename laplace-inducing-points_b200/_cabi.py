@@ -17,6 +17,9 @@ REGRESSOR, CLASSIFIER = 0, 1
 FACTOR_NONE, FACTOR_SQRT = 0, 1
 ZGRAD_GGN, ZGRAD_WT, ZGRAD_W, ZGRAD_JVP = 0, 1, 2, 3
 FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY = 0, 1, 2, 3
+LINOP_GGN, LINOP_GKL, LINOP_DENSE_SYM, LINOP_CALLBACK = 0, 1, 2, 3
+KRYLOV_LANCZOS, KRYLOV_GKL, KRYLOV_SLQ_LANCZOS, KRYLOV_SLQ_GKL, KRYLOV_FUNM, KRYLOV_CG, KRYLOV_HUTCHPP, KRYLOV_APPLY = 0, 1, 2, 3, 4, 5, 6, 7
+SLQ_LANCZOS, SLQ_GKL = 0, 1
 
 
 class LayerDesc(C.Structure):
@@ -26,6 +29,21 @@ class LayerDesc(C.Structure):
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# lip_matvec_fn: int fn(void* ctx, int32_t transpose, int64_t B, lip_stream_t stream)
+MATVEC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p)
+
+
+class LinOp(C.Structure):
+    """lip_linop of include/lip_b200.h"""
+    _fields_ = [("kind", C.c_int32), ("symmetric", C.c_int32), ("model", C.c_void_p),
+                ("scale", C.c_float), ("alpha", C.c_float), ("beta", C.c_float),
+                ("dense", C.c_void_p), ("n", C.c_int64), ("n_out", C.c_int64),
+                ("fn", MATVEC_FN), ("ctx", C.c_void_p),
+                ("cb_in", C.c_void_p), ("cb_out", C.c_void_p), ("cb_in_t", C.c_void_p), ("cb_out_t", C.c_void_p)]
+
+
+_LP = C.POINTER(LinOp)
 
 # name -> (restype, argtypes); every symbol declared in include/lip_b200.h
 SIGNATURES = {
@@ -67,6 +85,13 @@ SIGNATURES = {
     "lip_tridiag_scratch_bytes": (_SZ, [_I64, _I64, _I32]),
     "lip_tridiag_funm": (C.c_int, [_P, _P, _I64, _I64, _I32, _F, _P, _P, _P, _P, _P]),
     "lip_bidiag_to_tridiag": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
+    "lip_krylov_workspace_bytes": (_SZ, [_LP, _I32, _I64, _I64]),
+    "lip_linop_apply": (C.c_int, [_LP, _P, _P, _I64, _I32, _P, _SZ, _P]),
+    "lip_lanczos_tridiag": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "lip_gkl_bidiag": (C.c_int, [_LP, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "lip_slq_quadrature": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _I32, _F, _P, _P, _SZ, _P]),
+    "lip_funm_lanczos": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _F, _P, _I64, _P, _SZ, _P]),
+    "lip_cg_solve": (C.c_int, [_LP, _P, _P, _I64, _F, _F, _I64, _I32, _P, _P, _SZ, _P]),
     "lip_bench_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, _I32, _I32, _I32, C.POINTER(_F), _P]),
     "lip_selftest_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, C.POINTER(_F), _P]),
     "lip_selftest_conv_tc": (C.c_int, [_I32, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I64, _I32, C.POINTER(_F), C.POINTER(_F),

@@ -135,4 +135,5 @@ def point_sharded(local_fn: Callable[[torch.Tensor], torch.Tensor]) -> Callable[
     for attr in ("_lip_batched", "_lip_model", "_lip_kind"):
         if hasattr(local_fn, attr):
             setattr(global_fn, attr, getattr(local_fn, attr))
+    global_fn._lip_native = False      # needs the all-reduce: the Krylov routines must call it back, not run the local model alone
     return global_fn

@@ -1,0 +1,1001 @@
+// lip_krylov.cu — the Krylov recurrences of the hot path as on-stream composite entry points.
+//
+// Reference semantics (all third-party to the reference, see oracle/lip_oracle.py):
+//   matfree.decomp.tridiag_sym(k), reortho="full"      call sites src/sample.py:114, tests/test_sample.py:338
+//   matfree.decomp.bidiag(k)  (Golub-Kahan-Lanczos)     call site  src/train_inducing.py:156
+//   matfree.funm.funm_lanczos_sym / integrand_funm_sym / integrand_funm_product_logdet
+//                                                      src/sample.py:115, src/matfree_monkeypatch.py:25-41, src/train_inducing.py:157
+//   jax.scipy.sparse.linalg.cg                          src/stochtrace.py:146,192, src/sample.py:71
+//
+// Round 1 drove these loops from Python (17 590 launches and ~2 500 ctypes calls for one k = 409 logdet, tensors allocated inside
+// the loop, a .item() every 4 CG iterations).  Here ONE C-ABI call enqueues the whole recurrence on the caller's stream: the
+// operator is described by a lip_linop (a bound lip_model in one of its roles, a dense symmetric matrix, or a caller callback),
+// every scalar (norms, Lanczos / GKL coefficients, CG step sizes) stays on the device, nothing is allocated, and the host never
+// waits (CG: optional polling of a pinned flag for early exit).  The vector kernels are fused per recurrence step:
+//   axpy_norm   out = s1*x1 | x2  - c*y,  |out| by a last-block reduction           (GKL: u = A v - beta u_prev, alpha = |u|)
+//   project     h = Q w: warp-per-row dots against a shared-memory chunk of w, per-CTA partials, last-block fixed-order sum
+//   subtract    out = w/s - sum_j (h_j/s) Q_j, |out| by a last-block reduction      (the CGS pass + the norm of its result)
+//   scale_store q = w/|w| into the basis row AND the contiguous operand(s) of the next mat-vec
+// 8 vector launches per GKL step (round 1: ~30), 6 per Lanczos step with two CGS passes.
+// All reductions are deterministic: per-CTA partials summed in a fixed order by the last CTA to arrive (an integer ticket is
+// the only atomic), so results do not depend on scheduling.
+#include <algorithm>
+#include <vector>
+
+#include "lip_model.cuh"
+
+using namespace lip;
+
+namespace {
+
+constexpr int VT = 256;
+constexpr int RCHUNK = 2048;   // floats of w staged in shared memory per sub-chunk
+constexpr int MAXP = 512;      // most per-column partials (CTAs per column)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.f;
+  if (w == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) sm[0] = t;
+  __syncthreads();
+  t = sm[0];
+  __syncthreads();
+  return t;
+}
+
+// The calling CTA has written its partial results; returns true in exactly one CTA per column: the last to arrive.
+__device__ __forceinline__ bool last_block(unsigned* counter, unsigned total) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    is_last = (t == total - 1);
+    if (is_last) *counter = 0;          // ready for the next launch on this stream
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last != 0;
+}
+
+// sum of part[0..np) in a fixed order; result valid in every thread
+__device__ __forceinline__ float sum_fixed(const volatile float* part, int np, float* sm) {
+  float v = 0.f;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) v += part[i];
+  return block_sum(v, sm);
+}
+
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+inline int column_ctas(int64_t n, int64_t B, int per_cta) {
+  int64_t want = ceil_div(4 * 148, B);
+  if (want < 4) want = 4;
+  const int64_t most = ceil_div(n, per_cta);
+  if (want > most) want = most;
+  if (want > MAXP) want = MAXP;
+  return (int)(want < 1 ? 1 : want);
+}
+
+// ---- axpy_norm -----------------------------------------------------------------------------------------------------
+// out[b][j] = X[b][j] - c[b] * y[b][j]     X = s1 * x1[b][j] for j < n1, x2[b][j - n1] for j >= n1
+// nrm[b] = sqrt(sum_j out^2)  (optional).  c = coef[b] (NULL: no y term).
+struct AxpyNormArgs {
+  const float* x1; int64_t ld1; int64_t n1; float s1;
+  const float* x2; int64_t ld2;
+  const float* y; int64_t ldy; int64_t ysb;   // ysb: batch stride of y
+  const float* coef;
+  float* out; int64_t ldo;
+  float* part; float* nrm; unsigned* counter;
+  int64_t n;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(VT) axpy_norm_kernel(AxpyNormArgs a) {
+  __shared__ float sm[32];
+  const int b = blockIdx.y, np = gridDim.x;
+  const float c = a.coef ? a.coef[b] : 0.f;
+  const float* x1 = a.x1 + (int64_t)b * a.ld1;
+  const float* x2 = a.x2 ? a.x2 + (int64_t)b * a.ld2 : nullptr;
+  const float* y = a.coef ? a.y + (int64_t)b * a.ysb : nullptr;
+  float* out = a.out + (int64_t)b * a.ldo;
+  float acc = 0.f;
+  if (VEC == 4) {
+    const int64_t n4 = a.n >> 2, n14 = a.n1 >> 2;    // n1 % 4 == 0 is checked by the launcher in this mode
+    for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n4; i += (int64_t)np * VT) {
+      float4 v;
+      if (i < n14) {
+        v = __ldg(reinterpret_cast<const float4*>(x1) + i);
+        v.x *= a.s1; v.y *= a.s1; v.z *= a.s1; v.w *= a.s1;
+      } else {
+        v = __ldg(reinterpret_cast<const float4*>(x2) + (i - n14));
+      }
+      if (y) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(y) + i);
+        v.x -= c * q.x; v.y -= c * q.y; v.z -= c * q.z; v.w -= c * q.w;
+      }
+      reinterpret_cast<float4*>(out)[i] = v;
+      acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+      const int64_t j = (n4 << 2) + threadIdx.x;
+      float v = (j < a.n1) ? a.s1 * x1[j] : x2[j - a.n1];
+      if (y) v -= c * y[j];
+      out[j] = v;
+      acc += v * v;
+    }
+  } else {
+    for (int64_t j = blockIdx.x * (int64_t)VT + threadIdx.x; j < a.n; j += (int64_t)np * VT) {
+      float v = (j < a.n1) ? a.s1 * x1[j] : x2[j - a.n1];
+      if (y) v -= c * y[j];
+      out[j] = v;
+      acc += v * v;
+    }
+  }
+  if (!a.nrm) return;
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) a.part[(int64_t)b * np + blockIdx.x] = acc;
+  if (last_block(a.counter + b, np)) {
+    const float t = sum_fixed(a.part + (int64_t)b * np, np, sm);
+    if (threadIdx.x == 0) a.nrm[b] = sqrtf(t);
+  }
+}
+
+// ---- project: h[b][j] = sum_i Q[b][j][i] * w[b][i],  j < kk ----------------------------------------------------------
+struct ProjectArgs {
+  const float* Q; int64_t ldq; int64_t qsb; int kk;
+  const float* w; int64_t ldw;
+  float* part; int64_t kpad;     // part[b][cta][kpad]
+  float* h;                      // h[b][kpad]
+  unsigned* counter;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(VT) project_kernel(ProjectArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* ws = smem;              // RCHUNK
+  float* acc = smem + RCHUNK;    // kk
+  __shared__ float red[8][33];
+  const int b = blockIdx.y, cta = blockIdx.x, np = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = VT >> 5;
+  const int kk = a.kk;
+  for (int j = threadIdx.x; j < kk; j += VT) acc[j] = 0.f;
+  const int64_t nsub = (a.n + RCHUNK - 1) / RCHUNK;
+  const float* wb = a.w + (int64_t)b * a.ldw;
+  const float* Qb = a.Q + (int64_t)b * a.qsb;
+  for (int64_t sub = cta; sub < nsub; sub += np) {
+    const int64_t i0 = sub * RCHUNK;
+    const int len = (int)((a.n - i0) < RCHUNK ? (a.n - i0) : RCHUNK);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RCHUNK; i += VT) ws[i] = (i < len) ? wb[i0 + i] : 0.f;   // w may be unpadded (ldw = n)
+    __syncthreads();
+    const int len4 = (len + 3) >> 2;          // rows of Q are zero-padded to ldq (a multiple of 4) and ws is zero beyond len
+    for (int j = warp; j < kk; j += nw) {
+      const float4* q4 = reinterpret_cast<const float4*>(Qb + (int64_t)j * a.ldq + i0);
+      const float4* w4 = reinterpret_cast<const float4*>(ws);
+      float s = 0.f;
+#pragma unroll 4
+      for (int i = lane; i < len4; i += 32) {
+        const float4 q = __ldg(q4 + i), c = w4[i];
+        s += (q.x * c.x + q.y * c.y) + (q.z * c.z + q.w * c.w);
+      }
+      s = warp_sum(s);
+      if (lane == 0) acc[j] += s;             // row j is always handled by the same warp
+    }
+  }
+  __syncthreads();
+  float* pb = a.part + ((int64_t)b * np + cta) * a.kpad;
+  for (int j = threadIdx.x; j < kk; j += VT) pb[j] = acc[j];
+  if (!last_block(a.counter + b, np)) return;
+  // fixed-order sum over the np CTAs: 32 coefficients x 8 CTA lanes per pass, 8 tiles (256 coefficients) per outer pass
+  const volatile float* P = a.part + (int64_t)b * np * a.kpad;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j0 = 0; j0 < kk; j0 += 256) {
+    float s[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s[t] = 0.f;
+    for (int c = ty; c < np; c += 8) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int j = j0 + t * 32 + tx;
+        if (j < kk) s[t] += P[(int64_t)c * a.kpad + j];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      red[ty][tx] = s[t];
+      __syncthreads();
+      if (ty == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) tot += red[y][tx];
+        const int j = j0 + t * 32 + tx;
+        if (j < kk) a.h[(int64_t)b * a.kpad + j] = tot;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- subtract: out[b][i] = (w[b][i] - sum_j h[b][j] Q[b][j][i]) * inv,  inv = 1 / scal[b] (scal NULL: 1) ---------------
+// nrm[b] = |out| (optional).  In-place (out == w) is fine: every thread reads its own elements before writing them.
+struct SubtractArgs {
+  const float* Q; int64_t ldq; int64_t qsb; int kk;
+  const float* h; int64_t kpad;
+  const float* w; int64_t ldw; int w_scalar;      // w_scalar: w rows are not 16-byte aligned (contiguous [B, n] mat-vec output)
+  const float* scal;
+  float* out; int64_t ldo;
+  float* part; float* nrm; unsigned* counter;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(VT) subtract_kernel(SubtractArgs a) {
+  extern __shared__ float hs[];
+  __shared__ float sm[32];
+  const int b = blockIdx.y, np = gridDim.x, kk = a.kk;
+  const float inv = a.scal ? 1.f / a.scal[b] : 1.f;
+  for (int j = threadIdx.x; j < kk; j += VT) hs[j] = a.h[(int64_t)b * a.kpad + j];
+  __syncthreads();
+  const float* Qb = a.Q + (int64_t)b * a.qsb;
+  const float* wb = a.w + (int64_t)b * a.ldw;
+  float* ob = a.out + (int64_t)b * a.ldo;
+  const int64_t n4 = (a.n + 3) >> 2;          // padded rows: the tail lanes of the last float4 are zeros in w and Q
+  const int64_t step = a.ldq >> 2;
+  float nacc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n4; i += (int64_t)np * VT) {
+    float4 acc;
+    if (a.w_scalar) {
+      const int64_t j0 = i << 2;
+      acc.x = wb[j0];
+      acc.y = (j0 + 1 < a.n) ? wb[j0 + 1] : 0.f;
+      acc.z = (j0 + 2 < a.n) ? wb[j0 + 2] : 0.f;
+      acc.w = (j0 + 3 < a.n) ? wb[j0 + 3] : 0.f;
+    } else {
+      acc = *reinterpret_cast<const float4*>(wb + (i << 2));
+    }
+    const float4* q = reinterpret_cast<const float4*>(Qb) + i;
+    int j = 0;
+    for (; j + 4 <= kk; j += 4) {
+      const float4 q0 = __ldg(q + (int64_t)(j + 0) * step), q1 = __ldg(q + (int64_t)(j + 1) * step);
+      const float4 q2 = __ldg(q + (int64_t)(j + 2) * step), q3 = __ldg(q + (int64_t)(j + 3) * step);
+      const float h0 = hs[j], h1 = hs[j + 1], h2 = hs[j + 2], h3 = hs[j + 3];
+      acc.x -= h0 * q0.x + h1 * q1.x + h2 * q2.x + h3 * q3.x;
+      acc.y -= h0 * q0.y + h1 * q1.y + h2 * q2.y + h3 * q3.y;
+      acc.z -= h0 * q0.z + h1 * q1.z + h2 * q2.z + h3 * q3.z;
+      acc.w -= h0 * q0.w + h1 * q1.w + h2 * q2.w + h3 * q3.w;
+    }
+    for (; j < kk; ++j) {
+      const float4 q0 = __ldg(q + (int64_t)j * step);
+      const float h0 = hs[j];
+      acc.x -= h0 * q0.x; acc.y -= h0 * q0.y; acc.z -= h0 * q0.z; acc.w -= h0 * q0.w;
+    }
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    *reinterpret_cast<float4*>(ob + (i << 2)) = acc;
+    nacc += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+  }
+  if (!a.nrm) return;
+  nacc = block_sum(nacc, sm);
+  if (threadIdx.x == 0) a.part[(int64_t)b * np + blockIdx.x] = nacc;
+  if (last_block(a.counter + b, np)) {
+    const float t = sum_fixed(a.part + (int64_t)b * np, np, sm);
+    if (threadIdx.x == 0) a.nrm[b] = sqrtf(t);
+  }
+}
+
+// ---- scale_store: y = x / scal[b] into up to three destinations -------------------------------------------------------
+//   o1 (stride ld1, optional): all n columns              (the basis row)
+//   o2 (stride ld2, optional): columns [0, n2)            (contiguous operand of the next mat-vec)
+//   o3 (stride ld3, optional): columns [n2, n)            (second contiguous operand: the output-space part of a GKL u vector)
+struct ScaleStoreArgs {
+  const float* x; int64_t ldx;
+  const float* scal;
+  float* o1; int64_t ld1; int64_t o1sb;
+  float* o2; int64_t ld2; int64_t n2;
+  float* o3; int64_t ld3;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(VT) scale_store_kernel(ScaleStoreArgs a) {
+  const int b = blockIdx.y;
+  const float inv = a.scal ? 1.f / a.scal[b] : 1.f;
+  const float* xb = a.x + (int64_t)b * a.ldx;
+  float* o1 = a.o1 ? a.o1 + (int64_t)b * a.o1sb : nullptr;
+  float* o2 = a.o2 ? a.o2 + (int64_t)b * a.ld2 : nullptr;
+  float* o3 = a.o3 ? a.o3 + (int64_t)b * a.ld3 : nullptr;
+  for (int64_t j = blockIdx.x * (int64_t)VT + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * VT) {
+    const float v = xb[j] * inv;
+    if (o1) o1[j] = v;
+    if (j < a.n2) { if (o2) o2[j] = v; }
+    else if (o3) o3[j - a.n2] = v;
+  }
+}
+
+// ---- tiny bookkeeping kernels ----------------------------------------------------------------------------------------
+// dst[b*stride + idx] = src[b]
+__global__ void record_kernel(float* dst, int64_t stride, int64_t idx, const float* src, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) dst[(int64_t)b * stride + idx] = src[b];
+}
+// Lanczos step i: diag[i] = h[i];  off[i-1] = 0.5 * (h[i-1] + len)   (T = (H + H^T)/2 of the Arnoldi form)
+// (runs between the first projection of step i and its subtract, so `len` still holds |w| of step i-1 = H[i][i-1])
+__global__ void lanczos_record_kernel(float* diag, float* off, const float* h, int64_t kpad, const float* len, int i, int k, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  diag[(int64_t)b * k + i] = h[(int64_t)b * kpad + i];
+  if (i > 0) off[(int64_t)b * (k - 1) + i - 1] = 0.5f * (h[(int64_t)b * kpad + i - 1] + len[b]);
+}
+// out[b] = q[b] * nrm[b]^2
+__global__ void quad_scale_kernel(float* out, const float* q, const float* nrm, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = q[b] * nrm[b] * nrm[b];
+}
+// c[b][j] *= s[b]
+__global__ void rowscale_kernel(float* c, int64_t ld, const float* s, int k, int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < B * k) c[(int64_t)(idx / k) * ld + idx % k] *= s[idx / k];
+}
+// any[0] = OR_b active[b]
+__global__ void any_active_kernel(const int* active, int B, int* any) {
+  __shared__ int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) if (active[b]) s = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) *any = s;
+}
+
+// ---- dense symmetric operator  out = alpha * u + beta * (u G),  G [n, n] symmetric row-major, u [B, n] ------------------
+// (src/sample.py:120-125: the d x d Gram mat-vec inside the sampler's Lanczos.)  HBM / L2 bound: G is read once per 8 probes.
+// Grid (column tiles of 512, row splits); a thread owns 4 consecutive columns (one 16-byte load per row of G) for NB probes;
+// the partial sums over its row slice land in part[split][b][j]; the second kernel adds them in split order (deterministic)
+// and applies alpha, beta.  n % 4 == 0 and a 16-byte aligned G are required by the vector loads (else the scalar variant).
+constexpr int DS_MAXSPLIT = 32;
+template <int NB, int VEC>
+__global__ void __launch_bounds__(128) dense_sym_partial_kernel(const float* __restrict__ G, int64_t n, const float* __restrict__ u,
+                                                                int64_t ldu, int64_t b0, int64_t B, float* __restrict__ part,
+                                                                int64_t rows_per_split) {
+  __shared__ float us[NB][128];
+  const int64_t j = ((int64_t)blockIdx.x * 128 + threadIdx.x) * VEC;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r1 = (r0 + rows_per_split < n) ? r0 + rows_per_split : n;
+  float acc[NB][VEC];
+#pragma unroll
+  for (int p = 0; p < NB; ++p)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[p][c] = 0.f;
+  for (int64_t i0 = r0; i0 < r1; i0 += 128) {
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < NB; ++p) {
+      const int64_t i = i0 + threadIdx.x;
+      us[p][threadIdx.x] = (i < r1 && b0 + p < B) ? u[(b0 + p) * ldu + i] : 0.f;
+    }
+    __syncthreads();
+    if (j < n) {
+      const int lim = (int)((r1 - i0) < 128 ? (r1 - i0) : 128);
+#pragma unroll 4
+      for (int i = 0; i < lim; ++i) {
+        float g[VEC];
+        if (VEC == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(G + (i0 + i) * n + j));
+          g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+        } else {
+          g[0] = __ldg(G + (i0 + i) * n + j);
+        }
+#pragma unroll
+        for (int p = 0; p < NB; ++p) {
+          const float uv = us[p][i];
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) acc[p][c] += uv * g[c];
+        }
+      }
+    }
+  }
+  if (j < n) {
+#pragma unroll
+    for (int p = 0; p < NB; ++p)
+      if (b0 + p < B) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) part[((int64_t)blockIdx.y * B + b0 + p) * n + j + c] = acc[p][c];
+      }
+  }
+}
+
+__global__ void dense_sym_finish_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ u, int64_t ldu,
+                                        float* __restrict__ out, int64_t ldo, int64_t n, int64_t B, float alpha, float beta) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * B) return;
+  const int64_t b = idx / n, j = idx - b * n;
+  float s = 0.f;
+  for (int sp = 0; sp < nsplit; ++sp) s += part[((int64_t)sp * B + b) * n + j];
+  out[b * ldo + j] = alpha * u[b * ldu + j] + beta * s;
+}
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+struct Bump {          // carves the caller's workspace
+  char* p; char* end; bool ok = true;
+  Bump(void* ws, size_t bytes) : p((char*)align_up((uintptr_t)ws, 256)), end((char*)ws + bytes) {}
+  template <class T>
+  T* take(size_t count) {
+    char* q = p;
+    p += align_up(count * sizeof(T), 256);
+    if (p > end) ok = false;
+    return (T*)q;
+  }
+};
+inline size_t rsz(size_t count, size_t elt) { return align_up(count * elt, 256); }
+
+inline int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
+
+struct Op {
+  const lip_linop* op;
+  int64_t n_in = 0, n_out = 0;   // columns / rows of the operator
+  int64_t D = 0, d = 0;          // model kinds
+  bool symmetric = false;
+  void* mws = nullptr; size_t mws_bytes = 0;   // model workspace
+  float* dpart = nullptr; int nsplit = 0;      // dense-sym partials
+};
+
+int op_init(Op& o, const lip_linop* op) {
+  LIP_REQUIRE(op, "null operator");
+  o.op = op;
+  switch (op->kind) {
+    case LIP_LINOP_GGN:
+      LIP_REQUIRE(op->model && op->model->bound, "lip_linop GGN: model not bound");
+      o.D = op->model->D; o.d = op->model->M * op->model->K;
+      o.n_in = o.n_out = o.D; o.symmetric = true;
+      break;
+    case LIP_LINOP_GKL:
+      LIP_REQUIRE(op->model && op->model->bound, "lip_linop GKL: model not bound");
+      LIP_REQUIRE(op->alpha >= 0.f, "lip_linop GKL: alpha must be >= 0");
+      o.D = op->model->D; o.d = op->model->M * op->model->K;
+      o.n_in = o.D; o.n_out = o.D + o.d;
+      break;
+    case LIP_LINOP_DENSE_SYM:
+      LIP_REQUIRE(op->dense && op->n > 0, "lip_linop DENSE_SYM: null matrix");
+      o.n_in = o.n_out = op->n; o.symmetric = true;
+      break;
+    case LIP_LINOP_CALLBACK:
+      LIP_REQUIRE(op->fn && op->n > 0 && op->n_out > 0 && op->cb_in && op->cb_out, "lip_linop CALLBACK: fn, n, n_out, cb_in, cb_out required");
+      o.n_in = op->n; o.n_out = op->n_out; o.symmetric = op->symmetric != 0;
+      LIP_REQUIRE(!o.symmetric || o.n_in == o.n_out, "lip_linop CALLBACK: a symmetric operator must be square");
+      break;
+    default:
+      LIP_REQUIRE(false, "lip_linop: unknown kind %d", op->kind);
+  }
+  return LIP_OK;
+}
+
+size_t op_ws_bytes(const Op& o, int64_t B) {
+  const lip_linop* op = o.op;
+  if (op->kind == LIP_LINOP_GGN || op->kind == LIP_LINOP_GKL) return align_up(lip_workspace_bytes(op->model, B), 256) + 256;
+  if (op->kind == LIP_LINOP_DENSE_SYM) return rsz((size_t)DS_MAXSPLIT * B * op->n, 4) + 256;
+  return 256;
+}
+
+int op_carve(Op& o, Bump& bp, int64_t B) {
+  const lip_linop* op = o.op;
+  if (op->kind == LIP_LINOP_GGN || op->kind == LIP_LINOP_GKL) {
+    o.mws_bytes = lip_workspace_bytes(op->model, B);
+    o.mws = bp.take<char>(o.mws_bytes);
+  } else if (op->kind == LIP_LINOP_DENSE_SYM) {
+    o.dpart = bp.take<float>((size_t)DS_MAXSPLIT * B * op->n);
+  }
+  return LIP_OK;
+}
+
+// contiguous in [B, n_in] -> contiguous out [B, n_out]; symmetric kinds and CALLBACK only (GKL has its own two-segment path)
+int op_apply(Op& o, const float* in, float* out, int64_t B, int transpose, cudaStream_t st) {
+  const lip_linop* op = o.op;
+  if (op->kind == LIP_LINOP_GGN) {
+    return lip_ggn_vp(op->model, in, out, B, op->scale, op->alpha, o.mws, o.mws_bytes, st);
+  }
+  if (op->kind == LIP_LINOP_DENSE_SYM) {
+    const int64_t n = op->n;
+    const bool v4 = (n % 4 == 0) && al16(op->dense);
+    const int64_t tiles = ceil_div(n, v4 ? 512 : 128);
+    int nsplit = (int)std::min<int64_t>(DS_MAXSPLIT, std::max<int64_t>(1, (4 * 148) / tiles));
+    const int64_t rows = ceil_div(ceil_div(n, nsplit), 32) * 32;
+    nsplit = (int)ceil_div(n, rows);
+    dim3 grid((unsigned)tiles, (unsigned)nsplit);
+    for (int64_t b0 = 0; b0 < B; b0 += 8) {
+      if (v4) dense_sym_partial_kernel<8, 4><<<grid, 128, 0, st>>>(op->dense, n, in, n, b0, B, o.dpart, rows);
+      else dense_sym_partial_kernel<8, 1><<<grid, 128, 0, st>>>(op->dense, n, in, n, b0, B, o.dpart, rows);
+      LIP_LAUNCH_CHECK();
+    }
+    dense_sym_finish_kernel<<<(unsigned)ceil_div(n * B, 256), 256, 0, st>>>(o.dpart, nsplit, in, n, out, n, n, B, op->alpha,
+                                                                          op->beta);
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
+  if (op->kind == LIP_LINOP_CALLBACK) {
+    // the callback reads cb_in / cb_in_t and writes cb_out / cb_out_t (caller-owned, fixed for the whole recurrence)
+    const bool tr = transpose && !o.symmetric;
+    float* cin = tr ? op->cb_in_t : op->cb_in;
+    float* cout = tr ? op->cb_out_t : op->cb_out;
+    const int64_t ni = tr ? o.n_out : o.n_in, no = tr ? o.n_in : o.n_out;
+    LIP_REQUIRE(cin && cout, "lip_linop CALLBACK: transpose buffers missing");
+    if (in != cin) LIP_CHECK_CUDA(cudaMemcpyAsync(cin, in, sizeof(float) * (size_t)B * ni, cudaMemcpyDeviceToDevice, st));
+    const int rc = op->fn(op->ctx, tr ? 1 : 0, B, (lip_stream_t)st);
+    if (rc != 0) { set_error("lip_linop CALLBACK: the mat-vec callback failed (%d)", rc); return LIP_ERR_INVALID; }
+    if (out != cout) LIP_CHECK_CUDA(cudaMemcpyAsync(out, cout, sizeof(float) * (size_t)B * no, cudaMemcpyDeviceToDevice, st));
+    return LIP_OK;
+  }
+  LIP_REQUIRE(false, "op_apply: kind %d has no contiguous form", op->kind);
+}
+
+// ---- launch helpers --------------------------------------------------------------------------------------------------
+struct Red {            // reduction scratch shared by all kernels of a recurrence (stream order serialises its use)
+  float* part = nullptr;        // [B][MAXP]
+  unsigned* counter = nullptr;  // [B]
+  float* ppart = nullptr;       // projection partials [B][np][kpad]
+  float* h = nullptr;           // [B][kpad]
+  int64_t kpad = 0;
+};
+
+int launch_axpy_norm(AxpyNormArgs a, int64_t B, const Red& r, cudaStream_t st) {
+  a.part = r.part; a.counter = r.counter;
+  const bool v4 = al16(a.x1) && (a.ld1 % 4 == 0) && (a.n1 % 4 == 0 || a.n1 >= a.n) && (!a.x2 || (al16(a.x2) && a.ld2 % 4 == 0)) &&
+                  (!a.coef || (al16(a.y) && a.ldy % 4 == 0 && a.ysb % 4 == 0)) && al16(a.out) && (a.ldo % 4 == 0);
+  const int np = column_ctas(a.n, B, VT * 4 * 2);
+  dim3 grid(np, (unsigned)B);
+  if (v4) axpy_norm_kernel<4><<<grid, VT, 0, st>>>(a);
+  else axpy_norm_kernel<1><<<grid, VT, 0, st>>>(a);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+int launch_project(const float* Q, int64_t ldq, int64_t qsb, int kk, const float* w, int64_t ldw, int64_t n, int64_t B,
+                   const Red& r, cudaStream_t st) {
+  if (kk <= 0) return LIP_OK;
+  ProjectArgs a{Q, ldq, qsb, kk, w, ldw, r.ppart, r.kpad, r.h, r.counter, n};
+  const int np = column_ctas(n, B, RCHUNK);
+  dim3 grid(np, (unsigned)B);
+  project_kernel<<<grid, VT, sizeof(float) * (RCHUNK + (size_t)kk), st>>>(a);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+int launch_subtract(const float* Q, int64_t ldq, int64_t qsb, int kk, const float* w, int64_t ldw, const float* scal, float* out,
+                    int64_t ldo, float* nrm, int64_t n, int64_t B, const Red& r, cudaStream_t st) {
+  SubtractArgs a{Q, ldq, qsb, kk, r.h, r.kpad, w, ldw, (!al16(w) || ldw % 4 != 0) ? 1 : 0, scal, out, ldo, r.part, nrm, r.counter, n};
+  const int np = column_ctas(n, B, VT * 4);
+  dim3 grid(np, (unsigned)B);
+  subtract_kernel<<<grid, VT, sizeof(float) * (size_t)(kk > 0 ? kk : 1), st>>>(a);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+int launch_scale_store(ScaleStoreArgs a, int64_t B, cudaStream_t st) {
+  int64_t g = ceil_div(a.n, VT * 4);
+  const int64_t cap = std::max<int64_t>(4, ceil_div(8 * 148, B));
+  if (g > cap) g = cap;
+  dim3 grid((unsigned)(g < 1 ? 1 : g), (unsigned)B);
+  scale_store_kernel<<<grid, VT, 0, st>>>(a);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+int set_kernel_limits(int64_t k) {
+  const size_t need = sizeof(float) * (RCHUNK + (size_t)k);
+  LIP_REQUIRE(need <= 200 * 1024, "Krylov depth %lld too large for the shared-memory coefficient buffers", (long long)k);
+  if (need > 48 * 1024) {
+    LIP_CHECK_CUDA(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    LIP_CHECK_CUDA(cudaFuncSetAttribute(subtract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  }
+  return LIP_OK;
+}
+
+size_t red_bytes(int64_t n, int64_t B, int64_t k) {
+  const int64_t kpad = pad4(k);
+  const int np = column_ctas(n, B, RCHUNK);
+  return rsz((size_t)B * MAXP, 4) + rsz((size_t)B, 4) + rsz((size_t)B * np * kpad, 4) + rsz((size_t)B * kpad, 4);
+}
+
+int red_carve(Red& r, Bump& bp, int64_t n, int64_t B, int64_t k, cudaStream_t st) {
+  r.kpad = pad4(k);
+  const int np = column_ctas(n, B, RCHUNK);
+  r.part = bp.take<float>((size_t)B * MAXP);
+  r.counter = bp.take<unsigned>((size_t)B);
+  r.ppart = bp.take<float>((size_t)B * np * r.kpad);
+  r.h = bp.take<float>((size_t)B * r.kpad);
+  if (!bp.ok) return LIP_OK;      // the caller reports the workspace error
+  LIP_CHECK_CUDA(cudaMemsetAsync(r.counter, 0, sizeof(unsigned) * (size_t)B, st));
+  return LIP_OK;
+}
+
+// ---- Lanczos (matfree decomp.tridiag_sym, reortho="full") -------------------------------------------------------------
+size_t lanczos_ws_bytes(const Op& o, int64_t k, int64_t B) {
+  const int64_t n = o.n_in, ld = pad4(n);
+  return op_ws_bytes(o, B) + red_bytes(n, B, k) + 2 * rsz((size_t)B * ld, 4) + 2 * rsz((size_t)B * n, 4) + 4 * rsz((size_t)B, 4) + 8192;
+}
+
+int lanczos_run(Op& o, const float* v0, int64_t ldv0, int64_t k, int64_t B, int passes, float* Q, int64_t ldq, float* diag,
+                float* off, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t n = o.n_in;
+  LIP_REQUIRE(o.symmetric || o.n_in == o.n_out, "lanczos: the operator must be square");
+  LIP_REQUIRE(o.op->kind != LIP_LINOP_GKL, "lanczos: the GKL operator is rectangular (use lip_gkl_bidiag)");
+  LIP_REQUIRE(k >= 1 && k <= n, "num_matvecs=%lld exceeds the operator dimension %lld", (long long)k, (long long)n);
+  LIP_REQUIRE(passes == 1 || passes == 2, "lanczos: passes must be 1 or 2");
+  LIP_REQUIRE(Q && al16(Q) && ldq % 4 == 0 && ldq >= n, "lanczos: basis must be 16-byte aligned with ldq %% 4 == 0 and ldq >= n");
+  int rc = set_kernel_limits(k);
+  if (rc) return rc;
+  Bump bp(ws, ws_bytes);
+  op_carve(o, bp, B);
+  Red r;
+  rc = red_carve(r, bp, n, B, k, st);
+  if (rc) return rc;
+  const int64_t ld = pad4(n);
+  float* w = bp.take<float>((size_t)B * ld);        // working vector, padded rows
+  float* qc = bp.take<float>((size_t)B * n);        // contiguous mat-vec input
+  float* wc = bp.take<float>((size_t)B * n);        // contiguous mat-vec output
+  float* len = bp.take<float>((size_t)B);
+  float* nrm0 = bp.take<float>((size_t)B);
+  if (!bp.ok) { set_error("lanczos: workspace too small (%zu bytes given, %zu needed)", ws_bytes, lanczos_ws_bytes(o, k, B)); return LIP_ERR_WORKSPACE; }
+  const int64_t qsb = k * ldq;
+  const bool pad_tail = (ld != n);
+  if (pad_tail) LIP_CHECK_CUDA(cudaMemsetAsync(w, 0, sizeof(float) * (size_t)B * ld, st));
+  // q_0 = v0 / |v0|   (the basis rows must have zero padding: they are written column-exact into zeroed memory)
+  LIP_CHECK_CUDA(cudaMemsetAsync(Q, 0, sizeof(float) * (size_t)B * qsb, st));
+  {
+    AxpyNormArgs a{}; a.x1 = v0; a.ld1 = ldv0; a.n1 = n; a.s1 = 1.f; a.out = w; a.ldo = ld; a.nrm = nrm0; a.n = n;
+    rc = launch_axpy_norm(a, B, r, st); if (rc) return rc;
+    if (norm0) LIP_CHECK_CUDA(cudaMemcpyAsync(norm0, nrm0, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    ScaleStoreArgs s{}; s.x = w; s.ldx = ld; s.scal = nrm0; s.o1 = Q; s.ld1 = ldq; s.o1sb = qsb; s.o2 = qc; s.ld2 = n; s.n2 = n; s.n = n;
+    rc = launch_scale_store(s, B, st); if (rc) return rc;
+  }
+  const unsigned gB = (unsigned)ceil_div(B, 128);
+  for (int64_t i = 0; i < k; ++i) {
+    const int kk = (int)(i + 1);
+    rc = op_apply(o, qc, wc, B, 0, st); if (rc) return rc;
+    // two CGS passes against Q[0..i]; the first-pass coefficients are the Arnoldi column H[:, i]
+    rc = launch_project(Q, ldq, qsb, kk, wc, n, n, B, r, st); if (rc) return rc;
+    lanczos_record_kernel<<<gB, 128, 0, st>>>(diag, off, r.h, r.kpad, len, (int)i, (int)k, (int)B);
+    LIP_LAUNCH_CHECK();
+    rc = launch_subtract(Q, ldq, qsb, kk, wc, n, nullptr, w, ld, passes == 1 ? len : nullptr, n, B, r, st); if (rc) return rc;
+    if (passes == 2) {
+      rc = launch_project(Q, ldq, qsb, kk, w, ld, n, B, r, st); if (rc) return rc;
+      rc = launch_subtract(Q, ldq, qsb, kk, w, ld, nullptr, w, ld, len, n, B, r, st); if (rc) return rc;
+    }
+    if (i + 1 < k) {
+      ScaleStoreArgs s{}; s.x = w; s.ldx = ld; s.scal = len; s.o1 = Q + (i + 1) * ldq; s.ld1 = ldq; s.o1sb = qsb; s.o2 = qc; s.ld2 = n;
+      s.n2 = n; s.n = n;
+      rc = launch_scale_store(s, B, st); if (rc) return rc;
+    }
+  }
+  return LIP_OK;
+}
+
+// ---- Golub-Kahan-Lanczos (matfree decomp.bidiag, full re-orthogonalisation of both bases) -------------------------------
+size_t gkl_ws_bytes(const Op& o, int64_t k, int64_t B) {
+  const int64_t nc = o.n_in, nr = o.n_out, ldu = pad4(nr), ldv = pad4(nc);
+  return op_ws_bytes(o, B) + red_bytes(std::max(nc, nr), B, k) + rsz((size_t)B * ldu, 4) + rsz((size_t)B * ldv, 4) +
+         2 * rsz((size_t)B * nc, 4) + 2 * rsz((size_t)B * nr, 4) + 6 * rsz((size_t)B, 4) + 4096;
+}
+
+int gkl_run(Op& o, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* Us, int64_t ldu, float* Vs, int64_t ldv,
+            float* alphas, float* betas, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t nc = o.n_in, nr = o.n_out;
+  LIP_REQUIRE(k >= 1 && k <= std::min(nc, nr), "num_matvecs=%lld exceeds the operator dimensions (%lld, %lld)", (long long)k,
+              (long long)nr, (long long)nc);
+  LIP_REQUIRE(Us && Vs && al16(Us) && al16(Vs) && ldu % 4 == 0 && ldv % 4 == 0 && ldu >= nr && ldv >= nc,
+              "gkl: bases must be 16-byte aligned with leading dimensions that are multiples of 4");
+  int rc = set_kernel_limits(k);
+  if (rc) return rc;
+  Bump bp(ws, ws_bytes);
+  op_carve(o, bp, B);
+  Red r;
+  rc = red_carve(r, bp, std::max(nc, nr), B, k, st);
+  if (rc) return rc;
+  const bool gkl = o.op->kind == LIP_LINOP_GKL;
+  const int64_t D = o.D, d = o.d;
+  const int64_t lu = pad4(nr), lv = pad4(nc);
+  float* u = bp.take<float>((size_t)B * lu);          // working u, padded rows
+  float* v = bp.take<float>((size_t)B * lv);          // working v, padded rows
+  float* vc = bp.take<float>((size_t)B * nc);         // contiguous A input
+  float* wv = bp.take<float>((size_t)B * nc);         // contiguous A^T output
+  float* uc = bp.take<float>((size_t)B * nr);         // contiguous A^T input   (GKL kind: [B, D] part then [B, d] part)
+  float* tu = bp.take<float>((size_t)B * nr);         // contiguous A output    (GKL kind: only the [B, d] output-space part)
+  float* alpha = bp.take<float>((size_t)B);
+  float* beta = bp.take<float>((size_t)B);
+  float* nu = bp.take<float>((size_t)B);
+  float* nv = bp.take<float>((size_t)B);
+  float* nrm0 = bp.take<float>((size_t)B);
+  if (!bp.ok) { set_error("gkl: workspace too small (%zu bytes given, %zu needed)", ws_bytes, gkl_ws_bytes(o, k, B)); return LIP_ERR_WORKSPACE; }
+  const int64_t usb = k * ldu, vsb = k * ldv;
+  if (lu != nr) LIP_CHECK_CUDA(cudaMemsetAsync(u, 0, sizeof(float) * (size_t)B * lu, st));
+  if (lv != nc) LIP_CHECK_CUDA(cudaMemsetAsync(v, 0, sizeof(float) * (size_t)B * lv, st));
+  LIP_CHECK_CUDA(cudaMemsetAsync(Us, 0, sizeof(float) * (size_t)B * usb, st));
+  LIP_CHECK_CUDA(cudaMemsetAsync(Vs, 0, sizeof(float) * (size_t)B * vsb, st));
+  LIP_CHECK_CUDA(cudaMemsetAsync(betas, 0, sizeof(float) * (size_t)B * k, st));
+  const float sa = gkl ? sqrtf(o.op->alpha) : 0.f;
+  float* ucD = uc;                       // GKL kind: parameter-space part of u, [B, D]
+  float* ucd = uc + (size_t)B * D;       //           output-space part, [B, d]
+  // v_0 = v0 / |v0|
+  {
+    AxpyNormArgs a{}; a.x1 = v0; a.ld1 = ldv0; a.n1 = nc; a.s1 = 1.f; a.out = v; a.ldo = lv; a.nrm = nrm0; a.n = nc;
+    rc = launch_axpy_norm(a, B, r, st); if (rc) return rc;
+    if (norm0) LIP_CHECK_CUDA(cudaMemcpyAsync(norm0, nrm0, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    ScaleStoreArgs s{}; s.x = v; s.ldx = lv; s.scal = nrm0; s.o1 = Vs; s.ld1 = ldv; s.o1sb = vsb; s.o2 = vc; s.ld2 = nc; s.n2 = nc; s.n = nc;
+    rc = launch_scale_store(s, B, st); if (rc) return rc;
+  }
+  const unsigned gB = (unsigned)ceil_div(B, 128);
+  for (int64_t i = 0; i < k; ++i) {
+    // ---- u = A v_i - beta_i u_{i-1};  alpha_i = |u|
+    AxpyNormArgs a{};
+    if (gkl) {
+      rc = lip_wt_apply(o.op->model, vc, tu, B, o.op->scale, LIP_FACTOR_SQRT, o.mws, o.mws_bytes, st); if (rc) return rc;
+      a.x1 = vc; a.ld1 = D; a.n1 = D; a.s1 = sa; a.x2 = tu; a.ld2 = d;
+    } else {
+      rc = op_apply(o, vc, tu, B, 0, st); if (rc) return rc;
+      a.x1 = tu; a.ld1 = nr; a.n1 = nr; a.s1 = 1.f;
+    }
+    if (i > 0) { a.y = Us + (i - 1) * ldu; a.ldy = ldu; a.ysb = usb; a.coef = beta; }
+    a.out = u; a.ldo = lu; a.nrm = alpha; a.n = nr;
+    rc = launch_axpy_norm(a, B, r, st); if (rc) return rc;
+    record_kernel<<<gB, 128, 0, st>>>(alphas, k, i, alpha, (int)B);
+    LIP_LAUNCH_CHECK();
+    // ---- u <- normalise, CGS against U[0..i-1], renormalise, store
+    rc = launch_project(Us, ldu, usb, (int)i, u, lu, nr, B, r, st); if (rc) return rc;
+    rc = launch_subtract(Us, ldu, usb, (int)i, u, lu, alpha, u, lu, nu, nr, B, r, st); if (rc) return rc;
+    {
+      ScaleStoreArgs s{}; s.x = u; s.ldx = lu; s.scal = nu; s.o1 = Us + i * ldu; s.ld1 = ldu; s.o1sb = usb; s.n = nr;
+      if (gkl) { s.o2 = ucD; s.ld2 = D; s.n2 = D; s.o3 = ucd; s.ld3 = d; }
+      else { s.o2 = uc; s.ld2 = nr; s.n2 = nr; }
+      rc = launch_scale_store(s, B, st); if (rc) return rc;
+    }
+    if (i + 1 == k) break;              // the last v would not be used (matfree computes it; it does not enter B)
+    // ---- w = A^T u_i - alpha_i v_i;  beta_{i+1} = |w|
+    if (gkl) {
+      rc = lip_w_apply(o.op->model, ucd, wv, B, o.op->scale, LIP_FACTOR_SQRT, ucD, sa, o.mws, o.mws_bytes, st); if (rc) return rc;
+    } else {
+      rc = op_apply(o, uc, wv, B, 1, st); if (rc) return rc;
+    }
+    AxpyNormArgs c{}; c.x1 = wv; c.ld1 = nc; c.n1 = nc; c.s1 = 1.f; c.y = Vs + i * ldv; c.ldy = ldv; c.ysb = vsb; c.coef = alpha;
+    c.out = v; c.ldo = lv; c.nrm = beta; c.n = nc;
+    rc = launch_axpy_norm(c, B, r, st); if (rc) return rc;
+    record_kernel<<<gB, 128, 0, st>>>(betas, k, i + 1, beta, (int)B);
+    LIP_LAUNCH_CHECK();
+    rc = launch_project(Vs, ldv, vsb, (int)(i + 1), v, lv, nc, B, r, st); if (rc) return rc;
+    rc = launch_subtract(Vs, ldv, vsb, (int)(i + 1), v, lv, beta, v, lv, nv, nc, B, r, st); if (rc) return rc;
+    {
+      ScaleStoreArgs s{}; s.x = v; s.ldx = lv; s.scal = nv; s.o1 = Vs + (i + 1) * ldv; s.ld1 = ldv; s.o1sb = vsb; s.o2 = vc; s.ld2 = nc;
+      s.n2 = nc; s.n = nc;
+      rc = launch_scale_store(s, B, st); if (rc) return rc;
+    }
+  }
+  return LIP_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+size_t lip_krylov_workspace_bytes(const lip_linop* op, int32_t routine, int64_t k, int64_t B) {
+  Op o;
+  if (op_init(o, op) != LIP_OK || k <= 0 || B <= 0) return 0;
+  const int64_t nc = o.n_in, nr = o.n_out;
+  const size_t tri = lip_tridiag_scratch_bytes(k, B, 1) + 4 * rsz((size_t)B * k, 4);
+  switch (routine) {
+    case LIP_KRYLOV_LANCZOS: return lanczos_ws_bytes(o, k, B);
+    case LIP_KRYLOV_GKL: return gkl_ws_bytes(o, k, B);
+    case LIP_KRYLOV_SLQ_LANCZOS: return lanczos_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + tri + 4096;
+    case LIP_KRYLOV_SLQ_GKL:
+      return gkl_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + rsz((size_t)B * k * pad4(nr), 4) + tri + 4096;
+    case LIP_KRYLOV_FUNM: return lanczos_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + tri + rsz((size_t)B * pad4(nc), 4) + 4096;
+    case LIP_KRYLOV_APPLY: return op_ws_bytes(o, B) + rsz((size_t)B * (nr > nc ? nr : nc), 4) + 4096;
+    case LIP_KRYLOV_CG:
+      return op_ws_bytes(o, B) + 3 * rsz((size_t)B * nc, 4) + 4 * rsz((size_t)B, 4) + align_up(lip_dot_scratch_bytes(nc, B), 256) + 4096;
+    default: return 0;
+  }
+}
+
+int lip_linop_apply(const lip_linop* op, const float* in, float* out, int64_t B, int32_t transpose, void* workspace,
+                    size_t workspace_bytes, lip_stream_t stream) {
+  Op o;
+  int rc = op_init(o, op);
+  if (rc) return rc;
+  LIP_REQUIRE(in && out && in != out && workspace && B > 0, "lip_linop_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump bp(workspace, workspace_bytes);
+  op_carve(o, bp, B);
+  float* tmp = (op->kind == LIP_LINOP_GKL) ? bp.take<float>((size_t)B * (o.D + o.d)) : nullptr;
+  if (!bp.ok) {
+    set_error("lip_linop_apply: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              lip_krylov_workspace_bytes(op, LIP_KRYLOV_APPLY, 1, B));
+    return LIP_ERR_WORKSPACE;
+  }
+  if (op->kind != LIP_LINOP_GKL) return op_apply(o, in, out, B, transpose, st);
+  const float sa = sqrtf(op->alpha);
+  const int64_t D = o.D, d = o.d;
+  Red none;
+  if (!transpose) {          // out = [sqrt(alpha) v ; scale W^T v]
+    rc = lip_wt_apply(op->model, in, tmp, B, op->scale, LIP_FACTOR_SQRT, o.mws, o.mws_bytes, st);
+    if (rc) return rc;
+    AxpyNormArgs a{}; a.x1 = in; a.ld1 = D; a.n1 = D; a.s1 = sa; a.x2 = tmp; a.ld2 = d; a.out = out; a.ldo = D + d; a.n = D + d;
+    return launch_axpy_norm(a, B, none, st);
+  }
+  float* uD = tmp;           // out = sqrt(alpha) u[:D] + scale W u[D:]
+  float* ud = tmp + (size_t)B * D;
+  ScaleStoreArgs s{}; s.x = in; s.ldx = D + d; s.o2 = uD; s.ld2 = D; s.n2 = D; s.o3 = ud; s.ld3 = d; s.n = D + d;
+  rc = launch_scale_store(s, B, st);
+  if (rc) return rc;
+  return lip_w_apply(op->model, ud, out, B, op->scale, LIP_FACTOR_SQRT, uD, sa, o.mws, o.mws_bytes, st);
+}
+
+int lip_lanczos_tridiag(const lip_linop* op, const float* v0, int64_t ldv0, int64_t k, int64_t B, int32_t passes, float* Q,
+                        int64_t ldq, float* diag, float* off, float* norm0, void* workspace, size_t workspace_bytes,
+                        lip_stream_t stream) {
+  Op o;
+  int rc = op_init(o, op);
+  if (rc) return rc;
+  LIP_REQUIRE(v0 && diag && (off || k == 1) && workspace && B > 0 && ldv0 >= o.n_in, "lip_lanczos_tridiag: bad argument");
+  return lanczos_run(o, v0, ldv0, k, B, passes, Q, ldq, diag, off, norm0, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int lip_gkl_bidiag(const lip_linop* op, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* Us, int64_t ldu, float* Vs,
+                   int64_t ldv, float* alphas, float* betas, float* norm0, void* workspace, size_t workspace_bytes,
+                   lip_stream_t stream) {
+  Op o;
+  int rc = op_init(o, op);
+  if (rc) return rc;
+  LIP_REQUIRE(v0 && alphas && betas && workspace && B > 0 && ldv0 >= o.n_in, "lip_gkl_bidiag: bad argument");
+  return gkl_run(o, v0, ldv0, k, B, Us, ldu, Vs, ldv, alphas, betas, norm0, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form, int32_t fn,
+                       float clip_min, float* quad_out, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
+  Op o;
+  int rc = op_init(o, op);
+  if (rc) return rc;
+  LIP_REQUIRE(probes && quad_out && workspace && B > 0 && k > 0, "lip_slq_quadrature: bad argument");
+  LIP_REQUIRE(form == LIP_SLQ_LANCZOS || form == LIP_SLQ_GKL, "lip_slq_quadrature: unknown form %d", form);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nc = o.n_in, nr = o.n_out, ldv = pad4(nc), ldu = pad4(nr);
+  Bump bp(workspace, workspace_bytes);
+  float* td = bp.take<float>((size_t)B * k);
+  float* to = bp.take<float>((size_t)B * k);
+  float* al = bp.take<float>((size_t)B * k);
+  float* be = bp.take<float>((size_t)B * k);
+  float* nrm = bp.take<float>((size_t)B);
+  float* q = bp.take<float>((size_t)B);
+  void* tsc = bp.take<char>(lip_tridiag_scratch_bytes(k, B, 0));
+  float* Vs = bp.take<float>((size_t)B * k * ldv);
+  float* Us = form == LIP_SLQ_GKL ? bp.take<float>((size_t)B * k * ldu) : nullptr;
+  if (!bp.ok) {
+    set_error("lip_slq_quadrature: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              lip_krylov_workspace_bytes(op, form == LIP_SLQ_GKL ? LIP_KRYLOV_SLQ_GKL : LIP_KRYLOV_SLQ_LANCZOS, k, B));
+    return LIP_ERR_WORKSPACE;
+  }
+  const size_t rest = (size_t)(bp.end - bp.p);
+  if (form == LIP_SLQ_LANCZOS) {
+    rc = lanczos_run(o, probes, ldp, k, B, 2, Vs, ldv, td, to, nrm, bp.p, rest, st);
+  } else {
+    rc = gkl_run(o, probes, ldp, k, B, Us, ldu, Vs, ldv, al, be, nrm, bp.p, rest, st);
+    if (!rc) rc = lip_bidiag_to_tridiag(al, be, td, to, k, B, st);
+  }
+  if (rc) return rc;
+  rc = lip_tridiag_funm(td, to, k, B, fn, clip_min, q, nullptr, nullptr, tsc, st);
+  if (rc) return rc;
+  quad_scale_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(quad_out, q, nrm, (int)B);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv_in, int64_t k, int64_t B, int32_t fn, float clip_min,
+                     float* out, int64_t ldo, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
+  Op o;
+  int rc = op_init(o, op);
+  if (rc) return rc;
+  LIP_REQUIRE(v && out && workspace && B > 0 && k > 0 && ldo >= o.n_in, "lip_funm_lanczos: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = o.n_in, ldq = pad4(n);
+  Bump bp(workspace, workspace_bytes);
+  float* td = bp.take<float>((size_t)B * k);
+  float* to = bp.take<float>((size_t)B * k);
+  float* fe1 = bp.take<float>((size_t)B * k);
+  float* nrm = bp.take<float>((size_t)B);
+  float* tmp = bp.take<float>((size_t)B * ldq);
+  void* tsc = bp.take<char>(lip_tridiag_scratch_bytes(k, B, 1));
+  float* Q = bp.take<float>((size_t)B * k * ldq);
+  if (!bp.ok) {
+    set_error("lip_funm_lanczos: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              lip_krylov_workspace_bytes(op, LIP_KRYLOV_FUNM, k, B));
+    return LIP_ERR_WORKSPACE;
+  }
+  rc = lanczos_run(o, v, ldv_in, k, B, 2, Q, ldq, td, to, nrm, bp.p, (size_t)(bp.end - bp.p), st);
+  if (rc) return rc;
+  rc = lip_tridiag_funm(td, to, k, B, fn, clip_min, nullptr, fe1, nullptr, tsc, st);
+  if (rc) return rc;
+  rowscale_kernel<<<(unsigned)ceil_div(B * k, 256), 256, 0, st>>>(fe1, k, nrm, (int)k, (int)B);      // |v| f(T) e1
+  LIP_LAUNCH_CHECK();
+  rc = lip_basis_combine(Q, ldq, k, k, fe1, k, tmp, ldq, n, B, st);
+  if (rc) return rc;
+  LIP_CHECK_CUDA(cudaMemcpy2DAsync(out, sizeof(float) * ldo, tmp, sizeof(float) * ldq, sizeof(float) * n, (size_t)B,
+                                   cudaMemcpyDeviceToDevice, st));
+  return LIP_OK;
+}
+
+int lip_cg_solve(const lip_linop* op, const float* b, float* x, int64_t B, float tol, float atol, int64_t maxiter,
+                 int32_t check_every, int32_t* iters_out, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
+  Op o;
+  int rc = op_init(o, op);
+  if (rc) return rc;
+  LIP_REQUIRE(b && x && workspace && B > 0, "lip_cg_solve: bad argument");
+  LIP_REQUIRE(o.symmetric && o.op->kind != LIP_LINOP_GKL, "lip_cg_solve: the operator must be symmetric");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = o.n_in;
+  if (maxiter < 0) maxiter = 10 * n;          // jax.scipy.sparse.linalg.cg default
+  Bump bp(workspace, workspace_bytes);
+  op_carve(o, bp, B);
+  float* r = bp.take<float>((size_t)B * n);
+  float* p = bp.take<float>((size_t)B * n);
+  float* Ap = bp.take<float>((size_t)B * n);
+  float* gamma = bp.take<float>((size_t)B);
+  float* thresh = bp.take<float>((size_t)B);
+  int* active = bp.take<int>((size_t)B);
+  int* iters = bp.take<int>((size_t)B);
+  int* any = bp.take<int>(4);
+  void* dsc = bp.take<char>(lip_dot_scratch_bytes(n, B));
+  if (!bp.ok) {
+    set_error("lip_cg_solve: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              lip_krylov_workspace_bytes(op, LIP_KRYLOV_CG, 1, B));
+    return LIP_ERR_WORKSPACE;
+  }
+  rc = lip_cg_init(b, x, r, p, gamma, thresh, active, iters, tol, atol, n, B, dsc, st);
+  if (rc) return rc;
+  // early exit: every check_every iterations the OR of the active flags is copied to pinned host memory behind an event; the
+  // host looks at the PREVIOUS check (already complete or nearly so) and never blocks on the current one.  Iterations enqueued
+  // after convergence are no-ops for converged columns (their `active` flag is 0), so running ahead is harmless.
+  int* host_flag = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (check_every > 0) {
+    LIP_CHECK_CUDA(cudaHostAlloc((void**)&host_flag, 2 * sizeof(int), cudaHostAllocDefault));
+    host_flag[0] = host_flag[1] = 1;
+    LIP_CHECK_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    LIP_CHECK_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  }
+  int pending = -1, slot = 0;
+  int64_t it = 0;
+  int status = LIP_OK;
+  for (; it < maxiter; ++it) {
+    if (check_every > 0 && it % check_every == 0) {
+      if (pending >= 0) {
+        cudaError_t e = cudaEventSynchronize(ev[pending]);
+        if (e != cudaSuccess) { set_error("lip_cg_solve: %s", cudaGetErrorString(e)); status = LIP_ERR_CUDA; break; }
+        if (host_flag[pending] == 0) break;
+      }
+      any_active_kernel<<<1, 256, 0, st>>>(active, (int)B, any);
+      count_launch();
+      cudaMemcpyAsync(&host_flag[slot], any, sizeof(int), cudaMemcpyDeviceToHost, st);
+      cudaEventRecord(ev[slot], st);
+      pending = slot;
+      slot ^= 1;
+    }
+    status = op_apply(o, p, Ap, B, 0, st);
+    if (status) break;
+    status = lip_cg_step(x, r, p, Ap, gamma, thresh, active, iters, n, B, dsc, st);
+    if (status) break;
+  }
+  if (iters_out && status == LIP_OK) cudaMemcpyAsync(iters_out, iters, sizeof(int) * B, cudaMemcpyDeviceToDevice, st);
+  if (check_every > 0) {
+    cudaStreamSynchronize(st);       // the pinned flag and the events are released below
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    cudaFreeHost(host_flag);
+  }
+  return status;
+}
+
+}  // extern "C"

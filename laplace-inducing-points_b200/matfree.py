@@ -7,9 +7,10 @@
 
 matfree / jax are not in this image and matfree is unpinned in the reference (requirements.txt:5); the
 algorithms are restated from their published form (see oracle/lip_oracle.py header: "parity unpinned").
-Every routine is batched over a leading probe axis: vectors are [n] or [B, n].  The loops are host-driven
-(matvec closures are Python callables, as in the reference) but all vector work and all scalars stay on the
-device: lip_reorth / lip_cg_step / lip_tridiag_funm / lip_basis_combine of include/lip_b200.h.
+Every routine is batched over a leading probe axis: vectors are [n] or [B, n].  Each recurrence is ONE native call
+(lip_lanczos_tridiag / lip_gkl_bidiag / lip_cg_solve of include/lip_b200.h, csrc/lip_krylov.cu): closures built by this
+package (curvature_vp, gkl_target, dense_sym_operator) run without Python in the loop; any other callable is invoked
+through the library's mat-vec callback, once per step.  All vector work and all scalars stay on the device.
 """
 from __future__ import annotations
 
@@ -48,105 +49,191 @@ def batched(fn):
     return fn
 
 
+# ---------------------------------------------------------------------------------------------- operators
+class _NativeOp:
+    """A lip_linop (include/lip_b200.h) for a mat-vec closure, plus everything that must outlive the native call.
+
+    Closures built by this package carry what the library needs to run them without Python in the loop:
+      _lip_kind == "GGN"       (lla.compute_curvature_approx / ggn.compute_ggn_vp)   -> LIP_LINOP_GGN
+      _lip_kind == "GKL"       (gkl_target below)                                   -> LIP_LINOP_GKL
+      _lip_kind == "DENSE_SYM" (dense_sym_operator below)                           -> LIP_LINOP_DENSE_SYM
+    anything else is wrapped as LIP_LINOP_CALLBACK: the recurrence still runs inside ONE native call and the library calls back
+    into Python for the mat-vec only."""
+
+    def __init__(self, Av, vA, B, n_in, n_out, single, symmetric):
+        self.struct = cabi.LinOp()
+        self.exc = None
+        self.keep = []
+        kind = getattr(Av, "_lip_kind", None)
+        native = getattr(Av, "_lip_native", True) and getattr(Av, "_lip_model", None) is not None
+        if kind == "GGN" and native and symmetric:
+            bm = Av._lip_model
+            self.struct.kind, self.struct.model = cabi.LINOP_GGN, bm._h
+            self.struct.scale, self.struct.alpha = float(Av._lip_recal), float(Av._lip_alpha)
+            self.keep.append(bm)
+        elif kind == "GKL" and native and not symmetric:
+            bm = Av._lip_model
+            self.struct.kind, self.struct.model = cabi.LINOP_GKL, bm._h
+            self.struct.scale, self.struct.alpha = float(Av._lip_scale), float(Av._lip_alpha)
+            self.keep.append(bm)
+        elif kind == "DENSE_SYM" and symmetric:
+            G = Av._lip_dense
+            self.struct.kind, self.struct.dense, self.struct.n = cabi.LINOP_DENSE_SYM, G.data_ptr(), int(G.shape[0])
+            self.struct.alpha, self.struct.beta = float(Av._lip_alpha), float(Av._lip_beta)
+            self.keep.append(G)
+        else:
+            dev = _require_cuda()
+            self.cb_in = torch.empty(B, n_in, device=dev)
+            self.cb_out = torch.empty(B, n_out, device=dev)
+            self.struct.kind, self.struct.symmetric = cabi.LINOP_CALLBACK, 1 if symmetric else 0
+            self.struct.n, self.struct.n_out = n_in, n_out
+            self.struct.cb_in, self.struct.cb_out = self.cb_in.data_ptr(), self.cb_out.data_ptr()
+            if not symmetric:
+                self.cb_in_t = torch.empty(B, n_out, device=dev)
+                self.cb_out_t = torch.empty(B, n_in, device=dev)
+                self.struct.cb_in_t, self.struct.cb_out_t = self.cb_in_t.data_ptr(), self.cb_out_t.data_ptr()
+
+            def call(_ctx, transpose, nb, _stream):
+                try:
+                    if transpose:
+                        self.cb_out_t[:nb].copy_(_apply(vA, self.cb_in_t[:nb], single))
+                    else:
+                        self.cb_out[:nb].copy_(_apply(Av, self.cb_in[:nb], single))
+                    return 0
+                except BaseException as e:          # noqa: BLE001  (re-raised by check() after the native call returns)
+                    self.exc = e
+                    return 1
+
+            self.fn = cabi.MATVEC_FN(call)
+            self.struct.fn = self.fn
+
+    def ref(self):
+        import ctypes
+        return ctypes.byref(self.struct)
+
+    def check(self, rc, what):
+        if self.exc is not None:
+            exc, self.exc = self.exc, None
+            raise exc
+        cabi.check(rc, what)
+
+    def workspace(self, routine, k, B):
+        need = cabi.lib().lip_krylov_workspace_bytes(self.ref(), routine, k, B)
+        if need == 0:
+            raise ValueError("lip_krylov_workspace_bytes: " + cabi.lib().lip_last_error().decode("utf-8", "replace"))
+        buf = torch.empty(need, dtype=torch.uint8, device=_require_cuda())   # local: lives exactly as long as the recurrence
+        return buf, need
+
+
+def gkl_target(WTfun, Wfun, alpha):
+    """bidiag_target of train_inducing.py:166-169 for closures from ggn.compute_W_vps:  v -> [sqrt(alpha) v ; W^T v]  in R^{D+d}
+    (its transpose, which matfree obtains with jax.vjp, is `._lip_transpose`).  Passed to decomp.bidiag / the product-logdet
+    integrand the whole Golub-Kahan recurrence runs natively (LIP_LINOP_GKL)."""
+    bm = WTfun._lip_model
+    D, d = bm.D, bm.M * bm.K
+    sa = math.sqrt(float(alpha))
+
+    def Av(v):
+        V, single = _as2d(v)
+        out = torch.cat([sa * V, WTfun(V).reshape(V.shape[0], d)], dim=1)
+        return out[0] if single else out
+
+    def vA(u):
+        U, single = _as2d(u)
+        out = Wfun(U[:, D:].reshape((-1,) + ((bm.M,) if bm.model_type == "regressor" else (bm.M, bm.K)))).reshape(U.shape[0], D)
+        out = out + sa * U[:, :D]
+        return out[0] if single else out
+
+    for f, t in ((Av, vA), (vA, Av)):
+        f._lip_batched = True
+        f._lip_transpose = t
+    Av._lip_kind, Av._lip_model, Av._lip_scale, Av._lip_alpha = "GKL", bm, WTfun._lip_scale, float(alpha)
+    return Av
+
+
+def dense_sym_operator(G, alpha, beta):
+    """u -> alpha u + beta G u for a dense symmetric G (inner_fun_flat of sample.py:120-125); runs as LIP_LINOP_DENSE_SYM."""
+    G = dev_f32(G)
+    if G.dim() != 2 or G.shape[0] != G.shape[1]:
+        raise ValueError(f"dense_sym_operator: square matrix expected, got {tuple(G.shape)}")
+
+    def mv(u):
+        U, single = _as2d(u)
+        U = U.contiguous()
+        op = _NativeOp(mv, None, U.shape[0], G.shape[0], G.shape[0], single, symmetric=True)
+        out = torch.empty_like(U)
+        ws, need = op.workspace(cabi.KRYLOV_APPLY, 1, U.shape[0])
+        op.check(cabi.lib().lip_linop_apply(op.ref(), ptr(U), ptr(out), U.shape[0], 0, ptr(ws), need, stream()), "lip_linop_apply")
+        return out[0] if single else out
+
+    mv._lip_batched, mv._lip_kind, mv._lip_dense, mv._lip_alpha, mv._lip_beta = True, "DENSE_SYM", G, float(alpha), float(beta)
+    return mv
+
+
 # ---------------------------------------------------------------------------------------------- CG
-def cg(A: Callable, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, check_every=4):
+def cg(A: Callable, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, check_every=8):
     """jax.scipy.sparse.linalg.cg semantics: x0 = 0, stop when r.r <= max(tol^2 b.b, atol^2) or after
-    maxiter (default 10 n) iterations, identity preconditioner.  Returns (x, info) with info = iterations [B]."""
+    maxiter (default 10 n) iterations, identity preconditioner.  Returns (x, info) with info = iterations [B].
+    One native call (lip_cg_solve); check_every = 0 never synchronises (exactly maxiter masked iterations)."""
     if x0 is not None:
         raise NotImplementedError("cg: x0 is not used by the reference's call sites")
     L = cabi.lib()
     Bm, single = _as2d(b)
     Bm = Bm.contiguous()
     nb, n = Bm.shape
-    maxiter = 10 * n if maxiter is None else int(maxiter)
-    dev = Bm.device
+    op = _NativeOp(A, None, nb, n, n, single, symmetric=True)
     x = torch.empty_like(Bm)
-    r = torch.empty_like(Bm)
-    p = torch.empty_like(Bm)
-    gamma = torch.empty(nb, device=dev)
-    thresh = torch.empty(nb, device=dev)
-    active = torch.empty(nb, device=dev, dtype=torch.int32)
-    iters = torch.empty(nb, device=dev, dtype=torch.int32)
-    sc, _ = scratch(L.lip_dot_scratch_bytes(n, nb))
-    cabi.check(L.lip_cg_init(ptr(Bm), ptr(x), ptr(r), ptr(p), ptr(gamma), ptr(thresh), ptr(active), ptr(iters),
-                             float(tol), float(atol), n, nb, sc, stream()), "lip_cg_init")
-    k = 0
-    while k < maxiter:
-        if k % check_every == 0 and not bool(active.any().item()):
-            break
-        Ap = _apply(A, p, single).contiguous()
-        cabi.check(L.lip_cg_step(ptr(x), ptr(r), ptr(p), ptr(Ap), ptr(gamma), ptr(thresh), ptr(active), ptr(iters),
-                                 n, nb, sc, stream()), "lip_cg_step")
-        k += 1
+    iters = torch.empty(nb, device=Bm.device, dtype=torch.int32)
+    ws, need = op.workspace(cabi.KRYLOV_CG, 1, nb)
+    rc = L.lip_cg_solve(op.ref(), ptr(Bm), ptr(x), nb, float(tol), float(atol), -1 if maxiter is None else int(maxiter),
+                        int(check_every), ptr(iters), ptr(ws), need, stream())
+    op.check(rc, "lip_cg_solve")
     return (x[0] if single else x), (iters[0] if single else iters)
 
 
 # ---------------------------------------------------------------------------------------------- decompositions
 class _Tridiag:
-    """Result of tridiag_sym: basis Q [B, k, ldq] (rows are Lanczos vectors), diag [B,k], off [B,k-1]."""
+    """Result of tridiag_sym: basis Q [B, k, ldq] (rows are Lanczos vectors), diag [B,k], off [B,k-1], norm0 [B] = |v0|."""
 
-    def __init__(self, Q, ldq, n, diag, off):
-        self.Q, self.ldq, self.n, self.diag, self.off = Q, ldq, n, diag, off
+    def __init__(self, Q, ldq, n, diag, off, norm0=None):
+        self.Q, self.ldq, self.n, self.diag, self.off, self.norm0 = Q, ldq, n, diag, off, norm0
 
 
-def _tridiag_sym(num_matvecs: int, *, keep_basis=True):
-    """matfree.decomp.tridiag_sym(k), reortho='full' (Arnoldi form, T = (H + H^T)/2 on its three diagonals)."""
+def _tridiag_sym(num_matvecs: int, *, keep_basis=True, passes=2):
+    """matfree.decomp.tridiag_sym(k), reortho='full' (Arnoldi form, T = (H + H^T)/2 on its three diagonals): one
+    lip_lanczos_tridiag call."""
     k = int(num_matvecs)
 
     def decompose(matvec, vec):
         L = cabi.lib()
         V, single = _as2d(vec)
+        V = V.contiguous()
         nb, n = V.shape
         if k > n:
             raise ValueError(f"num_matvecs={k} exceeds the operator dimension {n}")
         dev = V.device
         ldq = _pad4(n)
-        Q = torch.zeros(nb, k, ldq, device=dev)
-        H = torch.zeros(nb, k, k, device=dev)          # H[b, step, coeff]
-        lengths = torch.zeros(nb, k, device=dev)       # |v| after step i
-        v = torch.zeros(nb, ldq, device=dev)
-        v[:, :n] = V
-        qc = torch.empty(nb, n, device=dev)
-        length = torch.empty(nb, device=dev)
-        hbuf = torch.zeros(nb, k, device=dev)
-        sc_dot, _ = scratch(max(L.lip_dot_scratch_bytes(n, nb), L.lip_reorth_scratch_bytes(n, nb, k)))
-        cabi.check(L.lip_dot(ptr(v), ptr(v), ptr(length), n, nb, ldq, ldq, sc_dot, stream()))
-        length.sqrt_()
-        for i in range(k):
-            qi = Q[:, i, :]
-            # q_i = v / |v|  (stored in the basis and, contiguous, as the matvec input)
-            cabi.check(L.lip_scale(ptr(length), 1, ptr(v), C_void(qi), n, nb, ldq, k * ldq, stream()))
-            cabi.check(L.lip_scale(ptr(length), 1, ptr(v), ptr(qc), n, nb, ldq, n, stream()))
-            w = _apply(matvec, qc, single)
-            v[:, :n] = w
-            cabi.check(L.lip_reorth(ptr(Q), ldq, i + 1, k, ptr(v), ldq, ptr(hbuf), ptr(length), 2, n, nb,
-                                    sc_dot, stream()), "lip_reorth")
-            H[:, i, :i + 1] = hbuf[:, :i + 1]
-            lengths[:, i] = length
-        idx = torch.arange(k, device=dev)
-        diag = H[:, idx, idx].contiguous()
-        if k > 1:
-            upper = H[:, idx[1:], idx[:-1]]            # H[i, i+1] = q_i . A q_{i+1}  (coeff i at step i+1)
-            off = (0.5 * (upper + lengths[:, :-1])).contiguous()
-        else:
-            off = torch.zeros(nb, 0, device=dev)
-        return _Tridiag(Q, ldq, n, diag, off), single
+        op = _NativeOp(matvec, None, nb, n, n, single, symmetric=True)
+        Q = torch.empty(nb, k, ldq, device=dev)
+        diag = torch.empty(nb, k, device=dev)
+        off = torch.empty(nb, max(k - 1, 1), device=dev)
+        norm0 = torch.empty(nb, device=dev)
+        ws, need = op.workspace(cabi.KRYLOV_LANCZOS, k, nb)
+        rc = L.lip_lanczos_tridiag(op.ref(), ptr(V), n, k, nb, int(passes), ptr(Q), ldq, ptr(diag), ptr(off), ptr(norm0),
+                                   ptr(ws), need, stream())
+        op.check(rc, "lip_lanczos_tridiag")
+        return _Tridiag(Q, ldq, n, diag, off[:, :k - 1].contiguous(), norm0), single
 
     return decompose
 
 
-def C_void(t: torch.Tensor):
-    import ctypes
-    return ctypes.c_void_p(t.data_ptr())
-
-
 class _Bidiag:
-    def __init__(self, alphas, betas):
-        self.alphas, self.betas = alphas, betas
+    def __init__(self, alphas, betas, Us=None, Vs=None, norm0=None):
+        self.alphas, self.betas, self.Us, self.Vs, self.norm0 = alphas, betas, Us, Vs, norm0
 
 
 def _bidiag(num_matvecs: int):
-    """matfree.decomp.bidiag(k): Golub-Kahan-Lanczos, full re-orthogonalisation of both bases.
+    """matfree.decomp.bidiag(k): Golub-Kahan-Lanczos, full re-orthogonalisation of both bases: one lip_gkl_bidiag call.
     decompose(Av, vA, v0): vA is A^T (matfree derives it with jax.vjp; closures from this package carry it as
     `._lip_transpose`, otherwise pass it)."""
     k = int(num_matvecs)
@@ -154,69 +241,30 @@ def _bidiag(num_matvecs: int):
     def decompose(Av, vA, v0):
         L = cabi.lib()
         V0, single = _as2d(v0)
+        V0 = V0.contiguous()
         nb, ncols = V0.shape
         dev = V0.device
-        ldv = _pad4(ncols)
-        vk = torch.zeros(nb, ldv, device=dev)
-        vk[:, :ncols] = V0
-        tmp = torch.empty(nb, device=dev)
-        vc = torch.empty(nb, ncols, device=dev)
-        sc0, _ = scratch(L.lip_dot_scratch_bytes(ncols, nb))
-        cabi.check(L.lip_dot(ptr(vk), ptr(vk), ptr(tmp), ncols, nb, ldv, ldv, sc0, stream()))
-        tmp.sqrt_()
-        cabi.check(L.lip_scale(ptr(tmp), 1, ptr(vk), ptr(vk), ncols, nb, ldv, ldv, stream()))
-        cabi.check(L.lip_scale(ptr(tmp), 1, ptr(V0.contiguous()), ptr(vc), ncols, nb, ncols, ncols, stream()))
-        probe = _apply(Av, vc, single)
-        nrows = probe.shape[1]
-        ldu = _pad4(nrows)
+        if getattr(Av, "_lip_kind", None) == "GKL" and getattr(Av, "_lip_model", None) is not None:
+            bm = Av._lip_model
+            nrows = bm.D + bm.M * bm.K
+        elif hasattr(Av, "_lip_out_dim"):
+            nrows = int(Av._lip_out_dim)
+        else:                      # learn the row count from one application (matfree traces the function instead)
+            nrows = int(_apply(Av, V0[:1], single).shape[1])
         if k > min(nrows, ncols):
             raise ValueError(f"num_matvecs={k} exceeds the operator dimensions ({nrows}, {ncols})")
-        Us = torch.zeros(nb, k, ldu, device=dev)
-        Vs = torch.zeros(nb, k, ldv, device=dev)
-        alphas = torch.zeros(nb, k, device=dev)
-        betas = torch.zeros(nb, k, device=dev)
-        beta = torch.zeros(nb, device=dev)
-        alpha = torch.empty(nb, device=dev)
-        uk = torch.zeros(nb, ldu, device=dev)
-        uc = torch.empty(nb, nrows, device=dev)
-        nrm = torch.empty(nb, device=dev)
-        ones = torch.ones(nb, device=dev)
-        sc, _ = scratch(max(L.lip_reorth_scratch_bytes(max(nrows, ncols), nb, k),
-                            L.lip_dot_scratch_bytes(max(nrows, ncols), nb)))
-        for i in range(k):
-            Vs[:, i, :] = vk
-            betas[:, i] = beta
-            vc.copy_(vk[:, :ncols])
-            Avk = probe if i == 0 else _apply(Av, vc, single)
-            uk[:, :nrows] = Avk
-            if i > 0:   # uk = A vk - beta * U_{i-1}
-                nbeta = -beta
-                cabi.check(L.lip_axpby(ptr(nbeta), C_void(Us[:, i - 1, :]), ptr(ones), ptr(uk),
-                                       nrows, nb, k * ldu, ldu, stream()))
-            # alpha = |uk|; uk /= alpha; CGS against all stored U; renormalise
-            cabi.check(L.lip_dot(ptr(uk), ptr(uk), ptr(alpha), nrows, nb, ldu, ldu, sc, stream()))
-            alpha.sqrt_()
-            cabi.check(L.lip_scale(ptr(alpha), 1, ptr(uk), ptr(uk), nrows, nb, ldu, ldu, stream()))
-            cabi.check(L.lip_reorth(ptr(Us), ldu, i, k, ptr(uk), ldu, None, ptr(nrm), 1, nrows, nb, sc, stream()))
-            cabi.check(L.lip_scale(ptr(nrm), 1, ptr(uk), ptr(uk), nrows, nb, ldu, ldu, stream()))
-            Us[:, i, :] = uk
-            alphas[:, i] = alpha
-            uc.copy_(uk[:, :nrows])
-            w = _apply(vA, uc, single)
-            # vk = A^T uk - alpha * V_i
-            vnew = torch.zeros(nb, ldv, device=dev)
-            vnew[:, :ncols] = w
-            nalpha = -alpha
-            cabi.check(L.lip_axpby(ptr(nalpha), C_void(Vs[:, i, :]), ptr(ones), ptr(vnew),
-                                   ncols, nb, k * ldv, ldv, stream()))
-            beta = torch.empty(nb, device=dev)
-            cabi.check(L.lip_dot(ptr(vnew), ptr(vnew), ptr(beta), ncols, nb, ldv, ldv, sc, stream()))
-            beta.sqrt_()
-            cabi.check(L.lip_scale(ptr(beta), 1, ptr(vnew), ptr(vnew), ncols, nb, ldv, ldv, stream()))
-            cabi.check(L.lip_reorth(ptr(Vs), ldv, i + 1, k, ptr(vnew), ldv, None, ptr(nrm), 1, ncols, nb, sc, stream()))
-            cabi.check(L.lip_scale(ptr(nrm), 1, ptr(vnew), ptr(vnew), ncols, nb, ldv, ldv, stream()))
-            vk = vnew
-        return _Bidiag(alphas, betas), single
+        op = _NativeOp(Av, vA, nb, ncols, nrows, single, symmetric=False)
+        ldu, ldv = _pad4(nrows), _pad4(ncols)
+        Us = torch.empty(nb, k, ldu, device=dev)
+        Vs = torch.empty(nb, k, ldv, device=dev)
+        alphas = torch.empty(nb, k, device=dev)
+        betas = torch.empty(nb, k, device=dev)
+        norm0 = torch.empty(nb, device=dev)
+        ws, need = op.workspace(cabi.KRYLOV_GKL, k, nb)
+        rc = L.lip_gkl_bidiag(op.ref(), ptr(V0), ncols, k, nb, ptr(Us), ldu, ptr(Vs), ldv, ptr(alphas), ptr(betas), ptr(norm0),
+                              ptr(ws), need, stream())
+        op.check(rc, "lip_gkl_bidiag")
+        return _Bidiag(alphas, betas, Us, Vs, norm0), single
 
     return decompose
 
@@ -284,14 +332,13 @@ def funm_lanczos_sym(dense_funm: DenseFunm, tridiag_sym):
         L = cabi.lib()
         V, single = _as2d(vec)
         nb, n = V.shape
-        length = torch.linalg.vector_norm(V, dim=1)
-        res, _ = tridiag_sym(matvec, V / length[:, None])
-        fe1 = dense_funm.apply_e1(res.diag, res.off)
+        res, _ = tridiag_sym(matvec, V)                       # normalises v itself; res.norm0 = |v|
+        fe1 = dense_funm.apply_e1(res.diag, res.off) * res.norm0[:, None]
         k = res.diag.shape[1]
         out = torch.empty(nb, res.ldq, device=V.device)
-        cabi.check(L.lip_basis_combine(ptr(res.Q), res.ldq, k, k, ptr(fe1), k, ptr(out), res.ldq, n, nb, stream()),
+        cabi.check(L.lip_basis_combine(ptr(res.Q), res.ldq, k, k, ptr(fe1.contiguous()), k, ptr(out), res.ldq, n, nb, stream()),
                    "lip_basis_combine")
-        out = out[:, :n] * length[:, None]
+        out = out[:, :n]
         return out[0] if single else out
 
     return batched(estimate)
@@ -302,9 +349,8 @@ def integrand_funm_sym(dense_funm: DenseFunm, tridiag_sym):
 
     def quadform(matvec, v0):
         V, single = _as2d(v0)
-        length = torch.linalg.vector_norm(V, dim=1)
-        res, _ = tridiag_sym(matvec, V / length[:, None])
-        q = dense_funm.quad_e1(res.diag, res.off) * length ** 2
+        res, _ = tridiag_sym(matvec, V)
+        q = dense_funm.quad_e1(res.diag, res.off) * res.norm0 ** 2
         return q[0] if single else q
 
     return batched(quadform)
@@ -327,8 +373,8 @@ def integrand_funm_product_logdet(bidiag):
             raise ValueError("integrand_funm_product_logdet: the transpose operator is required (pass vA=... or use a "
                              "closure built by this package)")
         V, single = _as2d(v0)
-        length = torch.linalg.vector_norm(V, dim=1)
-        res, _ = bidiag(Av, vA_, V / length[:, None])
+        res, _ = bidiag(Av, vA_, V)
+        length = res.norm0
         nb, k = res.alphas.shape
         td = torch.empty(nb, k, device=V.device)
         to = torch.empty(nb, max(k - 1, 1), device=V.device)

@@ -7,7 +7,7 @@ import torch
 
 from ._runtime import dev_f32
 from .ggn import _batched, build_WTW, compute_W_vps
-from .matfree import _generator, batched, decomp, funm_lanczos_sym
+from .matfree import _generator, decomp, dense_sym_operator, funm_lanczos_sym
 from .matfree_monkeypatch import dense_funm_sym_eigh
 
 
@@ -39,11 +39,9 @@ def inv_matsqrt_vp(state, Z, D, alpha, model_type, full_set_size=None, key=None,
         raise ValueError(f"tridiag_sym(2*M={2 * M}) exceeds the Gram dimension d={d} (regressors: SURVEY §3.4)")
     invmatsqrt = funm_lanczos_sym(invsqrt_fun, decomp.tridiag_sym(2 * M))
 
-    @batched
-    def inner_fun_flat(U):              # sample.py:120-125: u -> alpha u + beta WTW u   (dense d x d matvec)
-        U2 = U.reshape(-1, d)
-        out = alpha * U2 + beta * (U2 @ WTW)      # WTW symmetric
-        return out.reshape(U.shape)
+    # sample.py:120-125: u -> alpha u + beta WTW u, the dense d x d mat-vec inside the Lanczos recurrence (LIP_LINOP_DENSE_SYM:
+    # the whole 2M-step recurrence runs in one native call)
+    inner_fun_flat = dense_sym_operator(WTW, alpha, beta)
 
     def vp(v):
         V = dev_f32(v)

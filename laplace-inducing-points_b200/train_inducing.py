@@ -58,15 +58,10 @@ def alternative_objective_scalable(Z, X, state, alpha, model_type, key, full_set
     k = slq_num_matvecs if slq_num_matvecs is not None else int(M * 0.8)                         # :148
     sqrt_alpha = math.sqrt(alpha)
 
-    @matfree.batched
-    def bidiag_target(V):                                                                        # :166-169
-        V = V.reshape(-1, D)
-        return torch.cat([sqrt_alpha * V, WzT(V).reshape(V.shape[0], d_z)], dim=1)
-
-    @matfree.batched
-    def bidiag_target_T(U):                                   # jax.vjp of bidiag_target inside matfree.decomp.bidiag
-        U = U.reshape(-1, D + d_z)
-        return Wz(U[:, D:].reshape((-1,) + inner_shape)).add_(U[:, :D], alpha=sqrt_alpha)
+    # bidiag_target v -> [sqrt(alpha) v ; W_z^T v] (:166-169) and its transpose (jax.vjp inside matfree.decomp.bidiag): the
+    # closure pair carries the bound model, so the whole Golub-Kahan recurrence runs natively (LIP_LINOP_GKL)
+    bidiag_target = matfree.gkl_target(WzT, Wz, alpha)
+    bidiag_target_T = bidiag_target._lip_transpose
 
     problem = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(k))               # :156-157
     logdet_term = problem(bidiag_target, probes[:slq_samples], bidiag_target_T).mean()           # :159-163

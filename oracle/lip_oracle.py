@@ -267,25 +267,29 @@ def materialize_covariance(f_cov_vp, N, out_dim, mode="diag"):
 # ======================================================================================
 # jax.scipy.sparse.linalg.cg  (third-party, absent; restated from its published algorithm)
 # ======================================================================================
-def cg(A: Callable, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None):
+def cg(A: Callable, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, dtype=np.float64):
     """x0=0; stop when r.r <= max(tol^2 b.b, atol^2) or k == maxiter (default 10*n); M = identity.
-    Call sites: stochtrace.py:146,192; sample.py:71."""
-    b = np.asarray(b, dtype=np.float64)
+    Call sites: stochtrace.py:146,192; sample.py:71.
+    dtype=np.float32 runs the SAME recurrence in the reference's production precision (main.py:28): every vector, dot product
+    and scalar is float32, which is what shows the attainable accuracy of the reference's algorithm on ill-conditioned operators
+    (tests/test_gpu_config_parity.py::test_C2_*)."""
+    ft = np.dtype(dtype).type
+    b = np.asarray(b, dtype=dtype)
     n = b.size
     maxiter = 10 * n if maxiter is None else maxiter
-    x = np.zeros_like(b) if x0 is None else np.asarray(x0, dtype=np.float64).copy()
-    r = b - A(x) if x0 is not None else b.copy()
+    x = np.zeros_like(b) if x0 is None else np.asarray(x0, dtype=dtype).copy()
+    r = (b - np.asarray(A(x), dtype=dtype)) if x0 is not None else b.copy()
     p = r.copy()
-    gamma = float(r.ravel() @ r.ravel())
-    atol2 = max(tol * tol * float(b.ravel() @ b.ravel()), atol * atol)
+    gamma = ft(r.ravel() @ r.ravel())
+    atol2 = max(ft(tol) * ft(tol) * ft(b.ravel() @ b.ravel()), ft(atol) * ft(atol))
     k = 0
     while gamma > atol2 and k < maxiter:
-        Ap = np.asarray(A(p), dtype=np.float64)
-        a = gamma / float(p.ravel() @ Ap.ravel())
+        Ap = np.asarray(A(p), dtype=dtype)
+        a = ft(gamma / ft(p.ravel() @ Ap.ravel()))
         x = x + a * p
         r = r - a * Ap
-        gamma_ = float(r.ravel() @ r.ravel())
-        p = r + (gamma_ / gamma) * p
+        gamma_ = ft(r.ravel() @ r.ravel())
+        p = r + ft(gamma_ / gamma) * p
         gamma = gamma_
         k += 1
     return x, k
