@@ -234,6 +234,13 @@ int lip_basis_combine(const float* Q, int64_t ldq, int64_t kk, int64_t kmax, con
 size_t lip_tridiag_scratch_bytes(int64_t k, int64_t B, int32_t want_vectors);
 int lip_tridiag_funm(const float* diag, const float* off, int64_t k, int64_t B, int32_t fn, float clip_min,
                      float* quad_out, float* fe1_out, float* eig_out, void* scratch, lip_stream_t stream);
+/* The same with parameterised functions.  fn 4 = LIP_FN_SAMPLER, params = {alpha, beta, tau} (a HOST array of 3 floats):
+ *   psi(th) = (clip(th, clip_min)^{-1/2} - alpha^{-1/2}) / lam,  lam = (th - alpha)/beta;  psi = 0 where lam <= tau * lam_max.
+ * On the Lanczos matrix of alpha I + beta W^T W (src/sample.py:113-125) this is the whole output-space part of the posterior
+ * sampler: A^{-1/2} v = alpha^{-1/2} v + W psi(W^T W) W^T v — the two solves with the singular Gram of src/sample.py:81,135
+ * (jax.scipy.linalg.solve) become part of the matrix function, with the pseudo-inverse cut at the fp32 noise level tau. */
+int lip_tridiag_funm_p(const float* diag, const float* off, int64_t k, int64_t B, int32_t fn, float clip_min, const float* params,
+                       float* quad_out, float* fe1_out, float* eig_out, void* scratch, lip_stream_t stream);
 /* T = Bd^T Bd for upper-bidiagonal Bd = diag(alphas) + superdiag(betas[1:]):  tdiag[i] = a_i^2 + b_i^2
  * (b_0 := 0), toff[i] = a_i * b_{i+1}.  alphas, betas: [B,k]. */
 int lip_bidiag_to_tridiag(const float* alphas, const float* betas, float* tdiag, float* toff, int64_t k,
@@ -279,7 +286,7 @@ typedef enum {
   LIP_KRYLOV_LANCZOS = 0, LIP_KRYLOV_GKL = 1, LIP_KRYLOV_SLQ_LANCZOS = 2, LIP_KRYLOV_SLQ_GKL = 3, LIP_KRYLOV_FUNM = 4,
   LIP_KRYLOV_CG = 5, LIP_KRYLOV_HUTCHPP = 6, LIP_KRYLOV_APPLY = 7
 } lip_krylov_routine;
-/* workspace bytes of the routine below for depth k (CG, APPLY: ignored; HUTCHPP: s1) and B columns */
+/* workspace bytes of the routine below for depth k (CG, APPLY: ignored; HUTCHPP: k = s1, B = s2) and B columns */
 size_t lip_krylov_workspace_bytes(const lip_linop* op, int32_t routine, int64_t k, int64_t B);
 
 /* out = A in (transpose = 0: in [B, n] -> out [B, n_out]) or A^T in (transpose = 1), both contiguous: the operator on its own. */
@@ -310,9 +317,19 @@ typedef enum { LIP_SLQ_LANCZOS = 0, LIP_SLQ_GKL = 1 } lip_slq_form;
 int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form, int32_t fn,
                        float clip_min, float* quad_out, void* workspace, size_t workspace_bytes, lip_stream_t stream);
 
-/* matfree.funm.funm_lanczos_sym: out[b,:] = |v_b| Q_b f(T_b) e1 ~= f(A) v_b   (src/sample.py:113-115: f = 1/sqrt, clip_min = 1). */
+/* matfree.funm.funm_lanczos_sym: out[b,:] = |v_b| Q_b f(T_b) e1 ~= f(A) v_b   (src/sample.py:113-115: f = 1/sqrt, clip_min = 1).
+ * fn_params: host array for parameterised functions (lip_tridiag_funm_p), else NULL. */
 int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv, int64_t k, int64_t B, int32_t fn, float clip_min,
-                     float* out, int64_t ldo, void* workspace, size_t workspace_bytes, lip_stream_t stream);
+                     const float* fn_params, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, lip_stream_t stream);
+
+/* hutchpp_v2 (src/stochtrace.py:118-135):  tr X ~= tr(Q^T X Q) + tr(G_perp X G_perp^T) / s2,  S = probes[:s1], G = probes[s1:s1+s2],
+ * Q = orth(X S^T), G_perp = G - (G Q) Q^T.  probes: [s1 + s2, ldp] rows.  out: one float (device).
+ * jnp.linalg.qr of the [n, s1] block is a shifted CholeskyQR with three passes (float64 Gram by a tall-skinny reduction kernel, one-CTA
+ * Cholesky + triangular inverse, Q <- L^{-1} Y as a GEMM): the estimate depends on span(Q) only, so any orthonormal basis is the
+ * reference's.  info (optional, int32 device): non-zero when a Cholesky pivot was not positive (cond(X S^T) beyond ~1e7).
+ * Workspace: lip_krylov_workspace_bytes(op, LIP_KRYLOV_HUTCHPP, s1, s2). */
+int lip_hutchpp_v2(const lip_linop* op, const float* probes, int64_t ldp, int64_t s1, int64_t s2, float* out, int32_t* info,
+                   void* workspace, size_t workspace_bytes, lip_stream_t stream);
 
 /* jax.scipy.sparse.linalg.cg(A, b): x0 = 0, stop when r.r <= max(tol^2 b.b, atol^2) or after maxiter iterations (< 0: 10 n).
  * b, x: [B, n] contiguous.  check_every > 0: the host polls a pinned flag every check_every iterations and stops enqueueing once

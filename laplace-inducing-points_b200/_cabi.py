@@ -16,7 +16,7 @@ OP_BATCHNORM, OP_RES_SAVE, OP_RES_CONV2D, OP_RES_BATCHNORM, OP_RES_ADD, OP_GLOBA
 REGRESSOR, CLASSIFIER = 0, 1
 FACTOR_NONE, FACTOR_SQRT = 0, 1
 ZGRAD_GGN, ZGRAD_WT, ZGRAD_W, ZGRAD_JVP = 0, 1, 2, 3
-FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY = 0, 1, 2, 3
+FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY, FN_SAMPLER = 0, 1, 2, 3, 4
 LINOP_GGN, LINOP_GKL, LINOP_DENSE_SYM, LINOP_CALLBACK = 0, 1, 2, 3
 KRYLOV_LANCZOS, KRYLOV_GKL, KRYLOV_SLQ_LANCZOS, KRYLOV_SLQ_GKL, KRYLOV_FUNM, KRYLOV_CG, KRYLOV_HUTCHPP, KRYLOV_APPLY = 0, 1, 2, 3, 4, 5, 6, 7
 SLQ_LANCZOS, SLQ_GKL = 0, 1
@@ -84,13 +84,15 @@ SIGNATURES = {
     "lip_basis_combine": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _I64, _I64, _P]),
     "lip_tridiag_scratch_bytes": (_SZ, [_I64, _I64, _I32]),
     "lip_tridiag_funm": (C.c_int, [_P, _P, _I64, _I64, _I32, _F, _P, _P, _P, _P, _P]),
+    "lip_tridiag_funm_p": (C.c_int, [_P, _P, _I64, _I64, _I32, _F, C.POINTER(C.c_float), _P, _P, _P, _P, _P]),
     "lip_bidiag_to_tridiag": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
     "lip_krylov_workspace_bytes": (_SZ, [_LP, _I32, _I64, _I64]),
     "lip_linop_apply": (C.c_int, [_LP, _P, _P, _I64, _I32, _P, _SZ, _P]),
     "lip_lanczos_tridiag": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "lip_gkl_bidiag": (C.c_int, [_LP, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "lip_slq_quadrature": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _I32, _F, _P, _P, _SZ, _P]),
-    "lip_funm_lanczos": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _F, _P, _I64, _P, _SZ, _P]),
+    "lip_funm_lanczos": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _F, C.POINTER(C.c_float), _P, _I64, _P, _SZ, _P]),
+    "lip_hutchpp_v2": (C.c_int, [_LP, _P, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "lip_cg_solve": (C.c_int, [_LP, _P, _P, _I64, _F, _F, _I64, _I32, _P, _P, _SZ, _P]),
     "lip_bench_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, _I32, _I32, _I32, C.POINTER(_F), _P]),
     "lip_selftest_tc_gemm": (C.c_int, [_I32, _I64, _I64, _I64, _I64, C.POINTER(_F), _P]),

@@ -420,6 +420,135 @@ __global__ void dense_sym_finish_kernel(const float* __restrict__ part, int nspl
   out[b * ldo + j] = alpha * u[b * ldu + j] + beta * s;
 }
 
+
+// ---- tall-skinny building blocks of Hutch++ (src/stochtrace.py:118-135): the [n, s1] QR and the deflation G - (G Q) Q^T ------------
+// Row-stored blocks: Y [s, n] holds s vectors of length n (what the probe-batched operators produce).
+// gram:  P[a][b] = sum_j A[a][j] * Bm[b][j]   accumulated in float64 (the products of floats are exact in double, so the Gram of an
+// ill-conditioned block keeps 1e-16 relative accuracy and its Cholesky factor exists for cond(Y) up to ~1e7).  Grid (pair tiles of
+// 16 x 16, n splits); deterministic second stage.
+constexpr int GT = 16;          // pair tile
+constexpr int GC = 64;          // columns per shared-memory tile
+__global__ void __launch_bounds__(GT * GT) gram_partial_kernel(const float* __restrict__ A, int64_t lda, int sa, const float* __restrict__ Bm,
+                                                               int64_t ldb, int sb, int64_t n, int64_t cols_per_split,
+                                                               double* __restrict__ part) {
+  __shared__ float As[GT][GC + 1], Bs[GT][GC + 1];
+  const int tiles_b = (sb + GT - 1) / GT;
+  const int ta = blockIdx.x / tiles_b, tb = blockIdx.x % tiles_b;
+  const int ia = threadIdx.x / GT, ib = threadIdx.x % GT;
+  const int64_t c0 = (int64_t)blockIdx.y * cols_per_split;
+  const int64_t c1 = (c0 + cols_per_split < n) ? c0 + cols_per_split : n;
+  double acc = 0.0;
+  for (int64_t c = c0; c < c1; c += GC) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < GT * GC; idx += GT * GT) {
+      const int r = idx / GC, cc = idx % GC;
+      const int64_t col = c + cc;
+      const int ra = ta * GT + r, rb = tb * GT + r;
+      As[r][cc] = (ra < sa && col < c1) ? A[(int64_t)ra * lda + col] : 0.f;
+      Bs[r][cc] = (rb < sb && col < c1) ? Bm[(int64_t)rb * ldb + col] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int cc = 0; cc < GC; ++cc) acc += (double)As[ia][cc] * (double)Bs[ib][cc];
+  }
+  const int a = ta * GT + ia, b = tb * GT + ib;
+  if (a < sa && b < sb) part[((int64_t)blockIdx.y * sa + a) * sb + b] = acc;
+}
+
+// out[a][b] = sum over splits (fixed order); optional float copy
+__global__ void gram_finish_kernel(const double* __restrict__ part, int nsplit, int64_t count, double* __restrict__ out, float* __restrict__ outf) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double s = 0.0;
+  for (int sp = 0; sp < nsplit; ++sp) s += part[(int64_t)sp * count + i];
+  if (out) out[i] = s;
+  if (outf) outf[i] = (float)s;
+}
+
+// One CTA: C (s x s, float64, symmetric positive definite up to rounding) -> Tinv = L^{-1} with C + shift I = L L^T, as float [s][s]
+// (lower triangular, zeros above).  shift = 1e-13 * trace(C) keeps the factorisation alive on numerically rank-deficient blocks; the
+// second and third passes of CholeskyQR remove its effect.  flag[0] is set when a pivot is not positive.
+__global__ void __launch_bounds__(1024) chol_inv_kernel(double* __restrict__ C, int s, float* __restrict__ Tinv, double* __restrict__ Linv,
+                                                        int* __restrict__ flag) {
+  __shared__ double sh_piv;
+  __shared__ double red[32];
+  const int t = threadIdx.x, nt = blockDim.x;
+  double tr = 0.0;
+  for (int i = t; i < s; i += nt) tr += C[(int64_t)i * s + i];
+  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  if ((t & 31) == 0) red[t >> 5] = tr;
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (nt + 31) / 32; ++w) tot += red[w];
+    sh_piv = 1e-13 * tot;
+  }
+  __syncthreads();
+  const double shift = sh_piv;
+  __syncthreads();
+  for (int j = 0; j < s; ++j) {
+    if (t == 0) {
+      const double dj = C[(int64_t)j * s + j] + shift;
+      if (!(dj > 0.0)) *flag = 1;
+      sh_piv = sqrt(dj > 0.0 ? dj : 1.0);
+      C[(int64_t)j * s + j] = sh_piv;
+    }
+    __syncthreads();
+    const double piv = sh_piv;
+    for (int i = j + 1 + t; i < s; i += nt) C[(int64_t)i * s + j] /= piv;
+    __syncthreads();
+    // trailing update of the lower triangle: C[i][k] -= L[i][j] L[k][j], j < k <= i
+    const int m = s - j - 1;
+    for (int64_t idx = t; idx < (int64_t)m * m; idx += nt) {
+      const int i = j + 1 + (int)(idx / m), k = j + 1 + (int)(idx % m);
+      if (k <= i) C[(int64_t)i * s + k] -= C[(int64_t)i * s + j] * C[(int64_t)k * s + j];
+    }
+    __syncthreads();
+  }
+  // columns of L^{-1} by forward substitution, one column per thread
+  for (int c = t; c < s; c += nt) {
+    for (int i = 0; i < s; ++i) {
+      double x = 0.0;
+      if (i >= c) {
+        x = (i == c) ? 1.0 : 0.0;
+        for (int j = c; j < i; ++j) x -= C[(int64_t)i * s + j] * Linv[(int64_t)j * s + c];
+        x /= C[(int64_t)i * s + i];
+      }
+      Linv[(int64_t)i * s + c] = x;
+      Tinv[(int64_t)i * s + c] = (float)x;
+    }
+  }
+}
+
+// acc[0] (+)= scale * sum_{i<s} sum_j A[i][j] * Bm[i][j]   (float64 two-stage; the trace terms tr(Q^T X Q), tr(G_perp X G_perp^T))
+__global__ void __launch_bounds__(VT) rowdot_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
+                                                            int64_t ldb, int s, int64_t n, double* __restrict__ part) {
+  __shared__ double sm[VT / 32];
+  double acc = 0.0;
+  const int64_t total = (int64_t)s * n;
+  for (int64_t idx = blockIdx.x * (int64_t)VT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * VT) {
+    const int64_t i = idx / n, j = idx - i * n;
+    acc += (double)A[i * lda + j] * (double)Bm[i * ldb + j];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < VT / 32; ++w) t += sm[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void rowdot_finish_kernel(const double* __restrict__ part, int np, double scale, double* __restrict__ acc, int accumulate,
+                                     float* __restrict__ outf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double t = 0.0;
+  for (int i = 0; i < np; ++i) t += part[i];
+  const double v = (accumulate ? acc[0] : 0.0) + scale * t;
+  acc[0] = v;
+  if (outf) outf[0] = (float)v;
+}
+
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
@@ -778,6 +907,120 @@ int gkl_run(Op& o, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* U
   return LIP_OK;
 }
 
+
+// ---- Hutch++ v2 --------------------------------------------------------------------------------------------------------------------
+int launch_gram(const float* A, int64_t lda, int sa, const float* Bm, int64_t ldb, int sb, int64_t n, double* part, double* out,
+                float* outf, cudaStream_t st) {
+  const int tiles = (int)(ceil_div(sa, GT) * ceil_div(sb, GT));
+  int nsplit = (int)std::min<int64_t>(64, std::max<int64_t>(1, (3 * 148) / tiles));
+  int64_t cols = ceil_div(ceil_div(n, nsplit), GC) * GC;
+  nsplit = (int)ceil_div(n, cols);
+  dim3 grid((unsigned)tiles, (unsigned)nsplit);
+  gram_partial_kernel<<<grid, GT * GT, 0, st>>>(A, lda, sa, Bm, ldb, sb, n, cols, part);
+  LIP_LAUNCH_CHECK();
+  const int64_t count = (int64_t)sa * sb;
+  gram_finish_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(part, nsplit, count, out, outf);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+int launch_rowdot(const float* A, int64_t lda, const float* Bm, int64_t ldb, int s, int64_t n, double scale, double* part, double* acc,
+                  int accumulate, float* outf, cudaStream_t st) {
+  const int np = 4 * 148;
+  rowdot_partial_kernel<<<np, VT, 0, st>>>(A, lda, Bm, ldb, s, n, part);
+  LIP_LAUNCH_CHECK();
+  rowdot_finish_kernel<<<1, 32, 0, st>>>(part, np, scale, acc, accumulate, outf);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+// Out[so, n] = T[so, si] * In[si, n]  (+ add_scale * Add)   through the fp32 SIMT GEMM
+int small_times_tall(const float* T, int so, int si, const float* In, int64_t ldi, float* Out, int64_t ldo, int64_t n, float scale,
+                     const float* Add, float add_scale, cudaStream_t st) {
+  GemmProblem g;
+  g.M = so; g.N = n; g.K = si; g.batch = 1;
+  g.A1.ptr = T; g.A1.s0 = si; g.A1.s1 = 1;
+  g.B1.ptr = In; g.B1.s0 = ldi; g.B1.s1 = 1;
+  g.C = Out; g.c_sm = ldo;
+  g.epi.scale = scale;
+  if (Add) { g.epi.add = Add; g.epi.add_scale = add_scale; }
+  return gemm_simt(g, st);
+}
+
+size_t hutchpp_ws_bytes(const Op& o, int64_t s1, int64_t s2) {
+  const int64_t n = o.n_in, ld = pad4(n), sm = std::max(s1, s2);
+  return op_ws_bytes(o, sm) + 3 * rsz((size_t)s1 * ld, 4) + 2 * rsz((size_t)s2 * ld, 4) + rsz((size_t)64 * sm * sm, 8) +
+         3 * rsz((size_t)sm * sm, 8) + rsz((size_t)4 * 148, 8) + 16384;
+}
+
+int hutchpp_run(Op& o, const float* probes, int64_t ldp, int64_t s1, int64_t s2, float* out, int32_t* info, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+  const int64_t n = o.n_in;
+  LIP_REQUIRE(o.symmetric || o.n_in == o.n_out, "hutchpp: the operator must be square");
+  LIP_REQUIRE(o.op->kind != LIP_LINOP_GKL, "hutchpp: the GKL operator is rectangular");
+  LIP_REQUIRE(s1 >= 1 && s2 >= 1 && s1 <= 1024 && s1 <= n, "hutchpp: need 1 <= s1 <= min(n, 1024) and s2 >= 1 (s1=%lld, s2=%lld)",
+              (long long)s1, (long long)s2);
+  const int64_t sm = std::max(s1, s2), ld = pad4(n);
+  Bump bp(ws, ws_bytes);
+  op_carve(o, bp, sm);
+  float* Y = bp.take<float>((size_t)s1 * ld);        // X S^T, then scratch of the QR ping-pong
+  float* Q = bp.take<float>((size_t)s1 * ld);
+  float* XQ = bp.take<float>((size_t)s1 * ld);
+  float* Gp = bp.take<float>((size_t)s2 * ld);
+  float* XG = bp.take<float>((size_t)s2 * ld);
+  double* gpart = bp.take<double>((size_t)64 * sm * sm);
+  double* C = bp.take<double>((size_t)sm * sm);
+  double* Linv = bp.take<double>((size_t)sm * sm);
+  float* Tm = (float*)bp.take<double>((size_t)sm * sm);
+  double* dpart = bp.take<double>((size_t)4 * 148);
+  double* acc = bp.take<double>(2);
+  int* flag = bp.take<int>(4);
+  if (!bp.ok) { set_error("hutchpp: workspace too small (%zu bytes given, %zu needed)", ws_bytes, hutchpp_ws_bytes(o, s1, s2)); return LIP_ERR_WORKSPACE; }
+  LIP_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 4, st));
+  const float* S = probes;
+  const float* G = probes + s1 * ldp;
+  int rc;
+  // rows must be contiguous [s, n] for the operator; probes with ldp != n are compacted into Q first
+  const float* Sin = S;
+  if (ldp != n) {
+    LIP_CHECK_CUDA(cudaMemcpy2DAsync(Q, sizeof(float) * n, S, sizeof(float) * ldp, sizeof(float) * n, (size_t)s1, cudaMemcpyDeviceToDevice, st));
+    Sin = Q;
+  }
+  // Y = X S^T  (stochtrace.py:121-122)
+  float* Yc = XQ;                                     // contiguous [s1, n] result, re-laid with ld below when n % 4 != 0
+  rc = op_apply(o, Sin, Yc, s1, 0, st); if (rc) return rc;
+  // Q = qr(Y).Q (stochtrace.py:123) by shifted CholeskyQR, three passes: Gram in float64, Cholesky + triangular inverse in one CTA,
+  // Q <- L^{-1} Y with the SIMT GEMM.  Any orthonormal basis of span(Y) gives the same estimate (tr(Q^T X Q) and the deflation
+  // depend on the span only).
+  const float* src = Yc; int64_t lds = n;
+  float* bufs[2] = {Y, Q};
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = bufs[pass & 1];
+    rc = launch_gram(src, lds, (int)s1, src, lds, (int)s1, n, gpart, C, nullptr, st); if (rc) return rc;
+    chol_inv_kernel<<<1, 1024, 0, st>>>(C, (int)s1, Tm, Linv, flag);
+    LIP_LAUNCH_CHECK();
+    rc = small_times_tall(Tm, (int)s1, (int)s1, src, lds, dst, n, n, 1.f, nullptr, 0.f, st); if (rc) return rc;
+    src = dst; lds = n;
+  }
+  const float* Qf = src;                              // [s1, n] contiguous orthonormal rows (= bufs[0] = Y's storage)
+  // tr(Q^T X Q)  (stochtrace.py:126-127)
+  rc = op_apply(o, Qf, XQ, s1, 0, st); if (rc) return rc;
+  rc = launch_rowdot(XQ, n, Qf, n, (int)s1, n, 1.0, dpart, acc, 0, nullptr, st); if (rc) return rc;
+  // G_perp = G - (G Q) Q^T  (stochtrace.py:130-131): P = G Q^T-coefficients [s2, s1] in float64, then one GEMM with the -P Q + G epilogue
+  const float* Gin = G;
+  if (ldp != n) {
+    LIP_CHECK_CUDA(cudaMemcpy2DAsync(XG, sizeof(float) * n, G, sizeof(float) * ldp, sizeof(float) * n, (size_t)s2, cudaMemcpyDeviceToDevice, st));
+    Gin = XG;
+  }
+  rc = launch_gram(Gin, n, (int)s2, Qf, n, (int)s1, n, gpart, nullptr, Tm, st); if (rc) return rc;
+  rc = small_times_tall(Tm, (int)s2, (int)s1, Qf, n, Gp, n, n, -1.f, Gin, 1.f, st); if (rc) return rc;
+  // tr(G_perp X G_perp^T) / s2  (stochtrace.py:132-134)
+  rc = op_apply(o, Gp, XG, s2, 0, st); if (rc) return rc;
+  rc = launch_rowdot(Gp, n, XG, n, (int)s2, n, 1.0 / (double)s2, dpart, acc, 1, out, st); if (rc) return rc;
+  if (info) LIP_CHECK_CUDA(cudaMemcpyAsync(info, flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return LIP_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -795,6 +1038,7 @@ size_t lip_krylov_workspace_bytes(const lip_linop* op, int32_t routine, int64_t 
     case LIP_KRYLOV_SLQ_GKL:
       return gkl_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + rsz((size_t)B * k * pad4(nr), 4) + tri + 4096;
     case LIP_KRYLOV_FUNM: return lanczos_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + tri + rsz((size_t)B * pad4(nc), 4) + 4096;
+    case LIP_KRYLOV_HUTCHPP: return hutchpp_ws_bytes(o, k, B);
     case LIP_KRYLOV_APPLY: return op_ws_bytes(o, B) + rsz((size_t)B * (nr > nc ? nr : nc), 4) + 4096;
     case LIP_KRYLOV_CG:
       return op_ws_bytes(o, B) + 3 * rsz((size_t)B * nc, 4) + 4 * rsz((size_t)B, 4) + align_up(lip_dot_scratch_bytes(nc, B), 256) + 4096;
@@ -895,7 +1139,7 @@ int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, in
 }
 
 int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv_in, int64_t k, int64_t B, int32_t fn, float clip_min,
-                     float* out, int64_t ldo, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
+                     const float* fn_params, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
   Op o;
   int rc = op_init(o, op);
   if (rc) return rc;
@@ -917,7 +1161,7 @@ int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv_in, int64_
   }
   rc = lanczos_run(o, v, ldv_in, k, B, 2, Q, ldq, td, to, nrm, bp.p, (size_t)(bp.end - bp.p), st);
   if (rc) return rc;
-  rc = lip_tridiag_funm(td, to, k, B, fn, clip_min, nullptr, fe1, nullptr, tsc, st);
+  rc = lip_tridiag_funm_p(td, to, k, B, fn, clip_min, fn_params, nullptr, fe1, nullptr, tsc, st);
   if (rc) return rc;
   rowscale_kernel<<<(unsigned)ceil_div(B * k, 256), 256, 0, st>>>(fe1, k, nrm, (int)k, (int)B);      // |v| f(T) e1
   LIP_LAUNCH_CHECK();
@@ -926,6 +1170,15 @@ int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv_in, int64_
   LIP_CHECK_CUDA(cudaMemcpy2DAsync(out, sizeof(float) * ldo, tmp, sizeof(float) * ldq, sizeof(float) * n, (size_t)B,
                                    cudaMemcpyDeviceToDevice, st));
   return LIP_OK;
+}
+
+int lip_hutchpp_v2(const lip_linop* op, const float* probes, int64_t ldp, int64_t s1, int64_t s2, float* out, int32_t* info,
+                   void* workspace, size_t workspace_bytes, lip_stream_t stream) {
+  Op o;
+  int rc = op_init(o, op);
+  if (rc) return rc;
+  LIP_REQUIRE(probes && out && workspace && ldp >= o.n_in, "lip_hutchpp_v2: bad argument");
+  return hutchpp_run(o, probes, ldp, s1, s2, out, info, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int lip_cg_solve(const lip_linop* op, const float* b, float* x, int64_t B, float tol, float atol, int64_t maxiter,

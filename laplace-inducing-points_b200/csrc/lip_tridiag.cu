@@ -26,11 +26,24 @@ __device__ __forceinline__ double apply_fn(int fn, double x) {
   }
 }
 
+// fn 4 (LIP_FN_SAMPLER): the posterior sampler's matrix function of the Gram G = W^T W, evaluated on the Ritz values th of
+// alpha I + beta G (the operator src/sample.py:120-125 hands to Lanczos):
+//     psi(th) = ( clip(th, clip_min)^{-1/2} - alpha^{-1/2} ) / lam,   lam = (th - alpha) / beta   (the Ritz value of G),
+// and psi = 0 where lam <= tau * lam_max (the pseudo-inverse of the rank-deficient Gram: fp32 cannot tell those directions from
+// null(W)).  With y = W^T v it gives  A^{-1/2} v = alpha^{-1/2} v + W psi(G) y  — the formula of src/sample.py:117-143
+// (Higham et al., thm 1.2) with both singular solves (G^+ applied to f(..) y and to y) folded into the matrix function.
+__device__ __forceinline__ double sampler_fn(double th, double th_max, float clip_min, double alpha, double beta, double tau) {
+  const double lam = (th - alpha) / beta, lam_max = (th_max - alpha) / beta;
+  if (!(lam > tau * lam_max)) return 0.0;
+  const double c = (clip_min >= 0.f && th < (double)clip_min) ? (double)clip_min : th;
+  return (1.0 / sqrt(c) - 1.0 / sqrt(alpha)) / lam;
+}
+
 // scratch per problem (doubles): d[n] e[n] cs[n] sn[n] Zt[nrows*n]
 __global__ void tridiag_funm_kernel(const float* __restrict__ diag, const float* __restrict__ off, int n, int fn,
-                                    float clip_min, float* __restrict__ quad_out, float* __restrict__ fe1_out,
-                                    float* __restrict__ eig_out, double* __restrict__ scratch, int nrows,
-                                    int use_smem) {
+                                    float clip_min, float p0, float p1, float p2, float* __restrict__ quad_out,
+                                    float* __restrict__ fe1_out, float* __restrict__ eig_out, double* __restrict__ scratch,
+                                    int nrows, int use_smem) {
   extern __shared__ double smd[];
   const int b = blockIdx.x;
   const size_t per = (size_t)4 * n + (size_t)nrows * n;
@@ -122,12 +135,27 @@ __global__ void tridiag_funm_kernel(const float* __restrict__ diag, const float*
   }
   __syncthreads();
   const bool fail = sh_fail != 0;
+  __shared__ double sh_max;
+  if (fn == 4) {
+    if (threadIdx.x == 0) {
+      double mx = d[0];
+      for (int m2 = 1; m2 < n; ++m2) mx = fmax(mx, d[m2]);
+      sh_max = mx;
+    }
+    __syncthreads();
+  }
   // g[m] = f(clip(lambda_m)) * Z[0][m]  (stored in cs);  quad = sum_m g[m] * Z[0][m]
   for (int m2 = threadIdx.x; m2 < n; m2 += blockDim.x) {
     double lam = d[m2];
     if (eig_out) eig_out[(size_t)b * n + m2] = fail ? nanf("") : (float)lam;
-    if (clip_min >= 0.f && lam < (double)clip_min) lam = (double)clip_min;
-    cs[m2] = apply_fn(fn, lam) * Zt[(size_t)m2 * nrows + 0];
+    double fv;
+    if (fn == 4) {
+      fv = sampler_fn(lam, sh_max, clip_min, (double)p0, (double)p1, (double)p2);
+    } else {
+      if (clip_min >= 0.f && lam < (double)clip_min) lam = (double)clip_min;
+      fv = apply_fn(fn, lam);
+    }
+    cs[m2] = fv * Zt[(size_t)m2 * nrows + 0];
   }
   __syncthreads();
   if (quad_out && threadIdx.x == 0) {
@@ -166,8 +194,17 @@ size_t lip_tridiag_scratch_bytes(int64_t k, int64_t B, int32_t want_vectors) {
 
 int lip_tridiag_funm(const float* diag, const float* off, int64_t k, int64_t B, int32_t fn, float clip_min,
                      float* quad_out, float* fe1_out, float* eig_out, void* scratch, lip_stream_t stream) {
-  LIP_REQUIRE(diag && (off || k == 1) && scratch && k > 0 && B > 0, "lip_tridiag_funm: bad argument");
   LIP_REQUIRE(fn >= 0 && fn <= 3, "lip_tridiag_funm: unknown function %d", fn);
+  return lip_tridiag_funm_p(diag, off, k, B, fn, clip_min, nullptr, quad_out, fe1_out, eig_out, scratch, stream);
+}
+
+int lip_tridiag_funm_p(const float* diag, const float* off, int64_t k, int64_t B, int32_t fn, float clip_min, const float* params,
+                       float* quad_out, float* fe1_out, float* eig_out, void* scratch, lip_stream_t stream) {
+  LIP_REQUIRE(diag && (off || k == 1) && scratch && k > 0 && B > 0, "lip_tridiag_funm: bad argument");
+  LIP_REQUIRE(fn >= 0 && fn <= 4, "lip_tridiag_funm: unknown function %d", fn);
+  LIP_REQUIRE(fn != 4 || (params && params[0] > 0.f && params[1] > 0.f && params[2] >= 0.f),
+              "lip_tridiag_funm: LIP_FN_SAMPLER needs params = {alpha > 0, beta > 0, tau >= 0} (host array)");
+  const float p0 = params ? params[0] : 0.f, p1 = params ? params[1] : 0.f, p2 = params ? params[2] : 0.f;
   LIP_REQUIRE(quad_out || fe1_out || eig_out, "lip_tridiag_funm: no output requested");
   cudaStream_t st = (cudaStream_t)stream;
   const int n = (int)k;
@@ -183,8 +220,8 @@ int lip_tridiag_funm(const float* diag, const float* off, int64_t k, int64_t B, 
     LIP_CHECK_CUDA(cudaFuncSetAttribute(tridiag_funm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   }
   double* sc = (double*)align_up((uintptr_t)scratch, 16);
-  tridiag_funm_kernel<<<(unsigned)B, threads, use_smem ? smem : 0, st>>>(diag, off, n, fn, clip_min, quad_out, fe1_out,
-                                                                         eig_out, sc, nrows, use_smem);
+  tridiag_funm_kernel<<<(unsigned)B, threads, use_smem ? smem : 0, st>>>(diag, off, n, fn, clip_min, p0, p1, p2, quad_out,
+                                                                         fe1_out, eig_out, sc, nrows, use_smem);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
 }

@@ -21,7 +21,7 @@ from typing import Callable, Optional
 import torch
 
 from . import _cabi as cabi
-from ._runtime import _require_cuda, dev_f32, ptr, scratch, stream
+from ._runtime import _require_cuda, dev_f32, ptr, stream
 
 
 def _pad4(n: int) -> int:
@@ -273,7 +273,8 @@ decomp = SimpleNamespace(tridiag_sym=_tridiag_sym, bidiag=_bidiag)
 
 
 # ---------------------------------------------------------------------------------------------- funm
-_FN = {"log": cabi.FN_LOG, "invsqrt": cabi.FN_INVSQRT, "inv": cabi.FN_INV, "identity": cabi.FN_IDENTITY}
+_FN = {"log": cabi.FN_LOG, "invsqrt": cabi.FN_INVSQRT, "inv": cabi.FN_INV, "identity": cabi.FN_IDENTITY,
+       "sampler": cabi.FN_SAMPLER}
 
 
 class DenseFunm:
@@ -281,20 +282,23 @@ class DenseFunm:
     (lip_tridiag_funm): V f(clip(lambda, clip_min)) V^T.  clip_min=None -> matfree's own eigh;
     clip_min=1.0 -> the reference's patch (matfree_monkeypatch.py:19)."""
 
-    def __init__(self, fn: str, clip_min: Optional[float] = None):
+    def __init__(self, fn: str, clip_min: Optional[float] = None, params=None):
         if fn not in _FN:
             raise ValueError(f"unknown matrix function {fn!r}; supported {sorted(_FN)}")
         self.fn, self.clip_min = fn, clip_min
+        self.params = None if params is None else tuple(float(p) for p in params)   # "sampler": (alpha, beta, tau)
 
     def _run(self, diag, off, want_quad, want_fe1):
+        import ctypes
         L = cabi.lib()
         nb, k = diag.shape
         quad = torch.empty(nb, device=diag.device) if want_quad else None
         fe1 = torch.empty(nb, k, device=diag.device) if want_fe1 else None
-        sc, _ = scratch(L.lip_tridiag_scratch_bytes(k, nb, 1 if want_fe1 else 0))
-        cabi.check(L.lip_tridiag_funm(ptr(diag), ptr(off), k, nb, _FN[self.fn],
-                                      -1.0 if self.clip_min is None else float(self.clip_min),
-                                      ptr(quad), ptr(fe1), None, sc, stream()), "lip_tridiag_funm")
+        sc = torch.empty(L.lip_tridiag_scratch_bytes(k, nb, 1 if want_fe1 else 0), dtype=torch.uint8, device=diag.device)
+        par = (ctypes.c_float * 3)(*self.params) if self.params is not None else None
+        cabi.check(L.lip_tridiag_funm_p(ptr(diag), ptr(off), k, nb, _FN[self.fn],
+                                        -1.0 if self.clip_min is None else float(self.clip_min), par,
+                                        ptr(quad), ptr(fe1), None, ptr(sc), stream()), "lip_tridiag_funm")
         return quad, fe1
 
     def quad_e1(self, diag, off):

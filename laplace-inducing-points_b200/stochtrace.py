@@ -124,17 +124,30 @@ def apply_X(Xfun, Mx):
 
 
 def hutchpp_v2(Xfun, sampler, *, s1, s2):
-    """stochtrace.py:118-135"""
+    """stochtrace.py:118-135: tr(Q^T X Q) + tr(G_perp X G_perp^T)/s2 with Q = orth(X S^T), G_perp = G - (G Q) Q^T.
+    One native call (lip_hutchpp_v2): the [n, s1] QR is a three-pass shifted CholeskyQR on the library's own kernels (float64
+    tall-skinny Gram, one-CTA Cholesky, GEMM apply) and the deflation one GEMM; Xfun runs natively when it is one of this package's
+    closures, else through the mat-vec callback (2 s1 + s2 products in three batched calls)."""
+    from . import _cabi as cabi
+    from ._runtime import ptr, stream
+    from .matfree import _NativeOp
     e = dev_f32(sampler(...))
-    S, G = e[:s1], e[s1:]
-    Y = apply_X(Xfun, S)                                  # (n, s1)
-    Q, _ = torch.linalg.qr(Y, mode="reduced")
-    XQ = apply_X(Xfun, Q.T)
-    low_rank = (XQ * Q).sum()                             # tr(Q^T X Q)
-    G_perp = G - (G @ Q) @ Q.T
-    XGp = apply_X(Xfun, G_perp)
-    resid = (G_perp.T * XGp).sum() / s2                   # tr(G_perp X G_perp^T)
-    return low_rank + resid
+    if e.dim() != 2 or e.shape[0] < s1 + s2:
+        raise ValueError(f"hutchpp_v2: the sampler returned {tuple(e.shape)}, need at least s1 + s2 = {s1 + s2} probe rows")
+    e = e[:s1 + s2].contiguous()
+    n = e.shape[1]
+    sm = max(int(s1), int(s2))
+    op = _NativeOp(Xfun, None, sm, n, n, False, symmetric=True)
+    out = torch.empty(1, device=e.device)
+    info = torch.zeros(1, device=e.device, dtype=torch.int32)
+    L = cabi.lib()
+    need = L.lip_krylov_workspace_bytes(op.ref(), cabi.KRYLOV_HUTCHPP, int(s1), int(s2))
+    if need == 0:
+        raise ValueError("lip_hutchpp_v2: " + L.lip_last_error().decode("utf-8", "replace"))
+    ws = torch.empty(need, dtype=torch.uint8, device=e.device)
+    rc = L.lip_hutchpp_v2(op.ref(), ptr(e), n, int(s1), int(s2), ptr(out), ptr(info), ptr(ws), need, stream())
+    op.check(rc, "lip_hutchpp_v2")
+    return out[0]
 
 
 def _cg_matrix(Xfun):

@@ -117,6 +117,16 @@ def case_c3a(out):
     out["c3a_dense_invsqrt_true"] = (ce * g_true) @ V.T
     out["c3a_dense_invsqrt_clip"] = (ce * g_clip) @ V.T
     out["c3a_rank"] = np.array(int(rng_dirs.sum()))
+    # the same with the pseudo-inverse cut an fp32 implementation has to use (directions below 1e-6 lambda_max count as null(W));
+    # for alpha < 1 the clipped formula is DISCONTINUOUS at that cut (1 on range(W), alpha^{-1/2} on the complement), so which side
+    # a marginal direction falls on changes the result at the 1e-2 level — no fp32 method can be pinned tighter than that there
+    rng6 = lam > 1e-6 * lam.max()
+    g_clip6 = np.where(rng6, 1.0 / np.sqrt(np.clip(a2, 1.0, None)), 1.0 / math.sqrt(alpha))
+    out["c3a_dense_invsqrt_clip_tau1e-6"] = (ce * g_clip6) @ V.T
+    out["c3a_rank_tau1e-6"] = np.array(int(rng6.sum()))
+    # alpha = 1: the clip is inactive (alpha + beta lam >= 1), the reference's formula IS A^{-1/2} and is continuous in lam
+    a3 = 1.0 + beta * lam
+    out["c3a_dense_invsqrt_alpha1"] = (ce / np.sqrt(a3)) @ V.T
     print(f"[c3a] D={D} rank={int(rng_dirs.sum())} logdet={out['c3a_dense_logdet_gkl']:.6f} ({time.time() - t0:.1f} s)", flush=True)
 
 
@@ -165,9 +175,11 @@ CASES = {"c3a": case_c3a, "c3b_slq": case_c3b_slq, "c3b_hpp": case_c3b_hpp, "res
 
 def main():
     want = sys.argv[1:] or list(CASES)
-    out = dict(np.load(OUT)) if os.path.exists(OUT) else {}
     for name in want:
-        CASES[name](out)
+        new = {}
+        CASES[name](new)
+        out = dict(np.load(OUT)) if os.path.exists(OUT) else {}       # merge with whatever is on disk NOW (cases may run concurrently)
+        out.update(new)
         np.savez_compressed(OUT, **out)
     print("wrote", OUT, sorted(out))
 
