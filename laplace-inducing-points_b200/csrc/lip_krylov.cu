@@ -77,6 +77,25 @@ __device__ __forceinline__ float sum_fixed(const volatile float* part, int np, f
 
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// CTAs per column of the projection kernel: every CTA gets the same number q of RCHUNK sub-chunks (balanced), about 4 x 148 CTAs
+// over all columns; fewer, fatter CTAs also keep the last-block coefficient sum short
+inline int project_ctas(int64_t n, int64_t B) {
+  const int64_t nsub = (n + 2047) / 2048;
+  int64_t target = (4 * 148 + B - 1) / B;
+  if (target < 8) target = 8;
+  if (target > 512) target = 512;
+  const int64_t q = (nsub + target - 1) / target;
+  const int64_t np = (nsub + q - 1) / q;
+  return (int)(np < 1 ? 1 : np);
+}
+
+inline int project_ctas_max(int64_t B) {      // upper bound of project_ctas over all n
+  int64_t target = (4 * 148 + B - 1) / B;
+  if (target < 8) target = 8;
+  if (target > 512) target = 512;
+  return (int)target;
+}
+
 inline int column_ctas(int64_t n, int64_t B, int per_cta) {
   int64_t want = ceil_div(4 * 148, B);
   if (want < 4) want = 4;
@@ -196,22 +215,34 @@ __global__ void __launch_bounds__(VT) project_kernel(ProjectArgs a) {
   float* pb = a.part + ((int64_t)b * np + cta) * a.kpad;
   for (int j = threadIdx.x; j < kk; j += VT) pb[j] = acc[j];
   if (!last_block(a.counter + b, np)) return;
-  // fixed-order sum over the np CTAs: 32 coefficients x 8 CTA lanes per pass, 8 tiles (256 coefficients) per outer pass
-  const volatile float* P = a.part + (int64_t)b * np * a.kpad;
+  // fixed-order sum over the np CTAs: thread (tx, ty) adds the partials of coefficient j = j0 + 32 t + tx over CTAs c = ty, ty + 8, ...
+  // (4 CTAs x 4 tiles = 16 independent L2 loads in flight per thread), then the 8 lanes are added in lane order
+  const float* P = a.part + (int64_t)b * np * a.kpad;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int j0 = 0; j0 < kk; j0 += 256) {
-    float s[8];
+  for (int j0 = 0; j0 < kk; j0 += 128) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    int c = ty;
+    for (; c + 24 < np; c += 32) {
+      float v[4][4];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) s[t] = 0.f;
-    for (int c = ty; c < np; c += 8) {
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+        for (int t = 0; t < 4; ++t) {
+          const int j = j0 + t * 32 + tx;
+          v[u][t] = (j < kk) ? __ldcg(P + (int64_t)(c + 8 * u) * a.kpad + j) : 0.f;
+        }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s[t] += (v[0][t] + v[1][t]) + (v[2][t] + v[3][t]);
+    }
+    for (; c < np; c += 8) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
         const int j = j0 + t * 32 + tx;
-        if (j < kk) s[t] += P[(int64_t)c * a.kpad + j];
+        if (j < kk) s[t] += __ldcg(P + (int64_t)c * a.kpad + j);
       }
     }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < 4; ++t) {
       red[ty][tx] = s[t];
       __syncthreads();
       if (ty == 0) {
@@ -539,6 +570,10 @@ __global__ void __launch_bounds__(VT) rowdot_partial_kernel(const float* __restr
     part[blockIdx.x] = t;
   }
 }
+__global__ void eye_kernel(float* __restrict__ out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n * n) out[i] = (i / n == i % n) ? 1.f : 0.f;
+}
 __global__ void rowdot_finish_kernel(const double* __restrict__ part, int np, double scale, double* __restrict__ acc, int accumulate,
                                      float* __restrict__ outf) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -689,7 +724,7 @@ int launch_project(const float* Q, int64_t ldq, int64_t qsb, int kk, const float
                    const Red& r, cudaStream_t st) {
   if (kk <= 0) return LIP_OK;
   ProjectArgs a{Q, ldq, qsb, kk, w, ldw, r.ppart, r.kpad, r.h, r.counter, n};
-  const int np = column_ctas(n, B, RCHUNK);
+  const int np = project_ctas(n, B);
   dim3 grid(np, (unsigned)B);
   project_kernel<<<grid, VT, sizeof(float) * (RCHUNK + (size_t)kk), st>>>(a);
   LIP_LAUNCH_CHECK();
@@ -728,13 +763,13 @@ int set_kernel_limits(int64_t k) {
 
 size_t red_bytes(int64_t n, int64_t B, int64_t k) {
   const int64_t kpad = pad4(k);
-  const int np = column_ctas(n, B, RCHUNK);
+  const int np = project_ctas_max(B);
   return rsz((size_t)B * MAXP, 4) + rsz((size_t)B, 4) + rsz((size_t)B * np * kpad, 4) + rsz((size_t)B * kpad, 4);
 }
 
 int red_carve(Red& r, Bump& bp, int64_t n, int64_t B, int64_t k, cudaStream_t st) {
   r.kpad = pad4(k);
-  const int np = column_ctas(n, B, RCHUNK);
+  const int np = project_ctas_max(B);
   r.part = bp.take<float>((size_t)B * MAXP);
   r.counter = bp.take<unsigned>((size_t)B);
   r.ppart = bp.take<float>((size_t)B * np * r.kpad);
@@ -948,7 +983,9 @@ int small_times_tall(const float* T, int so, int si, const float* In, int64_t ld
 }
 
 size_t hutchpp_ws_bytes(const Op& o, int64_t s1, int64_t s2) {
-  const int64_t n = o.n_in, ld = pad4(n), sm = std::max(s1, s2);
+  const int64_t n = o.n_in, ld = pad4(n);
+  if (s1 > n) s1 = n;
+  const int64_t sm = std::max(s1, s2);
   return op_ws_bytes(o, sm) + 3 * rsz((size_t)s1 * ld, 4) + 2 * rsz((size_t)s2 * ld, 4) + rsz((size_t)64 * sm * sm, 8) +
          3 * rsz((size_t)sm * sm, 8) + rsz((size_t)4 * 148, 8) + 16384;
 }
@@ -958,8 +995,10 @@ int hutchpp_run(Op& o, const float* probes, int64_t ldp, int64_t s1, int64_t s2,
   const int64_t n = o.n_in;
   LIP_REQUIRE(o.symmetric || o.n_in == o.n_out, "hutchpp: the operator must be square");
   LIP_REQUIRE(o.op->kind != LIP_LINOP_GKL, "hutchpp: the GKL operator is rectangular");
-  LIP_REQUIRE(s1 >= 1 && s2 >= 1 && s1 <= 1024 && s1 <= n, "hutchpp: need 1 <= s1 <= min(n, 1024) and s2 >= 1 (s1=%lld, s2=%lld)",
-              (long long)s1, (long long)s2);
+  LIP_REQUIRE(s1 >= 1 && s2 >= 1, "hutchpp: need s1 >= 1 and s2 >= 1 (s1=%lld, s2=%lld)", (long long)s1, (long long)s2);
+  const bool full = s1 >= n;     // jnp.linalg.qr(reduced) of an [n, s1 >= n] block spans R^n: Q = I is that basis and the estimate is
+  if (full) s1 = n;              // tr(X) exactly (stochtrace.py:118-135, tests/test_stochtrace.py:90-97), G_perp = 0
+  LIP_REQUIRE(full || s1 <= 1024, "hutchpp: s1 = %lld exceeds 1024 (one-CTA Cholesky of the s1 x s1 Gram)", (long long)s1);
   const int64_t sm = std::max(s1, s2), ld = pad4(n);
   Bump bp(ws, ws_bytes);
   op_carve(o, bp, sm);
@@ -977,6 +1016,14 @@ int hutchpp_run(Op& o, const float* probes, int64_t ldp, int64_t s1, int64_t s2,
   int* flag = bp.take<int>(4);
   if (!bp.ok) { set_error("hutchpp: workspace too small (%zu bytes given, %zu needed)", ws_bytes, hutchpp_ws_bytes(o, s1, s2)); return LIP_ERR_WORKSPACE; }
   LIP_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 4, st));
+  if (full) {
+    eye_kernel<<<(unsigned)ceil_div(n * n, 256), 256, 0, st>>>(Q, n);
+    LIP_LAUNCH_CHECK();
+    int rcf = op_apply(o, Q, XQ, n, 0, st); if (rcf) return rcf;
+    rcf = launch_rowdot(XQ, n, Q, n, (int)n, n, 1.0, dpart, acc, 0, out, st); if (rcf) return rcf;
+    if (info) LIP_CHECK_CUDA(cudaMemcpyAsync(info, flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return LIP_OK;
+  }
   const float* S = probes;
   const float* G = probes + s1 * ldp;
   int rc;

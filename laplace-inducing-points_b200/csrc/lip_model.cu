@@ -92,6 +92,57 @@ __global__ void bias_grad_kernel(const float* __restrict__ Delta, const float* _
   out[(int64_t)b * out_sz + j] = v;
 }
 
+// The same for SMALL batches (Krylov recurrences push 1 - 8 probes): the one-thread-per-column kernel above is a serial chain of M
+// strided loads per thread on a grid of a few CTAs (measured 67 us for M = 512 at B = 1).  Here a 32 x 32 block gives each column
+// 32 row lanes (rows m = ty, ty + 32, ...: 16 loads per thread at M = 512) and adds the lanes in a fixed order.
+__global__ void __launch_bounds__(1024) bias_grad_rows_kernel(const float* __restrict__ Delta, const float* __restrict__ Delta_lo,
+                                                              int64_t M, int n, int64_t ld, float* __restrict__ out, int64_t out_sz,
+                                                              float scale, const float* __restrict__ add, int64_t add_sz,
+                                                              float add_scale) {
+  __shared__ float sm[32][33];
+  const int b = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (j < n) {
+    const float* d = Delta + (int64_t)b * M * ld + j;
+    int64_t m = ty;
+    for (; m + 96 < M; m += 128) {
+      const float a0 = d[m * ld], a1 = d[(m + 32) * ld], a2 = d[(m + 64) * ld], a3 = d[(m + 96) * ld];
+      acc += (a0 + a1) + (a2 + a3);
+    }
+    for (; m < M; m += 32) acc += d[m * ld];
+    if (Delta_lo) {
+      const float* e = Delta_lo + (int64_t)b * M * ld + j;
+      float acc2 = 0.f;
+      for (m = ty; m < M; m += 32) acc2 += e[m * ld];
+      acc += acc2;
+    }
+  }
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) t += sm[y][tx];
+    float v = scale * t;
+    if (add) v += add_scale * add[(int64_t)b * add_sz + j];
+    out[(int64_t)b * out_sz + j] = v;
+  }
+}
+
+// picks the row-parallel variant when the column-per-thread grid would leave most SMs idle
+static inline void launch_bias_grad_any(const float* Delta, const float* Delta_lo, int64_t rows, int n, int64_t ld, int64_t bc, float* out,
+                                        int64_t out_sz, float scale, const float* add, int64_t add_sz, float add_scale,
+                                        cudaStream_t st) {
+  if (rows >= 64 && lip::ceil_div(n, 128) * bc < 4 * 148) {
+    dim3 grid((unsigned)lip::ceil_div(n, 32), (unsigned)bc);
+    bias_grad_rows_kernel<<<grid, 1024, 0, st>>>(Delta, Delta_lo, rows, n, ld, out, out_sz, scale, add, add_sz, add_scale);
+  } else {
+    dim3 grid((unsigned)lip::ceil_div(n, 128), (unsigned)bc);
+    bias_grad_kernel<<<grid, 128, 0, st>>>(Delta, Delta_lo, rows, n, ld, out, out_sz, scale, add, add_sz, add_scale);
+  }
+}
+
 // Tall-skinny contiguous case (conv stages: rows = points x pixels, n = channels, ld == n): one CTA per batch entry, the
 // thread count is a multiple of n so every thread always sees the same column of the flat [rows * n] array.
 __global__ void colsum_flat_kernel(const float* __restrict__ Delta, long long rows, int n, float* __restrict__ out,
@@ -175,10 +226,8 @@ int launch_bias_grad(const float* Delta, const float* Delta_lo, int64_t rows, in
   }
   for (int64_t b0 = 0; b0 < B; b0 += 65535) {
     const int64_t bc = B - b0 < 65535 ? B - b0 : 65535;
-    dim3 grid((unsigned)ceil_div(n, 128), (unsigned)bc);
-    bias_grad_kernel<<<grid, 128, 0, st>>>(Delta + b0 * rows * ld, Delta_lo ? Delta_lo + b0 * rows * ld : nullptr, rows, n, ld,
-                                           out + b0 * out_sz, out_sz, scale, add ? add + b0 * add_sz : nullptr, add_sz,
-                                           add_scale);
+    launch_bias_grad_any(Delta + b0 * rows * ld, Delta_lo ? Delta_lo + b0 * rows * ld : nullptr, rows, n, ld, bc,
+                         out + b0 * out_sz, out_sz, scale, add ? add + b0 * add_sz : nullptr, add_sz, add_scale, st);
     LIP_LAUNCH_CHECK();
   }
   return LIP_OK;
@@ -424,14 +473,14 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
       if (rc) return rc;
     }
     {  // bias gradient: column sums of Delta_l (from the producing GEMM's epilogue when it was a tcgen05 GEMM)
-      dim3 grid((unsigned)ceil_div(Ld.out, 128), (unsigned)B);
+      int rcb;
       if (cur_colsum)
-        bias_grad_kernel<<<grid, 128, 0, st>>>(w.colsum, nullptr, nslots, Ld.out, cur_ld, out + Ld.boff, m->D, scale,
-                                               add ? add + Ld.boff : nullptr, m->D, add_scale);
+        rcb = launch_bias_grad(w.colsum, nullptr, nslots, Ld.out, cur_ld, B, out + Ld.boff, m->D, scale, add ? add + Ld.boff : nullptr,
+                               m->D, add_scale, st);
       else
-        bias_grad_kernel<<<grid, 128, 0, st>>>(d_hi, d_lo, m->M, Ld.out, cur_ld, out + Ld.boff, m->D, scale,
-                                               add ? add + Ld.boff : nullptr, m->D, add_scale);
-      LIP_LAUNCH_CHECK();
+        rcb = launch_bias_grad(d_hi, d_lo, m->M, Ld.out, cur_ld, B, out + Ld.boff, m->D, scale, add ? add + Ld.boff : nullptr, m->D,
+                               add_scale, st);
+      if (rcb) return rcb;
     }
     if (l > 0) {  // Delta_{l-1} = (Delta_l W_l^T) * phi'_{l-1}
       const bool next_split = m->tc_on && m->tc_layer[l - 1];

@@ -34,9 +34,18 @@ __device__ __forceinline__ double apply_fn(int fn, double x) {
 // (Higham et al., thm 1.2) with both singular solves (G^+ applied to f(..) y and to y) folded into the matrix function.
 __device__ __forceinline__ double sampler_fn(double th, double th_max, float clip_min, double alpha, double beta, double tau) {
   const double lam = (th - alpha) / beta, lam_max = (th_max - alpha) / beta;
+  const bool clipped = clip_min >= 0.f && alpha < (double)clip_min && th < (double)clip_min;
+  if (!clipped) {
+    // ((alpha + beta lam)^{-1/2} - alpha^{-1/2}) / lam without the cancellation: finite and smooth through lam = 0, so the noise-level
+    // Ritz values of the rank-deficient Gram (either sign) need no cut here
+    const double t = th > 1e-30 ? th : 1e-30;
+    const double st = sqrt(t), sa = sqrt(alpha);
+    return -beta / (st * sa * (st + sa));
+  }
+  // clipped branch (alpha < clip_min): (clip_min^{-1/2} - alpha^{-1/2}) / lam is singular at lam = 0 — the reference's formula jumps
+  // from clip_min^{-1/2} on range(W) to alpha^{-1/2} on null(W); directions below the cut count as null(W)
   if (!(lam > tau * lam_max)) return 0.0;
-  const double c = (clip_min >= 0.f && th < (double)clip_min) ? (double)clip_min : th;
-  return (1.0 / sqrt(c) - 1.0 / sqrt(alpha)) / lam;
+  return (1.0 / sqrt((double)clip_min) - 1.0 / sqrt(alpha)) / lam;
 }
 
 // scratch per problem (doubles): d[n] e[n] cs[n] sn[n] Zt[nrows*n]
