@@ -317,6 +317,27 @@ typedef enum { LIP_SLQ_LANCZOS = 0, LIP_SLQ_GKL = 1 } lip_slq_form;
 int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form, int32_t fn,
                        float clip_min, float* quad_out, void* workspace, size_t workspace_bytes, lip_stream_t stream);
 
+/* ---- multi-GPU: the same recurrence with its Krylov bases sharded over the ranks of a communicator ----------------------
+ * lip_comm is a NCCL communicator the library owns (NCCL is resolved at run time from the process: no link-time dependency).  Rank 0
+ * of a group obtains 128 id bytes with lip_comm_unique_id, the caller ships them to the other ranks (torch.distributed in the Python
+ * mirror), every rank calls lip_comm_create with the CUDA device it will use current. */
+typedef struct lip_comm lip_comm;
+int lip_comm_unique_id(void* id128);
+int lip_comm_create(const void* id128, int32_t world, int32_t rank, lip_comm** out);
+int lip_comm_destroy(lip_comm* comm);
+int lip_comm_world(const lip_comm* comm);
+int lip_comm_rank(const lip_comm* comm);
+int lip_comm_allreduce_sum(lip_comm* comm, float* buf, int64_t count, lip_stream_t stream);
+/* lip_slq_quadrature with the basis rows cut column-wise over comm's ranks: rank r owns n/S columns of every Krylov vector, so the
+ * O(k^2 n) re-orthogonalisation traffic that bounds the logdet is divided by S; the operator is applied replicated on the
+ * all-gathered vector (its latency does not shrink with the batch); norms and re-orthogonalisation coefficients are all-reduced
+ * (B resp. B x k floats per exchange).  Every rank passes the same FULL probes and receives the same quad_out.  comm == NULL or
+ * a single rank: lip_slq_quadrature.  Model operator kinds only.  Workspace: lip_slq_workspace_bytes(op, form, k, B, world). */
+int lip_slq_quadrature_sharded(const lip_linop* op, lip_comm* comm, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form,
+                               int32_t fn, float clip_min, float* quad_out, void* workspace, size_t workspace_bytes,
+                               lip_stream_t stream);
+size_t lip_slq_workspace_bytes(const lip_linop* op, int32_t form, int64_t k, int64_t B, int32_t world);
+
 /* matfree.funm.funm_lanczos_sym: out[b,:] = |v_b| Q_b f(T_b) e1 ~= f(A) v_b   (src/sample.py:113-115: f = 1/sqrt, clip_min = 1).
  * fn_params: host array for parameterised functions (lip_tridiag_funm_p), else NULL. */
 int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv, int64_t k, int64_t B, int32_t fn, float clip_min,

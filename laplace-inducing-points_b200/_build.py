@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblip_b200.so")
-SOURCES = ["lip_api.cu", "lip_gemm_simt.cu", "lip_gemm_tc.cu", "lip_conv_tc.cu", "lip_model.cu", "lip_cnn.cu", "lip_resnet.cu", "lip_vecops.cu", "lip_krylov.cu", "lip_tridiag.cu", "lip_zgrad.cu", "lip_eval.cu"]
+SOURCES = ["lip_api.cu", "lip_gemm_simt.cu", "lip_gemm_tc.cu", "lip_conv_tc.cu", "lip_model.cu", "lip_cnn.cu", "lip_resnet.cu", "lip_vecops.cu", "lip_krylov.cu", "lip_comm.cu", "lip_tridiag.cu", "lip_zgrad.cu", "lip_eval.cu"]
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17",
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                         os.remove(obj)
                 raise RuntimeError("nvcc failed:\n" + "".join(r.stdout + r.stderr for _, r in failed))
             objs = [obj for _, obj, _ in results]
-            res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs,
+            res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-ldl"],
                                  capture_output=True, text=True)
             for obj in objs:
                 os.remove(obj)

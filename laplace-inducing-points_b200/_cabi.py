@@ -91,6 +91,14 @@ SIGNATURES = {
     "lip_lanczos_tridiag": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "lip_gkl_bidiag": (C.c_int, [_LP, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "lip_slq_quadrature": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _I32, _F, _P, _P, _SZ, _P]),
+    "lip_comm_unique_id": (C.c_int, [_P]),
+    "lip_comm_create": (C.c_int, [_P, _I32, _I32, C.POINTER(_P)]),
+    "lip_comm_destroy": (C.c_int, [_P]),
+    "lip_comm_world": (C.c_int, [_P]),
+    "lip_comm_rank": (C.c_int, [_P]),
+    "lip_comm_allreduce_sum": (C.c_int, [_P, _P, _I64, _P]),
+    "lip_slq_quadrature_sharded": (C.c_int, [_LP, _P, _P, _I64, _I64, _I64, _I32, _I32, _F, _P, _P, _SZ, _P]),
+    "lip_slq_workspace_bytes": (_SZ, [_LP, _I32, _I64, _I64, _I32]),
     "lip_funm_lanczos": (C.c_int, [_LP, _P, _I64, _I64, _I64, _I32, _F, C.POINTER(C.c_float), _P, _I64, _P, _SZ, _P]),
     "lip_hutchpp_v2": (C.c_int, [_LP, _P, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "lip_cg_solve": (C.c_int, [_LP, _P, _P, _I64, _F, _F, _I64, _I32, _P, _P, _SZ, _P]),

@@ -116,6 +116,77 @@ def zgrad_sharded(zgrad_fn: Callable, cotangents: torch.Tensor, vectors: torch.T
     return allreduce_sum_(out)
 
 
+# ---------------------------------------------------------------------------------------------- Krylov-basis (D) sharding
+def group_layout(world_size: int, num_probes: int) -> Tuple[int, int]:
+    """(P, S): P probe groups of S ranks each, P * S = world_size.  Probes are the free axis (no communication at all), so P is the
+    largest divisor of world_size that does not exceed the probe count; the S ranks of a group share every Krylov vector of the
+    group's probes column-wise (lip_slq_quadrature_sharded).  4 probes on 8 GPUs -> (4, 2); on 2 GPUs -> (2, 1)."""
+    if world_size < 1 or num_probes < 1:
+        raise ValueError(f"bad layout request: world_size={world_size} num_probes={num_probes}")
+    P = max(p for p in range(1, world_size + 1) if world_size % p == 0 and p <= num_probes)
+    return P, world_size // P
+
+
+class NativeComm:
+    """A library-owned NCCL communicator (lip_comm) over a contiguous block of ranks of the default process group."""
+
+    def __init__(self, handle, world_size, rank):
+        self.handle, self.world, self.rank = handle, world_size, rank
+
+
+_NATIVE_COMMS = {}
+
+
+def native_comms(shard_size: int) -> Optional[NativeComm]:
+    """Collective over the default group: partitions the ranks into consecutive blocks of `shard_size` and returns this rank's
+    lip_comm (None when shard_size == 1).  The leaders' NCCL unique ids travel in one all-gather of 128 bytes per rank."""
+    rank, ws = world()
+    if shard_size <= 1 or ws == 1:
+        return None
+    if ws % shard_size:
+        raise ValueError(f"native_comms: shard_size={shard_size} does not divide world_size={ws}")
+    if shard_size in _NATIVE_COMMS:
+        return _NATIVE_COMMS[shard_size]
+    import ctypes
+    from . import _cabi as cabi
+    L = cabi.lib()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    leader = rank // shard_size * shard_size
+    buf = (ctypes.c_uint8 * 128)()
+    if rank == leader:
+        cabi.check(L.lip_comm_unique_id(buf), "lip_comm_unique_id")
+    mine = torch.tensor(list(buf), dtype=torch.uint8).to(dev)
+    allids = torch.empty(ws * 128, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allids, mine)
+    idb = (ctypes.c_uint8 * 128)(*allids[leader * 128:(leader + 1) * 128].cpu().tolist())
+    h = ctypes.c_void_p()
+    cabi.check(L.lip_comm_create(idb, shard_size, rank - leader, ctypes.byref(h)), "lip_comm_create")
+    comm = NativeComm(h, shard_size, rank - leader)
+    _NATIVE_COMMS[shard_size] = comm
+    return comm
+
+
+def slq_logdet_hybrid(matvec, probes: torch.Tensor, num_matvecs: int, *, form="gkl", fn="log", clip_min=None) -> torch.Tensor:
+    """mean_b |v_b|^2 e1^T f(T_b) e1 over ALL probe rows (matfree.stochtrace.estimator of an SLQ integrand, train_inducing.py:156-163)
+    on every GPU of the job: probes first (independent recurrences), then — when there are more GPUs than probes — the Krylov
+    bases of each probe are cut column-wise over the ranks of its group.  `probes` is the full [B, n] matrix, identical on every
+    rank.  One all-reduce of a float64 accumulator ends the call."""
+    from . import matfree
+    rank, ws = world()
+    B = probes.shape[0]
+    P, S = group_layout(ws, B)
+    comm = native_comms(S)
+    g = rank // S
+    mine = probes[probe_slice(B, g, P)]
+    acc = torch.zeros(1, dtype=torch.float64, device=probes.device)
+    if mine.shape[0] > 0:
+        q = matfree.slq_quadrature(matvec, mine, num_matvecs, form=form, fn=fn, clip_min=clip_min, comm=comm)
+        if rank % S == 0:                       # every rank of a group holds the same values: the leader contributes them
+            acc += q.double().sum()
+    allreduce_sum_(acc)
+    return (acc / B).to(torch.float32)[0]
+
+
 # ---------------------------------------------------------------------------------------------- point (M) sharding
 def point_slice(num_points: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> slice:
     """Contiguous, balanced slice of the inducing points owned by `rank` (sharding over M for large

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "lip_comm.cuh"
 #include "lip_model.cuh"
 
 using namespace lip;
@@ -116,6 +117,7 @@ struct AxpyNormArgs {
   float* out; int64_t ldo;
   float* part; float* nrm; unsigned* counter;
   int64_t n;
+  int sq_out;      // 1: nrm receives the sum of squares (a rank-local partial that is all-reduced before its square root)
 };
 
 template <int VEC>
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(VT) axpy_norm_kernel(AxpyNormArgs a) {
   if (threadIdx.x == 0) a.part[(int64_t)b * np + blockIdx.x] = acc;
   if (last_block(a.counter + b, np)) {
     const float t = sum_fixed(a.part + (int64_t)b * np, np, sm);
-    if (threadIdx.x == 0) a.nrm[b] = sqrtf(t);
+    if (threadIdx.x == 0) a.nrm[b] = a.sq_out ? t : sqrtf(t);
   }
 }
 
@@ -267,6 +269,7 @@ struct SubtractArgs {
   float* out; int64_t ldo;
   float* part; float* nrm; unsigned* counter;
   int64_t n;
+  int sq_out;
 };
 
 __global__ void __launch_bounds__(VT) subtract_kernel(SubtractArgs a) {
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(VT) subtract_kernel(SubtractArgs a) {
   if (threadIdx.x == 0) a.part[(int64_t)b * np + blockIdx.x] = nacc;
   if (last_block(a.counter + b, np)) {
     const float t = sum_fixed(a.part + (int64_t)b * np, np, sm);
-    if (threadIdx.x == 0) a.nrm[b] = sqrtf(t);
+    if (threadIdx.x == 0) a.nrm[b] = a.sq_out ? t : sqrtf(t);
   }
 }
 
@@ -351,6 +354,11 @@ __global__ void __launch_bounds__(VT) scale_store_kernel(ScaleStoreArgs a) {
 }
 
 // ---- tiny bookkeeping kernels ----------------------------------------------------------------------------------------
+// x[b] = sqrt(x[b])   (after the all-reduce of rank-local sums of squares)
+__global__ void sqrt_kernel(float* x, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) x[b] = sqrtf(x[b]);
+}
 // dst[b*stride + idx] = src[b]
 __global__ void record_kernel(float* dst, int64_t stride, int64_t idx, const float* src, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -706,10 +714,11 @@ struct Red {            // reduction scratch shared by all kernels of a recurren
   float* ppart = nullptr;       // projection partials [B][np][kpad]
   float* h = nullptr;           // [B][kpad]
   int64_t kpad = 0;
+  int sq_out = 0;               // sharded recurrences: norms leave the kernels as rank-local sums of squares
 };
 
 int launch_axpy_norm(AxpyNormArgs a, int64_t B, const Red& r, cudaStream_t st) {
-  a.part = r.part; a.counter = r.counter;
+  a.part = r.part; a.counter = r.counter; a.sq_out = r.sq_out;
   const bool v4 = al16(a.x1) && (a.ld1 % 4 == 0) && (a.n1 % 4 == 0 || a.n1 >= a.n) && (!a.x2 || (al16(a.x2) && a.ld2 % 4 == 0)) &&
                   (!a.coef || (al16(a.y) && a.ldy % 4 == 0 && a.ysb % 4 == 0)) && al16(a.out) && (a.ldo % 4 == 0);
   const int np = column_ctas(a.n, B, VT * 4 * 2);
@@ -733,7 +742,7 @@ int launch_project(const float* Q, int64_t ldq, int64_t qsb, int kk, const float
 
 int launch_subtract(const float* Q, int64_t ldq, int64_t qsb, int kk, const float* w, int64_t ldw, const float* scal, float* out,
                     int64_t ldo, float* nrm, int64_t n, int64_t B, const Red& r, cudaStream_t st) {
-  SubtractArgs a{Q, ldq, qsb, kk, r.h, r.kpad, w, ldw, (!al16(w) || ldw % 4 != 0) ? 1 : 0, scal, out, ldo, r.part, nrm, r.counter, n};
+  SubtractArgs a{Q, ldq, qsb, kk, r.h, r.kpad, w, ldw, (!al16(w) || ldw % 4 != 0) ? 1 : 0, scal, out, ldo, r.part, nrm, r.counter, n, r.sq_out};
   const int np = column_ctas(n, B, VT * 4);
   dim3 grid(np, (unsigned)B);
   subtract_kernel<<<grid, VT, sizeof(float) * (size_t)(kk > 0 ? kk : 1), st>>>(a);
@@ -779,62 +788,140 @@ int red_carve(Red& r, Bump& bp, int64_t n, int64_t B, int64_t k, cudaStream_t st
   return LIP_OK;
 }
 
+// ---- D-sharding of the Krylov vectors over the ranks of a lip_comm ---------------------------------------------------------
+// Rank r of S owns columns [off, off + nloc) of every parameter-space vector (and rows [doff, doff + dloc) of the output-space part
+// of a GKL u vector).  The basis — the O(k^2 n) re-orthogonalisation traffic that bounds SLQ — is cut S ways; the operator is applied
+// REPLICATED on the all-gathered vector (the probe-batched mat-vec at B <= 4 is latency-bound, so sharding it would not shorten it).
+// Per step: one all-gather of the new Krylov vector (+ one of its small output-space part for GKL) and one all-reduce per scalar /
+// coefficient vector; all enqueued on the caller's stream between the kernels that produce and consume them.
+struct Shard {
+  lip_comm* comm = nullptr;
+  const NcclApi* api = nullptr;
+  int S = 1, rank = 0;
+  int64_t Dsh = 0, off = 0, nloc = 0;    // D partition: shard width (multiple of 4), this rank's offset and length
+  int64_t dsh = 0, doff = 0, dloc = 0;   // d partition (GKL kind)
+};
+
+int shard_init(Shard& sh, lip_comm* comm, int64_t D, int64_t d) {
+  sh.comm = comm;
+  sh.api = nccl_api();
+  if (!sh.api) return LIP_ERR_UNSUPPORTED;
+  sh.S = comm->world; sh.rank = comm->rank;
+  sh.Dsh = pad4(ceil_div(D, sh.S));
+  sh.off = sh.rank * sh.Dsh;
+  sh.nloc = std::min<int64_t>(sh.Dsh, D - sh.off);
+  LIP_REQUIRE((int64_t)(sh.S - 1) * sh.Dsh < D, "sharded Krylov: %d ranks are too many for vectors of length %lld", sh.S, (long long)D);
+  if (d > 0) {
+    sh.dsh = pad4(ceil_div(d, sh.S));
+    sh.doff = std::min<int64_t>(sh.rank * sh.dsh, d);
+    sh.dloc = std::max<int64_t>(0, std::min<int64_t>(sh.dsh, d - sh.doff));
+  }
+  return LIP_OK;
+}
+
+int shard_allreduce(const Shard* sh, float* buf, size_t count, cudaStream_t st) {
+  if (!sh) return LIP_OK;
+  LIP_CHECK_NCCL(sh->api, sh->api->AllReduce(buf, buf, count, ncclFloat, ncclSum, sh->comm->comm, st));
+  count_launch();
+  return LIP_OK;
+}
+
+// rank-local sums of squares -> global norms
+int shard_norm(const Shard* sh, float* ssq, int64_t B, cudaStream_t st) {
+  if (!sh) return LIP_OK;
+  int rc = shard_allreduce(sh, ssq, (size_t)B, st);
+  if (rc) return rc;
+  sqrt_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(ssq, (int)B);
+  LIP_LAUNCH_CHECK();
+  return LIP_OK;
+}
+
+// loc [B][cnt] (this rank's zero-padded slice of every row) -> full [B][n] contiguous on every rank, n <= S * cnt
+int shard_allgather(const Shard* sh, const float* loc, int64_t cnt, float* gath, float* full, int64_t n, int64_t B, cudaStream_t st) {
+  const int64_t wide = (int64_t)sh->S * cnt;
+  float* dst = (wide == n) ? full : gath;
+  LIP_CHECK_NCCL(sh->api, sh->api->GroupStart());
+  for (int64_t b = 0; b < B; ++b)
+    LIP_CHECK_NCCL(sh->api, sh->api->AllGather(loc + b * cnt, dst + b * wide, (size_t)cnt, ncclFloat, sh->comm->comm, st));
+  LIP_CHECK_NCCL(sh->api, sh->api->GroupEnd());
+  count_launch();
+  if (dst != full)
+    LIP_CHECK_CUDA(cudaMemcpy2DAsync(full, sizeof(float) * n, gath, sizeof(float) * wide, sizeof(float) * n, (size_t)B,
+                                     cudaMemcpyDeviceToDevice, st));
+  return LIP_OK;
+}
+
 // ---- Lanczos (matfree decomp.tridiag_sym, reortho="full") -------------------------------------------------------------
 size_t lanczos_ws_bytes(const Op& o, int64_t k, int64_t B) {
   const int64_t n = o.n_in, ld = pad4(n);
-  return op_ws_bytes(o, B) + red_bytes(n, B, k) + 2 * rsz((size_t)B * ld, 4) + 2 * rsz((size_t)B * n, 4) + 4 * rsz((size_t)B, 4) + 8192;
+  return op_ws_bytes(o, B) + red_bytes(n, B, k) + 3 * rsz((size_t)B * (ld + 64), 4) + 2 * rsz((size_t)B * n, 4) + 4 * rsz((size_t)B, 4) + 8192;
 }
 
-int lanczos_run(Op& o, const float* v0, int64_t ldv0, int64_t k, int64_t B, int passes, float* Q, int64_t ldq, float* diag,
-                float* off, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
+// sh == nullptr: the whole vectors live on this GPU.  Otherwise Q holds this rank's column slice [B, k, ldq >= nloc] and v0 is the
+// FULL start vector (identical on every rank).
+int lanczos_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, int64_t B, int passes, float* Q, int64_t ldq,
+                float* diag, float* off, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t n = o.n_in;
   LIP_REQUIRE(o.symmetric || o.n_in == o.n_out, "lanczos: the operator must be square");
   LIP_REQUIRE(o.op->kind != LIP_LINOP_GKL, "lanczos: the GKL operator is rectangular (use lip_gkl_bidiag)");
   LIP_REQUIRE(k >= 1 && k <= n, "num_matvecs=%lld exceeds the operator dimension %lld", (long long)k, (long long)n);
   LIP_REQUIRE(passes == 1 || passes == 2, "lanczos: passes must be 1 or 2");
-  LIP_REQUIRE(Q && al16(Q) && ldq % 4 == 0 && ldq >= n, "lanczos: basis must be 16-byte aligned with ldq %% 4 == 0 and ldq >= n");
+  const int64_t nl = sh ? sh->nloc : n;            // columns this rank owns
+  const int64_t c0 = sh ? sh->off : 0;             // ... starting at
+  LIP_REQUIRE(Q && al16(Q) && ldq % 4 == 0 && ldq >= nl, "lanczos: basis must be 16-byte aligned with ldq %% 4 == 0 and ldq >= n");
   int rc = set_kernel_limits(k);
   if (rc) return rc;
   Bump bp(ws, ws_bytes);
   op_carve(o, bp, B);
   Red r;
-  rc = red_carve(r, bp, n, B, k, st);
+  rc = red_carve(r, bp, nl, B, k, st);
   if (rc) return rc;
-  const int64_t ld = pad4(n);
-  float* w = bp.take<float>((size_t)B * ld);        // working vector, padded rows
-  float* qc = bp.take<float>((size_t)B * n);        // contiguous mat-vec input
-  float* wc = bp.take<float>((size_t)B * n);        // contiguous mat-vec output
+  r.sq_out = sh ? 1 : 0;
+  const int64_t ld = pad4(nl);
+  const int64_t lq = sh ? sh->Dsh : n;               // row stride of the contiguous / gather-source copy of q
+  float* w = bp.take<float>((size_t)B * ld);         // working vector (this rank's slice), padded rows
+  float* qloc = sh ? bp.take<float>((size_t)B * lq) : nullptr;             // this rank's slice of q, zero-padded to the shard width
+  float* gath = sh ? bp.take<float>((size_t)B * sh->S * sh->Dsh) : nullptr;
+  float* qc = bp.take<float>((size_t)B * n);         // contiguous FULL mat-vec input
+  float* wc = bp.take<float>((size_t)B * n);         // contiguous FULL mat-vec output
   float* len = bp.take<float>((size_t)B);
   float* nrm0 = bp.take<float>((size_t)B);
-  if (!bp.ok) { set_error("lanczos: workspace too small (%zu bytes given, %zu needed)", ws_bytes, lanczos_ws_bytes(o, k, B)); return LIP_ERR_WORKSPACE; }
+  if (!bp.ok) { set_error("lanczos: workspace too small (%zu bytes given)", ws_bytes); return LIP_ERR_WORKSPACE; }
   const int64_t qsb = k * ldq;
-  const bool pad_tail = (ld != n);
-  if (pad_tail) LIP_CHECK_CUDA(cudaMemsetAsync(w, 0, sizeof(float) * (size_t)B * ld, st));
+  if (ld != nl) LIP_CHECK_CUDA(cudaMemsetAsync(w, 0, sizeof(float) * (size_t)B * ld, st));
+  if (sh) LIP_CHECK_CUDA(cudaMemsetAsync(qloc, 0, sizeof(float) * (size_t)B * lq, st));
   // q_0 = v0 / |v0|   (the basis rows must have zero padding: they are written column-exact into zeroed memory)
   LIP_CHECK_CUDA(cudaMemsetAsync(Q, 0, sizeof(float) * (size_t)B * qsb, st));
+  float* qdst = sh ? qloc : qc;
   {
-    AxpyNormArgs a{}; a.x1 = v0; a.ld1 = ldv0; a.n1 = n; a.s1 = 1.f; a.out = w; a.ldo = ld; a.nrm = nrm0; a.n = n;
+    AxpyNormArgs a{}; a.x1 = v0 + c0; a.ld1 = ldv0; a.n1 = nl; a.s1 = 1.f; a.out = w; a.ldo = ld; a.nrm = nrm0; a.n = nl;
     rc = launch_axpy_norm(a, B, r, st); if (rc) return rc;
+    rc = shard_norm(sh, nrm0, B, st); if (rc) return rc;
     if (norm0) LIP_CHECK_CUDA(cudaMemcpyAsync(norm0, nrm0, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
-    ScaleStoreArgs s{}; s.x = w; s.ldx = ld; s.scal = nrm0; s.o1 = Q; s.ld1 = ldq; s.o1sb = qsb; s.o2 = qc; s.ld2 = n; s.n2 = n; s.n = n;
+    ScaleStoreArgs s{}; s.x = w; s.ldx = ld; s.scal = nrm0; s.o1 = Q; s.ld1 = ldq; s.o1sb = qsb; s.o2 = qdst; s.ld2 = lq; s.n2 = nl; s.n = nl;
     rc = launch_scale_store(s, B, st); if (rc) return rc;
   }
   const unsigned gB = (unsigned)ceil_div(B, 128);
   for (int64_t i = 0; i < k; ++i) {
     const int kk = (int)(i + 1);
+    if (sh) { rc = shard_allgather(sh, qloc, sh->Dsh, gath, qc, n, B, st); if (rc) return rc; }
     rc = op_apply(o, qc, wc, B, 0, st); if (rc) return rc;
+    const float* wl = wc + c0;                      // this rank's slice of A q_i (row stride n)
     // two CGS passes against Q[0..i]; the first-pass coefficients are the Arnoldi column H[:, i]
-    rc = launch_project(Q, ldq, qsb, kk, wc, n, n, B, r, st); if (rc) return rc;
+    rc = launch_project(Q, ldq, qsb, kk, wl, n, nl, B, r, st); if (rc) return rc;
+    rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
     lanczos_record_kernel<<<gB, 128, 0, st>>>(diag, off, r.h, r.kpad, len, (int)i, (int)k, (int)B);
     LIP_LAUNCH_CHECK();
-    rc = launch_subtract(Q, ldq, qsb, kk, wc, n, nullptr, w, ld, passes == 1 ? len : nullptr, n, B, r, st); if (rc) return rc;
+    rc = launch_subtract(Q, ldq, qsb, kk, wl, n, nullptr, w, ld, passes == 1 ? len : nullptr, nl, B, r, st); if (rc) return rc;
     if (passes == 2) {
-      rc = launch_project(Q, ldq, qsb, kk, w, ld, n, B, r, st); if (rc) return rc;
-      rc = launch_subtract(Q, ldq, qsb, kk, w, ld, nullptr, w, ld, len, n, B, r, st); if (rc) return rc;
+      rc = launch_project(Q, ldq, qsb, kk, w, ld, nl, B, r, st); if (rc) return rc;
+      rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
+      rc = launch_subtract(Q, ldq, qsb, kk, w, ld, nullptr, w, ld, len, nl, B, r, st); if (rc) return rc;
     }
+    rc = shard_norm(sh, len, B, st); if (rc) return rc;
     if (i + 1 < k) {
-      ScaleStoreArgs s{}; s.x = w; s.ldx = ld; s.scal = len; s.o1 = Q + (i + 1) * ldq; s.ld1 = ldq; s.o1sb = qsb; s.o2 = qc; s.ld2 = n;
-      s.n2 = n; s.n = n;
+      ScaleStoreArgs s{}; s.x = w; s.ldx = ld; s.scal = len; s.o1 = Q + (i + 1) * ldq; s.ld1 = ldq; s.o1sb = qsb; s.o2 = qdst; s.ld2 = lq;
+      s.n2 = nl; s.n = nl;
       rc = launch_scale_store(s, B, st); if (rc) return rc;
     }
   }
@@ -845,103 +932,129 @@ int lanczos_run(Op& o, const float* v0, int64_t ldv0, int64_t k, int64_t B, int 
 size_t gkl_ws_bytes(const Op& o, int64_t k, int64_t B) {
   const int64_t nc = o.n_in, nr = o.n_out, ldu = pad4(nr), ldv = pad4(nc);
   return op_ws_bytes(o, B) + red_bytes(std::max(nc, nr), B, k) + rsz((size_t)B * ldu, 4) + rsz((size_t)B * ldv, 4) +
-         2 * rsz((size_t)B * nc, 4) + 2 * rsz((size_t)B * nr, 4) + 6 * rsz((size_t)B, 4) + 4096;
+         4 * rsz((size_t)B * (nc + 64), 4) + 3 * rsz((size_t)B * (nr + 64), 4) + 6 * rsz((size_t)B, 4) + 8192;
 }
 
-int gkl_run(Op& o, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* Us, int64_t ldu, float* Vs, int64_t ldv,
+// sh == nullptr: whole vectors.  Otherwise (GKL kind only) Us / Vs hold this rank's slices: a u vector is stored as
+// [its nloc parameter-space columns | its dloc output-space rows], a v vector as its nloc columns; v0 is the FULL start vector.
+int gkl_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* Us, int64_t ldu, float* Vs, int64_t ldv,
             float* alphas, float* betas, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t nc = o.n_in, nr = o.n_out;
+  const bool gkl = o.op->kind == LIP_LINOP_GKL;
+  LIP_REQUIRE(!sh || gkl, "sharded gkl: only the LIP_LINOP_GKL operator is supported");
   LIP_REQUIRE(k >= 1 && k <= std::min(nc, nr), "num_matvecs=%lld exceeds the operator dimensions (%lld, %lld)", (long long)k,
               (long long)nr, (long long)nc);
-  LIP_REQUIRE(Us && Vs && al16(Us) && al16(Vs) && ldu % 4 == 0 && ldv % 4 == 0 && ldu >= nr && ldv >= nc,
+  const int64_t D = o.D, d = o.d;
+  const int64_t ncl = sh ? sh->nloc : nc;                   // local length of a v vector
+  const int64_t nrl = sh ? sh->nloc + sh->dloc : nr;        // local length of a u vector
+  const int64_t c0 = sh ? sh->off : 0, d0 = sh ? sh->doff : 0;
+  LIP_REQUIRE(Us && Vs && al16(Us) && al16(Vs) && ldu % 4 == 0 && ldv % 4 == 0 && ldu >= nrl && ldv >= ncl,
               "gkl: bases must be 16-byte aligned with leading dimensions that are multiples of 4");
   int rc = set_kernel_limits(k);
   if (rc) return rc;
   Bump bp(ws, ws_bytes);
   op_carve(o, bp, B);
   Red r;
-  rc = red_carve(r, bp, std::max(nc, nr), B, k, st);
+  rc = red_carve(r, bp, std::max(ncl, nrl), B, k, st);
   if (rc) return rc;
-  const bool gkl = o.op->kind == LIP_LINOP_GKL;
-  const int64_t D = o.D, d = o.d;
-  const int64_t lu = pad4(nr), lv = pad4(nc);
-  float* u = bp.take<float>((size_t)B * lu);          // working u, padded rows
-  float* v = bp.take<float>((size_t)B * lv);          // working v, padded rows
-  float* vc = bp.take<float>((size_t)B * nc);         // contiguous A input
-  float* wv = bp.take<float>((size_t)B * nc);         // contiguous A^T output
-  float* uc = bp.take<float>((size_t)B * nr);         // contiguous A^T input   (GKL kind: [B, D] part then [B, d] part)
+  r.sq_out = sh ? 1 : 0;
+  const int64_t lu = pad4(nrl), lv = pad4(ncl);
+  float* u = bp.take<float>((size_t)B * lu);          // working u (local slice), padded rows
+  float* v = bp.take<float>((size_t)B * lv);          // working v (local slice), padded rows
+  float* vc = bp.take<float>((size_t)B * nc);         // contiguous FULL A input
+  float* wv = bp.take<float>((size_t)B * nc);         // contiguous FULL A^T output
+  float* uc = bp.take<float>((size_t)B * nr);         // contiguous A^T input   (GKL kind: [B, D] part then [B, d] part, both FULL width)
   float* tu = bp.take<float>((size_t)B * nr);         // contiguous A output    (GKL kind: only the [B, d] output-space part)
+  float* vloc = sh ? bp.take<float>((size_t)B * sh->Dsh) : nullptr;        // gather sources: zero-padded local slices
+  float* udloc = sh ? bp.take<float>((size_t)B * std::max<int64_t>(sh->dsh, 4)) : nullptr;
+  float* gath = sh ? bp.take<float>((size_t)B * sh->S * std::max(sh->Dsh, sh->dsh)) : nullptr;
   float* alpha = bp.take<float>((size_t)B);
   float* beta = bp.take<float>((size_t)B);
   float* nu = bp.take<float>((size_t)B);
   float* nv = bp.take<float>((size_t)B);
   float* nrm0 = bp.take<float>((size_t)B);
-  if (!bp.ok) { set_error("gkl: workspace too small (%zu bytes given, %zu needed)", ws_bytes, gkl_ws_bytes(o, k, B)); return LIP_ERR_WORKSPACE; }
+  if (!bp.ok) { set_error("gkl: workspace too small (%zu bytes given)", ws_bytes); return LIP_ERR_WORKSPACE; }
   const int64_t usb = k * ldu, vsb = k * ldv;
-  if (lu != nr) LIP_CHECK_CUDA(cudaMemsetAsync(u, 0, sizeof(float) * (size_t)B * lu, st));
-  if (lv != nc) LIP_CHECK_CUDA(cudaMemsetAsync(v, 0, sizeof(float) * (size_t)B * lv, st));
+  if (lu != nrl) LIP_CHECK_CUDA(cudaMemsetAsync(u, 0, sizeof(float) * (size_t)B * lu, st));
+  if (lv != ncl) LIP_CHECK_CUDA(cudaMemsetAsync(v, 0, sizeof(float) * (size_t)B * lv, st));
   LIP_CHECK_CUDA(cudaMemsetAsync(Us, 0, sizeof(float) * (size_t)B * usb, st));
   LIP_CHECK_CUDA(cudaMemsetAsync(Vs, 0, sizeof(float) * (size_t)B * vsb, st));
   LIP_CHECK_CUDA(cudaMemsetAsync(betas, 0, sizeof(float) * (size_t)B * k, st));
+  if (sh) {
+    LIP_CHECK_CUDA(cudaMemsetAsync(vloc, 0, sizeof(float) * (size_t)B * sh->Dsh, st));
+    LIP_CHECK_CUDA(cudaMemsetAsync(udloc, 0, sizeof(float) * (size_t)B * std::max<int64_t>(sh->dsh, 4), st));
+    LIP_CHECK_CUDA(cudaMemsetAsync(uc, 0, sizeof(float) * (size_t)B * nr, st));     // only this rank's columns of the [B, D] part are ever written
+  }
   const float sa = gkl ? sqrtf(o.op->alpha) : 0.f;
   float* ucD = uc;                       // GKL kind: parameter-space part of u, [B, D]
   float* ucd = uc + (size_t)B * D;       //           output-space part, [B, d]
   // v_0 = v0 / |v0|
   {
-    AxpyNormArgs a{}; a.x1 = v0; a.ld1 = ldv0; a.n1 = nc; a.s1 = 1.f; a.out = v; a.ldo = lv; a.nrm = nrm0; a.n = nc;
+    AxpyNormArgs a{}; a.x1 = v0 + c0; a.ld1 = ldv0; a.n1 = ncl; a.s1 = 1.f; a.out = v; a.ldo = lv; a.nrm = nrm0; a.n = ncl;
     rc = launch_axpy_norm(a, B, r, st); if (rc) return rc;
+    rc = shard_norm(sh, nrm0, B, st); if (rc) return rc;
     if (norm0) LIP_CHECK_CUDA(cudaMemcpyAsync(norm0, nrm0, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
-    ScaleStoreArgs s{}; s.x = v; s.ldx = lv; s.scal = nrm0; s.o1 = Vs; s.ld1 = ldv; s.o1sb = vsb; s.o2 = vc; s.ld2 = nc; s.n2 = nc; s.n = nc;
+    ScaleStoreArgs s{}; s.x = v; s.ldx = lv; s.scal = nrm0; s.o1 = Vs; s.ld1 = ldv; s.o1sb = vsb; s.n2 = ncl; s.n = ncl;
+    if (sh) { s.o2 = vloc; s.ld2 = sh->Dsh; } else { s.o2 = vc; s.ld2 = nc; }
     rc = launch_scale_store(s, B, st); if (rc) return rc;
   }
   const unsigned gB = (unsigned)ceil_div(B, 128);
   for (int64_t i = 0; i < k; ++i) {
     // ---- u = A v_i - beta_i u_{i-1};  alpha_i = |u|
+    if (sh) { rc = shard_allgather(sh, vloc, sh->Dsh, gath, vc, nc, B, st); if (rc) return rc; }
     AxpyNormArgs a{};
     if (gkl) {
       rc = lip_wt_apply(o.op->model, vc, tu, B, o.op->scale, LIP_FACTOR_SQRT, o.mws, o.mws_bytes, st); if (rc) return rc;
-      a.x1 = vc; a.ld1 = D; a.n1 = D; a.s1 = sa; a.x2 = tu; a.ld2 = d;
+      a.x1 = vc + c0; a.ld1 = D; a.n1 = ncl; a.s1 = sa; a.x2 = tu + d0; a.ld2 = d;
     } else {
       rc = op_apply(o, vc, tu, B, 0, st); if (rc) return rc;
       a.x1 = tu; a.ld1 = nr; a.n1 = nr; a.s1 = 1.f;
     }
     if (i > 0) { a.y = Us + (i - 1) * ldu; a.ldy = ldu; a.ysb = usb; a.coef = beta; }
-    a.out = u; a.ldo = lu; a.nrm = alpha; a.n = nr;
+    a.out = u; a.ldo = lu; a.nrm = alpha; a.n = nrl;
     rc = launch_axpy_norm(a, B, r, st); if (rc) return rc;
+    rc = shard_norm(sh, alpha, B, st); if (rc) return rc;
     record_kernel<<<gB, 128, 0, st>>>(alphas, k, i, alpha, (int)B);
     LIP_LAUNCH_CHECK();
     // ---- u <- normalise, CGS against U[0..i-1], renormalise, store
-    rc = launch_project(Us, ldu, usb, (int)i, u, lu, nr, B, r, st); if (rc) return rc;
-    rc = launch_subtract(Us, ldu, usb, (int)i, u, lu, alpha, u, lu, nu, nr, B, r, st); if (rc) return rc;
+    rc = launch_project(Us, ldu, usb, (int)i, u, lu, nrl, B, r, st); if (rc) return rc;
+    if (i > 0) { rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc; }
+    rc = launch_subtract(Us, ldu, usb, (int)i, u, lu, alpha, u, lu, nu, nrl, B, r, st); if (rc) return rc;
+    rc = shard_norm(sh, nu, B, st); if (rc) return rc;
     {
-      ScaleStoreArgs s{}; s.x = u; s.ldx = lu; s.scal = nu; s.o1 = Us + i * ldu; s.ld1 = ldu; s.o1sb = usb; s.n = nr;
-      if (gkl) { s.o2 = ucD; s.ld2 = D; s.n2 = D; s.o3 = ucd; s.ld3 = d; }
+      ScaleStoreArgs s{}; s.x = u; s.ldx = lu; s.scal = nu; s.o1 = Us + i * ldu; s.ld1 = ldu; s.o1sb = usb; s.n = nrl;
+      if (gkl && sh) { s.o2 = ucD + c0; s.ld2 = D; s.n2 = ncl; s.o3 = udloc; s.ld3 = sh->dsh; }
+      else if (gkl) { s.o2 = ucD; s.ld2 = D; s.n2 = D; s.o3 = ucd; s.ld3 = d; }
       else { s.o2 = uc; s.ld2 = nr; s.n2 = nr; }
       rc = launch_scale_store(s, B, st); if (rc) return rc;
     }
     if (i + 1 == k) break;              // the last v would not be used (matfree computes it; it does not enter B)
     // ---- w = A^T u_i - alpha_i v_i;  beta_{i+1} = |w|
     if (gkl) {
+      if (sh) { rc = shard_allgather(sh, udloc, sh->dsh, gath, ucd, d, B, st); if (rc) return rc; }
+      // sharded: ucD holds only this rank's columns (zeros elsewhere), so only this rank's columns of wv are meaningful - the ones used
       rc = lip_w_apply(o.op->model, ucd, wv, B, o.op->scale, LIP_FACTOR_SQRT, ucD, sa, o.mws, o.mws_bytes, st); if (rc) return rc;
     } else {
       rc = op_apply(o, uc, wv, B, 1, st); if (rc) return rc;
     }
-    AxpyNormArgs c{}; c.x1 = wv; c.ld1 = nc; c.n1 = nc; c.s1 = 1.f; c.y = Vs + i * ldv; c.ldy = ldv; c.ysb = vsb; c.coef = alpha;
-    c.out = v; c.ldo = lv; c.nrm = beta; c.n = nc;
+    AxpyNormArgs c{}; c.x1 = wv + c0; c.ld1 = nc; c.n1 = ncl; c.s1 = 1.f; c.y = Vs + i * ldv; c.ldy = ldv; c.ysb = vsb; c.coef = alpha;
+    c.out = v; c.ldo = lv; c.nrm = beta; c.n = ncl;
     rc = launch_axpy_norm(c, B, r, st); if (rc) return rc;
+    rc = shard_norm(sh, beta, B, st); if (rc) return rc;
     record_kernel<<<gB, 128, 0, st>>>(betas, k, i + 1, beta, (int)B);
     LIP_LAUNCH_CHECK();
-    rc = launch_project(Vs, ldv, vsb, (int)(i + 1), v, lv, nc, B, r, st); if (rc) return rc;
-    rc = launch_subtract(Vs, ldv, vsb, (int)(i + 1), v, lv, beta, v, lv, nv, nc, B, r, st); if (rc) return rc;
+    rc = launch_project(Vs, ldv, vsb, (int)(i + 1), v, lv, ncl, B, r, st); if (rc) return rc;
+    rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
+    rc = launch_subtract(Vs, ldv, vsb, (int)(i + 1), v, lv, beta, v, lv, nv, ncl, B, r, st); if (rc) return rc;
+    rc = shard_norm(sh, nv, B, st); if (rc) return rc;
     {
-      ScaleStoreArgs s{}; s.x = v; s.ldx = lv; s.scal = nv; s.o1 = Vs + (i + 1) * ldv; s.ld1 = ldv; s.o1sb = vsb; s.o2 = vc; s.ld2 = nc;
-      s.n2 = nc; s.n = nc;
+      ScaleStoreArgs s{}; s.x = v; s.ldx = lv; s.scal = nv; s.o1 = Vs + (i + 1) * ldv; s.ld1 = ldv; s.o1sb = vsb; s.n2 = ncl; s.n = ncl;
+      if (sh) { s.o2 = vloc; s.ld2 = sh->Dsh; } else { s.o2 = vc; s.ld2 = nc; }
       rc = launch_scale_store(s, B, st); if (rc) return rc;
     }
   }
   return LIP_OK;
 }
-
 
 // ---- Hutch++ v2 --------------------------------------------------------------------------------------------------------------------
 int launch_gram(const float* A, int64_t lda, int sa, const float* Bm, int64_t ldb, int sb, int64_t n, double* part, double* out,
@@ -1073,6 +1186,8 @@ int hutchpp_run(Op& o, const float* probes, int64_t ldp, int64_t s1, int64_t s2,
 // =====================================================================================================================
 extern "C" {
 
+static size_t slq_ws_bytes(const Op& o, int form, int64_t k, int64_t B, int world);
+
 size_t lip_krylov_workspace_bytes(const lip_linop* op, int32_t routine, int64_t k, int64_t B) {
   Op o;
   if (op_init(o, op) != LIP_OK || k <= 0 || B <= 0) return 0;
@@ -1081,9 +1196,8 @@ size_t lip_krylov_workspace_bytes(const lip_linop* op, int32_t routine, int64_t 
   switch (routine) {
     case LIP_KRYLOV_LANCZOS: return lanczos_ws_bytes(o, k, B);
     case LIP_KRYLOV_GKL: return gkl_ws_bytes(o, k, B);
-    case LIP_KRYLOV_SLQ_LANCZOS: return lanczos_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + tri + 4096;
-    case LIP_KRYLOV_SLQ_GKL:
-      return gkl_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + rsz((size_t)B * k * pad4(nr), 4) + tri + 4096;
+    case LIP_KRYLOV_SLQ_LANCZOS: return slq_ws_bytes(o, LIP_SLQ_LANCZOS, k, B, 1);
+    case LIP_KRYLOV_SLQ_GKL: return slq_ws_bytes(o, LIP_SLQ_GKL, k, B, 1);
     case LIP_KRYLOV_FUNM: return lanczos_ws_bytes(o, k, B) + rsz((size_t)B * k * pad4(nc), 4) + tri + rsz((size_t)B * pad4(nc), 4) + 4096;
     case LIP_KRYLOV_HUTCHPP: return hutchpp_ws_bytes(o, k, B);
     case LIP_KRYLOV_APPLY: return op_ws_bytes(o, B) + rsz((size_t)B * (nr > nc ? nr : nc), 4) + 4096;
@@ -1133,7 +1247,7 @@ int lip_lanczos_tridiag(const lip_linop* op, const float* v0, int64_t ldv0, int6
   int rc = op_init(o, op);
   if (rc) return rc;
   LIP_REQUIRE(v0 && diag && (off || k == 1) && workspace && B > 0 && ldv0 >= o.n_in, "lip_lanczos_tridiag: bad argument");
-  return lanczos_run(o, v0, ldv0, k, B, passes, Q, ldq, diag, off, norm0, workspace, workspace_bytes, (cudaStream_t)stream);
+  return lanczos_run(o, nullptr, v0, ldv0, k, B, passes, Q, ldq, diag, off, norm0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int lip_gkl_bidiag(const lip_linop* op, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* Us, int64_t ldu, float* Vs,
@@ -1143,18 +1257,43 @@ int lip_gkl_bidiag(const lip_linop* op, const float* v0, int64_t ldv0, int64_t k
   int rc = op_init(o, op);
   if (rc) return rc;
   LIP_REQUIRE(v0 && alphas && betas && workspace && B > 0 && ldv0 >= o.n_in, "lip_gkl_bidiag: bad argument");
-  return gkl_run(o, v0, ldv0, k, B, Us, ldu, Vs, ldv, alphas, betas, norm0, workspace, workspace_bytes, (cudaStream_t)stream);
+  return gkl_run(o, nullptr, v0, ldv0, k, B, Us, ldu, Vs, ldv, alphas, betas, norm0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form, int32_t fn,
-                       float clip_min, float* quad_out, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
+static size_t slq_ws_bytes(const Op& o, int form, int64_t k, int64_t B, int world) {
+  const int64_t nc = o.n_in, nr = o.n_out;
+  const int64_t ncl = pad4(ceil_div(nc, world)) + 4, nrl = ncl + pad4(ceil_div(std::max<int64_t>(o.d, 0), world)) + 4;
+  const size_t tri = lip_tridiag_scratch_bytes(k, B, 0) + 4 * rsz((size_t)B * k, 4) + 2 * rsz((size_t)B, 4);
+  size_t bases = rsz((size_t)B * k * pad4(world > 1 ? ncl : nc), 4);
+  if (form == LIP_SLQ_GKL) bases += rsz((size_t)B * k * pad4(world > 1 ? nrl : nr), 4);
+  return (form == LIP_SLQ_GKL ? gkl_ws_bytes(o, k, B) : lanczos_ws_bytes(o, k, B)) + bases + tri + 8192;
+}
+
+size_t lip_slq_workspace_bytes(const lip_linop* op, int32_t form, int64_t k, int64_t B, int32_t world) {
+  Op o;
+  if (op_init(o, op) != LIP_OK || k <= 0 || B <= 0 || world < 1) return 0;
+  return slq_ws_bytes(o, form, k, B, world);
+}
+
+int lip_slq_quadrature_sharded(const lip_linop* op, lip_comm* comm, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form,
+                               int32_t fn, float clip_min, float* quad_out, void* workspace, size_t workspace_bytes,
+                               lip_stream_t stream) {
   Op o;
   int rc = op_init(o, op);
   if (rc) return rc;
   LIP_REQUIRE(probes && quad_out && workspace && B > 0 && k > 0, "lip_slq_quadrature: bad argument");
   LIP_REQUIRE(form == LIP_SLQ_LANCZOS || form == LIP_SLQ_GKL, "lip_slq_quadrature: unknown form %d", form);
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t nc = o.n_in, nr = o.n_out, ldv = pad4(nc), ldu = pad4(nr);
+  Shard shard;
+  const Shard* sh = nullptr;
+  if (comm && comm->world > 1) {
+    LIP_REQUIRE(op->kind == LIP_LINOP_GGN || op->kind == LIP_LINOP_GKL, "sharded SLQ: the operator must be a model kind (GGN / GKL)");
+    rc = shard_init(shard, comm, o.D, form == LIP_SLQ_GKL ? o.d : 0);
+    if (rc) return rc;
+    sh = &shard;
+  }
+  const int64_t nc = o.n_in, nr = o.n_out;
+  const int64_t ldv = pad4(sh ? sh->nloc : nc), ldu = pad4(sh ? sh->nloc + sh->dloc : nr);
   Bump bp(workspace, workspace_bytes);
   float* td = bp.take<float>((size_t)B * k);
   float* to = bp.take<float>((size_t)B * k);
@@ -1167,22 +1306,31 @@ int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, in
   float* Us = form == LIP_SLQ_GKL ? bp.take<float>((size_t)B * k * ldu) : nullptr;
   if (!bp.ok) {
     set_error("lip_slq_quadrature: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
-              lip_krylov_workspace_bytes(op, form == LIP_SLQ_GKL ? LIP_KRYLOV_SLQ_GKL : LIP_KRYLOV_SLQ_LANCZOS, k, B));
+              slq_ws_bytes(o, form, k, B, sh ? sh->S : 1));
     return LIP_ERR_WORKSPACE;
   }
   const size_t rest = (size_t)(bp.end - bp.p);
   if (form == LIP_SLQ_LANCZOS) {
-    rc = lanczos_run(o, probes, ldp, k, B, 2, Vs, ldv, td, to, nrm, bp.p, rest, st);
+    rc = lanczos_run(o, sh, probes, ldp, k, B, 2, Vs, ldv, td, to, nrm, bp.p, rest, st);
   } else {
-    rc = gkl_run(o, probes, ldp, k, B, Us, ldu, Vs, ldv, al, be, nrm, bp.p, rest, st);
+    rc = gkl_run(o, sh, probes, ldp, k, B, Us, ldu, Vs, ldv, al, be, nrm, bp.p, rest, st);
     if (!rc) rc = lip_bidiag_to_tridiag(al, be, td, to, k, B, st);
   }
   if (rc) return rc;
-  rc = lip_tridiag_funm(td, to, k, B, fn, clip_min, q, nullptr, nullptr, tsc, st);
+  // GKL form: T = B^T B is positive semi-definite and matfree evaluates f on the squared SINGULAR VALUES of B (>= 0 by construction).
+  // The eigenvalue route can return -1e-13 |T| for a zero singular value of the decoupled post-breakdown block (weight ~1e-13, but
+  // log of it is NaN), so the spectrum is floored at a denormal-scale positive number, which is what the SVD route sees.
+  const float clip = (form == LIP_SLQ_GKL && clip_min < 0.f) ? 1e-30f : clip_min;
+  rc = lip_tridiag_funm(td, to, k, B, fn, clip, q, nullptr, nullptr, tsc, st);
   if (rc) return rc;
   quad_scale_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(quad_out, q, nrm, (int)B);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
+}
+
+int lip_slq_quadrature(const lip_linop* op, const float* probes, int64_t ldp, int64_t k, int64_t B, int32_t form, int32_t fn,
+                       float clip_min, float* quad_out, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
+  return lip_slq_quadrature_sharded(op, nullptr, probes, ldp, k, B, form, fn, clip_min, quad_out, workspace, workspace_bytes, stream);
 }
 
 int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv_in, int64_t k, int64_t B, int32_t fn, float clip_min,
@@ -1206,7 +1354,7 @@ int lip_funm_lanczos(const lip_linop* op, const float* v, int64_t ldv_in, int64_
               lip_krylov_workspace_bytes(op, LIP_KRYLOV_FUNM, k, B));
     return LIP_ERR_WORKSPACE;
   }
-  rc = lanczos_run(o, v, ldv_in, k, B, 2, Q, ldq, td, to, nrm, bp.p, (size_t)(bp.end - bp.p), st);
+  rc = lanczos_run(o, nullptr, v, ldv_in, k, B, 2, Q, ldq, td, to, nrm, bp.p, (size_t)(bp.end - bp.p), st);
   if (rc) return rc;
   rc = lip_tridiag_funm_p(td, to, k, B, fn, clip_min, fn_params, nullptr, fe1, nullptr, tsc, st);
   if (rc) return rc;

@@ -367,8 +367,10 @@ def integrand_funm_sym_logdet(tridiag_sym):
 
 def integrand_funm_product_logdet(bidiag):
     """matfree.funm.integrand_funm_product_logdet (train_inducing.py:157): |v|^2 e1^T V log(S^2) V^T e1 for the GKL
-    bidiagonal B = U S V^T, evaluated through the eigen-decomposition of T = B^T B (no clip: matfree's own)."""
-    dense = DenseFunm("log", None)
+    bidiagonal B = U S V^T, evaluated through the eigen-decomposition of T = B^T B.  matfree takes the SVD of B, whose squared
+    singular values are >= 0 by construction; the eigenvalue route can return -1e-13 |T| for a zero singular value of the
+    decoupled post-breakdown block (weight ~1e-13, but its log is NaN), so the spectrum is floored at 1e-30."""
+    dense = DenseFunm("log", 1e-30)
 
     def quadform(Av, v0, vA=None):
         L = cabi.lib()
@@ -388,6 +390,41 @@ def integrand_funm_product_logdet(bidiag):
         return q[0] if single else q
 
     return batched(quadform)
+
+
+def slq_quadrature(matvec, probes, num_matvecs, *, form="gkl", fn="log", clip_min=None, comm=None):
+    """The fused native SLQ integrand (lip_slq_quadrature / lip_slq_quadrature_sharded): per-probe |v|^2 e1^T f(T) e1, [B].
+    form "gkl": matvec is a gkl_target closure (integrand_funm_product_logdet, train_inducing.py:156-157);
+    form "lanczos": a symmetric closure (integrand_funm_sym; fn="log", clip_min=1.0 is the patched integrand_funm_sym_logdet).
+    comm: a _dist.NativeComm whose ranks share the Krylov bases column-wise (every rank passes the same probes)."""
+    L = cabi.lib()
+    P, single = _as2d(probes)
+    P = P.contiguous()
+    nb, n = P.shape
+    sym = form == "lanczos"
+    if not sym and form != "gkl":
+        raise ValueError(f"slq_quadrature: unknown form {form!r}")
+    if sym:
+        nout = n
+    else:
+        bm = getattr(matvec, "_lip_model", None)
+        if bm is None or getattr(matvec, "_lip_kind", None) != "GKL":
+            raise ValueError("slq_quadrature(form='gkl') needs a matfree.gkl_target closure")
+        nout = bm.D + bm.M * bm.K
+    op = _NativeOp(matvec, getattr(matvec, "_lip_transpose", None), nb, n, nout, single, symmetric=sym)
+    world = 1 if comm is None else comm.world
+    if world > 1 and op.struct.kind not in (cabi.LINOP_GGN, cabi.LINOP_GKL):
+        raise ValueError("sharded slq_quadrature needs one of this package's model closures (curvature_vp / gkl_target)")
+    f = cabi.SLQ_LANCZOS if sym else cabi.SLQ_GKL
+    need = L.lip_slq_workspace_bytes(op.ref(), f, int(num_matvecs), nb, world)
+    if need == 0:
+        raise ValueError("lip_slq_workspace_bytes: " + L.lip_last_error().decode("utf-8", "replace"))
+    ws = torch.empty(need, dtype=torch.uint8, device=P.device)
+    out = torch.empty(nb, device=P.device)
+    rc = L.lip_slq_quadrature_sharded(op.ref(), None if comm is None else comm.handle, ptr(P), n, int(num_matvecs), nb, f, _FN[fn],
+                                      -1.0 if clip_min is None else float(clip_min), ptr(out), ptr(ws), need, stream())
+    op.check(rc, "lip_slq_quadrature")
+    return out[0] if single else out
 
 
 funm = SimpleNamespace(dense_funm_sym_eigh=dense_funm_sym_eigh, funm_lanczos_sym=funm_lanczos_sym,

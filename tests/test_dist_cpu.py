@@ -165,3 +165,59 @@ def test_zgrad_sharded_sums_probe_slices(B):
     for r in range(ws):
         np.testing.assert_allclose(res[r][0], ref, rtol=1e-5, atol=1e-5)
     assert sum(res[r][1] for r in range(ws)) == B          # every probe pair is pushed exactly once
+
+
+# ---------------------------------------------------------------------------------------------- hybrid probe x basis sharding
+def test_group_layout_prefers_probe_groups():
+    assert _dist.group_layout(1, 4) == (1, 1)
+    assert _dist.group_layout(2, 4) == (2, 1)
+    assert _dist.group_layout(4, 4) == (4, 1)
+    assert _dist.group_layout(8, 4) == (4, 2)          # BASELINE's SLQ case: 4 probes on 8 GPUs -> pairs share a probe's bases
+    assert _dist.group_layout(8, 1) == (1, 8)
+    assert _dist.group_layout(8, 3) == (2, 4)
+    assert _dist.group_layout(6, 4) == (3, 2)
+    for ws in range(1, 17):
+        for B in range(1, 9):
+            P, S = _dist.group_layout(ws, B)
+            assert P * S == ws and 1 <= P <= B
+    with pytest.raises(ValueError):
+        _dist.group_layout(0, 4)
+
+
+def _hybrid_worker(rank, ws, port, B, force_S, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    _dist.init_from_env(backend="gloo")
+    from lip_b200 import matfree
+    g = torch.Generator().manual_seed(3)
+    probes = torch.randn(B, 17, generator=g)
+    seen = {}
+
+    def fake_quadrature(matvec, mine, k, *, form, fn, clip_min, comm):          # CPU stand-in for the native recurrence
+        seen["rows"], seen["comm"] = mine.clone(), comm
+        return (mine ** 2).sum(1) * k
+
+    def fake_comms(S):
+        return None if S == 1 else _dist.NativeComm(None, S, rank % S)
+
+    matfree.slq_quadrature, _dist.native_comms = fake_quadrature, fake_comms
+    if force_S:
+        _dist.group_layout = lambda w, b: (w // force_S, force_S)
+    got = float(_dist.slq_logdet_hybrid(None, probes, 5))
+    ref = float(((probes ** 2).sum(1) * 5).mean())
+    P, S = _dist.group_layout(ws, B)
+    ok = abs(got - ref) <= 1e-5 * abs(ref)
+    ok = ok and torch.equal(seen["rows"], probes[_dist.probe_slice(B, rank // S, P)])
+    ok = ok and ((seen["comm"] is None) == (S == 1)) and (S == 1 or seen["comm"].rank == rank % S)
+    out[rank] = 1.0 if ok else 0.0
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,force_S", [(4, 0), (1, 0), (3, 2)])
+def test_hybrid_slq_layout_world_size_2_gloo(B, force_S):
+    """world_size 2: (B=4 -> two probe groups, no basis sharding), (B=1 -> one group of two ranks sharing the probe's bases),
+    (B=3 forced into one 2-rank group): every probe is evaluated by exactly one group, group members see the same rows, only the
+    group leader contributes to the all-reduced mean."""
+    ws = 2
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_hybrid_worker, args=(ws, _free_port(), B, force_S, out), nprocs=ws, join=True)
+    assert [out[r] for r in range(ws)] == [1.0, 1.0]
