@@ -69,6 +69,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the Z-gradient / inducing-point training-step leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 (LeNet5) / C5 (ResNet1M) sub-records")
     ap.add_argument("--tensor-path", type=int, default=-1, help="-1 auto, 0 SIMT fp32, 1 tcgen05 3xTF32")
     ap.add_argument("--workload", default="mlp", choices=sorted(WORKLOADS), help="mlp = headline C3b; lenet5 = C4 conv path")
     ap.add_argument("--points", type=int, default=0, help="override the workload's number of inducing points M")
@@ -170,10 +171,12 @@ def measure_tf32_peak(torch):
     return 2 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def cpu_reference_products_per_s(ost, Z, n_products, steps=1, warmup=0):
+def cpu_reference_products_per_s(ost, Z, n_products=1, steps=2, warmup=1):
     """The reference's algorithm (src/ggn.py:133-144: sequential loop over the M points, per-point jvp, redundant
     forward, closed-form Hessian, per-point vjp) restated in torch fp32 on the host cores (oracle/, kind 'port':
-    JAX is not installed in this image so /root/reference cannot run)."""
+    JAX is not installed in this image so /root/reference cannot run).  ONE function for both arms (`cpu_baseline` of the GPU
+    line and `--impl reference`): `warmup` untimed passes (the first pass pays torch's thread-pool / autograd warm-up, which
+    made round 1's two numbers differ by 2x), then `steps` timed passes of `n_products` products each."""
     import numpy as np
     import torch
     from oracle import lip_oracle as O
@@ -196,6 +199,15 @@ def cpu_reference_products_per_s(ost, Z, n_products, steps=1, warmup=0):
     return n_products * len(times) / total, cores, total / len(times)
 
 
+def bench_config(args, world):
+    """The `config` object of BOTH arms (the driver compares them): the workload and the per-GPU probe batch the metric is quoted on."""
+    import numpy as np
+    D = {"mlp": 1_494_154, "lenet5": 61_706, "resnet1m": 1_084_586}[args.workload]
+    return {"workload": WORKLOAD, "probes_per_gpu": args.probes,
+            "l2": "inputs larger than L2 (V and out are %.2f GB each per GPU)" % (args.probes * D * 4 / 1e9),
+            "parallelism": f"probe-sharded x{world}"}
+
+
 def reference_import_status():
     """The unmodified reference (pip-installed from /root/reference into baseline/_ref) is pure Python on top
     of JAX / flax / matfree.  Returns None when it can be imported, else the reason it cannot (then the oracle port runs)."""
@@ -216,19 +228,74 @@ def run_reference(args):
     if rank != 0:
         return
     ost, _, Z = build_states(workload=args.workload)
-    # bounded sample: ONE product (all 512 points) per step so that --steps 10 --warmup 3 ends within minutes
-    args.cpu_probes = 1
-    pps, cores, sec = cpu_reference_products_per_s(ost, Z, args.cpu_probes, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    # bounded sample: ONE product (all M points) per step so that --steps 20 --warmup 5 ends within a minute; the metric is per product,
+    # so it is comparable with the GPU arm's batched steps (config.probes_per_gpu is the batch the GPU arm is quoted on)
+    n_prod = 1
+    pps, cores, sec = cpu_reference_products_per_s(ost, Z, n_prod, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
     why = reference_import_status()
-    sample = (f"{args.cpu_probes} products (all {M_POINTS} points each) per step, torch fp32 restatement of src/ggn.py:133-144 "
+    sample = (f"{n_prod} product (all {M_POINTS} points) per step, torch fp32 restatement of src/ggn.py:133-144 "
               f"(oracle port; the installed reference itself is not runnable here: {why})")
     line = {"impl": "reference", "metric": "ggn_vec_products_per_s", "value": pps, "unit": "products/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "probes_per_step": args.cpu_probes},
+            "config": bench_config(args, args.gpus),
             "cpu_baseline": {"value": pps, "unit": "products/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": pps, "unit": "products/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def measure_extra(name, points, probes, steps, warmup, shard_points, torch, dist, world, rank, dev):
+    """A secondary workload of BASELINE.json's configs (C4 LeNet5 probe-sharded, C5 ResNet1M point-sharded) measured like the headline:
+    `steps` curvature_vp calls over `probes` Rademacher probes, CUDA events, max over ranks.  Returns a sub-record."""
+    import numpy as np
+    from lip_b200 import lla
+    saved = (M_POINTS, N_FULL, ALPHA, FLOP_PER_PRODUCT, WORKLOAD)
+    try:
+        set_workload(name)
+        g = globals()
+        if points:
+            g["FLOP_PER_PRODUCT"] = FLOP_PER_PRODUCT // M_POINTS * points
+            g["WORKLOAD"] = WORKLOAD.replace(f"M={M_POINTS}", f"M={points}")
+            g["M_POINTS"] = points
+        ost, lst, Z = build_states(workload=name)
+        D = ost.flat()[0].size
+        Zd = torch.as_tensor(Z, device=dev)
+        t0 = time.perf_counter()
+        cvp = lla.compute_curvature_approx(lst, Zd, "classifier", ALPHA, full_set_size=N_FULL, shard_points=shard_points and world > 1)
+        torch.cuda.synchronize()
+        bind_s = time.perf_counter() - t0
+        seed = 3000 if shard_points else 3000 + rank           # point sharding: every rank pushes the SAME probes
+        V = torch.from_numpy(np.random.default_rng(seed).integers(0, 2, size=(probes, D), dtype=np.int8) * 2 - 1).to(dev).float()
+        for _ in range(warmup):
+            cvp(V)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(steps):
+            Y = cvp(V)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_step = float(ms.item()) / steps
+        total_products = probes * (1 if shard_points else world)
+        bm = getattr(cvp, "_lip_model", None)
+        rec = {"workload": WORKLOAD, "value": total_products / (ms_step * 1e-3), "unit": "products/s", "ms_per_step": ms_step,
+               "probes_per_step": total_products, "steps": steps, "warmup": warmup, "bind_seconds": bind_s,
+               "parallelism": (f"point-sharded x{world}: M/{world} points per GPU, one NCCL all-reduce of the [B, D] block per call"
+                               if shard_points and world > 1 else f"probe-sharded x{world}"),
+               "path": bm.path_name() if bm is not None and hasattr(bm, "path_name") else None,
+               "algorithmic_tflops": FLOP_PER_PRODUCT * total_products / (ms_step * 1e-3) / 1e12 / world,
+               "finite": bool(torch.isfinite(Y).all())}
+        del cvp, V, Y
+        torch.cuda.empty_cache()
+        return rec
+    finally:
+        g = globals()
+        g["M_POINTS"], g["N_FULL"], g["ALPHA"], g["FLOP_PER_PRODUCT"], g["WORKLOAD"] = saved
 
 
 def run_b200(args):
@@ -358,6 +425,37 @@ def run_b200(args):
                "note": "pinned bit-packed +-1 probes -> H2D -> lip_unpack_rademacher -> lla.compute_curvature_approx(...)(V) -> "
                        "v.(Gv) -> pinned host; H2D double-buffered, D2H pipelined two steps deep"}
 
+    # second end-to-end leg: GENERAL fp32 vectors (what a CG / Lanczos caller on the host would hand over): pinned [B, D] fp32 in,
+    # the full [B, D] fp32 result out, both inside the timed region (3.06 GB each way per step at B = 256: PCIe-bound by construction)
+    e2e_fp32 = None
+    if not args.no_e2e:
+        hV = torch.empty(B, D, dtype=torch.float32).pin_memory()
+        hV.copy_(V)
+        hY = torch.empty(B, D, dtype=torch.float32).pin_memory()
+        dV = torch.empty(B, D, device=dev)
+        n_e = max(2, min(args.steps, 4))
+
+        def e2e_fp32_run(n):
+            for _ in range(n):
+                dV.copy_(hV, non_blocking=True)
+                Y = cvp(dV)
+                hY.copy_(Y, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_fp32_run(1)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e2e_fp32_run(n_e)
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_fp32 = {"value": B * world * n_e / float(dt.item()), "unit": "products/s", "steps": n_e,
+                    "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * D * 4,
+                    "note": "pinned fp32 [B, D] vectors -> H2D -> lla.compute_curvature_approx(...)(V) -> [B, D] products -> D2H to pinned "
+                            "host, no overlap between steps: bounded by the host link, not by the kernels"}
+        del hV, hY, dV
+
     # the dominant kernel group on its own: ONE lip_ggn_vp call (all JVP / VJP GEMM launches) under CUDA events on the
     # launching stream, same inputs, no quadratic form / all-reduce around it -> roofline.achieved
     k0, k1 = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -397,52 +495,58 @@ def run_b200(args):
         Av = matfree.gkl_target(WzT, Wz, ALPHA)
         vA = Av._lip_transpose
 
-        integrand = matfree.funm.integrand_funm_product_logdet(matfree.decomp.bidiag(k))
-        quad = matfree.batched(lambda mv, E: integrand(mv, E, vA))
-        # identical probe matrix on every rank (probes are inputs); rank r runs rows probe_slice(ns)
+        # identical probe matrix on every rank (probes are inputs).  Layout: probes are split over the ranks first; with more GPUs
+        # than probes the Krylov bases of a probe are cut column-wise over the ranks of its group (_dist.slq_logdet_hybrid ->
+        # lip_slq_quadrature_sharded).  ONE native call per rank runs the whole recurrence.
         gp = torch.Generator(device=dev)
         gp.manual_seed(4242)
         slq_probes = torch.randint(0, 2, (ns, D), generator=gp, device=dev, dtype=torch.int8).float() * 2 - 1
+        layout = _dist.group_layout(world, ns)
+        _dist.slq_logdet_hybrid(Av, slq_probes, 8, form="gkl")            # warm-up: communicators, kernel attributes
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        l0 = L.lip_launch_count()
         t0 = time.perf_counter()
-        est = _dist.slq_sharded(quad, Av, slq_probes)
+        est = _dist.slq_logdet_hybrid(Av, slq_probes, k, form="gkl")
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        slq_launches = L.lip_launch_count() - l0
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         # the Lanczos form (integrand_funm_sym_logdet of src/matfree_monkeypatch.py:25-41, eigenvalues clipped to >= 1;
         # train_inducing.py:152-153) on the curvature operator itself, same probes and depth
-        from lip_b200 import matfree_monkeypatch
-        lz = matfree_monkeypatch.integrand_funm_sym_logdet(matfree.decomp.tridiag_sym(k))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        est_lz = _dist.slq_sharded(lz, cvp, slq_probes)
+        est_lz = _dist.slq_logdet_hybrid(cvp, slq_probes, k, form="lanczos", clip_min=1.0)
         torch.cuda.synchronize()
         dt_lz = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt_lz, op=dist.ReduceOp.MAX)
-        sl = _dist.probe_slice(ns, rank, world)
-        n_loc = max(sl.stop - sl.start, (ns + world - 1) // world)
+        Pg, Sg = layout
+        n_loc = (ns + Pg - 1) // Pg                  # probes of the busiest group
         # algorithmic re-orthogonalisation traffic of the slowest rank: step i reads i rows of U (n = D + d) and i + 1
-        # rows of V (n = D) twice each (project, subtract); SURVEY 8d
-        reorth_bytes = n_loc * 4 * sum(2 * i * (D + d) + 2 * (i + 1) * D for i in range(k))
+        # rows of V (n = D) twice each (project, subtract); SURVEY 8d.  A rank owns 1 / Sg of every row.
+        reorth_bytes = n_loc * 4 * sum(2 * i * (D + d) + 2 * (i + 1) * D for i in range(k)) // Sg
         secs = float(dt.item())
         hbm = None
         try:
             hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
         except Exception:
             pass
-        lz_bytes = n_loc * 4 * sum(2 * (i + 1) * D * 2 for i in range(k))      # CGS2: two passes over i + 1 rows of Q
-        slq = {"seconds": secs, "k": k, "probes": ns, "probes_per_gpu": n_loc, "logdet_estimate": float(est.item()),
+        lz_bytes = n_loc * 4 * sum(2 * (i + 1) * D * 2 for i in range(k)) // Sg      # CGS2: two passes over i + 1 rows of Q
+        slq = {"seconds": secs, "k": k, "probes": ns, "probes_per_group": n_loc, "logdet_estimate": float(est.item()),
+               "layout": {"probe_groups": Pg, "basis_shards_per_group": Sg,
+                          "note": "probes over groups of GPUs (no communication); inside a group the Krylov bases are cut column-wise "
+                                  "(one all-gather of the new vector + one all-reduce per norm / coefficient vector per step)"},
+               "launches_per_logdet": int(slq_launches),
                "lanczos_form": {"seconds": float(dt_lz.item()), "logdet_estimate_clip1": float(est_lz.item()),
                                 "form": "Lanczos tridiag_sym(k) on curvature_vp, full re-orthogonalisation (2 passes), "
                                         "log(clip(eig, 1)) quadrature",
                                 "reorth_GBps": lz_bytes / float(dt_lz.item()) / 1e9},
-               "form": "GKL bidiag on [sqrt(alpha) I; Wz^T], full re-orthogonalisation",
+               "form": "GKL bidiag on [sqrt(alpha) I; Wz^T], full re-orthogonalisation; one native call (lip_slq_quadrature_sharded)",
                "roofline": {"bound": "hbm", "achieved": reorth_bytes / secs / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": (reorth_bytes / secs / 1e9 / hbm) if hbm else None,
                             "algorithmic_bytes": reorth_bytes,
@@ -485,6 +589,17 @@ def run_b200(args):
                  "optimize_step_config": f"train_inducing.optimize_step, scalable objective + exact dZ + Adam: m={m_ref} inducing points, "
                                          f"|X|=256, st_samples={nb}, slq k={k_ref} x 2 probes (config/scale/mlp_mnist.yml sizes)"}
 
+    # ---- BASELINE configs 4 and 5 under the same clock: C4 LeNet5 probe-sharded, C5 ResNet1M (M = 4096) point-sharded ----
+    extras = None
+    if not args.no_extra and args.workload == "mlp":
+        del V
+        torch.cuda.empty_cache()
+        extras = {}
+        try:
+            extras["c4_lenet5"] = measure_extra("lenet5", 0, 256, 5, 3, False, torch, dist, world, rank, dev)
+            extras["c5_resnet1m_m4096"] = measure_extra("resnet1m", 4096, 4, 3, 3, True, torch, dist, world, rank, dev)
+        except Exception as e:              # noqa: BLE001  (the headline line must still be printed)
+            extras["error"] = f"{type(e).__name__}: {e}"
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -521,17 +636,32 @@ def run_b200(args):
                 "algorithmic_flop_per_launch_group": FLOP_PER_PRODUCT * B}
     cpu = None
     if not args.no_cpu and world == 1:
-        pps, cores, sec = cpu_reference_products_per_s(ost, Z, args.cpu_probes)
+        pps, cores, sec = cpu_reference_products_per_s(ost, Z, 1, steps=3, warmup=1)
         cpu = {"value": pps, "unit": "products/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_probes} products, torch fp32 restatement of src/ggn.py:133-144 (JAX not installed), {sec:.1f} s"}
+               "sample": f"3 timed passes of 1 product (all {M_POINTS} points) after 1 warm-up pass, torch fp32 restatement of "
+                         f"src/ggn.py:133-144 (JAX not installed), {sec:.1f} s per product; same function as --impl reference"}
     line = {"metric": "ggn_vec_products_per_s", "value": value, "unit": "products/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "probes_per_gpu": B, "path": path,
-                       "l2": "inputs larger than L2 (V and out are %.2f GB each per GPU)" % (B * D * 4 / 1e9),
-                       "parallelism": f"probe-sharded x{world}"},
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "slq_logdet": slq, "train_step": train, "hutchinson_trace_estimate": trace_est}
+            "config": bench_config(args, world), "path": path,
+            "clocks": sampler.summary(), "e2e": e2e, "e2e_fp32_vectors": e2e_fp32, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "slq_logdet": slq, "train_step": train, "hutchinson_trace_estimate": trace_est,
+            "extra_workloads": extras}
+    if extras and tf32_peak > 0:
+        hbm = peaks.get("hbm_gbs")
+        c4, c5 = extras.get("c4_lenet5"), extras.get("c5_resnet1m_m4096")
+        if c5:
+            c5["roofline"] = {"bound": "tensor", "achieved": c5["algorithmic_tflops"], "peak": peak, "unit": "TFLOP/s",
+                              "frac": c5["algorithmic_tflops"] / peak, "note": "per GPU; peak = the headline's TF32 / 3"}
+        if c4:
+            # LeNet5 (channels 1 / 6 / 16) cannot feed the tensor cores; its yardsticks are the fp32 FMA pipes and HBM.  Bytes: the tangents and
+            # cotangents of every stage written and read once per (probe, point) — 2 x 8,094 floats x 8 B — plus 8 D per product.
+            per_pair = 2 * (4704 + 1176 + 1600 + 400 + 120 + 84 + 10) * 8
+            gbps = (per_pair * 200 + 8 * 61_706) * c4["probes_per_step"] / (c4["ms_per_step"] * 1e-3) / 1e9 / world
+            c4["roofline"] = {"bound": "hbm", "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": (gbps / hbm) if hbm else None,
+                              "simt_fp32_tflops": c4["algorithmic_tflops"],
+                              "note": "per GPU; unfused-stage traffic model (tangent + cotangent of each stage stored once, read once); the SIMT "
+                                      "fp32 GEMMs on 1 / 6 / 16-channel convolutions are instruction-bound, far from either roof"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

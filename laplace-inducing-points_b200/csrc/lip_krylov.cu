@@ -619,6 +619,8 @@ struct Op {
   float* dpart = nullptr; int nsplit = 0;      // dense-sym partials
 };
 
+constexpr int64_t MAX_COLUMNS = 65535;     // blockIdx.y of the vector kernels
+
 int op_init(Op& o, const lip_linop* op) {
   LIP_REQUIRE(op, "null operator");
   o.op = op;
@@ -862,6 +864,7 @@ size_t lanczos_ws_bytes(const Op& o, int64_t k, int64_t B) {
 int lanczos_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, int64_t B, int passes, float* Q, int64_t ldq,
                 float* diag, float* off, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t n = o.n_in;
+  LIP_REQUIRE(B <= MAX_COLUMNS, "lanczos_run: at most 65535 probe columns per call, got %lld", (long long)B);
   LIP_REQUIRE(o.symmetric || o.n_in == o.n_out, "lanczos: the operator must be square");
   LIP_REQUIRE(o.op->kind != LIP_LINOP_GKL, "lanczos: the GKL operator is rectangular (use lip_gkl_bidiag)");
   LIP_REQUIRE(k >= 1 && k <= n, "num_matvecs=%lld exceeds the operator dimension %lld", (long long)k, (long long)n);
@@ -941,6 +944,7 @@ int gkl_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, in
             float* alphas, float* betas, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t nc = o.n_in, nr = o.n_out;
   const bool gkl = o.op->kind == LIP_LINOP_GKL;
+  LIP_REQUIRE(B <= MAX_COLUMNS, "gkl_run: at most 65535 probe columns per call, got %lld", (long long)B);
   LIP_REQUIRE(!sh || gkl, "sharded gkl: only the LIP_LINOP_GKL operator is supported");
   LIP_REQUIRE(k >= 1 && k <= std::min(nc, nr), "num_matvecs=%lld exceeds the operator dimensions (%lld, %lld)", (long long)k,
               (long long)nr, (long long)nc);

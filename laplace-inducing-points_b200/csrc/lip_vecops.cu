@@ -387,6 +387,7 @@ size_t lip_dot_scratch_bytes(int64_t n, int64_t B) {
 
 int lip_dot(const float* x, const float* y, float* out, int64_t n, int64_t B, int64_t ldx, int64_t ldy,
             void* scratch, lip_stream_t stream) {
+  LIP_REQUIRE(B <= 65535, "lip_dot: at most 65535 columns per call (grid.y limit), got %lld: split the batch", (long long)B);
   LIP_REQUIRE(x && y && out && scratch && n > 0 && B > 0, "lip_dot: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   int nch;
@@ -399,6 +400,7 @@ int lip_dot(const float* x, const float* y, float* out, int64_t n, int64_t B, in
 
 int lip_axpby(const float* a, const float* x, const float* c, float* y, int64_t n, int64_t B, int64_t ldx,
               int64_t ldy, lip_stream_t stream) {
+  LIP_REQUIRE(B <= 65535, "lip_axpby: at most 65535 columns per call (grid.y limit), got %lld: split the batch", (long long)B);
   LIP_REQUIRE(x && y && n > 0 && B > 0, "lip_axpby: bad argument");
   dim3 grid(ew_blocks(n), (unsigned)B);
   axpby_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, x, c, y, n, ldx, ldy);
@@ -408,6 +410,7 @@ int lip_axpby(const float* a, const float* x, const float* c, float* y, int64_t 
 
 int lip_scale(const float* s, int32_t invert, const float* x, float* y, int64_t n, int64_t B, int64_t ldx,
               int64_t ldy, lip_stream_t stream) {
+  LIP_REQUIRE(B <= 65535, "lip_scale: at most 65535 columns per call (grid.y limit), got %lld: split the batch", (long long)B);
   LIP_REQUIRE(s && x && y && n > 0 && B > 0, "lip_scale: bad argument");
   dim3 grid(ew_blocks(n), (unsigned)B);
   scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(s, invert, x, y, n, ldx, ldy);
@@ -435,6 +438,7 @@ int lip_unpack_rademacher(const uint8_t* bits, int64_t ldbits, float* out, int64
 
 int lip_cg_init(const float* b, float* x, float* r, float* p, float* gamma, float* thresh, int32_t* active,
                 int32_t* iters, float tol, float atol, int64_t n, int64_t B, void* scratch, lip_stream_t stream) {
+  LIP_REQUIRE(B <= 65535, "lip_cg_init: at most 65535 columns per call (grid.y limit), got %lld: split the batch", (long long)B);
   LIP_REQUIRE(b && x && r && p && gamma && thresh && active && iters && scratch && n > 0 && B > 0,
               "lip_cg_init: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -455,6 +459,7 @@ int lip_cg_init(const float* b, float* x, float* r, float* p, float* gamma, floa
 
 int lip_cg_step(float* x, float* r, float* p, const float* Ap, float* gamma, const float* thresh, int32_t* active,
                 int32_t* iters, int64_t n, int64_t B, void* scratch, lip_stream_t stream) {
+  LIP_REQUIRE(B <= 65535, "lip_cg_step: at most 65535 columns per call (grid.y limit), got %lld: split the batch", (long long)B);
   LIP_REQUIRE(x && r && p && Ap && gamma && thresh && active && iters && scratch && n > 0 && B > 0,
               "lip_cg_step: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -481,6 +486,7 @@ size_t lip_reorth_scratch_bytes(int64_t n, int64_t B, int64_t kmax) {
 
 int lip_reorth(const float* Q, int64_t ldq, int64_t kk, int64_t kmax, float* w, int64_t ldw, float* h_out,
                float* norm_out, int32_t passes, int64_t n, int64_t B, void* scratch, lip_stream_t stream) {
+  LIP_REQUIRE(B <= 65535, "lip_reorth: at most 65535 columns per call (grid.y limit), got %lld: split the batch", (long long)B);
   LIP_REQUIRE(Q && w && scratch && n > 0 && B > 0 && kk >= 0 && kk <= kmax && ldq >= n && ldw >= n,
               "lip_reorth: bad argument");
   LIP_REQUIRE(passes == 1 || passes == 2, "lip_reorth: passes must be 1 or 2");
@@ -525,6 +531,7 @@ int lip_reorth(const float* Q, int64_t ldq, int64_t kk, int64_t kmax, float* w, 
 
 int lip_basis_combine(const float* Q, int64_t ldq, int64_t kk, int64_t kmax, const float* c, int64_t ldc, float* out,
                       int64_t ldo, int64_t n, int64_t B, lip_stream_t stream) {
+  LIP_REQUIRE(B <= 65535, "lip_basis_combine: at most 65535 columns per call (grid.y limit), got %lld: split the batch", (long long)B);
   LIP_REQUIRE(Q && c && out && n > 0 && B > 0 && kk > 0 && kk <= kmax && ldq >= n && ldo >= n,
               "lip_basis_combine: bad argument");
   LIP_REQUIRE(kk * sizeof(float) <= 160 * 1024, "lip_basis_combine: basis too deep");

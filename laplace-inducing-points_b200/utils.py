@@ -163,11 +163,17 @@ def _latest(ckpt_dir, prefix):
 
 
 def save_checkpoint(train_state, ckpt_dir, prefix, step):
-    """utils.py:46-60: `<ckpt_dir>/<prefix>_<step>`; older steps of the same prefix are removed (flax keep=1, overwrite=True)."""
+    """utils.py:46-60: `<ckpt_dir>/<prefix>_<step>`; older steps of the same prefix are removed (flax keep=1, overwrite=True).
+    The reference serialises the WHOLE flax TrainState (step, params, opt_state, batch_stats) and restores it with
+    target=TrainState, which raises on a missing field: `opt_state` is therefore written whenever the state carries one (any
+    nested dict / list / tuple of arrays; tuples and lists become flax's {'0': ..., '1': ...} index dicts).  A state without an
+    optimiser (the evaluation-side TrainState of this package) writes an empty opt_state, which flax restores only into a target
+    whose opt_state is empty as well — such files are for this package's load_checkpoint and for target=None readers."""
     import os
     ckpt_dir = os.path.abspath(ckpt_dir)
     os.makedirs(ckpt_dir, exist_ok=True)
     sd = {"step": int(step), "params": _to_numpy_tree(train_state.params),
+          "opt_state": _to_numpy_tree(getattr(train_state, "opt_state", None) or {}),
           "batch_stats": _to_numpy_tree(getattr(train_state, "batch_stats", {}) or {})}
     old = _latest(ckpt_dir, prefix + "_")
     path = os.path.join(ckpt_dir, f"{prefix}_{step}")
@@ -192,12 +198,21 @@ def load_checkpoint(ckpt_dir, prefix, target=None):
         return sd
     params = _restore_like(target.params, sd["params"], "params")
     bs = _restore_like(getattr(target, "batch_stats", {}) or {}, sd.get("batch_stats", {}) or {}, "batch_stats")
-    return dataclasses.replace(target, params=params, batch_stats=bs)
+    fields = {"params": params, "batch_stats": bs}
+    if getattr(target, "opt_state", None) and sd.get("opt_state"):
+        fields["opt_state"] = _restore_like(_to_numpy_tree(target.opt_state), sd["opt_state"], "opt_state")
+    return dataclasses.replace(target, **{k: v for k, v in fields.items() if hasattr(target, k)})
 
 
 def _to_numpy_tree(t):
     if isinstance(t, dict):
         return {str(k): _to_numpy_tree(v) for k, v in t.items()}
+    if isinstance(t, (list, tuple)):                  # flax.serialization: sequences are dicts keyed by their index
+        if hasattr(t, "_asdict"):
+            return {str(k): _to_numpy_tree(v) for k, v in t._asdict().items()}
+        return {str(i): _to_numpy_tree(v) for i, v in enumerate(t)}
+    if t is None:
+        return {}
     if isinstance(t, torch.Tensor):
         return t.detach().cpu().numpy()
     return np.asarray(t)
@@ -210,6 +225,8 @@ def _restore_like(like, loaded, where):
                              f"do not match the target's {sorted(map(str, like))}")
         return {k: _restore_like(v, loaded[str(k)], f"{where}/{k}") for k, v in like.items()}
     arr = np.asarray(loaded)
+    if arr.size == 1 and int(np.size(like)) == 1:
+        arr = arr.reshape(np.shape(like))              # 0-d leaves (optimizer step counts) come back as one-element arrays
     if tuple(arr.shape) != tuple(np.shape(like)):
         raise ValueError(f"checkpoint {where}: shape {tuple(arr.shape)} does not match the target's {tuple(np.shape(like))}")
     return arr

@@ -64,3 +64,35 @@ def test_array_checkpoint_round_trip(tmp_path):
     np.testing.assert_array_equal(U.load_array_checkpoint(tmp_path, "ip_mnist", 40, device="cpu"), Z)
     with pytest.raises(FileNotFoundError):
         U.load_array_checkpoint(tmp_path, "ip_mnist", 41, device="cpu")
+
+
+def test_full_train_state_with_opt_state_round_trips(tmp_path):
+    """the reference saves the WHOLE flax TrainState (utils.py:46-60), opt_state included; flax's from_state_dict with
+    target=TrainState raises on a file without it.  A state shaped like optax's adam (a tuple of (ScaleByAdamState(count, mu, nu),
+    EmptyState())) is written in flax's index-keyed layout and restored."""
+    import collections
+    import dataclasses
+    U = _utils()
+    rng = np.random.default_rng(2)
+    params = {"Dense_0": {"bias": rng.standard_normal(3).astype(np.float32), "kernel": rng.standard_normal((2, 3)).astype(np.float32)}}
+    Adam = collections.namedtuple("ScaleByAdamState", ["count", "mu", "nu"])
+    zeros = {"Dense_0": {"bias": np.zeros(3, np.float32), "kernel": np.zeros((2, 3), np.float32)}}
+    opt = (Adam(np.int32(5), {k: {kk: vv + 1 for kk, vv in v.items()} for k, v in zeros.items()}, zeros), ())
+
+    @dataclasses.dataclass
+    class FullState:
+        params: dict
+        opt_state: tuple
+        batch_stats: dict
+        step: int = 0
+
+    st = FullState(params=params, opt_state=opt, batch_stats={})
+    U.save_checkpoint(st, tmp_path, "map_full", 9)
+    raw = U.load_checkpoint(tmp_path, "map_full")
+    assert set(raw) == {"step", "params", "opt_state", "batch_stats"}
+    assert set(raw["opt_state"]) == {"0", "1"} and set(raw["opt_state"]["0"]) == {"count", "mu", "nu"}
+    assert raw["opt_state"]["0"]["count"] == 5
+    np.testing.assert_array_equal(raw["opt_state"]["0"]["mu"]["Dense_0"]["bias"], np.ones(3, np.float32))
+    got = U.load_checkpoint(tmp_path, "map_full", target=st)
+    np.testing.assert_array_equal(got.params["Dense_0"]["kernel"], params["Dense_0"]["kernel"])
+    np.testing.assert_array_equal(got.opt_state["0"]["mu"]["Dense_0"]["kernel"], np.ones((2, 3), np.float32))

@@ -103,3 +103,38 @@ def test_batch_nll_and_eval_dataset_match_oracle():
     assert abs(nll_d - tot_nll) < 1e-6 and abs(acc_d - tot_acc) < 1e-9          # same keys -> same samples
     auc = ev.auroc_ood(lst, probs, [(cu(10.0 + batches[1][0]), None)], cu(Z), alpha, N, "classifier", 16, rng=3)
     assert 0.0 <= auc <= 1.0
+
+
+@pytest.mark.gpu
+def test_numpy_batch_generator_never_hits_a_stale_bound_model():
+    """the bind cache used to key non-torch inputs on id(Z); CPython recycles ids, so a generator that yields
+    numpy batches alternates between two ids and batch i+2 was scored with the logits of batch i.  Only torch tensors are cached
+    now (identity + version counter); numpy batches are bound afresh.  Checked on the model outputs and through eval_dataset."""
+    import torch
+    from lip_b200 import evaluate as ev, ggn
+    from test_gpu_parity import _setup
+    ost, lst, Z, _, _ = _setup("C2_xor")
+    Z = Z[:12]
+    rng = np.random.default_rng(5)
+    data = [rng.standard_normal((7, 2)).astype(np.float32) * (1 + i) for i in range(6)]
+
+    def gen():
+        for a in data:
+            yield a.copy()                   # a fresh temporary every time: ids recycle
+
+    for i, xb in enumerate(gen()):
+        bm = ggn._bind(lst, xb, "classifier")
+        assert rel_err(bm.outputs().cpu().numpy(), O.model_outputs(ost, data[i])) < 2e-6, i
+    # in-place edits of a torch tensor invalidate its entry
+    zt = torch.as_tensor(data[0], device="cuda").clone()
+    o1 = ggn._bind(lst, zt, "classifier").outputs().clone()
+    assert ggn._bind(lst, zt, "classifier") is ggn._bind(lst, zt, "classifier")
+    zt.mul_(3.0)
+    o2 = ggn._bind(lst, zt, "classifier").outputs()
+    assert rel_err(o2.cpu().numpy(), O.model_outputs(ost, 3.0 * data[0])) < 2e-6 and not torch.allclose(o1, o2)
+    # the dataset loop over numpy batches: per-batch NLL pieces equal the ones computed from CUDA tensors held in a list
+    labels = [rng.integers(0, 2, size=(7, 1)) for _ in data]
+    cu = lambda a: torch.as_tensor(a, device="cuda")
+    nll_np, acc_np = ev.eval_dataset(lst, ((a.copy(), b) for a, b in zip(data, labels)), cu(Z), 2.5, 800, "classifier", 32, rng=7)
+    nll_t, acc_t = ev.eval_dataset(lst, [(cu(a), cu(b)) for a, b in zip(data, labels)], cu(Z), 2.5, 800, "classifier", 32, rng=7)
+    assert abs(nll_np - nll_t) <= 1e-6 * abs(nll_t) and abs(acc_np - acc_t) < 1e-9

