@@ -117,13 +117,18 @@ def zgrad_sharded(zgrad_fn: Callable, cotangents: torch.Tensor, vectors: torch.T
 
 
 # ---------------------------------------------------------------------------------------------- Krylov-basis (D) sharding
-def group_layout(world_size: int, num_probes: int) -> Tuple[int, int]:
-    """(P, S): P probe groups of S ranks each, P * S = world_size.  Probes are the free axis (no communication at all), so P is the
-    largest divisor of world_size that does not exceed the probe count; the S ranks of a group share every Krylov vector of the
-    group's probes column-wise (lip_slq_quadrature_sharded).  4 probes on 8 GPUs -> (4, 2); on 2 GPUs -> (2, 1)."""
+def group_layout(world_size: int, num_probes: int, probes_per_group: int = 1) -> Tuple[int, int]:
+    """(P, S): P probe groups of S ranks each, P * S = world_size.  Inside a group the S ranks share every Krylov vector of the
+    group's probes column-wise (lip_slq_quadrature_sharded); across groups nothing is communicated.  Probes are the free axis, so P is
+    the largest divisor of world_size that leaves every group at least `probes_per_group` probes: 4 probes on 1 / 2 / 4 / 8 GPUs ->
+    (1, 1), (2, 1), (4, 1), (4, 2).  (probes_per_group = 2 with pipelines = 2 in slq_logdet_hybrid runs two recurrences per GPU on two
+    streams; measured on 2 x B200 it does not pay — 1.17 s against 0.92 s for the k = 409 logdet: the tcgen05 GEMM CTAs of one
+    pipeline cannot share an SM with the basis kernels of the other (shared memory), and two host threads contend for the launch path —
+    profiles/r02_dist_slq_2gpu.txt.)"""
     if world_size < 1 or num_probes < 1:
         raise ValueError(f"bad layout request: world_size={world_size} num_probes={num_probes}")
-    P = max(p for p in range(1, world_size + 1) if world_size % p == 0 and p <= num_probes)
+    want = max(1, num_probes // max(1, probes_per_group))
+    P = max(p for p in range(1, world_size + 1) if world_size % p == 0 and p <= want)
     return P, world_size // P
 
 
@@ -137,16 +142,18 @@ class NativeComm:
 _NATIVE_COMMS = {}
 
 
-def native_comms(shard_size: int) -> Optional[NativeComm]:
+def native_comms(shard_size: int, slot: int = 0) -> Optional[NativeComm]:
     """Collective over the default group: partitions the ranks into consecutive blocks of `shard_size` and returns this rank's
-    lip_comm (None when shard_size == 1).  The leaders' NCCL unique ids travel in one all-gather of 128 bytes per rank."""
+    lip_comm (None when shard_size == 1).  The leaders' NCCL unique ids travel in one all-gather of 128 bytes per rank.
+    `slot` distinguishes independent communicators over the same ranks (one per concurrent stream: operations on ONE NCCL
+    communicator must be enqueued in the same order on every rank, which two host threads cannot promise each other)."""
     rank, ws = world()
     if shard_size <= 1 or ws == 1:
         return None
     if ws % shard_size:
         raise ValueError(f"native_comms: shard_size={shard_size} does not divide world_size={ws}")
-    if shard_size in _NATIVE_COMMS:
-        return _NATIVE_COMMS[shard_size]
+    if (shard_size, slot) in _NATIVE_COMMS:
+        return _NATIVE_COMMS[(shard_size, slot)]
     import ctypes
     from . import _cabi as cabi
     L = cabi.lib()
@@ -162,25 +169,78 @@ def native_comms(shard_size: int) -> Optional[NativeComm]:
     h = ctypes.c_void_p()
     cabi.check(L.lip_comm_create(idb, shard_size, rank - leader, ctypes.byref(h)), "lip_comm_create")
     comm = NativeComm(h, shard_size, rank - leader)
-    _NATIVE_COMMS[shard_size] = comm
+    _NATIVE_COMMS[(shard_size, slot)] = comm
     return comm
 
 
-def slq_logdet_hybrid(matvec, probes: torch.Tensor, num_matvecs: int, *, form="gkl", fn="log", clip_min=None) -> torch.Tensor:
+_PIPELINE_MODELS = {}
+
+
+def _second_model(bm):
+    """BoundModel.clone() of `bm`, cached for as long as `bm` lives (weak on the original)."""
+    import weakref
+    hit = _PIPELINE_MODELS.get(id(bm))
+    if hit is not None and hit[0]() is bm:
+        return hit[1]
+    clone = bm.clone()
+    _PIPELINE_MODELS[id(bm)] = (weakref.ref(bm), clone)
+    if len(_PIPELINE_MODELS) > 4:
+        _PIPELINE_MODELS.pop(next(iter(_PIPELINE_MODELS)))
+    return clone
+
+
+def slq_logdet_hybrid(matvec, probes: torch.Tensor, num_matvecs: int, *, form="gkl", fn="log", clip_min=None,
+                      pipelines: int = 1) -> torch.Tensor:
     """mean_b |v_b|^2 e1^T f(T_b) e1 over ALL probe rows (matfree.stochtrace.estimator of an SLQ integrand, train_inducing.py:156-163)
-    on every GPU of the job: probes first (independent recurrences), then — when there are more GPUs than probes — the Krylov
-    bases of each probe are cut column-wise over the ranks of its group.  `probes` is the full [B, n] matrix, identical on every
-    rank.  One all-reduce of a float64 accumulator ends the call."""
+    on every GPU of the job.  Layout (group_layout): probes over groups of ranks; inside a group the Krylov bases are cut column-wise.
+    pipelines = 2 (experimental, off by default: see group_layout) runs a rank's probes as two concurrent recurrences — two host
+    threads, two CUDA streams, two model handles (BoundModel.clone), two communicators.  `probes` is the full [B, n] matrix, identical on every rank.  One all-reduce of a float64
+    accumulator ends the call."""
+    import threading
     from . import matfree
     rank, ws = world()
     B = probes.shape[0]
     P, S = group_layout(ws, B)
-    comm = native_comms(S)
     g = rank // S
     mine = probes[probe_slice(B, g, P)]
+    nmine = int(mine.shape[0])
+    npipe = max(1, min(int(pipelines), nmine)) if getattr(matvec, "_lip_model", None) is not None else 1
+    comms = [native_comms(S, slot) for slot in range(npipe)]             # collective: every rank creates the same set, in order
     acc = torch.zeros(1, dtype=torch.float64, device=probes.device)
-    if mine.shape[0] > 0:
-        q = matfree.slq_quadrature(matvec, mine, num_matvecs, form=form, fn=fn, clip_min=clip_min, comm=comm)
+    if nmine > 0:
+        if npipe == 1:
+            q = matfree.slq_quadrature(matvec, mine, num_matvecs, form=form, fn=fn, clip_min=clip_min, comm=comms[0])
+        else:
+            dev = probes.device
+            main = torch.cuda.current_stream(dev)
+            parts = [mine[probe_slice(nmine, i, npipe)] for i in range(npipe)]
+            models = [None] + [_second_model(matvec._lip_model) for _ in range(npipe - 1)]
+            if npipe > 2:
+                models = [None] + [matvec._lip_model.clone() for _ in range(npipe - 1)]
+            streams = [torch.cuda.Stream(device=dev) for _ in range(npipe)]
+            out, errs = [None] * npipe, [None] * npipe
+
+            def run(i):
+                try:
+                    torch.cuda.set_device(dev)                              # the CUDA current device is per host thread
+                    with torch.cuda.stream(streams[i]):
+                        streams[i].wait_stream(main)
+                        out[i] = matfree.slq_quadrature(matvec, parts[i], num_matvecs, form=form, fn=fn, clip_min=clip_min,
+                                                        comm=comms[i], model=models[i])
+                except BaseException as e:                                   # noqa: BLE001
+                    errs[i] = e
+
+            threads = [threading.Thread(target=run, args=(i,)) for i in range(npipe)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            for e in errs:
+                if e is not None:
+                    raise e
+            for s_ in streams:
+                main.wait_stream(s_)
+            q = torch.cat(out)
         if rank % S == 0:                       # every rank of a group holds the same values: the leader contributes them
             acc += q.double().sum()
     allreduce_sum_(acc)

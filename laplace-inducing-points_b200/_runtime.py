@@ -251,6 +251,7 @@ class BoundModel:
         if self.theta.numel() != spec.num_params:
             raise ValueError(f"flat parameter vector has {self.theta.numel()} entries, architecture needs {spec.num_params}")
         Zf = dev_f32(Z, self.device)
+        self._Z_src, self._tensor_path = Zf, tensor_path
         self.M = int(Zf.shape[0])
         self.Z = Zf.reshape(self.M, -1)
         in_features = spec.in_features if hasattr(spec, "in_features") else spec.dims[0]
@@ -276,6 +277,11 @@ class BoundModel:
                    "lip_model_bind")
         self._ws = Scratch()
         self.launches = 0
+
+    def clone(self) -> "BoundModel":
+        """A second, independent handle bound to the same weights and points (its own activation cache, flags and side stream):
+        what a second host thread / CUDA stream needs to run the operators concurrently with this one."""
+        return BoundModel(self.spec, self.theta, self._Z_src, self.logvar, self._tensor_path)
 
     def tensor_layers(self) -> int:
         """Number of layers / conv units whose GEMMs run on the tcgen05 path (0 = everything on the fp32 SIMT kernels)."""

@@ -60,19 +60,19 @@ class _NativeOp:
     anything else is wrapped as LIP_LINOP_CALLBACK: the recurrence still runs inside ONE native call and the library calls back
     into Python for the mat-vec only."""
 
-    def __init__(self, Av, vA, B, n_in, n_out, single, symmetric):
+    def __init__(self, Av, vA, B, n_in, n_out, single, symmetric, model=None):
         self.struct = cabi.LinOp()
         self.exc = None
         self.keep = []
         kind = getattr(Av, "_lip_kind", None)
         native = getattr(Av, "_lip_native", True) and getattr(Av, "_lip_model", None) is not None
         if kind == "GGN" and native and symmetric:
-            bm = Av._lip_model
+            bm = model if model is not None else Av._lip_model
             self.struct.kind, self.struct.model = cabi.LINOP_GGN, bm._h
             self.struct.scale, self.struct.alpha = float(Av._lip_recal), float(Av._lip_alpha)
             self.keep.append(bm)
         elif kind == "GKL" and native and not symmetric:
-            bm = Av._lip_model
+            bm = model if model is not None else Av._lip_model
             self.struct.kind, self.struct.model = cabi.LINOP_GKL, bm._h
             self.struct.scale, self.struct.alpha = float(Av._lip_scale), float(Av._lip_alpha)
             self.keep.append(bm)
@@ -392,11 +392,12 @@ def integrand_funm_product_logdet(bidiag):
     return batched(quadform)
 
 
-def slq_quadrature(matvec, probes, num_matvecs, *, form="gkl", fn="log", clip_min=None, comm=None):
+def slq_quadrature(matvec, probes, num_matvecs, *, form="gkl", fn="log", clip_min=None, comm=None, model=None):
     """The fused native SLQ integrand (lip_slq_quadrature / lip_slq_quadrature_sharded): per-probe |v|^2 e1^T f(T) e1, [B].
     form "gkl": matvec is a gkl_target closure (integrand_funm_product_logdet, train_inducing.py:156-157);
     form "lanczos": a symmetric closure (integrand_funm_sym; fn="log", clip_min=1.0 is the patched integrand_funm_sym_logdet).
-    comm: a _dist.NativeComm whose ranks share the Krylov bases column-wise (every rank passes the same probes)."""
+    comm: a _dist.NativeComm whose ranks share the Krylov bases column-wise (every rank passes the same probes).
+    model: a BoundModel.clone() to run on instead of the closure's own handle (a second concurrent stream needs its own)."""
     L = cabi.lib()
     P, single = _as2d(probes)
     P = P.contiguous()
@@ -411,7 +412,7 @@ def slq_quadrature(matvec, probes, num_matvecs, *, form="gkl", fn="log", clip_mi
         if bm is None or getattr(matvec, "_lip_kind", None) != "GKL":
             raise ValueError("slq_quadrature(form='gkl') needs a matfree.gkl_target closure")
         nout = bm.D + bm.M * bm.K
-    op = _NativeOp(matvec, getattr(matvec, "_lip_transpose", None), nb, n, nout, single, symmetric=sym)
+    op = _NativeOp(matvec, getattr(matvec, "_lip_transpose", None), nb, n, nout, single, symmetric=sym, model=model)
     world = 1 if comm is None else comm.world
     if world > 1 and op.struct.kind not in (cabi.LINOP_GGN, cabi.LINOP_GKL):
         raise ValueError("sharded slq_quadrature needs one of this package's model closures (curvature_vp / gkl_target)")

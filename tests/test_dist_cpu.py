@@ -175,7 +175,8 @@ def test_group_layout_prefers_probe_groups():
     assert _dist.group_layout(8, 4) == (4, 2)          # BASELINE's SLQ case: 4 probes on 8 GPUs -> pairs share a probe's bases
     assert _dist.group_layout(8, 1) == (1, 8)
     assert _dist.group_layout(8, 3) == (2, 4)
-    assert _dist.group_layout(6, 4) == (3, 2)
+    assert _dist.group_layout(8, 16) == (8, 1)
+    assert _dist.group_layout(8, 4, probes_per_group=2) == (2, 4)
     for ws in range(1, 17):
         for B in range(1, 9):
             P, S = _dist.group_layout(ws, B)
@@ -192,11 +193,11 @@ def _hybrid_worker(rank, ws, port, B, force_S, out):
     probes = torch.randn(B, 17, generator=g)
     seen = {}
 
-    def fake_quadrature(matvec, mine, k, *, form, fn, clip_min, comm):          # CPU stand-in for the native recurrence
+    def fake_quadrature(matvec, mine, k, *, form, fn, clip_min, comm, model=None):     # CPU stand-in for the native recurrence
         seen["rows"], seen["comm"] = mine.clone(), comm
         return (mine ** 2).sum(1) * k
 
-    def fake_comms(S):
+    def fake_comms(S, slot=0):
         return None if S == 1 else _dist.NativeComm(None, S, rank % S)
 
     matfree.slq_quadrature, _dist.native_comms = fake_quadrature, fake_comms
@@ -214,8 +215,8 @@ def _hybrid_worker(rank, ws, port, B, force_S, out):
 
 @pytest.mark.parametrize("B,force_S", [(4, 0), (1, 0), (3, 2)])
 def test_hybrid_slq_layout_world_size_2_gloo(B, force_S):
-    """world_size 2: (B=4 -> two probe groups, no basis sharding), (B=1 -> one group of two ranks sharing the probe's bases),
-    (B=3 forced into one 2-rank group): every probe is evaluated by exactly one group, group members see the same rows, only the
+    """world_size 2: (B=4 -> two probe groups, no basis sharding), (B=1 -> one group of two ranks sharing the probe's
+    bases), (B=3 forced into one 2-rank group): every probe is evaluated by exactly one group, group members see the same rows, only the
     group leader contributes to the all-reduced mean."""
     ws = 2
     out = mp.get_context("spawn").Manager().dict()

@@ -23,8 +23,20 @@ probes = torch.randint(0, 2, (4, D), generator=g, device=dev, dtype=torch.int8).
 comm = _dist.native_comms(ws)
 def say(*a):
     if rank == 0: print(*a, flush=True)
+class _NoDist:
+    @staticmethod
+    def barrier(): pass
+    @staticmethod
+    def all_reduce(*a, **k): pass
+    @staticmethod
+    def all_gather(lst, t): lst[0].copy_(t)
+    @staticmethod
+    def destroy_process_group(): pass
+    ReduceOp = dist.ReduceOp
+if ws == 1:
+    dist = _NoDist
 for form, op, clip in (("gkl", Av, None), ("lanczos", cvp, 1.0)):
-    for k in (8, 48):
+    for k in (8, 48) if ws > 1 else ():
         ref = matfree.slq_quadrature(op, probes[:2], k, form=form, clip_min=clip)
         got = matfree.slq_quadrature(op, probes[:2], k, form=form, clip_min=clip, comm=comm)
         rel = ((got - ref).abs() / ref.abs()).max().item()
@@ -65,7 +77,13 @@ for form, op, clip in (("gkl", Av, None), ("lanczos", cvp, 1.0)):
         est = _dist.slq_logdet_hybrid(op, probes, 409, form=form, clip_min=clip)
         torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    say(f"C3b {form} logdet k=409, 4 probes on {ws} GPUs (layout {_dist.group_layout(ws, 4)}): {dt.item():.3f} s, estimate {est.item():.8g}")
+    say(f"C3b {form} logdet k=409, 4 probes on {ws} GPUs (layout {_dist.group_layout(ws, 4)}, 2 pipelines): {dt.item():.3f} s, estimate {est.item():.8g}")
+    for rep in range(2):
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        est = _dist.slq_logdet_hybrid(op, probes, 409, form=form, clip_min=clip, pipelines=1)
+        torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    say(f"C3b {form} logdet k=409, 4 probes on {ws} GPUs (same layout, 1 pipeline): {dt.item():.3f} s, estimate {est.item():.8g}")
 if ws >= 2:
     # all ranks on ONE probe: pure basis sharding
     for rep in range(2):
