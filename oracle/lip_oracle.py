@@ -10,12 +10,19 @@ PARITY PINNING
     G3 (tests/fixtures.py:201-209 traces 6 / 3894, hutchpp_v2 exact for s1>=n, tests/test_stochtrace.py:90-97),
     G4 identities (vmap(ggn_vp)(I)==dense GGN, W(W^T(I))==GGN, L L^T==diag(p)-pp^T, null-space projector).
     See tests/test_oracle_golden.py.
-  * PARITY UNPINNED: matfree (requirements.txt:5, no version pin, source absent from /root/reference and
-    not installed) and jax (absent).  `tridiag_sym`, `bidiag`, `funm_lanczos_sym`, `integrand_funm_*`,
-    `estimator` and `cg` below restate the published algorithms of matfree>=0.1 / jax.scipy.sparse.linalg.cg
-    from memory; only the mathematics (not the rounding order) is anchored, through G2 and through
-    dense-linear-algebra cross checks in tests/.  No reference test touches decomp.bidiag +
-    integrand_funm_product_logdet or the clip(min=1.0) of matfree_monkeypatch.py:19.
+  * PARITY UNPINNED (against the third-party SOURCES): matfree (requirements.txt:5, no version pin, source absent from
+    /root/reference and not installed) and jax (absent).  `tridiag_sym`, `bidiag`, `funm_lanczos_sym`, `integrand_funm_*`,
+    `estimator` and `cg` below restate the published algorithms of matfree>=0.1 / jax.scipy.sparse.linalg.cg from memory.
+    No reference test touches decomp.bidiag + integrand_funm_product_logdet or the clip(min=1.0) of matfree_monkeypatch.py:19.
+  * What IS pinned for them (round 2): the mathematics, per probe, against an INDEPENDENT dense ground truth on the reference's own
+    operators — explicit Jacobians -> W -> float64 eigen-decomposition of alpha I + beta W W^T:
+      tests/test_oracle_golden.py::test_slq_integrands_on_the_model_operators_equal_dense_quadratic_forms   (1e-9, small model)
+      tests/golden/configs_v2.npz `c3a_dense_*` (C3a at its own size, M = 512, k = 409; checked here to 1e-13 while generating and
+      against the CUDA path in tests/test_gpu_config_parity.py), and G2.
+    What stays unpinned is matfree's / JAX's rounding ORDER — irrelevant at the 1e-4 tolerance wherever the quadrature is converged,
+    and the reason unconverged clipped-Lanczos quadratures are compared at 5e-4 (see the C3b test).
+  * `cg(..., dtype=np.float32)` runs the same recurrence in the reference's production precision: the yardstick for operators whose
+    condition number exceeds 1 / eps_fp32 (C2: 2e6), where no fp32 CG — JAX's included — reaches tol = 1e-5.
 """
 from __future__ import annotations
 
