@@ -180,4 +180,8 @@ int resnet_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float s
                     cudaStream_t st);
 int resnet_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,
                    float add_scale, void* ws, size_t bytes, cudaStream_t st);
+// gradients with respect to Z for residual programs (lip_resnet.cu)
+size_t resnet_zgrad_ws_bytes(const lip_model* m, int32_t mode, int64_t B);
+int resnet_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, float* out, int64_t B, float scale, int32_t per_probe,
+                 void* ws, size_t bytes, cudaStream_t st);
 }  // namespace lip

@@ -15,6 +15,8 @@
 // Tangents / cotangents live in four rotating [B, M, H, W, C] slots (block input, branch, shortcut, block output).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <new>
 #include <vector>
 
@@ -219,6 +221,35 @@ __global__ void global_mean_bwd_kernel(const float* __restrict__ g, float* __res
     const long long mz = idx / ((long long)HW * C);
     const int c = (int)(idx % C);
     out[idx] = inv * __ldg(g + mz * C + c);
+  }
+}
+
+// ---- gradients with respect to the input images Z (lip_zgrad for residual programs) ---------------------------------
+// One unit's step of the reverse pass (see resnet_zgrad):  ebar = mask * E,  qbar = mask * Q;  skip cotangents stored;
+//   rawE = g * ebar;   rawQ = g * qbar + rstd * dscale[b] * ebar      (the BatchNorm-scale tangent x xhat(Z) term)
+__global__ void rn_zgrad_bn_kernel(const float* __restrict__ E, const float* __restrict__ Q, const float* __restrict__ mask,
+                                   const float* __restrict__ g, const float* __restrict__ var, const float* __restrict__ dscale,
+                                   long long pstride, float* __restrict__ eskip, float* __restrict__ qskip, float* __restrict__ rawE,
+                                   float* __restrict__ rawQ, long long total, long long per_z, int C) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long z = idx / per_z, i = idx % per_z;
+    const int c = (int)(i % C);
+    float e = E[idx], q = Q[idx];
+    if (mask) { const float mk = __ldg(mask + i); e *= mk; q *= mk; }
+    if (eskip) { eskip[idx] = e; qskip[idx] = q; }
+    const float gc = __ldg(g + c);
+    rawE[idx] = gc * e;
+    rawQ[idx] = fmaf(gc, q, rsqrtf(__ldg(var + c) + BN_EPS) * __ldg(dscale + z * pstride + c) * e);
+  }
+}
+// per-probe re-lay of the tangent kernels for the transposed conv: Wt[b][(tap*cout + co)*cin + ci] = V[b][woff + (tap*cin + ci)*cout + co]
+__global__ void conv_wt_batched_kernel(const float* __restrict__ V, long long vstride, float* __restrict__ Wt, int taps, int cin, int cout) {
+  const int total = taps * cin * cout;
+  const float* W = V + (long long)blockIdx.y * vstride;
+  float* o = Wt + (long long)blockIdx.y * total;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ci = idx % cin, t = idx / cin, co = t % cout, tap = t / cout;
+    o[idx] = W[(tap * cin + ci) * cout + co];
   }
 }
 
@@ -730,6 +761,151 @@ int resnet_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float s
   if (factor == LIP_FACTOR_SQRT && m->model_type == LIP_CLASSIFIER) return launch_factor(out, out, m, B, 1, s, st);
   if (s != 1.f) return launch_scale_copy(out, out, B * m->M * m->K, s, st);
   return LIP_OK;
+}
+
+// ---- lip_zgrad for residual programs ---------------------------------------------------------------------------------------------
+// The network is piecewise linear in its activations (relu, BatchNorm in eval mode, convs, adds, mean), so the recurrences of
+// lip_zgrad.cu need no second derivative and no stored tangent; what is new against the plain conv stage programs (lip_cnn.cu) is
+//   * the BatchNorm SCALE tangent: dY contains xhat(Z) * dscale[b], and xhat = rstd * (conv(x, W) - mean) depends on Z, which adds
+//     rstd * dscale[b] * ebar to the cotangent that travels back through the shared kernel;
+//   * skip connections: both cotangent families (e = d s / d tangent-activation, q = d s / d activation) follow the slot rotation
+//     of rn_vjp_sweep (block input, branch, shortcut, output).
+// Per unit, in reverse order:   ebar = mask * e_out,  qbar = mask * q_out,  (e, q)[skip] <- (ebar, qbar)
+//     e[src] (+)= convT(g * ebar, W)
+//     q[src] (+)= convT(g * qbar + rstd * dscale[b] * ebar, W) + convT(g * ebar, dW[b])          (one dual-K implicit GEMM)
+// and at the stem dZ[b] = q[input].  All GEMMs are the fp32 SIMT implicit GEMMs (transposed-conv gather, ConvGather mode 3).
+struct RnZSizes { size_t inner, slot, raw, wt, head, small, fin, sum, total; };
+
+static RnZSizes rn_zsizes(const lip_model* m, int nseg, int64_t B) {
+  RnZSizes z{};
+  const RnSizes r = rn_sizes(m, B);
+  z.inner = align_up(resnet_ws_bytes(m, B), 256);
+  z.slot = r.slot;
+  z.raw = r.raw;
+  size_t wt = 0;
+  for (const ConvBN& u : m->RB) { const size_t v = (size_t)B * u.Kc() * u.cout; wt = v > wt ? v : wt; }
+  z.wt = align_up(wt, 64);
+  z.head = align_up((size_t)B * m->M * m->rn_C, 64);
+  z.small = align_up((size_t)nseg * B * m->M * m->K, 64);
+  z.fin = align_up((size_t)nseg * B * m->M * (size_t)m->in_h * m->in_w * m->in_c, 64);
+  z.sum = align_up((size_t)B * m->M * (size_t)m->in_h * m->in_w * m->in_c, 64);
+  z.total = z.inner + (4 * z.slot + z.raw + z.wt + z.head + 3 * z.small + z.fin + z.sum) * sizeof(float) + 1024;
+  return z;
+}
+
+size_t resnet_zgrad_ws_bytes(const lip_model* m, int32_t mode, int64_t B) {
+  return rn_zsizes(m, mode == LIP_ZGRAD_GGN ? 2 : 1, B).total;
+}
+
+int resnet_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, float* out, int64_t B, float scale, int32_t per_probe,
+                 void* ws, size_t bytes, cudaStream_t st) {
+  const int nseg = mode == LIP_ZGRAD_GGN ? 2 : 1;
+  const RnZSizes z = rn_zsizes(m, nseg, B);
+  if (!ws || bytes < z.total) {
+    set_error("lip_zgrad: workspace too small: need %zu bytes, got %zu", z.total, bytes);
+    return LIP_ERR_WORKSPACE;
+  }
+  RnWs w;
+  int rc = rn_carve(m, B, ws, z.inner, &w);
+  if (rc) return rc;
+  float* p = (float*)align_up((uintptr_t)ws + z.inner, 256);
+  float* Qs[4];
+  for (int i = 0; i < 4; ++i) { Qs[i] = p; p += z.slot; }
+  float* rawQ = p; p += z.raw;
+  float* wtb = p; p += z.wt;
+  float* qhead = p; p += z.head;
+  float* dl = p; p += z.small;
+  float* Cc = p; p += z.small;
+  float* Gf = p; p += z.small;
+  float* fin = p; p += z.fin;
+  float* sum = p;
+  float** Es = w.slot;
+  float* rawE = w.raw;
+  const float* Vseg[2] = {X1, mode == LIP_ZGRAD_GGN ? X2 : nullptr};
+  const int64_t M = m->M;
+  const int64_t small_seg = B * M * m->K;
+  const int HW = m->rn_H * m->rn_W, C = m->rn_C;
+  const int64_t img = (int64_t)m->in_h * m->in_w * m->in_c;
+
+  for (int sg = 0; sg < nseg; ++sg) {   // forward tangent pass: only the tangent logits are needed
+    rc = rn_jvp_sweep(m, Vseg[sg], B, w, dl + sg * small_seg, st);
+    if (rc) return rc;
+  }
+  rc = launch_zgrad_rows(mode, m, dl, X2, Cc, Gf, B, scale, st);
+  if (rc) return rc;
+
+  for (int sg = 0; sg < nseg; ++sg) {
+    const float* V = Vseg[sg];
+    const float* c_rows = Cc + sg * small_seg;
+    const float* g_rows = Gf + sg * small_seg;
+    {  // head: e_mean = c Wd^T,  q_mean = c dWd[b]^T + g Wd^T, then back through the global mean
+      GemmProblem e;
+      e.M = M; e.N = C; e.K = m->K; e.batch = B;
+      e.A1 = {c_rows, M * (int64_t)m->K, m->K, 1};
+      e.B1 = {m->theta + m->rn_dense_woff, 0, 1, m->K};
+      e.C = w.head; e.c_sz = M * (int64_t)C; e.c_sm = C;
+      rc = gemm_simt(e, st);
+      if (rc) return rc;
+      GemmProblem q;
+      q.M = M; q.N = C; q.K = m->K; q.batch = B;
+      q.A1 = {c_rows, M * (int64_t)m->K, m->K, 1};
+      q.B1 = {V + m->rn_dense_woff, m->D, 1, m->K};
+      q.A2 = {g_rows, M * (int64_t)m->K, m->K, 1};
+      q.B2 = {m->theta + m->rn_dense_woff, 0, 1, m->K};
+      q.K2 = m->K;
+      q.C = qhead; q.c_sz = M * (int64_t)C; q.c_sm = C;
+      rc = gemm_simt(q, st);
+      if (rc) return rc;
+      const long long total = (long long)B * M * HW * C;
+      global_mean_bwd_kernel<<<ew_grid(total), 256, 0, st>>>(w.head, Es[m->rn_last_slot], total, HW, C);
+      LIP_LAUNCH_CHECK();
+      global_mean_bwd_kernel<<<ew_grid(total), 256, 0, st>>>(qhead, Qs[m->rn_last_slot], total, HW, C);
+      LIP_LAUNCH_CHECK();
+    }
+    for (int i = (int)m->RB.size() - 1; i >= 0; --i) {
+      const ConvBN& u = m->RB[i];
+      const int64_t R = M * u.P(), Kc = u.Kc();
+      const long long per_z = R * (long long)u.cout, total = per_z * B;
+      rn_zgrad_bn_kernel<<<ew_grid(total), 256, 0, st>>>(Es[u.dst], Qs[u.dst], u.mask, u.g, m->rn_stats + u.stats_off + u.cout,
+                                                         V + u.scale_off, m->D, u.skip >= 0 ? Es[u.skip] : nullptr,
+                                                         u.skip >= 0 ? Qs[u.skip] : nullptr, rawE, rawQ, total, per_z, u.cout);
+      LIP_LAUNCH_CHECK();
+      {
+        const int tot = (int)(Kc * u.cout);
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div(tot, 256), 256), (unsigned)B);
+        conv_wt_batched_kernel<<<grid, 256, 0, st>>>(V + u.woff, m->D, wtb, u.kh * u.kw, u.cin, u.cout);
+        LIP_LAUNCH_CHECK();
+      }
+      const int64_t in_elems = M * (int64_t)u.Hi * u.Wi * u.cin;
+      if (u.src != -2) {   // e[src] (+)= convT(rawE, W)
+        GemmProblem e;
+        e.M = M * (int64_t)u.Hi * u.Wi; e.N = u.cin; e.K = (int64_t)u.kh * u.kw * u.cout; e.batch = B;
+        e.A1.ptr = rawE; e.A1.sz = per_z; e.A1.conv = u.gather(3);
+        e.B1 = {u.Wt, 0, u.cin, 1};
+        e.C = Es[u.src]; e.c_sz = in_elems; e.c_sm = u.cin;
+        if (u.accumulate) { e.epi.add = e.C; e.epi.add_sz = e.c_sz; e.epi.add_scale = 1.f; }
+        rc = gemm_simt(e, st);
+        if (rc) return rc;
+      }
+      GemmProblem q;       // q[src] (+)= convT(rawQ, W) + convT(rawE, dW[b])
+      q.M = M * (int64_t)u.Hi * u.Wi; q.N = u.cin; q.K = (int64_t)u.kh * u.kw * u.cout; q.batch = B;
+      q.A1.ptr = rawQ; q.A1.sz = per_z; q.A1.conv = u.gather(3);
+      q.B1 = {u.Wt, 0, u.cin, 1};
+      q.A2.ptr = rawE; q.A2.sz = per_z; q.A2.conv = u.gather(3);
+      q.B2 = {wtb, Kc * (int64_t)u.cout, u.cin, 1};
+      q.K2 = q.K;
+      q.C = (u.src == -2) ? fin + (int64_t)sg * B * M * img : Qs[u.src]; q.c_sz = in_elems; q.c_sm = u.cin;
+      if (u.src != -2 && u.accumulate) { q.epi.add = q.C; q.epi.add_sz = q.c_sz; q.epi.add_scale = 1.f; }
+      rc = gemm_simt(q, st);
+      if (rc) return rc;
+    }
+  }
+  // sum over probes (and, in GGN mode, over the two tangent families)
+  const int64_t per0 = M * img;
+  if (!per_probe) return launch_batch_sum(fin, out, per0, (int64_t)nseg * B, st);
+  if (nseg == 2) return launch_batch_sum(fin, out, B * per0, 2, st);
+  (void)sum;
+  return launch_scale_copy(fin, out, B * per0, 1.f, st);
 }
 
 int resnet_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,

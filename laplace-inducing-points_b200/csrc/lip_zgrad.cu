@@ -503,7 +503,8 @@ using namespace lip;
 extern "C" {
 
 size_t lip_zgrad_workspace_bytes(const lip_model* m, int32_t mode, int64_t B) {
-  if (!m || !m->bound || B <= 0 || m->is_resnet) return 0;
+  if (!m || !m->bound || B <= 0) return 0;
+  if (m->is_resnet) return resnet_zgrad_ws_bytes(m, mode, B);
   if (m->is_cnn) return cnn_zgrad_ws_bytes(m, mode, B);
   if (zg_tc_ok(m)) return zg_tc_sizes(m, B, mode == LIP_ZGRAD_GGN ? 2 : 1).total;
   return zg_bytes(m, mode == LIP_ZGRAD_GGN ? 2 * B : B);
@@ -514,11 +515,8 @@ int lip_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, floa
   LIP_REQUIRE(m && X1 && X2 && out && B > 0, "lip_zgrad: null argument or B <= 0");
   LIP_REQUIRE(mode >= LIP_ZGRAD_GGN && mode <= LIP_ZGRAD_JVP, "lip_zgrad: bad mode %d", mode);
   if (!m->bound) { set_error("lip_zgrad: model not bound"); return LIP_ERR_NOT_BOUND; }
-  if (m->is_resnet) {
-    set_error("lip_zgrad: gradients with respect to Z are built for dense programs and relu conv stage programs (residual programs: not yet)");
-    return LIP_ERR_UNSUPPORTED;
-  }
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->is_resnet) return resnet_zgrad(m, mode, X1, X2, out, B, scale, per_probe, workspace, workspace_bytes, st);
   if (m->is_cnn) return cnn_zgrad(m, mode, X1, X2, out, B, scale, per_probe, workspace, workspace_bytes, st);
   if (zg_tc_ok(m)) return zgrad_tc(m, mode, X1, X2, out, B, scale, per_probe, workspace, workspace_bytes, st);
   const int nL = (int)m->L.size();

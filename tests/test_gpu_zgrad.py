@@ -211,15 +211,33 @@ def test_lenet5_zgrad_matches_oracle():
     assert rel_err(WTf.zgrad(cu(Y), cu(V)).cpu().numpy().reshape(Z.shape), WTz_ref(Y, V)) < TOL
 
 
-def test_zgrad_rejects_residual_programs_and_bad_shapes():
+@pytest.mark.parametrize("shape,M", [((8, 8, 3), 3), ((32, 32, 3), 2)])
+def test_resnet1m_zgrad_matches_oracle(shape, M):
+    """lip_zgrad for residual programs (ResNet1M, src/scalemodels.py:70-157; round 2): d/dZ with respect to the input IMAGES through
+    convs, BatchNorm in eval mode (its scale tangent multiplies xhat(Z): the extra term of the q recurrence), skip connections, the 1x1
+    strided shortcuts, the global mean and the head — against torch.func.grad through the oracle's float64 restatement of ggn.py."""
     from lip_b200 import ggn
-    from lip_b200._cabi import LipError
-    ost, lst = make_pair("resnet1m", n_out=10, in_shape=(8, 8, 3), seed=1)
-    Z = np.random.default_rng(2).random((2, 8, 8, 3)).astype(np.float32)
-    vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier")
+    ost, lst = make_pair("resnet1m", n_out=10, in_shape=shape, seed=3)
+    rng = np.random.default_rng(4)
+    Z = rng.random((M,) + shape).astype(np.float32)
     D = ost.flat()[0].size
-    with pytest.raises((LipError, ValueError, RuntimeError)):
-        vp.zgrad(torch.zeros(1, D, device="cuda"), torch.zeros(1, D, device="cuda"))
+    U, V = _probes(D, 2, 23)
+    Y = rng.standard_normal((2, M, 10)).astype(np.float32)
+    ref = O.ggn_vp_zgrad(ost, Z, "classifier", U, V, full_set_size=500, per_probe=True)
+    vp = ggn.compute_ggn_vp(lst, cu(Z), "classifier", full_set_size=500)
+    got = vp.zgrad(cu(U), cu(V), per_probe=True).cpu().numpy().reshape(ref.shape)
+    e = rel_err(got, ref)
+    print(f"ResNet1M {shape} M={M}: ggn zgrad rel err {e:.2e} ({vp._lip_model.path_name()})")
+    assert e < TOL
+    assert rel_err(vp.zgrad(cu(U), cu(V)).cpu().numpy().reshape(Z.shape), ref.sum(0)) < TOL
+    Wz_ref, WTz_ref = O.W_vps_zgrad(ost, Z, "classifier", full_set_size=500)
+    Wf, WTf = ggn.compute_W_vps(lst, cu(Z), "classifier", full_set_size=500)
+    assert rel_err(Wf.zgrad(cu(U), cu(Y)).cpu().numpy().reshape(Z.shape), Wz_ref(U, Y)) < TOL
+    assert rel_err(WTf.zgrad(cu(Y), cu(V)).cpu().numpy().reshape(Z.shape), WTz_ref(Y, V)) < TOL
+
+
+def test_zgrad_rejects_bad_shapes():
+    from lip_b200 import ggn
     ost, lst, Z2, mt, N = _setup("C2_xor")
     vp2 = ggn.compute_ggn_vp(lst, cu(Z2), mt)
     with pytest.raises(ValueError):
