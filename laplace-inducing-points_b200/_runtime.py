@@ -55,6 +55,31 @@ def scratch(nbytes: int):
     return _GLOBAL_SCRATCH.get(nbytes)
 
 
+class _SharedWorkspace:
+    """Operator workspace shared by every BoundModel that issues work on the same (device, stream): calls on one stream are
+    ordered, so they can reuse one buffer — an objective that binds three models (S_X, W_z, W_x) needs the LARGEST of their
+    workspaces, not the sum (a ResNet1M at M = 100 asks for tens of GB per 256-probe block).  Different streams get different buffers."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, nbytes: int) -> Tuple[C.c_void_p, int]:
+        dev = torch.cuda.current_device()
+        key = (dev, torch.cuda.current_stream().cuda_stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < int(nbytes):
+            self.bufs.pop(key, None)
+            del buf
+            buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", dev))
+            self.bufs[key] = buf
+            if len(self.bufs) > 8:                       # streams come and go (CUDA-graph capture, pipelines): keep the table small
+                self.bufs.pop(next(iter(self.bufs)))
+        return C.c_void_p(buf.data_ptr()), buf.numel()
+
+
+_SHARED_WS = _SharedWorkspace()
+
+
 class MLPSpec:
     """Architecture of an MLP extracted from a reference-layout parameter tree (Dense_i: bias, kernel)."""
 
@@ -275,7 +300,7 @@ class BoundModel:
                        "lip_model_set_bn_stats")
         cabi.check(L.lip_model_bind(self._h, ptr(self.theta), ptr(self.Z), self.M, self.logvar, stream()),
                    "lip_model_bind")
-        self._ws = Scratch()
+        self._ws = _SHARED_WS
         self.launches = 0
 
     def clone(self) -> "BoundModel":

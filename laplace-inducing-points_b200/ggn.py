@@ -255,6 +255,15 @@ def compute_ggn_dense(state, Z, model_type, full_set_size=None):
     return GGN.T.contiguous(), flat_params, unravel_fn
 
 
+def _gram_block(bm, want: int, budget: int = 24 << 30) -> int:
+    """one-hot columns per pass of the native Gram builders, halved until the operator workspace fits the budget"""
+    L = cabi.lib()
+    b = max(1, int(want))
+    while b > 1 and int(L.lip_gram_workspace_bytes(bm._h, b)) > budget:
+        b //= 2
+    return b
+
+
 def build_WTW(W, WT, inner_shape, d, *, dtype=torch.float32, block=64):
     """ggn.py:198-227: dense Gram W^T W (d x d), symmetrised from the upper triangle.
     When W/WT are this module's closures over one bound model the native lip_gram_wtw runs; otherwise the
@@ -262,7 +271,7 @@ def build_WTW(W, WT, inner_shape, d, *, dtype=torch.float32, block=64):
     bm = getattr(W, "_lip_model", None)
     if bm is not None and bm is getattr(WT, "_lip_model", None) and getattr(W, "_lip_kind", "") == "W" \
             and getattr(WT, "_lip_kind", "") == "WT" and d == bm.M * bm.K:
-        G = bm.gram(scale=W._lip_scale, block=max(int(block), 256))
+        G = bm.gram(scale=W._lip_scale, block=_gram_block(bm, max(int(block), 256)))
         return G.to(dtype) if dtype not in (float, None) and isinstance(dtype, torch.dtype) else G
     dev = torch.device("cuda", torch.cuda.current_device())
     G = torch.zeros(d, d, device=dev, dtype=torch.float32)
@@ -284,7 +293,8 @@ def build_WTWz(WT, W_z, inner_shape_z, *, d, dtype=torch.float32, block=64):
     bx, bz = getattr(WT, "_lip_model", None), getattr(W_z, "_lip_model", None)
     if bx is not None and bz is not None and getattr(WT, "_lip_kind", "") == "WT" and getattr(W_z, "_lip_kind", "") == "W" \
             and d == bx.M * bx.K and d_z == bz.M * bz.K:
-        return bx.gram_cross(bz, WT._lip_scale, W_z._lip_scale, block=max(int(block), 256))     # native lip_gram_cross
+        return bx.gram_cross(bz, WT._lip_scale, W_z._lip_scale, block=min(_gram_block(bx, max(int(block), 256)),
+                                                                          _gram_block(bz, max(int(block), 256))))     # native lip_gram_cross
     dev = torch.device("cuda", torch.cuda.current_device())
     G = torch.zeros(d, d_z, device=dev)
     eye = torch.eye(d_z, device=dev)

@@ -75,9 +75,27 @@ def _f64(x):
     return x.to(torch.float64)
 
 
-def _probe_block(D: int, want: int) -> int:
-    """how many [D]-vectors to push through the operators at once (bounded scratch)"""
-    return max(1, min(int(want), (1 << 28) // max(D, 1)))
+_WS_BUDGET = 24 << 30        # bytes of operator workspace one block of probes may take (conv programs: [B, M, H, W, C] slots)
+
+
+def _probe_block(D: int, want: int, models=(), zgrad_mode=None) -> int:
+    """how many [D]-vectors to push through the operators at once: bounded probe block (1 GiB of floats) AND bounded operator
+    workspace on every model in `models` (lip_workspace_bytes, and lip_zgrad_workspace_bytes when zgrad_mode is given) — residual
+    conv programs keep several [B, M, H, W, C] tangent / cotangent slots, so 256 probes at M = 100 CIFAR images would ask for 60 GB."""
+    from . import _cabi as cabi
+    b = max(1, min(int(want), (1 << 28) // max(D, 1)))
+    L = cabi.lib()
+
+    def need(bm, nb):
+        n = int(L.lip_workspace_bytes(bm._h, nb))
+        if zgrad_mode is not None:
+            n = max(n, int(L.lip_zgrad_workspace_bytes(bm._h, zgrad_mode, nb)))
+        return n
+
+    for bm in models:
+        while b > 1 and need(bm, b) > _WS_BUDGET:
+            b = max(1, b // 2)
+    return b
 
 
 _PSD_MAX = 4096
@@ -198,7 +216,8 @@ def _exact_value_and_zgrad(p):
     Gbar = (Minv @ G @ Minv) / alpha ** 2 + gamma / alpha ** 3 * (Minv @ (C.T @ C) @ Minv)
     Cbar = -2.0 * gamma / alpha ** 2 * (C @ Minv)
     Wz, W, bz = p["Wz"], p["W"], p["bz"]
-    blk = _probe_block(D, 256)
+    from . import _cabi as cabi
+    blk = _probe_block(D, 256, models=(bz, W._lip_model), zgrad_mode=cabi.ZGRAD_W)
     dZ = torch.zeros(p["M"], bz.Z.shape[1], device=G.device, dtype=torch.float32)
     onehot = torch.eye(d_z, device=G.device, dtype=torch.float32)
     for k0 in range(0, d_z, blk):
@@ -241,7 +260,8 @@ def variational_grad_dense(Z, X, state, alpha, model_type, key=None, full_set_si
     Zt = dev_f32(Z)
     vp = compute_ggn_vp(state, Zt, model_type, full_set_size)
     eye = torch.eye(D, device=Zt.device, dtype=torch.float32)
-    blk = _probe_block(D, 512)
+    from . import _cabi as cabi
+    blk = _probe_block(D, 512, models=(vp._lip_model,), zgrad_mode=cabi.ZGRAD_GGN)
     dZ = torch.zeros(Zt.shape[0], vp._lip_model.Z.shape[1], device=Zt.device, dtype=torch.float32)
     for k0 in range(0, D, blk):
         k1 = min(D, k0 + blk)
@@ -293,7 +313,8 @@ def variational_grad_scalable(Z, X, state, alpha, model_type, key, full_set_size
         # to one-hot columns directly and loses accuracy there when alpha / beta is below the Gram's rounding noise.)
         Wz, Sz_inv, S_vp, d_z = parts["Wz"], parts["Sz_inv"], parts["S_vp"], parts["d_z"]
         beta = N / int(Zt.shape[0])
-        blk = _probe_block(D, 256)
+        from . import _cabi as cabi
+        blk = _probe_block(D, 256, models=(Wz._lip_model, S_vp._lip_model), zgrad_mode=cabi.ZGRAD_W)
         onehot = torch.eye(d_z, device=Zt.device, dtype=torch.float32)
         dZ = torch.zeros(int(Zt.shape[0]), Wz._lip_model.Z.shape[1], device=Zt.device, dtype=torch.float32)
         for k0 in range(0, d_z, blk):
