@@ -30,7 +30,7 @@ using namespace lip;
 namespace {
 
 constexpr int VT = 256;
-constexpr int RCHUNK = 2048;   // floats of w staged in shared memory per sub-chunk
+constexpr int RCHUNK = 1024;   // floats of w staged in shared memory per sub-chunk (one 8-deep batch of float4 loads per lane and row)
 constexpr int MAXP = 512;      // most per-column partials (CTAs per column)
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -81,20 +81,21 @@ inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // CTAs per column of the projection kernel: every CTA gets the same number q of RCHUNK sub-chunks (balanced), about 4 x 148 CTAs
 // over all columns; fewer, fatter CTAs also keep the last-block coefficient sum short
 inline int project_ctas(int64_t n, int64_t B) {
-  const int64_t nsub = (n + 2047) / 2048;
-  int64_t target = (4 * 148 + B - 1) / B;
-  if (target < 8) target = 8;
-  if (target > 512) target = 512;
-  const int64_t q = (nsub + target - 1) / target;
-  const int64_t np = (nsub + q - 1) / q;
+  const int64_t nsub = (n + RCHUNK - 1) / RCHUNK;
+  // two CTAs per SM over all columns (2 x 148 CTAs: every SM gets the same number), each CTA walking nsub / np sub-chunks in a
+  // strided order: with ~5 B sub-chunks per CTA at n = 1.5 M the imbalance between CTAs is one sub-chunk in 5 B or less
+  int64_t np = (2 * 148 + B - 1) / B;
+  if (np < 8) np = 8;
+  if (np > 512) np = 512;
+  if (np > nsub) np = nsub;
   return (int)(np < 1 ? 1 : np);
 }
 
 inline int project_ctas_max(int64_t B) {      // upper bound of project_ctas over all n
-  int64_t target = (4 * 148 + B - 1) / B;
-  if (target < 8) target = 8;
-  if (target > 512) target = 512;
-  return (int)target;
+  int64_t np = (2 * 148 + B - 1) / B;
+  if (np < 8) np = 8;
+  if (np > 512) np = 512;
+  return (int)np;
 }
 
 inline int column_ctas(int64_t n, int64_t B, int per_cta) {
@@ -200,17 +201,62 @@ __global__ void __launch_bounds__(VT) project_kernel(ProjectArgs a) {
     for (int i = threadIdx.x; i < RCHUNK; i += VT) ws[i] = (i < len) ? wb[i0 + i] : 0.f;   // w may be unpadded (ldw = n)
     __syncthreads();
     const int len4 = (len + 3) >> 2;          // rows of Q are zero-padded to ldq (a multiple of 4) and ws is zero beyond len
-    for (int j = warp; j < kk; j += nw) {
-      const float4* q4 = reinterpret_cast<const float4*>(Qb + (int64_t)j * a.ldq + i0);
-      const float4* w4 = reinterpret_cast<const float4*>(ws);
-      float s = 0.f;
-#pragma unroll 4
-      for (int i = lane; i < len4; i += 32) {
-        const float4 q = __ldg(q4 + i), c = w4[i];
-        s += (q.x * c.x + q.y * c.y) + (q.z * c.z + q.w * c.w);
+    const float4* w4 = reinterpret_cast<const float4*>(ws);
+    const float* Qs = Qb + i0;
+    if (len4 == RCHUNK / 4) {
+      // full sub-chunk: a lane holds 8 float4 of the row (one 4 KB row segment per warp) and the NEXT row's 8 loads are issued
+      // before the current row is reduced, so every warp keeps 4 - 8 KB in flight (16 warps per SM: enough to cover HBM latency)
+      float4 qa[8], qb[8];
+      int j = warp;
+      if (j < kk) {
+        const float4* q4 = reinterpret_cast<const float4*>(Qs + (int64_t)j * a.ldq);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) qa[u] = __ldg(q4 + lane + 32 * u);
       }
-      s = warp_sum(s);
-      if (lane == 0) acc[j] += s;             // row j is always handled by the same warp
+      while (j < kk) {
+        const int j1 = j + nw;
+        if (j1 < kk) {
+          const float4* q4 = reinterpret_cast<const float4*>(Qs + (int64_t)j1 * a.ldq);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) qb[u] = __ldg(q4 + lane + 32 * u);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 c = w4[lane + 32 * u];
+          s += (qa[u].x * c.x + qa[u].y * c.y) + (qa[u].z * c.z + qa[u].w * c.w);
+        }
+        s = warp_sum(s);
+        if (lane == 0) acc[j] += s;             // row j is always handled by the same warp
+        if (j1 >= kk) break;
+        const int j2 = j1 + nw;
+        if (j2 < kk) {
+          const float4* q4 = reinterpret_cast<const float4*>(Qs + (int64_t)j2 * a.ldq);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) qa[u] = __ldg(q4 + lane + 32 * u);
+        }
+        s = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 c = w4[lane + 32 * u];
+          s += (qb[u].x * c.x + qb[u].y * c.y) + (qb[u].z * c.z + qb[u].w * c.w);
+        }
+        s = warp_sum(s);
+        if (lane == 0) acc[j1] += s;
+        j = j2;
+      }
+    } else {
+      for (int j = warp; j < kk; j += nw) {
+        const float4* q4 = reinterpret_cast<const float4*>(Qs + (int64_t)j * a.ldq);
+        float s = 0.f;
+#pragma unroll 4
+        for (int i = lane; i < len4; i += 32) {
+          const float4 q = __ldg(q4 + i), c = w4[i];
+          s += (q.x * c.x + q.y * c.y) + (q.z * c.z + q.w * c.w);
+        }
+        s = warp_sum(s);
+        if (lane == 0) acc[j] += s;
+      }
     }
   }
   __syncthreads();

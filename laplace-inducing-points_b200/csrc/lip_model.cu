@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(1024) bias_grad_rows_kernel(const float* __res
 static inline void launch_bias_grad_any(const float* Delta, const float* Delta_lo, int64_t rows, int n, int64_t ld, int64_t bc, float* out,
                                         int64_t out_sz, float scale, const float* add, int64_t add_sz, float add_scale,
                                         cudaStream_t st) {
-  if (rows >= 64 && lip::ceil_div(n, 128) * bc < 4 * 148) {
+  if (rows >= 64 && lip::ceil_div(n, 128) * bc < 148) {       // measured: at 256 CTAs the column-per-thread form is the faster one
     dim3 grid((unsigned)lip::ceil_div(n, 32), (unsigned)bc);
     bias_grad_rows_kernel<<<grid, 1024, 0, st>>>(Delta, Delta_lo, rows, n, ld, out, out_sz, scale, add, add_sz, add_scale);
   } else {
@@ -194,6 +194,158 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict
       C[co] = acc;
     }
   }
+}
+
+// ---- fused head of lip_ggn_vp -------------------------------------------------------------------------------------------------------
+// For a narrow last layer (K <= 16 outputs, e.g. the 128 -> 10 logit layer of the MNIST MLP) everything between the last wide JVP GEMM
+// and the first wide VJP GEMM is one kernel, one CTA per probe (all resident at once at 256 probes), PC points per pass:
+//   t_i   = A_i dW[b] + dA_i[b] W + db[b]                 (head JVP; ggn.py:139-141)
+//   D_i   = H_i t_i  (softmax Hessian rows; regressor: t_i)  (ggn.py:125-131)
+//   gW[b] += A_i^T D_i,   gb[b] += D_i                     (head weight / bias gradient, + alpha V in the epilogue; ggn.py:143)
+//   Dn_i  = (D_i W^T) * phi'_i                             (delta of the layer below, stored as the TF32 (hi, lo) pair its GEMMs read)
+// Replaces five launches (row-per-thread head JVP 85 us, factor rows 8 us, folded head weight gradient 168 us, bias gradient 24 us,
+// head delta back-propagation 126 us per 256-probe call) whose intermediates ([B, M, K] logit tangents twice) went through HBM.
+constexpr int HEAD_PC = 32;      // points per pass
+constexpr int HEAD_KP = 17;      // padded row of the [in][K] weight tiles (odd: conflict-free column access)
+struct HeadArgs {
+  const float* A;                           // [M, in] cached input activations of the head
+  const float* dA; long long dA_sz; int dA_ld;   // [B][M][dA_ld] masked tangent of the head's input (plain fp32)
+  const float* V; const float* theta; long long D;
+  long long woff, boff;                     // head kernel [in, K] / bias [K] offsets in the flat vector
+  int in, K; long long M;
+  const float* P; const float* S;           // softmax rows [M, K] (null: regressor, H = identity)
+  const float* mask;                        // phi' of the layer below at the bound points, [M, in]
+  float* out; float scale; const float* add; float add_scale;
+  float* Dn_hi; float* Dn_lo; long long Dn_sz; int Dn_ld;
+};
+
+__global__ void __launch_bounds__(256) head_fused_kernel(HeadArgs a) {
+  extern __shared__ float sm[];
+  const int in = a.in, K = a.K, lda = in + 1;
+  float* dWs = sm;                                   // [in][KP]
+  float* Ws = dWs + in * HEAD_KP;                    // [in][KP]
+  float* As = Ws + in * HEAD_KP;                     // [PC][in + 1]
+  float* dAs = As + HEAD_PC * lda;                   // [PC][in + 1]
+  float* part = dAs + HEAD_PC * lda;                 // [8][PC][K]
+  float* Ds = part + 8 * HEAD_PC * K;                // [PC][KP]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const long long b = blockIdx.x;
+  const float* Vb = a.V + b * a.D;
+  for (int idx = t; idx < in * K; idx += 256) {
+    const int k = idx / K, n = idx - k * K;
+    dWs[k * HEAD_KP + n] = Vb[a.woff + idx];
+    Ws[k * HEAD_KP + n] = a.theta[a.woff + idx];
+  }
+  // weight-gradient accumulators: pair p = t + 256 r  ->  (k, n) = (p / K, p % K)
+  float gw[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) gw[r] = 0.f;
+  const int npairs = in * K, R = (npairs + 255) >> 8;
+  float gb = 0.f;                                    // threads t < K
+  const int ks = in >> 3;                            // k slice per warp in the JVP step (in % 8 == 0)
+  const float* dAb = a.dA + b * a.dA_sz;
+  float* Dh = a.Dn_hi + b * a.Dn_sz;
+  float* Dl = a.Dn_lo ? a.Dn_lo + b * a.Dn_sz : nullptr;
+  for (long long i0 = 0; i0 < a.M; i0 += HEAD_PC) {
+    const int valid = (int)((a.M - i0) < HEAD_PC ? (a.M - i0) : HEAD_PC);
+    __syncthreads();
+    for (int idx = t; idx < HEAD_PC * in; idx += 256) {
+      const int i = idx / in, k = idx - i * in;
+      const bool ok = i < valid;
+      As[i * lda + k] = ok ? __ldg(a.A + (i0 + i) * in + k) : 0.f;
+      dAs[i * lda + k] = ok ? dAb[(i0 + i) * a.dA_ld + k] : 0.f;
+    }
+    __syncthreads();
+    {  // head JVP partials: lane = point, warp = k slice
+      float acc[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+      const float* ar = As + lane * lda;
+      const float* dr = dAs + lane * lda;
+      for (int k = warp * ks; k < (warp + 1) * ks; ++k) {
+        const float av = ar[k], dv = dr[k];
+        const float* w1 = dWs + k * HEAD_KP;
+        const float* w2 = Ws + k * HEAD_KP;
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+          if (n < K) acc[n] = fmaf(av, w1[n], fmaf(dv, w2[n], acc[n]));
+      }
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < K) part[(warp * HEAD_PC + lane) * K + n] = acc[n];
+    }
+    __syncthreads();
+    for (int idx = t; idx < HEAD_PC * K; idx += 256) {      // sum the 8 slices in a fixed order, add the bias tangent
+      const int i = idx / K, n = idx - i * K;
+      float v = Vb[a.boff + n];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += part[(g * HEAD_PC + i) * K + n];
+      Ds[i * HEAD_KP + n] = (i < valid) ? v : 0.f;
+    }
+    __syncthreads();
+    if (a.P && t < valid) {                                  // D = H t = p * t - p (p . t)   (one thread per point)
+      const float* p = a.P + (i0 + t) * K;
+      float* u = Ds + t * HEAD_KP;
+      float dot = 0.f;
+      for (int n = 0; n < K; ++n) dot = fmaf(__ldg(p + n), u[n], dot);
+      for (int n = 0; n < K; ++n) { const float pn = __ldg(p + n); u[n] = pn * u[n] - pn * dot; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {                           // head weight gradient
+      const int pidx = t + (r << 8);
+      if (r < R && pidx < npairs) {
+        const int k = pidx / K, n = pidx - k * K;
+        float s = gw[r];
+        for (int i = 0; i < HEAD_PC; ++i) s = fmaf(As[i * lda + k], Ds[i * HEAD_KP + n], s);
+        gw[r] = s;
+      }
+    }
+    if (t < K) {
+      float s = gb;
+      for (int i = 0; i < HEAD_PC; ++i) s += Ds[i * HEAD_KP + t];
+      gb = s;
+    }
+    for (int idx = t; idx < HEAD_PC * in; idx += 256) {      // delta of the layer below
+      const int i = idx / in, k = idx - i * in;
+      if (i >= valid) continue;
+      const float* d = Ds + i * HEAD_KP;
+      const float* w = Ws + k * HEAD_KP;
+      float v = 0.f;
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < K) v = fmaf(d[n], w[n], v);
+      v *= __ldg(a.mask + (i0 + i) * in + k);
+      const long long co = (i0 + i) * a.Dn_ld + k;
+      if (Dl) {
+        const float h = tf32_round(v);
+        Dh[co] = h;
+        Dl[co] = tf32_round(v - h);
+      } else {
+        Dh[co] = v;
+      }
+    }
+  }
+  float* ob = a.out + b * a.D;
+  const float* ab = a.add ? a.add + b * a.D : nullptr;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int pidx = t + (r << 8);
+    if (r < R && pidx < npairs) {
+      float v = a.scale * gw[r];
+      if (ab) v += a.add_scale * ab[a.woff + pidx];
+      ob[a.woff + pidx] = v;
+    }
+  }
+  if (t < K) {
+    float v = a.scale * gb;
+    if (ab) v += a.add_scale * ab[a.boff + t];
+    ob[a.boff + t] = v;
+  }
+}
+
+static inline size_t head_smem_bytes(int in, int K) {
+  return sizeof(float) * ((size_t)2 * in * HEAD_KP + (size_t)2 * HEAD_PC * (in + 1) + (size_t)8 * HEAD_PC * K + (size_t)HEAD_PC * HEAD_KP);
 }
 
 __global__ void onehot_rows_kernel(float* __restrict__ U, int64_t d, int64_t start, int64_t blk) {
@@ -308,12 +460,26 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
 // leading dimension of the intermediate produced by layer l (its output width), padded on the tensor path
 static inline int ld_of(const lip_model* m, int width) { return m->tc_on ? pad4(width) : width; }
 
+// the fused head kernel applies: dense program with >= 2 layers whose last layer is a narrow SIMT layer
+static inline bool head_fusable(const lip_model* m) {
+  static const bool off = getenv("LIP_HEAD_FUSE") && atoi(getenv("LIP_HEAD_FUSE")) == 0;
+  const int nL = (int)m->L.size();
+  if (off || nL < 2 || m->is_cnn || m->is_resnet) return false;
+  if (m->tc_on && m->tc_layer[nL - 1]) return false;
+  const DenseLayer& Lh = m->L[nL - 1];
+  if (Lh.out > 16 || Lh.in > 256 || Lh.in % 8 != 0 || Lh.in < 8) return false;
+  return head_smem_bytes(Lh.in, Lh.out) <= 200 * 1024;
+}
+
 // ---- JVP sweep: V[B,D] -> dlogits written to `dst` ([B,M,K], contiguous).  Intermediates ping-pong in ws.
 // keep_hi / keep_lo (optional, [nL - 1] pointers): layer l < nL - 1 writes its masked tangent dA_{l+1} there instead of into the
 // ping-pong buffers, so a later reverse pass (lip_zgrad.cu) can read every layer's tangent.
+// stop_layer (default: all): run layers [0, stop_layer) only; with stop_layer = nL - 1 the masked tangent of the head's input is left in
+// w.hi[(nL - 2) & 1] (plain fp32 when the head is a SIMT layer) for the fused head kernel.
 int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float* dst, cudaStream_t st,
-              float* const* keep_hi = nullptr, float* const* keep_lo = nullptr) {
+              float* const* keep_hi = nullptr, float* const* keep_lo = nullptr, int stop_layer = -1) {
   const int nL = (int)m->L.size();
+  const int nRun = stop_layer < 0 ? nL : stop_layer;
   const float* prev_hi = nullptr;
   const float* prev_lo = nullptr;
   int prev_ld = 0;
@@ -352,7 +518,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       }
     }
   }
-  for (int l = 0; l < nL; ++l) {
+  for (int l = 0; l < nRun; ++l) {
     const DenseLayer& Ld = m->L[l];
     const bool last = (l == nL - 1);
     const bool tc = m->tc_on && m->tc_layer[l];
@@ -429,22 +595,28 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
 }
 
 // ---- VJP sweep: Delta_L (plain fp32, [B,M,K] contiguous) in w.hi[src]; writes out[B,D] = scale * J^T delta + add_scale * add.
+// start_layer (default nL - 1): the sweep starts at that layer with its delta already in w.hi[src] (/ w.lo[src] when that layer is a
+// tensor-core layer): the fused head kernel has produced the delta of layer nL - 2 and the head's own gradients.
 int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, float scale, const float* add,
-              float add_scale, cudaStream_t st) {
+              float add_scale, cudaStream_t st, int start_layer = -1) {
   const int nL = (int)m->L.size();
+  const int lfirst = start_layer < 0 ? nL - 1 : start_layer;
   int cur = src;
   int cur_ld = m->K;
   bool cur_split = false;
   bool cur_colsum = false;   // w.colsum holds the column sums of the current delta (written by the GEMM that produced it)
   const int64_t nslots = colsum_slots(m);
-  if (m->tc_on && m->tc_layer[nL - 1]) {
+  if (lfirst < nL - 1) {
+    cur_ld = ld_of(m, m->L[lfirst].out);
+    cur_split = m->tc_on && m->tc_layer[lfirst];
+  } else if (m->tc_on && m->tc_layer[nL - 1]) {
     // the top layer runs on the tensor cores: re-lay Delta_L as padded hi/lo
     const int ldp = pad4(m->K);
     int rc = tf32_split(w.hi[cur], m->K, w.hi[cur ^ 1], w.lo[cur ^ 1], ldp, B * m->M, m->K, st);
     if (rc) return rc;
     cur ^= 1; cur_ld = ldp; cur_split = true;
   }
-  for (int l = nL - 1; l >= 0; --l) {
+  for (int l = lfirst; l >= 0; --l) {
     const DenseLayer& Ld = m->L[l];
     const bool tc = m->tc_on && m->tc_layer[l];
     const float* d_hi = w.hi[cur];
@@ -796,6 +968,34 @@ int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal,
   int rc = carve(m, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
   const int nL = (int)m->L.size();
+  if (head_fusable(m)) {
+    // wide layers: JVP sweep up to the head's input; head JVP + output-space Hessian + head gradients + delta of the layer below in
+    // one kernel; VJP sweep from the layer below
+    rc = jvp_sweep(m, V, B, w, nullptr, st, nullptr, nullptr, nL - 1);
+    if (rc) return rc;
+    const DenseLayer& Lh = m->L[nL - 1];
+    const int s = (nL - 2) & 1;
+    const bool below_tc = m->tc_on && m->tc_layer[nL - 2];
+    HeadArgs a{};
+    a.A = m->A[nL - 1];
+    a.dA = w.hi[s]; a.dA_ld = ld_of(m, Lh.in); a.dA_sz = m->M * (long long)a.dA_ld;
+    a.V = V; a.theta = m->theta; a.D = m->D; a.woff = Lh.woff; a.boff = Lh.boff; a.in = Lh.in; a.K = Lh.out; a.M = m->M;
+    a.P = m->model_type == LIP_CLASSIFIER ? m->P : nullptr; a.S = m->S;
+    a.mask = m->dphi[nL - 2];
+    a.out = out; a.scale = recal; a.add = alpha != 0.f ? V : nullptr; a.add_scale = alpha;
+    a.Dn_hi = w.hi[s ^ 1]; a.Dn_lo = below_tc ? w.lo[s ^ 1] : nullptr; a.Dn_ld = a.dA_ld; a.Dn_sz = a.dA_sz;
+    const size_t smem = head_smem_bytes(Lh.in, Lh.out);
+    if (smem > 48 * 1024) LIP_CHECK_CUDA(cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t b0 = 0; b0 < B; b0 += 65535 * 32) {
+      const int64_t bc = B - b0 < 65535 * 32 ? B - b0 : 65535 * 32;
+      HeadArgs c = a;
+      c.V += b0 * m->D; c.out += b0 * m->D; if (c.add) c.add += b0 * m->D;
+      c.dA += b0 * a.dA_sz; c.Dn_hi += b0 * a.Dn_sz; if (c.Dn_lo) c.Dn_lo += b0 * a.Dn_sz;
+      head_fused_kernel<<<(unsigned)bc, 256, smem, st>>>(c);
+      LIP_LAUNCH_CHECK();
+    }
+    return vjp_sweep(m, s ^ 1, B, w, out, recal, alpha != 0.f ? V : nullptr, alpha, st, nL - 2);
+  }
   // dlogits land in the buffer the last hidden layer did NOT use, so the VJP can ping-pong from it
   const int src = (nL - 1) & 1;
   float* dl = w.hi[src];
