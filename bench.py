@@ -328,14 +328,18 @@ def run_b200(args):
 
     rng = np.random.default_rng(2000 + rank)
     host_i8 = torch.from_numpy(rng.integers(0, 2, size=(B, D), dtype=np.int8) * 2 - 1).pin_memory()
-    V = host_i8.to(dev).float()
+    # +-1 probes in padded rows, marked exactly-TF32 (what stochtrace._rademacher / unpack_rademacher hand out): lip_ggn_vp_ex then
+    # reads the probe block in place instead of running the TF32 split pass
+    from lip_b200._runtime import exact_tf32_block
+    V = exact_tf32_block(B, D, dev)
+    V.copy_(host_i8.to(dev).float())
     q = torch.empty(B, device=dev)
     acc = torch.zeros(1, device=dev)
     sc, _ = scratch(L.lip_dot_scratch_bytes(D, B))
 
     def step(Vin):
         Y = cvp(Vin)                                                  # [B, D]: one lip_ggn_vp call
-        _cabi.check(L.lip_dot(ptr(Vin), ptr(Y), ptr(q), D, B, D, D, sc, stream()))
+        _cabi.check(L.lip_dot(ptr(Vin), ptr(Y), ptr(q), D, B, Vin.stride(0), D, sc, stream()))
         part = q.sum(0, keepdim=True)
         if world > 1:
             dist.all_reduce(part)                                     # trace accumulator (probe-sharded Hutchinson)
@@ -382,7 +386,7 @@ def run_b200(args):
         nbytes_row = host_bits.shape[1]
         copy_stream = torch.cuda.Stream()
         bufs = [torch.empty(B, nbytes_row, dtype=torch.uint8, device=dev) for _ in range(2)]
-        vbuf = torch.empty(B, D, device=dev)
+        vbuf = exact_tf32_block(B, D, dev)
         evs = [torch.cuda.Event() for _ in range(2)]
         host_q = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
         qev = [torch.cuda.Event() for _ in range(2)]

@@ -121,6 +121,17 @@ size_t lip_workspace_bytes(const lip_model* m, int64_t B);
  * curvature_vp (src/lla.py:19-23).  recal = N/M (x exp(-logvar) for regressors, ggn.py:109-113). */
 int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha,
                void* workspace, size_t workspace_bytes, lip_stream_t stream);
+/* The same with explicit row strides (V: [B, ldv], out: [B, ldo], both >= D, floats) and flags.
+ * LIP_PROBES_EXACT_TF32: the caller vouches that every entry of V is exactly representable in TF32 (10 mantissa bits) — the
+ * reference's Rademacher +-1 probes (src/stochtrace.py:28, src/train_inducing.py:139) and one-hot blocks are.  When in addition the
+ * rows are TMA-addressable (V 16-byte aligned, ldv % 4 == 0, kernel offsets and layer widths multiples of 4 floats) the tcgen05 JVP
+ * GEMMs read the probe block IN PLACE and the TF32 split pass (12 % of a call) disappears.  A plain [B, D] block qualifies only when
+ * D % 4 == 0; callers that own their probe buffers pad the rows (the MNIST MLP's D = 1,494,154 -> ldv = 1,494,156).  Without the flag,
+ * or where a layer does not qualify, the call behaves exactly like lip_ggn_vp.  With the flag set on data that is NOT exactly TF32 the
+ * low 13 mantissa bits of V are ignored (results lose fp32 accuracy; nothing else breaks). */
+#define LIP_PROBES_EXACT_TF32 1
+int lip_ggn_vp_ex(lip_model* m, const float* V, int64_t ldv, float* out, int64_t ldo, int64_t B, float recal, float alpha,
+                  int32_t flags, void* workspace, size_t workspace_bytes, lip_stream_t stream);
 
 /* out[b,i,:] = scale * F_i^T J_i V[b,:]      V: [B, D] -> out: [B, M, K]
  * factor=SQRT replaces WTfun (src/ggn.py:54-62,84-85); factor=NONE is the batched JVP of lla.py:153. */
@@ -194,6 +205,8 @@ int lip_scale(const float* s, int32_t invert, const float* x, float* y, int64_t 
  * 7 of byte 0 is element 0) -> out[b, j] = bit ? +1 : -1, j < n.  Host probes for Hutchinson / SLQ
  * (src/stochtrace.py:28, src/train_inducing.py:139) then cross PCIe at 1 bit per element instead of 32. */
 int lip_unpack_rademacher(const uint8_t* bits, int64_t ldbits, float* out, int64_t n, int64_t B, lip_stream_t stream);
+/* the same into rows of stride ldo >= n floats (padded probe rows for lip_ggn_vp_ex) */
+int lip_unpack_rademacher_ld(const uint8_t* bits, int64_t ldbits, float* out, int64_t ldo, int64_t n, int64_t B, lip_stream_t stream);
 
 /* One CG iteration's vector work for jax.scipy.sparse.linalg.cg semantics (call sites
  * src/stochtrace.py:146,192; src/sample.py:71): given Ap = A p,

@@ -20,6 +20,7 @@ FN_LOG, FN_INVSQRT, FN_INV, FN_IDENTITY, FN_SAMPLER = 0, 1, 2, 3, 4
 LINOP_GGN, LINOP_GKL, LINOP_DENSE_SYM, LINOP_CALLBACK = 0, 1, 2, 3
 KRYLOV_LANCZOS, KRYLOV_GKL, KRYLOV_SLQ_LANCZOS, KRYLOV_SLQ_GKL, KRYLOV_FUNM, KRYLOV_CG, KRYLOV_HUTCHPP, KRYLOV_APPLY = 0, 1, 2, 3, 4, 5, 6, 7
 SLQ_LANCZOS, SLQ_GKL = 0, 1
+PROBES_EXACT_TF32 = 1
 
 
 class LayerDesc(C.Structure):
@@ -63,6 +64,7 @@ SIGNATURES = {
     "lip_model_outputs": (C.c_int, [_P, _P, _P]),
     "lip_workspace_bytes": (_SZ, [_P, _I64]),
     "lip_ggn_vp": (C.c_int, [_P, _P, _P, _I64, _F, _F, _P, _SZ, _P]),
+    "lip_ggn_vp_ex": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _F, _F, _I32, _P, _SZ, _P]),
     "lip_wt_apply": (C.c_int, [_P, _P, _P, _I64, _F, _I32, _P, _SZ, _P]),
     "lip_w_apply": (C.c_int, [_P, _P, _P, _I64, _F, _I32, _P, _F, _P, _SZ, _P]),
     "lip_gram_wtw": (C.c_int, [_P, _P, _F, _I64, _P, _SZ, _P]),
@@ -77,6 +79,7 @@ SIGNATURES = {
     "lip_axpby": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "lip_scale": (C.c_int, [_P, _I32, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "lip_unpack_rademacher": (C.c_int, [_P, _I64, _P, _I64, _I64, _P]),
+    "lip_unpack_rademacher_ld": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P]),
     "lip_cg_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P]),
     "lip_cg_init": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I64, _I64, _P, _P]),
     "lip_reorth_scratch_bytes": (_SZ, [_I64, _I64, _I64]),

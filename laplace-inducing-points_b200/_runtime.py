@@ -27,6 +27,33 @@ def dev_f32(x, device=None) -> torch.Tensor:
     return torch.as_tensor(np.asarray(x), dtype=torch.float32).to(device).contiguous()
 
 
+def pad4(n: int) -> int:
+    return (int(n) + 3) // 4 * 4
+
+
+def exact_tf32_block(rows: int, n: int, device=None) -> torch.Tensor:
+    """An uninitialised [rows, n] float32 view of a [rows, pad4(n)] buffer, marked as holding exactly-TF32 data: the layout and the
+    promise lip_ggn_vp_ex needs to read a probe block in place (LIP_PROBES_EXACT_TF32).  Only code that then FILLS it with such
+    data (+-1 Rademacher probes, one-hot rows) may use it: stochtrace._rademacher, unpack_rademacher, sampler_rademacher."""
+    device = device or _require_cuda()
+    buf = torch.empty(rows, pad4(n), device=device, dtype=torch.float32)
+    view = buf[:, :n]
+    view._lip_exact_tf32 = True
+    return view
+
+
+def is_exact_tf32(t) -> bool:
+    return isinstance(t, torch.Tensor) and getattr(t, "_lip_exact_tf32", False)
+
+
+def row_strided_f32(x, device=None) -> torch.Tensor:
+    """dev_f32 that keeps a 2-D CUDA float32 tensor with unit column stride as it is (no .contiguous() copy of padded rows)."""
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 \
+            and x.stride(0) >= x.shape[1] and (device is None or x.device == device):
+        return x
+    return dev_f32(x, device)
+
+
 def ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -338,14 +365,18 @@ class BoundModel:
 
     # ---- operators (all probe-batched: leading dim B) ----
     def ggn_vp(self, V: torch.Tensor, recal: float, alpha: float = 0.0) -> torch.Tensor:
-        V = dev_f32(V, self.device)
+        exact = is_exact_tf32(V)
+        V = row_strided_f32(V, self.device)
         self._check_last(V, self.D, "parameter-space vector")
         single = V.dim() == 1
-        Vb = V.reshape(-1, self.D)
+        Vb = V.reshape(-1, self.D) if V.dim() != 2 else V
         B = Vb.shape[0]
-        out = torch.empty_like(Vb)
+        ldv = Vb.stride(0) if B > 1 else max(Vb.stride(0), self.D)
+        out = torch.empty(B, self.D, device=self.device, dtype=torch.float32)
         ws, nb = self._workspace(B)
-        cabi.check(cabi.lib().lip_ggn_vp(self._h, ptr(Vb), ptr(out), B, recal, alpha, ws, nb, stream()), "lip_ggn_vp")
+        flags = cabi.PROBES_EXACT_TF32 if exact else 0
+        cabi.check(cabi.lib().lip_ggn_vp_ex(self._h, ptr(Vb), ldv, ptr(out), self.D, B, recal, alpha, flags, ws, nb, stream()),
+                   "lip_ggn_vp")
         return out.reshape(self.D) if single else out
 
     def wt(self, V: torch.Tensor, scale: float = 1.0, factor: int = cabi.FACTOR_SQRT) -> torch.Tensor:

@@ -210,7 +210,8 @@ constexpr int HEAD_KP = 17;      // padded row of the [in][K] weight tiles (odd:
 struct HeadArgs {
   const float* A;                           // [M, in] cached input activations of the head
   const float* dA; long long dA_sz; int dA_ld;   // [B][M][dA_ld] masked tangent of the head's input (plain fp32)
-  const float* V; const float* theta; long long D;
+  const float* V; const float* theta; long long D;   // D: probe stride of V
+  long long ldo, lda;                       // probe strides of out / add
   long long woff, boff;                     // head kernel [in, K] / bias [K] offsets in the flat vector
   int in, K; long long M;
   const float* P; const float* S;           // softmax rows [M, K] (null: regressor, H = identity)
@@ -326,8 +327,8 @@ __global__ void __launch_bounds__(256) head_fused_kernel(HeadArgs a) {
       }
     }
   }
-  float* ob = a.out + b * a.D;
-  const float* ab = a.add ? a.add + b * a.D : nullptr;
+  float* ob = a.out + b * a.ldo;
+  const float* ab = a.add ? a.add + b * a.lda : nullptr;
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const int pidx = t + (r << 8);
@@ -425,6 +426,10 @@ struct Workspace {
   float* vs_lo;
   float* colsum;    // per-32-row-block column sums of the delta written by a tcgen05 delta-backprop GEMM: [B][nslots][ldmax]
   size_t per_buf;   // floats
+  // row strides (floats) of the caller's blocks: V (JVP input / bias source), out (VJP output), add (VJP epilogue operand).
+  // D unless the caller hands over padded rows (lip_ggn_vp_ex), which is what lets TMA read the probe block in place.
+  int64_t ldv = 0, ldo = 0, lda = 0;
+  bool exact = false;   // LIP_PROBES_EXACT_TF32: V's entries are exactly TF32-representable (+-1 probes, one-hot blocks)
 };
 
 static inline int64_t colsum_slots(const lip_model* m) { return ceil_div(m->M, 128) * 4; }
@@ -446,6 +451,8 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
   float* base = (float*)align_up((uintptr_t)ws, 256);
   size_t per = align_up((size_t)B * (size_t)m->M * (size_t)(m->tc_on ? m->ldmax : m->maxw), 64);
   w->per_buf = per;
+  w->ldv = w->ldo = w->lda = m->D;
+  w->exact = false;
   w->hi[0] = base; w->hi[1] = base + per;
   w->lo[0] = w->lo[1] = w->vs_hi = w->vs_lo = w->colsum = nullptr;
   if (m->tc_on) {
@@ -459,6 +466,15 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
 
 // leading dimension of the intermediate produced by layer l (its output width), padded on the tensor path
 static inline int ld_of(const lip_model* m, int width) { return m->tc_on ? pad4(width) : width; }
+
+// Layer l's probe block V[b, woff_l ...] can be the tcgen05 GEMM's B operand where it lies: the caller vouches that its entries are
+// exactly TF32-representable (no lo part: +-1 Rademacher probes, one-hot blocks) and every TMA requirement holds - 16-byte aligned
+// base, row stride `out` and probe stride ldv multiples of 4 floats.  (For the reference's [B, D] blocks with D % 4 != 0 - the
+// MNIST MLP has D = 1,494,154 - the probe stride breaks this, which is why callers that own their probe buffers pad the rows.)
+static inline bool inplace_ok(const lip_model* m, int l, const float* V, const Workspace& w) {
+  const DenseLayer& Ld = m->L[l];
+  return w.exact && m->tc_on && m->tc_layer[l] && (((uintptr_t)(V + Ld.woff)) & 15) == 0 && Ld.out % 4 == 0 && w.ldv % 4 == 0;
+}
 
 // the fused head kernel applies: dense program with >= 2 layers whose last layer is a narrow SIMT layer
 static inline bool head_fusable(const lip_model* m) {
@@ -502,6 +518,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
     LIP_CHECK_CUDA(cudaMemsetAsync(m->lo_nz, 0, sizeof(int) * nL, ss));
     for (int l = 0; l < nL; ++l) {
       if (!m->tc_layer[l]) continue;
+      if (inplace_ok(m, l, V, w)) continue;     // exactly-TF32 probes in TMA-aligned rows: the GEMM reads V itself, no split pass
       const DenseLayer& Ld = m->L[l];
       const int64_t ldw = m->W_ld[l], bsz = (int64_t)Ld.in * ldw;
       float* hi = w.vs_hi + B * m->split_off[l];
@@ -510,7 +527,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       for (int c = 0; c < nch; ++c) {
         const int64_t b0 = nch == 1 ? 0 : c * chunk, b1 = nch == 1 ? B : (b0 + chunk < B ? b0 + chunk : B);
         if (b1 > b0) {
-          int rc = tf32_split3(V + b0 * m->D + Ld.woff, m->D, Ld.out, hi + b0 * bsz, lo + b0 * bsz, bsz, ldw, b1 - b0, Ld.in,
+          int rc = tf32_split3(V + b0 * w.ldv + Ld.woff, w.ldv, Ld.out, hi + b0 * bsz, lo + b0 * bsz, bsz, ldw, b1 - b0, Ld.in,
                                Ld.out, ss, m->lo_nz + l);
           if (rc) return rc;
         }
@@ -535,6 +552,11 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       p.A1.hi = m->A_hi[l]; p.A1.lo = m->A_lo[l]; p.A1.ld = m->A_ld[l]; p.A1.sz = m->M * m->A_ld[l]; p.A1.major_k = 1;
       p.a_batched = 0;
       p.B1.hi = vs_hi; p.B1.lo = vs_lo; p.B1.ld = ldw; p.B1.sz = (int64_t)Ld.in * ldw; p.B1.major_k = 0;
+      if (inplace_ok(m, l, V, w)) {
+        // the probe's [in, out] block where the caller put it: row stride `out`, probe stride ldv; its lo part is zero by contract
+        // (lo_nz[l] stays 0 after the memset above, so the kernels never touch the lo map, which only has to be encodable)
+        p.B1.hi = V + Ld.woff; p.B1.lo = V + Ld.woff; p.B1.ld = Ld.out; p.B1.sz = w.ldv;
+      }
       p.b_batched = 1;
       // exactly-TF32 probes (Rademacher +-1, one-hot): the split found no lo part -> skip its loads / MMAs.  Not in the
       // probe-chunked overlap mode, where a later chunk's split may still be running when the first GEMM starts.
@@ -547,7 +569,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
         p.K2 = Ld.in;
       }
       p.C = out_hi; p.C_lo = out_lo; p.c_sz = m->M * (int64_t)out_ld; p.c_sm = out_ld;
-      p.epi.bias = V + Ld.boff; p.epi.bias_sz = m->D;
+      p.epi.bias = V + Ld.boff; p.epi.bias_sz = w.ldv;
       if (!last) { p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out; }
       int rc = LIP_OK;
       if (overlap && l == first_tc && l == 0) {
@@ -575,7 +597,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       GemmProblem p;
       p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = B;
       p.A1 = {m->A[l], 0, Ld.in, 1};
-      p.B1 = {V + Ld.woff, m->D, Ld.out, 1};
+      p.B1 = {V + Ld.woff, w.ldv, Ld.out, 1};
       if (l > 0) {
         // a SIMT layer always reads a plain fp32 intermediate (its producer saw next_tc == false)
         p.A2 = {prev_hi, m->M * (int64_t)prev_ld, prev_ld, 1};
@@ -584,7 +606,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       }
       p.C = out_hi; p.c_sz = m->M * (int64_t)out_ld; p.c_sm = out_ld;
       p.epi.C_lo = out_lo;
-      p.epi.bias = V + Ld.boff; p.epi.bias_sz = m->D;
+      p.epi.bias = V + Ld.boff; p.epi.bias_sz = w.ldv;
       if (!last) { p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out; }
       int rc = gemm_simt(p, st);
       if (rc) return rc;
@@ -628,9 +650,9 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
       p.a_batched = 0;
       p.B1.hi = d_hi; p.B1.lo = d_lo; p.B1.ld = cur_ld; p.B1.sz = m->M * (int64_t)cur_ld; p.B1.major_k = 0;
       p.b_batched = 1;
-      p.C = out + Ld.woff; p.c_sz = m->D; p.c_sm = Ld.out;
+      p.C = out + Ld.woff; p.c_sz = w.ldo; p.c_sm = Ld.out;
       p.epi.scale = scale;
-      if (add) { p.epi.add = add + Ld.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+      if (add) { p.epi.add = add + Ld.woff; p.epi.add_sz = w.lda; p.epi.add_scale = add_scale; }
       int rc = gemm_tc(p, st);
       if (rc) return rc;
     } else {
@@ -638,19 +660,19 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
       p.M = Ld.in; p.N = Ld.out; p.K = m->M; p.batch = B;
       p.A1 = {m->A[l], 0, 1, Ld.in};
       p.B1 = {d_hi, m->M * (int64_t)cur_ld, cur_ld, 1};
-      p.C = out + Ld.woff; p.c_sz = m->D; p.c_sm = Ld.out;
+      p.C = out + Ld.woff; p.c_sz = w.ldo; p.c_sm = Ld.out;
       p.epi.scale = scale;
-      if (add) { p.epi.add = add + Ld.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+      if (add) { p.epi.add = add + Ld.woff; p.epi.add_sz = w.lda; p.epi.add_scale = add_scale; }
       int rc = gemm_simt(p, st);
       if (rc) return rc;
     }
     {  // bias gradient: column sums of Delta_l (from the producing GEMM's epilogue when it was a tcgen05 GEMM)
       int rcb;
       if (cur_colsum)
-        rcb = launch_bias_grad(w.colsum, nullptr, nslots, Ld.out, cur_ld, B, out + Ld.boff, m->D, scale, add ? add + Ld.boff : nullptr,
-                               m->D, add_scale, st);
+        rcb = launch_bias_grad(w.colsum, nullptr, nslots, Ld.out, cur_ld, B, out + Ld.boff, w.ldo, scale, add ? add + Ld.boff : nullptr,
+                               w.lda, add_scale, st);
       else
-        rcb = launch_bias_grad(d_hi, d_lo, m->M, Ld.out, cur_ld, B, out + Ld.boff, m->D, scale, add ? add + Ld.boff : nullptr, m->D,
+        rcb = launch_bias_grad(d_hi, d_lo, m->M, Ld.out, cur_ld, B, out + Ld.boff, w.ldo, scale, add ? add + Ld.boff : nullptr, w.lda,
                                add_scale, st);
       if (rcb) return rcb;
     }
@@ -958,15 +980,27 @@ size_t lip_workspace_bytes(const lip_model* m, int64_t B) {
 
 int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* workspace,
                size_t workspace_bytes, lip_stream_t stream) {
+  return lip_ggn_vp_ex(m, V, m ? m->D : 0, out, m ? m->D : 0, B, recal, alpha, 0, workspace, workspace_bytes, stream);
+}
+
+int lip_ggn_vp_ex(lip_model* m, const float* V, int64_t ldv, float* out, int64_t ldo, int64_t B, float recal, float alpha,
+                  int32_t flags, void* workspace, size_t workspace_bytes, lip_stream_t stream) {
   LIP_REQUIRE(m && V && out && B > 0, "lip_ggn_vp: null argument or B <= 0");
   LIP_REQUIRE(V != out, "lip_ggn_vp: in-place operation is not supported");
   if (!m->bound) { set_error("lip_ggn_vp: model not bound"); return LIP_ERR_NOT_BOUND; }
+  LIP_REQUIRE(ldv >= m->D && ldo >= m->D, "lip_ggn_vp: row strides (%lld, %lld) are smaller than D = %lld", (long long)ldv,
+              (long long)ldo, (long long)m->D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (m->is_resnet) return resnet_ggn_vp(m, V, out, B, recal, alpha, workspace, workspace_bytes, st);
-  if (m->is_cnn) return cnn_ggn_vp(m, V, out, B, recal, alpha, workspace, workspace_bytes, st);
+  if (m->is_resnet || m->is_cnn) {
+    LIP_REQUIRE(ldv == m->D && ldo == m->D, "lip_ggn_vp_ex: conv programs take contiguous [B, D] blocks");
+    if (m->is_resnet) return resnet_ggn_vp(m, V, out, B, recal, alpha, workspace, workspace_bytes, st);
+    return cnn_ggn_vp(m, V, out, B, recal, alpha, workspace, workspace_bytes, st);
+  }
   Workspace w;
   int rc = carve(m, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
+  w.ldv = ldv; w.lda = ldv; w.ldo = ldo;
+  w.exact = (flags & LIP_PROBES_EXACT_TF32) != 0;
   const int nL = (int)m->L.size();
   if (head_fusable(m)) {
     // wide layers: JVP sweep up to the head's input; head JVP + output-space Hessian + head gradients + delta of the layer below in
@@ -979,7 +1013,7 @@ int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal,
     HeadArgs a{};
     a.A = m->A[nL - 1];
     a.dA = w.hi[s]; a.dA_ld = ld_of(m, Lh.in); a.dA_sz = m->M * (long long)a.dA_ld;
-    a.V = V; a.theta = m->theta; a.D = m->D; a.woff = Lh.woff; a.boff = Lh.boff; a.in = Lh.in; a.K = Lh.out; a.M = m->M;
+    a.V = V; a.theta = m->theta; a.D = w.ldv; a.ldo = w.ldo; a.lda = w.lda; a.woff = Lh.woff; a.boff = Lh.boff; a.in = Lh.in; a.K = Lh.out; a.M = m->M;
     a.P = m->model_type == LIP_CLASSIFIER ? m->P : nullptr; a.S = m->S;
     a.mask = m->dphi[nL - 2];
     a.out = out; a.scale = recal; a.add = alpha != 0.f ? V : nullptr; a.add_scale = alpha;
@@ -989,7 +1023,7 @@ int lip_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal,
     for (int64_t b0 = 0; b0 < B; b0 += 65535 * 32) {
       const int64_t bc = B - b0 < 65535 * 32 ? B - b0 : 65535 * 32;
       HeadArgs c = a;
-      c.V += b0 * m->D; c.out += b0 * m->D; if (c.add) c.add += b0 * m->D;
+      c.V += b0 * w.ldv; c.out += b0 * w.ldo; if (c.add) c.add += b0 * w.lda;
       c.dA += b0 * a.dA_sz; c.Dn_hi += b0 * a.Dn_sz; if (c.Dn_lo) c.Dn_lo += b0 * a.Dn_sz;
       head_fused_kernel<<<(unsigned)bc, 256, smem, st>>>(c);
       LIP_LAUNCH_CHECK();

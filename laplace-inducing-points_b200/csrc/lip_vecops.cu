@@ -122,12 +122,12 @@ __global__ void scale_kernel(const float* __restrict__ s, int invert, const floa
 
 // one thread per packed byte -> 8 consecutive floats; flat grid-stride over all B * ceil(n/8) bytes
 __global__ void __launch_bounds__(256) unpack_rademacher_kernel(const uint8_t* __restrict__ bits, int64_t ldbits,
-                                                                float* __restrict__ out, int64_t n, int64_t B) {
+                                                                float* __restrict__ out, int64_t ldo, int64_t n, int64_t B) {
   const int64_t nbytes = (n + 7) >> 3, total = nbytes * B;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = idx / nbytes, i = idx - b * nbytes;
     const unsigned v = bits[b * ldbits + i];
-    float* o = out + b * n + (i << 3);
+    float* o = out + b * ldo + (i << 3);
     const int64_t left = n - (i << 3);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -139,11 +139,11 @@ __global__ void __launch_bounds__(256) unpack_rademacher_kernel(const uint8_t* _
 // contiguous bytes per instruction; four lanes share a packed byte (broadcast load).  The byte-per-thread form above makes every
 // lane write 8 scalars 32 bytes apart (8 store instructions per warp, each touching 32 sectors).
 __global__ void __launch_bounds__(256) unpack_rademacher2_kernel(const uint8_t* __restrict__ bits, int64_t ldbits,
-                                                                 float* __restrict__ out, int64_t n, int64_t B) {
+                                                                 float* __restrict__ out, int64_t ldo, int64_t n, int64_t B) {
   const int64_t half = n >> 1;
   const int b = blockIdx.y;
   const uint8_t* row = bits + (int64_t)b * ldbits;
-  float2* o = reinterpret_cast<float2*>(out + (int64_t)b * n);
+  float2* o = reinterpret_cast<float2*>(out + (int64_t)b * ldo);
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < half; j += (int64_t)gridDim.x * blockDim.x) {
     const unsigned v = __ldg(row + (j >> 2));
     const int sh = 6 - 2 * (int)(j & 3);                 // element 2j is bit 7 - (2j & 7) of its byte (numpy.packbits order)
@@ -419,19 +419,23 @@ int lip_scale(const float* s, int32_t invert, const float* x, float* y, int64_t 
 }
 
 int lip_unpack_rademacher(const uint8_t* bits, int64_t ldbits, float* out, int64_t n, int64_t B, lip_stream_t stream) {
-  LIP_REQUIRE(bits && out && n > 0 && B > 0 && ldbits * 8 >= n, "lip_unpack_rademacher: bad argument");
-  if (n % 2 == 0 && B <= 65535 && ((uintptr_t)out & 7) == 0) {
+  return lip_unpack_rademacher_ld(bits, ldbits, out, n, n, B, stream);
+}
+
+int lip_unpack_rademacher_ld(const uint8_t* bits, int64_t ldbits, float* out, int64_t ldo, int64_t n, int64_t B, lip_stream_t stream) {
+  LIP_REQUIRE(bits && out && n > 0 && B > 0 && ldbits * 8 >= n && ldo >= n, "lip_unpack_rademacher: bad argument");
+  if (n % 2 == 0 && ldo % 2 == 0 && B <= 65535 && ((uintptr_t)out & 7) == 0) {
     int64_t gx = ceil_div(n / 2, 256 * 4);
     if (gx > 148 * 4) gx = 148 * 4;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)B);
-    unpack_rademacher2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, ldbits, out, n, B);
+    unpack_rademacher2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, ldbits, out, ldo, n, B);
     LIP_LAUNCH_CHECK();
     return LIP_OK;
   }
   int64_t g = ceil_div((n + 7) / 8 * B, 256);
   if (g > 148 * 16) g = 148 * 16;
-  unpack_rademacher_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(bits, ldbits, out, n, B);
+  unpack_rademacher_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(bits, ldbits, out, ldo, n, B);
   LIP_LAUNCH_CHECK();
   return LIP_OK;
 }

@@ -446,8 +446,11 @@ def sampler_rademacher(x_like, /, *, num):
     n = int(dev_f32(x_like).numel())
 
     def sample(key):
+        from ._runtime import exact_tf32_block
         g = _generator(key)
-        return (torch.randint(0, 2, (num, n), generator=g, device=g.device, dtype=torch.int8).float() * 2 - 1)
+        out = exact_tf32_block(num, n, g.device)
+        out.copy_(torch.randint(0, 2, (num, n), generator=g, device=g.device, dtype=torch.int8).float() * 2 - 1)
+        return out
 
     return sample
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import torch
 
-from ._runtime import _require_cuda, dev_f32
+from ._runtime import _require_cuda, dev_f32, exact_tf32_block, is_exact_tf32
 from .matfree import _generator, cg
 
 
@@ -18,6 +18,8 @@ def vmap(fn, in_axes=0, out_axes=0):
     """jax.vmap for matvec closures: batched closures get the whole block, others are looped."""
 
     def mapped(X):
+        if in_axes == 0 and out_axes == 0 and is_exact_tf32(X) and getattr(fn, "_lip_batched", False):
+            return fn(X)                        # padded +-1 probe rows go to the operator as they are (read in place by the GEMMs)
         X = dev_f32(X)
         Xr = X if in_axes == 0 else X.transpose(0, 1)
         if getattr(fn, "_lip_batched", False):
@@ -46,14 +48,29 @@ def unpack_rademacher(bits, n: int, out=None):
     bits = bits.contiguous()
     B = bits.shape[0]
     if out is None:
-        out = torch.empty(B, n, device=bits.device, dtype=torch.float32)
-    cabi.check(cabi.lib().lip_unpack_rademacher(ptr(bits), bits.shape[1], ptr(out), n, B, stream()), "lip_unpack_rademacher")
+        out = exact_tf32_block(B, n, bits.device)         # padded rows + the exactly-TF32 mark: lip_ggn_vp_ex reads them in place
+    if out.dim() != 2 or out.shape != (B, n) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("unpack_rademacher: out must be a [B, n] float32 tensor with unit column stride")
+    cabi.check(cabi.lib().lip_unpack_rademacher_ld(ptr(bits), bits.shape[1], ptr(out), out.stride(0), n, B, stream()),
+               "lip_unpack_rademacher")
+    out._lip_exact_tf32 = True                            # +-1 by construction
     return out
 
 
 def _rademacher(seed, shape):
+    """+-1 probes [B, n] in padded rows, marked exactly-TF32 (src/stochtrace.py:28): the layout lip_ggn_vp_ex reads in place."""
     g = _generator(seed)
-    return torch.randint(0, 2, shape, generator=g, device=g.device, dtype=torch.int8).float() * 2 - 1
+    out = exact_tf32_block(shape[0], shape[1], g.device)
+    out.copy_(torch.randint(0, 2, tuple(shape), generator=g, device=g.device, dtype=torch.int8).float() * 2 - 1)
+    return out
+
+
+def mark_exact_tf32(t):
+    """Declare that a [B, n] CUDA float32 tensor holds only values exactly representable in TF32 (+-1 probes, one-hot rows, small
+    integers): operators may then skip the TF32 split of the block (LIP_PROBES_EXACT_TF32).  The promise is the caller's; it does
+    not survive slicing or arithmetic (the attribute lives on this tensor object), and it must be dropped if the data is edited."""
+    t._lip_exact_tf32 = True
+    return t
 
 
 def _normal(seed, shape):

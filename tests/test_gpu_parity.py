@@ -694,3 +694,48 @@ def test_materialize_covariance_probes_an_operator():
     np.testing.assert_allclose(diag, np.asarray(ref_diag).reshape(N, out_dim), rtol=1e-12)
     with pytest.raises(ValueError):
         lla.materialize_covariance(f, N, out_dim, mode="banana")
+
+
+def test_exact_tf32_probes_are_read_in_place():
+    """lip_ggn_vp_ex with LIP_PROBES_EXACT_TF32 (round 2): +-1 Rademacher probes handed over in padded rows (stochtrace._rademacher,
+    unpack_rademacher) are the tcgen05 JVP GEMMs' B operand where they lie - no TF32 split pass.  Same numbers as the split path
+    (bit for bit: the hi part IS the probe, the lo part is zero) and as the float64 oracle; rows that are not TMA-addressable, and
+    unmarked data, take the split path."""
+    from lip_b200 import lla, stochtrace, _cabi
+    from lip_b200._runtime import exact_tf32_block
+    L = _cabi.lib()
+    for name in ("tc_ragged", "tc_small"):            # D = 45,159 (D % 4 = 3) and D = 21,322 (D % 4 = 2)
+        hidden, n_out, in_dim, M, N = TC_CONFIGS[name]
+        ost, lst = make_pair("large", hidden=hidden, n_out=n_out, in_dim=in_dim, seed=77)
+        rng = np.random.default_rng(81)
+        Z = rng.random((M, in_dim)).astype(np.float32)
+        D = ost.flat()[0].size
+        E = rng.choice([-1.0, 1.0], size=(5, D)).astype(np.float32)
+        cvp = lla.compute_curvature_approx(lst, cu(Z), "classifier", 0.02, full_set_size=N, tensor_path=True)
+        ref_vp = O.compute_curvature_approx(ost, Z, "classifier", 0.02, full_set_size=N)
+        ref = np.stack([ref_vp(v) for v in E.astype(np.float64)])
+        plain = cvp(cu(E))                                        # unmarked, contiguous [B, D]: split path
+        Vp = exact_tf32_block(5, D)
+        Vp.copy_(cu(E))
+        assert Vp.stride(0) % 4 == 0 and Vp.stride(0) >= D
+        l0 = L.lip_launch_count()
+        fast = cvp(Vp)
+        n_fast = L.lip_launch_count() - l0
+        l0 = L.lip_launch_count()
+        cvp(cu(E))
+        n_plain = L.lip_launch_count() - l0
+        assert n_fast < n_plain                                    # the split kernels are gone
+        assert torch.equal(fast, plain)
+        assert rel_err(fast.cpu().numpy(), ref) < TOL_GGN
+        # the estimator entry point generates such probes itself
+        tr = float(stochtrace.stochastic_trace_estimator_mvp(cvp, D, 3, num_samples=16))
+        eps = stochtrace._rademacher(3, (16, D))
+        assert stochtrace.is_exact_tf32(eps) and eps.stride(0) % 4 == 0
+        tr_ref = O.stochastic_trace_estimator_mvp(ref_vp, eps.cpu().numpy().astype(np.float64))
+        assert abs(tr - tr_ref) <= TOL_EST * abs(tr_ref)
+        # packed wire format -> padded rows on the device
+        bits = torch.as_tensor(stochtrace.pack_rademacher(E), device="cuda")
+        up = stochtrace.unpack_rademacher(bits, D)
+        assert stochtrace.is_exact_tf32(up) and torch.equal(up, cu(E)) and torch.equal(cvp(up), plain)
+        # a slice of the padded block is a new tensor object: unmarked, still row-strided -> split path with the padded stride
+        assert torch.equal(cvp(Vp[1:4]), plain[1:4])
