@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblip_b200.so")
-SOURCES = ["lip_api.cu", "lip_gemm_simt.cu", "lip_gemm_tc.cu", "lip_conv_tc.cu", "lip_model.cu", "lip_cnn.cu", "lip_resnet.cu", "lip_vecops.cu", "lip_krylov.cu", "lip_comm.cu", "lip_tridiag.cu", "lip_zgrad.cu", "lip_eval.cu"]
+SOURCES = ["lip_api.cu", "lip_gemm_simt.cu", "lip_gemm_tc.cu", "lip_conv_tc.cu", "lip_model.cu", "lip_cnn.cu", "lip_cnn_fused.cu", "lip_resnet.cu", "lip_vecops.cu", "lip_krylov.cu", "lip_comm.cu", "lip_tridiag.cu", "lip_zgrad.cu", "lip_eval.cu"]
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17",

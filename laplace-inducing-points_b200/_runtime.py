@@ -372,6 +372,9 @@ class BoundModel:
         Vb = V.reshape(-1, self.D) if V.dim() != 2 else V
         B = Vb.shape[0]
         ldv = Vb.stride(0) if B > 1 else max(Vb.stride(0), self.D)
+        if ldv != self.D and isinstance(self.spec, (ConvProgramSpec, ResNetProgramSpec)):
+            # conv stage programs read dense [B, D] blocks (lip_ggn_vp_ex): padded probe rows are repacked once
+            Vb, ldv, exact = Vb.contiguous(), self.D, False
         out = torch.empty(B, self.D, device=self.device, dtype=torch.float32)
         ws, nb = self._workspace(B)
         flags = cabi.PROBES_EXACT_TF32 if exact else 0

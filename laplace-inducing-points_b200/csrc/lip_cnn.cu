@@ -21,7 +21,8 @@ void lip_model::free_cnn_cache() {
   for (auto& s : CS) {
     if (s.Aop) cudaFree(s.Aop);
     if (s.dphi) cudaFree(s.dphi);
-    s.Aop = s.dphi = nullptr;
+    if (s.Xin) cudaFree(s.Xin);
+    s.Aop = s.dphi = s.Xin = nullptr;
   }
   if (cnn_tmp_out) cudaFree(cnn_tmp_out);
   if (cnn_tmp_x) cudaFree(cnn_tmp_x);
@@ -318,6 +319,12 @@ int cnn_jvp_sweep(lip_model* m, const float* V, int64_t B, const CnnWs& w, float
     const ConvStage& s = m->CS[i];
     const bool last = (i == nS - 1);
     const int64_t R = m->M * (int64_t)s.P;
+    if (!last && cnn_stage_fusable(m, i)) {     // conv + mask + pool in one kernel, no patch buffer
+      int rc = cnn_fused_jvp(m, i, V, m->D, T, w.t[i & 1], B, st);
+      if (rc) return rc;
+      T = w.t[i & 1];
+      continue;
+    }
     const float* A2 = nullptr;
     if (i > 0) {
       if (s.type == 1) {
@@ -358,48 +365,60 @@ int cnn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const CnnWs& w, floa
   const int nS = (int)m->CS.size();
   const size_t col_elems = cnn_sizes(m, B).col;
   const float* d = dl;     // delta w.r.t. the pre-activation of stage i, [B, M*P, cout]
+  const float* tin_f = nullptr;   // set when stage i runs fused: the gradient w.r.t. its pooled output, [B, M, out_per_point]
   for (int i = nS - 1; i >= 0; --i) {
     const ConvStage& s = m->CS[i];
     const int64_t R = m->M * (int64_t)s.P;
-    {  // weight gradient [Kc x cout] = Aop^T [Kc x R] . d [R x cout], written in place into out[b, woff ...]
-      GemmProblem p;
-      p.M = s.Kc; p.N = s.cout; p.K = R; p.batch = B;
-      p.A1 = {s.Aop, 0, 1, s.Kc};
-      p.B1 = {d, R * (int64_t)s.cout, s.cout, 1};
-      p.C = out + s.woff; p.c_sz = m->D; p.c_sm = s.cout;
-      p.epi.scale = scale;
-      if (add) { p.epi.add = add + s.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
-      p.splitk_ws = w.col; p.splitk_ws_elems = (int64_t)col_elems;      // col is free here (used again by the G GEMM below)
-      int rc = gemm_simt(p, st);
+    const float* tin = nullptr;     // gradient w.r.t. the output of stage i-1, [B, M, out_per_point(i-1)]
+    if (tin_f) {                    // unpool + mask, kernel / bias gradients and the delta back-propagation in one kernel
+      float* gin = (i > 0) ? (tin_f == w.t[0] ? w.t[1] : w.t[0]) : nullptr;
+      int rc = cnn_fused_vjp(m, i, tin_f, gin, out, B, scale, add, add_scale, w.col, (int64_t)col_elems, st);
       if (rc) return rc;
-      rc = launch_bias_grad(d, nullptr, R, s.cout, s.cout, B, out + s.boff, m->D, scale, add ? add + s.boff : nullptr, m->D,
-                            add_scale, st);
-      if (rc) return rc;
+      if (i == 0) break;
+      tin = gin;
+    } else {
+      {  // weight gradient [Kc x cout] = Aop^T [Kc x R] . d [R x cout], written in place into out[b, woff ...]
+        GemmProblem p;
+        p.M = s.Kc; p.N = s.cout; p.K = R; p.batch = B;
+        p.A1 = {s.Aop, 0, 1, s.Kc};
+        p.B1 = {d, R * (int64_t)s.cout, s.cout, 1};
+        p.C = out + s.woff; p.c_sz = m->D; p.c_sm = s.cout;
+        p.epi.scale = scale;
+        if (add) { p.epi.add = add + s.woff; p.epi.add_sz = m->D; p.epi.add_scale = add_scale; }
+        p.splitk_ws = w.col; p.splitk_ws_elems = (int64_t)col_elems;      // col is free here (used again by the G GEMM below)
+        int rc = gemm_simt(p, st);
+        if (rc) return rc;
+        rc = launch_bias_grad(d, nullptr, R, s.cout, s.cout, B, out + s.boff, m->D, scale, add ? add + s.boff : nullptr, m->D,
+                              add_scale, st);
+        if (rc) return rc;
+      }
+      if (i == 0) break;
+      const ConvStage& sp = m->CS[i - 1];
+      // G = d . W^T : [R x Kc] per probe
+      const bool fuse_mask = (s.type == 0 && !sp.pool && sp.P == 1);      // dense after dense: mask in the epilogue
+      float* G = (s.type == 1) ? w.col : (fuse_mask ? ((d == w.raw) ? w.raw2 : w.raw) : w.t[0]);
+      {
+        GemmProblem p;
+        p.M = R; p.N = s.Kc; p.K = s.cout; p.batch = B;
+        p.A1 = {d, R * (int64_t)s.cout, s.cout, 1};
+        p.B1 = {m->theta + s.woff, 0, 1, s.cout};
+        p.C = G; p.c_sz = R * (int64_t)s.Kc; p.c_sm = s.Kc;
+        if (fuse_mask) { p.epi.mask = sp.dphi; p.epi.mask_sm = s.Kc; }
+        int rc = gemm_simt(p, st);
+        if (rc) return rc;
+      }
+      if (fuse_mask) { d = G; continue; }
+      tin = G;
+      if (s.type == 1) {
+        int rc = launch_col2im(w.col, w.t[0], B * m->M, s, st);
+        if (rc) return rc;
+        tin = w.t[0];
+      }
     }
-    if (i == 0) break;
-    const ConvStage& sp = m->CS[i - 1];
-    // G = d . W^T : [R x Kc] per probe
-    const bool fuse_mask = (s.type == 0 && !sp.pool && sp.P == 1);      // dense after dense: mask in the epilogue
-    float* G = (s.type == 1) ? w.col : (fuse_mask ? ((d == w.raw) ? w.raw2 : w.raw) : w.t[0]);
-    {
-      GemmProblem p;
-      p.M = R; p.N = s.Kc; p.K = s.cout; p.batch = B;
-      p.A1 = {d, R * (int64_t)s.cout, s.cout, 1};
-      p.B1 = {m->theta + s.woff, 0, 1, s.cout};
-      p.C = G; p.c_sz = R * (int64_t)s.Kc; p.c_sm = s.Kc;
-      if (fuse_mask) { p.epi.mask = sp.dphi; p.epi.mask_sm = s.Kc; }
-      int rc = gemm_simt(p, st);
-      if (rc) return rc;
-    }
-    if (fuse_mask) { d = G; continue; }
-    const float* tin = G;     // gradient w.r.t. the output of stage i-1, [B, M, out_per_point(i-1)]
-    if (s.type == 1) {
-      int rc = launch_col2im(w.col, w.t[0], B * m->M, s, st);
-      if (rc) return rc;
-      tin = w.t[0];
-    }
+    if (cnn_stage_fusable(m, i - 1)) { tin_f = tin; continue; }
+    tin_f = nullptr;
     float* dn = (d == w.raw) ? w.raw2 : w.raw;
-    int rc = launch_unpool_mask(tin, dn, B, m->M, sp, st);
+    int rc = launch_unpool_mask(tin, dn, B, m->M, m->CS[i - 1], st);
     if (rc) return rc;
     d = dn;
   }
@@ -523,6 +542,9 @@ int cnn_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaSt
     if (s.type == 1) {
       int rc = launch_im2col(X, s.Aop, M, s, st);
       if (rc) return rc;
+      const size_t xin = sizeof(float) * (size_t)M * s.Hi * s.Wi * s.cin;
+      LIP_CHECK_CUDA(cudaMalloc(&s.Xin, xin + 256));
+      LIP_CHECK_CUDA(cudaMemcpyAsync(s.Xin, X, xin, cudaMemcpyDeviceToDevice, st));
     } else if (X != s.Aop) {
       LIP_CHECK_CUDA(cudaMemcpyAsync(s.Aop, X, sizeof(float) * (size_t)R * s.Kc, cudaMemcpyDeviceToDevice, st));
     }

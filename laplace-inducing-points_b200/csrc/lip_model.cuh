@@ -21,6 +21,7 @@ struct ConvStage {
   int Kc = 0;            // contraction length: kh*kw*cin (in_features for dense)
   float* Aop = nullptr;  // bound cache: [M*P, Kc] im2col patches (conv) or the stage input (dense)
   float* dphi = nullptr; // bound cache: [M*P, cout] activation derivative (null for the last stage)
+  float* Xin = nullptr;  // bound cache (conv): [M, Hi, Wi, cin] stage input image, read by the fused stage kernels (lip_cnn_fused.cu)
   int64_t out_per_point() const { return pool ? (int64_t)Hp * Wp * cout : (int64_t)P * cout; }
 };
 
@@ -170,6 +171,14 @@ int cnn_wt_apply(lip_model* m, const float* V, float* out, int64_t B, float scal
                  cudaStream_t st);
 int cnn_w_apply(lip_model* m, const float* U, float* out, int64_t B, float scale, int32_t factor, const float* add,
                 float add_scale, void* ws, size_t bytes, cudaStream_t st);
+// fused conv + mask + pool stage kernels for LeNet5-shaped stages (lip_cnn_fused.cu); LIP_CNN_FUSE=0 keeps the im2col + GEMM path
+bool cnn_stage_fusable(const lip_model* m, int stage);
+// out[B, M, Hp, Wp, cout] = avgpool2(phi' * (conv(Xin, dW[b]) + conv(T[b], W) + db[b]));  T = nullptr at stage 0
+int cnn_fused_jvp(const lip_model* m, int stage, const float* V, int64_t ldv, const float* T, float* out, int64_t B, cudaStream_t st);
+// tin: gradient w.r.t. the pooled stage output; writes the stage's kernel / bias gradient blocks of out[B, D] (scale, + add_scale * add)
+// and, for stage > 0, gin = the gradient w.r.t. the stage input [B, M, Hi, Wi, cin]
+int cnn_fused_vjp(const lip_model* m, int stage, const float* tin, float* gin, float* out, int64_t B, float scale, const float* add,
+                  float add_scale, float* scratch, int64_t scratch_elems, cudaStream_t st);
 // residual conv programs (lip_resnet.cu)
 int resnet_parse(lip_model* m, const lip_layer_desc* layers, int32_t n_layers, int64_t num_params);
 int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaStream_t st);

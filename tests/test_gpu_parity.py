@@ -388,13 +388,15 @@ def test_headline_config_matches_oracle():
 
 
 # --------------------------------------------------------------------------------- conv stage programs (LeNet5)
-def test_lenet5_operators_match_oracle():
+@pytest.mark.parametrize("M", [5, 18])
+def test_lenet5_operators_match_oracle(M):
     """M3 (scalemodels.py:11-49): forward, GGN-vector product, W, W^T and the W W^T == GGN identity against the float64
-    oracle (torch autograd through the restated LeNet5) on identical weights / points / probes."""
+    oracle (torch autograd through the restated LeNet5) on identical weights / points / probes.  M = 5 / 18 leave ragged
+    image groups in the fused stage kernels (8 / 4 images per CTA, 2 in flight; lip_cnn_fused.cu)."""
     from lip_b200 import ggn, lla
     ost, lst = make_pair("lenet5", seed=31)
     rng = np.random.default_rng(32)
-    M, N = 5, 60000
+    N = 60000
     Z = rng.random((M, 28, 28, 1)).astype(np.float32)
     D = ost.flat()[0].size
     assert D == 61706
@@ -434,6 +436,9 @@ def test_lenet5_hutchinson_and_predictive():
     cvp = lla.compute_curvature_approx(lst, cu(Z), "classifier", alpha, full_set_size=1000)
     got = float(stochtrace.stochastic_trace_estimator_mvp(cvp, D, 0, eps=cu(eps)))
     assert abs(got - ref) <= TOL_EST * abs(ref)
+    # probes drawn by the estimator itself live in padded rows (stride pad4(D) != D): conv programs repack them
+    own = float(stochtrace.stochastic_trace_estimator_mvp(cvp, D, 3, num_samples=8))
+    assert np.isfinite(own) and abs(own - ref) < 0.5 * abs(ref)
     # plain Jacobian-vector products at new inputs (factor NONE): J_X w
     Xnew = rng.random((3, 28, 28, 1)).astype(np.float32)
     w = rng.standard_normal((2, D)).astype(np.float32)
