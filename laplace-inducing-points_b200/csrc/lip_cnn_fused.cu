@@ -25,7 +25,9 @@ template <int CIN_, int COUT_, int HI_, int WI_, int PAD_>
 struct Geo {
   static constexpr int CIN = CIN_, COUT = COUT_, HI = HI_, WI = WI_, PAD = PAD_, KS = 5;
   static constexpr int HO = HI + 2 * PAD - KS + 1, WO = WI + 2 * PAD - KS + 1, HP = HO / 2, WP = WO / 2;
-  static constexpr int HS = HI + 2 * PAD, WS = (WI + 2 * PAD + 1) & ~1;     // zero-padded planar input image in shared memory
+  // zero-padded planar input image in shared memory; the row stride is even (8-byte row loads) and not a multiple of 32 floats
+  // (threads that read different rows of one plane would otherwise all hit the same banks)
+  static constexpr int HS = HI + 2 * PAD, WS0 = (WI + 2 * PAD + 1) & ~1, WS = (WS0 % 32 == 0) ? WS0 + 2 : WS0;
   static constexpr int PLANE = HS * WS;
   static constexpr int KK = KS * KS * CIN;                                  // rows of the flax HWIO kernel [(dy, dx, ci), co]
   static constexpr int CP = (COUT + 3) & ~3;                                // channel count padded to whole float4
@@ -62,6 +64,21 @@ __device__ __forceinline__ void lds_vec(const float* p, float (&r)[N]) {      //
   }
 }
 
+template <int N>
+__device__ __forceinline__ void ldg_vec(const float* p, float (&r)[N]) {      // N = 4: p 16-byte aligned; N = 6: p 8-byte aligned
+  static_assert(N == 4 || N == 6, "unsupported vector width");
+  if constexpr (N == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; i += 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(p + i));
+      r[i] = v.x; r[i + 1] = v.y;
+    }
+  }
+}
+
 // ---- JVP: conv + bias tangent + activation mask + 2x2 average pool ---------------------------------------------------------------
 struct ConvJvpArgs {
   const float* X;       // [M, HI, WI, CIN]      stage input at the bound points
@@ -72,7 +89,7 @@ struct ConvJvpArgs {
   const float* dphi;    // [M, HO, WO, COUT]
   float* out;           // [B, M, HP, WP, COUT]
   long long ldv;
-  int M, IMG;           // images per CTA
+  int M, IMG, ROUNDS;   // images staged per round, rounds per CTA (the kernels stay in shared memory across rounds)
 };
 
 template <class G, bool DUAL>
@@ -81,7 +98,7 @@ constexpr int jvp_smem_floats(int IMG) {
 }
 
 template <class G, int CO_T, bool DUAL, int NT>
-__global__ void __launch_bounds__(NT) conv5_jvp_pool_kernel(ConvJvpArgs a) {
+__global__ void __launch_bounds__(NT, 2) conv5_jvp_pool_kernel(ConvJvpArgs a) {
   constexpr int CIN = G::CIN, COUT = G::COUT, KS = G::KS, CP = G::CP, KK = G::KK, PLANE = G::PLANE, WS = G::WS;
   constexpr int NCG = COUT / CO_T, NW = G::HP * G::WP;
   static_assert(COUT % CO_T == 0 && (CO_T == 4 || CO_T == 6 || CO_T == 8), "channel group");
@@ -93,12 +110,11 @@ __global__ void __launch_bounds__(NT) conv5_jvp_pool_kernel(ConvJvpArgs a) {
   float* sT = sX + a.IMG * CIN * PLANE;              // same (DUAL)
   const int tid = threadIdx.x;
   const long long b = blockIdx.y;
-  const int m0 = blockIdx.x * a.IMG;
-  const int nimg = a.M - m0 < a.IMG ? a.M - m0 : a.IMG;
 
   for (int i = tid; i < a.IMG * CIN * PLANE * (DUAL ? 2 : 1); i += NT) sX[i] = 0.f;
   {
     const float* dW = a.V + b * a.ldv;
+#pragma unroll 8
     for (int i = tid; i < KK * CP; i += NT) {
       const int k = i / CP, c = i - k * CP;
       sdW[i] = c < COUT ? __ldg(dW + k * COUT + c) : 0.f;
@@ -107,90 +123,130 @@ __global__ void __launch_bounds__(NT) conv5_jvp_pool_kernel(ConvJvpArgs a) {
     if (tid < 16) sdb[tid] = tid < COUT ? __ldg(a.Vb + b * a.ldv + tid) : 0.f;
   }
   __syncthreads();
+
+  constexpr int PER = G::HI * G::WI * CIN;
+  static_assert(PER % 4 == 0, "images are staged with 16-byte loads");
+  for (int rd = 0; rd < a.ROUNDS; ++rd) {
+  const int m0 = (blockIdx.x * a.ROUNDS + rd) * a.IMG;
+  const int nimg = a.M - m0 < a.IMG ? a.M - m0 : a.IMG;
+  if (nimg <= 0) break;
+  if (rd > 0) __syncthreads();
   {
-    constexpr int PER = G::HI * G::WI * CIN;
-    const float* Xg = a.X + (long long)m0 * PER;
-    const float* Tg = DUAL ? a.T + (b * a.M + m0) * PER : nullptr;
-    for (int i = tid; i < nimg * PER; i += NT) {
-      const int img = i / PER, r = i - img * PER;
-      const int pix = r / CIN, ci = r - pix * CIN;
-      const int y = pix / G::WI, x = pix - y * G::WI;
-      const int o = (img * CIN + ci) * PLANE + (y + G::PAD) * WS + x + G::PAD;
-      sX[o] = __ldg(Xg + i);
-      if (DUAL) sT[o] = __ldg(Tg + i);
+    const float4* Xg = reinterpret_cast<const float4*>(a.X + (long long)m0 * PER);
+    const float4* Tg = DUAL ? reinterpret_cast<const float4*>(a.T + (b * a.M + m0) * PER) : nullptr;
+    const int total4 = nimg * (PER / 4);
+    constexpr int U = DUAL ? 2 : 4;
+    for (int i0 = tid; i0 < total4; i0 += NT * U) {
+      float4 vx[U], vt[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * NT;
+        if (i < total4) {
+          vx[u] = __ldg(Xg + i);
+          if (DUAL) vt[u] = __ldg(Tg + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * NT;
+        if (i < total4) {
+          const float ex[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+          const float et[4] = {DUAL ? vt[u].x : 0.f, DUAL ? vt[u].y : 0.f, DUAL ? vt[u].z : 0.f, DUAL ? vt[u].w : 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = 4 * i + j;
+            const int img = e / PER, r = e - img * PER;
+            const int pix = r / CIN, ci = r - pix * CIN;
+            const int y = pix / G::WI, x = pix - y * G::WI;
+            const int o = (img * CIN + ci) * PLANE + (y + G::PAD) * WS + x + G::PAD;
+            sX[o] = ex[j];
+            if (DUAL) sT[o] = et[j];
+          }
+        }
+      }
     }
   }
   __syncthreads();
 
-  const int total = nimg * NW * NCG;
+  // one item = (image pair, pool window, channel group): a register tile of 2 images x (2x2 positions) x CO_T channels, so that
+  // every kernel vector read from shared memory feeds 8 * CO_T FMAs (the shared-memory pipe delivers 128 B/clk/SM: with 4
+  // positions per thread the kernel reads alone would bound the loop).  The two operand pairs (X, dW) and (T, W) run one after
+  // the other over the same accumulators, which halves the row registers.
+  const int npair = (nimg + 1) >> 1;
+  const int total = npair * NW * NCG;
   for (int it = tid; it < total; it += NT) {
     const int cg = it % NCG, w = it / NCG;
-    const int img = w / NW, wi = w - img * NW;
+    const int pr = w / NW, wi = w - pr * NW;
     const int yp = wi / G::WP, xp = wi - yp * G::WP;
     const int co0 = cg * CO_T;
-    float acc[2][2][CO_T];
+    float acc[2][2][2][CO_T];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int g = 0; g < 2; ++g)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int c = 0; c < CO_T; ++c) acc[i][j][c] = 0.f;
-    const int woff = img * CIN * PLANE + 2 * yp * WS + 2 * xp;
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < CO_T; ++c) acc[g][i][j][c] = 0.f;
+    const int woff = 2 * pr * CIN * PLANE + 2 * yp * WS + 2 * xp;
 #pragma unroll 1
-    for (int ci = 0; ci < CIN; ++ci) {
-      const float* px = sX + woff + ci * PLANE;
-      const float* pt = sT + woff + ci * PLANE;
-      float ra[KS + 1], rb[KS + 1], ta[KS + 1], tb[KS + 1];
-      lds_row(px, ra);
-      if (DUAL) lds_row(pt, ta);
+    for (int pass = 0; pass < (DUAL ? 2 : 1); ++pass) {
+      const float* src = (pass ? sT : sX) + woff;
+      const float* wsm = (pass ? sW : sdW) + co0;
+#pragma unroll 1
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float* p0 = src + ci * PLANE;
+        const float* p1 = p0 + CIN * PLANE;
+        float ra0[KS + 1], rb0[KS + 1], ra1[KS + 1], rb1[KS + 1];
+        lds_row(p0, ra0);
+        lds_row(p1, ra1);
 #pragma unroll
-      for (int dy = 0; dy < KS; ++dy) {
-        lds_row(px + (dy + 1) * WS, rb);
-        if (DUAL) lds_row(pt + (dy + 1) * WS, tb);
+        for (int dy = 0; dy < KS; ++dy) {
+          lds_row(p0 + (dy + 1) * WS, rb0);
+          lds_row(p1 + (dy + 1) * WS, rb1);
 #pragma unroll
-        for (int dx = 0; dx < KS; ++dx) {
-          const int k = ((dy * KS + dx) * CIN + ci) * CP + co0;
-          float wv[CO_T];
-          lds_vec(sdW + k, wv);
-#pragma unroll
-          for (int c = 0; c < CO_T; ++c) {
-            acc[0][0][c] = fmaf(ra[dx], wv[c], acc[0][0][c]);
-            acc[0][1][c] = fmaf(ra[dx + 1], wv[c], acc[0][1][c]);
-            acc[1][0][c] = fmaf(rb[dx], wv[c], acc[1][0][c]);
-            acc[1][1][c] = fmaf(rb[dx + 1], wv[c], acc[1][1][c]);
-          }
-          if (DUAL) {
-            lds_vec(sW + k, wv);
+          for (int dx = 0; dx < KS; ++dx) {
+            float wv[CO_T];
+            lds_vec(wsm + ((dy * KS + dx) * CIN + ci) * CP, wv);
 #pragma unroll
             for (int c = 0; c < CO_T; ++c) {
-              acc[0][0][c] = fmaf(ta[dx], wv[c], acc[0][0][c]);
-              acc[0][1][c] = fmaf(ta[dx + 1], wv[c], acc[0][1][c]);
-              acc[1][0][c] = fmaf(tb[dx], wv[c], acc[1][0][c]);
-              acc[1][1][c] = fmaf(tb[dx + 1], wv[c], acc[1][1][c]);
+              acc[0][0][0][c] = fmaf(ra0[dx], wv[c], acc[0][0][0][c]);
+              acc[0][0][1][c] = fmaf(ra0[dx + 1], wv[c], acc[0][0][1][c]);
+              acc[0][1][0][c] = fmaf(rb0[dx], wv[c], acc[0][1][0][c]);
+              acc[0][1][1][c] = fmaf(rb0[dx + 1], wv[c], acc[0][1][1][c]);
+              acc[1][0][0][c] = fmaf(ra1[dx], wv[c], acc[1][0][0][c]);
+              acc[1][0][1][c] = fmaf(ra1[dx + 1], wv[c], acc[1][0][1][c]);
+              acc[1][1][0][c] = fmaf(rb1[dx], wv[c], acc[1][1][0][c]);
+              acc[1][1][1][c] = fmaf(rb1[dx + 1], wv[c], acc[1][1][1][c]);
             }
           }
-        }
 #pragma unroll
-        for (int j = 0; j <= KS; ++j) { ra[j] = rb[j]; if (DUAL) ta[j] = tb[j]; }
+          for (int j = 0; j <= KS; ++j) { ra0[j] = rb0[j]; ra1[j] = rb1[j]; }
+        }
       }
     }
     // bias tangent, activation mask, 2x2 mean
-    const long long m = m0 + img;
-    float s[CO_T];
 #pragma unroll
-    for (int c = 0; c < CO_T; ++c) s[c] = 0.f;
+    for (int g = 0; g < 2; ++g) {
+      if (2 * pr + g >= nimg) break;          // odd tail: the second image of the last pair is not there
+      const long long m = m0 + 2 * pr + g;
+      float s[CO_T];
 #pragma unroll
-    for (int oy = 0; oy < 2; ++oy)
+      for (int c = 0; c < CO_T; ++c) s[c] = 0.f;
 #pragma unroll
-      for (int ox = 0; ox < 2; ++ox) {
-        const float* dp = a.dphi + ((m * G::HO + 2 * yp + oy) * G::WO + 2 * xp + ox) * COUT + co0;
+      for (int oy = 0; oy < 2; ++oy)
 #pragma unroll
-        for (int c = 0; c < CO_T; ++c) s[c] = fmaf(acc[oy][ox][c] + sdb[co0 + c], __ldg(dp + c), s[c]);
-      }
-    float* op = a.out + ((b * a.M + m) * NW + wi) * COUT + co0;
+        for (int ox = 0; ox < 2; ++ox) {
+          const float* dp = a.dphi + ((m * G::HO + 2 * yp + oy) * G::WO + 2 * xp + ox) * COUT + co0;
 #pragma unroll
-    for (int c = 0; c < CO_T; ++c) op[c] = 0.25f * s[c];
+          for (int c = 0; c < CO_T; ++c) s[c] = fmaf(acc[g][oy][ox][c] + sdb[co0 + c], __ldg(dp + c), s[c]);
+        }
+      float* op = a.out + ((b * a.M + m) * NW + wi) * COUT + co0;
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) op[c] = 0.25f * s[c];
+    }
   }
+  }   // rounds
 }
 
 // ---- VJP: unpool + mask, kernel / bias gradient partials, delta back-propagation ------------------------------------------------------
@@ -204,27 +260,35 @@ struct ConvVjpArgs {
   int M, G, per_cta;    // images per CTA (a multiple of IF)
 };
 
+// row stride of the delta image in shared memory: = 4 (mod 32) floats, so that threads on different rows read different banks
+__host__ __device__ constexpr int delta_row_stride(int wd_cp) { return wd_cp + (36 - wd_cp % 32) % 32; }
+
 template <class G, int IF, bool DGRAD>
 constexpr int vjp_smem_floats(int NT) {
   constexpr int BD = DGRAD ? G::KS - 1 - G::PAD : 0;
-  return IF * (G::HO + 2 * BD) * (G::WO + 2 * BD) * G::CP + IF * G::CIN * G::PLANE + (DGRAD ? G::KK * G::COUT : 0) + NT;
+  return IF * (G::HO + 2 * BD) * delta_row_stride((G::WO + 2 * BD) * G::CP) + IF * G::CIN * G::PLANE + (DGRAD ? G::KK * G::COUT : 0) +
+         NT * 6;
 }
 
-// CO_T: channels per kernel-gradient thread; RS: row slices of the output image per kernel-gradient thread group; IF: images in flight
-template <class G, int CO_T, int RS, int IF, bool DGRAD, int NT>
+// CO_T / CI_T: output / input channels per kernel-gradient thread; RS: row slices of the output image; IF: images in flight
+template <class G, int CO_T, int CI_T, int RS, int IF, bool DGRAD, int NT>
 __global__ void __launch_bounds__(NT, 2) conv5_vjp_kernel(ConvVjpArgs a) {
   constexpr int CIN = G::CIN, COUT = G::COUT, KS = G::KS, CP = G::CP, KK = G::KK, PLANE = G::PLANE, WS = G::WS, HS = G::HS;
   constexpr int HO = G::HO, WO = G::WO, HI = G::HI, WI = G::WI, PAD = G::PAD;
   constexpr int BD = DGRAD ? KS - 1 - PAD : 0, HD = HO + 2 * BD, WD = WO + 2 * BD;
-  constexpr int NCH = COUT / CO_T, NTW = KS * CIN * NCH * RS, ROWS = HO / RS;
-  constexpr int SD = IF * HD * WD * CP, SX = IF * CIN * PLANE, SW = DGRAD ? KK * COUT : 0;
-  static_assert(COUT % CO_T == 0 && HO % RS == 0 && IF * NTW <= NT && NT % CP == 0, "thread roles");
+  constexpr int DRS = delta_row_stride(WD * CP);
+  constexpr int NCH = COUT / CO_T, NCI = CIN / CI_T, NTW = KS * NCI * NCH * RS, ROWS = HO / RS;
+  constexpr int SD = IF * HD * DRS, SX = IF * CIN * PLANE, SW = DGRAD ? KK * COUT : 0;
+  static_assert(CIN % CI_T == 0, "input channel group");
+  // phase A items: CW channels of one pixel (6 -> three 8-byte loads, else one 16-byte load), stored as CWP floats of the padded row
+  constexpr int CW = (COUT % 4 == 0) ? 4 : COUT, CWP = (CW + 3) & ~3, NCHK = COUT / CW;
+  static_assert(COUT % CO_T == 0 && HO % RS == 0 && IF * NTW <= NT && NT % NCHK == 0 && NCHK * CWP == CP, "thread roles");
   static_assert(IF * RS * KK * CP <= SD, "the reduction scratch aliases the delta images");
   extern __shared__ __align__(16) float sm[];
-  float* sD = sm;                 // [IF][HD][WD][CP]   delta w.r.t. the pre-activation, zero border for the transposed conv
+  float* sD = sm;                 // [IF][HD][DRS >= WD*CP]  delta w.r.t. the pre-activation, zero border for the transposed conv
   float* sX = sD + SD;            // [IF][CIN][HS][WS]  zero-padded planar input
   float* sW = sX + SX;            // [KK][COUT]
-  float* sB = sW + SW;            // [NT]
+  float* sB = sW + SW;            // [NT][CW]
   const int tid = threadIdx.x;
   const long long b = blockIdx.y;
   const int g = blockIdx.x;
@@ -235,58 +299,116 @@ __global__ void __launch_bounds__(NT, 2) conv5_vjp_kernel(ConvVjpArgs a) {
   if (DGRAD)
     for (int i = tid; i < KK * COUT; i += NT) sW[i] = __ldg(a.W + i);
 
-  // kernel-gradient role: (tap row dy, input channel ci, channel group ch, row slice rs) of image slot img
+  // kernel-gradient role: (tap row dy, channel group ch, row slice rs, input channel group ci) of image slot img; dy varies
+  // fastest: the lanes of a warp then share delta pixels (broadcast) and read neighbouring input rows
   const bool wrole = tid < IF * NTW;
-  const int w_ch = tid % NCH, w_rs = (tid / NCH) % RS, w_ci = (tid / (NCH * RS)) % CIN, w_dy = (tid / (NCH * RS * CIN)) % KS;
+  const int w_dy = tid % KS, w_ch = (tid / KS) % NCH, w_rs = (tid / (KS * NCH)) % RS, w_ci = ((tid / (KS * NCH * RS)) % NCI) * CI_T;
   const int w_img = tid / NTW;
-  float acc[KS][CO_T];
+  float acc[CI_T][KS][CO_T];
 #pragma unroll
-  for (int i = 0; i < KS; ++i)
+  for (int g = 0; g < CI_T; ++g)
 #pragma unroll
-    for (int c = 0; c < CO_T; ++c) acc[i][c] = 0.f;
-  float bsum = 0.f;
+    for (int i = 0; i < KS; ++i)
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) acc[g][i][c] = 0.f;
+  float bsum[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) bsum[j] = 0.f;
+  const int a_chunk = tid % NCHK;
   __syncthreads();
 
   for (int mb = m_begin; mb < m_end; mb += IF) {
-    // phase A: d = phi' * unpool(t_in) / 4 and the planar input images
-    for (int e = tid; e < IF * HO * WO * CP; e += NT) {
-      const int c = e % CP, q = e / CP;
-      const int pos = q % (HO * WO), img = q / (HO * WO);
-      const int y = pos / WO, x = pos - y * WO;
-      const long long m = mb + img;
-      float v = 0.f;
-      if (c < COUT && m < m_end)
-        v = 0.25f * __ldg(a.dphi + (m * (HO * WO) + pos) * COUT + c) *
-            __ldg(a.tin + (((b * a.M + m) * G::HP + (y >> 1)) * G::WP + (x >> 1)) * COUT + c);
-      sD[((img * HD + y + BD) * WD + x + BD) * CP + c] = v;
-      bsum += v;
-    }
-    for (int e = tid; e < IF * HI * WI * CIN; e += NT) {
-      const int ci = e % CIN, q = e / CIN;
-      const int pix = q % (HI * WI), img = q / (HI * WI);
-      const int y = pix / WI, x = pix - y * WI;
-      const long long m = mb + img;
-      sX[((img * CIN + ci) * HS + y + PAD) * WS + x + PAD] = m < m_end ? __ldg(a.X + (m * (HI * WI) + pix) * CIN + ci) : 0.f;
+    // phase A: d = phi' * unpool(t_in) / 4 and the planar input images.  One item = CW channels of one pixel; the global loads of
+    // a batch of items are issued before any of them is used (the phase is latency-bound otherwise)
+    {
+      constexpr int NITEM = IF * HO * WO * NCHK;
+      constexpr int UA = 4;
+      for (int e0 = tid; e0 < NITEM; e0 += NT * UA) {
+        float dp[UA][CW], tv[UA][CW];
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+          const int e = e0 + u * NT;
+          const int q = e / NCHK;                       // chunk = e % NCHK = tid % NCHK (NT % NCHK == 0)
+          const int pos = q % (HO * WO), img = q / (HO * WO);
+          const int y = pos / WO, x = pos - y * WO;
+          const long long m = mb + img;
+          const bool ok = e < NITEM && m < m_end;
+#pragma unroll
+          for (int j = 0; j < CW; ++j) dp[u][j] = tv[u][j] = 0.f;
+          if (ok) {
+            ldg_vec<CW>(a.dphi + (m * (HO * WO) + pos) * COUT + a_chunk * CW, dp[u]);
+            ldg_vec<CW>(a.tin + (((b * a.M + m) * G::HP + (y >> 1)) * G::WP + (x >> 1)) * COUT + a_chunk * CW, tv[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+          const int e = e0 + u * NT;
+          if (e < NITEM) {
+            const int q = e / NCHK;
+            const int pos = q % (HO * WO), img = q / (HO * WO);
+            const int y = pos / WO, x = pos - y * WO;
+            float v[CWP];
+#pragma unroll
+            for (int j = 0; j < CWP; ++j) v[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) { v[j] = 0.25f * dp[u][j] * tv[u][j]; bsum[j] += v[j]; }
+            float* dst = sD + (img * HD + y + BD) * DRS + (x + BD) * CP + a_chunk * CWP;
+#pragma unroll
+            for (int j = 0; j < CWP; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+      constexpr int PERX = HI * WI * CIN;
+      static_assert(PERX % 4 == 0, "images are staged with 16-byte loads");
+      constexpr int NX4 = IF * PERX / 4;
+      for (int i0 = tid; i0 < NX4; i0 += NT * 2) {
+        float4 vx[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * NT;
+          const int img = i / (PERX / 4);
+          vx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < NX4 && mb + img < m_end) vx[u] = __ldg(reinterpret_cast<const float4*>(a.X + (long long)mb * PERX) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * NT;
+          if (i < NX4) {
+            const float ex[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 4 * i + j;
+              const int img = e / PERX, r = e - img * PERX;
+              const int pix = r / CIN, ci = r - pix * CIN;
+              const int y = pix / WI, x = pix - y * WI;
+              sX[((img * CIN + ci) * HS + y + PAD) * WS + x + PAD] = ex[j];
+            }
+          }
+        }
+      }
     }
     __syncthreads();
 
     // phase B: gW[(dy, dx, ci), co] += sum_{y, x} X[y + dy, x + dx, ci] * d[y, x, co]
     if (wrole) {
       const float* xr = sX + ((w_img * CIN + w_ci) * HS + w_dy) * WS;
-      const float* dr = sD + ((w_img * HD + BD) * WD + BD) * CP + w_ch * CO_T;
+      const float* dr = sD + (w_img * HD + BD) * DRS + BD * CP + w_ch * CO_T;
 #pragma unroll 1
       for (int yy = 0; yy < ROWS; ++yy) {
         const int y = w_rs * ROWS + yy;
-        float ar[WS];
-        lds_row(xr + y * WS, ar);
+        float ar[CI_T][WS];
+#pragma unroll
+        for (int g = 0; g < CI_T; ++g) lds_row(xr + g * PLANE + y * WS, ar[g]);
 #pragma unroll
         for (int x = 0; x < WO; ++x) {
           float dv[CO_T];
-          lds_vec(dr + (y * WD + x) * CP, dv);
+          lds_vec(dr + y * DRS + x * CP, dv);
 #pragma unroll
-          for (int dx = 0; dx < KS; ++dx)
+          for (int g = 0; g < CI_T; ++g)
 #pragma unroll
-            for (int c = 0; c < CO_T; ++c) acc[dx][c] = fmaf(ar[x + dx], dv[c], acc[dx][c]);
+            for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+              for (int c = 0; c < CO_T; ++c) acc[g][dx][c] = fmaf(ar[g][x + dx], dv[c], acc[g][dx][c]);
         }
       }
     }
@@ -309,7 +431,7 @@ __global__ void __launch_bounds__(NT, 2) conv5_vjp_kernel(ConvVjpArgs a) {
           const int yy = yi + PAD - dy;
           if (yy < 0 || yy >= HO) continue;
           // pixel p with tap dx reads padded column xi0 + p - dx + (PAD + BD) = xi0 + p - dx + KS - 1
-          const float* dp = sD + ((img * HD + yy + BD) * WD + xi0) * CP + k4 * 4;
+          const float* dp = sD + (img * HD + yy + BD) * DRS + xi0 * CP + k4 * 4;
           float4 ds[XT + KS - 1];
 #pragma unroll
           for (int j = 0; j < XT + KS - 1; ++j) ds[j] = *reinterpret_cast<const float4*>(dp + j * CP);
@@ -350,12 +472,15 @@ __global__ void __launch_bounds__(NT, 2) conv5_vjp_kernel(ConvVjpArgs a) {
   if (wrole) {
     const int slot = w_img * RS + w_rs;
 #pragma unroll
-    for (int dx = 0; dx < KS; ++dx)
+    for (int g = 0; g < CI_T; ++g)
 #pragma unroll
-      for (int c = 0; c < CO_T; ++c)
-        red[(slot * KK + (w_dy * KS + dx) * CIN + w_ci) * CP + w_ch * CO_T + c] = acc[dx][c];
+      for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c)
+          red[(slot * KK + (w_dy * KS + dx) * CIN + w_ci + g) * CP + w_ch * CO_T + c] = acc[g][dx][c];
   }
-  sB[tid] = bsum;
+#pragma unroll
+  for (int j = 0; j < CW; ++j) sB[tid * CW + j] = bsum[j];
   __syncthreads();
   float* part = a.part + (b * a.G + g) * (long long)(KK * COUT + COUT);
   for (int o = tid; o < KK * COUT; o += NT) {
@@ -365,9 +490,10 @@ __global__ void __launch_bounds__(NT, 2) conv5_vjp_kernel(ConvVjpArgs a) {
     for (int slot = 0; slot < IF * RS; ++slot) s += red[(slot * KK + k) * CP + c];
     part[o] = s;
   }
-  if (tid < COUT) {
+  if (tid < COUT) {        // channel tid = chunk * CW + j: summed over the threads of that chunk in a fixed order
+    const int chunk = tid / CW, j = tid - chunk * CW;
     float s = 0.f;
-    for (int t = tid; t < NT; t += CP) s += sB[t];
+    for (int t = chunk; t < NT; t += NCHK) s += sB[t * CW + j];
     part[KK * COUT + tid] = s;
   }
 }
@@ -401,9 +527,12 @@ bool fuse_enabled() {
 template <class G, int CO_T, bool DUAL, int NT>
 int launch_jvp(const ConvStage& s, const lip_model* m, const float* V, int64_t ldv, const float* T, float* out, int64_t B, int IMG,
                cudaStream_t st) {
+  // rounds per CTA: amortise the kernel staging while keeping >= ~16 CTAs per SM over the probe block (a short last wave)
+  int64_t rounds = ceil_div(m->M, IMG) * B / (148 * 16);
+  rounds = rounds < 1 ? 1 : (rounds > 8 ? 8 : rounds);
   ConvJvpArgs a;
   a.X = s.Xin; a.T = T; a.W = m->theta + s.woff; a.V = V + s.woff; a.Vb = V + s.boff; a.dphi = s.dphi; a.out = out;
-  a.ldv = ldv; a.M = (int)m->M; a.IMG = IMG;
+  a.ldv = ldv; a.M = (int)m->M; a.IMG = IMG; a.ROUNDS = (int)rounds;
   const size_t smem = sizeof(float) * (size_t)jvp_smem_floats<G, DUAL>(IMG);
   auto kern = conv5_jvp_pool_kernel<G, CO_T, DUAL, NT>;
   static bool attr_done = false;
@@ -411,7 +540,7 @@ int launch_jvp(const ConvStage& s, const lip_model* m, const float* V, int64_t l
     LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_done = true;
   }
-  const unsigned gx = (unsigned)ceil_div(m->M, IMG);
+  const unsigned gx = (unsigned)ceil_div(m->M, IMG * rounds);
   for (int64_t b0 = 0; b0 < B; b0 += 65535) {
     const int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
     ConvJvpArgs c = a;
@@ -424,12 +553,12 @@ int launch_jvp(const ConvStage& s, const lip_model* m, const float* V, int64_t l
   return LIP_OK;
 }
 
-template <class G, int CO_T, int RS, int IF, bool DGRAD, int NT>
+template <class G, int CO_T, int CI_T, int RS, int IF, bool DGRAD, int NT>
 int launch_vjp(const ConvStage& s, const lip_model* m, const float* tin, float* gin, float* out, int64_t B, float scale,
                const float* add, float add_scale, float* scratch, int64_t scratch_elems, cudaStream_t st) {
   const int64_t M = m->M;
-  // enough CTAs for ~8 per SM over the whole probe block, each looping over a multiple of IF images
-  int64_t Gn = ceil_div(148 * 8, B);
+  // enough CTAs for ~16 per SM over the whole probe block (a short last wave), each looping over a multiple of IF images
+  int64_t Gn = ceil_div(148 * 16, B);
   const int64_t maxG = ceil_div(M, IF);
   Gn = Gn < 1 ? 1 : (Gn > maxG ? maxG : Gn);
   const int64_t per_cta = ceil_div(ceil_div(M, Gn), IF) * IF;
@@ -441,7 +570,7 @@ int launch_vjp(const ConvStage& s, const lip_model* m, const float* tin, float* 
     return LIP_ERR_WORKSPACE;
   }
   const size_t smem = sizeof(float) * (size_t)vjp_smem_floats<G, IF, DGRAD>(NT);
-  auto kern = conv5_vjp_kernel<G, CO_T, RS, IF, DGRAD, NT>;
+  auto kern = conv5_vjp_kernel<G, CO_T, CI_T, RS, IF, DGRAD, NT>;
   static bool attr_done = false;
   if (!attr_done) {
     LIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -476,15 +605,17 @@ bool cnn_stage_fusable(const lip_model* m, int i) {
 
 int cnn_fused_jvp(const lip_model* m, int i, const float* V, int64_t ldv, const float* T, float* out, int64_t B, cudaStream_t st) {
   const ConvStage& s = m->CS[i];
-  if (i == 0) return launch_jvp<GeoC1, 6, false, 224>(s, m, V, ldv, nullptr, out, B, 8, st);
-  return launch_jvp<GeoC2, 8, true, 224>(s, m, V, ldv, T, out, B, 4, st);
+  if (i == 0) return launch_jvp<GeoC1, 6, false, 224>(s, m, V, ldv, nullptr, out, B, 16, st);     // 8 pairs x 196 windows = 7 x 224
+  return launch_jvp<GeoC2, 8, true, 256>(s, m, V, ldv, T, out, B, 10, st);     // 5 pairs x 25 windows x 2 groups = 250 items of 256
 }
 
 int cnn_fused_vjp(const lip_model* m, int i, const float* tin, float* gin, float* out, int64_t B, float scale, const float* add,
                   float add_scale, float* scratch, int64_t scratch_elems, cudaStream_t st) {
   const ConvStage& s = m->CS[i];
-  if (i == 0) return launch_vjp<GeoC1, 6, 28, 2, false, 288>(s, m, tin, nullptr, out, B, scale, add, add_scale, scratch, scratch_elems, st);
-  return launch_vjp<GeoC2, 4, 1, 2, true, 256>(s, m, tin, gin, out, B, scale, add, add_scale, scratch, scratch_elems, st);
+  if (i == 0)
+    return launch_vjp<GeoC1, 6, 1, 28, 2, false, 288>(s, m, tin, nullptr, out, B, scale, add, add_scale, scratch, scratch_elems, st);
+  // one input channel per kernel-gradient thread and no row slices measured faster than 2 x 2 (register pressure): 6.22 vs 6.46 ms / step
+  return launch_vjp<GeoC2, 4, 1, 1, 2, true, 256>(s, m, tin, gin, out, B, scale, add, add_scale, scratch, scratch_elems, st);
 }
 
 }  // namespace lip
