@@ -660,12 +660,17 @@ def run_b200(args):
         if c4:
             # LeNet5 (channels 1 / 6 / 16) cannot feed the tensor cores; its yardsticks are the fp32 FMA pipes and HBM.  Bytes: the tangents and
             # cotangents of every stage written and read once per (probe, point) — 2 x 8,094 floats x 8 B — plus 8 D per product.
-            per_pair = 2 * (4704 + 1176 + 1600 + 400 + 120 + 84 + 10) * 8
+            # With the fused stage kernels (lip_cnn_fused.cu) only the POOLED tangents / cotangents cross HBM.
+            per_pair = 2 * (1176 + 400 + 120 + 84 + 10) * 8
             gbps = (per_pair * 200 + 8 * 61_706) * c4["probes_per_step"] / (c4["ms_per_step"] * 1e-3) / 1e9 / world
-            c4["roofline"] = {"bound": "hbm", "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": (gbps / hbm) if hbm else None,
-                              "simt_fp32_tflops": c4["algorithmic_tflops"],
-                              "note": "per GPU; unfused-stage traffic model (tangent + cotangent of each stage stored once, read once); the SIMT "
-                                      "fp32 GEMMs on 1 / 6 / 16-channel convolutions are instruction-bound, far from either roof"}
+            clk = (line["clocks"] or {}).get("sm_max_mhz") or 1965.0
+            fma_peak = 148 * 128 * 2 * clk * 1e6 / 1e12
+            c4["roofline"] = {"bound": "fp32-fma", "achieved": c4["algorithmic_tflops"], "peak": fma_peak, "unit": "TFLOP/s",
+                              "frac": c4["algorithmic_tflops"] / fma_peak,
+                              "hbm": {"achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": (gbps / hbm) if hbm else None,
+                                      "bytes_per_probe_point": per_pair},
+                              "note": "per GPU; peak = 148 SMs x 128 FMA lanes x 2 x max SM clock (exact fp32: 1 / 6 / 16 channels are below any "
+                                      "tensor-core tile); hbm = pooled tangent + cotangent of each stage written once and read once + 8 D per product"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -98,6 +98,9 @@ int64_t lip_model_num_points(const lip_model* m);
 int lip_model_set_tensor_path(lip_model* m, int32_t enable);
 /* number of dense layers whose GEMMs run on the tcgen05 path for the current binding (0 = SIMT only) */
 int lip_model_tensor_layers(const lip_model* m);
+/* number of conv stages of a conv stage program (LeNet5, src/scalemodels.py:11-49) that run as ONE fused kernel per direction
+ * (conv + activation mask + pool, no patch buffer: csrc/lip_cnn_fused.cu) for the current binding; 0 = im2col + GEMM */
+int lip_model_fused_stages(const lip_model* m);
 
 /* Bind weights theta[D] (flat, reference order) and points Z[M, in_features]; runs and caches the forward
  * pass (activations, activation derivatives, softmax p and sqrt p).  Replaces the per-call forward passes of

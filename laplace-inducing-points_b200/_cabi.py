@@ -59,6 +59,7 @@ SIGNATURES = {
     "lip_model_num_points": (_I64, [_P]),
     "lip_model_set_tensor_path": (C.c_int, [_P, _I32]),
     "lip_model_tensor_layers": (C.c_int, [_P]),
+    "lip_model_fused_stages": (C.c_int, [_P]),
     "lip_model_bind": (C.c_int, [_P, _P, _P, _I64, _F, _P]),
     "lip_model_set_bn_stats": (C.c_int, [_P, _P, _I64, _P]),
     "lip_model_outputs": (C.c_int, [_P, _P, _P]),

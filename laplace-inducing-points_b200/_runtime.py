@@ -344,6 +344,10 @@ class BoundModel:
         total = len(self.spec.layers)
         if isinstance(self.spec, ResNetProgramSpec) and n:
             return f"implicit-GEMM conv: tcgen05-3xtf32 ({n} conv units) + simt-fp32 ({total} conv/dense stages in all)"
+        if isinstance(self.spec, ConvProgramSpec):
+            nf = int(cabi.lib().lip_model_fused_stages(self._h))
+            if nf:
+                return f"fused conv+mask+pool stage kernels ({nf} conv stages, no patch buffer) + simt-fp32 GEMMs ({total} stages in all)"
         if isinstance(self.spec, (ConvProgramSpec, ResNetProgramSpec)):
             return f"im2col + simt-fp32 ({total} conv/dense stages)"
         return f"tcgen05-3xtf32 ({n}/{total} layers) + simt-fp32" if n else "simt-fp32"

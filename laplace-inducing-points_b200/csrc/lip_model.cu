@@ -843,6 +843,13 @@ int lip_model_tensor_layers(const lip_model* m) {
   return n;
 }
 
+int lip_model_fused_stages(const lip_model* m) {
+  if (!m || !m->bound || !m->is_cnn) return 0;
+  int n = 0;
+  for (int i = 0; i + 1 < (int)m->CS.size(); ++i) n += lip::cnn_stage_fusable(m, i) ? 1 : 0;
+  return n;
+}
+
 int lip_model_set_tensor_path(lip_model* m, int32_t enable) {
   LIP_REQUIRE(m != nullptr, "null model");
   m->use_tc = enable ? 1 : 0;
