@@ -621,7 +621,7 @@ def run_b200(args):
     # over the call's launches); only valid for the configuration it was captured on
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_ggn_vp.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_ggn_vp.json")))
         if args.workload == "mlp" and B == 256:
             traffic = tj["traffic_bytes"]
     except Exception:

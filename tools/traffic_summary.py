@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sums DRAM bytes / time over the launches of ONE lip_ggn_vp call from an
 `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` log of bench.py (mlp workload) and writes
-profiles/r01_traffic_ggn_vp.json (read by bench.py for roofline.traffic).  usage: traffic_summary.py traffic_step.csv out.json"""
+profiles/r02_traffic_ggn_vp.json (read by bench.py for roofline.traffic; r01_traffic_ggn_vp.json is round 1's capture).  usage: traffic_summary.py traffic_step.csv out.json"""
 import collections, csv, json, sys
 lines = [l for l in open(sys.argv[1]) if not l.startswith('==')]
 rows = list(csv.DictReader(lines))
