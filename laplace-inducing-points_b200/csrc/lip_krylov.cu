@@ -19,6 +19,9 @@
 // 8 vector launches per GKL step (round 1: ~30), 6 per Lanczos step with two CGS passes.
 // All reductions are deterministic: per-CTA partials summed in a fixed order by the last CTA to arrive (an integer ticket is
 // the only atomic), so results do not depend on scheduling.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -180,6 +183,7 @@ struct ProjectArgs {
   float* h;                      // h[b][kpad]
   unsigned* counter;
   int64_t n;
+  const int* gate;               // optional: columns with gate[b] == 0 are skipped (conditional second re-orthogonalisation pass)
 };
 
 __global__ void __launch_bounds__(VT) project_kernel(ProjectArgs a) {
@@ -188,6 +192,7 @@ __global__ void __launch_bounds__(VT) project_kernel(ProjectArgs a) {
   float* acc = smem + RCHUNK;    // kk
   __shared__ float red[8][33];
   const int b = blockIdx.y, cta = blockIdx.x, np = gridDim.x;
+  if (a.gate && a.gate[b] == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = VT >> 5;
   const int kk = a.kk;
   for (int j = threadIdx.x; j < kk; j += VT) acc[j] = 0.f;
@@ -316,12 +321,14 @@ struct SubtractArgs {
   float* part; float* nrm; unsigned* counter;
   int64_t n;
   int sq_out;
+  const int* gate;     // optional: columns with gate[b] == 0 are skipped
 };
 
 __global__ void __launch_bounds__(VT) subtract_kernel(SubtractArgs a) {
   extern __shared__ float hs[];
   __shared__ float sm[32];
   const int b = blockIdx.y, np = gridDim.x, kk = a.kk;
+  if (a.gate && a.gate[b] == 0) return;
   const float inv = a.scal ? 1.f / a.scal[b] : 1.f;
   for (int j = threadIdx.x; j < kk; j += VT) hs[j] = a.h[(int64_t)b * a.kpad + j];
   __syncthreads();
@@ -417,6 +424,51 @@ __global__ void lanczos_record_kernel(float* diag, float* off, const float* h, i
   if (b >= B) return;
   diag[(int64_t)b * k + i] = h[(int64_t)b * kpad + i];
   if (i > 0) off[(int64_t)b * (k - 1) + i - 1] = 0.5f * (h[(int64_t)b * kpad + i - 1] + len[b]);
+}
+// e[b][i] = val, e[b][i-1] = 0: the coefficient vector of basis vector i (reduced GKL u vectors)
+__global__ void unit_kernel(float* e, int64_t ld, int64_t i, float val, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  e[(int64_t)b * ld + i] = val;
+  if (i > 0) e[(int64_t)b * ld + i - 1] = 0.f;
+}
+// beta[b] *= nv[b];  dst[b*stride + idx] = beta[b]   (reduced GKL: the norm AFTER the projection is the bidiagonal entry)
+// Breakdown: when the projection leaves less than 1e-6 of the vector (the fp32 noise floor is ~1e-7) the Krylov space is exhausted and
+// beta_{i+1} = 0 in exact arithmetic.  The column is marked dead: beta_{i+1} and every later beta are recorded as 0, later alphas as 1,
+// so the trailing block of the bidiagonal is exactly decoupled from e1 (it carries weight ~1e-13 in the explicit recurrence, which keeps
+// iterating on rounding noise there); nv is set to 1 so that the remainder is stored unscaled instead of blown up to unit norm.
+__global__ void beta_fix_kernel(float* dst, int64_t stride, int64_t idx, float* beta, float* nv, int* dead, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (dead[b] || !(nv[b] >= 1e-6f)) {
+    dead[b] = 1;
+    beta[b] = 0.f;
+    nv[b] = 1.f;
+    dst[(int64_t)b * stride + idx] = 0.f;
+    return;
+  }
+  const float t = beta[b] * nv[b];
+  beta[b] = t;
+  dst[(int64_t)b * stride + idx] = t;
+}
+// dst[b*stride + idx] = dead[b] ? 1 : src[b]
+__global__ void record_alive_kernel(float* dst, int64_t stride, int64_t idx, const float* src, const int* dead, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) dst[(int64_t)b * stride + idx] = dead[b] ? 1.f : src[b];
+}
+// "twice is enough": gate[b] = 1 when the projection removed more than half of the (unit) vector, i.e. cancellation left the
+// remainder with a relative error that a second pass has to clean up;  count[0] += number of gated columns (diagnostics)
+__global__ void reorth_gate_kernel(int* gate, const float* nv, float thr, int B, int* count) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int g = !(nv[b] >= thr) ? 1 : 0;       // NaN gates too
+  gate[b] = g;
+  if (g && count) atomicAdd(count, 1);
+}
+// nv[b] = gate[b] ? nv2[b] : nv[b]
+__global__ void gate_merge_kernel(float* nv, const float* nv2, const int* gate, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && gate[b]) nv[b] = nv2[b];
 }
 // out[b] = q[b] * nrm[b]^2
 __global__ void quad_scale_kernel(float* out, const float* q, const float* nrm, int B) {
@@ -778,9 +830,9 @@ int launch_axpy_norm(AxpyNormArgs a, int64_t B, const Red& r, cudaStream_t st) {
 }
 
 int launch_project(const float* Q, int64_t ldq, int64_t qsb, int kk, const float* w, int64_t ldw, int64_t n, int64_t B,
-                   const Red& r, cudaStream_t st) {
+                   const Red& r, cudaStream_t st, const int* gate = nullptr) {
   if (kk <= 0) return LIP_OK;
-  ProjectArgs a{Q, ldq, qsb, kk, w, ldw, r.ppart, r.kpad, r.h, r.counter, n};
+  ProjectArgs a{Q, ldq, qsb, kk, w, ldw, r.ppart, r.kpad, r.h, r.counter, n, gate};
   const int np = project_ctas(n, B);
   dim3 grid(np, (unsigned)B);
   project_kernel<<<grid, VT, sizeof(float) * (RCHUNK + (size_t)kk), st>>>(a);
@@ -789,8 +841,9 @@ int launch_project(const float* Q, int64_t ldq, int64_t qsb, int kk, const float
 }
 
 int launch_subtract(const float* Q, int64_t ldq, int64_t qsb, int kk, const float* w, int64_t ldw, const float* scal, float* out,
-                    int64_t ldo, float* nrm, int64_t n, int64_t B, const Red& r, cudaStream_t st) {
-  SubtractArgs a{Q, ldq, qsb, kk, r.h, r.kpad, w, ldw, (!al16(w) || ldw % 4 != 0) ? 1 : 0, scal, out, ldo, r.part, nrm, r.counter, n, r.sq_out};
+                    int64_t ldo, float* nrm, int64_t n, int64_t B, const Red& r, cudaStream_t st, const int* gate = nullptr) {
+  SubtractArgs a{Q, ldq, qsb, kk, r.h, r.kpad, w, ldw, (!al16(w) || ldw % 4 != 0) ? 1 : 0, scal, out, ldo, r.part, nrm, r.counter, n, r.sq_out,
+                 gate};
   const int np = column_ctas(n, B, VT * 4);
   dim3 grid(np, (unsigned)B);
   subtract_kernel<<<grid, VT, sizeof(float) * (size_t)(kk > 0 ? kk : 1), st>>>(a);
@@ -981,22 +1034,35 @@ int lanczos_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k
 size_t gkl_ws_bytes(const Op& o, int64_t k, int64_t B) {
   const int64_t nc = o.n_in, nr = o.n_out, ldu = pad4(nr), ldv = pad4(nc);
   return op_ws_bytes(o, B) + red_bytes(std::max(nc, nr), B, k) + rsz((size_t)B * ldu, 4) + rsz((size_t)B * ldv, 4) +
-         4 * rsz((size_t)B * (nc + 64), 4) + 3 * rsz((size_t)B * (nr + 64), 4) + 6 * rsz((size_t)B, 4) + 8192;
+         4 * rsz((size_t)B * (nc + 64), 4) + 3 * rsz((size_t)B * (nr + 64), 4) + 6 * rsz((size_t)B, 4) + 8192 +
+         rsz((size_t)B * pad4(k), 4) + 3 * rsz((size_t)B + 4, 4);      // reduced u basis: unit vectors, second-pass gates, dead flags
 }
 
 // sh == nullptr: whole vectors.  Otherwise (GKL kind only) Us / Vs hold this rank's slices: a u vector is stored as
 // [its nloc parameter-space columns | its dloc output-space rows], a v vector as its nloc columns; v0 is the FULL start vector.
+//
+// reduced (LIP_LINOP_GKL only; the u basis is not returned): for A = [sqrt(alpha) I; W^T] the parameter-space block of every u vector
+// lies in span(v_0 .. v_i) - u_i[:D] = V c_i - so u_i is carried as the SHORT vector [c_i (k coefficients) ; u_i[D:] (d entries)].
+// With V orthonormal (it is re-orthogonalised every step) the Euclidean inner product of the short vectors IS the inner product of
+// the long ones, A v_i = [sqrt(alpha) e_i ; W^T v_i], and since A^T u_i - alpha_i v_i is re-orthogonalised against V anyway,
+//   v_{i+1} beta_{i+1} = (I - V V^T)(A^T u_i - alpha_i v_i) = (I - V V^T)(W u_i[D:] - alpha_i v_i)
+// (the sqrt(alpha) V c_i term is annihilated by the projection), with beta_{i+1} read AFTER the projection.  Same recurrence in exact
+// arithmetic, same rounding level in fp32, but the O(k^2 (D + d)) re-orthogonalisation traffic of the u basis - half of the HBM bytes
+// of a GKL logdet, and half of its memory - becomes O(k^2 (k + d)): L2-resident.  In a sharded run the short u side is simply
+// replicated on every rank (no collective).
 int gkl_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, int64_t B, float* Us, int64_t ldu, float* Vs, int64_t ldv,
-            float* alphas, float* betas, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st) {
+            float* alphas, float* betas, float* norm0, void* ws, size_t ws_bytes, cudaStream_t st, bool reduced = false) {
   const int64_t nc = o.n_in, nr = o.n_out;
   const bool gkl = o.op->kind == LIP_LINOP_GKL;
+  LIP_REQUIRE(!reduced || gkl, "gkl_run: the reduced u basis needs the LIP_LINOP_GKL operator");
+  const int64_t kp = pad4(k);
   LIP_REQUIRE(B <= MAX_COLUMNS, "gkl_run: at most 65535 probe columns per call, got %lld", (long long)B);
   LIP_REQUIRE(!sh || gkl, "sharded gkl: only the LIP_LINOP_GKL operator is supported");
   LIP_REQUIRE(k >= 1 && k <= std::min(nc, nr), "num_matvecs=%lld exceeds the operator dimensions (%lld, %lld)", (long long)k,
               (long long)nr, (long long)nc);
   const int64_t D = o.D, d = o.d;
   const int64_t ncl = sh ? sh->nloc : nc;                   // local length of a v vector
-  const int64_t nrl = sh ? sh->nloc + sh->dloc : nr;        // local length of a u vector
+  const int64_t nrl = reduced ? kp + d : (sh ? sh->nloc + sh->dloc : nr);        // local length of a u vector
   const int64_t c0 = sh ? sh->off : 0, d0 = sh ? sh->doff : 0;
   LIP_REQUIRE(Us && Vs && al16(Us) && al16(Vs) && ldu % 4 == 0 && ldv % 4 == 0 && ldu >= nrl && ldv >= ncl,
               "gkl: bases must be 16-byte aligned with leading dimensions that are multiples of 4");
@@ -1008,7 +1074,14 @@ int gkl_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, in
   rc = red_carve(r, bp, std::max(ncl, nrl), B, k, st);
   if (rc) return rc;
   r.sq_out = sh ? 1 : 0;
+  Red ru = r;                                         // reduction scratch / collectives of the u side
+  const Shard* shu = reduced ? nullptr : sh;
+  if (reduced) ru.sq_out = 0;
   const int64_t lu = pad4(nrl), lv = pad4(ncl);
+  float* ebuf = reduced ? bp.take<float>((size_t)B * kp) : nullptr;   // sqrt(alpha) e_i
+  int* gate = reduced ? bp.take<int>((size_t)B + 4) : nullptr;        // [B] second-pass gates + [1] how many fired
+  int* dead = reduced ? bp.take<int>((size_t)B + 4) : nullptr;        // [B] columns whose Krylov space is exhausted
+  float* nv2 = reduced ? bp.take<float>((size_t)B) : nullptr;
   float* u = bp.take<float>((size_t)B * lu);          // working u (local slice), padded rows
   float* v = bp.take<float>((size_t)B * lv);          // working v (local slice), padded rows
   float* vc = bp.take<float>((size_t)B * nc);         // contiguous FULL A input
@@ -1026,6 +1099,12 @@ int gkl_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, in
   if (!bp.ok) { set_error("gkl: workspace too small (%zu bytes given)", ws_bytes); return LIP_ERR_WORKSPACE; }
   const int64_t usb = k * ldu, vsb = k * ldv;
   if (lu != nrl) LIP_CHECK_CUDA(cudaMemsetAsync(u, 0, sizeof(float) * (size_t)B * lu, st));
+  if (reduced) {
+    LIP_CHECK_CUDA(cudaMemsetAsync(ebuf, 0, sizeof(float) * (size_t)B * kp, st));
+    LIP_CHECK_CUDA(cudaMemsetAsync(gate, 0, sizeof(int) * ((size_t)B + 4), st));
+    LIP_CHECK_CUDA(cudaMemsetAsync(dead, 0, sizeof(int) * ((size_t)B + 4), st));
+    LIP_CHECK_CUDA(cudaMemsetAsync(nv2, 0, sizeof(float) * (size_t)B, st));
+  }
   if (lv != ncl) LIP_CHECK_CUDA(cudaMemsetAsync(v, 0, sizeof(float) * (size_t)B * lv, st));
   LIP_CHECK_CUDA(cudaMemsetAsync(Us, 0, sizeof(float) * (size_t)B * usb, st));
   LIP_CHECK_CUDA(cudaMemsetAsync(Vs, 0, sizeof(float) * (size_t)B * vsb, st));
@@ -1055,32 +1134,42 @@ int gkl_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, in
     AxpyNormArgs a{};
     if (gkl) {
       rc = lip_wt_apply(o.op->model, vc, tu, B, o.op->scale, LIP_FACTOR_SQRT, o.mws, o.mws_bytes, st); if (rc) return rc;
-      a.x1 = vc + c0; a.ld1 = D; a.n1 = ncl; a.s1 = sa; a.x2 = tu + d0; a.ld2 = d;
+      if (reduced) {
+        unit_kernel<<<gB, 128, 0, st>>>(ebuf, kp, i, sa, (int)B);
+        LIP_LAUNCH_CHECK();
+        a.x1 = ebuf; a.ld1 = kp; a.n1 = kp; a.s1 = 1.f; a.x2 = tu; a.ld2 = d;
+      } else {
+        a.x1 = vc + c0; a.ld1 = D; a.n1 = ncl; a.s1 = sa; a.x2 = tu + d0; a.ld2 = d;
+      }
     } else {
       rc = op_apply(o, vc, tu, B, 0, st); if (rc) return rc;
       a.x1 = tu; a.ld1 = nr; a.n1 = nr; a.s1 = 1.f;
     }
     if (i > 0) { a.y = Us + (i - 1) * ldu; a.ldy = ldu; a.ysb = usb; a.coef = beta; }
     a.out = u; a.ldo = lu; a.nrm = alpha; a.n = nrl;
-    rc = launch_axpy_norm(a, B, r, st); if (rc) return rc;
-    rc = shard_norm(sh, alpha, B, st); if (rc) return rc;
-    record_kernel<<<gB, 128, 0, st>>>(alphas, k, i, alpha, (int)B);
+    rc = launch_axpy_norm(a, B, ru, st); if (rc) return rc;
+    rc = shard_norm(shu, alpha, B, st); if (rc) return rc;
+    if (reduced) record_alive_kernel<<<gB, 128, 0, st>>>(alphas, k, i, alpha, dead, (int)B);
+    else record_kernel<<<gB, 128, 0, st>>>(alphas, k, i, alpha, (int)B);
     LIP_LAUNCH_CHECK();
     // ---- u <- normalise, CGS against U[0..i-1], renormalise, store
-    rc = launch_project(Us, ldu, usb, (int)i, u, lu, nrl, B, r, st); if (rc) return rc;
-    if (i > 0) { rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc; }
-    rc = launch_subtract(Us, ldu, usb, (int)i, u, lu, alpha, u, lu, nu, nrl, B, r, st); if (rc) return rc;
-    rc = shard_norm(sh, nu, B, st); if (rc) return rc;
+    rc = launch_project(Us, ldu, usb, (int)i, u, lu, nrl, B, ru, st); if (rc) return rc;
+    if (i > 0) { rc = shard_allreduce(shu, ru.h, (size_t)B * ru.kpad, st); if (rc) return rc; }
+    rc = launch_subtract(Us, ldu, usb, (int)i, u, lu, alpha, u, lu, nu, nrl, B, ru, st); if (rc) return rc;
+    rc = shard_norm(shu, nu, B, st); if (rc) return rc;
     {
       ScaleStoreArgs s{}; s.x = u; s.ldx = lu; s.scal = nu; s.o1 = Us + i * ldu; s.ld1 = ldu; s.o1sb = usb; s.n = nrl;
-      if (gkl && sh) { s.o2 = ucD + c0; s.ld2 = D; s.n2 = ncl; s.o3 = udloc; s.ld3 = sh->dsh; }
+      if (reduced) { s.o2 = nullptr; s.n2 = kp; s.o3 = ucd; s.ld3 = d; }
+      else if (gkl && sh) { s.o2 = ucD + c0; s.ld2 = D; s.n2 = ncl; s.o3 = udloc; s.ld3 = sh->dsh; }
       else if (gkl) { s.o2 = ucD; s.ld2 = D; s.n2 = D; s.o3 = ucd; s.ld3 = d; }
       else { s.o2 = uc; s.ld2 = nr; s.n2 = nr; }
       rc = launch_scale_store(s, B, st); if (rc) return rc;
     }
     if (i + 1 == k) break;              // the last v would not be used (matfree computes it; it does not enter B)
     // ---- w = A^T u_i - alpha_i v_i;  beta_{i+1} = |w|
-    if (gkl) {
+    if (reduced) {
+      rc = lip_w_apply(o.op->model, ucd, wv, B, o.op->scale, LIP_FACTOR_SQRT, nullptr, 0.f, o.mws, o.mws_bytes, st); if (rc) return rc;
+    } else if (gkl) {
       if (sh) { rc = shard_allgather(sh, udloc, sh->dsh, gath, ucd, d, B, st); if (rc) return rc; }
       // sharded: ucD holds only this rank's columns (zeros elsewhere), so only this rank's columns of wv are meaningful - the ones used
       rc = lip_w_apply(o.op->model, ucd, wv, B, o.op->scale, LIP_FACTOR_SQRT, ucD, sa, o.mws, o.mws_bytes, st); if (rc) return rc;
@@ -1091,17 +1180,42 @@ int gkl_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k, in
     c.out = v; c.ldo = lv; c.nrm = beta; c.n = ncl;
     rc = launch_axpy_norm(c, B, r, st); if (rc) return rc;
     rc = shard_norm(sh, beta, B, st); if (rc) return rc;
-    record_kernel<<<gB, 128, 0, st>>>(betas, k, i + 1, beta, (int)B);
-    LIP_LAUNCH_CHECK();
+    if (!reduced) {
+      record_kernel<<<gB, 128, 0, st>>>(betas, k, i + 1, beta, (int)B);
+      LIP_LAUNCH_CHECK();
+    }
     rc = launch_project(Vs, ldv, vsb, (int)(i + 1), v, lv, ncl, B, r, st); if (rc) return rc;
     rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
     rc = launch_subtract(Vs, ldv, vsb, (int)(i + 1), v, lv, beta, v, lv, nv, ncl, B, r, st); if (rc) return rc;
     rc = shard_norm(sh, nv, B, st); if (rc) return rc;
+    if (reduced) {
+      // W u_i[D:] - alpha_i v_i still carries the sqrt(alpha) V c_i component that the explicit recurrence cancels by addition; where
+      // the projection removed most of the vector (small beta_{i+1}, or a breakdown) the remainder is re-orthogonalised once more -
+      // per column, decided on the device: the second-pass kernels return at once for the other columns
+      reorth_gate_kernel<<<gB, 128, 0, st>>>(gate, nv, 0.5f, (int)B, gate + B);
+      LIP_LAUNCH_CHECK();
+      rc = launch_project(Vs, ldv, vsb, (int)(i + 1), v, lv, ncl, B, r, st, gate); if (rc) return rc;
+      rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
+      rc = launch_subtract(Vs, ldv, vsb, (int)(i + 1), v, lv, nullptr, v, lv, nv2, ncl, B, r, st, gate); if (rc) return rc;
+      rc = shard_norm(sh, nv2, B, st); if (rc) return rc;
+      gate_merge_kernel<<<gB, 128, 0, st>>>(nv, nv2, gate, (int)B);
+      LIP_LAUNCH_CHECK();
+      // beta_{i+1} = |(I - V V^T)(W u_i[D:] - alpha_i v_i)| = (norm before the projection) x (norm of the projected unit vector)
+      beta_fix_kernel<<<gB, 128, 0, st>>>(betas, k, i + 1, beta, nv, dead, (int)B);
+      LIP_LAUNCH_CHECK();
+    }
     {
       ScaleStoreArgs s{}; s.x = v; s.ldx = lv; s.scal = nv; s.o1 = Vs + (i + 1) * ldv; s.ld1 = ldv; s.o1sb = vsb; s.n2 = ncl; s.n = ncl;
       if (sh) { s.o2 = vloc; s.ld2 = sh->Dsh; } else { s.o2 = vc; s.ld2 = nc; }
       rc = launch_scale_store(s, B, st); if (rc) return rc;
     }
+  }
+  if (reduced && getenv("LIP_GKL_DEBUG")) {      // diagnostics only (synchronises): how many (step, column) pairs took the second pass
+    int fired = 0;
+    LIP_CHECK_CUDA(cudaStreamSynchronize(st));
+    LIP_CHECK_CUDA(cudaMemcpy(&fired, gate + B, sizeof(int), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[lip gkl reduced] k=%lld B=%lld: second re-orthogonalisation pass on %d of %lld (step, column) pairs\n", (long long)k,
+            (long long)B, fired, (long long)((k - 1) * B));
   }
   return LIP_OK;
 }
@@ -1310,12 +1424,22 @@ int lip_gkl_bidiag(const lip_linop* op, const float* v0, int64_t ldv0, int64_t k
   return gkl_run(o, nullptr, v0, ldv0, k, B, Us, ldu, Vs, ldv, alphas, betas, norm0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// the GKL logdet of the structured operator carries its u basis in reduced form (gkl_run); LIP_GKL_REDUCED=0 keeps the explicit basis
+static bool slq_reduced(const Op& o, int form) {
+  static const int on = [] {
+    const char* e = getenv("LIP_GKL_REDUCED");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on && form == LIP_SLQ_GKL && o.op->kind == LIP_LINOP_GKL;
+}
+
 static size_t slq_ws_bytes(const Op& o, int form, int64_t k, int64_t B, int world) {
   const int64_t nc = o.n_in, nr = o.n_out;
   const int64_t ncl = pad4(ceil_div(nc, world)) + 4, nrl = ncl + pad4(ceil_div(std::max<int64_t>(o.d, 0), world)) + 4;
   const size_t tri = lip_tridiag_scratch_bytes(k, B, 0) + 4 * rsz((size_t)B * k, 4) + 2 * rsz((size_t)B, 4);
   size_t bases = rsz((size_t)B * k * pad4(world > 1 ? ncl : nc), 4);
-  if (form == LIP_SLQ_GKL) bases += rsz((size_t)B * k * pad4(world > 1 ? nrl : nr), 4);
+  if (slq_reduced(o, form)) bases += rsz((size_t)B * k * pad4(pad4(k) + o.d), 4);
+  else if (form == LIP_SLQ_GKL) bases += rsz((size_t)B * k * pad4(world > 1 ? nrl : nr), 4);
   return (form == LIP_SLQ_GKL ? gkl_ws_bytes(o, k, B) : lanczos_ws_bytes(o, k, B)) + bases + tri + 8192;
 }
 
@@ -1343,7 +1467,8 @@ int lip_slq_quadrature_sharded(const lip_linop* op, lip_comm* comm, const float*
     sh = &shard;
   }
   const int64_t nc = o.n_in, nr = o.n_out;
-  const int64_t ldv = pad4(sh ? sh->nloc : nc), ldu = pad4(sh ? sh->nloc + sh->dloc : nr);
+  const bool reduced = slq_reduced(o, form);
+  const int64_t ldv = pad4(sh ? sh->nloc : nc), ldu = reduced ? pad4(pad4(k) + o.d) : pad4(sh ? sh->nloc + sh->dloc : nr);
   Bump bp(workspace, workspace_bytes);
   float* td = bp.take<float>((size_t)B * k);
   float* to = bp.take<float>((size_t)B * k);
@@ -1363,7 +1488,21 @@ int lip_slq_quadrature_sharded(const lip_linop* op, lip_comm* comm, const float*
   if (form == LIP_SLQ_LANCZOS) {
     rc = lanczos_run(o, sh, probes, ldp, k, B, 2, Vs, ldv, td, to, nrm, bp.p, rest, st);
   } else {
-    rc = gkl_run(o, sh, probes, ldp, k, B, Us, ldu, Vs, ldv, al, be, nrm, bp.p, rest, st);
+    rc = gkl_run(o, sh, probes, ldp, k, B, Us, ldu, Vs, ldv, al, be, nrm, bp.p, rest, st, reduced);
+    if (!rc && getenv("LIP_GKL_DEBUG")) {        // diagnostics only (synchronises): the bidiagonal of the first column
+      std::vector<float> ha((size_t)k), hb((size_t)k);
+      LIP_CHECK_CUDA(cudaStreamSynchronize(st));
+      LIP_CHECK_CUDA(cudaMemcpy(ha.data(), al, sizeof(float) * k, cudaMemcpyDeviceToHost));
+      LIP_CHECK_CUDA(cudaMemcpy(hb.data(), be, sizeof(float) * k, cudaMemcpyDeviceToHost));
+      int64_t bad = -1;
+      for (int64_t i = 0; i < k && bad < 0; ++i) if (!(ha[i] == ha[i]) || !(hb[i] == hb[i]) || ha[i] > 1e30f || hb[i] > 1e30f) bad = i;
+      fprintf(stderr, "[lip gkl] reduced=%d k=%lld first non-finite bidiagonal entry: %lld\n", (int)reduced, (long long)k, (long long)bad);
+      const bool all = getenv("LIP_GKL_DEBUG")[0] == '2';
+      const int64_t lo = all ? 0 : (bad >= 0 ? std::max<int64_t>(0, bad - 4) : 0);
+      const int64_t hi = all ? (bad >= 0 ? bad + 1 : k) : (bad >= 0 ? std::min<int64_t>(k, bad + 2) : std::min<int64_t>(k, 8));
+      for (int64_t i = lo; i < hi; ++i) fprintf(stderr, "   i=%lld alpha=%.6e beta=%.6e\n", (long long)i, ha[i], hb[i]);
+      if (bad < 0) for (int64_t i = std::max<int64_t>(8, k - 6); i < k; ++i) fprintf(stderr, "   i=%lld alpha=%.6e beta=%.6e\n", (long long)i, ha[i], hb[i]);
+    }
     if (!rc) rc = lip_bidiag_to_tridiag(al, be, td, to, k, B, st);
   }
   if (rc) return rc;
