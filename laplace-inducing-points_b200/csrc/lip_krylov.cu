@@ -378,6 +378,100 @@ __global__ void __launch_bounds__(VT) subtract_kernel(SubtractArgs a) {
   }
 }
 
+// ---- short vectors (n <= SHORT_N): many basis rows, few columns ------------------------------------------------------------------
+// The kernels above cut the COLUMNS of a long vector over the CTAs; on a short one (the reduced u vectors of the GKL logdet, k + d =
+// 5 532 floats at C3b; the d = M K vectors of the sampler's Gram-space Lanczos) that leaves 6 CTAs walking hundreds of rows one after
+// the other (60 us per launch at 300 rows).  Here the ROWS carry the parallelism: one warp per basis row for the coefficients, and
+// (64 float4 columns) x (4 row groups) per CTA for the update, summed over the row groups in a fixed order.
+constexpr int64_t SHORT_N = 16384;
+constexpr int SCG = 64, SRG = VT / SCG;
+
+__global__ void __launch_bounds__(VT) project_short_kernel(ProjectArgs a) {
+  const int b = blockIdx.y;
+  if (a.gate && a.gate[b] == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (VT / 32) + warp;
+  if (j >= a.kk) return;
+  const float* wb = a.w + (int64_t)b * a.ldw;
+  const float4* q = reinterpret_cast<const float4*>(a.Q + (int64_t)b * a.qsb + (int64_t)j * a.ldq);
+  const bool wal = (((uintptr_t)wb) & 15) == 0;
+  const int64_t n4 = (a.n + 3) >> 2;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int64_t i = lane; i < n4; i += 32) {
+    const float4 qv = __ldg(q + i);
+    float4 wv;
+    if (wal) {
+      wv = __ldg(reinterpret_cast<const float4*>(wb) + i);
+    } else {
+      const int64_t j0 = i << 2;
+      wv.x = wb[j0];
+      wv.y = (j0 + 1 < a.n) ? wb[j0 + 1] : 0.f;
+      wv.z = (j0 + 2 < a.n) ? wb[j0 + 2] : 0.f;
+      wv.w = (j0 + 3 < a.n) ? wb[j0 + 3] : 0.f;
+    }
+    acc += (qv.x * wv.x + qv.y * wv.y) + (qv.z * wv.z + qv.w * wv.w);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) a.h[(int64_t)b * a.kpad + j] = acc;
+}
+
+__global__ void __launch_bounds__(VT) subtract_short_kernel(SubtractArgs a) {
+  extern __shared__ __align__(16) float hs[];      // kk coefficients (padded to 4), then SRG x SCG float4 partial sums
+  __shared__ float sm[32];
+  const int b = blockIdx.y, np = gridDim.x, kk = a.kk;
+  if (a.gate && a.gate[b] == 0) return;
+  float4* ps = reinterpret_cast<float4*>(hs + ((kk + 3) & ~3));
+  const float inv = a.scal ? 1.f / a.scal[b] : 1.f;
+  for (int j = threadIdx.x; j < kk; j += VT) hs[j] = a.h[(int64_t)b * a.kpad + j];
+  __syncthreads();
+  const int cg = threadIdx.x % SCG, rg = threadIdx.x / SCG;
+  const int64_t i = (int64_t)blockIdx.x * SCG + cg;          // float4 column
+  const int64_t n4 = (a.n + 3) >> 2, step = a.ldq >> 2;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    const float4* q = reinterpret_cast<const float4*>(a.Q + (int64_t)b * a.qsb) + i;
+#pragma unroll 8
+    for (int j = rg; j < kk; j += SRG) {
+      const float4 q0 = __ldg(q + (int64_t)j * step);
+      const float h0 = hs[j];
+      acc.x = fmaf(h0, q0.x, acc.x); acc.y = fmaf(h0, q0.y, acc.y); acc.z = fmaf(h0, q0.z, acc.z); acc.w = fmaf(h0, q0.w, acc.w);
+    }
+  }
+  ps[rg * SCG + cg] = acc;
+  __syncthreads();
+  float nacc = 0.f;
+  if (rg == 0 && i < n4) {
+    const float* wb = a.w + (int64_t)b * a.ldw;
+    float4 w;
+    if (a.w_scalar) {
+      const int64_t j0 = i << 2;
+      w.x = wb[j0];
+      w.y = (j0 + 1 < a.n) ? wb[j0 + 1] : 0.f;
+      w.z = (j0 + 2 < a.n) ? wb[j0 + 2] : 0.f;
+      w.w = (j0 + 3 < a.n) ? wb[j0 + 3] : 0.f;
+    } else {
+      w = *reinterpret_cast<const float4*>(wb + (i << 2));
+    }
+    float4 t = ps[cg];
+#pragma unroll
+    for (int g = 1; g < SRG; ++g) {
+      const float4 u = ps[g * SCG + cg];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    w.x = (w.x - t.x) * inv; w.y = (w.y - t.y) * inv; w.z = (w.z - t.z) * inv; w.w = (w.w - t.w) * inv;
+    *reinterpret_cast<float4*>(a.out + (int64_t)b * a.ldo + (i << 2)) = w;
+    nacc = (w.x * w.x + w.y * w.y) + (w.z * w.z + w.w * w.w);
+  }
+  if (!a.nrm) return;
+  nacc = block_sum(nacc, sm);
+  if (threadIdx.x == 0) a.part[(int64_t)b * np + blockIdx.x] = nacc;
+  if (last_block(a.counter + b, np)) {
+    const float t = sum_fixed(a.part + (int64_t)b * np, np, sm);
+    if (threadIdx.x == 0) a.nrm[b] = a.sq_out ? t : sqrtf(t);
+  }
+}
+
 // ---- scale_store: y = x / scal[b] into up to three destinations -------------------------------------------------------
 //   o1 (stride ld1, optional): all n columns              (the basis row)
 //   o2 (stride ld2, optional): columns [0, n2)            (contiguous operand of the next mat-vec)
@@ -817,6 +911,14 @@ struct Red {            // reduction scratch shared by all kernels of a recurren
   int sq_out = 0;               // sharded recurrences: norms leave the kernels as rank-local sums of squares
 };
 
+bool short_vector_kernels() {
+  static const int on = [] {
+    const char* e = getenv("LIP_KRYLOV_SHORT");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on != 0;
+}
+
 int launch_axpy_norm(AxpyNormArgs a, int64_t B, const Red& r, cudaStream_t st) {
   a.part = r.part; a.counter = r.counter; a.sq_out = r.sq_out;
   const bool v4 = al16(a.x1) && (a.ld1 % 4 == 0) && (a.n1 % 4 == 0 || a.n1 >= a.n) && (!a.x2 || (al16(a.x2) && a.ld2 % 4 == 0)) &&
@@ -833,6 +935,11 @@ int launch_project(const float* Q, int64_t ldq, int64_t qsb, int kk, const float
                    const Red& r, cudaStream_t st, const int* gate = nullptr) {
   if (kk <= 0) return LIP_OK;
   ProjectArgs a{Q, ldq, qsb, kk, w, ldw, r.ppart, r.kpad, r.h, r.counter, n, gate};
+  if (n <= SHORT_N && short_vector_kernels()) {
+    project_short_kernel<<<dim3((unsigned)ceil_div(kk, VT / 32), (unsigned)B), VT, 0, st>>>(a);
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
   const int np = project_ctas(n, B);
   dim3 grid(np, (unsigned)B);
   project_kernel<<<grid, VT, sizeof(float) * (RCHUNK + (size_t)kk), st>>>(a);
@@ -844,6 +951,13 @@ int launch_subtract(const float* Q, int64_t ldq, int64_t qsb, int kk, const floa
                     int64_t ldo, float* nrm, int64_t n, int64_t B, const Red& r, cudaStream_t st, const int* gate = nullptr) {
   SubtractArgs a{Q, ldq, qsb, kk, r.h, r.kpad, w, ldw, (!al16(w) || ldw % 4 != 0) ? 1 : 0, scal, out, ldo, r.part, nrm, r.counter, n, r.sq_out,
                  gate};
+  if (n <= SHORT_N && short_vector_kernels() && kk <= 4096) {
+    const int64_t n4 = (n + 3) >> 2;
+    const size_t smem = sizeof(float) * (size_t)(((kk + 3) & ~3) + VT * 4);
+    subtract_short_kernel<<<dim3((unsigned)ceil_div(n4, SCG), (unsigned)B), VT, smem, st>>>(a);
+    LIP_LAUNCH_CHECK();
+    return LIP_OK;
+  }
   const int np = column_ctas(n, B, VT * 4);
   dim3 grid(np, (unsigned)B);
   subtract_kernel<<<grid, VT, sizeof(float) * (size_t)(kk > 0 ? kk : 1), st>>>(a);

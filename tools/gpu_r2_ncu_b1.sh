@@ -17,5 +17,5 @@ torch.cuda.synchronize()
 print(q)
 PY
 timeout 300 python /tmp/slq_b1.py > gpurun_out/r2_b1_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 10600 -c 105 --csv --log-file gpurun_out/r2_launches_slq_b1_step300.csv python /tmp/slq_b1.py > gpurun_out/r2_b1_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 12000 -c 120 --csv --log-file gpurun_out/r2_launches_slq_b1_reduced_step300.csv python /tmp/slq_b1.py > gpurun_out/r2_b1_ncu.log 2>&1
 python tools/summarize_launches.py gpurun_out/r2_launches_slq_b1_step300.csv 25
