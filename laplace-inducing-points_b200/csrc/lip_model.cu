@@ -638,11 +638,22 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
     if (rc) return rc;
     cur ^= 1; cur_ld = ldp; cur_split = true;
   }
+  // One or two probes (the mat-vecs of a single-probe Krylov recurrence): every GEMM is a handful of CTAs and the sweep is a chain of
+  // launch latencies.  The weight-gradient GEMM of a layer does not feed the delta chain, so it runs on the side stream next to the
+  // delta back-propagation of the same layer (fork / join with events: capturable).  The only shared buffer is the delta itself: the
+  // back-propagation of layer l - 1 overwrites the buffer that the weight gradient of layer l + 1 ... l reads, hence the wait below.
+  static const int fork_env = getenv("LIP_VJP_FORK") ? atoi(getenv("LIP_VJP_FORK")) : 1;
+  const bool fork = fork_env && m->tc_on && m->side != nullptr && B <= 2 &&
+                    (int)m->ev_split.size() >= nL * lip_model::SPLIT_CHUNKS && lip_model::SPLIT_CHUNKS >= 2;
+  cudaEvent_t wg_done = nullptr;       // weight gradient still reading the delta buffer that the next back-propagation overwrites
+  cudaEvent_t wg_last = nullptr;
   for (int l = lfirst; l >= 0; --l) {
     const DenseLayer& Ld = m->L[l];
     const bool tc = m->tc_on && m->tc_layer[l];
     const float* d_hi = w.hi[cur];
     const float* d_lo = cur_split ? w.lo[cur] : nullptr;
+    cudaEvent_t wg_prev = wg_done;
+    wg_done = nullptr;
     if (tc) {  // weight gradient [in x out] = A_l^T [in x M] * Delta [M x out]
       TcGemmProblem p;
       p.M = Ld.in; p.N = Ld.out; p.K = m->M; p.batch = B;
@@ -653,8 +664,18 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
       p.C = out + Ld.woff; p.c_sz = w.ldo; p.c_sm = Ld.out;
       p.epi.scale = scale;
       if (add) { p.epi.add = add + Ld.woff; p.epi.add_sz = w.lda; p.epi.add_scale = add_scale; }
-      int rc = gemm_tc(p, st);
-      if (rc) return rc;
+      if (fork) {
+        cudaEvent_t ready = m->ev_split[l * lip_model::SPLIT_CHUNKS], done = m->ev_split[l * lip_model::SPLIT_CHUNKS + 1];
+        LIP_CHECK_CUDA(cudaEventRecord(ready, st));
+        LIP_CHECK_CUDA(cudaStreamWaitEvent(m->side, ready, 0));
+        int rc = gemm_tc(p, m->side);
+        if (rc) return rc;
+        LIP_CHECK_CUDA(cudaEventRecord(done, m->side));
+        wg_done = wg_last = done;
+      } else {
+        int rc = gemm_tc(p, st);
+        if (rc) return rc;
+      }
     } else {
       GemmProblem p;
       p.M = Ld.in; p.N = Ld.out; p.K = m->M; p.batch = B;
@@ -677,6 +698,7 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
       if (rcb) return rcb;
     }
     if (l > 0) {  // Delta_{l-1} = (Delta_l W_l^T) * phi'_{l-1}
+      if (wg_prev) LIP_CHECK_CUDA(cudaStreamWaitEvent(st, wg_prev, 0));     // the weight gradient of layer l + 1 has read w.hi[cur ^ 1]
       const bool next_split = m->tc_on && m->tc_layer[l - 1];
       const int nxt = cur ^ 1;
       const int nxt_ld = ld_of(m, Ld.in);
@@ -712,8 +734,11 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
         if (rc) return rc;
       }
       cur = nxt; cur_ld = nxt_ld; cur_split = next_split; cur_colsum = tc;
+    } else if (wg_prev) {
+      LIP_CHECK_CUDA(cudaStreamWaitEvent(st, wg_prev, 0));
     }
   }
+  if (wg_last) LIP_CHECK_CUDA(cudaStreamWaitEvent(st, wg_last, 0));         // join: the side stream's last weight gradient
   return LIP_OK;
 }
 
