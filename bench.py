@@ -435,18 +435,40 @@ def run_b200(args):
     if not args.no_e2e:
         hV = torch.empty(B, D, dtype=torch.float32).pin_memory()
         hV.copy_(V)
-        hY = torch.empty(B, D, dtype=torch.float32).pin_memory()
-        dV = torch.empty(B, D, device=dev)
-        n_e = max(2, min(args.steps, 4))
+        hYs = [torch.empty(B, D, dtype=torch.float32).pin_memory() for _ in range(2)]
+        dVs = [torch.empty(B, D, device=dev) for _ in range(2)]
+        n_e = max(2, min(args.steps, 6))
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
         def e2e_fp32_run(n):
-            for _ in range(n):
-                dV.copy_(hV, non_blocking=True)
-                Y = cvp(dV)
-                hY.copy_(Y, non_blocking=True)
+            # the host link is full duplex: step i + 1 is copied in and step i - 1 copied out while step i computes (two device input
+            # buffers, two pinned output buffers, one copy stream per direction)
+            main_s = torch.cuda.current_stream(dev)
+            ev_in = [torch.cuda.Event() for _ in range(2)]
+            ev_done = [torch.cuda.Event() for _ in range(2)]
+            ev_out = [torch.cuda.Event() for _ in range(2)]
+            keep = [None, None]
+            for i in range(n):
+                j = i % 2
+                with torch.cuda.stream(s_in):
+                    if i >= 2:
+                        s_in.wait_event(ev_done[j])              # the product of step i - 2 has consumed this input buffer
+                    dVs[j].copy_(hV, non_blocking=True)
+                    ev_in[j].record(s_in)
+                main_s.wait_event(ev_in[j])
+                Y = cvp(dVs[j])
+                ev_done[j].record(main_s)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[j])
+                    if i >= 2:
+                        s_out.wait_event(ev_out[j])              # (stream order already guarantees it)
+                    hYs[j].copy_(Y, non_blocking=True)
+                    ev_out[j].record(s_out)
+                Y.record_stream(s_out)
+                keep[j] = Y
             torch.cuda.synchronize()
 
-        e2e_fp32_run(1)
+        e2e_fp32_run(2)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -457,8 +479,9 @@ def run_b200(args):
         e2e_fp32 = {"value": B * world * n_e / float(dt.item()), "unit": "products/s", "steps": n_e,
                     "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * D * 4,
                     "note": "pinned fp32 [B, D] vectors -> H2D -> lla.compute_curvature_approx(...)(V) -> [B, D] products -> D2H to pinned "
-                            "host, no overlap between steps: bounded by the host link, not by the kernels"}
-        del hV, hY, dV
+                            "host; copies double-buffered on one stream per direction (full-duplex link): bounded by the host link, not by "
+                            "the kernels"}
+        del hV, hYs, dVs
 
     # the dominant kernel group on its own: ONE lip_ggn_vp call (all JVP / VJP GEMM launches) under CUDA events on the
     # launching stream, same inputs, no quadratic form / all-reduce around it -> roofline.achieved
