@@ -572,14 +572,16 @@ def run_b200(args):
             hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
         except Exception:
             pass
-        lz_bytes = n_loc * 4 * sum(2 * (i + 1) * D * 2 for i in range(k)) // Sg      # CGS2: two passes over i + 1 rows of Q
+        # three-term pass (2 rows) + ONE full pass (project, subtract) over i + 1 rows of Q; two full passes (CGS2) read twice as much
+        lz_bytes = n_loc * 4 * sum(2 * (i + 1) * D + 4 * D for i in range(k)) // Sg
         slq = {"seconds": secs, "k": k, "probes": ns, "probes_per_group": n_loc, "logdet_estimate": float(est.item()),
                "layout": {"probe_groups": Pg, "basis_shards_per_group": Sg,
                           "note": "probes over groups of GPUs (no communication); inside a group the Krylov bases are cut column-wise "
                                   "(one all-gather of the new vector + one all-reduce per norm / coefficient vector per step)"},
                "launches_per_logdet": int(slq_launches),
                "lanczos_form": {"seconds": float(dt_lz.item()), "logdet_estimate_clip1": float(est_lz.item()),
-                                "form": "Lanczos tridiag_sym(k) on curvature_vp, full re-orthogonalisation (2 passes), "
+                                "form": "Lanczos tridiag_sym(k) on curvature_vp, full re-orthogonalisation (three-term pass + one full "
+                                        "pass, a second full pass per column where the first removed more than half), "
                                         "log(clip(eig, 1)) quadrature",
                                 "reorth_GBps": lz_bytes / float(dt_lz.item()) / 1e9},
                "form": "GKL bidiag on [sqrt(alpha) I; Wz^T], full re-orthogonalisation; one native call (lip_slq_quadrature_sharded)"

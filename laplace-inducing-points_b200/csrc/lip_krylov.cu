@@ -559,6 +559,11 @@ __global__ void reorth_gate_kernel(int* gate, const float* nv, float thr, int B,
   gate[b] = g;
   if (g && count) atomicAdd(count, 1);
 }
+// gate[b] = 1 when the pass left less than `thr` of what it started from (after[b] < thr * before[b])
+__global__ void ratio_gate_kernel(int* gate, const float* after, const float* before, float thr, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) gate[b] = !(after[b] >= thr * before[b]) ? 1 : 0;
+}
 // nv[b] = gate[b] ? nv2[b] : nv[b]
 __global__ void gate_merge_kernel(float* nv, const float* nv2, const int* gate, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1069,7 +1074,7 @@ int shard_allgather(const Shard* sh, const float* loc, int64_t cnt, float* gath,
 // ---- Lanczos (matfree decomp.tridiag_sym, reortho="full") -------------------------------------------------------------
 size_t lanczos_ws_bytes(const Op& o, int64_t k, int64_t B) {
   const int64_t n = o.n_in, ld = pad4(n);
-  return op_ws_bytes(o, B) + red_bytes(n, B, k) + 3 * rsz((size_t)B * (ld + 64), 4) + 2 * rsz((size_t)B * n, 4) + 4 * rsz((size_t)B, 4) + 8192;
+  return op_ws_bytes(o, B) + red_bytes(n, B, k) + 3 * rsz((size_t)B * (ld + 64), 4) + 2 * rsz((size_t)B * n, 4) + 8 * rsz((size_t)B + 4, 4) + 8192;
 }
 
 // sh == nullptr: the whole vectors live on this GPU.  Otherwise Q holds this rank's column slice [B, k, ldq >= nloc] and v0 is the
@@ -1102,7 +1107,11 @@ int lanczos_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k
   float* wc = bp.take<float>((size_t)B * n);         // contiguous FULL mat-vec output
   float* len = bp.take<float>((size_t)B);
   float* nrm0 = bp.take<float>((size_t)B);
+  float* nrm1 = bp.take<float>((size_t)B);           // three-term form: norm after the two-row pass / after a gated extra pass
+  float* len2 = bp.take<float>((size_t)B);
+  int* gate = bp.take<int>((size_t)B + 4);
   if (!bp.ok) { set_error("lanczos: workspace too small (%zu bytes given)", ws_bytes); return LIP_ERR_WORKSPACE; }
+  LIP_CHECK_CUDA(cudaMemsetAsync(len2, 0, sizeof(float) * (size_t)B, st));
   const int64_t qsb = k * ldq;
   if (ld != nl) LIP_CHECK_CUDA(cudaMemsetAsync(w, 0, sizeof(float) * (size_t)B * ld, st));
   if (sh) LIP_CHECK_CUDA(cudaMemsetAsync(qloc, 0, sizeof(float) * (size_t)B * lq, st));
@@ -1118,11 +1127,46 @@ int lanczos_run(Op& o, const Shard* sh, const float* v0, int64_t ldv0, int64_t k
     rc = launch_scale_store(s, B, st); if (rc) return rc;
   }
   const unsigned gB = (unsigned)ceil_div(B, 128);
+  static const int three_term = getenv("LIP_LANCZOS_3TERM") ? atoi(getenv("LIP_LANCZOS_3TERM")) : 1;
   for (int64_t i = 0; i < k; ++i) {
     const int kk = (int)(i + 1);
     if (sh) { rc = shard_allgather(sh, qloc, sh->Dsh, gath, qc, n, B, st); if (rc) return rc; }
     rc = op_apply(o, qc, wc, B, 0, st); if (rc) return rc;
     const float* wl = wc + c0;                      // this rank's slice of A q_i (row stride n)
+    if (passes == 2 && three_term) {
+      // Two CGS passes, the first one restricted to the two rows that carry everything but rounding: A q_i - (q_i^T A q_i) q_i -
+      // (q_{i-1}^T A q_i) q_{i-1} is the three-term recurrence, after which A q_i has only eps |A| left along the older vectors, and
+      // the ONE full pass that follows removes that without cancellation.  Same tridiagonal (the recorded coefficients are rows i - 1
+      // and i of the first pass in both forms), same orthogonality, half the basis traffic of two full passes.  Where the full pass
+      // still removes more than half of the vector - a breakdown: A q_i lies in span(Q), e.g. the sampler's Lanczos that runs past the
+      // numerical rank of the Gram - the column takes a second full pass (decided on the device, per column).
+      const int64_t j0 = i > 0 ? i - 1 : 0;
+      const int k2 = (int)(i - j0 + 1);
+      rc = launch_project(Q + j0 * ldq, ldq, qsb, k2, wl, n, nl, B, r, st); if (rc) return rc;
+      rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
+      lanczos_record_kernel<<<gB, 128, 0, st>>>(diag, off, r.h - j0, r.kpad, len, (int)i, (int)k, (int)B);
+      LIP_LAUNCH_CHECK();
+      rc = launch_subtract(Q + j0 * ldq, ldq, qsb, k2, wl, n, nullptr, w, ld, nrm1, nl, B, r, st); if (rc) return rc;
+      rc = shard_norm(sh, nrm1, B, st); if (rc) return rc;
+      rc = launch_project(Q, ldq, qsb, kk, w, ld, nl, B, r, st); if (rc) return rc;
+      rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
+      rc = launch_subtract(Q, ldq, qsb, kk, w, ld, nullptr, w, ld, len, nl, B, r, st); if (rc) return rc;
+      rc = shard_norm(sh, len, B, st); if (rc) return rc;
+      ratio_gate_kernel<<<gB, 128, 0, st>>>(gate, len, nrm1, 0.5f, (int)B);
+      LIP_LAUNCH_CHECK();
+      rc = launch_project(Q, ldq, qsb, kk, w, ld, nl, B, r, st, gate); if (rc) return rc;
+      rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
+      rc = launch_subtract(Q, ldq, qsb, kk, w, ld, nullptr, w, ld, len2, nl, B, r, st, gate); if (rc) return rc;
+      rc = shard_norm(sh, len2, B, st); if (rc) return rc;
+      gate_merge_kernel<<<gB, 128, 0, st>>>(len, len2, gate, (int)B);
+      LIP_LAUNCH_CHECK();
+      if (i + 1 < k) {
+        ScaleStoreArgs s{}; s.x = w; s.ldx = ld; s.scal = len; s.o1 = Q + (i + 1) * ldq; s.ld1 = ldq; s.o1sb = qsb; s.o2 = qdst; s.ld2 = lq;
+        s.n2 = nl; s.n = nl;
+        rc = launch_scale_store(s, B, st); if (rc) return rc;
+      }
+      continue;
+    }
     // two CGS passes against Q[0..i]; the first-pass coefficients are the Arnoldi column H[:, i]
     rc = launch_project(Q, ldq, qsb, kk, wl, n, nl, B, r, st); if (rc) return rc;
     rc = shard_allreduce(sh, r.h, (size_t)B * r.kpad, st); if (rc) return rc;
