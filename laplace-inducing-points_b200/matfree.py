@@ -266,6 +266,7 @@ def _bidiag(num_matvecs: int):
         op.check(rc, "lip_gkl_bidiag")
         return _Bidiag(alphas, betas, Us, Vs, norm0), single
 
+    decompose._lip_num_matvecs = k
     return decompose
 
 
@@ -379,6 +380,13 @@ def integrand_funm_product_logdet(bidiag):
             raise ValueError("integrand_funm_product_logdet: the transpose operator is required (pass vA=... or use a "
                              "closure built by this package)")
         V, single = _as2d(v0)
+        k_native = getattr(bidiag, "_lip_num_matvecs", None)
+        if (k_native is not None and getattr(Av, "_lip_kind", None) == "GKL" and getattr(Av, "_lip_model", None) is not None
+                and vA_ is getattr(Av, "_lip_transpose", None)):
+            # this package's own bidiag_target closure through this package's own decomposition: the whole integrand is ONE native
+            # call (lip_slq_quadrature) that never materialises the u basis (csrc/lip_krylov.cu gkl_run, reduced form)
+            q = slq_quadrature(Av, V, k_native, form="gkl", fn="log", clip_min=None)
+            return q[0] if single else q
         res, _ = bidiag(Av, vA_, V)
         length = res.norm0
         nb, k = res.alphas.shape
