@@ -347,7 +347,8 @@ class BoundModel:
         if isinstance(self.spec, ConvProgramSpec):
             nf = int(cabi.lib().lip_model_fused_stages(self._h))
             if nf:
-                return f"fused conv+mask+pool stage kernels ({nf} conv stages, no patch buffer) + simt-fp32 GEMMs ({total} stages in all)"
+                tail = f"dense tail on tcgen05-3xtf32 ({n} layers) + simt-fp32" if n else "simt-fp32 GEMMs"
+                return f"fused conv+mask+pool stage kernels ({nf} conv stages, no patch buffer) + {tail} ({total} stages in all)"
         if isinstance(self.spec, (ConvProgramSpec, ResNetProgramSpec)):
             return f"im2col + simt-fp32 ({total} conv/dense stages)"
         return f"tcgen05-3xtf32 ({n}/{total} layers) + simt-fp32" if n else "simt-fp32"

@@ -268,6 +268,8 @@ int launch_unpool_mask(const float* tin, float* d, int64_t B, int64_t M, const C
 
 // ---- workspace --------------------------------------------------------------------------------------------------------
 struct CnnWs {
+  void* tail_ws = nullptr;   // workspace of the dense tail's sweeps (lip_model::tail)
+  size_t tail_bytes = 0;
   float* t[2];    // stage outputs / tangent images, ping-pong          [B * max_s M*out_per_point]
   float* raw;     // pre-pool stage output / delta w.r.t. pre-activation [B * max_s M*P*cout]   (x2: delta ping-pong)
   float* raw2;
@@ -308,6 +310,10 @@ int cnn_carve(const lip_model* m, int64_t B, void* ws, size_t bytes, CnnWs* w) {
   w->t[0] = base; w->t[1] = base + z.t;
   w->raw = base + 2 * z.t; w->raw2 = w->raw + z.raw;
   w->col = w->raw2 + z.raw;
+  if (m->tail_on) {
+    w->tail_ws = (void*)align_up((uintptr_t)(w->col + z.col), 256);
+    w->tail_bytes = mlp_tail_ws_bytes(m->tail, B);
+  }
   return LIP_OK;
 }
 
@@ -319,6 +325,8 @@ int cnn_jvp_sweep(lip_model* m, const float* V, int64_t B, const CnnWs& w, float
     const ConvStage& s = m->CS[i];
     const bool last = (i == nS - 1);
     const int64_t R = m->M * (int64_t)s.P;
+    if (m->tail_on && i == m->tail_first)       // the dense tail on the MLP sweeps (tcgen05 for the wide layers)
+      return mlp_tail_jvp(m->tail, V, m->D, T, B, w.tail_ws, w.tail_bytes, dst, st);
     if (!last && cnn_stage_fusable(m, i)) {     // conv + mask + pool in one kernel, no patch buffer
       int rc = cnn_fused_jvp(m, i, V, m->D, T, w.t[i & 1], B, st);
       if (rc) return rc;
@@ -366,7 +374,22 @@ int cnn_vjp_sweep(lip_model* m, const float* dl, int64_t B, const CnnWs& w, floa
   const size_t col_elems = cnn_sizes(m, B).col;
   const float* d = dl;     // delta w.r.t. the pre-activation of stage i, [B, M*P, cout]
   const float* tin_f = nullptr;   // set when stage i runs fused: the gradient w.r.t. its pooled output, [B, M, out_per_point]
-  for (int i = nS - 1; i >= 0; --i) {
+  int istart = nS - 1;
+  if (m->tail_on) {               // the dense tail on the MLP sweeps; it hands back the cotangent of its input features
+    float* cot = m->tail_first > 0 ? w.t[0] : nullptr;
+    int rc = mlp_tail_vjp(m->tail, dl, B, w.tail_ws, w.tail_bytes, out, m->D, scale, add, m->D, add_scale, cot, st);
+    if (rc) return rc;
+    if (m->tail_first == 0) return LIP_OK;
+    istart = m->tail_first - 1;
+    if (cnn_stage_fusable(m, istart)) {
+      tin_f = cot;
+    } else {
+      rc = launch_unpool_mask(cot, w.raw, B, m->M, m->CS[istart], st);
+      if (rc) return rc;
+      d = w.raw;
+    }
+  }
+  for (int i = istart; i >= 0; --i) {
     const ConvStage& s = m->CS[i];
     const int64_t R = m->M * (int64_t)s.P;
     const float* tin = nullptr;     // gradient w.r.t. the output of stage i-1, [B, M, out_per_point(i-1)]
@@ -514,6 +537,16 @@ int cnn_parse(lip_model* m, const lip_layer_desc* layers, int32_t n_layers, int6
   LIP_REQUIRE(counted == num_params, "lip_model_create: layers hold %lld parameters but num_params = %lld", (long long)counted,
               (long long)num_params);
   m->K = m->CS.back().cout;
+  {  // trailing dense stages as a dense program of their own (see lip_model::tail)
+    int i0 = (int)m->CS.size();
+    while (i0 > 0 && m->CS[i0 - 1].type == 0) --i0;
+    if (m->tail) { lip_model_destroy(m->tail); m->tail = nullptr; }
+    m->tail_first = i0;
+    if (i0 < (int)m->CS.size()) {
+      m->tail = mlp_make_tail(m->CS, i0, m->model_type, m->D);
+      LIP_REQUIRE(m->tail != nullptr, "lip_model_create: out of host memory");
+    }
+  }
   return LIP_OK;
 }
 
@@ -571,13 +604,21 @@ int cnn_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaSt
     if (rc) return rc;
   }
   m->tc_on = false;
+  m->tail_on = false;
+  static const bool tail_off = getenv("LIP_CNN_TC_TAIL") && atoi(getenv("LIP_CNN_TC_TAIL")) == 0;
+  if (m->tail && !tail_off && m->use_tc != 0) {
+    m->tail->use_tc = m->use_tc;
+    int rc = lip_model_bind(m->tail, theta, m->CS[m->tail_first].Aop, M, m->logvar, (lip_stream_t)st);
+    if (rc) return rc;
+    m->tail_on = m->tail->tc_on;       // worth it only when some layer reaches the tensor cores; else the stage path's skinny kernels
+  }
   m->bound = true;
   return LIP_OK;
 }
 
 size_t cnn_ws_bytes(const lip_model* m, int64_t B) {
   const CnnSizes z = cnn_sizes(m, B);
-  return (2 * z.t + 2 * z.raw + z.col) * sizeof(float) + 512;
+  return (2 * z.t + 2 * z.raw + z.col) * sizeof(float) + 512 + (m->tail_on ? align_up(mlp_tail_ws_bytes(m->tail, B), 256) + 512 : 0);
 }
 
 int cnn_ggn_vp(lip_model* m, const float* V, float* out, int64_t B, float recal, float alpha, void* ws, size_t bytes,

@@ -493,12 +493,15 @@ static inline bool head_fusable(const lip_model* m) {
 // stop_layer (default: all): run layers [0, stop_layer) only; with stop_layer = nL - 1 the masked tangent of the head's input is left in
 // w.hi[(nL - 2) & 1] (plain fp32 when the head is a SIMT layer) for the fused head kernel.
 int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float* dst, cudaStream_t st,
-              float* const* keep_hi = nullptr, float* const* keep_lo = nullptr, int stop_layer = -1) {
+              float* const* keep_hi = nullptr, float* const* keep_lo = nullptr, int stop_layer = -1, const float* t0_hi = nullptr,
+              const float* t0_lo = nullptr, int t0_ld = 0) {
   const int nL = (int)m->L.size();
   const int nRun = stop_layer < 0 ? nL : stop_layer;
-  const float* prev_hi = nullptr;
-  const float* prev_lo = nullptr;
-  int prev_ld = 0;
+  // (t0_hi, t0_lo, t0_ld): tangent of the program's INPUT, [B, M, t0_ld] (a dense tail behind conv stages); null for a program whose
+  // input is data
+  const float* prev_hi = t0_hi;
+  const float* prev_lo = t0_lo;
+  int prev_ld = t0_ld;
   // TF32 (hi, lo) splits of the probes' weight blocks: HBM-bound, independent of everything but V.  They run on the
   // model's side stream, layer by layer, while the compute-bound GEMMs of the earlier layers run on `st`; the first
   // tensor-core layer is additionally cut into probe chunks so that only its first chunk's split is exposed.
@@ -561,7 +564,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       // exactly-TF32 probes (Rademacher +-1, one-hot): the split found no lo part -> skip its loads / MMAs.  Not in the
       // probe-chunked overlap mode, where a later chunk's split may still be running when the first GEMM starts.
       if (!(overlap && l == first_tc && l == 0)) p.B1.lo_nz = m->lo_nz + l;
-      if (l > 0) {
+      if (prev_hi) {
         p.A2.hi = prev_hi; p.A2.lo = prev_lo; p.A2.ld = prev_ld; p.A2.sz = m->M * (int64_t)prev_ld; p.A2.major_k = 1;
         p.a2_batched = 1;
         p.B2.hi = m->W_hi[l]; p.B2.lo = m->W_lo[l]; p.B2.ld = ldw; p.B2.sz = (int64_t)Ld.in * ldw; p.B2.major_k = 0;
@@ -598,7 +601,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = B;
       p.A1 = {m->A[l], 0, Ld.in, 1};
       p.B1 = {V + Ld.woff, w.ldv, Ld.out, 1};
-      if (l > 0) {
+      if (prev_hi) {
         // a SIMT layer always reads a plain fp32 intermediate (its producer saw next_tc == false)
         p.A2 = {prev_hi, m->M * (int64_t)prev_ld, prev_ld, 1};
         p.B2 = {m->theta + Ld.woff, 0, Ld.out, 1};
@@ -620,7 +623,7 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
 // start_layer (default nL - 1): the sweep starts at that layer with its delta already in w.hi[src] (/ w.lo[src] when that layer is a
 // tensor-core layer): the fused head kernel has produced the delta of layer nL - 2 and the head's own gradients.
 int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, float scale, const float* add,
-              float add_scale, cudaStream_t st, int start_layer = -1) {
+              float add_scale, cudaStream_t st, int start_layer = -1, float* cot_in = nullptr) {
   const int nL = (int)m->L.size();
   const int lfirst = start_layer < 0 ? nL - 1 : start_layer;
   int cur = src;
@@ -734,8 +737,29 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
         if (rc) return rc;
       }
       cur = nxt; cur_ld = nxt_ld; cur_split = next_split; cur_colsum = tc;
-    } else if (wg_prev) {
-      LIP_CHECK_CUDA(cudaStreamWaitEvent(st, wg_prev, 0));
+    } else {
+      if (wg_prev) LIP_CHECK_CUDA(cudaStreamWaitEvent(st, wg_prev, 0));
+      if (cot_in) {   // cotangent of the program's input: Delta_0 W_0^T, plain fp32 [B, M, in_0] (no activation below a program input)
+        if (tc) {
+          TcGemmProblem p;
+          p.M = m->M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
+          p.A1.hi = d_hi; p.A1.lo = d_lo; p.A1.ld = cur_ld; p.A1.sz = m->M * (int64_t)cur_ld; p.A1.major_k = 1;
+          p.a_batched = 1;
+          p.B1.hi = m->W_hi[l]; p.B1.lo = m->W_lo[l]; p.B1.ld = m->W_ld[l]; p.B1.sz = (int64_t)Ld.in * m->W_ld[l];
+          p.B1.major_k = 1; p.b_batched = 0;
+          p.C = cot_in; p.C_lo = nullptr; p.c_sz = m->M * (int64_t)Ld.in; p.c_sm = Ld.in;
+          int rc = gemm_tc(p, st);
+          if (rc) return rc;
+        } else {
+          GemmProblem p;
+          p.M = m->M; p.N = Ld.in; p.K = Ld.out; p.batch = B;
+          p.A1 = {d_hi, m->M * (int64_t)cur_ld, cur_ld, 1};
+          p.B1 = {m->theta + Ld.woff, 0, 1, Ld.out};
+          p.C = cot_in; p.c_sz = m->M * (int64_t)Ld.in; p.c_sm = Ld.in;
+          int rc = gemm_simt(p, st);
+          if (rc) return rc;
+        }
+      }
     }
   }
   if (wg_last) LIP_CHECK_CUDA(cudaStreamWaitEvent(st, wg_last, 0));         // join: the side stream's last weight gradient
@@ -745,6 +769,65 @@ int vjp_sweep(lip_model* m, int src, int64_t B, const Workspace& w, float* out, 
 }  // namespace
 
 namespace lip {
+// ---- a dense program as the tail of a conv stage program (lip_cnn.cu) ----
+lip_model* mlp_make_tail(const std::vector<ConvStage>& stages, int first, int model_type, int64_t D) {
+  lip_model* t = new (std::nothrow) lip_model();
+  if (!t) return nullptr;
+  t->model_type = model_type;
+  t->D = D;
+  for (size_t i = (size_t)first; i < stages.size(); ++i) {
+    const ConvStage& s = stages[i];
+    DenseLayer L;
+    L.in = s.cin; L.out = s.cout; L.boff = s.boff; L.woff = s.woff; L.act = s.act;
+    t->L.push_back(L);
+  }
+  t->K = t->L.back().out;
+  t->maxw = 0;
+  for (auto& L : t->L) t->maxw = L.out > t->maxw ? L.out : t->maxw;
+  return t;
+}
+
+static inline size_t tail_t0_floats(const lip_model* t, int64_t B) { return align_up((size_t)B * t->M * (size_t)pad4(t->L[0].in), 64); }
+
+size_t mlp_tail_ws_bytes(const lip_model* t, int64_t B) {
+  return align_up(ws_bytes(t, B), 256) + 2 * tail_t0_floats(t, B) * sizeof(float) + 512;
+}
+
+int mlp_tail_jvp(lip_model* t, const float* V, int64_t ldv, const float* T0, int64_t B, void* ws, size_t bytes, float* dlogits,
+                 cudaStream_t st) {
+  LIP_REQUIRE(ws && bytes >= mlp_tail_ws_bytes(t, B), "dense tail: workspace too small");
+  Workspace w;
+  const size_t inner = align_up(ws_bytes(t, B), 256);
+  int rc = carve(t, B, ws, inner, &w);
+  if (rc) return rc;
+  w.ldv = ldv;
+  const int in0 = t->L[0].in;
+  const float* t_hi = T0;
+  const float* t_lo = nullptr;
+  int t_ld = in0;
+  if (t->tc_on && t->tc_layer[0]) {      // layer 0 reads its input tangent as a TF32 (hi, lo) pair through TMA
+    float* s_hi = (float*)align_up((uintptr_t)ws + inner, 256);
+    float* s_lo = s_hi + tail_t0_floats(t, B);
+    const int ld0 = pad4(in0);
+    rc = tf32_split3(T0, t->M * (int64_t)in0, in0, s_hi, s_lo, t->M * (int64_t)ld0, ld0, B, t->M, in0, st, nullptr);
+    if (rc) return rc;
+    t_hi = s_hi; t_lo = s_lo; t_ld = ld0;
+  }
+  return jvp_sweep(t, V, B, w, dlogits, st, nullptr, nullptr, -1, t_hi, t_lo, t_ld);
+}
+
+int mlp_tail_vjp(lip_model* t, const float* dl, int64_t B, void* ws, size_t bytes, float* out, int64_t ldo, float scale,
+                 const float* add, int64_t lda, float add_scale, float* cot_in, cudaStream_t st) {
+  LIP_REQUIRE(ws && bytes >= mlp_tail_ws_bytes(t, B), "dense tail: workspace too small");
+  Workspace w;
+  int rc = carve(t, B, ws, align_up(ws_bytes(t, B), 256), &w);
+  if (rc) return rc;
+  w.ldo = ldo; w.lda = lda;
+  rc = launch_scale_copy(dl, w.hi[0], B * t->M * (int64_t)t->K, 1.f, st);
+  if (rc) return rc;
+  return vjp_sweep(t, 0, B, w, out, scale, add, add_scale, st, -1, cot_in);
+}
+
 // ---- MLP sweep pieces shared with lip_zgrad.cu ----
 size_t mlp_ws_bytes(const lip_model* m, int64_t B) { return ws_bytes(m, B); }
 int mlp_ld(const lip_model* m, int width) { return ld_of(m, width); }
@@ -847,6 +930,7 @@ int lip_model_create(const lip_layer_desc* layers, int32_t n_layers, int32_t mod
 
 int lip_model_destroy(lip_model* m) {
   if (!m) return LIP_OK;
+  if (m->tail) { lip_model_destroy(m->tail); m->tail = nullptr; }
   m->free_cache();
   for (auto e : m->ev_split) cudaEventDestroy(e);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -862,6 +946,7 @@ int64_t lip_model_num_outputs(const lip_model* m) { return m ? m->K : -1; }
 int64_t lip_model_num_points(const lip_model* m) { return (m && m->bound) ? m->M : -1; }
 
 int lip_model_tensor_layers(const lip_model* m) {
+  if (m && m->bound && m->is_cnn && m->tail_on) return lip_model_tensor_layers(m->tail);
   if (!m || !m->bound || !m->tc_on) return 0;
   int n = 0;
   for (char c : m->tc_layer) n += c ? 1 : 0;

@@ -94,6 +94,11 @@ struct lip_model {
   std::vector<ConvStage> CS;   // stages of a conv program
   float* cnn_tmp_out = nullptr;          // bind-time scratch
   float* cnn_tmp_x = nullptr;
+  // the trailing DENSE stages of a conv stage program as a dense program of their own (absolute offsets into the same flat parameter
+  // vector), bound at the features the conv stages produce: its sweeps put LeNet5's 400 -> 120 -> 84 layers on the tcgen05 path
+  lip_model* tail = nullptr;
+  int tail_first = -1;                   // index in CS of the first stage the tail covers
+  bool tail_on = false;                  // decided at bind time (at least one tail layer runs on the tensor cores)
 
   // ---- residual conv programs (ResNet1M): see lip_resnet.cu ----
   bool is_resnet = false;
@@ -151,6 +156,14 @@ int cnn_zgrad(lip_model* m, int32_t mode, const float* X1, const float* X2, floa
 int zgrad_prepare(lip_model* m, cudaStream_t st);
 // MLP sweep pieces shared with lip_zgrad.cu (defined in lip_model.cu)
 size_t mlp_ws_bytes(const lip_model* m, int64_t B);
+// a dense program used as the tail of a conv stage program (lip_cnn.cu): built from the stages' offsets, swept with a given input
+// tangent T0 [B, M, in0] (JVP) and returning the input cotangent [B, M, in0] (VJP).  Workspace: mlp_tail_ws_bytes.
+lip_model* mlp_make_tail(const std::vector<ConvStage>& stages, int first, int model_type, int64_t D);
+size_t mlp_tail_ws_bytes(const lip_model* tail, int64_t B);
+int mlp_tail_jvp(lip_model* tail, const float* V, int64_t ldv, const float* T0, int64_t B, void* ws, size_t bytes, float* dlogits,
+                 cudaStream_t st);
+int mlp_tail_vjp(lip_model* tail, const float* dl, int64_t B, void* ws, size_t bytes, float* out, int64_t ldo, float scale,
+                 const float* add, int64_t lda, float add_scale, float* cot_in, cudaStream_t st);
 int mlp_ld(const lip_model* m, int width);
 int mlp_jvp_keep(lip_model* m, const float* V, int64_t B, void* ws, size_t bytes, float* dl, float* const* keep_hi,
                  float* const* keep_lo, const float** vs_hi, const float** vs_lo, cudaStream_t st);
