@@ -705,7 +705,8 @@ def run_b200(args):
                               "hbm": {"achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": (gbps / hbm) if hbm else None,
                                       "bytes_per_probe_point": per_pair},
                               "note": "per GPU; peak = 148 SMs x 128 FMA lanes x 2 x max SM clock (exact fp32: 1 / 6 / 16 channels are below any "
-                                      "tensor-core tile); hbm = pooled tangent + cotangent of each stage written once and read once + 8 D per product"}
+                                      "tensor-core tile; the 400-120-84 dense tail, 17 % of the FLOP, runs as tcgen05 3xTF32 GEMMs); hbm = pooled tangent + "
+                                      "cotangent of each stage written once and read once + 8 D per product"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
