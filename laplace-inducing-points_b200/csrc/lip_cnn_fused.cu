@@ -272,7 +272,7 @@ constexpr int vjp_smem_floats(int NT) {
 
 // CO_T / CI_T: output / input channels per kernel-gradient thread; RS: row slices of the output image; IF: images in flight
 template <class G, int CO_T, int CI_T, int RS, int IF, bool DGRAD, int NT>
-__global__ void __launch_bounds__(NT, 2) conv5_vjp_kernel(ConvVjpArgs a) {
+__global__ void __launch_bounds__(NT, DGRAD ? 2 : 3) conv5_vjp_kernel(ConvVjpArgs a) {
   constexpr int CIN = G::CIN, COUT = G::COUT, KS = G::KS, CP = G::CP, KK = G::KK, PLANE = G::PLANE, WS = G::WS, HS = G::HS;
   constexpr int HO = G::HO, WO = G::WO, HI = G::HI, WI = G::WI, PAD = G::PAD;
   constexpr int BD = DGRAD ? KS - 1 - PAD : 0, HD = HO + 2 * BD, WD = WO + 2 * BD;
