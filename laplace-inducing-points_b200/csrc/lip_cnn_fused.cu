@@ -516,6 +516,138 @@ __global__ void __launch_bounds__(256) cnn_part_finish_kernel(const float* __res
   }
 }
 
+// ---- ResNet1M stem: 3x3 conv (3 -> 32 channels, 32x32 image, SAME) JVP + BatchNorm-JVP epilogue ---------------------------------------
+// The stem's JVP has no tangent input (its source is data): out = mask * (g * conv(X, dW[b]) + xhat * dscale[b] + dbeta[b]), stored as
+// the TF32 (hi, lo) pair the next tcgen05 conv reads.  As a SIMT implicit GEMM (K = 27, N = 32) plus a separate BatchNorm pass it
+// moved 2.1 GB of fp32 through HBM twice at 0.2 TB/s (11.9 ms of a 225 ms call at M = 4096); here the image sits in shared memory,
+// a thread owns 4 pixels x 8 channels, and the only HBM traffic is xhat / mask in and the pair out.
+struct StemJvpArgs {
+  const float* X;        // [M, 32, 32, 3]
+  const float* V;        // probe block at the kernel offset (probe stride ldv)
+  const float* dscale;   // ... at the BatchNorm scale / bias offsets
+  const float* dbeta;
+  const float* g;        // [32]
+  const float* xhat;     // [M, 1024, 32]
+  const float* mask;     // [M, 1024, 32] or null
+  float* out;            // [B, M, 1024, 32]
+  float* out_lo;         // same, or null (plain fp32 tangent)
+  long long ldv;
+  int M, IMG, ROUNDS;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2) stem3_jvp_bn_kernel(StemJvpArgs a) {
+  constexpr int CIN = 3, COUT = 32, KS = 3, H = 32, W = 32, HS = 34, WS = 34, PLANE = HS * WS, KK = KS * KS * CIN, PER = H * W * CIN;
+  constexpr int XT = 4, CO_T = 8, NCG = COUT / CO_T, NQ = H * (W / XT);     // pixel quads per image
+  extern __shared__ __align__(16) float sm[];
+  float* sdW = sm;                         // [KK][COUT]
+  float* sP = sdW + KK * COUT;             // g, dscale, dbeta: 3 x [COUT]
+  float* sX = sP + 3 * COUT;               // [IMG][CIN][HS][WS]
+  const int tid = threadIdx.x;
+  const long long b = blockIdx.y;
+  for (int i = tid; i < a.IMG * CIN * PLANE; i += NT) sX[i] = 0.f;
+  {
+    const float* dW = a.V + b * a.ldv;
+#pragma unroll 4
+    for (int i = tid; i < KK * COUT; i += NT) sdW[i] = __ldg(dW + i);
+    if (tid < COUT) {
+      sP[tid] = __ldg(a.g + tid);
+      sP[COUT + tid] = __ldg(a.dscale + b * a.ldv + tid);
+      sP[2 * COUT + tid] = __ldg(a.dbeta + b * a.ldv + tid);
+    }
+  }
+  __syncthreads();
+  for (int rd = 0; rd < a.ROUNDS; ++rd) {
+    const int m0 = (blockIdx.x * a.ROUNDS + rd) * a.IMG;
+    const int nimg = a.M - m0 < a.IMG ? a.M - m0 : a.IMG;
+    if (nimg <= 0) break;
+    if (rd > 0) __syncthreads();
+    {
+      const float4* Xg = reinterpret_cast<const float4*>(a.X + (long long)m0 * PER);
+      const int total4 = nimg * (PER / 4);
+      for (int i0 = tid; i0 < total4; i0 += NT * 4) {
+        float4 vx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (i0 + u * NT < total4) vx[u] = __ldg(Xg + i0 + u * NT);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * NT;
+          if (i < total4) {
+            const float ex[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 4 * i + j;
+              const int img = e / PER, r = e - img * PER;
+              const int pix = r / CIN, ci = r - pix * CIN;
+              const int y = pix / W, x = pix - y * W;
+              sX[(img * CIN + ci) * PLANE + (y + 1) * WS + x + 1] = ex[j];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int total = nimg * NQ * NCG;
+    for (int it = tid; it < total; it += NT) {
+      const int cg = it % NCG, w = it / NCG;
+      const int img = w / NQ, q = w - img * NQ;
+      const int y = q / (W / XT), x0 = (q - y * (W / XT)) * XT;
+      const int co0 = cg * CO_T;
+      float acc[XT][CO_T];
+#pragma unroll
+      for (int p = 0; p < XT; ++p)
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c) acc[p][c] = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy) {
+          float xr[XT + KS - 1];
+          lds_row(sX + (img * CIN + ci) * PLANE + (y + dy) * WS + x0, xr);
+#pragma unroll
+          for (int dx = 0; dx < KS; ++dx) {
+            float wv[CO_T];
+            lds_vec(sdW + ((dy * KS + dx) * CIN + ci) * COUT + co0, wv);
+#pragma unroll
+            for (int p = 0; p < XT; ++p)
+#pragma unroll
+              for (int c = 0; c < CO_T; ++c) acc[p][c] = fmaf(xr[p + dx], wv[c], acc[p][c]);
+          }
+        }
+      const long long m = m0 + img;
+#pragma unroll
+      for (int p = 0; p < XT; ++p) {
+        const long long i = ((m * H + y) * W + x0 + p) * COUT + co0;            // index inside one probe's tensor
+        const long long o = (b * a.M * (long long)(H * W) * COUT) + i;
+        float xh[CO_T], mk[CO_T], hi[CO_T], lo[CO_T];
+        const float4 x0v = __ldg(reinterpret_cast<const float4*>(a.xhat + i)), x1v = __ldg(reinterpret_cast<const float4*>(a.xhat + i + 4));
+        xh[0] = x0v.x; xh[1] = x0v.y; xh[2] = x0v.z; xh[3] = x0v.w; xh[4] = x1v.x; xh[5] = x1v.y; xh[6] = x1v.z; xh[7] = x1v.w;
+        if (a.mask) {
+          const float4 m0v = __ldg(reinterpret_cast<const float4*>(a.mask + i)), m1v = __ldg(reinterpret_cast<const float4*>(a.mask + i + 4));
+          mk[0] = m0v.x; mk[1] = m0v.y; mk[2] = m0v.z; mk[3] = m0v.w; mk[4] = m1v.x; mk[5] = m1v.y; mk[6] = m1v.z; mk[7] = m1v.w;
+        }
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c) {
+          float v = fmaf(sP[co0 + c], acc[p][c], fmaf(xh[c], sP[COUT + co0 + c], sP[2 * COUT + co0 + c]));
+          if (a.mask) v *= mk[c];
+          if (a.out_lo) {
+            const float hh = tf32_round(v);
+            hi[c] = hh; lo[c] = tf32_round(v - hh);
+          } else {
+            hi[c] = v;
+          }
+        }
+        *reinterpret_cast<float4*>(a.out + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a.out + o + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        if (a.out_lo) {
+          *reinterpret_cast<float4*>(a.out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<float4*>(a.out_lo + o + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
+    }
+  }
+}
+
 bool fuse_enabled() {
   static const int on = [] {
     const char* e = getenv("LIP_CNN_FUSE");
@@ -594,6 +726,35 @@ int launch_vjp(const ConvStage& s, const lip_model* m, const float* tin, float* 
 }
 
 }  // namespace
+
+bool resnet_stem_fusable(const ConvBN& u) {
+  return fuse_enabled() && u.src == -2 && u.skip < 0 && u.cin == 3 && u.cout == 32 && u.kh == 3 && u.kw == 3 && u.stride == 1 &&
+         u.pad_h == 1 && u.pad_w == 1 && u.Hi == 32 && u.Wi == 32 && u.Ho == 32 && u.Wo == 32 && u.Xin && u.xhat && u.g;
+}
+
+int resnet_stem_jvp(const lip_model* m, const ConvBN& u, const float* V, int64_t ldv, float* out, float* out_lo, int64_t B,
+                    cudaStream_t st) {
+  constexpr int NT = 256, IMG = 2;
+  StemJvpArgs a;
+  a.X = u.Xin; a.V = V + u.woff; a.dscale = V + u.scale_off; a.dbeta = V + u.beta_off; a.g = u.g; a.xhat = u.xhat; a.mask = u.mask;
+  a.ldv = ldv; a.M = (int)m->M; a.IMG = IMG;
+  int64_t rounds = ceil_div(m->M, IMG) * B / (148 * 16);
+  rounds = rounds < 1 ? 1 : (rounds > 16 ? 16 : rounds);
+  a.ROUNDS = (int)rounds;
+  const size_t smem = sizeof(float) * (size_t)(27 * 32 + 3 * 32 + IMG * 3 * 34 * 34);
+  const unsigned gx = (unsigned)ceil_div(m->M, IMG * rounds);
+  const int64_t per_probe = m->M * (int64_t)(32 * 32 * 32);
+  for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+    const int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
+    StemJvpArgs c = a;
+    c.V += b0 * ldv; c.dscale += b0 * ldv; c.dbeta += b0 * ldv;
+    c.out = out + b0 * per_probe;
+    c.out_lo = out_lo ? out_lo + b0 * per_probe : nullptr;
+    stem3_jvp_bn_kernel<NT><<<dim3(gx, (unsigned)nb), NT, smem, st>>>(c);
+    LIP_LAUNCH_CHECK();
+  }
+  return LIP_OK;
+}
 
 bool cnn_stage_fusable(const lip_model* m, int i) {
   if (!fuse_enabled() || i < 0 || i >= (int)m->CS.size()) return false;

@@ -192,6 +192,10 @@ int cnn_fused_jvp(const lip_model* m, int stage, const float* V, int64_t ldv, co
 // and, for stage > 0, gin = the gradient w.r.t. the stage input [B, M, Hi, Wi, cin]
 int cnn_fused_vjp(const lip_model* m, int stage, const float* tin, float* gin, float* out, int64_t B, float scale, const float* add,
                   float add_scale, float* scratch, int64_t scratch_elems, cudaStream_t st);
+// ResNet1M stem (3 -> 32 channels, 3x3, 32x32): conv JVP + BatchNorm-JVP in one kernel (lip_cnn_fused.cu)
+bool resnet_stem_fusable(const ConvBN& u);
+int resnet_stem_jvp(const lip_model* m, const ConvBN& u, const float* V, int64_t ldv, float* out, float* out_lo, int64_t B,
+                    cudaStream_t st);
 // residual conv programs (lip_resnet.cu)
 int resnet_parse(lip_model* m, const lip_layer_desc* layers, int32_t n_layers, int64_t num_params);
 int resnet_bind(lip_model* m, const float* theta, const float* Z, int64_t M, cudaStream_t st);

@@ -371,6 +371,10 @@ int rn_jvp_sweep(lip_model* m, const float* V, int64_t B, const RnWs& w, float* 
       }
       c.C_out = w.raw;
       rc = conv_tc(c, st);
+    } else if (resnet_stem_fusable(u)) {
+      rc = resnet_stem_jvp(m, u, V, m->D, w.slot[u.dst], pairs ? w.slot_lo[u.dst] : nullptr, B, st);
+      if (rc) return rc;
+      continue;
     } else {
       GemmProblem p;
       p.M = R; p.N = u.cout; p.K = Kc; p.batch = B;
