@@ -425,6 +425,7 @@ struct Workspace {
   float* vs_hi;     // split tangent-weight block of the current layer, [B][in][ldw]
   float* vs_lo;
   float* colsum;    // per-32-row-block column sums of the delta written by a tcgen05 delta-backprop GEMM: [B][nslots][ldmax]
+  float* pre;       // one- / two-probe sweeps: mask * (A_l dW_l) of every layer, computed on the side stream, [layer][min(B,2)][M][ldmax]
   size_t per_buf;   // floats
   // row strides (floats) of the caller's blocks: V (JVP input / bias source), out (VJP output), add (VJP epilogue operand).
   // D unless the caller hands over padded rows (lip_ggn_vp_ex), which is what lets TMA read the probe block in place.
@@ -438,7 +439,8 @@ size_t ws_bytes(const lip_model* m, int64_t B) {
   size_t per = align_up((size_t)B * (size_t)m->M * (size_t)(m->tc_on ? m->ldmax : m->maxw), 64);
   size_t total = 2 * per;
   if (m->tc_on) total += 2 * per + 2 * align_up((size_t)B * (size_t)m->sum_split, 64) +
-                        align_up((size_t)B * (size_t)colsum_slots(m) * (size_t)m->ldmax, 64);
+                        align_up((size_t)B * (size_t)colsum_slots(m) * (size_t)m->ldmax, 64) +
+                        align_up((size_t)(B < 2 ? B : 2) * m->L.size() * (size_t)m->M * (size_t)m->ldmax, 64);
   return total * sizeof(float) + 256;
 }
 
@@ -454,12 +456,13 @@ int carve(const lip_model* m, int64_t B, void* ws, size_t bytes, Workspace* w) {
   w->ldv = w->ldo = w->lda = m->D;
   w->exact = false;
   w->hi[0] = base; w->hi[1] = base + per;
-  w->lo[0] = w->lo[1] = w->vs_hi = w->vs_lo = w->colsum = nullptr;
+  w->lo[0] = w->lo[1] = w->vs_hi = w->vs_lo = w->colsum = w->pre = nullptr;
   if (m->tc_on) {
     w->lo[0] = base + 2 * per; w->lo[1] = base + 3 * per;
     size_t vs = align_up((size_t)B * (size_t)m->sum_split, 64);
     w->vs_hi = base + 4 * per; w->vs_lo = w->vs_hi + vs;
     w->colsum = w->vs_lo + vs;
+    w->pre = w->colsum + align_up((size_t)B * (size_t)colsum_slots(m) * (size_t)m->ldmax, 64);
   }
   return LIP_OK;
 }
@@ -538,6 +541,44 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       }
     }
   }
+  // One or two probes: the sweep is a chain of latency-bound GEMMs, and half of every link - the A_l dW_l term - does not depend on
+  // the chain at all.  Those products (already masked: the mask distributes over the sum) run on the side stream, all layers at once,
+  // while the chain does T_l W_l + bias, masks, and adds them in its epilogue.  Same sums, K halved on the critical path.
+  static const int pre_env = getenv("LIP_JVP_FORK") ? atoi(getenv("LIP_JVP_FORK")) : 1;
+  const bool pre_fork = pre_env && m->tc_on && m->side != nullptr && B <= 2 && !overlap && w.pre != nullptr &&
+                        (int)m->ev_split.size() >= nL * lip_model::SPLIT_CHUNKS && lip_model::SPLIT_CHUNKS >= 4;
+  const size_t pre_stride = (size_t)B * (size_t)m->M * (size_t)m->ldmax;
+  auto has_pre = [&](int l) {      // layers whose A dW term is split off: tensor-core layers with a tangent input, not the last one
+    return pre_fork && l < nRun && l < nL - 1 && m->tc_layer[l] && (l > 0 || t0_hi != nullptr);
+  };
+  if (pre_fork) {
+    bool any = false;
+    for (int l = 0; l < nRun; ++l) any = any || has_pre(l);
+    if (any) {
+      LIP_CHECK_CUDA(cudaEventRecord(m->ev_fork, st));              // the probe splits above are on `st`
+      LIP_CHECK_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+      for (int l = 0; l < nRun; ++l) {
+        if (!has_pre(l)) continue;
+        const DenseLayer& Ld = m->L[l];
+        const int64_t ldw = m->W_ld[l];
+        const int out_ld = ld_of(m, Ld.out);
+        TcGemmProblem p;
+        p.M = m->M; p.N = Ld.out; p.K = Ld.in; p.batch = B;
+        p.A1.hi = m->A_hi[l]; p.A1.lo = m->A_lo[l]; p.A1.ld = m->A_ld[l]; p.A1.sz = m->M * m->A_ld[l]; p.A1.major_k = 1;
+        p.a_batched = 0;
+        p.B1.hi = w.vs_hi + B * m->split_off[l]; p.B1.lo = w.vs_lo + B * m->split_off[l]; p.B1.ld = ldw;
+        p.B1.sz = (int64_t)Ld.in * ldw; p.B1.major_k = 0;
+        if (inplace_ok(m, l, V, w)) { p.B1.hi = V + Ld.woff; p.B1.lo = V + Ld.woff; p.B1.ld = Ld.out; p.B1.sz = w.ldv; }
+        p.b_batched = 1;
+        p.B1.lo_nz = m->lo_nz + l;
+        p.C = w.pre + l * pre_stride; p.C_lo = nullptr; p.c_sz = m->M * (int64_t)out_ld; p.c_sm = out_ld;
+        p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out;
+        int rc = gemm_tc(p, m->side);
+        if (rc) return rc;
+        LIP_CHECK_CUDA(cudaEventRecord(m->ev_split[l * lip_model::SPLIT_CHUNKS + 2], m->side));
+      }
+    }
+  }
   for (int l = 0; l < nRun; ++l) {
     const DenseLayer& Ld = m->L[l];
     const bool last = (l == nL - 1);
@@ -574,6 +615,14 @@ int jvp_sweep(lip_model* m, const float* V, int64_t B, const Workspace& w, float
       p.C = out_hi; p.C_lo = out_lo; p.c_sz = m->M * (int64_t)out_ld; p.c_sm = out_ld;
       p.epi.bias = V + Ld.boff; p.epi.bias_sz = w.ldv;
       if (!last) { p.epi.mask = m->dphi[l]; p.epi.mask_sm = Ld.out; }
+      if (has_pre(l)) {
+        // the chain link alone: T_l W_l + bias, masked, + the side stream's mask * (A_l dW_l)
+        p.A1 = p.A2; p.a_batched = 1;
+        p.B1 = p.B2; p.b_batched = 0; p.B1.lo_nz = nullptr;
+        p.A2 = TcOperand(); p.B2 = TcOperand(); p.K2 = 0; p.a2_batched = 0; p.b2_batched = 0;
+        p.epi.add = w.pre + l * pre_stride; p.epi.add_sz = m->M * (int64_t)out_ld; p.epi.add_scale = 1.f;
+        LIP_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_split[l * lip_model::SPLIT_CHUNKS + 2], 0));
+      }
       int rc = LIP_OK;
       if (overlap && l == first_tc && l == 0) {
         // probe-chunked: chunk c starts as soon as its split has landed
