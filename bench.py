@@ -102,6 +102,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.active = True          # samples are kept only while this is set (the timed region)
         self.nvml = None
         try:
             import pynvml
@@ -123,6 +124,9 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self.stop_flag:
             try:
+                if not self.active:
+                    time.sleep(0.002)
+                    continue
                 if self.nvml is not None:
                     self.samples.append(self._sample_nvml())
                     time.sleep(0.01)
@@ -349,21 +353,26 @@ def run_b200(args):
     # tensor roofline denominator, first reading (cool GPU); a second one is taken after the runs and the LARGER of the two
     # is used, so a throttled reading can only lower the reported fraction
     tf32_peak_pre = measure_tf32_peak(torch) if rank == 0 else 0.0
+    # NVML is initialised and the sampler thread started BEFORE the warm-up and the barrier: its start-up cost differs from rank to
+    # rank (10 - 100 ms), and paid between the barrier and the timed loop it de-synchronised the ranks, so that the first all-reduce of
+    # the loop absorbed the skew - up to 3 ms per step over a 10-step run on 8 GPUs.  It only keeps samples inside the timed region.
+    sampler = ClockSampler(local)
+    sampler.active = False
+    sampler.start()
     for _ in range(args.warmup):
         step(V)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = L.lip_launch_count()
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    torch.cuda.synchronize()
+    sampler.active = True
     e0.record()
     for _ in range(args.steps):
         step(V)
     e1.record()
     torch.cuda.synchronize()
+    sampler.active = False
     launches = L.lip_launch_count() - l0
     if world > 1:
         dist.barrier()
